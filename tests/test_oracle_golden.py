@@ -1,0 +1,152 @@
+"""The CPU oracle against the reference's own outputs (tests/golden, written by oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from contrastive_lift_b200 import synthetic as syn
+from oracle import clift_oracle as orc
+from oracle import refload
+import golden_util as gu
+
+
+def tn(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def test_rays_golden():
+    fx = gu.load("rays")
+    for i in range(3):
+        h, w = (int(v) for v in fx[f"cam{i}_hw"])
+        rays = orc.make_rays(h, w, tn(fx[f"cam{i}_K"]), tn(fx[f"cam{i}_c2w"]))
+        assert torch.equal(rays, tn(fx[f"cam{i}_rays"]))
+
+
+def test_distloss_matches_definition_and_gradcheck():
+    fx = gu.load("distloss")
+    w, m, iv = tn(fx["w"]), tn(fx["m"]), tn(fx["iv"])
+    assert torch.allclose(orc.distortion_loss(w, m, iv), tn(fx["value"]), rtol=1e-10)
+    assert torch.allclose(orc.distortion_loss_bruteforce(w, m, iv), tn(fx["value"]), rtol=1e-12)
+    wg = w.clone().requires_grad_(True)
+    assert torch.autograd.gradcheck(lambda t: orc.distortion_loss(t, m, iv), (wg,))
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_render_inference_golden(name):
+    fx = gu.load(name)
+    params, cfg, rays = gu.render_inputs(fx)
+    with torch.no_grad():
+        out, det = orc.render_forward(params, cfg, rays, None, False, detail=True)
+    # indices / positions / masks: bit-exact
+    assert torch.equal(det["z"].expand(rays.shape[0], -1), tn(fx["inf_z"]))
+    assert torch.equal(det["inbox"], tn(fx["inf_inbox"]))
+    assert torch.equal(det["xyz"], tn(fx["inf_xyz"]))
+    assert torch.equal(det["active"], tn(fx["inf_active"]))
+    assert torch.equal(det["sigma"], tn(fx["inf_sigma"]))
+    assert torch.equal(det["weight"], tn(fx["inf_weight"]))
+    for got, key in zip(out[:4], ("inf_rgb", "inf_sem", "inf_ins", "inf_depth")):
+        assert torch.equal(got, tn(fx[key])), key
+    assert torch.equal(out[5], tn(fx["inf_dist"]))
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+@pytest.mark.parametrize("tag", ["trn", "trn2"])
+def test_render_training_golden(name, tag):
+    fx = gu.load(name)
+    params, cfg, rays = gu.render_inputs(fx)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    out = orc.render_forward(p, cfg, rays, tn(fx[f"{tag}_jitter"]), bool(fx[f"{tag}_coin"]))
+    for i, key in enumerate(("rgb", "sem", "ins", "depth")):
+        assert torch.equal(out[i], tn(fx[f"{tag}_{key}"])), key
+    loss = gu.train_loss(out, fx, tag)
+    assert torch.allclose(loss.detach(), tn(fx[f"{tag}_loss"]), rtol=1e-6)
+    loss.backward()
+    for k, v in p.items():
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        dig = gu.grad_digest(g)
+        assert np.allclose(dig, fx[f"{tag}_gdig/{k}"], rtol=1e-4, atol=1e-9), k
+        if f"{tag}_grad/{k}" in fx.files:
+            assert torch.allclose(g, tn(fx[f"{tag}_grad/{k}"]), rtol=1e-5, atol=1e-9), k
+    # the instance head never receives gradient through a loss on rgb/sem only; here w_ins gives it one:
+    assert p["render_instance_mlp.mlp.0.weight"].grad is not None
+    # density factors get no gradient from the semantic / instance maps (stop_semantic_grad)
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_instance_and_segment_golden(name):
+    fx = gu.load(name)
+    params, cfg, rays = gu.render_inputs(fx)
+    ins, pts = orc.render_instance_feature(params, cfg, rays, tn(fx["insf_jitter"]))
+    assert torch.equal(ins, tn(fx["insf_map"])) and torch.equal(pts, tn(fx["insf_pts"]))
+    seg = orc.render_segment_feature(params, cfg, rays, tn(fx["segf_jitter"]))
+    assert torch.equal(seg, tn(fx["segf_map"]))
+
+
+def test_losses_golden():
+    fx = gu.load("losses")
+    ci = 0
+    while f"sf{ci}_feats" in fx.files:
+        feats = tn(fx[f"sf{ci}_feats"]).requires_grad_(True)
+        loss = orc.slow_fast_loss(feats, tn(fx[f"sf{ci}_labels"]), tn(fx[f"sf{ci}_conf"]))
+        ref = tn(fx[f"sf{ci}_loss"])
+        if torch.isnan(ref):
+            assert torch.isnan(loss)
+        else:
+            assert torch.allclose(loss.detach(), ref, rtol=1e-6, atol=0)
+            if loss.requires_grad:
+                loss.backward()
+                assert torch.allclose(feats.grad, tn(fx[f"sf{ci}_grad"]), rtol=1e-5, atol=1e-9)
+        ci += 1
+    assert ci == 6
+    ci = 0
+    while f"ct{ci}_feats" in fx.files:
+        feats = tn(fx[f"ct{ci}_feats"]).requires_grad_(True)
+        loss = orc.contrastive_loss(feats, tn(fx[f"ct{ci}_labels"]), float(fx[f"ct{ci}_temp"]))
+        assert torch.allclose(loss.detach(), tn(fx[f"ct{ci}_loss"]), rtol=1e-6)
+        loss.backward()
+        assert torch.allclose(feats.grad, tn(fx[f"ct{ci}_grad"]), rtol=1e-5, atol=1e-9)
+        ci += 1
+    assert ci == 3
+    # EMA
+    p = syn.make_field_params(int(fx["ema_seed"]), (8, 8, 8), 4, 3)
+    slow = [p[f"render_instance_mlp.slow_mlp.{k}.{t}"].clone() for k in (0, 2, 4, 6) for t in ("weight", "bias")]
+    fast = [p[f"render_instance_mlp.mlp.{k}.{t}"] for k in (0, 2, 4, 6) for t in ("weight", "bias")]
+    orc.ema_update(slow, fast, 0.9)
+    assert torch.equal(slow[-2], tn(fx["ema_last_weight"])) and torch.equal(slow[1], tn(fx["ema_first_bias"]))
+    # TV
+    p2 = syn.make_field_params(int(fx["tv_seed"]), tuple(int(v) for v in fx["tv_grid"]), 3, 3)
+    pq = {k: v.clone().requires_grad_(True) for k, v in p2.items()}
+    tot = orc.total_tv_loss(pq)
+    assert torch.allclose(tot.detach(), tn(fx["tv_total"]), rtol=1e-6)
+    assert torch.allclose(orc.tv_loss(p2["density_plane.0"]), tn(fx["tv_plane0"]), rtol=1e-6)
+    tot.backward()
+    assert torch.allclose(pq["density_plane.1"].grad, tn(fx["tv_grad_density_plane.1"]), rtol=1e-5, atol=1e-10)
+
+
+def test_explicit_bilinear_matches_library_sampler():
+    params = syn.make_field_params(1, (9, 13, 11), 3, 3)
+    g = torch.Generator().manual_seed(0)
+    xyz = torch.rand(500, 3, generator=g) * 2.2 - 1.1          # includes out-of-range taps (zero padding)
+    a = orc.density(params, xyz)
+    b = orc.density(params, xyz, explicit=True)
+    assert torch.allclose(a, b, rtol=2e-5, atol=1e-6)
+    fa = orc.vm_feature(params, "appearance", xyz)
+    fb = orc.vm_feature(params, "appearance", xyz, explicit=True)
+    assert torch.allclose(fa, fb, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+def test_oracle_against_live_reference_random_config():
+    """Fresh, un-fixtured comparison with the imported reference (build container only)."""
+    grid = (12, 10, 14)
+    params = syn.make_field_params(77, grid, 6, 2)
+    aabb = syn.default_aabb()
+    model = refload.build_model(params, grid, 6, 2)
+    rend = refload.build_renderer(aabb, grid)
+    cfg = orc.RenderConfig(aabb=aabb, grid_dim=grid).refresh()
+    assert cfg.n_samples == rend.n_samples
+    rays = syn.random_rays(5, 64)
+    with torch.no_grad():
+        ref = rend(model, rays, 1.0, False, False)
+        got = orc.render_forward(params, cfg, rays)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
