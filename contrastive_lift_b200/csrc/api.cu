@@ -1,0 +1,202 @@
+// extern "C" surface of libclift_b200.so: error state, configuration checks and the render pipeline
+// (march -> scan -> fill -> heads -> finish) on the caller's stream.  See include/clift_b200.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+
+#include "launchers.h"
+
+namespace clift {
+
+static thread_local char g_error[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+static int check_mlp(const clift_mlp& m, const char* name, int expect_out) {
+    if (m.n_layers < 1 || m.n_layers > CLIFT_MAX_LAYERS) {
+        set_error("%s: n_layers %d outside [1,%d]", name, m.n_layers, CLIFT_MAX_LAYERS);
+        return CLIFT_ERR_UNSUPPORTED;
+    }
+    for (int l = 0; l <= m.n_layers; ++l)
+        if (m.dims[l] < 1 || m.dims[l] > CLIFT_MAX_WIDTH) {
+            set_error("%s: width %d of layer %d outside [1,%d]", name, m.dims[l], l, CLIFT_MAX_WIDTH);
+            return CLIFT_ERR_UNSUPPORTED;
+        }
+    for (int l = 0; l < m.n_layers; ++l)
+        if (!m.wt[l] || !m.bias[l]) {
+            set_error("%s: null weight/bias pointer at layer %d", name, l);
+            return CLIFT_ERR_ARG;
+        }
+    if (expect_out > 0 && m.dims[m.n_layers] != expect_out) {
+        set_error("%s: output width %d != %d", name, m.dims[m.n_layers], expect_out);
+        return CLIFT_ERR_ARG;
+    }
+    return CLIFT_OK;
+}
+
+static int check_field(const clift_field* f, int heads) {
+    CLIFT_CHECK_ARG(f != nullptr, "null field");
+    for (int k = 0; k < 3; ++k) CLIFT_CHECK_ARG(f->grid[k] >= 2, "grid dimension < 2");
+    CLIFT_CHECK_SUPPORTED(f->density_comps % 16 == 0 && f->density_comps >= 16 && f->density_comps <= 48,
+                          "density_comps must be 16, 32 or 48");
+    for (int m = 0; m < 3; ++m) CLIFT_CHECK_ARG(f->density_plane[m] && f->density_line[m], "null density factor");
+    if (heads & CLIFT_HEAD_RGB) {
+        CLIFT_CHECK_SUPPORTED(f->appearance_comps % 16 == 0 && f->appearance_comps >= 16 && f->appearance_comps <= 64,
+                              "appearance_comps must be 16..64 in steps of 16");
+        for (int m = 0; m < 3; ++m) CLIFT_CHECK_ARG(f->appearance_plane[m] && f->appearance_line[m], "null appearance factor");
+        CLIFT_CHECK_ARG(f->basis != nullptr, "null basis");
+        CLIFT_CHECK_SUPPORTED(f->pe_view >= 1 && f->pe_feat >= 1, "view-independent rgb head (pe_view=pe_feat=0)");
+        const int n_in = f->dim_appearance * (1 + 2 * f->pe_feat) + 3 * (1 + 2 * f->pe_view);
+        CLIFT_CHECK_SUPPORTED(n_in <= CLIFT_MAX_WIDTH && 3 * f->appearance_comps <= CLIFT_MAX_WIDTH, "rgb head input too wide");
+        int rc = check_mlp(f->rgb, "rgb mlp", 3);
+        if (rc) return rc;
+        CLIFT_CHECK_ARG(f->rgb.dims[0] == n_in, "rgb mlp input width does not match dim_appearance/pe");
+    }
+    if (heads & CLIFT_HEAD_SEMANTIC) {
+        CLIFT_CHECK_SUPPORTED(f->num_classes >= 1 && f->num_classes <= CLIFT_MAX_HEAD_OUT, "num_classes outside [1,64]");
+        int rc = check_mlp(f->semantic, "semantic mlp", f->num_classes);
+        if (rc) return rc;
+        CLIFT_CHECK_ARG(f->semantic.dims[0] == 3 + 6 * f->pe_sem, "semantic mlp input width != 3+6*pe_sem");
+    }
+    if (heads & CLIFT_HEAD_INSTANCE) {
+        CLIFT_CHECK_SUPPORTED(f->dim_instance >= 1 && f->dim_instance <= CLIFT_MAX_HEAD_OUT, "dim_instance outside [1,64]");
+        int rc = check_mlp(f->instance_fast, "instance mlp", f->dim_instance);
+        if (rc) return rc;
+        CLIFT_CHECK_ARG(f->instance_fast.dims[0] == 3 + 6 * f->pe_ins, "instance mlp input width != 3+6*pe_ins");
+        if (f->slow_fast) {
+            rc = check_mlp(f->instance_slow, "instance slow mlp", f->dim_instance);
+            if (rc) return rc;
+        }
+    }
+    return CLIFT_OK;
+}
+
+static int check_cfg(const clift_render_cfg* c) {
+    CLIFT_CHECK_ARG(c != nullptr, "null cfg");
+    CLIFT_CHECK_ARG(c->n_samples >= 2, "n_samples < 2");
+    CLIFT_CHECK_ARG(c->step_size > 0.0f, "step_size <= 0");
+    return CLIFT_OK;
+}
+
+static int out_width(const clift_field* f) { return 3 + f->num_classes + f->dim_instance * (f->slow_fast ? 2 : 1); }
+
+}  // namespace clift
+
+using namespace clift;
+
+extern "C" int32_t clift_abi_version(void) { return CLIFT_ABI_VERSION; }
+extern "C" const char* clift_last_error(void) { return g_error; }
+extern "C" int64_t clift_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int32_t clift_sample_points(const clift_render_cfg* cfg, const float* rays, const float* jitter, int64_t n_rays,
+                                       float* z, float* xyz, uint8_t* inbox, void* stream) {
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    CLIFT_CHECK_ARG(rays && n_rays >= 0, "null rays");
+    return launch_sample_points(cfg, rays, jitter, n_rays, z, xyz, inbox, (cudaStream_t)stream);
+}
+
+extern "C" int32_t clift_density(const clift_field* field, const float* xyz, int64_t n, float* sigma, void* stream) {
+    int rc = check_field(field, 0);
+    if (rc) return rc;
+    CLIFT_CHECK_ARG(xyz && sigma && n >= 0, "null pointer");
+    return launch_density(field, xyz, n, sigma, (cudaStream_t)stream);
+}
+
+extern "C" int64_t clift_render_workspace_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays,
+                                                int64_t max_active) {
+    if (!cfg || !field || n_rays < 0) return CLIFT_ERR_ARG;
+    if (max_active <= 0) max_active = n_rays * cfg->n_samples;
+    return carve_workspace(nullptr, n_rays, cfg->n_samples, max_active, out_width(field)).bytes;
+}
+
+extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
+                                        const float* jitter, int64_t n_rays, int32_t add_background, void* workspace,
+                                        int64_t workspace_bytes, int64_t max_active, const clift_render_out* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_cfg(cfg);
+    if (rc) return rc;
+    rc = check_field(field, cfg->heads);
+    if (rc) return rc;
+    CLIFT_CHECK_ARG(rays && out && workspace && n_rays >= 0, "null pointer");
+    CLIFT_CHECK_ARG(n_rays * (int64_t)cfg->n_samples < (1ll << 31), "n_rays*n_samples must be < 2^31 per call");
+    if (n_rays == 0) return CLIFT_OK;
+    if (max_active <= 0) max_active = n_rays * cfg->n_samples;
+    const int C = field->num_classes, DI = field->dim_instance * (field->slow_fast ? 2 : 1);
+    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, out_width(field));
+    if (ws.bytes > workspace_bytes) {
+        set_error("clift_render_forward: workspace %lld bytes < required %lld", (long long)workspace_bytes, (long long)ws.bytes);
+        return CLIFT_ERR_WORKSPACE;
+    }
+    const int heads = cfg->heads;
+    CLIFT_CHECK_ARG(out->opacity && out->depth, "opacity and depth outputs are required");
+    if (heads & CLIFT_HEAD_RGB) CLIFT_CHECK_ARG(out->rgb && out->rgb_raw, "rgb and rgb_raw outputs required for the rgb head");
+    if (heads & CLIFT_HEAD_SEMANTIC)
+        CLIFT_CHECK_ARG(out->semantic && out->semantic_raw, "semantic and semantic_raw outputs required for the semantic head");
+    if (heads & CLIFT_HEAD_INSTANCE) CLIFT_CHECK_ARG(out->instance, "instance output required for the instance head");
+    if (out->dist_reg) CLIFT_CHECK_ARG(out->dist_ray, "dist_ray is required when dist_reg is requested");
+
+    CLIFT_CUDA(cudaMemsetAsync(ws.stats, 0, 16 * sizeof(int32_t), stream));
+    MarchParams M;
+    M.g = make_geom(cfg);
+    M.f = make_factors(field, false);
+    M.shift = field->density_shift;
+    M.lines_in_smem = 0;
+    M.rays = rays;
+    M.jitter = jitter;
+    M.n_rays = n_rays;
+    M.w_dense = out->weights ? out->weights : ws.w_dense;
+    M.count = ws.count;
+    M.opacity = out->opacity;
+    M.depth = out->depth;
+    M.dist_ray = out->dist_ray;
+    M.points = out->points;
+    M.stats = reinterpret_cast<unsigned long long*>(ws.stats);
+    rc = launch_march(M, stream);
+    if (rc) return rc;
+    if (heads) {
+        rc = launch_scan(ws.count, ws.offset, ws.bsum, M.stats, n_rays, max_active, stream);
+        if (rc) return rc;
+        Workspace wf = ws;
+        wf.w_dense = M.w_dense;
+        rc = launch_fill(cfg, rays, jitter, n_rays, wf, max_active, stream);
+        if (rc) return rc;
+        if (heads & CLIFT_HEAD_RGB) CLIFT_CUDA(cudaMemsetAsync(out->rgb_raw, 0, n_rays * 3 * sizeof(float), stream));
+        if (heads & CLIFT_HEAD_SEMANTIC) CLIFT_CUDA(cudaMemsetAsync(out->semantic_raw, 0, n_rays * C * sizeof(float), stream));
+        if (heads & CLIFT_HEAD_INSTANCE) CLIFT_CUDA(cudaMemsetAsync(out->instance, 0, n_rays * DI * sizeof(float), stream));
+        rc = launch_heads_forward(cfg, field, rays, ws, max_active, n_rays, (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr,
+                                  (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr,
+                                  (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr, out->save_for_backward != 0, stream);
+        if (rc) return rc;
+    }
+    return launch_finish(n_rays, C, cfg->semantic_softmax, add_background, out->opacity,
+                         (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr, (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr,
+                         (heads & CLIFT_HEAD_RGB) ? out->rgb : nullptr, (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic : nullptr,
+                         out->dist_ray, out->dist_reg, stream);
+}
+
+extern "C" int32_t clift_render_stats(const void* workspace, int64_t* stats4, void* stream) {
+    CLIFT_CHECK_ARG(workspace && stats4, "null pointer");
+    CLIFT_CUDA(cudaMemcpyAsync(stats4, workspace, 4 * sizeof(int64_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CLIFT_OK;
+}

@@ -1,0 +1,29 @@
+// Internal host-side launch functions (one per kernel family).  Return clift_status.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "march.cuh"
+
+namespace clift {
+
+int launch_march(const MarchParams& P, cudaStream_t stream);
+int launch_scan(const int32_t* count, int32_t* offset, int32_t* bsum, unsigned long long* stats, int64_t n, int64_t cap,
+                cudaStream_t stream);
+int launch_fill(const clift_render_cfg* cfg, const float* rays, const float* jitter, int64_t n_rays, const Workspace& ws,
+                int64_t cap, cudaStream_t stream);
+int launch_finish(int64_t n_rays, int n_cls, int softmax, int add_bg, const float* opacity, const float* rgb_raw,
+                  const float* sem_raw, float* rgb, float* sem, const float* dist_ray, float* dist_reg, cudaStream_t stream);
+int launch_sample_points(const clift_render_cfg* cfg, const float* rays, const float* jitter, int64_t n_rays, float* z,
+                         float* xyz, uint8_t* inbox, cudaStream_t stream);
+int launch_density(const clift_field* field, const float* xyz, int64_t n, float* sigma, cudaStream_t stream);
+
+// heads.cu
+int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
+                         int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, bool save_rgb,
+                         cudaStream_t stream);
+
+// pack.cu
+int launch_transpose(const float* src, float* dst, int rows, int cols, int dst_rows_pad, int dst_cols_pad, cudaStream_t stream);
+
+}  // namespace clift

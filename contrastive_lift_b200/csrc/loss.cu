@@ -1,0 +1,320 @@
+// Contrastive-fusion losses on rendered embeddings, each as ONE fused forward+gradient kernel.
+//   slow-fast loss  : trainer/train_panopli_tensorf.py:256-310   (N <= ~1024 rays of one image)
+//   EMA of slow net : trainer/train_panopli_tensorf.py:325-329
+//   vanilla loss    : model/loss/loss.py:62-82
+//   TV regulariser  : model/loss/loss.py:9-26 (tensoRF.py:248-290 supplies the 1e-2*lambda scale)
+// The reference needs torch.unique, per-label Python loops, boolean-mask indexing (host syncs) and an
+// (N/2)^2 cdist; here one CTA keeps features/labels in shared memory, resolves label groups by
+// first-occurrence scans, and all reductions use a fixed tree so the result is run-to-run identical.
+#include "launchers.h"
+
+namespace clift {
+namespace {
+
+constexpr int kLossThreads = 1024;
+
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.0f;
+    if (warp == 0) {
+        t = warp_sum(t);
+        if (lane == 0) s_red[32] = t;
+    }
+    __syncthreads();
+    return s_red[32];
+}
+
+// ----------------------------------------------------------------------------------------------
+// slow-fast
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __restrict__ feats, const long long* __restrict__ labels,
+                                                                const float* __restrict__ conf, int n, int d,
+                                                                float* __restrict__ loss_out, float* __restrict__ grad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_red[33];
+    const int nf = n / 2, ns = n - nf, w2 = 2 * d;
+    long long* s_lab = reinterpret_cast<long long*>(smem_raw);      // [n]
+    float* s_feat = reinterpret_cast<float*>(s_lab + n);              // [n][2d]
+    float* s_cent = s_feat + (size_t)n * w2;                          // [ns][d] centroid of slow sample j's label group
+    float* s_num = s_cent + (size_t)ns * d;                           // [nf]
+    float* s_den = s_num + nf;                                        // [nf]
+    float* s_cw = s_den + nf;                                         // [nf] concentration weight conf*e/(n_l), 0 if label unmatched
+    int* s_rep = reinterpret_cast<int*>(s_cw + nf);                   // [nf] slow representative (absolute index) or -1
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_lab[i] = labels[i];
+    for (int i = threadIdx.x; i < n * w2; i += blockDim.x) s_feat[i] = feats[i];
+    if (grad)
+        for (int i = threadIdx.x; i < n * w2; i += blockDim.x) grad[i] = 0.0f;
+    __syncthreads();
+    if (nf == 0 || ns == 0) {   // trainer:285-288
+        if (threadIdx.x == 0) loss_out[0] = 0.0f;
+        return;
+    }
+    // slow centroids: every slow sample gets the mean of its label group (members summed in index order)
+    for (int j = threadIdx.x; j < ns; j += blockDim.x) {
+        const long long l = s_lab[nf + j];
+        int cnt = 0;
+        for (int k = 0; k < d; ++k) s_cent[j * d + k] = 0.0f;
+        for (int jj = 0; jj < ns; ++jj)
+            if (s_lab[nf + jj] == l) {
+                ++cnt;
+                for (int k = 0; k < d; ++k) s_cent[j * d + k] += s_feat[(nf + jj) * w2 + d + k];
+            }
+        for (int k = 0; k < d; ++k) s_cent[j * d + k] /= (float)cnt;
+    }
+    __syncthreads();
+    float my_conc = 0.0f, my_logp = 0.0f, my_valid = 0.0f, my_first = 0.0f;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const long long l = s_lab[i];
+        int rep = -1;
+        for (int j = 0; j < ns; ++j)
+            if (s_lab[nf + j] == l) {
+                rep = j;
+                break;
+            }
+        int n_l = 0;
+        bool first = true;
+        for (int ii = 0; ii < nf; ++ii)
+            if (s_lab[ii] == l) {
+                ++n_l;
+                if (ii < i) first = false;
+            }
+        float cw = 0.0f;
+        if (rep >= 0) {
+            float dsq = 0.0f;
+            for (int k = 0; k < d; ++k) {
+                const float df = s_feat[i * w2 + k] - s_cent[rep * d + k];
+                dsq += df * df;
+            }
+            cw = expf(-dsq) * conf[i] / (float)n_l;
+            my_conc += cw;
+            if (first) my_first += 1.0f;
+        }
+        s_cw[i] = cw;
+        s_rep[i] = rep;
+        float num = 0.0f, den = 0.0f;
+        for (int j = 0; j < ns; ++j) {
+            float dsq = 0.0f;
+            for (int k = 0; k < d; ++k) {
+                const float df = s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k];
+                dsq += df * df;
+            }
+            const float e = expf(expf(-sqrtf(dsq)));
+            den += e;
+            if (s_lab[nf + j] == l) num += e;
+        }
+        s_num[i] = num;
+        s_den[i] = den;
+        const float prob = num / den;
+        if (prob != 0.0f) {
+            my_logp += logf(prob);
+            my_valid += 1.0f;
+        }
+    }
+    const float conc = block_sum(my_conc, s_red);
+    const float n_int = block_sum(my_first, s_red);
+    const float logp = block_sum(my_logp, s_red);
+    const float n_valid = block_sum(my_valid, s_red);
+    if (threadIdx.x == 0) {
+        float l = 0.0f;
+        if (n_int > 0.0f) l = -conc / n_int;
+        l += -(logp / n_valid);      // 0/0 -> NaN like mean() of an empty selection
+        loss_out[0] = l;
+    }
+    if (!grad) return;
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        const long long l = s_lab[i];
+        const float num = s_num[i], den = s_den[i];
+        const bool valid = (num / den) != 0.0f;
+        for (int k = 0; k < d; ++k) {
+            float g = 0.0f;
+            if (s_rep[i] >= 0) g += 2.0f * s_cw[i] / n_int * (s_feat[i * w2 + k] - s_cent[s_rep[i] * d + k]);
+            grad[i * w2 + k] = g;
+        }
+        if (!valid) continue;
+        for (int j = 0; j < ns; ++j) {
+            float dsq = 0.0f;
+            for (int k = 0; k < d; ++k) {
+                const float df = s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k];
+                dsq += df * df;
+            }
+            const float dist = sqrtf(dsq);
+            if (dist == 0.0f) continue;   // cdist backward yields 0 at coincident points
+            const float s = expf(-dist), e = expf(s);
+            const float c = ((s_lab[nf + j] == l ? 1.0f / num : 0.0f) - 1.0f / den) * e * s / (dist * n_valid);
+            for (int k = 0; k < d; ++k) grad[i * w2 + k] += c * (s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// vanilla contrastive (loss.py:62-82)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kLossThreads) contrastive_kernel(const float* __restrict__ feats, const long long* __restrict__ labels,
+                                                                   int n, int d, float temperature, float* __restrict__ loss_out,
+                                                                   float* __restrict__ grad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_red[33];
+    long long* s_lab = reinterpret_cast<long long*>(smem_raw);   // [n]
+    float* s_feat = reinterpret_cast<float*>(s_lab + n);           // [n][d]
+    float* s_a = s_feat + (size_t)n * d;                           // [n] 1/p_i if i contributes else 0
+    float* s_b = s_a + n;                                          // [n] 1/Z_i if i contributes else 0
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_lab[i] = labels[i];
+    for (int i = threadIdx.x; i < n * d; i += blockDim.x) s_feat[i] = feats[i];
+    __syncthreads();
+    float my_log = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long l = s_lab[i];
+        float p = 0.0f, z = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            float dsq = 0.0f;
+            for (int k = 0; k < d; ++k) {
+                const float df = s_feat[i * d + k] - s_feat[j * d + k];
+                dsq += df * df;
+            }
+            const bool pos = (j != i) && (s_lab[j] == l);
+            const float e = expf(expf(-dsq / (pos ? temperature : 1.0f)));
+            z += e;
+            if (pos) p += e;
+        }
+        const float prob = p / z;
+        const bool valid = prob != 0.0f;
+        if (valid) my_log += logf(prob);
+        s_a[i] = valid ? 1.0f / p : 0.0f;
+        s_b[i] = valid ? 1.0f / z : 0.0f;
+    }
+    const float tot = block_sum(my_log, s_red);
+    if (threadIdx.x == 0) loss_out[0] = -tot / (float)n;
+    if (!grad) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long l = s_lab[i];
+        for (int k = 0; k < d; ++k) grad[i * d + k] = 0.0f;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            float dsq = 0.0f;
+            for (int k = 0; k < d; ++k) {
+                const float df = s_feat[i * d + k] - s_feat[j * d + k];
+                dsq += df * df;
+            }
+            const bool pos = s_lab[j] == l;
+            const float temp = pos ? temperature : 1.0f;
+            const float s = expf(-dsq / temp), e = expf(s);
+            const float m = pos ? 1.0f : 0.0f;
+            const float c = e * s * (2.0f / temp) * ((m * s_a[i] - s_b[i]) + (m * s_a[j] - s_b[j])) / (float)n;
+            for (int k = 0; k < d; ++k) grad[i * d + k] += c * (s_feat[i * d + k] - s_feat[j * d + k]);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// EMA, TV
+// ----------------------------------------------------------------------------------------------
+__global__ void ema_kernel(float* __restrict__ slow, const float* __restrict__ fast, int64_t n, float m, float om) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slow[i] = __fadd_rn(__fmul_rn(slow[i], m), __fmul_rn(om, fast[i]));   // mul_ then add_ of a scaled copy
+}
+
+// single CTA, fixed-order sum: planes are <= a few M elements and this runs once per step per plane
+__global__ void __launch_bounds__(1024) tv_value_kernel(const float* __restrict__ x, int C, int H, int W, float* __restrict__ out) {
+    __shared__ float s_red[33];
+    const int64_t n = (int64_t)H * W * C;
+    float th = 0.0f, tw = 0.0f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int64_t pix = i / C;
+        const int h = (int)(pix / W), w = (int)(pix - (int64_t)h * W);
+        const float v = x[i];
+        if (h + 1 < H) {
+            const float dd = x[i + (int64_t)W * C] - v;
+            th += dd * dd;
+        }
+        if (w + 1 < W) {
+            const float dd = x[i + C] - v;
+            tw += dd * dd;
+        }
+    }
+    const float sh = block_sum(th, s_red);
+    const float sw = block_sum(tw, s_red);
+    if (threadIdx.x == 0) {
+        const float cnt_h = (float)((double)C * (H - 1) * W + 1e-4), cnt_w = (float)((double)C * H * (W - 1) + 1e-4);
+        out[0] = 2.0f * (sh / cnt_h + sw / cnt_w);
+    }
+}
+
+__global__ void __launch_bounds__(256) tv_grad_kernel(const float* __restrict__ x, int C, int H, int W, float* __restrict__ g,
+                                                      float scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)H * W * C) return;
+    const int64_t pix = i / C;
+    const int h = (int)(pix / W), w = (int)(pix - (int64_t)h * W);
+    const float cnt_h = (float)((double)C * (H - 1) * W + 1e-4), cnt_w = (float)((double)C * H * (W - 1) + 1e-4);
+    const float v = x[i];
+    float gh = 0.0f, gw = 0.0f;
+    if (h > 0) gh += v - x[i - (int64_t)W * C];
+    if (h + 1 < H) gh -= x[i + (int64_t)W * C] - v;
+    if (w > 0) gw += v - x[i - C];
+    if (w + 1 < W) gw -= x[i + C] - v;
+    g[i] += scale * 4.0f * (gh / cnt_h + gw / cnt_w);
+}
+
+}  // namespace
+}  // namespace clift
+
+using namespace clift;
+
+extern "C" int32_t clift_slowfast_loss(const float* features, const int64_t* labels, const float* confidences, int32_t n,
+                                       int32_t d, float* loss, float* grad_features, void* stream) {
+    CLIFT_CHECK_ARG(features && labels && confidences && loss && n >= 0 && d > 0, "null pointer or bad size");
+    if (n == 0) {
+        CLIFT_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), (cudaStream_t)stream));
+        return CLIFT_OK;
+    }
+    const int nf = n / 2, ns = n - nf;
+    const size_t smem = (size_t)n * 8 + (size_t)n * 2 * d * 4 + (size_t)ns * d * 4 + (size_t)nf * 4 * 4 + 64;
+    CLIFT_CHECK_SUPPORTED(smem <= 200 * 1024, "slow-fast loss: N*d too large for one CTA's shared memory");
+    CLIFT_CUDA(cudaFuncSetAttribute(slowfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slowfast_kernel<<<1, kLossThreads, smem, (cudaStream_t)stream>>>(features, (const long long*)labels, confidences, n, d, loss,
+                                                                     grad_features);
+    CLIFT_AFTER_LAUNCH("slowfast_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_contrastive_loss(const float* features, const int64_t* labels, int32_t n, int32_t dim,
+                                          float temperature, float* loss, float* grad_features, void* stream) {
+    CLIFT_CHECK_ARG(features && labels && loss && n > 0 && dim > 0, "null pointer or bad size");
+    const size_t smem = (size_t)n * 8 + (size_t)n * dim * 4 + (size_t)n * 8 + 64;
+    CLIFT_CHECK_SUPPORTED(smem <= 200 * 1024, "contrastive loss: N*D too large for one CTA's shared memory");
+    CLIFT_CUDA(cudaFuncSetAttribute(contrastive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    contrastive_kernel<<<1, kLossThreads, smem, (cudaStream_t)stream>>>(features, (const long long*)labels, n, dim, temperature,
+                                                                        loss, grad_features);
+    CLIFT_AFTER_LAUNCH("contrastive_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_ema_update(float* slow, const float* fast, int64_t n, float momentum, void* stream) {
+    CLIFT_CHECK_ARG(slow && fast && n >= 0, "null pointer or bad size");
+    if (n == 0) return CLIFT_OK;
+    // the reference scales by the Python double (1 - momentum) rounded to fp32 when it meets the tensor
+    const float om = (float)(1.0 - (double)momentum);
+    ema_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(slow, fast, n, momentum, om);
+    CLIFT_AFTER_LAUNCH("ema_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_tv_loss(const float* plane_hwc, int32_t comps, int32_t h, int32_t w, float* loss, float* grad_hwc,
+                                 float grad_scale, void* stream) {
+    CLIFT_CHECK_ARG(plane_hwc && comps > 0 && h > 0 && w > 0, "null pointer or bad size");
+    if (loss) {
+        tv_value_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(plane_hwc, comps, h, w, loss);
+        CLIFT_AFTER_LAUNCH("tv_value_kernel");
+    }
+    if (grad_hwc) {
+        const int64_t n = (int64_t)comps * h * w;
+        tv_grad_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(plane_hwc, comps, h, w, grad_hwc, grad_scale);
+        CLIFT_AFTER_LAUNCH("tv_grad_kernel");
+    }
+    return CLIFT_OK;
+}

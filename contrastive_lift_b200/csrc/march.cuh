@@ -1,0 +1,96 @@
+// Launch-parameter blocks shared between march.cu, heads.cu and api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace clift {
+
+struct GeomParams {   // TensoRFRenderer constants, by value
+    float amin[3], amax[3], inv[3];
+    float step, scale, thres;
+    int S;
+};
+
+struct FactorParams {   // one VM factor set (density / appearance), packed layout
+    const float* plane[3];
+    const float* line[3];
+    int pw[3], ph[3], ll[3];   // plane width/height, line length per mode
+    int comps;
+};
+
+struct MarchParams {
+    GeomParams g;
+    FactorParams f;
+    float shift;
+    int lines_in_smem;
+    const float* rays;
+    const float* jitter;
+    int64_t n_rays;
+    float* w_dense;     // [B,S]
+    int32_t* count;     // [B]
+    float* opacity;     // [B]
+    float* depth;       // [B]
+    float* dist_ray;    // [B] or null
+    float* points;      // [B,3] or null
+    unsigned long long* stats;   // [8] u64: 0 n_active 1 n_inbox 2 overflow
+};
+
+inline GeomParams make_geom(const clift_render_cfg* c) {
+    GeomParams g;
+    for (int k = 0; k < 3; ++k) {
+        g.amin[k] = c->aabb_min[k];
+        g.amax[k] = c->aabb_max[k];
+        g.inv[k] = c->inv_extent[k];
+    }
+    g.step = c->step_size;
+    g.scale = c->distance_scale;
+    g.thres = c->weight_thres;
+    g.S = c->n_samples;
+    return g;
+}
+
+inline FactorParams make_factors(const clift_field* f, bool appearance) {
+    FactorParams p;
+    for (int m = 0; m < 3; ++m) {
+        p.plane[m] = appearance ? f->appearance_plane[m] : f->density_plane[m];
+        p.line[m] = appearance ? f->appearance_line[m] : f->density_line[m];
+        p.pw[m] = f->grid[mode_a(m)];
+        p.ph[m] = f->grid[mode_b(m)];
+        p.ll[m] = f->grid[mode_v(m)];
+    }
+    p.comps = appearance ? f->appearance_comps : f->density_comps;
+    return p;
+}
+
+#ifdef __CUDACC__
+// One quad lane's share (channels ch, ch+16, ...) of  sum_modes sum_c P_c(x_a,x_b) * L_c(x_v).
+// `lines_s` != null: density line factors staged in shared memory, modes back to back.
+template <int NV>
+__device__ __forceinline__ float vm_dot_partial(const FactorParams& f, const float* lines_s, float x0, float x1, float x2,
+                                                int q) {
+    const float xs[3] = {x0, x1, x2};
+    float acc = 0.0f;
+    int soff = 0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const Tap2 t2 = make_tap2(xs[mode_a(m)], xs[mode_b(m)], f.pw[m], f.ph[m]);
+        const Tap1 t1 = make_tap1(xs[mode_v(m)], f.ll[m]);
+        const float* line = lines_s ? lines_s + soff : f.line[m];
+        soff += f.ll[m] * f.comps;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const int ch = v * 16 + q * 4;
+            const float4 p = plane_tap(f.plane[m], t2, f.pw[m], f.comps, ch);
+            const float4 l = line_tap(line, t1, f.comps, ch);
+            acc = fmaf(p.x, l.x, acc);
+            acc = fmaf(p.y, l.y, acc);
+            acc = fmaf(p.z, l.z, acc);
+            acc = fmaf(p.w, l.w, acc);
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+#endif
+
+}  // namespace clift

@@ -1,0 +1,198 @@
+/*
+ * clift_b200.h - C ABI of libclift_b200.so: the B200 (sm_100a) implementation of the
+ * volumetric-render + contrastive-fusion hot path of yashbhalgat/Contrastive-Lift.
+ *
+ * The reference has no FFI of its own (it is pure Python over ATen); each entry point below
+ * replaces one group of reference functions, cited as file:line relative to the reference tree.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - plain C, no torch types; every array is a caller-owned DEVICE pointer to contiguous fp32
+ *    (int32/int64 where stated); shapes are explicit integers; `stream` is a cudaStream_t passed
+ *    as void* (the caller's current stream).
+ *  - calls are stream-ordered, never synchronise the device, never allocate device memory;
+ *    scratch comes from a caller-provided workspace sized by clift_render_workspace_bytes().
+ *  - every function returns 0 on success or a negative clift_status; clift_last_error() gives the
+ *    message for the calling thread.  Nothing throws across the boundary.
+ *  - there is no CPU fallback: without a CUDA device every compute call returns CLIFT_ERR_CUDA.
+ */
+#ifndef CLIFT_B200_H
+#define CLIFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLIFT_ABI_VERSION 1
+#define CLIFT_MAX_LAYERS 8
+#define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
+#define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
+#define CLIFT_TILE 128           /* active samples per head tile */
+
+typedef enum {
+    CLIFT_OK = 0,
+    CLIFT_ERR_ARG = -1,          /* null pointer, negative size, misaligned buffer */
+    CLIFT_ERR_UNSUPPORTED = -2,  /* configuration outside the compiled envelope */
+    CLIFT_ERR_CUDA = -3,         /* CUDA runtime / launch failure (message has the cudaError) */
+    CLIFT_ERR_WORKSPACE = -4     /* workspace too small */
+} clift_status;
+
+/* One fully-connected stack (nn.Sequential of Linear/ReLU: tensoRF.py:393-397, 473-490, 577-582).
+ * Weights are the PACKED form written by clift_pack_linear(): W^T, row-major [k_pad][n_pad] with
+ * k_pad = round_up(in,16), n_pad = round_up(out,64), zero filled; bias is [n_pad] zero filled. */
+typedef struct {
+    int32_t n_layers;
+    int32_t dims[CLIFT_MAX_LAYERS + 1];       /* logical widths: in, hidden..., out */
+    const float* wt[CLIFT_MAX_LAYERS];
+    const float* bias[CLIFT_MAX_LAYERS];
+} clift_mlp;
+
+/* Gradient mirror of clift_mlp (same packed shapes); null pointers = do not accumulate. */
+typedef struct {
+    float* wt[CLIFT_MAX_LAYERS];
+    float* bias[CLIFT_MAX_LAYERS];
+} clift_mlp_grad;
+
+/* TensorVMSplit parameters (tensoRF.py:32-106) in the kernels' HBM layout.
+ * plane i: channel-last [H=grid[b]][W=grid[a]][comps] with (a,b)=matrix_mode[i] in {(0,1),(0,2),(1,2)}
+ * line  i: [grid[v]][comps] with v=vector_mode[i] in {2,1,0};  written by clift_pack_plane/line(). */
+typedef struct {
+    int32_t grid[3];                 /* samples per axis x,y,z (renderer.grid_dim) */
+    int32_t density_comps;           /* 16 (supported: 16, 32, 48) */
+    int32_t appearance_comps;        /* 48 (supported: 16, 32, 48, 64) */
+    int32_t dim_appearance;          /* 27 */
+    int32_t pe_view, pe_feat;        /* 2, 2 (tensoRF.py:400-418) */
+    int32_t pe_sem, pe_ins;          /* 0, 0 */
+    int32_t num_classes;             /* semantic head width C */
+    int32_t dim_instance;            /* per-net embedding width d (max_instances) */
+    int32_t slow_fast;               /* 1: instance output is [fast | slow], 2d wide */
+    float density_shift;             /* -10 */
+    const float* density_plane[3];
+    const float* density_line[3];
+    const float* appearance_plane[3];
+    const float* appearance_line[3];
+    const float* basis;              /* appearance_basis_mat packed as a 1-layer clift_mlp weight */
+    clift_mlp rgb;                   /* render_appearance_mlp.mlp       (H1) */
+    clift_mlp semantic;              /* render_semantic_mlp.mlp         (H2) */
+    clift_mlp instance_fast;         /* render_instance_mlp.mlp         (H3) */
+    clift_mlp instance_slow;         /* render_instance_mlp.slow_mlp    (H3) */
+} clift_field;
+
+typedef struct {
+    float* density_plane[3];
+    float* density_line[3];
+    float* appearance_plane[3];
+    float* appearance_line[3];
+    float* basis;
+    clift_mlp_grad rgb, semantic, instance_fast, instance_slow;
+} clift_field_grad;
+
+/* TensoRFRenderer constants (renderer:39-78). */
+typedef struct {
+    float aabb_min[3], aabb_max[3];  /* renderer.bbox_aabb */
+    float inv_extent[3];             /* renderer.inv_box_extent = 2/extent (fp32, as stored) */
+    float step_size;                 /* renderer.step_size */
+    int32_t n_samples;               /* renderer.n_samples */
+    float distance_scale;            /* 25 */
+    float weight_thres;              /* raymarch_weight_thres 1e-4 */
+    int32_t semantic_softmax;        /* semantic_weight_mode == "softmax" */
+    int32_t heads;                   /* bit mask of CLIFT_HEAD_* to evaluate */
+} clift_render_cfg;
+
+#define CLIFT_HEAD_RGB 1
+#define CLIFT_HEAD_SEMANTIC 2
+#define CLIFT_HEAD_INSTANCE 4
+#define CLIFT_HEAD_ALL 7
+
+/* Per-call outputs of the march + heads (all [n_rays, ...], fp32). Null = not wanted. */
+typedef struct {
+    float* rgb;          /* [B,3]   final: clamp(raw + bg*(1-opacity), 0, 1)       renderer:164-167 */
+    float* semantic;     /* [B,C]   final: log(p/(sum+1e-8)+1e-8) in softmax mode  renderer:160-162 */
+    float* instance;     /* [B,2d]  (or [B,d] without slow net)                    renderer:149    */
+    float* depth;        /* [B]     sum w*t                                        renderer:174    */
+    float* opacity;      /* [B]     sum w                                          renderer:137    */
+    float* dist_reg;     /* [1]     mean over rays of the distortion loss          renderer:101    */
+    float* rgb_raw;      /* [B,3]   sum w*rgb before bg/clamp   (saved for backward) */
+    float* semantic_raw; /* [B,C]   sum w*sem before normalise  (saved for backward) */
+    float* dist_ray;     /* [B]     per-ray distortion loss */
+    float* points;       /* [B,3]   o + depth*d (forward_instance_feature, renderer:211-213) */
+    float* weights;      /* [B,S]   dense compositing weights w_i (parity tests); null = keep in workspace */
+    int32_t save_for_backward; /* 1: keep per-sample rgb in the workspace for clift_render_backward */
+} clift_render_out;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int32_t clift_abi_version(void);
+const char* clift_last_error(void);
+/* Number of kernel launches issued by this library since load (all threads); bench.py's gpu_launches. */
+int64_t clift_launch_count(void);
+
+/* ---- layout packing (one transpose kernel; used for parameters and, inverted, for gradients) --- */
+/* (1,C,H,W) -> [H][W][C]  and back.   tensoRF.py:99-106 layouts. */
+int32_t clift_pack_plane(const float* nchw, float* hwc, int32_t comps, int32_t h, int32_t w, void* stream);
+int32_t clift_unpack_plane(const float* hwc, float* nchw, int32_t comps, int32_t h, int32_t w, void* stream);
+/* nn.Linear weight [out][in] (+ bias[out] or null) -> packed W^T [k_pad][n_pad], bias [n_pad]; and back. */
+int32_t clift_pack_linear(const float* w, const float* b, float* wt, float* bias_pad,
+                          int32_t n_out, int32_t n_in, void* stream);
+int32_t clift_unpack_linear(const float* wt, const float* bias_pad, float* w, float* b,
+                            int32_t n_out, int32_t n_in, void* stream);
+
+/* ---- R1-R4: util/ray.py:8-12,25-31,46-54,81-99 + dataset/base.py:211-219 ------------------------
+ * rays[row*W+col] = [o(3), d(3), near, far]; intrinsics (3x3) and cam2world (4x4) are HOST row-major.
+ * *bad_rays (device int32) counts rays whose sphere determinant is negative (the reference asserts). */
+int32_t clift_gen_rays(const float* intrinsics9, const float* cam2world16, int32_t height, int32_t width,
+                       float near, float radius, float* rays, int32_t* bad_rays, void* stream);
+
+/* ---- S1,S3: renderer:800-817, 633-634.  Debug/parity entry: materialises what the march computes
+ * on the fly.  z [B,S], xyz [B,S,3] (normalised), inbox [B,S] uint8; jitter [B] or null. */
+int32_t clift_sample_points(const clift_render_cfg* cfg, const float* rays, const float* jitter, int64_t n_rays,
+                            float* z, float* xyz, uint8_t* inbox, void* stream);
+
+/* ---- F1: tensoRF.py:108-125  sigma[n] = softplus(sum_modes sum_c P*L + shift) at normalised xyz [n,3]. */
+int32_t clift_density(const clift_field* field, const float* xyz, int64_t n, float* sigma, void* stream);
+
+/* ---- S1-C3: TensoRFRenderer.forward (renderer:80-176), forward_instance_feature (:178-217),
+ * forward_segment_feature (:259-300) - selected by cfg->heads.
+ *  rays [B,8]; jitter [B] = perturb*U[0,1) or null (inference); add_background = outcome of
+ *  `white_bg or (is_train and rand<0.5)` (renderer:164) - RNG stays with the caller for parity.
+ *  max_active bounds the compacted active-sample list (<= 0: worst case n_rays*n_samples); one call
+ *  handles n_rays*n_samples < 2^31 - callers split larger frames.                                */
+int64_t clift_render_workspace_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays,
+                                     int64_t max_active);
+int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
+                             const float* jitter, int64_t n_rays, int32_t add_background,
+                             void* workspace, int64_t workspace_bytes, int64_t max_active,
+                             const clift_render_out* out, void* stream);
+/* Counters of the last forward on this workspace, copied device-to-device into int64 stats4[4] =
+ * {n_active (weight > thres), n_inbox, overflow flag (n_active > max_active), n_tiles}. */
+int32_t clift_render_stats(const void* workspace, int64_t* stats4, void* stream);
+
+/* Backward of clift_render_forward given dL/d(rgb, semantic, instance, dist_reg) (null = zero).
+ * Re-marches the rays (recompute, nothing [B,S,K]-sized is saved), and accumulates (+=) into `grad`
+ * in packed layout.  Semantic/instance gradients stop at the heads (stop_semantic_grad, renderer:144). */
+int32_t clift_render_backward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
+                              const float* jitter, int64_t n_rays, int32_t add_background,
+                              void* workspace, int64_t workspace_bytes, int64_t max_active,
+                              const clift_render_out* saved, const float* g_rgb, const float* g_semantic,
+                              const float* g_instance, const float* g_dist_reg,
+                              const clift_field_grad* grad, void* stream);
+
+/* ---- L1: slow-fast contrastive loss, trainer/train_panopli_tensorf.py:256-310 (forward + gradient).
+ * features [N,2d] = [fast|slow], labels int64 [N], confidences [N]; loss [1]; grad_features [N,2d]
+ * (d loss / d features for upstream 1; only fast half / fast columns are non-zero).            */
+int32_t clift_slowfast_loss(const float* features, const int64_t* labels, const float* confidences,
+                            int32_t n, int32_t d, float* loss, float* grad_features, void* stream);
+/* trainer:325-329: slow = slow*momentum + (1-momentum)*fast over a flat fp32 arena. */
+int32_t clift_ema_update(float* slow, const float* fast, int64_t n, float momentum, void* stream);
+/* ---- L2: model/loss/loss.py:62-82. features [N,D]. */
+int32_t clift_contrastive_loss(const float* features, const int64_t* labels, int32_t n, int32_t dim,
+                               float temperature, float* loss, float* grad_features, void* stream);
+/* ---- TV: model/loss/loss.py:9-26 on a packed plane [H][W][C]; adds scale*dTV/dplane into grad (may be null). */
+int32_t clift_tv_loss(const float* plane_hwc, int32_t comps, int32_t h, int32_t w, float* loss,
+                      float* grad_hwc, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIFT_B200_H */
