@@ -32,6 +32,14 @@ int sm_count() {
     return cached;
 }
 
+static bool g_profile = false;
+static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static bool g_ev_valid = false;
+
+static void profile_mark(int i, cudaStream_t stream) {
+    if (g_profile && g_ev[i]) cudaEventRecord(g_ev[i], stream);
+}
+
 static int check_mlp(const clift_mlp& m, const char* name, int expect_out) {
     if (m.n_layers < 1 || m.n_layers > CLIFT_MAX_LAYERS) {
         set_error("%s: n_layers %d outside [1,%d]", name, m.n_layers, CLIFT_MAX_LAYERS);
@@ -124,10 +132,11 @@ extern "C" int32_t clift_density(const clift_field* field, const float* xyz, int
 }
 
 extern "C" int64_t clift_render_workspace_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays,
-                                                int64_t max_active) {
+                                                int64_t max_active, int32_t save_for_backward) {
     if (!cfg || !field || n_rays < 0) return CLIFT_ERR_ARG;
     if (max_active <= 0) max_active = n_rays * cfg->n_samples;
-    return carve_workspace(nullptr, n_rays, cfg->n_samples, max_active, out_width(field)).bytes;
+    const StashLayout lay = make_stash_layout(field, cfg->heads);
+    return carve_workspace(nullptr, n_rays, cfg->n_samples, max_active, out_width(field), save_for_backward != 0, &lay).bytes;
 }
 
 extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
@@ -138,12 +147,18 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
     if (rc) return rc;
     rc = check_field(field, cfg->heads);
     if (rc) return rc;
-    CLIFT_CHECK_ARG(rays && out && workspace && n_rays >= 0, "null pointer");
+    CLIFT_CHECK_ARG(n_rays >= 0 && out, "negative n_rays or null out");
+    if (n_rays == 0) {   // empty chunk: nothing to launch except the (empty) mean
+        if (out->dist_reg) CLIFT_CUDA(cudaMemsetAsync(out->dist_reg, 0, sizeof(float), stream));
+        return CLIFT_OK;
+    }
+    CLIFT_CHECK_ARG(rays && workspace, "null pointer");
     CLIFT_CHECK_ARG(n_rays * (int64_t)cfg->n_samples < (1ll << 31), "n_rays*n_samples must be < 2^31 per call");
-    if (n_rays == 0) return CLIFT_OK;
     if (max_active <= 0) max_active = n_rays * cfg->n_samples;
     const int C = field->num_classes, DI = field->dim_instance * (field->slow_fast ? 2 : 1);
-    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, out_width(field));
+    const bool save = out->save_for_backward != 0;
+    const StashLayout lay = make_stash_layout(field, cfg->heads);
+    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, out_width(field), save, &lay);
     if (ws.bytes > workspace_bytes) {
         set_error("clift_render_forward: workspace %lld bytes < required %lld", (long long)workspace_bytes, (long long)ws.bytes);
         return CLIFT_ERR_WORKSPACE;
@@ -166,14 +181,18 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
     M.jitter = jitter;
     M.n_rays = n_rays;
     M.w_dense = out->weights ? out->weights : ws.w_dense;
+    M.sigma_dense = save ? ws.sigma_dense : nullptr;
+    M.trans_dense = save ? ws.trans_dense : nullptr;
     M.count = ws.count;
     M.opacity = out->opacity;
     M.depth = out->depth;
     M.dist_ray = out->dist_ray;
     M.points = out->points;
     M.stats = reinterpret_cast<unsigned long long*>(ws.stats);
+    profile_mark(0, stream);
     rc = launch_march(M, stream);
     if (rc) return rc;
+    profile_mark(1, stream);
     if (heads) {
         rc = launch_scan(ws.count, ws.offset, ws.bsum, M.stats, n_rays, max_active, stream);
         if (rc) return rc;
@@ -184,15 +203,38 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         if (heads & CLIFT_HEAD_RGB) CLIFT_CUDA(cudaMemsetAsync(out->rgb_raw, 0, n_rays * 3 * sizeof(float), stream));
         if (heads & CLIFT_HEAD_SEMANTIC) CLIFT_CUDA(cudaMemsetAsync(out->semantic_raw, 0, n_rays * C * sizeof(float), stream));
         if (heads & CLIFT_HEAD_INSTANCE) CLIFT_CUDA(cudaMemsetAsync(out->instance, 0, n_rays * DI * sizeof(float), stream));
+        profile_mark(2, stream);
         rc = launch_heads_forward(cfg, field, rays, ws, max_active, n_rays, (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr,
                                   (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr,
-                                  (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr, out->save_for_backward != 0, stream);
+                                  (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr, save ? &lay : nullptr, stream);
         if (rc) return rc;
+    } else {
+        profile_mark(2, stream);
     }
-    return launch_finish(n_rays, C, cfg->semantic_softmax, add_background, out->opacity,
+    profile_mark(3, stream);
+    rc = launch_finish(n_rays, C, cfg->semantic_softmax, add_background, out->opacity,
                          (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr, (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr,
                          (heads & CLIFT_HEAD_RGB) ? out->rgb : nullptr, (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic : nullptr,
                          out->dist_ray, out->dist_reg, stream);
+    profile_mark(4, stream);
+    g_ev_valid = g_profile;
+    return rc;
+}
+
+extern "C" int32_t clift_profile_enable(int32_t on) {
+    if (on && !g_ev[0])
+        for (int i = 0; i < 5; ++i) CLIFT_CUDA(cudaEventCreate(&g_ev[i]));
+    g_profile = on != 0;
+    g_ev_valid = false;
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_profile_stage_ms(float* ms4) {
+    CLIFT_CHECK_ARG(ms4 != nullptr, "null pointer");
+    CLIFT_CHECK_ARG(g_ev_valid, "no profiled clift_render_forward since clift_profile_enable(1)");
+    CLIFT_CUDA(cudaEventSynchronize(g_ev[4]));
+    for (int i = 0; i < 4; ++i) CLIFT_CUDA(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+    return CLIFT_OK;
 }
 
 extern "C" int32_t clift_render_stats(const void* workspace, int64_t* stats4, void* stream) {

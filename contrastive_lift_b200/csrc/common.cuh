@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/clift_b200.h"
 
@@ -52,17 +53,73 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 static inline int k_pad(int k) { return (int)round_up(k, 16); }
 static inline int n_pad(int n) { return (int)round_up(n, 64); }
+static inline int dgrad_pad(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 256); }
 
 // tensoRF.py:61-62
 __host__ __device__ __forceinline__ int mode_a(int m) { return m == 2 ? 1 : 0; }
 __host__ __device__ __forceinline__ int mode_b(int m) { return m == 0 ? 1 : 2; }
 __host__ __device__ __forceinline__ int mode_v(int m) { return 2 - m; }
 
+// Per-tile activation stash of the training path.  Every row is CLIFT_TILE floats (one value per record of
+// the tile); a tile's rows are contiguous.  MLP ids: 0 semantic, 1 instance fast, 2 instance slow, 3 rgb, 4 basis.
+//   a_off[id][l] : rows holding the INPUT of layer l (k_pad(dims[l]) rows, zero padded)
+//   z_off[id][l] : rows holding dL/d(pre-activation OUTPUT of layer l) (n_pad(dims[l+1]) rows, zero padded)
+//   prob_off     : softmax probabilities of the semantic head (n_pad(C) rows)
+struct StashLayout {
+    int a_off[5][CLIFT_MAX_LAYERS];
+    int z_off[5][CLIFT_MAX_LAYERS];
+    int prob_off;
+    int a_rows, z_rows;   // rows per tile in the A / Z stash
+};
+
+inline const clift_mlp* field_mlp(const clift_field* f, int id, clift_mlp* basis_tmp) {
+    switch (id) {
+        case 0: return &f->semantic;
+        case 1: return &f->instance_fast;
+        case 2: return &f->instance_slow;
+        case 3: return &f->rgb;
+        default:
+            memset(basis_tmp, 0, sizeof(*basis_tmp));
+            basis_tmp->n_layers = 1;
+            basis_tmp->dims[0] = 3 * f->appearance_comps;
+            basis_tmp->dims[1] = f->dim_appearance;
+            basis_tmp->wt[0] = f->basis;
+            basis_tmp->w_dgrad[0] = f->basis_dgrad;
+            return basis_tmp;
+    }
+}
+
+inline StashLayout make_stash_layout(const clift_field* f, int heads) {
+    StashLayout L;
+    memset(&L, 0, sizeof(L));
+    int a = 0, z = 0;
+    for (int id = 0; id < 5; ++id) {
+        const bool on = (id == 0 && (heads & CLIFT_HEAD_SEMANTIC)) || (id == 1 && (heads & CLIFT_HEAD_INSTANCE)) ||
+                        (id == 2 && (heads & CLIFT_HEAD_INSTANCE) && f->slow_fast) || (id >= 3 && (heads & CLIFT_HEAD_RGB));
+        if (!on) continue;
+        clift_mlp tmp;
+        const clift_mlp* m = field_mlp(f, id, &tmp);
+        for (int l = 0; l < m->n_layers; ++l) {
+            L.a_off[id][l] = a;
+            a += k_pad(m->dims[l]);
+            L.z_off[id][l] = z;
+            z += n_pad(m->dims[l + 1]);
+        }
+        if (id == 0) {
+            L.prob_off = a;
+            a += n_pad(f->num_classes);
+        }
+    }
+    L.a_rows = a;
+    L.z_rows = z;
+    return L;
+}
+
 // ---------------------------------------------------------------------------------------
 // Workspace carve-up (host side).  All regions 256-byte aligned.
 // ---------------------------------------------------------------------------------------
 struct Workspace {
-    int32_t* stats;     // [16]: 0 n_active, 1 n_inbox(lo), 2 overflow flag, 3 n_tiles
+    int32_t* stats;     // [16]: u64 view: 0 n_active, 1 n_inbox, 2 overflow flag, 3 n_tiles
     float* w_dense;     // [B*S] compositing weights (march -> fill, backward)
     int32_t* count;     // [B] active samples per ray
     int32_t* offset;    // [B+1] exclusive scan of count
@@ -70,16 +127,23 @@ struct Workspace {
     float4* rec_pos;    // [cap] (x,y,z normalised, w)
     int32_t* rec_ray;   // [cap] ray index
     int32_t* rec_idx;   // [cap] sample index within the ray
-    float* rec_rgb;     // [cap*4] per-record rgb (training: needed by the weight gradient)
-    float* g_w;         // [B*S] dL/dw_i (backward)
-    float* g_ray;       // [B*(3+C+2d+2)] per-ray upstream after the epilogue backward
+    // ---- training only (save_for_backward) ----
+    float* rec_rgb;     // [cap*4] per-record rgb (the weight gradient needs it)
+    float* sigma_dense; // [B*S]
+    float* trans_dense; // [B*S] transmittance T_i
+    float* g_w;         // [B*S] dL/dw_i through the rgb map (heads backward -> march backward)
+    float* g_ray;       // [B*(out_width+2)] per-ray upstream after the epilogue backward
+    float* stash_a;     // [tiles * a_rows * CLIFT_TILE]
+    float* stash_z;     // [tiles * z_rows * CLIFT_TILE]
     int64_t bytes;
 };
 
 static const int kScanBlock = 2048;
 
-inline Workspace carve_workspace(void* base, int64_t n_rays, int n_samples, int64_t cap, int out_width) {
+inline Workspace carve_workspace(void* base, int64_t n_rays, int n_samples, int64_t cap, int out_width, bool save,
+                                 const StashLayout* layout) {
     Workspace w;
+    memset(&w, 0, sizeof(w));
     char* p = (char*)base;
     int64_t off = 0;
     auto take = [&](int64_t bytes) {
@@ -87,17 +151,24 @@ inline Workspace carve_workspace(void* base, int64_t n_rays, int n_samples, int6
         off += round_up(bytes, 256);
         return r;
     };
+    const int64_t tiles = ceil_div(cap, CLIFT_TILE);
     w.stats = (int32_t*)take(16 * sizeof(int32_t));
     w.w_dense = (float*)take(n_rays * n_samples * sizeof(float));
     w.count = (int32_t*)take(n_rays * sizeof(int32_t));
     w.offset = (int32_t*)take((n_rays + 1) * sizeof(int32_t));
     w.bsum = (int32_t*)take((ceil_div(n_rays, kScanBlock) + 2) * sizeof(int32_t));
-    w.rec_pos = (float4*)take(cap * sizeof(float4));
-    w.rec_ray = (int32_t*)take(cap * sizeof(int32_t));
-    w.rec_idx = (int32_t*)take(cap * sizeof(int32_t));
-    w.rec_rgb = (float*)take(cap * 4 * sizeof(float));
-    w.g_w = (float*)take(n_rays * n_samples * sizeof(float));
-    w.g_ray = (float*)take(n_rays * (int64_t)(out_width + 8) * sizeof(float));
+    w.rec_pos = (float4*)take(tiles * CLIFT_TILE * sizeof(float4));
+    w.rec_ray = (int32_t*)take(tiles * CLIFT_TILE * sizeof(int32_t));
+    w.rec_idx = (int32_t*)take(tiles * CLIFT_TILE * sizeof(int32_t));
+    if (save) {
+        w.rec_rgb = (float*)take(tiles * CLIFT_TILE * 4 * sizeof(float));
+        w.sigma_dense = (float*)take(n_rays * n_samples * sizeof(float));
+        w.trans_dense = (float*)take(n_rays * n_samples * sizeof(float));
+        w.g_w = (float*)take(n_rays * n_samples * sizeof(float));
+        w.g_ray = (float*)take(n_rays * (int64_t)(out_width + 2) * sizeof(float));
+        w.stash_a = (float*)take(tiles * (int64_t)layout->a_rows * CLIFT_TILE * sizeof(float));
+        w.stash_z = (float*)take(tiles * (int64_t)layout->z_rows * CLIFT_TILE * sizeof(float));
+    }
     w.bytes = off;
     return w;
 }

@@ -41,6 +41,8 @@ struct HeadsParams {
     float* sem_raw;
     float* ins;
     float* rec_rgb;
+    float* stash_a;     // training: per-tile layer inputs (StashLayout), else null
+    StashLayout lay;
 };
 
 struct Smem {
@@ -131,9 +133,19 @@ __device__ __forceinline__ void run_layer(const Smem& sm, const float* wt, const
         mlp_layer<4>(sm, wt, bias, kp, relu);
 }
 
-__device__ __forceinline__ void run_mlp(const Smem& sm, const clift_mlp& mlp) {
-    for (int l = 0; l < mlp.n_layers; ++l)
+// rows [0,rows) of act -> global rows (coalesced: one row = kTile consecutive floats)
+__device__ __forceinline__ void store_rows(const Smem& sm, float* __restrict__ dst, int rows) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    const float4* s4 = reinterpret_cast<const float4*>(sm.act);
+    for (int i = threadIdx.x; i < rows * (kTile / 4); i += kThreads) d4[i] = s4[i];
+}
+
+// `stash` (may be null) = this tile's A-stash base; a_off = the MLP's row offsets: the INPUT of every layer is saved.
+__device__ __forceinline__ void run_mlp(const Smem& sm, const clift_mlp& mlp, float* stash = nullptr, const int* a_off = nullptr) {
+    for (int l = 0; l < mlp.n_layers; ++l) {
+        if (stash) store_rows(sm, stash + (size_t)a_off[l] * kTile, (mlp.dims[l] + 15) & ~15);
         run_layer(sm, mlp.wt[l], mlp.bias[l], mlp.dims[l], mlp.dims[l + 1], l + 1 < mlp.n_layers);
+    }
 }
 
 // rows [0,3) = xyz, then sin/cos positional encoding (dimension-major, frequency-minor), zero pad to 16.
@@ -274,12 +286,12 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
         __syncthreads();
         const int n_runs = s_nruns;
 
+        float* stash = P.stash_a ? P.stash_a + (size_t)tile * P.lay.a_rows * kTile : nullptr;
         if (P.heads & CLIFT_HEAD_SEMANTIC) {
             build_xyz_input(sm, P.pe_sem);
-            run_mlp(sm, P.sem);
-            if (tid < kTile) {
-                const float w = sm.pos[tid].w;
-                if (P.softmax) {
+            run_mlp(sm, P.sem, stash, P.lay.a_off[0]);
+            if (P.softmax) {
+                if (tid < kTile) {
                     float mx = -INFINITY;
                     for (int c = 0; c < P.n_cls; ++c) mx = fmaxf(mx, sm.act[(size_t)c * kTile + tid]);
                     float tot = 0.0f;
@@ -288,12 +300,15 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
                         sm.act[(size_t)c * kTile + tid] = e;
                         tot += e;
                     }
-                    const float sc = w / tot;
-                    for (int c = 0; c < P.n_cls; ++c) sm.act[(size_t)c * kTile + tid] *= sc;
-                } else {
-                    for (int c = 0; c < P.n_cls; ++c) sm.act[(size_t)c * kTile + tid] *= w;
+                    for (int c = 0; c < P.n_cls; ++c) sm.act[(size_t)c * kTile + tid] /= tot;
+                }
+                __syncthreads();
+                if (stash) {
+                    store_rows(sm, stash + (size_t)P.lay.prob_off * kTile, P.n_cls);
+                    __syncthreads();
                 }
             }
+            for (int idx = tid; idx < P.n_cls * kTile; idx += kThreads) sm.act[idx] *= sm.pos[idx % kTile].w;
             __syncthreads();
             reduce_runs(sm, n_runs, P.n_cls, P.sem_raw, P.n_cls, 0);
         }
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
             const int width = P.d_ins * (P.slow_fast ? 2 : 1);
             for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
                 build_xyz_input(sm, P.pe_ins);
-                run_mlp(sm, net == 0 ? P.insf : P.inss);
+                run_mlp(sm, net == 0 ? P.insf : P.inss, stash, P.lay.a_off[1 + net]);
                 for (int idx = tid; idx < P.d_ins * kTile; idx += kThreads) sm.act[idx] *= sm.pos[idx % kTile].w;
                 __syncthreads();
                 reduce_runs(sm, n_runs, P.d_ins, P.ins, width, net * P.d_ins);
@@ -309,9 +324,10 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
         }
         if (P.heads & CLIFT_HEAD_RGB) {
             gather_appearance<NV>(sm, P.app);
+            if (stash) store_rows(sm, stash + (size_t)P.lay.a_off[4][0] * kTile, 3 * P.app.comps);
             run_layer(sm, P.basis_wt, nullptr, 3 * P.app.comps, P.dim_app, false);
             build_rgb_input(sm, P.dim_app, P.pe_feat, P.pe_view);
-            run_mlp(sm, P.rgb);
+            run_mlp(sm, P.rgb, stash, P.lay.a_off[3]);
             for (int idx = tid; idx < 3 * kTile; idx += kThreads) {
                 const int m = idx % kTile;
                 const float c = 1.0f / (1.0f + expf(-sm.act[idx]));
@@ -324,10 +340,406 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
     }
 }
 
+
+// =================================================================================================
+// Backward of the heads (training).  Two kernel families:
+//   heads_backward_kernel : per tile, fused across layers - output gradient, softmax/sigmoid backward, data gradients
+//                           layer by layer with the dgrad-packed weights (same FFMA tile GEMM as the forward), ReLU
+//                           masks from the A-stash, bias gradients, dL/dw through rgb, positional-encoding backward and
+//                           the scatter of the appearance-factor gradients.  Every layer's dZ goes to the Z-stash.
+//   wgrad_kernel          : per layer, dW^T[k][n] += sum over records A[k][m] * dZ[n][m]  (split over tiles).
+// =================================================================================================
+struct HeadsBwdParams {
+    const float4* rec_pos;
+    const int32_t* rec_ray;
+    const int32_t* rec_idx;
+    const float* rec_rgb;
+    const unsigned long long* stats;
+    long long cap;
+    int S;
+    FactorParams app;
+    float* g_app_plane[3];
+    float* g_app_line[3];
+    const float* basis_dgrad;
+    int dim_app, pe_view, pe_feat;
+    clift_mlp rgb, sem, insf, inss;
+    clift_mlp_grad g_rgb_mlp, g_sem_mlp, g_insf_mlp, g_inss_mlp;
+    int n_cls, d_ins, slow_fast, softmax;
+    int do_rgb, do_sem, do_ins;
+    const float* g_ray;      // [B][ray_stride]: g_rgb_raw(3) | g_sem_raw(C) | g_ins(DI) | g_opacity
+    int ray_stride, off_sem, off_ins;
+    float* g_w;              // [B*S]
+    const float* stash_a;
+    float* stash_z;
+    StashLayout lay;
+};
+
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// rows [0, rows_pad) of act -> Z-stash; rows [0, n_out) summed over the tile into the bias gradient.
+__device__ __forceinline__ void emit_dz(const Smem& sm, float* __restrict__ zdst, int rows_pad, int n_out, float* __restrict__ g_bias) {
+    store_rows(sm, zdst, rows_pad);
+    if (g_bias) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int r = warp; r < n_out; r += kThreads / 32) {
+            const float4 v = *reinterpret_cast<const float4*>(sm.act + (size_t)r * kTile + lane * 4);
+            const float s = warp_sum((v.x + v.y) + (v.z + v.w));
+            if (lane == 0) atomicAdd(g_bias + r, s);
+        }
+    }
+}
+
+// dA[k][m] = sum_n W[n][k] dZ[n][m] with the clift_pack_linear_dgrad() operand ([up16(out)][dgrad_pad(in)])
+__device__ __forceinline__ void run_dgrad(const Smem& sm, const float* w_dgrad, int n_out, int n_in) {
+    const int np = n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256);
+    const int kp = (n_out + 15) & ~15;
+    if (np == 64)
+        mlp_layer<1>(sm, w_dgrad, nullptr, kp, false);
+    else if (np == 128)
+        mlp_layer<2>(sm, w_dgrad, nullptr, kp, false);
+    else
+        mlp_layer<4>(sm, w_dgrad, nullptr, kp, false);
+}
+
+// act rows [0, n_pad(out)) hold dZ of the LAST layer (pad rows zero).  Walks the stack backwards.
+// On return (need_input_grad) act rows [0, dgrad_pad(dims[0])) hold dL/d(input of layer 0).
+__device__ __forceinline__ void mlp_backward(const Smem& sm, const clift_mlp& mlp, const clift_mlp_grad& g, const float* stash_a,
+                                             float* stash_z, const int* a_off, const int* z_off, bool need_input_grad) {
+    for (int l = mlp.n_layers - 1; l >= 0; --l) {
+        const int n_out = mlp.dims[l + 1], n_in = mlp.dims[l];
+        emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
+        if (l == 0 && !need_input_grad) break;
+        run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
+        if (l > 0) {   // ReLU mask from the saved input of layer l (= post-ReLU output of layer l-1)
+            const float4* a4 = reinterpret_cast<const float4*>(stash_a + (size_t)a_off[l] * kTile);
+            float4* d4 = reinterpret_cast<float4*>(sm.act);
+            const int rows = (n_in + 15) & ~15;
+            for (int i = threadIdx.x; i < rows * (kTile / 4); i += kThreads) {
+                const float4 a = a4[i];
+                float4 d = d4[i];
+                d.x = a.x > 0.0f ? d.x : 0.0f;
+                d.y = a.y > 0.0f ? d.y : 0.0f;
+                d.z = a.z > 0.0f ? d.z : 0.0f;
+                d.w = a.w > 0.0f ? d.w : 0.0f;
+                d4[i] = d;
+            }
+            // rows [rows, n_pad(n_in)) are zero already (dgrad weights are zero padded)
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void scatter_appearance(const Smem& sm, const HeadsBwdParams& P, int nv) {
+    const FactorParams& f = P.app;
+    const int q = threadIdx.x & 3;
+#pragma unroll 1
+    for (int pass = 0; pass < kTile / 64; ++pass) {
+        const int m = pass * 64 + (threadIdx.x >> 2);
+        if (m >= nv) continue;
+        const float4 p = sm.pos[m];
+        const float xs[3] = {p.x, p.y, p.z};
+#pragma unroll
+        for (int mode = 0; mode < 3; ++mode) {
+            const int W = f.pw[mode];
+            const Tap2 t2 = make_tap2(xs[mode_a(mode)], xs[mode_b(mode)], W, f.ph[mode]);
+            const Tap1 t1 = make_tap1(xs[mode_v(mode)], f.ll[mode]);
+            const int64_t row0 = (int64_t)t2.y0 * W, row1 = row0 + W;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const int ch = v * 16 + q * 4;
+                const float4 pv = plane_tap(f.plane[mode], t2, W, f.comps, ch);
+                const float4 lv = line_tap(f.line[mode], t1, f.comps, ch);
+                const float* g = sm.act + (size_t)(mode * f.comps + ch) * kTile + m;
+                const float g0 = g[0], g1 = g[kTile], g2 = g[2 * kTile], g3 = g[3 * kTile];
+                // d plane = g * L * bilinear weight ; d line = g * P * linear weight
+                const float a0 = g0 * lv.x, a1 = g1 * lv.y, a2 = g2 * lv.z, a3 = g3 * lv.w;
+                float* gp = P.g_app_plane[mode];
+                if (t2.w00 != 0.0f) red_add4(gp + (row0 + t2.x0) * f.comps + ch, a0 * t2.w00, a1 * t2.w00, a2 * t2.w00, a3 * t2.w00);
+                if (t2.w10 != 0.0f) red_add4(gp + (row0 + t2.x0 + 1) * f.comps + ch, a0 * t2.w10, a1 * t2.w10, a2 * t2.w10, a3 * t2.w10);
+                if (t2.w01 != 0.0f) red_add4(gp + (row1 + t2.x0) * f.comps + ch, a0 * t2.w01, a1 * t2.w01, a2 * t2.w01, a3 * t2.w01);
+                if (t2.w11 != 0.0f) red_add4(gp + (row1 + t2.x0 + 1) * f.comps + ch, a0 * t2.w11, a1 * t2.w11, a2 * t2.w11, a3 * t2.w11);
+                const float b0 = g0 * pv.x, b1 = g1 * pv.y, b2 = g2 * pv.z, b3 = g3 * pv.w;
+                float* gl = P.g_app_line[mode];
+                if (t1.w0 != 0.0f) red_add4(gl + (int64_t)t1.z0 * f.comps + ch, b0 * t1.w0, b1 * t1.w0, b2 * t1.w0, b3 * t1.w0);
+                if (t1.w1 != 0.0f) red_add4(gl + (int64_t)(t1.z0 + 1) * f.comps + ch, b0 * t1.w1, b1 * t1.w1, b2 * t1.w1, b3 * t1.w1);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __grid_constant__ HeadsBwdParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem sm;
+    sm.act = reinterpret_cast<float*>(smem_raw);
+    sm.wslab = sm.act + kActRows * kTile;
+    sm.pos = reinterpret_cast<float4*>(sm.wslab + 2 * kSlabRows * 256);
+    sm.ray = reinterpret_cast<int*>(sm.pos + kTile);
+    sm.runs = sm.ray + kTile;
+    sm.dir = reinterpret_cast<float*>(sm.runs + kTile + 4);   // here: [3][kTile] saved rgb of the records
+
+    const long long n_act = min((long long)P.stats[0], P.cap);
+    const long long n_tiles = (n_act + kTile - 1) / kTile;
+    const int tid = threadIdx.x;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long base = tile * kTile;
+        const int nv = (int)min((long long)kTile, n_act - base);
+        __syncthreads();
+        if (tid < kTile) {
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            int ray = -1;
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+            if (tid < nv) {
+                p = P.rec_pos[base + tid];
+                ray = P.rec_ray[base + tid];
+                if (P.do_rgb) {
+                    const float4 c = *reinterpret_cast<const float4*>(P.rec_rgb + (base + tid) * 4);
+                    c0 = c.x, c1 = c.y, c2 = c.z;
+                }
+            }
+            sm.pos[tid] = p;
+            sm.ray[tid] = ray;
+            sm.dir[tid] = c0;
+            sm.dir[kTile + tid] = c1;
+            sm.dir[2 * kTile + tid] = c2;
+        }
+        __syncthreads();
+        const float* sa = P.stash_a + (size_t)tile * P.lay.a_rows * kTile;
+        float* sz = P.stash_z + (size_t)tile * P.lay.z_rows * kTile;
+
+        if (P.do_sem) {
+            // dOut_c = w * g_sem_raw[ray][c]; softmax backward with the saved probabilities
+            const int rows = (P.n_cls + 63) & ~63;
+            if (tid < kTile) {
+                const int ray = sm.ray[tid];
+                const float w = sm.pos[tid].w;
+                const float* g = P.g_ray + (int64_t)max(ray, 0) * P.ray_stride + P.off_sem;
+                if (P.softmax) {
+                    const float* pr = sa + (size_t)P.lay.prob_off * kTile + tid;
+                    float dot = 0.0f;
+                    for (int c = 0; c < P.n_cls; ++c) dot += (ray >= 0 ? w * g[c] : 0.0f) * pr[(size_t)c * kTile];
+                    for (int c = 0; c < P.n_cls; ++c) {
+                        const float d = ray >= 0 ? w * g[c] : 0.0f;
+                        sm.act[(size_t)c * kTile + tid] = pr[(size_t)c * kTile] * (d - dot);
+                    }
+                } else {
+                    for (int c = 0; c < P.n_cls; ++c) sm.act[(size_t)c * kTile + tid] = ray >= 0 ? w * g[c] : 0.0f;
+                }
+                for (int c = P.n_cls; c < rows; ++c) sm.act[(size_t)c * kTile + tid] = 0.0f;
+            }
+            __syncthreads();
+            mlp_backward(sm, P.sem, P.g_sem_mlp, sa, sz, P.lay.a_off[0], P.lay.z_off[0], false);
+        }
+        if (P.do_ins) {
+            for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
+                const int rows = (P.d_ins + 63) & ~63;
+                if (tid < kTile) {
+                    const int ray = sm.ray[tid];
+                    const float w = sm.pos[tid].w;
+                    const float* g = P.g_ray + (int64_t)max(ray, 0) * P.ray_stride + P.off_ins + net * P.d_ins;
+                    for (int c = 0; c < P.d_ins; ++c) sm.act[(size_t)c * kTile + tid] = ray >= 0 ? w * g[c] : 0.0f;
+                    for (int c = P.d_ins; c < rows; ++c) sm.act[(size_t)c * kTile + tid] = 0.0f;
+                }
+                __syncthreads();
+                mlp_backward(sm, net == 0 ? P.insf : P.inss, net == 0 ? P.g_insf_mlp : P.g_inss_mlp, sa, sz,
+                             P.lay.a_off[1 + net], P.lay.z_off[1 + net], false);
+            }
+        }
+        if (P.do_rgb) {
+            if (tid < kTile) {
+                const int ray = sm.ray[tid];
+                const float w = sm.pos[tid].w;
+                const float* g = P.g_ray + (int64_t)max(ray, 0) * P.ray_stride;
+                float gw = 0.0f;
+                for (int k = 0; k < 3; ++k) {
+                    const float c = sm.dir[k * kTile + tid];
+                    const float gk = ray >= 0 ? g[k] : 0.0f;
+                    gw += gk * c;
+                    sm.act[(size_t)k * kTile + tid] = w * gk * c * (1.0f - c);   // through the sigmoid
+                }
+                for (int c = 3; c < 64; ++c) sm.act[(size_t)c * kTile + tid] = 0.0f;
+                if (ray >= 0) P.g_w[(int64_t)ray * P.S + P.rec_idx[base + tid]] = gw;
+            }
+            __syncthreads();
+            mlp_backward(sm, P.rgb, P.g_rgb_mlp, sa, sz, P.lay.a_off[3], P.lay.z_off[3], true);
+            // positional-encoding backward: dfeat_a = dIn[a] + sum_j 2^j (cos_aj * dIn[sin_aj] - sin_aj * dIn[cos_aj])
+            const int A = P.dim_app, pf = P.pe_feat;
+            const int o_sf = A + 3, o_cf = o_sf + A * pf;
+            const float* in = sa + (size_t)P.lay.a_off[3][0] * kTile;
+            // dfeat goes to the spare rows [192, 192+A) first (the MLP input occupies rows < 192), then down to [0, A)
+            float* spare = sm.act + (size_t)192 * kTile;
+            for (int idx = tid; idx < A * kTile; idx += kThreads) {
+                const int a = idx / kTile, m = idx - a * kTile;
+                float v = sm.act[(size_t)a * kTile + m];
+                for (int j = 0; j < pf; ++j) {
+                    const int rs = o_sf + a * pf + j, rc = o_cf + a * pf + j;
+                    const float sv = in[(size_t)rs * kTile + m], cv = in[(size_t)rc * kTile + m];
+                    v += (float)(1 << j) * (cv * sm.act[(size_t)rs * kTile + m] - sv * sm.act[(size_t)rc * kTile + m]);
+                }
+                spare[idx] = v;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < 64 * kTile; idx += kThreads) sm.act[idx] = idx < A * kTile ? spare[idx] : 0.0f;
+            __syncthreads();
+            // basis layer: dZ = dfeat (64 rows, zero padded) -> Z-stash, then dprod = basis^T dfeat
+            store_rows(sm, sz + (size_t)P.lay.z_off[4][0] * kTile, 64);
+            run_dgrad(sm, P.basis_dgrad, A, 3 * P.app.comps);
+            scatter_appearance<NV>(sm, P, nv);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// wgrad: dWt[k][n] += sum_tiles sum_m A[t][k][m] * Z[t][n][m].   64x64 output block per CTA, 4x4 per thread,
+// record dimension streamed in 32-wide slabs through a cp.async double buffer (row stride 36: 16 B aligned, conflict-free).
+// -------------------------------------------------------------------------------------------------
+struct WgradParams {
+    const float* a;      // stash_a + a_off*kTile
+    const float* z;      // stash_z + z_off*kTile
+    long long a_tile_stride, z_tile_stride;   // floats
+    int K, N;            // valid rows (k_pad(in), n_pad(out)); output pitch = N
+    float* out;          // packed dWt [K][N]
+    const unsigned long long* stats;
+    long long cap;
+    int splits;
+};
+
+constexpr int kWgSlab = 32;
+constexpr int kWgPitch = kWgSlab + 4;
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ WgradParams P) {
+    __shared__ __align__(16) float sA[2][64 * kWgPitch];
+    __shared__ __align__(16) float sZ[2][64 * kWgPitch];
+    const long long n_act = min((long long)P.stats[0], P.cap);
+    const long long n_tiles = (n_act + kTile - 1) / kTile;
+    const int kb = blockIdx.x * 64, nb = blockIdx.y * 64, split = blockIdx.z;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    const long long n_slabs = ((n_tiles - split + P.splits - 1) / P.splits) * (kTile / kWgSlab);   // slabs this CTA walks
+    auto issue = [&](long long s) {
+        const long long tile = split + (s / (kTile / kWgSlab)) * P.splits;
+        const int m0 = (int)(s % (kTile / kWgSlab)) * kWgSlab;
+        const int buf = (int)(s & 1);
+        const float* ga = P.a + tile * P.a_tile_stride + m0;
+        const float* gz = P.z + tile * P.z_tile_stride + m0;
+        // 64 rows x 8 chunks of 16 B per operand = 512 chunks; 256 threads -> 2 each per operand
+        for (int c = tid; c < 64 * (kWgSlab / 4); c += 256) {
+            const int r = c / (kWgSlab / 4), q = c % (kWgSlab / 4);
+            if (kb + r < P.K) cp_async16(&sA[buf][r * kWgPitch + q * 4], ga + (size_t)(kb + r) * kTile + q * 4);
+            if (nb + r < P.N) cp_async16(&sZ[buf][r * kWgPitch + q * 4], gz + (size_t)(nb + r) * kTile + q * 4);
+        }
+        cp_async_commit();
+    };
+    // rows beyond K / N are never loaded: zero them once so they contribute nothing
+    for (int i = tid; i < 2 * 64 * kWgPitch; i += 256) {
+        (&sA[0][0])[i] = 0.0f;
+        (&sZ[0][0])[i] = 0.0f;
+    }
+    __syncthreads();
+    if (n_slabs > 0) issue(0);
+    for (long long s = 0; s < n_slabs; ++s) {
+        if (s + 1 < n_slabs) {
+            issue(s + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float* a = sA[s & 1];
+        const float* z = sZ[s & 1];
+#pragma unroll
+        for (int mm = 0; mm < kWgSlab; mm += 4) {
+            float4 av[4], zv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const float4*>(a + (ty + 16 * i) * kWgPitch + mm);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) zv[j] = *reinterpret_cast<const float4*>(z + (tx + 16 * j) * kWgPitch + mm);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    acc[i][j] = fmaf(av[i].x, zv[j].x, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].y, zv[j].y, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].z, zv[j].z, acc[i][j]);
+                    acc[i][j] = fmaf(av[i].w, zv[j].w, acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = kb + ty + 16 * i, n = nb + tx + 16 * j;
+            if (k < P.K && n < P.N && acc[i][j] != 0.0f) atomicAdd(P.out + (size_t)k * P.N + n, acc[i][j]);
+        }
+}
+
+// -------------------------------------------------------------------------------------------------
+// per-ray epilogue backward (renderer:160-167): g_rgb -> g_rgb_raw (+ g_opacity), g_sem -> g_sem_raw, g_ins copy
+// -------------------------------------------------------------------------------------------------
+struct RayBwdParams {
+    int64_t n_rays;
+    int n_cls, d_all, softmax, add_bg, stride, off_sem, off_ins;
+    const float* opacity;
+    const float* rgb_raw;
+    const float* sem_raw;
+    const float* g_rgb;
+    const float* g_sem;
+    const float* g_ins;
+    float* g_ray;
+};
+
+__global__ void __launch_bounds__(256) ray_backward_kernel(const __grid_constant__ RayBwdParams P) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= P.n_rays) return;
+    float* o = P.g_ray + r * P.stride;
+    float g_opa = 0.0f;
+    for (int k = 0; k < 3; ++k) {
+        float g = 0.0f;
+        if (P.g_rgb) {
+            float v = P.rgb_raw[r * 3 + k];
+            if (P.add_bg) v = v + (1.0f - P.opacity[r]);
+            g = (v >= 0.0f && v <= 1.0f) ? P.g_rgb[r * 3 + k] : 0.0f;   // clamp passes gradient on the closed interval
+            if (P.add_bg) g_opa -= g;
+        }
+        o[k] = g;
+    }
+    o[P.stride - 1] = g_opa;
+    if (P.g_sem) {
+        const float* s = P.sem_raw + r * P.n_cls;
+        const float* g = P.g_sem + r * P.n_cls;
+        if (P.softmax) {
+            float tot = 0.0f;
+            for (int c = 0; c < P.n_cls; ++c) tot += s[c];
+            tot += 1e-8f;
+            float dot = 0.0f;   // sum_j (dL/dp_j) * s_j
+            for (int c = 0; c < P.n_cls; ++c) dot += g[c] / (s[c] / tot + 1e-8f) * s[c];
+            for (int c = 0; c < P.n_cls; ++c) o[P.off_sem + c] = g[c] / (s[c] / tot + 1e-8f) / tot - dot / (tot * tot);
+        } else {
+            for (int c = 0; c < P.n_cls; ++c) o[P.off_sem + c] = g[c];
+        }
+    } else {
+        for (int c = 0; c < P.n_cls; ++c) o[P.off_sem + c] = 0.0f;
+    }
+    for (int c = 0; c < P.d_all; ++c) o[P.off_ins + c] = P.g_ins ? P.g_ins[r * P.d_all + c] : 0.0f;
+}
+
 }  // namespace
 
 int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
-                         int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, bool save_rgb,
+                         int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, const StashLayout* lay,
                          cudaStream_t stream) {
     HeadsParams P;
     P.rec_pos = ws.rec_pos;
@@ -357,7 +769,9 @@ int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, 
     P.rgb_raw = rgb_raw;
     P.sem_raw = sem_raw;
     P.ins = ins;
-    P.rec_rgb = save_rgb ? ws.rec_rgb : nullptr;
+    P.rec_rgb = lay ? ws.rec_rgb : nullptr;
+    P.stash_a = lay ? ws.stash_a : nullptr;
+    if (lay) P.lay = *lay;
     if (P.heads == 0 || n_rays <= 0) return CLIFT_OK;
     const int grid = sm_count();
 #define CLIFT_HEADS_CASE(NV)                                                                                          \
@@ -378,6 +792,171 @@ int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, 
     }
 #undef CLIFT_HEADS_CASE
     CLIFT_AFTER_LAUNCH("heads_forward_kernel");
+    return CLIFT_OK;
+}
+
+}  // namespace clift
+
+namespace clift {
+
+static int launch_wgrad(const Workspace& ws, const StashLayout& lay, int id, int l, const clift_mlp* m, float* out, int64_t cap,
+                        cudaStream_t stream) {
+    if (!out) return CLIFT_OK;
+    WgradParams W;
+    W.a = ws.stash_a + (size_t)lay.a_off[id][l] * kTile;
+    W.z = ws.stash_z + (size_t)lay.z_off[id][l] * kTile;
+    W.a_tile_stride = (long long)lay.a_rows * kTile;
+    W.z_tile_stride = (long long)lay.z_rows * kTile;
+    W.K = k_pad(m->dims[l]);
+    W.N = n_pad(m->dims[l + 1]);
+    W.out = out;
+    W.stats = reinterpret_cast<const unsigned long long*>(ws.stats);
+    W.cap = cap;
+    const int bk = (int)ceil_div(W.K, 64), bn = (int)ceil_div(W.N, 64);
+    W.splits = std::max(1, (2 * sm_count()) / (bk * bn));
+    dim3 grid(bk, bn, W.splits);
+    wgrad_kernel<<<grid, 256, 0, stream>>>(W);
+    CLIFT_AFTER_LAUNCH("wgrad_kernel");
+    return CLIFT_OK;
+}
+
+// Per-ray epilogue backward -> heads backward (dgrad, stash dZ, bias grads, dL/dw, appearance scatter) -> wgrad per layer.
+int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field, const Workspace& ws, const StashLayout& lay,
+                          int64_t cap, int64_t n_rays, int add_bg, const clift_render_out* saved, const float* g_rgb,
+                          const float* g_sem, const float* g_ins, const clift_field_grad* grad, int* ray_stride_out,
+                          cudaStream_t stream) {
+    const int C = field->num_classes, DI = field->dim_instance * (field->slow_fast ? 2 : 1);
+    const int stride = 3 + C + DI + 1;
+    *ray_stride_out = stride;
+    const int heads = cfg->heads;
+    const bool do_rgb = (heads & CLIFT_HEAD_RGB) && g_rgb;
+    const bool do_sem = (heads & CLIFT_HEAD_SEMANTIC) && g_sem && grad->semantic.wt[0];
+    const bool do_ins = (heads & CLIFT_HEAD_INSTANCE) && g_ins && grad->instance_fast.wt[0];
+    {
+        RayBwdParams R;
+        R.n_rays = n_rays;
+        R.n_cls = C;
+        R.d_all = DI;
+        R.softmax = cfg->semantic_softmax;
+        R.add_bg = add_bg;
+        R.stride = stride;
+        R.off_sem = 3;
+        R.off_ins = 3 + C;
+        R.opacity = saved->opacity;
+        R.rgb_raw = saved->rgb_raw;
+        R.sem_raw = saved->semantic_raw;
+        R.g_rgb = do_rgb ? g_rgb : nullptr;
+        R.g_sem = do_sem ? g_sem : nullptr;
+        R.g_ins = do_ins ? g_ins : nullptr;
+        R.g_ray = ws.g_ray;
+        ray_backward_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, stream>>>(R);
+        CLIFT_AFTER_LAUNCH("ray_backward_kernel");
+    }
+    if (!(do_rgb || do_sem || do_ins)) return CLIFT_OK;
+    HeadsBwdParams P;
+    memset(&P, 0, sizeof(P));
+    P.rec_pos = ws.rec_pos;
+    P.rec_ray = ws.rec_ray;
+    P.rec_idx = ws.rec_idx;
+    P.rec_rgb = ws.rec_rgb;
+    P.stats = reinterpret_cast<const unsigned long long*>(ws.stats);
+    P.cap = cap;
+    P.S = cfg->n_samples;
+    P.app = make_factors(field, true);
+    for (int m = 0; m < 3; ++m) {
+        P.g_app_plane[m] = grad->appearance_plane[m];
+        P.g_app_line[m] = grad->appearance_line[m];
+    }
+    P.basis_dgrad = field->basis_dgrad;
+    P.dim_app = field->dim_appearance;
+    P.pe_view = field->pe_view;
+    P.pe_feat = field->pe_feat;
+    P.rgb = field->rgb;
+    P.sem = field->semantic;
+    P.insf = field->instance_fast;
+    P.inss = field->instance_slow;
+    P.g_rgb_mlp = grad->rgb;
+    P.g_sem_mlp = grad->semantic;
+    P.g_insf_mlp = grad->instance_fast;
+    P.g_inss_mlp = grad->instance_slow;
+    P.n_cls = C;
+    P.d_ins = field->dim_instance;
+    P.slow_fast = field->slow_fast;
+    P.softmax = cfg->semantic_softmax;
+    P.do_rgb = do_rgb;
+    P.do_sem = do_sem;
+    P.do_ins = do_ins;
+    P.g_ray = ws.g_ray;
+    P.ray_stride = stride;
+    P.off_sem = 3;
+    P.off_ins = 3 + C;
+    P.g_w = ws.g_w;
+    P.stash_a = ws.stash_a;
+    P.stash_z = ws.stash_z;
+    P.lay = lay;
+    if (do_rgb) {
+        for (int m = 0; m < 3; ++m)
+            if (!P.g_app_plane[m] || !P.g_app_line[m]) {
+                set_error("clift_render_backward: rgb gradient requested without appearance factor gradient buffers");
+                return CLIFT_ERR_ARG;
+            }
+        if (!field->basis_dgrad || !grad->basis) {
+            set_error("clift_render_backward: rgb gradient requested without basis dgrad operand / gradient buffer");
+            return CLIFT_ERR_ARG;
+        }
+        if (k_pad(field->rgb.dims[0]) > 192 || field->dim_appearance > 64) {
+            set_error("clift_render_backward: rgb head input wider than 192 is not supported in training");
+            return CLIFT_ERR_UNSUPPORTED;
+        }
+        CLIFT_CUDA(cudaMemsetAsync(ws.g_w, 0, n_rays * (int64_t)cfg->n_samples * sizeof(float), stream));
+    }
+    auto need_dgrad = [&](const clift_mlp& m, bool from0) {
+        for (int l = from0 ? 0 : 1; l < m.n_layers; ++l)
+            if (!m.w_dgrad[l]) return false;
+        return true;
+    };
+    if ((do_rgb && !need_dgrad(field->rgb, true)) || (do_sem && !need_dgrad(field->semantic, false)) ||
+        (do_ins && (!need_dgrad(field->instance_fast, false) || (field->slow_fast && !need_dgrad(field->instance_slow, false))))) {
+        set_error("clift_render_backward: field lacks the w_dgrad operands (pack with clift_pack_linear_dgrad)");
+        return CLIFT_ERR_ARG;
+    }
+    const int grid = sm_count();
+#define CLIFT_HEADS_BWD_CASE(NV)                                                                                       \
+    case NV: {                                                                                                         \
+        CLIFT_CUDA(cudaFuncSetAttribute(heads_backward_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                        (int)kSmemBytes));                                                             \
+        heads_backward_kernel<NV><<<grid, kThreads, kSmemBytes, stream>>>(P);                                          \
+        break;                                                                                                         \
+    }
+    switch (P.app.comps / 16) {
+        CLIFT_HEADS_BWD_CASE(1)
+        CLIFT_HEADS_BWD_CASE(2)
+        CLIFT_HEADS_BWD_CASE(3)
+        CLIFT_HEADS_BWD_CASE(4)
+        default:
+            set_error("launch_heads_backward: appearance_comps %d not in {16,32,48,64}", P.app.comps);
+            return CLIFT_ERR_UNSUPPORTED;
+    }
+#undef CLIFT_HEADS_BWD_CASE
+    CLIFT_AFTER_LAUNCH("heads_backward_kernel");
+    // weight gradients, one split-K GEMM per layer
+    int rc;
+    clift_mlp tmp;
+    if (do_sem)
+        for (int l = 0; l < field->semantic.n_layers; ++l)
+            if ((rc = launch_wgrad(ws, lay, 0, l, &field->semantic, grad->semantic.wt[l], cap, stream))) return rc;
+    if (do_ins) {
+        for (int l = 0; l < field->instance_fast.n_layers; ++l)
+            if ((rc = launch_wgrad(ws, lay, 1, l, &field->instance_fast, grad->instance_fast.wt[l], cap, stream))) return rc;
+        if (field->slow_fast)
+            for (int l = 0; l < field->instance_slow.n_layers; ++l)
+                if ((rc = launch_wgrad(ws, lay, 2, l, &field->instance_slow, grad->instance_slow.wt[l], cap, stream))) return rc;
+    }
+    if (do_rgb) {
+        for (int l = 0; l < field->rgb.n_layers; ++l)
+            if ((rc = launch_wgrad(ws, lay, 3, l, &field->rgb, grad->rgb.wt[l], cap, stream))) return rc;
+        if ((rc = launch_wgrad(ws, lay, 4, 0, field_mlp(field, 4, &tmp), grad->basis, cap, stream))) return rc;
+    }
     return CLIFT_OK;
 }
 

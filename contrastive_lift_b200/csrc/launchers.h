@@ -20,8 +20,16 @@ int launch_density(const clift_field* field, const float* xyz, int64_t n, float*
 
 // heads.cu
 int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
-                         int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, bool save_rgb,
+                         int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, const StashLayout* lay,
                          cudaStream_t stream);
+
+int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field, const Workspace& ws, const StashLayout& lay,
+                          int64_t cap, int64_t n_rays, int add_bg, const clift_render_out* saved, const float* g_rgb,
+                          const float* g_sem, const float* g_ins, const clift_field_grad* grad, int* ray_stride_out,
+                          cudaStream_t stream);
+int launch_march_backward(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const float* jitter,
+                          int64_t n_rays, const Workspace& ws, int ray_stride, const float* g_dist, bool have_g_w,
+                          const clift_field_grad* grad, cudaStream_t stream);
 
 // pack.cu
 int launch_transpose(const float* src, float* dst, int rows, int cols, int dst_rows_pad, int dst_cols_pad, cudaStream_t stream);

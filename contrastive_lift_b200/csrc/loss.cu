@@ -294,12 +294,12 @@ extern "C" int32_t clift_contrastive_loss(const float* features, const int64_t* 
     return CLIFT_OK;
 }
 
-extern "C" int32_t clift_ema_update(float* slow, const float* fast, int64_t n, float momentum, void* stream) {
+extern "C" int32_t clift_ema_update(float* slow, const float* fast, int64_t n, double momentum, void* stream) {
     CLIFT_CHECK_ARG(slow && fast && n >= 0, "null pointer or bad size");
     if (n == 0) return CLIFT_OK;
     // the reference scales by the Python double (1 - momentum) rounded to fp32 when it meets the tensor
-    const float om = (float)(1.0 - (double)momentum);
-    ema_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(slow, fast, n, momentum, om);
+    const float om = (float)(1.0 - momentum);
+    ema_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(slow, fast, n, (float)momentum, om);
     CLIFT_AFTER_LAUNCH("ema_kernel");
     return CLIFT_OK;
 }

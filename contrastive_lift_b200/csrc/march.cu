@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
             float x[3];
             const bool in = sample_point(g, t, G.amin, G.amax, G.inv, x) && valid;
             const unsigned inm = __ballot_sync(0xffffffffu, in);
-            float w = 0.0f;
+            float w = 0.0f, sigma_out = 0.0f, trans_out = T_run;
             if (inm != 0u) {
                 n_in += __popc(inm);
                 float feat = 0.0f;
@@ -114,7 +114,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
                 }
                 float ex = __shfl_up_sync(0xffffffffu, pr, 1);
                 if (lane == 0) ex = 1.0f;
-                w = alpha * (T_run * ex);
+                trans_out = T_run * ex;
+                sigma_out = sigma;
+                w = alpha * trans_out;
                 T_run *= __shfl_sync(0xffffffffu, pr, 31);
                 const float mid = (i < S - 1) ? __fmul_rn(__fadd_rn(tn, t), 0.5f) : sample_t(g, G.step, S - 2);
                 // exclusive prefix sums of w and w*mid for the distortion loss
@@ -138,7 +140,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
                 dep += w * t;
                 n_act += __popc(__ballot_sync(0xffffffffu, w > G.thres));
             }
-            if (valid) wrow[i] = w;
+            if (valid) {
+                wrow[i] = w;
+                if (P.sigma_dense) {
+                    P.sigma_dense[ray * S + i] = sigma_out;
+                    P.trans_dense[ray * S + i] = trans_out;
+                }
+            }
         }
         opa = warp_sum(opa);
         dep = warp_sum(dep);
@@ -406,6 +414,164 @@ __global__ void __launch_bounds__(256) density_kernel(const __grid_constant__ Fa
     if (s < n && q == 0) sigma[s] = softplus_f(acc + shift);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Backward of the march (renderer:97-101,137,164 through raw_to_alpha, softplus and the VM lookup).
+// One warp per ray, samples walked from the far end in chunks of 32 so that the suffix sums
+//   S_i = sum_{j>i} w_j g_j   (compositing)      W_{>i}, WM_{>i}   (distortion loss)
+// are running carries.  sigma_i and T_i come from the forward's dense buffers (bit-identical alpha, w).
+//   g_i      = dL/dw_i = g_opacity + g_w_rgb[i] + gD/B * (2/3 w_i d_i + 2 (m_i W_<i - WM_<i + WM_>i - m_i W_>i))
+//   dL/da_i  = T_i g_i - S_i / (1 - a_i + 1e-10)
+//   dL/dsig  = dL/da_i * d_i * scale * (1 - a_i),   dL/dfeat = dL/dsig * (1 - exp(-sigma_i))   [softplus' = sigmoid]
+// and dL/dfeat is scattered to the 18 taps x comps of the density factors with 16-byte vector reductions.
+// ---------------------------------------------------------------------------------------
+struct MarchBwdParams {
+    GeomParams g;
+    FactorParams f;
+    const float* rays;
+    const float* jitter;
+    int64_t n_rays;
+    const float* sigma_dense;
+    const float* trans_dense;
+    const float* g_w;        // [B,S] or null
+    const float* g_ray;      // [B][stride], g_opacity at [stride-1]
+    int ray_stride;
+    const float* g_dist;     // device scalar or null
+    float* g_plane[3];
+    float* g_line[3];
+};
+
+__device__ __forceinline__ void red_add4f(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float suffix_inclusive(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_down_sync(0xffffffffu, v, o);
+        if (lane + o < 32) v += t;
+    }
+    return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) march_backward_kernel(const __grid_constant__ MarchBwdParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const GeomParams& G = P.g;
+    const FactorParams& F = P.f;
+    const int S = G.S;
+    const int n_chunks = (S + 31) >> 5;
+    const int q = lane & 3;
+    const float gD = P.g_dist ? __ldg(P.g_dist) / (float)P.n_rays : 0.0f;
+
+    for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerCta + warp; ray < P.n_rays; ray += (int64_t)gridDim.x * kWarpsPerCta) {
+        const float rv = lane < 8 ? __ldg(P.rays + ray * 8 + lane) : 0.0f;
+        RayGeom g;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            g.o[k] = __shfl_sync(0xffffffffu, rv, k);
+            g.d[k] = __shfl_sync(0xffffffffu, rv, 3 + k);
+        }
+        g.t_min = ray_t_min(g.o, g.d, __shfl_sync(0xffffffffu, rv, 6), __shfl_sync(0xffffffffu, rv, 7), G.amin, G.amax);
+        g.has_jit = P.jitter != nullptr;
+        g.jit = g.has_jit ? __ldg(P.jitter + ray) : 0.0f;
+        const float g_opa = __ldg(P.g_ray + ray * P.ray_stride + P.ray_stride - 1);
+        const float* srow = P.sigma_dense + ray * S;
+        const float* trow = P.trans_dense + ray * S;
+        const float* gwrow = P.g_w ? P.g_w + ray * S : nullptr;
+
+        float W_tot = 0.0f, WM_tot = 0.0f;
+        if (gD != 0.0f) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int i = c * 32 + lane;
+                if (i < S) {
+                    const float t = sample_t(g, G.step, i), tn = sample_t(g, G.step, i + 1);
+                    const float delta = (i < S - 1) ? __fsub_rn(tn, t) : 0.0f;
+                    const float mid = (i < S - 1) ? __fmul_rn(__fadd_rn(tn, t), 0.5f) : sample_t(g, G.step, S - 2);
+                    const float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-srow[i], __fmul_rn(delta, G.scale))));
+                    const float w = alpha * trow[i];
+                    W_tot += w;
+                    WM_tot += w * mid;
+                }
+            }
+            W_tot = warp_sum(W_tot);
+            WM_tot = warp_sum(WM_tot);
+        }
+
+        float S_run = 0.0f, Wgt_run = 0.0f, WMgt_run = 0.0f;
+        for (int c = n_chunks - 1; c >= 0; --c) {
+            const int i = c * 32 + lane;
+            const bool valid = i < S;
+            const float t = sample_t(g, G.step, i), tn = sample_t(g, G.step, i + 1);
+            float x[3];
+            const bool in = sample_point(g, t, G.amin, G.amax, G.inv, x) && valid;
+            const float delta = (valid && i < S - 1) ? __fsub_rn(tn, t) : 0.0f;
+            const float mid = (i < S - 1) ? __fmul_rn(__fadd_rn(tn, t), 0.5f) : sample_t(g, G.step, S - 2);
+            const float sigma = valid ? srow[i] : 0.0f;
+            const float T = valid ? trow[i] : 0.0f;
+            const float alpha = __fsub_rn(1.0f, expf(__fmul_rn(-sigma, __fmul_rn(delta, G.scale))));
+            const float w = alpha * T;
+            const float wm = w * mid;
+            // distortion-loss part of dL/dw
+            const float sw = suffix_inclusive(w, lane), swm = suffix_inclusive(wm, lane);
+            const float W_gt = Wgt_run + (sw - w), WM_gt = WMgt_run + (swm - wm);
+            Wgt_run += __shfl_sync(0xffffffffu, sw, 0);
+            WMgt_run += __shfl_sync(0xffffffffu, swm, 0);
+            float gi = g_opa + ((gwrow && valid) ? gwrow[i] : 0.0f);
+            if (gD != 0.0f) {
+                const float W_lt = W_tot - W_gt - w, WM_lt = WM_tot - WM_gt - wm;
+                gi += gD * ((2.0f / 3.0f) * w * delta + 2.0f * (mid * W_lt - WM_lt + WM_gt - mid * W_gt));
+            }
+            if (!valid) gi = 0.0f;
+            const float wg = w * gi;
+            const float swg = suffix_inclusive(wg, lane);
+            const float S_i = S_run + (swg - wg);
+            S_run += __shfl_sync(0xffffffffu, swg, 0);
+            const float fac = __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+            const float d_alpha = T * gi - S_i / fac;
+            const float d_sigma = d_alpha * __fmul_rn(delta, G.scale) * (1.0f - alpha);
+            const float dsp = sigma > 20.0f ? 1.0f : -expm1f(-sigma);
+            const float dfeat = in ? d_sigma * dsp : 0.0f;
+            const unsigned nz = __ballot_sync(0xffffffffu, dfeat != 0.0f);
+            if (nz == 0u) continue;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                if (((nz >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
+                const int src = j * 8 + (lane >> 2);
+                const float sx = __shfl_sync(0xffffffffu, x[0], src);
+                const float sy = __shfl_sync(0xffffffffu, x[1], src);
+                const float sz = __shfl_sync(0xffffffffu, x[2], src);
+                const float df = __shfl_sync(0xffffffffu, dfeat, src);
+                if (df == 0.0f) continue;
+                const float xs[3] = {sx, sy, sz};
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const int W = F.pw[m];
+                    const Tap2 t2 = make_tap2(xs[mode_a(m)], xs[mode_b(m)], W, F.ph[m]);
+                    const Tap1 t1 = make_tap1(xs[mode_v(m)], F.ll[m]);
+                    const int64_t row0 = (int64_t)t2.y0 * W, row1 = row0 + W;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        const int ch = v * 16 + q * 4;
+                        const float4 pv = plane_tap(F.plane[m], t2, W, F.comps, ch);
+                        const float4 lv = line_tap(F.line[m], t1, F.comps, ch);
+                        const float a0 = df * lv.x, a1 = df * lv.y, a2 = df * lv.z, a3 = df * lv.w;
+                        float* gp = P.g_plane[m];
+                        if (t2.w00 != 0.0f) red_add4f(gp + (row0 + t2.x0) * F.comps + ch, a0 * t2.w00, a1 * t2.w00, a2 * t2.w00, a3 * t2.w00);
+                        if (t2.w10 != 0.0f) red_add4f(gp + (row0 + t2.x0 + 1) * F.comps + ch, a0 * t2.w10, a1 * t2.w10, a2 * t2.w10, a3 * t2.w10);
+                        if (t2.w01 != 0.0f) red_add4f(gp + (row1 + t2.x0) * F.comps + ch, a0 * t2.w01, a1 * t2.w01, a2 * t2.w01, a3 * t2.w01);
+                        if (t2.w11 != 0.0f) red_add4f(gp + (row1 + t2.x0 + 1) * F.comps + ch, a0 * t2.w11, a1 * t2.w11, a2 * t2.w11, a3 * t2.w11);
+                        const float b0 = df * pv.x, b1 = df * pv.y, b2 = df * pv.z, b3 = df * pv.w;
+                        float* gl = P.g_line[m];
+                        if (t1.w0 != 0.0f) red_add4f(gl + (int64_t)t1.z0 * F.comps + ch, b0 * t1.w0, b1 * t1.w0, b2 * t1.w0, b3 * t1.w0);
+                        if (t1.w1 != 0.0f) red_add4f(gl + (int64_t)(t1.z0 + 1) * F.comps + ch, b0 * t1.w1, b1 * t1.w1, b2 * t1.w1, b3 * t1.w1);
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
@@ -512,6 +678,43 @@ int launch_density(const clift_field* field, const float* xyz, int64_t n, float*
             return CLIFT_ERR_UNSUPPORTED;
     }
     CLIFT_AFTER_LAUNCH("density_kernel");
+    return CLIFT_OK;
+}
+
+}  // namespace clift
+
+namespace clift {
+
+int launch_march_backward(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const float* jitter,
+                          int64_t n_rays, const Workspace& ws, int ray_stride, const float* g_dist, bool have_g_w,
+                          const clift_field_grad* grad, cudaStream_t stream) {
+    MarchBwdParams P;
+    P.g = make_geom(cfg);
+    P.f = make_factors(field, false);
+    P.rays = rays;
+    P.jitter = jitter;
+    P.n_rays = n_rays;
+    P.sigma_dense = ws.sigma_dense;
+    P.trans_dense = ws.trans_dense;
+    P.g_w = have_g_w ? ws.g_w : nullptr;
+    P.g_ray = ws.g_ray;
+    P.ray_stride = ray_stride;
+    P.g_dist = g_dist;
+    for (int m = 0; m < 3; ++m) {
+        P.g_plane[m] = grad->density_plane[m];
+        P.g_line[m] = grad->density_line[m];
+    }
+    const int grid = (int)std::min<int64_t>(ceil_div(n_rays, kWarpsPerCta), (int64_t)sm_count() * 6);
+    if (grid <= 0) return CLIFT_OK;
+    switch (P.f.comps / 16) {
+        case 1: march_backward_kernel<1><<<grid, kWarpsPerCta * 32, 0, stream>>>(P); break;
+        case 2: march_backward_kernel<2><<<grid, kWarpsPerCta * 32, 0, stream>>>(P); break;
+        case 3: march_backward_kernel<3><<<grid, kWarpsPerCta * 32, 0, stream>>>(P); break;
+        default:
+            set_error("launch_march_backward: density_comps %d not in {16,32,48}", P.f.comps);
+            return CLIFT_ERR_UNSUPPORTED;
+    }
+    CLIFT_AFTER_LAUNCH("march_backward_kernel");
     return CLIFT_OK;
 }
 

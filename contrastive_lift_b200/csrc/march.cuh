@@ -26,6 +26,8 @@ struct MarchParams {
     const float* jitter;
     int64_t n_rays;
     float* w_dense;     // [B,S]
+    float* sigma_dense; // [B,S] or null (training)
+    float* trans_dense; // [B,S] or null (training)
     int32_t* count;     // [B]
     float* opacity;     // [B]
     float* depth;       // [B]

@@ -29,6 +29,14 @@ __global__ void copy_pad_kernel(const float* __restrict__ src, int n, float* __r
     if (i < n_dst) dst[i] = (src && i < n) ? src[i] : 0.0f;
 }
 
+__global__ void copy2d_pad_kernel(const float* __restrict__ src, int s_rows, int s_cols, float* __restrict__ dst, int d_rows,
+                                  int d_cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d_rows * d_cols) return;
+    const int r = i / d_cols, c = i - r * d_cols;
+    dst[i] = (r < s_rows && c < s_cols) ? src[(int64_t)r * s_cols + c] : 0.0f;
+}
+
 }  // namespace
 
 static int transpose_pad(const float* src, int s_pitch, int s_rows, int s_cols, float* dst, int d_rows, int d_cols,
@@ -77,5 +85,14 @@ extern "C" int32_t clift_unpack_linear(const float* wt, const float* bias_pad, f
         copy_pad_kernel<<<(unsigned)ceil_div(n_out, 256), 256, 0, (cudaStream_t)stream>>>(bias_pad, n_out, b, n_out);
         CLIFT_AFTER_LAUNCH("copy_pad_kernel");
     }
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32_t n_out, int32_t n_in, void* stream) {
+    CLIFT_CHECK_ARG(w && w_dgrad && n_out > 0 && n_in > 0, "null pointer or non-positive size");
+    CLIFT_CHECK_SUPPORTED(n_in <= CLIFT_MAX_WIDTH && n_out <= CLIFT_MAX_WIDTH, "layer wider than CLIFT_MAX_WIDTH");
+    const int rows = k_pad(n_out), cols = dgrad_pad(n_in);
+    copy2d_pad_kernel<<<(unsigned)ceil_div((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(w, n_out, n_in, w_dgrad, rows, cols);
+    CLIFT_AFTER_LAUNCH("copy2d_pad_kernel");
     return CLIFT_OK;
 }

@@ -1,0 +1,461 @@
+"""Host-side mirror of ``TensorVMSplit`` (reference model/radiance_field/tensoRF.py:32-315).
+
+Same constructor signature, attribute names and ``state_dict`` keys as the reference, so the
+reference's trainer (trainer/train_panopli_tensorf.py:55-65, 99-103, 259, 449-457) and inference
+scripts (inference/render_panopli.py:77-98) can construct it, load their checkpoints into it and
+hand it to ``TensoRFRenderer``.  The parameters stay ordinary ``nn.Parameter``s in checkpoint layout
+(optimizers, EMA and DDP-style all-reduce see what they expect); the kernels read a *packed* copy
+(channel-last planes, transposed/padded Linear weights) that is refreshed through
+``clift_pack_*`` whenever a parameter's version counter moves.
+
+There is no PyTorch implementation of the field here: every lookup/MLP runs inside
+libclift_b200.so.  Configurations outside the compiled envelope raise ``CliftError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import lib as L
+
+MATRIX_MODE = [[0, 1], [0, 2], [1, 2]]
+VECTOR_MODE = [2, 1, 0]
+
+
+def _sequential(n_in: int, width: int, n_out: int, n_layers: int) -> nn.Sequential:
+    layers: List[nn.Module] = [nn.Linear(n_in, width)]
+    for _ in range(n_layers - 2):
+        layers += [nn.ReLU(inplace=True), nn.Linear(width, width)]
+    layers += [nn.ReLU(inplace=True), nn.Linear(width, n_out)]
+    return nn.Sequential(*layers)
+
+
+class _HeadBase(nn.Module):
+    """Parameter container with the reference head's attribute names.  The arithmetic of
+    ``forward`` lives in the fused CUDA kernels; calling the module directly is not a supported path."""
+
+    def forward(self, *args, **kwargs):  # pragma: no cover - guard
+        raise L.CliftError(f"{type(self).__name__} is evaluated inside the fused clift_render_* kernels; "
+                           "call TensoRFRenderer.forward / forward_instance_feature / forward_segment_feature")
+
+
+class MLPRenderFeature(_HeadBase):
+    """tensoRF.py:383-418 (parameters only)."""
+
+    def __init__(self, in_channels, out_channels=3, pe_view=2, pe_feat=2, dim_mlp_color=128, output_activation=torch.sigmoid):
+        super().__init__()
+        self.pe_view, self.pe_feat = pe_view, pe_feat
+        self.output_channels = out_channels
+        self.view_independent = pe_view == 0 and pe_feat == 0
+        self.in_feat_mlp = 2 * pe_view * 3 + 2 * pe_feat * in_channels + in_channels + (3 if not self.view_independent else 0)
+        self.output_activation = output_activation
+        self.mlp = _sequential(self.in_feat_mlp, dim_mlp_color, out_channels, 3)
+        nn.init.constant_(self.mlp[-1].bias, 0)
+
+
+class MLPRenderInstanceFeature(_HeadBase):
+    """tensoRF.py:462-511 (parameters only)."""
+
+    def __init__(self, in_channels, out_channels, num_mlp_layers=5, dim_mlp=256, pe_feat=0,
+                 output_activation=nn.Softmax(dim=-1), use_features=False, slow_fast_mode=False):
+        super().__init__()
+        self.output_channels = out_channels
+        self.output_activation = output_activation
+        self.pe_feat = pe_feat
+        self.use_features = use_features
+        self.slow_fast_mode = slow_fast_mode
+        self.in_feat_mlp = 2 * pe_feat * in_channels + in_channels + (64 if use_features else 0)
+        self.mlp = _sequential(self.in_feat_mlp, dim_mlp, out_channels, num_mlp_layers)
+        if slow_fast_mode:
+            self.slow_mlp = _sequential(self.in_feat_mlp, dim_mlp, out_channels, num_mlp_layers)
+
+
+class MLPRenderSemanticFeature(_HeadBase):
+    """tensoRF.py:565-594 (parameters only)."""
+
+    def __init__(self, in_channels, out_channels, pe_feat=0, num_mlp_layers=5, dim_mlp=256,
+                 output_activation=nn.Identity(), use_features=False):
+        super().__init__()
+        self.output_channels = out_channels
+        self.output_activation = output_activation
+        self.pe_feat = pe_feat
+        self.use_features = use_features
+        self.in_feat_mlp = 2 * pe_feat * in_channels + in_channels + (64 if use_features else 0)
+        self.mlp = _sequential(self.in_feat_mlp, dim_mlp, out_channels, num_mlp_layers)
+
+
+def _linears(seq: nn.Sequential) -> List[nn.Linear]:
+    return [m for m in seq if isinstance(m, nn.Linear)]
+
+
+class _PackedMlp:
+    """Device buffers of one Linear stack in kernel layout + their gradient mirrors."""
+
+    def __init__(self, linears: Sequence[nn.Linear], device, with_bias: bool = True):
+        self.linears = list(linears)
+        self.dims = [self.linears[0].in_features] + [l.out_features for l in self.linears]
+        self.wt = [torch.zeros((L.k_pad(l.in_features), L.n_pad(l.out_features)), device=device) for l in self.linears]
+        self.bias = [torch.zeros((L.n_pad(l.out_features),), device=device) for l in self.linears]
+        self.w_dgrad: List[Optional[torch.Tensor]] = [None] * len(self.linears)
+        self.g_wt: List[Optional[torch.Tensor]] = [None] * len(self.linears)
+        self.g_bias: List[Optional[torch.Tensor]] = [None] * len(self.linears)
+
+    def pack(self, lib, stream, training: bool):
+        for i, l in enumerate(self.linears):
+            L.check(lib.clift_pack_linear(L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None,
+                                          L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
+            if training:
+                if self.w_dgrad[i] is None:
+                    self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
+                L.check(lib.clift_pack_linear_dgrad(L.ptr(l.weight.data), L.ptr(self.w_dgrad[i]), l.out_features,
+                                                    l.in_features, stream))
+
+    def fill(self, m: L.Mlp):
+        m.n_layers = len(self.linears)
+        for i, d in enumerate(self.dims):
+            m.dims[i] = d
+        for i in range(len(self.linears)):
+            m.wt[i] = L.ptr(self.wt[i])
+            m.bias[i] = L.ptr(self.bias[i])
+            m.w_dgrad[i] = L.ptr(self.w_dgrad[i])
+
+    def grad_buffers(self, g: L.MlpGrad, want: bool):
+        for i in range(len(self.linears)):
+            if want:
+                if self.g_wt[i] is None:
+                    self.g_wt[i] = torch.zeros_like(self.wt[i])
+                    self.g_bias[i] = torch.zeros_like(self.bias[i])
+                else:
+                    self.g_wt[i].zero_()
+                    self.g_bias[i].zero_()
+                g.wt[i] = L.ptr(self.g_wt[i])
+                g.bias[i] = L.ptr(self.g_bias[i])
+            else:
+                g.wt[i] = None
+                g.bias[i] = None
+
+    def unpack_grads(self, lib, stream) -> List[torch.Tensor]:
+        """-> [dW0, db0, dW1, db1, ...] in nn.Linear layout."""
+        out = []
+        for i, l in enumerate(self.linears):
+            gw = torch.empty_like(l.weight)
+            gb = torch.empty_like(l.bias) if l.bias is not None else None
+            L.check(lib.clift_unpack_linear(L.ptr(self.g_wt[i]), L.ptr(self.g_bias[i]), L.ptr(gw), L.ptr(gb),
+                                            l.out_features, l.in_features, stream))
+            out.append(gw)
+            if gb is not None:
+                out.append(gb)
+        return out
+
+
+class TensorVMSplit(nn.Module):
+    """Drop-in for the reference class of the same name (tensoRF.py:32-315)."""
+
+    def __init__(self, grid_dim, num_density_comps=(16, 16, 16), num_appearance_comps=(48, 48, 48), num_semantics_comps=None,
+                 num_instance_comps=None, dim_appearance=27, dim_semantics=27, dim_instances=27, splus_density_shift=-10,
+                 pe_view=2, pe_feat=2, dim_mlp_color=128, dim_mlp_semantics=128, dim_mlp_instance=256, num_semantic_classes=0,
+                 dim_feature_instance=None, output_mlp_semantics=torch.nn.Softmax(dim=-1), use_semantic_mlp=False,
+                 use_instance_mlp=False, use_feature_reg=False, use_distilled_features_semantic=False,
+                 use_distilled_features_instance=False, num_feature_comps=(48, 48, 48), pe_sem=0, pe_ins=0,
+                 slow_fast_mode=False, use_proj=False):
+        super().__init__()
+        if use_distilled_features_semantic or use_distilled_features_instance:
+            raise L.CliftError("distilled-feature grids are outside the B200 hot path (off in every shipped contrastive config)")
+        if use_proj:
+            raise L.CliftError("use_proj (SlowFastProjLayer) is outside the B200 hot path (off in every shipped config)")
+        if not use_semantic_mlp or (dim_feature_instance is not None and not use_instance_mlp):
+            raise L.CliftError("grid-mode semantic/instance heads (allgrid.yaml) are not built yet: "
+                               "use_mlp_for_semantics/use_mlp_for_instances must be True")
+        if use_feature_reg:
+            raise L.CliftError("use_feature_regularization is not reachable from shipped configs and is not built")
+        if len(set(num_density_comps)) != 1 or len(set(num_appearance_comps)) != 1:
+            raise L.CliftError("per-mode component counts must be equal")
+        self.num_density_comps = num_density_comps
+        self.num_appearance_comps = num_appearance_comps
+        self.num_semantics_comps = num_semantics_comps
+        self.num_instance_comps = num_instance_comps
+        self.dim_appearance = dim_appearance
+        self.dim_semantics = dim_semantics
+        self.dim_instances = dim_instances
+        self.dim_feature_instance = dim_feature_instance
+        ins_out_channels = dim_feature_instance // 2 if slow_fast_mode else dim_feature_instance
+        self.num_semantic_classes = num_semantic_classes
+        self.splus_density_shift = splus_density_shift
+        self.use_semantic_mlp = use_semantic_mlp
+        self.use_instance_mlp = use_instance_mlp
+        self.slow_fast_mode = slow_fast_mode
+        self.use_proj = use_proj
+        self.use_feature_reg = False
+        self.pe_view, self.pe_feat = pe_view, pe_feat
+        self.pe_sem, self.pe_ins = pe_sem, pe_ins
+        self.dim_mlp_color = dim_mlp_color
+        self.matrix_mode = MATRIX_MODE
+        self.vector_mode = VECTOR_MODE
+        self.density_plane, self.density_line = self.init_one_svd(num_density_comps, grid_dim, 0.1)
+        self.appearance_plane, self.appearance_line = self.init_one_svd(num_appearance_comps, grid_dim, 0.1)
+        self.appearance_basis_mat = nn.Linear(sum(num_appearance_comps), dim_appearance, bias=False)
+        self.render_appearance_mlp = MLPRenderFeature(dim_appearance, 3, pe_view, pe_feat, dim_mlp_color)
+        self.semantic_plane = self.semantic_line = self.semantic_basis_mat = None
+        self.instance_plane = self.instance_line = self.instance_basis_mat = None
+        self.render_semantic_mlp = self.render_instance_mlp = None
+        if dim_feature_instance is not None:
+            self.render_instance_mlp = MLPRenderInstanceFeature(3, ins_out_channels, pe_feat=pe_ins, num_mlp_layers=4,
+                                                                dim_mlp=dim_mlp_instance, output_activation=nn.Identity(),
+                                                                slow_fast_mode=slow_fast_mode)
+        self.render_semantic_mlp = MLPRenderSemanticFeature(3, num_semantic_classes, pe_feat=pe_sem,
+                                                            output_activation=output_mlp_semantics)
+        self.use_distilled_features_semantic = False
+        self.use_distilled_features_instance = False
+        self.num_feature_comps = num_feature_comps
+        self.feature_plane = self.feature_line = self.feature_basis_mat = self.render_feature_mlp = None
+        self._packed: Optional["PackedField"] = None
+
+    # ---- construction helpers (tensoRF.py:99-106) ---------------------------------------------
+    def init_one_svd(self, n_components, grid_resolution, scale):
+        plane_coef, line_coef = [], []
+        for i in range(3):
+            vec_id = VECTOR_MODE[i]
+            m0, m1 = MATRIX_MODE[i]
+            plane_coef.append(nn.Parameter(scale * torch.randn((1, n_components[i], grid_resolution[m1], grid_resolution[m0]))))
+            line_coef.append(nn.Parameter(scale * torch.randn((1, n_components[i], grid_resolution[vec_id], 1))))
+        return nn.ParameterList(plane_coef), nn.ParameterList(line_coef)
+
+    @property
+    def semantic_softmax(self) -> bool:
+        return isinstance(self.render_semantic_mlp.output_activation, nn.Softmax)
+
+    def grid_dim(self) -> Tuple[int, int, int]:
+        """(gx, gy, gz) read back from the factor shapes (they change under shrink / upsample)."""
+        return (self.density_plane[0].shape[3], self.density_plane[0].shape[2], self.density_line[0].shape[2])
+
+    # ---- packed view ---------------------------------------------------------------------------
+    def packed(self, training: bool) -> "PackedField":
+        if self._packed is None or not self._packed.matches(self):
+            self._packed = PackedField(self)
+        self._packed.refresh(training)
+        return self._packed
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def invalidate_packed(self) -> None:
+        """Call after mutating parameters through ``.data`` outside a training render."""
+        self._packed = None
+
+    # ---- F1 point-wise entry (tensoRF.py:114-125); parity / dense-alpha use ---------------------
+    @torch.no_grad()
+    def compute_density(self, xyz_sampled: torch.Tensor) -> torch.Tensor:
+        lib = L.load()
+        pk = self.packed(False)
+        xyz = xyz_sampled.detach().reshape(-1, 3).contiguous().float()
+        sigma = torch.empty((xyz.shape[0],), device=xyz.device)
+        L.check(lib.clift_density(C.byref(pk.field), L.ptr(xyz), xyz.shape[0], L.ptr(sigma), L.stream_ptr(xyz.device)))
+        return sigma.view(xyz_sampled.shape[:-1])
+
+    # ---- grid surgery (tensoRF.py:158-197): parameter objects are replaced, packed view dropped --
+    @torch.no_grad()
+    def shrink(self, t_l, b_r):
+        for i in range(3):
+            v = VECTOR_MODE[i]
+            self.density_line[i] = nn.Parameter(self.density_line[i].data[..., t_l[v]:b_r[v], :].contiguous())
+            self.appearance_line[i] = nn.Parameter(self.appearance_line[i].data[..., t_l[v]:b_r[v], :].contiguous())
+            m0, m1 = MATRIX_MODE[i]
+            self.density_plane[i] = nn.Parameter(self.density_plane[i].data[..., t_l[m1]:b_r[m1], t_l[m0]:b_r[m0]].contiguous())
+            self.appearance_plane[i] = nn.Parameter(self.appearance_plane[i].data[..., t_l[m1]:b_r[m1], t_l[m0]:b_r[m0]].contiguous())
+        self._packed = None
+
+    @torch.no_grad()
+    def upsample_volume_grid(self, res_target):
+        self.appearance_plane, self.appearance_line = self.upsample_plane_line(self.appearance_plane, self.appearance_line, res_target)
+        self.density_plane, self.density_line = self.upsample_plane_line(self.density_plane, self.density_line, res_target)
+        self._packed = None
+
+    @torch.no_grad()
+    def upsample_plane_line(self, plane_coef, line_coef, res_target):
+        # epoch-boundary utility: stock bilinear resize, not on the per-step path
+        for i in range(3):
+            v = VECTOR_MODE[i]
+            m0, m1 = MATRIX_MODE[i]
+            plane_coef[i] = nn.Parameter(F.interpolate(plane_coef[i].data, size=(res_target[m1], res_target[m0]),
+                                                       mode="bilinear", align_corners=True))
+            line_coef[i] = nn.Parameter(F.interpolate(line_coef[i].data, size=(res_target[v], 1), mode="bilinear",
+                                                      align_corners=True))
+        return plane_coef, line_coef
+
+    # ---- optimizer groups (tensoRF.py:199-246) --------------------------------------------------
+    def get_optimizable_parameters(self, lr_grid, lr_net, weight_decay=0):
+        grad_vars = [{'params': self.density_line, 'lr': lr_grid, 'weight_decay': weight_decay},
+                     {'params': self.appearance_line, 'lr': lr_grid},
+                     {'params': self.density_plane, 'lr': lr_grid, 'weight_decay': weight_decay},
+                     {'params': self.appearance_plane, 'lr': lr_grid},
+                     {'params': self.appearance_basis_mat.parameters(), 'lr': lr_net},
+                     {'params': self.render_appearance_mlp.parameters(), 'lr': lr_net}]
+        if self.render_semantic_mlp is not None:
+            grad_vars.append({'params': self.render_semantic_mlp.parameters(), 'lr': lr_net})
+        return grad_vars
+
+    def get_optimizable_density_parameters(self, lr_grid):
+        return [{'params': self.density_line, 'lr': lr_grid}, {'params': self.density_plane, 'lr': lr_grid}]
+
+    def get_optimizable_segment_parameters(self, lr_grid, lr_net, _weight_decay=0):
+        return [{'params': self.render_semantic_mlp.parameters(), 'lr': lr_net}] if self.render_semantic_mlp is not None else []
+
+    def get_optimizable_instance_parameters(self, lr_grid, lr_net, using_DINO=False):
+        grad_vars = []
+        if self.render_instance_mlp is not None:
+            grad_vars.append({'params': self.render_instance_mlp.mlp.parameters(), 'lr': lr_net})
+        if self.slow_fast_mode and not using_DINO:
+            grad_vars.append({'params': self.render_instance_mlp.slow_mlp.parameters(), 'lr': lr_net})
+        return grad_vars
+
+    # ---- TV regulariser (tensoRF.py:248-290) via clift_tv_loss -----------------------------------
+    def tv_loss_density(self, regularizer=None):
+        from .loss import plane_tv
+        return sum(plane_tv(p) * 1e-2 for p in self.density_plane)
+
+    def tv_loss_appearance(self, regularizer=None):
+        from .loss import plane_tv
+        return sum(plane_tv(p) * 1e-2 for p in self.appearance_plane)
+
+    def tv_loss_semantics(self, regularizer=None):
+        return 0
+
+    def tv_loss_instances(self, regularizer=None):
+        return 0
+
+    def total_tv_loss(self, regularizer, config, current_epoch):
+        """Same signature as tensoRF.py:281-290.  ``regularizer`` (the reference's TVLoss module) is
+        accepted and ignored: the stencil runs in clift_tv_loss.  Semantic/instance planes do not exist
+        in MLP-head mode, so their terms are zero as in the reference."""
+        return self.tv_loss_density() * config.lambda_tv_density + self.tv_loss_appearance() * config.lambda_tv_appearance
+
+
+class PackedField:
+    """Kernel-layout copy of a TensorVMSplit's parameters + the ctypes descriptor handed to the C ABI."""
+
+    def __init__(self, model: TensorVMSplit):
+        self.lib = L.load()
+        dev = model.density_plane[0].device
+        if dev.type != "cuda":
+            raise L.CliftError("TensorVMSplit must live on a CUDA device: libclift_b200 has no CPU path")
+        self.device = dev
+        self.grid = model.grid_dim()
+        self.ids = self._ids(model)
+        self.versions: Optional[Tuple[int, ...]] = None
+        self.trained = False
+        self.model_params = list(model.parameters())
+        mk = lambda plist: [torch.empty((p.shape[2], p.shape[3], p.shape[1]), device=dev) for p in plist]
+        mkl = lambda plist: [torch.empty((p.shape[2], p.shape[1]), device=dev) for p in plist]
+        self.planes = {"density": mk(model.density_plane), "appearance": mk(model.appearance_plane)}
+        self.lines = {"density": mkl(model.density_line), "appearance": mkl(model.appearance_line)}
+        self.src = {"density": (model.density_plane, model.density_line),
+                    "appearance": (model.appearance_plane, model.appearance_line)}
+        self.basis = _PackedMlp([model.appearance_basis_mat], dev)
+        self.rgb = _PackedMlp(_linears(model.render_appearance_mlp.mlp), dev)
+        self.sem = _PackedMlp(_linears(model.render_semantic_mlp.mlp), dev)
+        self.insf = _PackedMlp(_linears(model.render_instance_mlp.mlp), dev) if model.render_instance_mlp is not None else None
+        self.inss = (_PackedMlp(_linears(model.render_instance_mlp.slow_mlp), dev)
+                     if model.render_instance_mlp is not None and model.slow_fast_mode else None)
+        f = L.Field()
+        L.fill3(f.grid, self.grid)
+        f.density_comps = model.num_density_comps[0]
+        f.appearance_comps = model.num_appearance_comps[0]
+        f.dim_appearance = model.dim_appearance
+        f.pe_view, f.pe_feat, f.pe_sem, f.pe_ins = model.pe_view, model.pe_feat, model.pe_sem, model.pe_ins
+        f.num_classes = model.num_semantic_classes
+        f.dim_instance = model.render_instance_mlp.output_channels if model.render_instance_mlp is not None else 0
+        f.slow_fast = 1 if model.slow_fast_mode else 0
+        f.density_shift = float(model.splus_density_shift)
+        for i in range(3):
+            f.density_plane[i] = L.ptr(self.planes["density"][i])
+            f.density_line[i] = L.ptr(self.lines["density"][i])
+            f.appearance_plane[i] = L.ptr(self.planes["appearance"][i])
+            f.appearance_line[i] = L.ptr(self.lines["appearance"][i])
+        self.field = f
+        self.grad = L.FieldGrad()
+        self.g_planes: Dict[str, List[Optional[torch.Tensor]]] = {"density": [None] * 3, "appearance": [None] * 3}
+        self.g_lines: Dict[str, List[Optional[torch.Tensor]]] = {"density": [None] * 3, "appearance": [None] * 3}
+
+    @staticmethod
+    def _ids(model) -> Tuple[int, ...]:
+        return tuple(id(p) for p in model.parameters())
+
+    def matches(self, model) -> bool:
+        return self.ids == self._ids(model) and self.device == model.density_plane[0].device
+
+    def refresh(self, training: bool) -> None:
+        # Inference renders reuse the packed copy while no parameter version moved.  Training renders always
+        # repack: the reference's EMA writes through ``.data`` (trainer:325-329), which version counters miss.
+        versions = tuple(p._version for p in self.model_params) + (L.param_epoch(),)
+        if not training and versions == self.versions:
+            return
+        lib, st = self.lib, L.stream_ptr(self.device)
+        for name in ("density", "appearance"):
+            planes, lines = self.src[name]
+            for i in range(3):
+                p, l = planes[i].data, lines[i].data
+                L.check(lib.clift_pack_plane(L.ptr(p), L.ptr(self.planes[name][i]), p.shape[1], p.shape[2], p.shape[3], st))
+                L.check(lib.clift_pack_plane(L.ptr(l), L.ptr(self.lines[name][i]), l.shape[1], l.shape[2], 1, st))
+        for m in (self.basis, self.rgb, self.sem, self.insf, self.inss):
+            if m is not None:
+                m.pack(lib, st, training)
+        f = self.field
+        f.basis = L.ptr(self.basis.wt[0])
+        f.basis_dgrad = L.ptr(self.basis.w_dgrad[0])
+        self.rgb.fill(f.rgb)
+        self.sem.fill(f.semantic)
+        if self.insf is not None:
+            self.insf.fill(f.instance_fast)
+        if self.inss is not None:
+            self.inss.fill(f.instance_slow)
+        self.versions = versions
+        self.trained = self.trained or training
+
+    # ---- gradient side ---------------------------------------------------------------------------
+    def prepare_grads(self, want_density: bool, want_rgb: bool, want_sem: bool, want_ins: bool) -> L.FieldGrad:
+        g = self.grad
+        for name, want in (("density", want_density), ("appearance", want_rgb)):
+            for i in range(3):
+                if want:
+                    if self.g_planes[name][i] is None:
+                        self.g_planes[name][i] = torch.zeros_like(self.planes[name][i])
+                        self.g_lines[name][i] = torch.zeros_like(self.lines[name][i])
+                    else:
+                        self.g_planes[name][i].zero_()
+                        self.g_lines[name][i].zero_()
+                gp = L.ptr(self.g_planes[name][i]) if want else None
+                gl = L.ptr(self.g_lines[name][i]) if want else None
+                if name == "density":
+                    g.density_plane[i], g.density_line[i] = gp, gl
+                else:
+                    g.appearance_plane[i], g.appearance_line[i] = gp, gl
+        dummy = L.MlpGrad()
+        self.basis.grad_buffers(dummy, want_rgb)
+        g.basis = dummy.wt[0]
+        self.rgb.grad_buffers(g.rgb, want_rgb)
+        self.sem.grad_buffers(g.semantic, want_sem)
+        if self.insf is not None:
+            self.insf.grad_buffers(g.instance_fast, want_ins)
+        if self.inss is not None:
+            self.inss.grad_buffers(g.instance_slow, want_ins)
+        return g
+
+    def unpack_factor_grads(self, name: str) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+        lib, st = self.lib, L.stream_ptr(self.device)
+        planes, lines = self.src[name]
+        gp, gl = [], []
+        for i in range(3):
+            p, l = planes[i], lines[i]
+            a = torch.empty_like(p.data)
+            b = torch.empty_like(l.data)
+            L.check(lib.clift_unpack_plane(L.ptr(self.g_planes[name][i]), L.ptr(a), p.shape[1], p.shape[2], p.shape[3], st))
+            L.check(lib.clift_unpack_plane(L.ptr(self.g_lines[name][i]), L.ptr(b), l.shape[1], l.shape[2], 1, st))
+            gp.append(a)
+            gl.append(b)
+        return gp, gl

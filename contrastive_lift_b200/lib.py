@@ -1,0 +1,170 @@
+"""ctypes binding of libclift_b200.so (include/clift_b200.h).
+
+The library is the product: there is no Python/PyTorch fallback for any compute entry.  If the
+shared object is missing or a call fails, an exception is raised - nothing is silently rerouted.
+PyTorch is used only for device memory (caching allocator), streams and torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+MAX_LAYERS = 8
+ABI_VERSION = 2
+
+HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
+
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+
+class Mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)),
+                ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS)]
+
+
+class MlpGrad(C.Structure):
+    _fields_ = [("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS)]
+
+
+class Field(C.Structure):
+    _fields_ = [("grid", C.c_int32 * 3), ("density_comps", C.c_int32), ("appearance_comps", C.c_int32),
+                ("dim_appearance", C.c_int32), ("pe_view", C.c_int32), ("pe_feat", C.c_int32),
+                ("pe_sem", C.c_int32), ("pe_ins", C.c_int32), ("num_classes", C.c_int32),
+                ("dim_instance", C.c_int32), ("slow_fast", C.c_int32), ("density_shift", C.c_float),
+                ("density_plane", _vp * 3), ("density_line", _vp * 3),
+                ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp), ("basis_dgrad", _vp),
+                ("rgb", Mlp), ("semantic", Mlp), ("instance_fast", Mlp), ("instance_slow", Mlp)]
+
+
+class FieldGrad(C.Structure):
+    _fields_ = [("density_plane", _vp * 3), ("density_line", _vp * 3),
+                ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp),
+                ("rgb", MlpGrad), ("semantic", MlpGrad), ("instance_fast", MlpGrad), ("instance_slow", MlpGrad)]
+
+
+class RenderCfg(C.Structure):
+    _fields_ = [("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("inv_extent", C.c_float * 3),
+                ("step_size", C.c_float), ("n_samples", C.c_int32), ("distance_scale", C.c_float),
+                ("weight_thres", C.c_float), ("semantic_softmax", C.c_int32), ("heads", C.c_int32)]
+
+
+class RenderOut(C.Structure):
+    _fields_ = [("rgb", _vp), ("semantic", _vp), ("instance", _vp), ("depth", _vp), ("opacity", _vp),
+                ("dist_reg", _vp), ("rgb_raw", _vp), ("semantic_raw", _vp), ("dist_ray", _vp),
+                ("points", _vp), ("weights", _vp), ("save_for_backward", C.c_int32)]
+
+
+class CliftError(RuntimeError):
+    pass
+
+
+_LIB: Optional[C.CDLL] = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libclift_b200.so")
+
+# name -> (restype, argtypes); every symbol include/clift_b200.h declares
+SIGNATURES = {
+    "clift_abi_version": (C.c_int32, []),
+    "clift_last_error": (C.c_char_p, []),
+    "clift_launch_count": (C.c_int64, []),
+    "clift_profile_enable": (C.c_int32, [C.c_int32]),
+    "clift_profile_stage_ms": (C.c_int32, [_fp]),
+    "clift_pack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "clift_unpack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "clift_pack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_unpack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_pack_linear_dgrad": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_gen_rays": (C.c_int32, [_fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp]),
+    "clift_sample_points": (C.c_int32, [C.POINTER(RenderCfg), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "clift_density": (C.c_int32, [C.POINTER(Field), _vp, C.c_int64, _vp, _vp]),
+    "clift_render_workspace_bytes": (C.c_int64, [C.POINTER(RenderCfg), C.POINTER(Field), C.c_int64, C.c_int64,
+                                                       C.c_int32]),
+    "clift_render_forward": (C.c_int32, [C.POINTER(RenderCfg), C.POINTER(Field), _vp, _vp, C.c_int64, C.c_int32,
+                                         _vp, C.c_int64, C.c_int64, C.POINTER(RenderOut), _vp]),
+    "clift_render_stats": (C.c_int32, [_vp, _vp, _vp]),
+    "clift_render_backward": (C.c_int32, [C.POINTER(RenderCfg), C.POINTER(Field), _vp, _vp, C.c_int64, C.c_int32,
+                                          _vp, C.c_int64, C.c_int64, C.POINTER(RenderOut), _vp, _vp, _vp, _vp,
+                                          C.POINTER(FieldGrad), _vp]),
+    "clift_slowfast_loss": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]),
+    "clift_ema_update": (C.c_int32, [_vp, _vp, C.c_int64, C.c_double, _vp]),
+    "clift_contrastive_loss": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp]),
+    "clift_tv_loss": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_float, _vp]),
+}
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (never a site-packages copy) and type every entry point."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise CliftError(f"{LIB_PATH} is missing: run `python -m contrastive_lift_b200.build` "
+                         "(there is no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.clift_abi_version()
+    if got != ABI_VERSION:
+        raise CliftError(f"libclift_b200.so has ABI {got}, the Python host expects {ABI_VERSION}: rebuild")
+    _LIB = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().clift_last_error().decode(errors="replace")
+        raise CliftError(f"clift status {rc}: {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise CliftError("libclift_b200 takes device pointers: got a CPU tensor (no CPU fallback exists)")
+    if not t.is_contiguous():
+        raise CliftError("non-contiguous tensor passed to libclift_b200")
+    return t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().clift_launch_count())
+
+
+def k_pad(k: int) -> int:
+    return (k + 15) // 16 * 16
+
+
+def n_pad(n: int) -> int:
+    return (n + 63) // 64 * 64
+
+
+def dgrad_pad(n: int) -> int:
+    return 64 if n <= 64 else (128 if n <= 128 else 256)
+
+
+_PARAM_EPOCH = 0
+
+
+def bump_param_epoch() -> None:
+    """Invalidate every cached packed-parameter copy (parameters changed behind autograd's version counters)."""
+    global _PARAM_EPOCH
+    _PARAM_EPOCH += 1
+
+
+def param_epoch() -> int:
+    return _PARAM_EPOCH
+
+
+def fill3(arr, values: Sequence) -> None:
+    for i in range(3):
+        arr[i] = values[i]

@@ -1,0 +1,306 @@
+"""Host-side mirror of ``TensoRFRenderer`` (reference model/renderer/panopli_tensoRF_renderer.py:37-300).
+
+Same constructor, buffers (``bbox_aabb, grid_dim, inv_box_extent, units``), attributes
+(``step_size, n_samples, step_ratio``) and method signatures as the reference, so the call sites
+trainer/train_panopli_tensorf.py:110,131,143 and inference/render_panopli.py:115 work unchanged.
+Each of the three render entries is ONE call into libclift_b200.so through an autograd.Function;
+chunking (config.chunk) is still honoured by the callers but no longer needed for memory.
+
+RNG parity: the reference draws the per-ray jitter with ``torch.rand_like`` on a CPU tensor and the
+random-background coin with ``torch.rand((1,))`` from the CPU default generator, per chunk call
+(renderer:807-810, 164).  The same draws are made here, in the same order, and passed to the kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import lib as L
+from .field import TensorVMSplit
+
+_WORKSPACES = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    """Grow-only per-device scratch (the C ABI never allocates)."""
+    ws = _WORKSPACES.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = None
+        _WORKSPACES.pop(device, None)
+        ws = torch.empty((int(nbytes * 1.25) + 1024,), dtype=torch.uint8, device=device)
+        _WORKSPACES[device] = ws
+    return ws
+
+
+class _Render(torch.autograd.Function):
+    """clift_render_forward / clift_render_backward.  ``params`` are the model parameters in
+    ``model.named_parameters()`` order; they are inputs only so autograd routes gradients to them."""
+
+    @staticmethod
+    def forward(ctx, renderer, model, rays, jitter, add_bg, heads, want_points, need_grad, *params):
+        lib = L.load()
+        dev = rays.device
+        pk = model.packed(need_grad)
+        cfg = renderer._cfg(model, heads)
+        B = rays.shape[0]
+        C_, DI = model.num_semantic_classes, (model.dim_feature_instance or 0)
+        new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        out = L.RenderOut()
+        t = {"depth": new(B), "opacity": new(B)}
+        if heads & L.HEAD_RGB:
+            t["rgb"], t["rgb_raw"] = new(B, 3), new(B, 3)
+            t["dist_ray"], t["dist_reg"] = new(B), new(1)
+        if heads & L.HEAD_SEMANTIC:
+            t["semantic"], t["semantic_raw"] = new(B, C_), new(B, C_)
+        if heads & L.HEAD_INSTANCE:
+            t["instance"] = new(B, DI)
+        if want_points:
+            t["points"] = new(B, 3)
+        for k, v in t.items():
+            setattr(out, k, L.ptr(v))
+        out.save_for_backward = 1 if need_grad else 0
+        cap = renderer.max_active(B)
+        while True:
+            nbytes = lib.clift_render_workspace_bytes(C.byref(cfg), C.byref(pk.field), B, cap, out.save_for_backward)
+            if nbytes < 0:
+                L.check(int(nbytes))
+            ws = _workspace(dev, nbytes)
+            L.check(lib.clift_render_forward(C.byref(cfg), C.byref(pk.field), L.ptr(rays), L.ptr(jitter), B, int(add_bg),
+                                             L.ptr(ws), ws.numel(), cap, C.byref(out), L.stream_ptr(dev)))
+            if B == 0 or not renderer.check_overflow:
+                break
+            n_act, _, overflow, _ = renderer.last_stats(dev)       # one 32-byte D2H (the reference syncs ~10x per call)
+            if not overflow:
+                break
+            cap = (n_act + 127) // 128 * 128                          # rerun with the exact active-sample count
+        ctx.need_grad = need_grad
+        if need_grad:
+            ctx.renderer, ctx.model, ctx.pk, ctx.cfg = renderer, model, pk, cfg
+            ctx.rays, ctx.jitter, ctx.add_bg, ctx.heads, ctx.cap = rays, jitter, add_bg, heads, cap
+            # only tensors that are NOT outputs are kept on ctx (an output kept here would be a reference cycle)
+            ctx.t = {k: t[k] for k in ("rgb_raw", "semantic_raw", "opacity") if k in t}
+            ctx.ws = ws
+            ctx.param_names = [n for n, _ in model.named_parameters()]
+            renderer._live_ctx = ctx
+        empty = rays.new_zeros((0,))
+        res = (t.get("rgb", empty), t.get("semantic", empty), t.get("instance", empty), t["depth"],
+               t["dist_reg"].reshape(()) if "dist_reg" in t else empty, t.get("points", empty))
+        ctx.mark_non_differentiable(res[3], res[5])
+        renderer.last_opacity = t["opacity"]
+        return res
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sem, g_ins, _g_depth, g_dist, _g_pts):
+        if not ctx.need_grad:
+            raise L.CliftError("backward through a render that was run without need_grad")
+        renderer, model, pk = ctx.renderer, ctx.model, ctx.pk
+        if renderer._live_ctx is not ctx:
+            raise L.CliftError("the render workspace was overwritten by a later render call before backward ran: "
+                               "call backward before the next training-mode render on this renderer")
+        lib = L.load()
+        dev = ctx.rays.device
+        heads = ctx.heads
+        prep = lambda g, on: g.contiguous().float() if (g is not None and on and g.numel() > 0) else None
+        g_rgb = prep(g_rgb, heads & L.HEAD_RGB)
+        g_sem = prep(g_sem, heads & L.HEAD_SEMANTIC)
+        g_ins = prep(g_ins, heads & L.HEAD_INSTANCE)
+        g_dist = prep(g_dist.reshape(1) if g_dist is not None and g_dist.numel() == 1 else None, heads & L.HEAD_RGB)
+        want_density = (g_rgb is not None or g_dist is not None) and not ctx.renderer._density_frozen(heads)
+        fg = pk.prepare_grads(want_density, g_rgb is not None, g_sem is not None, g_ins is not None)
+        saved = L.RenderOut()
+        for k, v in ctx.t.items():
+            setattr(saved, k, L.ptr(v))
+        saved.save_for_backward = 1
+        B = ctx.rays.shape[0]
+        L.check(lib.clift_render_backward(C.byref(ctx.cfg), C.byref(pk.field), L.ptr(ctx.rays), L.ptr(ctx.jitter), B,
+                                          int(ctx.add_bg), L.ptr(ctx.ws), ctx.ws.numel(), ctx.cap,
+                                          C.byref(saved), L.ptr(g_rgb), L.ptr(g_sem), L.ptr(g_ins), L.ptr(g_dist),
+                                          C.byref(fg), L.stream_ptr(dev)))
+        renderer._live_ctx = None
+        st = L.stream_ptr(dev)
+        grads = {}
+        if want_density:
+            gp, gl = pk.unpack_factor_grads("density")
+            for i in range(3):
+                grads[f"density_plane.{i}"], grads[f"density_line.{i}"] = gp[i], gl[i]
+        if g_rgb is not None:
+            gp, gl = pk.unpack_factor_grads("appearance")
+            for i in range(3):
+                grads[f"appearance_plane.{i}"], grads[f"appearance_line.{i}"] = gp[i], gl[i]
+            grads["appearance_basis_mat.weight"] = pk.basis.unpack_grads(lib, st)[0]
+            for n, g in zip(_mlp_names("render_appearance_mlp.mlp", pk.rgb), pk.rgb.unpack_grads(lib, st)):
+                grads[n] = g
+        if g_sem is not None:
+            for n, g in zip(_mlp_names("render_semantic_mlp.mlp", pk.sem), pk.sem.unpack_grads(lib, st)):
+                grads[n] = g
+        if g_ins is not None and pk.insf is not None:
+            for n, g in zip(_mlp_names("render_instance_mlp.mlp", pk.insf), pk.insf.unpack_grads(lib, st)):
+                grads[n] = g
+            if pk.inss is not None:
+                for n, g in zip(_mlp_names("render_instance_mlp.slow_mlp", pk.inss), pk.inss.unpack_grads(lib, st)):
+                    grads[n] = g
+        return (None,) * 8 + tuple(grads.get(n) for n in ctx.param_names)
+
+
+def _mlp_names(prefix: str, pm) -> List[str]:
+    names = []
+    for i, l in enumerate(pm.linears):
+        names.append(f"{prefix}.{2 * i}.weight")
+        if l.bias is not None:
+            names.append(f"{prefix}.{2 * i}.bias")
+    return names
+
+
+class TensoRFRenderer(nn.Module):
+    """Drop-in for the reference class of the same name (renderer:37-300)."""
+
+    def __init__(self, bbox_aabb, grid_dim, stop_semantic_grad=True, semantic_weight_mode="none", step_ratio=0.5,
+                 distance_scale=25, raymarch_weight_thres=0.0001, alpha_mask_threshold=0.0075, parent_renderer_ref=None,
+                 instance_id=0, feature_stop_grad=False, verbose=False):
+        super().__init__()
+        if not stop_semantic_grad:
+            raise L.CliftError("stop_semantic_grad=False is not built (every shipped config uses True, panopli_paper.yaml:35)")
+        self.register_buffer("bbox_aabb", torch.as_tensor(bbox_aabb, dtype=torch.float32).clone())
+        self.register_buffer("grid_dim", torch.LongTensor(list(grid_dim)))
+        self.register_buffer("inv_box_extent", torch.zeros([3]))
+        self.register_buffer("units", torch.zeros([3]))
+        self.semantic_weight_mode = semantic_weight_mode
+        self.parent_renderer_ref = parent_renderer_ref
+        self.step_ratio = step_ratio
+        self.distance_scale = distance_scale
+        self.raymarch_weight_thres = raymarch_weight_thres
+        self.alpha_mask_threshold = alpha_mask_threshold
+        self.step_size = None
+        self.n_samples = None
+        self.stop_semantic_grad = stop_semantic_grad
+        self.feature_stop_grad = feature_stop_grad
+        self.instance_id = instance_id
+        self.verbose = verbose
+        # Capacity of the compacted active-sample list, per ray (active = weight > raymarch_weight_thres).  An
+        # overflow is detected after the call (check_overflow) and the call is repeated at the exact size.
+        self.max_active_per_ray = 192
+        self.check_overflow = True
+        self._live_ctx = None
+        self._host = None
+        self.last_opacity = None
+        self.update_step_size(self.grid_dim)
+
+    # ---- renderer:59-78 ---------------------------------------------------------------------------
+    def update_step_size(self, grid_dim):
+        box_extent = self.bbox_aabb[1] - self.bbox_aabb[0]
+        self.grid_dim.data = torch.tensor(grid_dim, device=self.bbox_aabb.device) if isinstance(grid_dim, tuple) else grid_dim
+        self.inv_box_extent.data = 2.0 / box_extent
+        self.units.data = box_extent / (self.grid_dim - 1 + 1e-3)
+        self.step_size = torch.mean(self.units) * self.step_ratio
+        box_diag = torch.sqrt(torch.sum(torch.square(box_extent)))
+        self.n_samples = int((box_diag / self.step_size).item()) + 1
+        self._host = None
+        if self.verbose:
+            print(f"[{self.instance_id:02d}] aabb {self.bbox_aabb.view(-1).tolist()} grid {self.grid_dim.tolist()} "
+                  f"step {float(self.step_size):.6f} samples {self.n_samples}")
+
+    def update_step_ratio(self, step_ratio):
+        self.step_ratio = step_ratio
+        self.step_size = torch.mean(self.units) * self.step_ratio
+        box_extent = self.bbox_aabb[1] - self.bbox_aabb[0]
+        box_diag = torch.sqrt(torch.sum(torch.square(box_extent)))
+        self.n_samples = int((box_diag / self.step_size).item()) + 1
+        self._host = None
+
+    def _apply(self, fn, *a, **k):
+        self._host = None
+        r = super()._apply(fn, *a, **k)
+        if self.step_size is not None and torch.is_tensor(self.step_size):
+            self.step_size = fn(self.step_size)
+        return r
+
+    def get_target_resolution(self, n_voxels):
+        xyz_min, xyz_max = self.bbox_aabb
+        voxel_size = ((xyz_max - xyz_min).prod() / n_voxels).pow(1 / 3)
+        target_res = ((xyz_max - xyz_min) / voxel_size).long().tolist()
+        return tuple(max(x, 1) for x in target_res)
+
+    def max_active(self, n_rays: int) -> int:
+        """<= 0 means worst case (every sample active) to the C ABI."""
+        if self.max_active_per_ray <= 0:
+            return 0
+        return max(128, int(n_rays) * min(int(self.max_active_per_ray), int(self.n_samples)))
+
+    # ---- descriptor for the C ABI -----------------------------------------------------------------
+    def _cfg(self, model: TensorVMSplit, heads: int) -> L.RenderCfg:
+        if self._host is None:       # one D2H of 10 floats per geometry change, not per call
+            self._host = (self.bbox_aabb.detach().cpu().tolist(), self.inv_box_extent.detach().cpu().tolist(),
+                          float(self.step_size))
+        aabb, inv, step = self._host
+        cfg = L.RenderCfg()
+        L.fill3(cfg.aabb_min, aabb[0])
+        L.fill3(cfg.aabb_max, aabb[1])
+        L.fill3(cfg.inv_extent, inv)
+        cfg.step_size = step
+        cfg.n_samples = int(self.n_samples)
+        cfg.distance_scale = float(self.distance_scale)
+        cfg.weight_thres = float(self.raymarch_weight_thres)
+        cfg.semantic_softmax = 1 if self.semantic_weight_mode == "softmax" else 0
+        cfg.heads = heads
+        if tuple(self.grid_dim.tolist()) != tuple(model.grid_dim()):
+            raise L.CliftError(f"renderer.grid_dim {self.grid_dim.tolist()} != model factor grid {model.grid_dim()}")
+        return cfg
+
+    @staticmethod
+    def _density_frozen(heads: int) -> bool:
+        # forward_instance_feature / forward_segment_feature evaluate density under no_grad (renderer:187-190, 268-271)
+        return not (heads & L.HEAD_RGB)
+
+    def _jitter(self, rays, perturb, is_train) -> Optional[torch.Tensor]:
+        if is_train and perturb != 0:
+            u = perturb * torch.rand((rays.shape[0], 1))          # CPU default generator, as renderer:808-810
+            return u.reshape(-1).to(rays.device, non_blocking=True).contiguous()
+        return None
+
+    def _run(self, tensorf, rays, jitter, add_bg, heads, want_points):
+        if not rays.is_cuda:
+            raise L.CliftError("rays must be a CUDA tensor: this renderer has no CPU path")
+        rays = rays.detach().contiguous().float()
+        params = [p for _, p in tensorf.named_parameters()]
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _Render.apply(self, tensorf, rays, jitter, add_bg, heads, want_points, need_grad, *params)
+
+    # ---- renderer:80-176 --------------------------------------------------------------------------
+    def forward(self, tensorf, rays, perturb, white_bg, is_train):
+        jitter = self._jitter(rays, perturb, is_train)
+        add_bg = bool(white_bg or (is_train and bool(torch.rand((1,)) < 0.5)))     # renderer:164, CPU coin per call
+        rgb, sem, ins, depth, dist, _ = self._run(tensorf, rays, jitter, add_bg, self._heads(tensorf), False)
+        return rgb, sem, ins, depth, torch.zeros([1, 1], device=rays.device), dist
+
+    @staticmethod
+    def _heads(tensorf) -> int:
+        h = L.HEAD_RGB | L.HEAD_SEMANTIC
+        if tensorf.render_instance_mlp is not None:
+            h |= L.HEAD_INSTANCE
+        return h
+
+    # ---- renderer:178-217 -------------------------------------------------------------------------
+    def forward_instance_feature(self, tensorf, rays, perturb, is_train):
+        jitter = self._jitter(rays, perturb, is_train)
+        _, _, ins, _, _, pts = self._run(tensorf, rays, jitter, False, L.HEAD_INSTANCE, True)
+        return ins, pts
+
+    # ---- renderer:259-300 -------------------------------------------------------------------------
+    def forward_segment_feature(self, tensorf, rays, perturb, is_train):
+        jitter = self._jitter(rays, perturb, is_train)
+        _, seg, _, _, _, _ = self._run(tensorf, rays, jitter, False, L.HEAD_SEMANTIC, False)
+        return seg
+
+    # ---- diagnostics ------------------------------------------------------------------------------
+    def last_stats(self, device) -> Tuple[int, int, int, int]:
+        """(n_active, n_inbox, overflow, n_tiles) of the last render on ``device`` (one small D2H)."""
+        ws = _WORKSPACES[torch.device(device) if not isinstance(device, torch.device) else device]
+        st = torch.empty((4,), dtype=torch.int64, device=ws.device)
+        L.check(L.load().clift_render_stats(L.ptr(ws), L.ptr(st), L.stream_ptr(ws.device)))
+        return tuple(int(v) for v in st.cpu().tolist())
+
+    def update_bbox_aabb_and_shrink(self, tensorf, fractional_lenience=1.0):
+        raise L.CliftError("update_bbox_aabb_and_shrink (epoch-boundary dense-alpha sweep, SURVEY 8f rank 3) is not built yet")

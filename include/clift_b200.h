@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 1
+#define CLIFT_ABI_VERSION 2
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -47,6 +47,10 @@ typedef struct {
     int32_t dims[CLIFT_MAX_LAYERS + 1];       /* logical widths: in, hidden..., out */
     const float* wt[CLIFT_MAX_LAYERS];
     const float* bias[CLIFT_MAX_LAYERS];
+    /* training only (may be null for inference): the same weights in the data-gradient layout written
+     * by clift_pack_linear_dgrad(): W row-major [round_up(out,16)][dgrad_pad(in)], zero filled, where
+     * dgrad_pad(in) = 64, 128 or 256 (smallest that fits). */
+    const float* w_dgrad[CLIFT_MAX_LAYERS];
 } clift_mlp;
 
 /* Gradient mirror of clift_mlp (same packed shapes); null pointers = do not accumulate. */
@@ -74,6 +78,7 @@ typedef struct {
     const float* appearance_plane[3];
     const float* appearance_line[3];
     const float* basis;              /* appearance_basis_mat packed as a 1-layer clift_mlp weight */
+    const float* basis_dgrad;        /* ... and in clift_pack_linear_dgrad() layout (training only, else null) */
     clift_mlp rgb;                   /* render_appearance_mlp.mlp       (H1) */
     clift_mlp semantic;              /* render_semantic_mlp.mlp         (H2) */
     clift_mlp instance_fast;         /* render_instance_mlp.mlp         (H3) */
@@ -119,7 +124,7 @@ typedef struct {
     float* dist_ray;     /* [B]     per-ray distortion loss */
     float* points;       /* [B,3]   o + depth*d (forward_instance_feature, renderer:211-213) */
     float* weights;      /* [B,S]   dense compositing weights w_i (parity tests); null = keep in workspace */
-    int32_t save_for_backward; /* 1: keep per-sample rgb in the workspace for clift_render_backward */
+    int32_t save_for_backward; /* 1: keep what clift_render_backward needs in the workspace */
 } clift_render_out;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -127,6 +132,15 @@ int32_t clift_abi_version(void);
 const char* clift_last_error(void);
 /* Number of kernel launches issued by this library since load (all threads); bench.py's gpu_launches. */
 int64_t clift_launch_count(void);
+
+/* Per-stage device timing of clift_render_forward for bench.py's roofline figures.  When enabled, CUDA events
+ * are recorded on the caller's stream between the stages of every forward; clift_profile_stage_ms() waits for
+ * the last profiled forward and returns its stage durations in ms:
+ *   ms[0] march (sampling+density+scan+compositing)  ms[1] active-sample scan+compaction
+ *   ms[2] MLP heads                                   ms[3] per-ray epilogue
+ * Off by default (no events, no synchronisation).  Not thread-safe: one profiled stream at a time. */
+int32_t clift_profile_enable(int32_t on);
+int32_t clift_profile_stage_ms(float* ms4);
 
 /* ---- layout packing (one transpose kernel; used for parameters and, inverted, for gradients) --- */
 /* (1,C,H,W) -> [H][W][C]  and back.   tensoRF.py:99-106 layouts. */
@@ -137,6 +151,8 @@ int32_t clift_pack_linear(const float* w, const float* b, float* wt, float* bias
                           int32_t n_out, int32_t n_in, void* stream);
 int32_t clift_unpack_linear(const float* wt, const float* bias_pad, float* w, float* b,
                             int32_t n_out, int32_t n_in, void* stream);
+/* nn.Linear weight [out][in] -> zero padded copy [round_up(out,16)][dgrad_pad(in)] (data-gradient operand). */
+int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32_t n_out, int32_t n_in, void* stream);
 
 /* ---- R1-R4: util/ray.py:8-12,25-31,46-54,81-99 + dataset/base.py:211-219 ------------------------
  * rays[row*W+col] = [o(3), d(3), near, far]; intrinsics (3x3) and cam2world (4x4) are HOST row-major.
@@ -159,7 +175,7 @@ int32_t clift_density(const clift_field* field, const float* xyz, int64_t n, flo
  *  max_active bounds the compacted active-sample list (<= 0: worst case n_rays*n_samples); one call
  *  handles n_rays*n_samples < 2^31 - callers split larger frames.                                */
 int64_t clift_render_workspace_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays,
-                                     int64_t max_active);
+                                     int64_t max_active, int32_t save_for_backward);
 int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
                              const float* jitter, int64_t n_rays, int32_t add_background,
                              void* workspace, int64_t workspace_bytes, int64_t max_active,
@@ -169,8 +185,11 @@ int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* fie
 int32_t clift_render_stats(const void* workspace, int64_t* stats4, void* stream);
 
 /* Backward of clift_render_forward given dL/d(rgb, semantic, instance, dist_reg) (null = zero).
- * Re-marches the rays (recompute, nothing [B,S,K]-sized is saved), and accumulates (+=) into `grad`
- * in packed layout.  Semantic/instance gradients stop at the heads (stop_semantic_grad, renderer:144). */
+ * Must follow a forward with out->save_for_backward = 1 on the SAME workspace (which then holds the
+ * per-sample sigma / transmittance / weights, the compacted active-sample records and the per-layer
+ * head activations of those records).  Accumulates (+=) into `grad` in packed layout; null members are
+ * skipped.  Semantic/instance gradients stop at the heads (stop_semantic_grad=True, renderer:144-149):
+ * density factors receive gradient only through rgb and dist_reg.  The workspace is consumed. */
 int32_t clift_render_backward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
                               const float* jitter, int64_t n_rays, int32_t add_background,
                               void* workspace, int64_t workspace_bytes, int64_t max_active,
@@ -183,8 +202,9 @@ int32_t clift_render_backward(const clift_render_cfg* cfg, const clift_field* fi
  * (d loss / d features for upstream 1; only fast half / fast columns are non-zero).            */
 int32_t clift_slowfast_loss(const float* features, const int64_t* labels, const float* confidences,
                             int32_t n, int32_t d, float* loss, float* grad_features, void* stream);
-/* trainer:325-329: slow = slow*momentum + (1-momentum)*fast over a flat fp32 arena. */
-int32_t clift_ema_update(float* slow, const float* fast, int64_t n, float momentum, void* stream);
+/* trainer:325-329: slow = slow*momentum + (1-momentum)*fast over a flat fp32 arena.  `momentum` is the Python
+ * double: the reference rounds momentum and (1 - momentum) to fp32 separately, which needs the double here. */
+int32_t clift_ema_update(float* slow, const float* fast, int64_t n, double momentum, void* stream);
 /* ---- L2: model/loss/loss.py:62-82. features [N,D]. */
 int32_t clift_contrastive_loss(const float* features, const int64_t* labels, int32_t n, int32_t dim,
                                float temperature, float* loss, float* grad_features, void* stream);

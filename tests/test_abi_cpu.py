@@ -1,0 +1,94 @@
+"""CPU-side checks of the boundary: the C-ABI library loads here (no GPU) and exports every symbol the header
+declares; the Python host mirrors the reference's constructor/state_dict surface; compute calls refuse CPU tensors."""
+import os
+import re
+
+import pytest
+import torch
+
+import contrastive_lift_b200 as cl
+from contrastive_lift_b200 import lib as L
+from contrastive_lift_b200 import synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "clift_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(clift_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = header_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(L.SIGNATURES) == names, "lib.py SIGNATURES must list exactly the header's entry points"
+    assert lib.clift_abi_version() == L.ABI_VERSION
+
+
+def test_struct_sizes_match_header_layout():
+    import ctypes as C
+    assert C.sizeof(L.Mlp) == 4 + 4 * 9 + 8 * 8 * 3
+    assert C.sizeof(L.RenderCfg) == 4 * 9 + 4 * 6
+    assert C.sizeof(L.RenderOut) == 8 * 11 + 8
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(L.CliftError):
+        L.ptr(torch.zeros(4))
+    params = syn.make_field_params(0, (8, 8, 8), 4, 3)
+    model = cl.TensorVMSplit([8, 8, 8], num_semantic_classes=4, dim_feature_instance=6, use_semantic_mlp=True,
+                             use_instance_mlp=True, slow_fast_mode=True)
+    model.load_state_dict(params)
+    rend = cl.TensoRFRenderer(syn.default_aabb(), [8, 8, 8], semantic_weight_mode="softmax")
+    with pytest.raises(L.CliftError):
+        rend(model, syn.random_rays(0, 8), 1.0, False, False)
+    with pytest.raises(L.CliftError):
+        cl.slow_fast_loss(torch.zeros(8, 6), torch.zeros(8, dtype=torch.long), torch.zeros(8))
+
+
+def test_state_dict_keys_and_shapes_match_reference_checkpoint_layout():
+    grid = (12, 10, 14)
+    params = syn.make_field_params(1, grid, 21, 3)
+    model = cl.TensorVMSplit(list(grid), num_semantics_comps=(32, 32, 32), num_instance_comps=(32, 32, 32),
+                             num_semantic_classes=21, dim_feature_instance=6, use_semantic_mlp=True,
+                             use_instance_mlp=True, slow_fast_mode=True)
+    sd = model.state_dict()
+    assert sorted(sd) == sorted(params)
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(params[k].shape), k
+    rend = cl.TensoRFRenderer(syn.default_aabb(), list(grid), semantic_weight_mode="softmax")
+    assert sorted(rend.state_dict()) == ["bbox_aabb", "grid_dim", "inv_box_extent", "units"]
+    assert rend.n_samples == int((12 ** 0.5) / float(rend.step_size)) + 1
+
+
+def test_renderer_geometry_matches_oracle():
+    from oracle import clift_oracle as orc
+    for grid, ratio in (((128, 128, 128), 0.5), ((20, 24, 16), 0.37), ((192, 150, 171), 0.25)):
+        aabb = torch.tensor([[-1.0, -0.9, -1.0], [1.0, 0.8, 0.7]])
+        rend = cl.TensoRFRenderer(aabb, list(grid), step_ratio=0.5)
+        rend.update_step_ratio(ratio)
+        cfg = orc.RenderConfig(aabb=aabb, grid_dim=grid, step_ratio=ratio).refresh()
+        assert rend.n_samples == cfg.n_samples and torch.equal(rend.step_size, cfg.step_size)
+        assert torch.equal(rend.inv_box_extent, cfg.inv_extent) and torch.equal(rend.units, cfg.units)
+
+
+def test_optimizer_groups_follow_reference():
+    model = cl.TensorVMSplit([8, 8, 8], num_semantic_classes=4, dim_feature_instance=6, use_semantic_mlp=True,
+                             use_instance_mlp=True, slow_fast_mode=True)
+    g = model.get_optimizable_parameters(0.02, 0.001, weight_decay=1e-8)
+    assert [x["lr"] for x in g] == [0.02, 0.02, 0.02, 0.02, 0.001, 0.001, 0.001]
+    assert g[0]["weight_decay"] == 1e-8 and "weight_decay" not in g[1]
+    gi = model.get_optimizable_instance_parameters(0.02, 0.001, using_DINO=True)
+    assert len(gi) == 1 and len(list(gi[0]["params"])) == 8
+    assert len(model.get_optimizable_instance_parameters(0.02, 0.001, using_DINO=False)) == 2
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(L.CliftError):
+        cl.TensorVMSplit([8, 8, 8], num_semantic_classes=4, dim_feature_instance=6, use_semantic_mlp=False)
+    with pytest.raises(L.CliftError):
+        cl.TensoRFRenderer(syn.default_aabb(), [8, 8, 8], stop_semantic_grad=False)

@@ -1,0 +1,343 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the reference-pinned fixtures and the oracle.
+
+Tolerances (BASELINE.json north_star): ray ordering / sample indices / positions / in-box mask bit-exact;
+sigma, rgb, semantic, instance, depth within 1e-4 relative; losses within 1e-3.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import contrastive_lift_b200 as cl
+from contrastive_lift_b200 import lib as L
+from contrastive_lift_b200 import synthetic as syn
+from oracle import clift_oracle as orc
+import golden_util as gu
+import gpu_util as gpu
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+
+
+def tn(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def case(name):
+    fx = gu.load(name)
+    params, cfg, rays = gu.render_inputs(fx)
+    model, rend = gpu.build(params, cfg.grid_dim, int(fx["n_cls"]), int(fx["n_ins"]), bool(fx["slow_fast"]),
+                            bool(fx["softmax"]), cfg.aabb, float(fx["step_ratio"]))
+    assert rend.n_samples == int(fx["n_samples"])
+    assert float(rend.step_size) == float(fx["step_size"])
+    return fx, params, cfg, rays, model, rend
+
+
+def test_library_is_the_cuda_one():
+    lib = L.load()
+    assert lib.clift_abi_version() == L.ABI_VERSION
+    with pytest.raises(L.CliftError):
+        L.ptr(torch.zeros(3))          # CPU tensors are refused: there is no CPU path
+
+
+def test_gen_rays_matches_reference():
+    fx = gu.load("rays")
+    for i in range(3):
+        h, w = (int(v) for v in fx[f"cam{i}_hw"])
+        rays = cl.get_rays_checked(h, w, fx[f"cam{i}_K"], fx[f"cam{i}_c2w"]).cpu()
+        ref = tn(fx[f"cam{i}_rays"])
+        assert torch.equal(rays[:, :7], ref[:, :7]), "origins / directions / near must be bit-exact"
+        # far: sqrt.rn vs the CPU's vectorised sqrt -> at most 1 ulp on a small fraction of rays
+        ulp = (rays[:, 7].view(torch.int32) - ref[:, 7].view(torch.int32)).abs()
+        assert int(ulp.max()) <= 1 and float((ulp > 0).float().mean()) < 0.02
+
+
+def test_gen_rays_outside_sphere_raises():
+    k, c2w = syn.camera(8, 8, position=(0.0, 0.0, -3.0))
+    with pytest.raises(AssertionError):
+        cl.get_rays_checked(8, 8, k.numpy(), c2w.numpy())
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_sampling_bit_exact(name):
+    fx, params, cfg, rays, model, rend = case(name)
+    lib = L.load()
+    B, S = rays.shape[0], rend.n_samples
+    for jit_key in (None, "trn_jitter"):
+        jitter = tn(fx[jit_key]).reshape(-1).cuda().contiguous() if jit_key else None
+        z = torch.empty((B, S), device="cuda")
+        xyz = torch.empty((B, S, 3), device="cuda")
+        inbox = torch.empty((B, S), dtype=torch.uint8, device="cuda")
+        rc = rend._cfg(model, L.HEAD_ALL)
+        L.check(lib.clift_sample_points(C.byref(rc), L.ptr(rays.cuda()), L.ptr(jitter), B, L.ptr(z), L.ptr(xyz),
+                                        L.ptr(inbox), L.stream_ptr(z.device)))
+        if jit_key is None:
+            ref_z, ref_xyz, ref_in = tn(fx["inf_z"]), tn(fx["inf_xyz"]), tn(fx["inf_inbox"])
+        else:
+            pts, ref_z, ref_in = orc.sample_points(rays, cfg.aabb, cfg.n_samples, cfg.step_size, tn(fx[jit_key]))
+            ref_xyz = orc.normalize_points(pts, cfg.aabb, cfg.inv_extent)
+        assert torch.equal(z.cpu(), ref_z.expand(B, -1))
+        assert torch.equal(xyz.cpu(), ref_xyz)
+        assert torch.equal(inbox.cpu().bool(), ref_in)
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_density_matches_reference(name):
+    fx, params, cfg, rays, model, rend = case(name)
+    inbox = tn(fx["inf_inbox"])
+    xyz = tn(fx["inf_xyz"])[inbox]
+    sigma = model.compute_density(xyz.cuda()).cpu()
+    ref = tn(fx["inf_sigma"])[inbox]
+    assert torch.allclose(sigma, ref, rtol=REL, atol=1e-7), float((sigma - ref).abs().max())
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_render_inference_golden(name):
+    fx, params, cfg, rays, model, rend = case(name)
+    with torch.no_grad():
+        rgb, sem, ins, depth, feats, dist = rend(model, rays.cuda(), 1.0, False, False)
+    assert feats.shape == (1, 1) and rgb.grad_fn is None
+    n_act, n_in, overflow, _ = rend.last_stats("cuda:0")
+    assert n_in == int(fx["inf_inbox"].sum()), "in-box sample count must be exact"
+    flips = abs(n_act - int(fx["inf_active"].sum()))
+    assert flips <= 2 and overflow == 0, f"active-mask flips {flips}"
+    assert gpu.rel_err(rgb, tn(fx["inf_rgb"])) < REL
+    assert gpu.rel_err(ins, tn(fx["inf_ins"])) < REL
+    assert gpu.rel_err(depth, tn(fx["inf_depth"])) < REL
+    assert gpu.rel_err(dist, tn(fx["inf_dist"])) < REL
+    ref_sem = tn(fx["inf_sem"])
+    if bool(fx["softmax"]):      # log-probabilities: compare in probability space and absolutely in log space
+        assert gpu.rel_err(sem.exp(), ref_sem.exp()) < REL
+        assert float((sem.cpu() - ref_sem).abs().max()) < 2e-3
+    else:
+        assert gpu.rel_err(sem, ref_sem) < REL
+    assert gpu.rel_err(rend.last_opacity, tn(fx["inf_weight"]).sum(-1)) < REL
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_dense_weights_match(name):
+    """clift_render_forward's optional [B,S] weight dump against the reference's raw_to_alpha output."""
+    fx, params, cfg, rays, model, rend = case(name)
+    lib = L.load()
+    B, S = rays.shape[0], rend.n_samples
+    pk = model.packed(False)
+    rc = rend._cfg(model, 0)
+    out = L.RenderOut()
+    w = torch.empty((B, S), device="cuda")
+    depth, opa = torch.empty((B,), device="cuda"), torch.empty((B,), device="cuda")
+    out.weights, out.depth, out.opacity = L.ptr(w), L.ptr(depth), L.ptr(opa)
+    nb = lib.clift_render_workspace_bytes(C.byref(rc), C.byref(pk.field), B, 0, 0)
+    ws = torch.empty((nb,), dtype=torch.uint8, device="cuda")
+    L.check(lib.clift_render_forward(C.byref(rc), C.byref(pk.field), L.ptr(rays.cuda()), None, B, 0, L.ptr(ws), nb, 0,
+                                     C.byref(out), L.stream_ptr(w.device)))
+    ref = tn(fx["inf_weight"])
+    assert float((w.cpu() - ref).abs().max()) < REL * float(ref.max())
+    act = (w.cpu() > 1e-4)
+    assert int((act != tn(fx["inf_active"])).sum()) <= 2
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+@pytest.mark.parametrize("tag,seed", [("trn", 7), ("trn2", 8)])
+def test_render_training_forward_rng_parity(name, tag, seed):
+    """is_train=True: the shim must draw jitter and the background coin like the reference (renderer:807-810,164)."""
+    fx, params, cfg, rays, model, rend = case(name)
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        rgb, sem, ins, depth, _, dist = rend(model, rays.cuda(), 1.0, False, True)
+    assert gpu.rel_err(rgb, tn(fx[f"{tag}_rgb"])) < REL
+    assert gpu.rel_err(ins, tn(fx[f"{tag}_ins"])) < REL
+    assert gpu.rel_err(depth, tn(fx[f"{tag}_depth"])) < REL
+    assert gpu.rel_err(dist, tn(fx[f"{tag}_dist"])) < REL
+    ref_sem = tn(fx[f"{tag}_sem"])
+    assert gpu.rel_err(sem.exp() if bool(fx["softmax"]) else sem, ref_sem.exp() if bool(fx["softmax"]) else ref_sem) < REL
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_instance_and_segment_golden(name):
+    fx, params, cfg, rays, model, rend = case(name)
+    with torch.no_grad():
+        torch.manual_seed(11)
+        ins, pts = rend.forward_instance_feature(model, rays.cuda(), 1.0, True)
+        torch.manual_seed(12)
+        seg = rend.forward_segment_feature(model, rays.cuda(), 1.0, True)
+    assert gpu.rel_err(ins, tn(fx["insf_map"])) < REL
+    assert gpu.rel_err(pts, tn(fx["insf_pts"])) < REL
+    ref = tn(fx["segf_map"])
+    assert gpu.rel_err(seg.exp() if bool(fx["softmax"]) else seg, ref.exp() if bool(fx["softmax"]) else ref) < REL
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+@pytest.mark.parametrize("tag,seed", [("trn", 7), ("trn2", 8)])
+def test_render_training_gradients_golden(name, tag, seed):
+    fx, params, cfg, rays, model, rend = case(name)
+    torch.manual_seed(seed)
+    out = rend(model, rays.cuda(), 1.0, False, True)
+    assert out[0].grad_fn is not None and out[3].grad_fn is None       # depth carries no grad (renderer:173)
+    loss = gu.train_loss(out, fx, tag)
+    assert abs(float(loss) - float(fx[f"{tag}_loss"])) < 1e-3 * abs(float(fx[f"{tag}_loss"]))
+    loss.backward()
+    worst = {}
+    for k, p in model.named_parameters():
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        dig = gu.grad_digest(g)
+        ref = fx[f"{tag}_gdig/{k}"]
+        scale = max(float(np.abs(ref[3:]).max()), 1e-12)
+        # head of the digest: sum, L1, L2^2 ; tail: strided samples
+        assert abs(dig[1] - ref[1]) <= 2e-3 * max(ref[1], 1e-12), (k, dig[:3], ref[:3])
+        assert abs(dig[2] - ref[2]) <= 4e-3 * max(ref[2], 1e-20), (k, dig[:3], ref[:3])
+        err = float(np.abs(dig[3:] - ref[3:]).max()) / scale
+        worst[k] = err
+        assert err < 2e-3, (k, err)
+        if f"{tag}_grad/{k}" in fx.files:
+            full = tn(fx[f"{tag}_grad/{k}"])
+            assert gpu.rel_err(g, full) < 2e-3, k
+    # instance head gets gradient only because this test's loss touches instance_map
+    assert model.render_instance_mlp.mlp[0].weight.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES)
+def test_instance_pass_gradients_reach_only_instance_head(name):
+    fx, params, cfg, rays, model, rend = case(name)
+    torch.manual_seed(11)
+    ins, pts = rend.forward_instance_feature(model, rays.cuda(), 1.0, True)
+    assert ins.grad_fn is not None and pts.grad_fn is None
+    w = torch.linspace(-1, 1, ins.numel(), device="cuda").view_as(ins)
+    (ins * w).sum().backward()
+    # oracle gradient for the same scalar
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    oi, _ = orc.render_instance_feature(p, cfg, rays, tn(fx["insf_jitter"]))
+    (oi * w.cpu()).sum().backward()
+    for k, prm in model.named_parameters():
+        if k.startswith("render_instance_mlp"):
+            assert gpu.rel_err(prm.grad, p[k].grad) < 2e-3, k
+        else:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
+
+
+def test_losses_golden():
+    fx = gu.load("losses")
+    ci = 0
+    while f"sf{ci}_feats" in fx.files:
+        feats = tn(fx[f"sf{ci}_feats"]).cuda().requires_grad_(True)
+        loss = cl.slow_fast_loss(feats, tn(fx[f"sf{ci}_labels"]).cuda(), tn(fx[f"sf{ci}_conf"]).cuda())
+        ref = float(fx[f"sf{ci}_loss"])
+        if np.isnan(ref):
+            assert torch.isnan(loss)
+        else:
+            assert abs(float(loss) - ref) <= 1e-3 * max(abs(ref), 1e-6), (ci, float(loss), ref)
+            if f"sf{ci}_grad" in fx.files and ref != 0.0:
+                loss.backward()
+                assert gpu.rel_err(feats.grad, tn(fx[f"sf{ci}_grad"])) < 1e-3, ci
+        ci += 1
+    assert ci == 6
+    ci = 0
+    while f"ct{ci}_feats" in fx.files:
+        feats = tn(fx[f"ct{ci}_feats"]).cuda().requires_grad_(True)
+        loss = cl.contrastive_loss(feats, tn(fx[f"ct{ci}_labels"]).cuda(), float(fx[f"ct{ci}_temp"]))
+        ref = float(fx[f"ct{ci}_loss"])
+        assert abs(float(loss) - ref) <= 1e-3 * abs(ref)
+        loss.backward()
+        assert gpu.rel_err(feats.grad, tn(fx[f"ct{ci}_grad"])) < 1e-3
+        ci += 1
+    assert ci == 3
+
+
+def test_ema_bit_exact_and_tv_golden():
+    fx = gu.load("losses")
+    p = syn.make_field_params(int(fx["ema_seed"]), (8, 8, 8), 4, 3)
+    slow = [p[f"render_instance_mlp.slow_mlp.{k}.{t}"].clone().cuda() for k in (0, 2, 4, 6) for t in ("weight", "bias")]
+    fast = [p[f"render_instance_mlp.mlp.{k}.{t}"].cuda() for k in (0, 2, 4, 6) for t in ("weight", "bias")]
+    cl.ema_update(slow, fast, 0.9)
+    assert torch.equal(slow[-2].cpu(), tn(fx["ema_last_weight"])) and torch.equal(slow[1].cpu(), tn(fx["ema_first_bias"]))
+    grid = tuple(int(v) for v in fx["tv_grid"])
+    p2 = syn.make_field_params(int(fx["tv_seed"]), grid, 3, 3)
+    plane0 = p2["density_plane.0"].cuda()
+    assert abs(float(cl.plane_tv(plane0)) - float(fx["tv_plane0"])) <= 1e-5 * float(fx["tv_plane0"])
+    model, _ = gpu.build(p2, grid, 3, 3, True, True, syn.default_aabb(), 0.5)
+
+    class Cfg:
+        lambda_tv_density, lambda_tv_appearance, lambda_tv_semantics, lambda_tv_instances = 0.1, 0.01, 0.0, 0.0
+        late_semantic_optimization, instance_optimization_epoch = 0, 0
+    tot = model.total_tv_loss(None, Cfg, 5)
+    assert abs(float(tot) - float(fx["tv_total"])) <= 1e-5 * float(fx["tv_total"])
+    tot.backward()
+    assert gpu.rel_err(model.density_plane[1].grad, tn(fx["tv_grad_density_plane.1"])) < 1e-4
+
+
+def test_edge_cases_empty_and_missing_rays():
+    fx, params, cfg, rays, model, rend = case("render_a")
+    with torch.no_grad():
+        out = rend(model, rays[:0].cuda(), 1.0, False, False)
+        assert out[0].shape == (0, 3) and out[1].shape[0] == 0
+        # rays that miss the box entirely: zero opacity, rgb 0 (no background), depth 0
+        miss = rays[:4].clone()
+        miss[:, 0:3] = torch.tensor([0.0, 0.0, -0.95])
+        miss[:, 3:6] = torch.tensor([0.0, 0.0, -1.0])
+        miss[:, 7] = 0.02
+        rgb, sem, ins, depth, _, dist = rend(model, miss.cuda(), 1.0, False, False)
+        ref = orc.render_forward(params, cfg, miss)
+        assert gpu.rel_err(rgb, ref[0]) < REL or float(ref[0].abs().max()) == 0.0
+        assert float(rgb.abs().max()) <= float(ref[0].abs().max()) + 1e-6
+        assert torch.allclose(depth.cpu(), ref[3], atol=1e-6)
+        assert torch.allclose(sem.cpu(), ref[1], atol=1e-4)
+        # a single ray, and a ray count that is not a multiple of the warp/CTA shape
+        one = rend(model, rays[:1].cuda(), 1.0, False, False)
+        assert gpu.rel_err(one[0], tn(fx["inf_rgb"])[:1]) < 5 * REL
+        odd = rend(model, rays[:37].cuda(), 1.0, False, False)
+        assert gpu.rel_err(odd[0], tn(fx["inf_rgb"])[:37]) < REL
+
+
+def test_active_list_overflow_is_reported():
+    fx, params, cfg, rays, model, rend = case("render_a")
+    rend.max_active_per_ray = 1
+    rend.check_overflow = False
+    with torch.no_grad():
+        rend(model, rays.cuda(), 1.0, False, False)
+    n_act, _, overflow, _ = rend.last_stats("cuda:0")
+    assert overflow == 1 and n_act > rays.shape[0]
+    # with the check on, the shim repeats the call at the exact size and the result is the full one
+    rend.check_overflow = True
+    with torch.no_grad():
+        out = rend(model, rays.cuda(), 1.0, False, False)
+    assert rend.last_stats("cuda:0")[2] == 0
+    assert gpu.rel_err(out[0], tn(fx["inf_rgb"])) < REL
+
+
+def test_full_size_properties():
+    """BASELINE-size frame (400x400, S=512, all heads): properties that need no CPU oracle run."""
+    grid = (128, 128, 128)
+    params = syn.make_field_params(0, grid, 21, 3)
+    aabb = syn.default_aabb()
+    ratio = orc.ratio_for_samples(aabb, grid, 512)
+    model, rend = gpu.build(params, grid, 21, 3, True, True, aabb, ratio)
+    assert rend.n_samples == 512
+    k, c2w = syn.camera(400, 400)
+    rays = cl.get_rays_checked(400, 400, k.numpy(), c2w.numpy())
+    with torch.no_grad():
+        full = rend(model, rays, 1.0, False, False)
+        n_act, n_in, overflow, _ = rend.last_stats("cuda:0")
+        assert overflow == 0 and n_act > 0 and n_in > n_act
+        # ray independence: any chunking (the reference's chunk=2048 loop) gives the same per-ray results
+        idx = torch.arange(0, rays.shape[0], 7, device="cuda")
+        part = rend(model, rays[idx].contiguous(), 1.0, False, False)
+        for a, b in zip(full[:4], part[:4]):
+            assert torch.allclose(a[idx], b, rtol=1e-5, atol=1e-6)
+        # run-to-run reproducibility
+        again = rend(model, rays, 1.0, False, False)
+        assert torch.equal(full[0], again[0]) and torch.equal(full[3], again[3])
+    rgb, sem, ins, depth = full[:4]
+    assert float(rgb.min()) >= 0.0 and float(rgb.max()) <= 1.0
+    opa = rend.last_opacity
+    assert float(opa.max()) <= 1.0 + 1e-4 and float(opa.mean()) > 0.5
+    # softmax-mode semantics are log-probabilities of a normalised distribution wherever the ray hit something
+    hit = opa > 0.5
+    assert torch.allclose(sem[hit].exp().sum(-1), torch.ones_like(opa[hit]), atol=1e-3)
+    # spot-check 64 rays of the full frame against the CPU oracle
+    pick = torch.linspace(0, rays.shape[0] - 1, 64).long()
+    cfg = orc.RenderConfig(aabb=aabb, grid_dim=grid, step_ratio=ratio).refresh()
+    ref = orc.render_forward(params, cfg, rays[pick.cuda()].cpu())
+    assert gpu.rel_err(rgb[pick.cuda()], ref[0]) < REL
+    assert gpu.rel_err(ins[pick.cuda()], ref[2]) < REL
+    assert gpu.rel_err(depth[pick.cuda()], ref[3]) < REL
+    assert gpu.rel_err(sem[pick.cuda()].exp(), ref[1].exp()) < REL
