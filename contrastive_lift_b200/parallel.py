@@ -1,0 +1,75 @@
+"""Data-parallel plumbing for the render path: one process per GPU, parameters replicated,
+rays sharded, gradients mean-all-reduced once per backward over a flat fp32 arena.
+
+This reproduces what the reference gets from Lightning's DDPStrategy (trainer/__init__.py:95-108): each rank renders
+its own rays, every ``manual_backward`` (trainer:198, :220) is followed by a mean of the gradients over ranks.  The
+path has no other exchange step (rays are independent; the slow-fast loss keeps whole images on one rank, as DDP's
+DistributedSampler does), so torch.distributed's NCCL all-reduce over NVLink is the only collective.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of ``n`` rays owned by ``rank`` (ray order is preserved across ranks)."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_rays(rays: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    b, e = shard_range(rays.shape[0], rank, world)
+    return rays[b:e]
+
+
+def gather_rays_output(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Inverse of shard_rays for an output map [n_local, K]: all-gather with the shard sizes of shard_range()."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    parts = [local.new_empty((e - b,) + tuple(local.shape[1:])) for b, e in sizes]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts, 0)
+
+
+@torch.no_grad()
+def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, average: bool = True) -> int:
+    """Sum (then 1/world) every parameter's ``.grad`` across ranks through ONE flat buffer / one collective.
+
+    Parameters whose grad is None on this rank (heads not evaluated in this pass - the reference needs
+    ``find_unused_parameters=True`` for the same reason) contribute zeros and stay None.  Returns the number of
+    bytes reduced."""
+    plist: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+    if not plist or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    dev = plist[0].device
+    total = sum(p.numel() for p in plist)
+    flat = torch.zeros((total,), dtype=torch.float32, device=dev)
+    off = 0
+    for p in plist:
+        if p.grad is not None:
+            flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+        off += p.numel()
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        flat.mul_(1.0 / dist.get_world_size(group))
+    off = 0
+    for p in plist:
+        if p.grad is not None:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+        off += p.numel()
+    return total * 4
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Replicate rank ``src``'s parameters and buffers (what DDP does at construction)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
