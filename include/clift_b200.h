@@ -154,6 +154,14 @@ int32_t clift_unpack_linear(const float* wt, const float* bias_pad, float* w, fl
 /* nn.Linear weight [out][in] -> zero padded copy [round_up(out,16)][dgrad_pad(in)] (data-gradient operand). */
 int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32_t n_out, int32_t n_in, void* stream);
 
+/* Tensor-core operand of one nn.Linear for the tcgen05 head kernels: W [out][in] -> tf32-exact (hi, lo) pairs in
+ * 16-row K slabs, each slab [hi|lo][4 k-chunks][n_pad=round_up(out,32)][4]; clift_tc_weight_floats() sizes it. */
+int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in);
+int32_t clift_pack_linear_tc(const float* w, float* dst, int32_t n_out, int32_t n_in, void* stream);
+/* Bring-up / parity entry for the tensor-core GEMM core: out[128][round_up(n_out,32)] = a[128][k] * W^T with the
+ * 3xTF32 split (one CTA).  Used by tests only. */
+int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, void* stream);
+
 /* ---- R1-R4: util/ray.py:8-12,25-31,46-54,81-99 + dataset/base.py:211-219 ------------------------
  * rays[row*W+col] = [o(3), d(3), near, far]; intrinsics (3x3) and cam2world (4x4) are HOST row-major.
  * *bad_rays (device int32) counts rays whose sphere determinant is negative (the reference asserts). */
