@@ -204,9 +204,20 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         if (heads & CLIFT_HEAD_SEMANTIC) CLIFT_CUDA(cudaMemsetAsync(out->semantic_raw, 0, n_rays * C * sizeof(float), stream));
         if (heads & CLIFT_HEAD_INSTANCE) CLIFT_CUDA(cudaMemsetAsync(out->instance, 0, n_rays * DI * sizeof(float), stream));
         profile_mark(2, stream);
-        rc = launch_heads_forward(cfg, field, rays, ws, max_active, n_rays, (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr,
-                                  (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr,
-                                  (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr, save ? &lay : nullptr, stream);
+        float* o_rgb = (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr;
+        float* o_sem = (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr;
+        float* o_ins = (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr;
+        bool use_tc = false;
+        if (cfg->head_path == CLIFT_HEADS_TENSOR) {
+            CLIFT_CHECK_SUPPORTED(!save, "the tensor-core head path does not record the training stash (use CLIFT_HEADS_AUTO/FMA)");
+            use_tc = true;
+        } else if (cfg->head_path == CLIFT_HEADS_AUTO) {
+            use_tc = !save && heads_tc_available(field, heads);
+        }
+        if (use_tc)
+            rc = launch_heads_forward_tc(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream);
+        else
+            rc = launch_heads_forward(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, save ? &lay : nullptr, stream);
         if (rc) return rc;
     } else {
         profile_mark(2, stream);

@@ -24,8 +24,12 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemALo = 256;      // column offset of A_lo
 
 struct TcSmem {
-    float* a_hi;        // [kTcMaxK/4][128][4]
+    float* a_hi;        // [kTcMaxK/4][128][4]   (also the [c][128] scratch of the final epilogues)
     float* w;           // [kTcStages][kTcStageFloats]
+    float* feat;        // [32][128] appearance features of the tile (rgb input construction)
+    int* ray;           // [128]
+    int* runs;          // [129]
+    int* n_runs;        // [1]
     uint64_t* full;     // [kTcStages]
     uint64_t* empty;    // [kTcStages]
     uint64_t* bar_a;    // A operand ready (row threads -> MMA)
@@ -33,13 +37,19 @@ struct TcSmem {
     uint32_t* tmem_base;
 };
 
-constexpr size_t kTcSmemBytes = (size_t)kTcMaxK * kTcRows * 4 + (size_t)kTcStages * kTcStageFloats * 4 + 256;
+constexpr int kTcFeatRows = 32;
+constexpr size_t kTcSmemBytes = (size_t)kTcMaxK * kTcRows * 4 + (size_t)kTcStages * kTcStageFloats * 4 +
+                                (size_t)kTcFeatRows * kTcRows * 4 + (2 * kTcRows + 8) * 4 + 256;
 
 __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
     TcSmem s;
     s.a_hi = reinterpret_cast<float*>(raw);
     s.w = s.a_hi + kTcMaxK * kTcRows;
-    s.full = reinterpret_cast<uint64_t*>(s.w + kTcStages * kTcStageFloats);
+    s.feat = s.w + kTcStages * kTcStageFloats;
+    s.ray = reinterpret_cast<int*>(s.feat + kTcFeatRows * kTcRows);
+    s.runs = s.ray + kTcRows;
+    s.n_runs = s.runs + kTcRows + 1;
+    s.full = reinterpret_cast<uint64_t*>(s.n_runs + 7);
     s.empty = s.full + kTcStages;
     s.bar_a = s.empty + kTcStages;
     s.bar_d = s.bar_a + 1;
@@ -178,6 +188,299 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
     if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// production kernel: all heads of one 128-record tile per iteration, persistent over tiles
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTcMaxGemms = 24;
+
+struct TcHeadsParams {
+    const float4* rec_pos;
+    const int32_t* rec_ray;
+    const unsigned long long* stats;
+    long long cap;
+    const float* rays;
+    FactorParams app;
+    int dim_app, pe_view, pe_feat, pe_sem, pe_ins;
+    int n_cls, d_ins, slow_fast, softmax, heads;
+    // GEMM schedule of one tile, in issue order: semantic | instance fast | instance slow | basis | rgb
+    int n_gemms;
+    TcGemm g[kTcMaxGemms];
+    const float* bias[kTcMaxGemms];   // [n_pad] or null
+    int n_sem, n_ins, n_rgb;          // layers per stack (0 = head off)
+    float* rgb_raw;
+    float* sem_raw;
+    float* ins;
+};
+
+// hidden-layer epilogue: D -> +bias -> ReLU -> next layer's A operand
+__device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, uint32_t lane_base, int row, int n_pad, const float* __restrict__ bias) {
+    for (int c0 = 0; c0 < n_pad; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_base + (uint32_t)c0, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f), 0.0f);
+        tc_put8(s, lane_base, row, c0, v);
+        tc_put8(s, lane_base, row, c0 + 8, v + 8);
+    }
+}
+
+// final-layer epilogue: D (+bias) -> scratch[c][row] for c < n_out (scratch = a_hi region, K-major like the FFMA kernel)
+__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, uint32_t lane_base, int row, int n_out, const float* __restrict__ bias) {
+    for (int c0 = 0; c0 < n_out; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(lane_base + (uint32_t)c0, v);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < n_out) s.a_hi[(size_t)(c0 + i) * kTcRows + row] = v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f);
+    }
+}
+
+// xyz (+ sin/cos PE, dimension-major frequency-minor) -> A operand, zero padded to a multiple of 8
+__device__ __forceinline__ void tc_build_xyz(const TcSmem& s, uint32_t lane_base, int row, const float4& p, int pe) {
+    const int n_in = 3 + 6 * pe;
+    const float xyz[3] = {p.x, p.y, p.z};
+    for (int k0 = 0; k0 < n_in; k0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = k0 + i;
+            float x = 0.0f;
+            if (r < 3) {
+                x = r == 0 ? xyz[0] : (r == 1 ? xyz[1] : xyz[2]);
+            } else if (r < n_in) {
+                const int j = (r - 3) % (3 * pe);
+                const int d = j / pe;
+                const float arg = (d == 0 ? xyz[0] : (d == 1 ? xyz[1] : xyz[2])) * (float)(1 << (j % pe));
+                x = (r - 3 < 3 * pe) ? sinf(arg) : cosf(arg);
+            }
+            v[i] = x;
+        }
+        tc_put8(s, lane_base, row, k0, v);
+    }
+}
+
+// 128 row threads: sum rows [0,nch) of scratch over each ray run (fixed order) and add into dst[ray*stride + col0 + c]
+__device__ __forceinline__ void tc_reduce_runs(const TcSmem& s, int rt, int nch, float* __restrict__ dst, int stride, int col0) {
+    tc::named_bar_sync(1, kTcRows);
+    const int n_runs = *s.n_runs;
+    for (int idx = rt; idx < n_runs * nch; idx += kTcRows) {
+        const int r = idx / nch, c = idx - r * nch;
+        const int m0 = s.runs[r], m1 = s.runs[r + 1];
+        float acc = 0.0f;
+        for (int m = m0; m < m1; ++m) acc += s.a_hi[(size_t)c * kTcRows + m];
+        atomicAdd(dst + (int64_t)s.ray[m0] * stride + col0 + c, acc);
+    }
+    tc::named_bar_sync(1, kTcRows);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const __grid_constant__ TcHeadsParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem s = carve_tc_smem(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTcStages; ++i) {
+            tc::mbar_init(&s.full[i], 1);
+            tc::mbar_init(&s.empty[i], 1);
+        }
+        tc::mbar_init(s.bar_a, 1);
+        tc::mbar_init(s.bar_d, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(s.tmem_base, kTmemCols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s.tmem_base;
+    const long long n_act = min((long long)P.stats[0], P.cap);
+    const long long n_tiles = (n_act + kTcRows - 1) / kTcRows;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            PipeState ps;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int gi = 0; gi < P.n_gemms; ++gi) tc_produce(s, P.g[gi], ps);
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            PipeState ps;
+            uint32_t count = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int gi = 0; gi < P.n_gemms; ++gi, ++count) tc_issue(s, P.g[gi], ps, tmem, count & 1);
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int rt = threadIdx.x - 64;                      // 0..127 among the row threads
+        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+        uint32_t count = 0;                                    // GEMMs consumed so far (bar_d parity)
+        auto wait_d = [&]() {
+            tc::mbar_wait(s.bar_d, count & 1);
+            ++count;
+            tc::fence_after_sync();
+        };
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long base = tile * kTcRows;
+            const int nv = (int)min((long long)kTcRows, n_act - base);
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            int ray = -1;
+            if (row < nv) {
+                p = P.rec_pos[base + row];
+                ray = P.rec_ray[base + row];
+            }
+            s.ray[row] = ray;
+            tc::named_bar_sync(1, kTcRows);
+            if (warp == 2) {   // run starts, in record order
+                int n = 0;
+                for (int w4 = 0; w4 < kTcRows / 32; ++w4) {
+                    const int m = w4 * 32 + lane;
+                    const bool start = m < nv && (m == 0 || s.ray[m] != s.ray[m - 1]);
+                    const unsigned bits = __ballot_sync(0xffffffffu, start);
+                    if (start) s.runs[n + __popc(bits & ((1u << lane) - 1u))] = m;
+                    n += __popc(bits);
+                }
+                if (lane == 0) {
+                    s.runs[n] = nv;
+                    *s.n_runs = n;
+                }
+            }
+            int gi = 0;
+            if (P.n_sem > 0) {
+                tc_build_xyz(s, lane_base, row, p, P.pe_sem);
+                tc_publish_a(s);
+                for (int l = 0; l < P.n_sem; ++l, ++gi) {
+                    wait_d();
+                    if (l + 1 < P.n_sem) {
+                        tc_epilogue_hidden(s, lane_base, row, P.g[gi].n_pad, P.bias[gi]);
+                        tc_publish_a(s);
+                    } else {
+                        tc_epilogue_final(s, lane_base, row, P.n_cls, P.bias[gi]);
+                    }
+                }
+                // softmax over the thread's own column of the scratch, then the compositing weight
+                if (P.softmax) {
+                    float mx = -INFINITY;
+                    for (int c = 0; c < P.n_cls; ++c) mx = fmaxf(mx, s.a_hi[(size_t)c * kTcRows + row]);
+                    float tot = 0.0f;
+                    for (int c = 0; c < P.n_cls; ++c) {
+                        const float e = expf(s.a_hi[(size_t)c * kTcRows + row] - mx);
+                        s.a_hi[(size_t)c * kTcRows + row] = e;
+                        tot += e;
+                    }
+                    for (int c = 0; c < P.n_cls; ++c) s.a_hi[(size_t)c * kTcRows + row] = (s.a_hi[(size_t)c * kTcRows + row] / tot) * p.w;
+                } else {
+                    for (int c = 0; c < P.n_cls; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
+                }
+                tc_reduce_runs(s, rt, P.n_cls, P.sem_raw, P.n_cls, 0);
+            }
+            if (P.n_ins > 0) {
+                const int width = P.d_ins * (P.slow_fast ? 2 : 1);
+                for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
+                    tc_build_xyz(s, lane_base, row, p, P.pe_ins);
+                    tc_publish_a(s);
+                    for (int l = 0; l < P.n_ins; ++l, ++gi) {
+                        wait_d();
+                        if (l + 1 < P.n_ins) {
+                            tc_epilogue_hidden(s, lane_base, row, P.g[gi].n_pad, P.bias[gi]);
+                            tc_publish_a(s);
+                        } else {
+                            tc_epilogue_final(s, lane_base, row, P.d_ins, P.bias[gi]);
+                        }
+                    }
+                    for (int c = 0; c < P.d_ins; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
+                    tc_reduce_runs(s, rt, P.d_ins, P.ins, width, net * P.d_ins);
+                }
+            }
+            if (P.n_rgb > 0) {
+                const FactorParams& f = P.app;
+                // appearance gather: 18 taps x comps channels -> plane*line products, 8 channels per put
+                const float xs[3] = {p.x, p.y, p.z};
+#pragma unroll 1
+                for (int mode = 0; mode < 3; ++mode) {
+                    const Tap2 t2 = make_tap2(xs[mode_a(mode)], xs[mode_b(mode)], f.pw[mode], f.ph[mode]);
+                    const Tap1 t1 = make_tap1(xs[mode_v(mode)], f.ll[mode]);
+#pragma unroll
+                    for (int v8 = 0; v8 < NV * 2; ++v8) {
+                        const int ch = v8 * 8;
+                        const float4 pa = plane_tap(f.plane[mode], t2, f.pw[mode], f.comps, ch);
+                        const float4 la = line_tap(f.line[mode], t1, f.comps, ch);
+                        const float4 pb = plane_tap(f.plane[mode], t2, f.pw[mode], f.comps, ch + 4);
+                        const float4 lb = line_tap(f.line[mode], t1, f.comps, ch + 4);
+                        const float v[8] = {pa.x * la.x, pa.y * la.y, pa.z * la.z, pa.w * la.w,
+                                            pb.x * lb.x, pb.y * lb.y, pb.z * lb.z, pb.w * lb.w};
+                        tc_put8(s, lane_base, row, mode * f.comps + ch, v);
+                    }
+                }
+                tc_publish_a(s);
+                wait_d();   // basis GEMM: features in D columns [0, dim_app)
+                const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
+                for (int c0 = 0; c0 < A; c0 += 16) {
+                    float v[16];
+                    tc::tmem_ld16(lane_base + (uint32_t)c0, v);
+                    tc::tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < A) s.feat[(size_t)(c0 + i) * kTcRows + row] = v[i];
+                }
+                ++gi;
+                float dir[3] = {0.f, 0.f, 1.f};
+                if (ray >= 0) {
+                    dir[0] = __ldg(P.rays + (int64_t)ray * 8 + 3);
+                    dir[1] = __ldg(P.rays + (int64_t)ray * 8 + 4);
+                    dir[2] = __ldg(P.rays + (int64_t)ray * 8 + 5);
+                }
+                // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418)
+                const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
+                for (int k0 = 0; k0 < n_in; k0 += 8) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = k0 + i;
+                        float x = 0.0f;
+                        if (r < A) {
+                            x = s.feat[(size_t)r * kTcRows + row];
+                        } else if (r < o_sf) {
+                            x = r - A == 0 ? dir[0] : (r - A == 1 ? dir[1] : dir[2]);
+                        } else if (r < o_sd) {
+                            const int j = (r < o_cf) ? r - o_sf : r - o_cf;
+                            const float arg = s.feat[(size_t)(j / pf) * kTcRows + row] * (float)(1 << (j % pf));
+                            x = (r < o_cf) ? sinf(arg) : cosf(arg);
+                        } else if (r < n_in) {
+                            const int j = (r < o_cd) ? r - o_sd : r - o_cd;
+                            const int d = j / pv;
+                            const float arg = (d == 0 ? dir[0] : (d == 1 ? dir[1] : dir[2])) * (float)(1 << (j % pv));
+                            x = (r < o_cd) ? sinf(arg) : cosf(arg);
+                        }
+                        v[i] = x;
+                    }
+                    tc_put8(s, lane_base, row, k0, v);
+                }
+                tc_publish_a(s);
+                for (int l = 0; l < P.n_rgb; ++l, ++gi) {
+                    wait_d();
+                    if (l + 1 < P.n_rgb) {
+                        tc_epilogue_hidden(s, lane_base, row, P.g[gi].n_pad, P.bias[gi]);
+                        tc_publish_a(s);
+                    } else {
+                        tc_epilogue_final(s, lane_base, row, 3, P.bias[gi]);
+                    }
+                }
+                for (int c = 0; c < 3; ++c) {
+                    const float x = s.a_hi[(size_t)c * kTcRows + row];
+                    s.a_hi[(size_t)c * kTcRows + row] = (1.0f / (1.0f + expf(-x))) * p.w;
+                }
+                tc_reduce_runs(s, rt, 3, P.rgb_raw, 3, 0);
+            }
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
 // W [out][in] -> [slab][hi|lo][4 k-chunks][n_pad][4]  (zero padded; hi/lo tf32-exact)
 __global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, int n_in, float* __restrict__ dst, int n_pad, int slabs) {
     const int64_t total = (int64_t)slabs * kTcSlabK * n_pad;
@@ -195,6 +498,110 @@ __global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, in
 }
 
 }  // namespace
+}  // namespace clift
+
+
+namespace clift {
+
+static bool tc_add_stack(TcHeadsParams& P, const clift_mlp& m) {
+    for (int l = 0; l < m.n_layers; ++l) {
+        if (!m.w_tc[l] || P.n_gemms >= kTcMaxGemms) return false;
+        TcGemm& g = P.g[P.n_gemms];
+        g.w = m.w_tc[l];
+        g.k_steps = (int)ceil_div(m.dims[l], 8);
+        g.n_pad = (int)round_up(m.dims[l + 1], 32);
+        if (m.dims[l] > kTcMaxK || g.n_pad > 256) return false;
+        P.bias[P.n_gemms] = m.bias[l];
+        ++P.n_gemms;
+    }
+    return true;
+}
+
+bool heads_tc_available(const clift_field* f, int heads) {
+    auto ok = [](const clift_mlp& m) {
+        for (int l = 0; l < m.n_layers; ++l)
+            if (!m.w_tc[l] || m.dims[l] > kTcMaxK || m.dims[l + 1] > 256) return false;
+        return m.n_layers >= 1;
+    };
+    if ((heads & CLIFT_HEAD_SEMANTIC) && !ok(f->semantic)) return false;
+    if ((heads & CLIFT_HEAD_INSTANCE) && (!ok(f->instance_fast) || (f->slow_fast && !ok(f->instance_slow)))) return false;
+    if ((heads & CLIFT_HEAD_RGB) && (!ok(f->rgb) || !f->basis_tc || f->dim_appearance > kTcFeatRows || f->appearance_comps % 8)) return false;
+    return true;
+}
+
+int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
+                            int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream) {
+    TcHeadsParams P;
+    memset(&P, 0, sizeof(P));
+    P.rec_pos = ws.rec_pos;
+    P.rec_ray = ws.rec_ray;
+    P.stats = reinterpret_cast<const unsigned long long*>(ws.stats);
+    P.cap = cap;
+    P.rays = rays;
+    P.app = make_factors(field, true);
+    P.dim_app = field->dim_appearance;
+    P.pe_view = field->pe_view;
+    P.pe_feat = field->pe_feat;
+    P.pe_sem = field->pe_sem;
+    P.pe_ins = field->pe_ins;
+    P.n_cls = field->num_classes;
+    P.d_ins = field->dim_instance;
+    P.slow_fast = field->slow_fast;
+    P.softmax = cfg->semantic_softmax;
+    P.rgb_raw = rgb_raw;
+    P.sem_raw = sem_raw;
+    P.ins = ins;
+    bool ok = true;
+    if (sem_raw) {
+        P.n_sem = field->semantic.n_layers;
+        ok = ok && tc_add_stack(P, field->semantic);
+    }
+    if (ins) {
+        P.n_ins = field->instance_fast.n_layers;
+        ok = ok && tc_add_stack(P, field->instance_fast);
+        if (field->slow_fast) ok = ok && tc_add_stack(P, field->instance_slow);
+    }
+    if (rgb_raw) {
+        P.n_rgb = field->rgb.n_layers;
+        if (P.n_gemms < kTcMaxGemms && field->basis_tc) {
+            TcGemm& g = P.g[P.n_gemms];
+            g.w = field->basis_tc;
+            g.k_steps = (int)ceil_div(3 * field->appearance_comps, 8);
+            g.n_pad = (int)round_up(field->dim_appearance, 32);
+            P.bias[P.n_gemms] = nullptr;
+            ++P.n_gemms;
+        } else {
+            ok = false;
+        }
+        ok = ok && tc_add_stack(P, field->rgb);
+    }
+    if (!ok) {
+        set_error("launch_heads_forward_tc: field lacks tensor-core operands (clift_pack_linear_tc) or exceeds the envelope");
+        return CLIFT_ERR_UNSUPPORTED;
+    }
+    if (P.n_gemms == 0 || n_rays <= 0) return CLIFT_OK;
+    const int grid = sm_count();
+#define CLIFT_TC_CASE(NV)                                                                                              \
+    case NV: {                                                                                                         \
+        CLIFT_CUDA(cudaFuncSetAttribute(heads_tc_forward_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)kTcSmemBytes));                                                           \
+        heads_tc_forward_kernel<NV><<<grid, kTcThreads, kTcSmemBytes, stream>>>(P);                                    \
+        break;                                                                                                         \
+    }
+    switch (P.app.comps / 16) {
+        CLIFT_TC_CASE(1)
+        CLIFT_TC_CASE(2)
+        CLIFT_TC_CASE(3)
+        CLIFT_TC_CASE(4)
+        default:
+            set_error("launch_heads_forward_tc: appearance_comps %d not in {16,32,48,64}", P.app.comps);
+            return CLIFT_ERR_UNSUPPORTED;
+    }
+#undef CLIFT_TC_CASE
+    CLIFT_AFTER_LAUNCH("heads_tc_forward_kernel");
+    return CLIFT_OK;
+}
+
 }  // namespace clift
 
 using namespace clift;

@@ -102,6 +102,7 @@ class _PackedMlp:
         self.wt = [torch.zeros((L.k_pad(l.in_features), L.n_pad(l.out_features)), device=device) for l in self.linears]
         self.bias = [torch.zeros((L.n_pad(l.out_features),), device=device) for l in self.linears]
         self.w_dgrad: List[Optional[torch.Tensor]] = [None] * len(self.linears)
+        self.w_tc: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.g_wt: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.g_bias: List[Optional[torch.Tensor]] = [None] * len(self.linears)
 
@@ -109,6 +110,11 @@ class _PackedMlp:
         for i, l in enumerate(self.linears):
             L.check(lib.clift_pack_linear(L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None,
                                           L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
+            nf = lib.clift_tc_weight_floats(l.out_features, l.in_features)
+            if nf > 0:      # inside the tensor-core envelope: keep the tf32 hi/lo operand current as well
+                if self.w_tc[i] is None:
+                    self.w_tc[i] = torch.zeros((nf,), device=self.wt[i].device)
+                L.check(lib.clift_pack_linear_tc(L.ptr(l.weight.data), L.ptr(self.w_tc[i]), l.out_features, l.in_features, stream))
             if training:
                 if self.w_dgrad[i] is None:
                     self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
@@ -123,6 +129,7 @@ class _PackedMlp:
             m.wt[i] = L.ptr(self.wt[i])
             m.bias[i] = L.ptr(self.bias[i])
             m.w_dgrad[i] = L.ptr(self.w_dgrad[i])
+            m.w_tc[i] = L.ptr(self.w_tc[i])
 
     def grad_buffers(self, g: L.MlpGrad, want: bool):
         for i in range(len(self.linears)):
@@ -408,6 +415,7 @@ class PackedField:
         f = self.field
         f.basis = L.ptr(self.basis.wt[0])
         f.basis_dgrad = L.ptr(self.basis.w_dgrad[0])
+        f.basis_tc = L.ptr(self.basis.w_tc[0])
         self.rgb.fill(f.rgb)
         self.sem.fill(f.semantic)
         if self.insf is not None:

@@ -13,9 +13,10 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
+HEADS_AUTO, HEADS_FMA, HEADS_TENSOR = 0, 1, 2
 
 _fp = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -23,7 +24,7 @@ _vp = C.c_void_p
 
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)),
-                ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS)]
+                ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS), ("w_tc", _vp * MAX_LAYERS)]
 
 
 class MlpGrad(C.Structure):
@@ -36,7 +37,7 @@ class Field(C.Structure):
                 ("pe_sem", C.c_int32), ("pe_ins", C.c_int32), ("num_classes", C.c_int32),
                 ("dim_instance", C.c_int32), ("slow_fast", C.c_int32), ("density_shift", C.c_float),
                 ("density_plane", _vp * 3), ("density_line", _vp * 3),
-                ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp), ("basis_dgrad", _vp),
+                ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp), ("basis_dgrad", _vp), ("basis_tc", _vp),
                 ("rgb", Mlp), ("semantic", Mlp), ("instance_fast", Mlp), ("instance_slow", Mlp)]
 
 
@@ -49,7 +50,8 @@ class FieldGrad(C.Structure):
 class RenderCfg(C.Structure):
     _fields_ = [("aabb_min", C.c_float * 3), ("aabb_max", C.c_float * 3), ("inv_extent", C.c_float * 3),
                 ("step_size", C.c_float), ("n_samples", C.c_int32), ("distance_scale", C.c_float),
-                ("weight_thres", C.c_float), ("semantic_softmax", C.c_int32), ("heads", C.c_int32)]
+                ("weight_thres", C.c_float), ("semantic_softmax", C.c_int32), ("heads", C.c_int32),
+                ("head_path", C.c_int32)]
 
 
 class RenderOut(C.Structure):

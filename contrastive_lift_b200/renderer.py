@@ -183,6 +183,8 @@ class TensoRFRenderer(nn.Module):
         # overflow is detected after the call (check_overflow) and the call is repeated at the exact size.
         self.max_active_per_ray = 192
         self.check_overflow = True
+        # lib.HEADS_AUTO: tcgen05 tensor-core heads for inference, FP32-FMA heads for training forwards
+        self.head_path = L.HEADS_AUTO
         self._live_ctx = None
         self._host = None
         self.last_opacity = None
@@ -245,6 +247,7 @@ class TensoRFRenderer(nn.Module):
         cfg.weight_thres = float(self.raymarch_weight_thres)
         cfg.semantic_softmax = 1 if self.semantic_weight_mode == "softmax" else 0
         cfg.heads = heads
+        cfg.head_path = int(self.head_path)
         if tuple(self.grid_dim.tolist()) != tuple(model.grid_dim()):
             raise L.CliftError(f"renderer.grid_dim {self.grid_dim.tolist()} != model factor grid {model.grid_dim()}")
         return cfg

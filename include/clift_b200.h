@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 2
+#define CLIFT_ABI_VERSION 3
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -51,6 +51,8 @@ typedef struct {
      * by clift_pack_linear_dgrad(): W row-major [round_up(out,16)][dgrad_pad(in)], zero filled, where
      * dgrad_pad(in) = 64, 128 or 256 (smallest that fits). */
     const float* w_dgrad[CLIFT_MAX_LAYERS];
+    /* tensor-core operand written by clift_pack_linear_tc() (null = the FP32-FMA head kernel is used) */
+    const float* w_tc[CLIFT_MAX_LAYERS];
 } clift_mlp;
 
 /* Gradient mirror of clift_mlp (same packed shapes); null pointers = do not accumulate. */
@@ -79,6 +81,7 @@ typedef struct {
     const float* appearance_line[3];
     const float* basis;              /* appearance_basis_mat packed as a 1-layer clift_mlp weight */
     const float* basis_dgrad;        /* ... and in clift_pack_linear_dgrad() layout (training only, else null) */
+    const float* basis_tc;           /* ... and in clift_pack_linear_tc() layout (tensor-core heads, else null) */
     clift_mlp rgb;                   /* render_appearance_mlp.mlp       (H1) */
     clift_mlp semantic;              /* render_semantic_mlp.mlp         (H2) */
     clift_mlp instance_fast;         /* render_instance_mlp.mlp         (H3) */
@@ -104,7 +107,14 @@ typedef struct {
     float weight_thres;              /* raymarch_weight_thres 1e-4 */
     int32_t semantic_softmax;        /* semantic_weight_mode == "softmax" */
     int32_t heads;                   /* bit mask of CLIFT_HEAD_* to evaluate */
+    int32_t head_path;               /* CLIFT_HEADS_AUTO / _FMA / _TENSOR */
 } clift_render_cfg;
+
+/* MLP-head implementation: AUTO = tcgen05 tensor cores (3xTF32, fp32-faithful) for inference when the field carries
+ * w_tc operands, FP32 FMA otherwise and always for save_for_backward forwards (they record the training stash). */
+#define CLIFT_HEADS_AUTO 0
+#define CLIFT_HEADS_FMA 1
+#define CLIFT_HEADS_TENSOR 2
 
 #define CLIFT_HEAD_RGB 1
 #define CLIFT_HEAD_SEMANTIC 2

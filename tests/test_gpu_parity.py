@@ -92,9 +92,11 @@ def test_density_matches_reference(name):
     assert torch.allclose(sigma, ref, rtol=REL, atol=1e-7), float((sigma - ref).abs().max())
 
 
+@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR], ids=["fma", "tcgen05"])
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
-def test_render_inference_golden(name):
+def test_render_inference_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
+    rend.head_path = path
     with torch.no_grad():
         rgb, sem, ins, depth, feats, dist = rend(model, rays.cuda(), 1.0, False, False)
     assert feats.shape == (1, 1) and rgb.grad_fn is None
@@ -153,9 +155,11 @@ def test_render_training_forward_rng_parity(name, tag, seed):
     assert gpu.rel_err(sem.exp() if bool(fx["softmax"]) else sem, ref_sem.exp() if bool(fx["softmax"]) else ref_sem) < REL
 
 
+@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR], ids=["fma", "tcgen05"])
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
-def test_instance_and_segment_golden(name):
+def test_instance_and_segment_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
+    rend.head_path = path
     with torch.no_grad():
         torch.manual_seed(11)
         ins, pts = rend.forward_instance_feature(model, rays.cuda(), 1.0, True)
@@ -304,7 +308,8 @@ def test_active_list_overflow_is_reported():
     assert gpu.rel_err(out[0], tn(fx["inf_rgb"])) < REL
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR], ids=["fma", "tcgen05"])
+def test_full_size_properties(path):
     """BASELINE-size frame (400x400, S=512, all heads): properties that need no CPU oracle run."""
     grid = (128, 128, 128)
     params = syn.make_field_params(0, grid, 21, 3)
@@ -312,6 +317,7 @@ def test_full_size_properties():
     ratio = orc.ratio_for_samples(aabb, grid, 512)
     model, rend = gpu.build(params, grid, 21, 3, True, True, aabb, ratio)
     assert rend.n_samples == 512
+    rend.head_path = path
     k, c2w = syn.camera(400, 400)
     rays = cl.get_rays_checked(400, 400, k.numpy(), c2w.numpy())
     with torch.no_grad():
