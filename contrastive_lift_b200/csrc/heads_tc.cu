@@ -14,12 +14,16 @@
 namespace clift {
 namespace {
 
-constexpr int kTcThreads = 192;
 constexpr int kTcRows = 128;            // records per tile = UMMA M
+constexpr int kTcRowThreads = 256;      // two threads per record: column halves
+constexpr int kTcThreads = 64 + kTcRowThreads;
 constexpr int kTcMaxK = 256;
-constexpr int kTcStages = 2;
-constexpr int kTcSlabK = 16;            // K rows per weight stage
+constexpr int kTcStages = 4;
+constexpr int kTcSlabK = 8;             // K rows per weight stage = one tcgen05.mma k-step
 constexpr int kTcStageFloats = 2 * kTcSlabK * 256;   // hi + lo, N up to 256
+constexpr int kTcFeatRows = 32;
+constexpr int kTcMaxGemms = 24;
+constexpr int kTcBiasFloats = 17 * 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemALo = 256;      // column offset of A_lo
 
@@ -27,6 +31,7 @@ struct TcSmem {
     float* a_hi;        // [kTcMaxK/4][128][4]   (also the [c][128] scratch of the final epilogues)
     float* w;           // [kTcStages][kTcStageFloats]
     float* feat;        // [32][128] appearance features of the tile (rgb input construction)
+    float* bias;        // [kTcBiasFloats] all biases of the schedule, loaded once per CTA
     int* ray;           // [128]
     int* runs;          // [129]
     int* n_runs;        // [1]
@@ -37,16 +42,17 @@ struct TcSmem {
     uint32_t* tmem_base;
 };
 
-constexpr int kTcFeatRows = 32;
 constexpr size_t kTcSmemBytes = (size_t)kTcMaxK * kTcRows * 4 + (size_t)kTcStages * kTcStageFloats * 4 +
-                                (size_t)kTcFeatRows * kTcRows * 4 + (2 * kTcRows + 8) * 4 + 256;
+                                (size_t)kTcFeatRows * kTcRows * 4 + (size_t)kTcBiasFloats * 4 + (2 * kTcRows + 8) * 4 + 256;
+static_assert(kTcSmemBytes <= 232448, "shared memory budget of one sm_100a CTA");
 
 __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
     TcSmem s;
     s.a_hi = reinterpret_cast<float*>(raw);
     s.w = s.a_hi + kTcMaxK * kTcRows;
     s.feat = s.w + kTcStages * kTcStageFloats;
-    s.ray = reinterpret_cast<int*>(s.feat + kTcFeatRows * kTcRows);
+    s.bias = s.feat + kTcFeatRows * kTcRows;
+    s.ray = reinterpret_cast<int*>(s.bias + kTcBiasFloats);
     s.runs = s.ray + kTcRows;
     s.n_runs = s.runs + kTcRows + 1;
     s.full = reinterpret_cast<uint64_t*>(s.n_runs + 7);
@@ -57,24 +63,23 @@ __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
     return s;
 }
 
-// One GEMM of the schedule: D[128 x n_pad] = A[128 x k_pad] * W^T, weights packed by clift_pack_linear_tc.
+// One GEMM of the schedule: D[128 x n_pad] = A[128 x 8*k_steps] * W^T, weights packed by clift_pack_linear_tc.
 struct TcGemm {
-    const float* w;     // [slabs][2][4][n_pad][4]
+    const float* w;     // [k_steps][hi|lo][2][n_pad][4]
     int k_steps;        // ceil(K / 8)
     int n_pad;          // multiple of 32, <= 256
 };
 
-struct PipeState {      // ring position shared by construction between producer and MMA warps
-    uint32_t slab = 0;  // running slab counter over the whole kernel
+struct PipeState {      // ring position; producer and MMA warps advance it identically
+    uint32_t slab = 0;
     __device__ __forceinline__ int stage() const { return slab % kTcStages; }
     __device__ __forceinline__ uint32_t phase() const { return (slab / kTcStages) & 1; }
 };
 
 // warp 0, one lane: stream the GEMM's weight slabs
 __device__ __forceinline__ void tc_produce(const TcSmem& s, const TcGemm& g, PipeState& ps) {
-    const int slabs = (g.k_steps + 1) / 2;
     const uint32_t bytes = 2u * kTcSlabK * g.n_pad * 4u;
-    for (int i = 0; i < slabs; ++i, ++ps.slab) {
+    for (int i = 0; i < g.k_steps; ++i, ++ps.slab) {
         tc::mbar_wait(&s.empty[ps.stage()], ps.phase() ^ 1);
         tc::mbar_arrive_expect_tx(&s.full[ps.stage()], bytes);
         tc::bulk_load(s.w + (size_t)ps.stage() * kTcStageFloats, g.w + (size_t)i * (2 * kTcSlabK * g.n_pad), bytes, &s.full[ps.stage()]);
@@ -88,37 +93,31 @@ __device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeS
     const uint32_t w_lbo = (uint32_t)g.n_pad * 16u;
     tc::mbar_wait(s.bar_a, a_parity);
     tc::fence_after_sync();
-    const int slabs = (g.k_steps + 1) / 2;
-    for (int i = 0; i < slabs; ++i, ++ps.slab) {
+    for (int ks = 0; ks < g.k_steps; ++ks, ++ps.slab) {
         tc::mbar_wait(&s.full[ps.stage()], ps.phase());
         tc::fence_after_sync();
         const uint32_t w_hi = tc::smem_addr(s.w + (size_t)ps.stage() * kTcStageFloats);
         const uint32_t w_lo = w_hi + (uint32_t)kTcSlabK * g.n_pad * 4u;
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-            const int ks = i * 2 + kk;
-            if (ks >= g.k_steps) break;
-            const uint64_t a_desc = tc::make_smem_desc(a_base + (uint32_t)ks * 2u * (kTcRows * 16u), kTcRows * 16u, 128u);
-            const uint64_t bh = tc::make_smem_desc(w_hi + (uint32_t)kk * 2u * w_lbo, w_lbo, 128u);
-            const uint64_t bl = tc::make_smem_desc(w_lo + (uint32_t)kk * 2u * w_lbo, w_lbo, 128u);
-            tc::mma_ss(tmem, a_desc, bh, idesc, ks > 0 ? 1u : 0u);
-            tc::mma_ss(tmem, a_desc, bl, idesc, 1u);
-            tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
-        }
+        const uint64_t a_desc = tc::make_smem_desc(a_base + (uint32_t)ks * 2u * (kTcRows * 16u), kTcRows * 16u, 128u);
+        const uint64_t bh = tc::make_smem_desc(w_hi, w_lbo, 128u);
+        const uint64_t bl = tc::make_smem_desc(w_lo, w_lbo, 128u);
+        tc::mma_ss(tmem, a_desc, bh, idesc, ks > 0 ? 1u : 0u);
+        tc::mma_ss(tmem, a_desc, bl, idesc, 1u);
+        tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
         tc::mma_commit(&s.empty[ps.stage()]);
     }
     tc::mma_commit(s.bar_d);
 }
 
 // row thread: write 8 consecutive K values (k0 multiple of 8) of its record into the A operand (hi -> smem, lo -> TMEM)
-__device__ __forceinline__ void tc_put8(const TcSmem& s, uint32_t tmem_lane_base, int row, int k0, const float* v) {
+__device__ __forceinline__ void tc_put8(const TcSmem& s, uint32_t lane_base, int row, int k0, const float* v) {
     float hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) tc::split_tf32(v[i], hi[i], lo[i]);
     float4* dst = reinterpret_cast<float4*>(s.a_hi + ((size_t)(k0 >> 2) * kTcRows + row) * 4);
     dst[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
     dst[kTcRows] = make_float4(hi[4], hi[5], hi[6], hi[7]);
-    tc::tmem_st8(tmem_lane_base + kTmemALo + (uint32_t)k0, lo);
+    tc::tmem_st8(lane_base + kTmemALo + (uint32_t)k0, lo);
 }
 
 // row threads: publish the A operand they just wrote
@@ -126,17 +125,27 @@ __device__ __forceinline__ void tc_publish_a(const TcSmem& s) {
     tc::tmem_wait_st();
     tc::fence_proxy_async_smem();
     tc::fence_before_sync();
-    tc::named_bar_sync(1, kTcRows);
-    if ((threadIdx.x & 127) == 64) tc::mbar_arrive(s.bar_a);   // any single row thread
+    tc::named_bar_sync(1, kTcRowThreads);
+    if (threadIdx.x == 64) tc::mbar_arrive(s.bar_a);
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// parity / bring-up kernel: out[128][n_pad] = a[128][K] * W^T (no bias), one CTA
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float* __restrict__ a, int K, TcGemm g, float* __restrict__ out) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    TcSmem s = carve_tc_smem(smem_raw);
-    const int warp = threadIdx.x >> 5;
+struct RowId {
+    int row, half, rt;          // record row 0..127, column half 0/1, index among the row threads 0..255
+    uint32_t lane_base;         // TMEM address of this warp's lane quarter
+};
+
+__device__ __forceinline__ RowId make_row_id(uint32_t tmem) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RowId r;
+    const int quarter = warp & 3;           // the TMEM lane quarter a warp may touch is warp_id % 4
+    r.row = quarter * 32 + lane;
+    r.half = (warp - 2) >> 2;
+    r.rt = threadIdx.x - 64;
+    r.lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    return r;
+}
+
+__device__ __forceinline__ void tc_init(const TcSmem& s) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcStages; ++i) {
             tc::mbar_init(&s.full[i], 1);
@@ -146,12 +155,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
         tc::mbar_init(s.bar_d, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(s.tmem_base, kTmemCols);
+    if ((threadIdx.x >> 5) == 1) tc::tmem_alloc(s.tmem_base, kTmemCols);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    const uint32_t tmem = *s.tmem_base;
+}
 
+// ---------------------------------------------------------------------------------------------------------
+// parity / bring-up kernel: out[128][n_pad] = a[128][K] * W^T (no bias), one CTA
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float* __restrict__ a, int K, TcGemm g, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem s = carve_tc_smem(smem_raw);
+    const int warp = threadIdx.x >> 5;
+    tc_init(s);
+    const uint32_t tmem = *s.tmem_base;
     if (warp == 0) {
         if (tc::elect_one()) {
             PipeState ps;
@@ -163,24 +181,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
             tc_issue(s, g, ps, tmem, 0);
         }
     } else {
-        const int quarter = warp & 3;                        // TMEM lane quarter this warp may touch
-        const int row = quarter * 32 + (threadIdx.x & 31);
-        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
-        for (int k0 = 0; k0 < g.k_steps * 8; k0 += 8) {
+        const RowId r = make_row_id(tmem);
+        for (int k0 = r.half * 8; k0 < g.k_steps * 8; k0 += 16) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (k0 + i < K) ? a[(size_t)row * K + k0 + i] : 0.0f;
-            tc_put8(s, lane_base, row, k0, v);
+            for (int i = 0; i < 8; ++i) v[i] = (k0 + i < K) ? a[(size_t)r.row * K + k0 + i] : 0.0f;
+            tc_put8(s, r.lane_base, r.row, k0, v);
         }
         tc_publish_a(s);
         tc::mbar_wait(s.bar_d, 0);
         tc::fence_after_sync();
-        for (int c0 = 0; c0 < g.n_pad; c0 += 16) {
+        for (int c0 = r.half * 16; c0 < g.n_pad; c0 += 32) {
             float v[16];
-            tc::tmem_ld16(lane_base + (uint32_t)c0, v);
+            tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
             tc::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) out[(size_t)row * g.n_pad + c0 + i] = v[i];
+            for (int i = 0; i < 16; ++i) out[(size_t)r.row * g.n_pad + c0 + i] = v[i];
         }
         tc::fence_before_sync();
     }
@@ -188,12 +204,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
     if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
-
 // ---------------------------------------------------------------------------------------------------------
 // production kernel: all heads of one 128-record tile per iteration, persistent over tiles
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kTcMaxGemms = 24;
-
 struct TcHeadsParams {
     const float4* rec_pos;
     const int32_t* rec_ray;
@@ -206,74 +219,94 @@ struct TcHeadsParams {
     // GEMM schedule of one tile, in issue order: semantic | instance fast | instance slow | basis | rgb
     int n_gemms;
     TcGemm g[kTcMaxGemms];
-    const float* bias[kTcMaxGemms];   // [n_pad] or null
+    const float* bias[kTcMaxGemms];   // [>= n_pad] or null
+    int bias_off[kTcMaxGemms];        // offset into the shared-memory bias table, -1 = no bias
     int n_sem, n_ins, n_rgb;          // layers per stack (0 = head off)
     float* rgb_raw;
     float* sem_raw;
     float* ins;
 };
 
-// hidden-layer epilogue: D -> +bias -> ReLU -> next layer's A operand
-__device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, uint32_t lane_base, int row, int n_pad, const float* __restrict__ bias) {
-    for (int c0 = 0; c0 < n_pad; c0 += 16) {
+// hidden-layer epilogue: D -> +bias -> ReLU -> next layer's A operand.  Each of a record's two threads converts one
+// half of the columns, 16 at a time, with the next TMEM load in flight while the current chunk is processed.
+__device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, const RowId& r, int n_pad, int bias_off) {
+    const int half_cols = n_pad >> 1;                 // multiple of 16
+    const int c_begin = r.half * half_cols, c_end = c_begin + half_cols;
+    float nxt[16];
+    tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, nxt);
+    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         float v[16];
-        tc::tmem_ld16(lane_base + (uint32_t)c0, v);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f), 0.0f);
-        tc_put8(s, lane_base, row, c0, v);
-        tc_put8(s, lane_base, row, c0 + 8, v + 8);
+        for (int i = 0; i < 16; ++i) v[i] = nxt[i];
+        if (c0 + 16 < c_end) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + 16), nxt);
+        if (bias_off >= 0) {
+            const float4* b4 = reinterpret_cast<const float4*>(s.bias + bias_off + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 b = b4[i];
+                v[4 * i + 0] += b.x;
+                v[4 * i + 1] += b.y;
+                v[4 * i + 2] += b.z;
+                v[4 * i + 3] += b.w;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        tc_put8(s, r.lane_base, r.row, c0, v);
+        tc_put8(s, r.lane_base, r.row, c0 + 8, v + 8);
     }
 }
 
-// final-layer epilogue: D (+bias) -> scratch[c][row] for c < n_out (scratch = a_hi region, K-major like the FFMA kernel)
-__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, uint32_t lane_base, int row, int n_out, const float* __restrict__ bias) {
+// final-layer epilogue (half 0 threads): D (+bias) -> scratch[c][row] for c < n_out (scratch = a_hi region)
+__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, const RowId& r, int n_out, int bias_off) {
+    if (r.half != 0) return;
     for (int c0 = 0; c0 < n_out; c0 += 16) {
         float v[16];
-        tc::tmem_ld16(lane_base + (uint32_t)c0, v);
+        tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
         tc::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (c0 + i < n_out) s.a_hi[(size_t)(c0 + i) * kTcRows + row] = v[i] + (bias ? __ldg(bias + c0 + i) : 0.0f);
+            if (c0 + i < n_out) s.a_hi[(size_t)(c0 + i) * kTcRows + r.row] = v[i] + (bias_off >= 0 ? s.bias[bias_off + c0 + i] : 0.0f);
     }
 }
 
 // xyz (+ sin/cos PE, dimension-major frequency-minor) -> A operand, zero padded to a multiple of 8
-__device__ __forceinline__ void tc_build_xyz(const TcSmem& s, uint32_t lane_base, int row, const float4& p, int pe) {
+__device__ __forceinline__ void tc_build_xyz(const TcSmem& s, const RowId& r, const float4& p, int pe) {
     const int n_in = 3 + 6 * pe;
     const float xyz[3] = {p.x, p.y, p.z};
-    for (int k0 = 0; k0 < n_in; k0 += 8) {
+    for (int k0 = r.half * 8; k0 < n_in; k0 += 16) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int r = k0 + i;
+            const int q = k0 + i;
             float x = 0.0f;
-            if (r < 3) {
-                x = r == 0 ? xyz[0] : (r == 1 ? xyz[1] : xyz[2]);
-            } else if (r < n_in) {
-                const int j = (r - 3) % (3 * pe);
+            if (q < 3) {
+                x = q == 0 ? xyz[0] : (q == 1 ? xyz[1] : xyz[2]);
+            } else if (q < n_in) {
+                const int j = (q - 3) % (3 * pe);
                 const int d = j / pe;
                 const float arg = (d == 0 ? xyz[0] : (d == 1 ? xyz[1] : xyz[2])) * (float)(1 << (j % pe));
-                x = (r - 3 < 3 * pe) ? sinf(arg) : cosf(arg);
+                x = (q - 3 < 3 * pe) ? sinf(arg) : cosf(arg);
             }
             v[i] = x;
         }
-        tc_put8(s, lane_base, row, k0, v);
+        tc_put8(s, r.lane_base, r.row, k0, v);
     }
 }
 
-// 128 row threads: sum rows [0,nch) of scratch over each ray run (fixed order) and add into dst[ray*stride + col0 + c]
+// row threads: sum rows [0,nch) of scratch over each ray run (fixed order) and add into dst[ray*stride + col0 + c]
 __device__ __forceinline__ void tc_reduce_runs(const TcSmem& s, int rt, int nch, float* __restrict__ dst, int stride, int col0) {
-    tc::named_bar_sync(1, kTcRows);
+    tc::named_bar_sync(1, kTcRowThreads);
     const int n_runs = *s.n_runs;
-    for (int idx = rt; idx < n_runs * nch; idx += kTcRows) {
+    for (int idx = rt; idx < n_runs * nch; idx += kTcRowThreads) {
         const int r = idx / nch, c = idx - r * nch;
         const int m0 = s.runs[r], m1 = s.runs[r + 1];
         float acc = 0.0f;
         for (int m = m0; m < m1; ++m) acc += s.a_hi[(size_t)c * kTcRows + m];
         atomicAdd(dst + (int64_t)s.ray[m0] * stride + col0 + c, acc);
     }
-    tc::named_bar_sync(1, kTcRows);
+    tc::named_bar_sync(1, kTcRowThreads);
 }
 
 template <int NV>
@@ -281,19 +314,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem s = carve_tc_smem(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kTcStages; ++i) {
-            tc::mbar_init(&s.full[i], 1);
-            tc::mbar_init(&s.empty[i], 1);
-        }
-        tc::mbar_init(s.bar_a, 1);
-        tc::mbar_init(s.bar_d, 1);
-        tc::fence_barrier_init();
-    }
-    if (warp == 1) tc::tmem_alloc(s.tmem_base, kTmemCols);
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
+    for (int gi = 0; gi < P.n_gemms; ++gi)
+        if (P.bias_off[gi] >= 0)
+            for (int i = threadIdx.x; i < P.g[gi].n_pad; i += kTcThreads) s.bias[P.bias_off[gi] + i] = P.bias[gi][i];
+    tc_init(s);
     const uint32_t tmem = *s.tmem_base;
     const long long n_act = min((long long)P.stats[0], P.cap);
     const long long n_tiles = (n_act + kTcRows - 1) / kTcRows;
@@ -312,10 +336,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 for (int gi = 0; gi < P.n_gemms; ++gi, ++count) tc_issue(s, P.g[gi], ps, tmem, count & 1);
         }
     } else {
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const int rt = threadIdx.x - 64;                      // 0..127 among the row threads
-        const uint32_t lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+        const RowId r = make_row_id(tmem);
+        const int row = r.row;
         uint32_t count = 0;                                    // GEMMs consumed so far (bar_d parity)
         auto wait_d = [&]() {
             tc::mbar_wait(s.bar_d, count & 1);
@@ -331,8 +353,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 p = P.rec_pos[base + row];
                 ray = P.rec_ray[base + row];
             }
-            s.ray[row] = ray;
-            tc::named_bar_sync(1, kTcRows);
+            if (r.half == 0) s.ray[row] = ray;
+            tc::named_bar_sync(1, kTcRowThreads);
             if (warp == 2) {   // run starts, in record order
                 int n = 0;
                 for (int w4 = 0; w4 < kTcRows / 32; ++w4) {
@@ -349,54 +371,58 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
             }
             int gi = 0;
             if (P.n_sem > 0) {
-                tc_build_xyz(s, lane_base, row, p, P.pe_sem);
+                tc_build_xyz(s, r, p, P.pe_sem);
                 tc_publish_a(s);
                 for (int l = 0; l < P.n_sem; ++l, ++gi) {
                     wait_d();
                     if (l + 1 < P.n_sem) {
-                        tc_epilogue_hidden(s, lane_base, row, P.g[gi].n_pad, P.bias[gi]);
+                        tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
                         tc_publish_a(s);
                     } else {
-                        tc_epilogue_final(s, lane_base, row, P.n_cls, P.bias[gi]);
+                        tc_epilogue_final(s, r, P.n_cls, P.bias_off[gi]);
                     }
                 }
-                // softmax over the thread's own column of the scratch, then the compositing weight
-                if (P.softmax) {
-                    float mx = -INFINITY;
-                    for (int c = 0; c < P.n_cls; ++c) mx = fmaxf(mx, s.a_hi[(size_t)c * kTcRows + row]);
-                    float tot = 0.0f;
-                    for (int c = 0; c < P.n_cls; ++c) {
-                        const float e = expf(s.a_hi[(size_t)c * kTcRows + row] - mx);
-                        s.a_hi[(size_t)c * kTcRows + row] = e;
-                        tot += e;
+                if (r.half == 0) {   // softmax over the thread's own column of the scratch, then the compositing weight
+                    if (P.softmax) {
+                        float mx = -INFINITY;
+                        for (int c = 0; c < P.n_cls; ++c) mx = fmaxf(mx, s.a_hi[(size_t)c * kTcRows + row]);
+                        float tot = 0.0f;
+                        for (int c = 0; c < P.n_cls; ++c) {
+                            const float e = expf(s.a_hi[(size_t)c * kTcRows + row] - mx);
+                            s.a_hi[(size_t)c * kTcRows + row] = e;
+                            tot += e;
+                        }
+                        for (int c = 0; c < P.n_cls; ++c)
+                            s.a_hi[(size_t)c * kTcRows + row] = (s.a_hi[(size_t)c * kTcRows + row] / tot) * p.w;
+                    } else {
+                        for (int c = 0; c < P.n_cls; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
                     }
-                    for (int c = 0; c < P.n_cls; ++c) s.a_hi[(size_t)c * kTcRows + row] = (s.a_hi[(size_t)c * kTcRows + row] / tot) * p.w;
-                } else {
-                    for (int c = 0; c < P.n_cls; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
                 }
-                tc_reduce_runs(s, rt, P.n_cls, P.sem_raw, P.n_cls, 0);
+                tc_reduce_runs(s, r.rt, P.n_cls, P.sem_raw, P.n_cls, 0);
             }
             if (P.n_ins > 0) {
                 const int width = P.d_ins * (P.slow_fast ? 2 : 1);
                 for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
-                    tc_build_xyz(s, lane_base, row, p, P.pe_ins);
+                    tc_build_xyz(s, r, p, P.pe_ins);
                     tc_publish_a(s);
                     for (int l = 0; l < P.n_ins; ++l, ++gi) {
                         wait_d();
                         if (l + 1 < P.n_ins) {
-                            tc_epilogue_hidden(s, lane_base, row, P.g[gi].n_pad, P.bias[gi]);
+                            tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
                             tc_publish_a(s);
                         } else {
-                            tc_epilogue_final(s, lane_base, row, P.d_ins, P.bias[gi]);
+                            tc_epilogue_final(s, r, P.d_ins, P.bias_off[gi]);
                         }
                     }
-                    for (int c = 0; c < P.d_ins; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
-                    tc_reduce_runs(s, rt, P.d_ins, P.ins, width, net * P.d_ins);
+                    if (r.half == 0)
+                        for (int c = 0; c < P.d_ins; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
+                    tc_reduce_runs(s, r.rt, P.d_ins, P.ins, width, net * P.d_ins);
                 }
             }
             if (P.n_rgb > 0) {
                 const FactorParams& f = P.app;
-                // appearance gather: 18 taps x comps channels -> plane*line products, 8 channels per put
+                // appearance gather: 18 taps x comps channels -> plane*line products; the record's two threads
+                // alternate over the 8-channel groups
                 const float xs[3] = {p.x, p.y, p.z};
 #pragma unroll 1
                 for (int mode = 0; mode < 3; ++mode) {
@@ -404,6 +430,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     const Tap1 t1 = make_tap1(xs[mode_v(mode)], f.ll[mode]);
 #pragma unroll
                     for (int v8 = 0; v8 < NV * 2; ++v8) {
+                        if (((mode * NV * 2 + v8) & 1) != r.half) continue;   // warp-uniform
                         const int ch = v8 * 8;
                         const float4 pa = plane_tap(f.plane[mode], t2, f.pw[mode], f.comps, ch);
                         const float4 la = line_tap(f.line[mode], t1, f.comps, ch);
@@ -411,21 +438,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                         const float4 lb = line_tap(f.line[mode], t1, f.comps, ch + 4);
                         const float v[8] = {pa.x * la.x, pa.y * la.y, pa.z * la.z, pa.w * la.w,
                                             pb.x * lb.x, pb.y * lb.y, pb.z * lb.z, pb.w * lb.w};
-                        tc_put8(s, lane_base, row, mode * f.comps + ch, v);
+                        tc_put8(s, r.lane_base, row, mode * f.comps + ch, v);
                     }
                 }
                 tc_publish_a(s);
                 wait_d();   // basis GEMM: features in D columns [0, dim_app)
                 const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
-                for (int c0 = 0; c0 < A; c0 += 16) {
-                    float v[16];
-                    tc::tmem_ld16(lane_base + (uint32_t)c0, v);
-                    tc::tmem_wait_ld();
+                if (r.half == 0) {
+                    for (int c0 = 0; c0 < A; c0 += 16) {
+                        float v[16];
+                        tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
+                        tc::tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (c0 + i < A) s.feat[(size_t)(c0 + i) * kTcRows + row] = v[i];
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < A) s.feat[(size_t)(c0 + i) * kTcRows + row] = v[i];
+                    }
                 }
                 ++gi;
+                tc::named_bar_sync(1, kTcRowThreads);
                 float dir[3] = {0.f, 0.f, 1.f};
                 if (ray >= 0) {
                     dir[0] = __ldg(P.rays + (int64_t)ray * 8 + 3);
@@ -434,45 +464,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 }
                 // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418)
                 const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
-                for (int k0 = 0; k0 < n_in; k0 += 8) {
+                for (int k0 = r.half * 8; k0 < n_in; k0 += 16) {
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int r = k0 + i;
+                        const int q = k0 + i;
                         float x = 0.0f;
-                        if (r < A) {
-                            x = s.feat[(size_t)r * kTcRows + row];
-                        } else if (r < o_sf) {
-                            x = r - A == 0 ? dir[0] : (r - A == 1 ? dir[1] : dir[2]);
-                        } else if (r < o_sd) {
-                            const int j = (r < o_cf) ? r - o_sf : r - o_cf;
+                        if (q < A) {
+                            x = s.feat[(size_t)q * kTcRows + row];
+                        } else if (q < o_sf) {
+                            x = q - A == 0 ? dir[0] : (q - A == 1 ? dir[1] : dir[2]);
+                        } else if (q < o_sd) {
+                            const int j = (q < o_cf) ? q - o_sf : q - o_cf;
                             const float arg = s.feat[(size_t)(j / pf) * kTcRows + row] * (float)(1 << (j % pf));
-                            x = (r < o_cf) ? sinf(arg) : cosf(arg);
-                        } else if (r < n_in) {
-                            const int j = (r < o_cd) ? r - o_sd : r - o_cd;
+                            x = (q < o_cf) ? sinf(arg) : cosf(arg);
+                        } else if (q < n_in) {
+                            const int j = (q < o_cd) ? q - o_sd : q - o_cd;
                             const int d = j / pv;
                             const float arg = (d == 0 ? dir[0] : (d == 1 ? dir[1] : dir[2])) * (float)(1 << (j % pv));
-                            x = (r < o_cd) ? sinf(arg) : cosf(arg);
+                            x = (q < o_cd) ? sinf(arg) : cosf(arg);
                         }
                         v[i] = x;
                     }
-                    tc_put8(s, lane_base, row, k0, v);
+                    tc_put8(s, r.lane_base, row, k0, v);
                 }
                 tc_publish_a(s);
                 for (int l = 0; l < P.n_rgb; ++l, ++gi) {
                     wait_d();
                     if (l + 1 < P.n_rgb) {
-                        tc_epilogue_hidden(s, lane_base, row, P.g[gi].n_pad, P.bias[gi]);
+                        tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
                         tc_publish_a(s);
                     } else {
-                        tc_epilogue_final(s, lane_base, row, 3, P.bias[gi]);
+                        tc_epilogue_final(s, r, 3, P.bias_off[gi]);
                     }
                 }
-                for (int c = 0; c < 3; ++c) {
-                    const float x = s.a_hi[(size_t)c * kTcRows + row];
-                    s.a_hi[(size_t)c * kTcRows + row] = (1.0f / (1.0f + expf(-x))) * p.w;
-                }
-                tc_reduce_runs(s, rt, 3, P.rgb_raw, 3, 0);
+                if (r.half == 0)
+                    for (int c = 0; c < 3; ++c) {
+                        const float x = s.a_hi[(size_t)c * kTcRows + row];
+                        s.a_hi[(size_t)c * kTcRows + row] = (1.0f / (1.0f + expf(-x))) * p.w;
+                    }
+                tc_reduce_runs(s, r.rt, 3, P.rgb_raw, 3, 0);
             }
         }
         tc::fence_before_sync();
@@ -481,7 +512,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
     if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
-// W [out][in] -> [slab][hi|lo][4 k-chunks][n_pad][4]  (zero padded; hi/lo tf32-exact)
+// W [out][in] -> [k-step][hi|lo][2 k-chunks][n_pad][4]  (zero padded; hi/lo tf32-exact)
 __global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, int n_in, float* __restrict__ dst, int n_pad, int slabs) {
     const int64_t total = (int64_t)slabs * kTcSlabK * n_pad;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -490,7 +521,7 @@ __global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, in
     const float x = (k < n_in && n < n_out) ? w[(size_t)n * n_in + k] : 0.0f;
     float hi, lo;
     tc::split_tf32(x, hi, lo);
-    const int slab = k / kTcSlabK, kc = (k % kTcSlabK) / 4, ki = k & 3;
+    const int slab = k / kTcSlabK, kc = (k % kTcSlabK) / 4, ki = k & 3;   // kc in {0,1}
     float* base = dst + (size_t)slab * (2 * kTcSlabK * n_pad);
     const size_t off = ((size_t)kc * n_pad + n) * 4 + ki;
     base[off] = hi;
@@ -512,7 +543,7 @@ static bool tc_add_stack(TcHeadsParams& P, const clift_mlp& m) {
         g.n_pad = (int)round_up(m.dims[l + 1], 32);
         if (m.dims[l] > kTcMaxK || g.n_pad > 256) return false;
         P.bias[P.n_gemms] = m.bias[l];
-        ++P.n_gemms;
+        ++P.n_gemms;   // bias_off is assigned in launch_heads_forward_tc
     }
     return true;
 }
@@ -580,6 +611,15 @@ int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* fiel
         return CLIFT_ERR_UNSUPPORTED;
     }
     if (P.n_gemms == 0 || n_rays <= 0) return CLIFT_OK;
+    int bias_floats = 0;
+    for (int gi = 0; gi < P.n_gemms; ++gi) {
+        P.bias_off[gi] = P.bias[gi] ? bias_floats : -1;
+        if (P.bias[gi]) bias_floats += P.g[gi].n_pad;
+    }
+    if (bias_floats > kTcBiasFloats) {
+        set_error("launch_heads_forward_tc: bias table of %d floats exceeds the shared-memory budget", bias_floats);
+        return CLIFT_ERR_UNSUPPORTED;
+    }
     const int grid = sm_count();
 #define CLIFT_TC_CASE(NV)                                                                                              \
     case NV: {                                                                                                         \

@@ -165,7 +165,8 @@ int32_t clift_unpack_linear(const float* wt, const float* bias_pad, float* w, fl
 int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32_t n_out, int32_t n_in, void* stream);
 
 /* Tensor-core operand of one nn.Linear for the tcgen05 head kernels: W [out][in] -> tf32-exact (hi, lo) pairs in
- * 16-row K slabs, each slab [hi|lo][4 k-chunks][n_pad=round_up(out,32)][4]; clift_tc_weight_floats() sizes it. */
+ * 8-row K slabs (one tcgen05.mma k-step), each slab [hi|lo][2 k-chunks][n_pad=round_up(out,32)][4];
+ * clift_tc_weight_floats() sizes it. */
 int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in);
 int32_t clift_pack_linear_tc(const float* w, float* dst, int32_t n_out, int32_t n_in, void* stream);
 /* Bring-up / parity entry for the tensor-core GEMM core: out[128][round_up(n_out,32)] = a[128][k] * W^T with the
