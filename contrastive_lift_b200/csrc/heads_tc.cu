@@ -15,7 +15,8 @@ namespace clift {
 namespace {
 
 constexpr int kTcRows = 128;            // records per tile = UMMA M
-constexpr int kTcRowThreads = 256;      // two threads per record: column halves
+constexpr int kTcParts = 4;             // threads per record (each takes every kTcParts-th column chunk)
+constexpr int kTcRowThreads = kTcRows * kTcParts;
 constexpr int kTcThreads = 64 + kTcRowThreads;
 constexpr int kTcMaxK = 256;
 constexpr int kTcStages = 4;
@@ -87,12 +88,14 @@ __device__ __forceinline__ void tc_produce(const TcSmem& s, const TcGemm& g, Pip
 }
 
 // warp 1, one lane: issue the 3xTF32 MMAs of one GEMM
-__device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeState& ps, uint32_t tmem, uint32_t a_parity) {
+__device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeState& ps, uint32_t tmem, uint32_t a_parity,
+                                         long long* trace = nullptr) {
     const uint32_t idesc = tc::make_idesc_tf32(kTcRows, g.n_pad);
     const uint32_t a_base = tc::smem_addr(s.a_hi);
     const uint32_t w_lbo = (uint32_t)g.n_pad * 16u;
     tc::mbar_wait(s.bar_a, a_parity);
     tc::fence_after_sync();
+    if (trace) trace[3] = clock64();
     for (int ks = 0; ks < g.k_steps; ++ks, ++ps.slab) {
         tc::mbar_wait(&s.full[ps.stage()], ps.phase());
         tc::fence_after_sync();
@@ -107,6 +110,7 @@ __device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeS
         tc::mma_commit(&s.empty[ps.stage()]);
     }
     tc::mma_commit(s.bar_d);
+    if (trace) trace[4] = clock64();
 }
 
 // row thread: write 8 consecutive K values (k0 multiple of 8) of its record into the A operand (hi -> smem, lo -> TMEM)
@@ -130,7 +134,7 @@ __device__ __forceinline__ void tc_publish_a(const TcSmem& s) {
 }
 
 struct RowId {
-    int row, half, rt;          // record row 0..127, column half 0/1, index among the row threads 0..255
+    int row, half, rt;          // record row 0..127, part 0..kTcParts-1 of the record's threads, index among the row threads
     uint32_t lane_base;         // TMEM address of this warp's lane quarter
 };
 
@@ -139,7 +143,7 @@ __device__ __forceinline__ RowId make_row_id(uint32_t tmem) {
     RowId r;
     const int quarter = warp & 3;           // the TMEM lane quarter a warp may touch is warp_id % 4
     r.row = quarter * 32 + lane;
-    r.half = (warp - 2) >> 2;
+    r.half = (warp - 2) >> 2;               // warps 2..5 part 0, 6..9 part 1, ...
     r.rt = threadIdx.x - 64;
     r.lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     return r;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
         }
     } else {
         const RowId r = make_row_id(tmem);
-        for (int k0 = r.half * 8; k0 < g.k_steps * 8; k0 += 16) {
+        for (int k0 = r.half * 8; k0 < g.k_steps * 8; k0 += 8 * kTcParts) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = (k0 + i < K) ? a[(size_t)r.row * K + k0 + i] : 0.0f;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
         tc_publish_a(s);
         tc::mbar_wait(s.bar_d, 0);
         tc::fence_after_sync();
-        for (int c0 = r.half * 16; c0 < g.n_pad; c0 += 32) {
+        for (int c0 = r.half * 16; c0 < g.n_pad; c0 += 16 * kTcParts) {
             float v[16];
             tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
             tc::tmem_wait_ld();
@@ -225,21 +229,27 @@ struct TcHeadsParams {
     float* rgb_raw;
     float* sem_raw;
     float* ins;
+    long long* trace;                 // debug: [4 tiles][kTcMaxGemms][6] clock64 stamps of CTA 0, or null
 };
 
-// hidden-layer epilogue: D -> +bias -> ReLU -> next layer's A operand.  Each of a record's two threads converts one
-// half of the columns, 16 at a time, with the next TMEM load in flight while the current chunk is processed.
+__device__ __forceinline__ void tc_stamp(const TcHeadsParams& P, long long tile_local, int gi, int slot) {
+    if (P.trace && blockIdx.x == 0 && tile_local < 4) P.trace[(tile_local * kTcMaxGemms + gi) * 6 + slot] = clock64();
+}
+
+// hidden-layer epilogue: D -> +bias -> ReLU -> next layer's A operand.  A record's kTcParts threads take the 16-column
+// chunks round-robin; the next TMEM load is in flight while the current chunk is processed.
 __device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, const RowId& r, int n_pad, int bias_off) {
-    const int half_cols = n_pad >> 1;                 // multiple of 16
-    const int c_begin = r.half * half_cols, c_end = c_begin + half_cols;
+    constexpr int kStride = 16 * kTcParts;
+    const int c_begin = r.half * 16;
+    if (c_begin >= n_pad) return;
     float nxt[16];
     tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, nxt);
-    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    for (int c0 = c_begin; c0 < n_pad; c0 += kStride) {
         float v[16];
         tc::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = nxt[i];
-        if (c0 + 16 < c_end) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + 16), nxt);
+        if (c0 + kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), nxt);
         if (bias_off >= 0) {
             const float4* b4 = reinterpret_cast<const float4*>(s.bias + bias_off + c0);
 #pragma unroll
@@ -275,7 +285,7 @@ __device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, const RowId& 
 __device__ __forceinline__ void tc_build_xyz(const TcSmem& s, const RowId& r, const float4& p, int pe) {
     const int n_in = 3 + 6 * pe;
     const float xyz[3] = {p.x, p.y, p.z};
-    for (int k0 = r.half * 8; k0 < n_in; k0 += 16) {
+    for (int k0 = r.half * 8; k0 < n_in; k0 += 8 * kTcParts) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -332,19 +342,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
         if (tc::elect_one()) {
             PipeState ps;
             uint32_t count = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int gi = 0; gi < P.n_gemms; ++gi, ++count) tc_issue(s, P.g[gi], ps, tmem, count & 1);
+            long long tl = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl)
+                for (int gi = 0; gi < P.n_gemms; ++gi, ++count) {
+                    tc_issue(s, P.g[gi], ps, tmem, count & 1, P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kTcMaxGemms + gi) * 6 : nullptr);
+                }
         }
     } else {
         const RowId r = make_row_id(tmem);
         const int row = r.row;
         uint32_t count = 0;                                    // GEMMs consumed so far (bar_d parity)
+        long long tl = -1;
+        int gi = 0;
         auto wait_d = [&]() {
             tc::mbar_wait(s.bar_d, count & 1);
             ++count;
             tc::fence_after_sync();
+            if (threadIdx.x == 64) tc_stamp(P, tl, gi, 0);
+        };
+        auto publish = [&](int g_next) {
+            if (threadIdx.x == 64) tc_stamp(P, tl, g_next, 1);
+            tc_publish_a(s);
+            if (threadIdx.x == 64) tc_stamp(P, tl, g_next, 2);
         };
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ++tl;
             const long long base = tile * kTcRows;
             const int nv = (int)min((long long)kTcRows, n_act - base);
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -369,15 +391,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     *s.n_runs = n;
                 }
             }
-            int gi = 0;
+            gi = 0;
             if (P.n_sem > 0) {
                 tc_build_xyz(s, r, p, P.pe_sem);
-                tc_publish_a(s);
+                publish(gi);
                 for (int l = 0; l < P.n_sem; ++l, ++gi) {
                     wait_d();
                     if (l + 1 < P.n_sem) {
                         tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
-                        tc_publish_a(s);
+                        publish(gi + 1);
                     } else {
                         tc_epilogue_final(s, r, P.n_cls, P.bias_off[gi]);
                     }
@@ -404,12 +426,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 const int width = P.d_ins * (P.slow_fast ? 2 : 1);
                 for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
                     tc_build_xyz(s, r, p, P.pe_ins);
-                    tc_publish_a(s);
+                    publish(gi);
                     for (int l = 0; l < P.n_ins; ++l, ++gi) {
                         wait_d();
                         if (l + 1 < P.n_ins) {
                             tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
-                            tc_publish_a(s);
+                            publish(gi + 1);
                         } else {
                             tc_epilogue_final(s, r, P.d_ins, P.bias_off[gi]);
                         }
@@ -430,7 +452,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     const Tap1 t1 = make_tap1(xs[mode_v(mode)], f.ll[mode]);
 #pragma unroll
                     for (int v8 = 0; v8 < NV * 2; ++v8) {
-                        if (((mode * NV * 2 + v8) & 1) != r.half) continue;   // warp-uniform
+                        if (((mode * NV * 2 + v8) % kTcParts) != r.half) continue;   // warp-uniform
                         const int ch = v8 * 8;
                         const float4 pa = plane_tap(f.plane[mode], t2, f.pw[mode], f.comps, ch);
                         const float4 la = line_tap(f.line[mode], t1, f.comps, ch);
@@ -441,7 +463,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                         tc_put8(s, r.lane_base, row, mode * f.comps + ch, v);
                     }
                 }
-                tc_publish_a(s);
+                publish(gi);
                 wait_d();   // basis GEMM: features in D columns [0, dim_app)
                 const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
                 if (r.half == 0) {
@@ -464,7 +486,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 }
                 // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418)
                 const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
-                for (int k0 = r.half * 8; k0 < n_in; k0 += 16) {
+                for (int k0 = r.half * 8; k0 < n_in; k0 += 8 * kTcParts) {
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -488,12 +510,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     }
                     tc_put8(s, r.lane_base, row, k0, v);
                 }
-                tc_publish_a(s);
+                publish(gi);
                 for (int l = 0; l < P.n_rgb; ++l, ++gi) {
                     wait_d();
                     if (l + 1 < P.n_rgb) {
                         tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
-                        tc_publish_a(s);
+                        publish(gi + 1);
                     } else {
                         tc_epilogue_final(s, r, 3, P.bias_off[gi]);
                     }
@@ -560,6 +582,9 @@ bool heads_tc_available(const clift_field* f, int heads) {
     return true;
 }
 
+static long long* g_tc_trace = nullptr;
+void set_tc_trace(long long* p) { g_tc_trace = p; }
+
 int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
                             int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream) {
     TcHeadsParams P;
@@ -582,6 +607,7 @@ int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* fiel
     P.rgb_raw = rgb_raw;
     P.sem_raw = sem_raw;
     P.ins = ins;
+    P.trace = g_tc_trace;
     bool ok = true;
     if (sem_raw) {
         P.n_sem = field->semantic.n_layers;
@@ -645,6 +671,11 @@ int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* fiel
 }  // namespace clift
 
 using namespace clift;
+
+extern "C" int32_t clift_debug_tc_trace(long long* device_buf) {
+    clift::set_tc_trace(device_buf);
+    return CLIFT_OK;
+}
 
 extern "C" int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in) {
     if (n_out <= 0 || n_in <= 0 || n_out > 256 || n_in > kTcMaxK) return CLIFT_ERR_UNSUPPORTED;

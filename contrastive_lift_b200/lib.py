@@ -82,6 +82,7 @@ SIGNATURES = {
     "clift_tc_weight_floats": (C.c_int64, [C.c_int32, C.c_int32]),
     "clift_pack_linear_tc": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_debug_tc_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_debug_tc_trace": (C.c_int32, [_vp]),
     "clift_gen_rays": (C.c_int32, [_fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "clift_sample_points": (C.c_int32, [C.POINTER(RenderCfg), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "clift_density": (C.c_int32, [C.POINTER(Field), _vp, C.c_int64, _vp, _vp]),

@@ -173,6 +173,11 @@ int32_t clift_pack_linear_tc(const float* w, float* dst, int32_t n_out, int32_t 
  * 3xTF32 split (one CTA).  Used by tests only. */
 int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, void* stream);
 
+/* Debug: device buffer of 4*24*6 int64 that CTA 0 of the tensor-core head kernel fills with clock64() stamps per
+ * (tile, GEMM): 0 accumulator seen, 1 next operand written, 2 operand published, 3 MMA thread saw operand,
+ * 4 MMAs issued.  null disables. */
+int32_t clift_debug_tc_trace(long long* device_buf);
+
 /* ---- R1-R4: util/ray.py:8-12,25-31,46-54,81-99 + dataset/base.py:211-219 ------------------------
  * rays[row*W+col] = [o(3), d(3), near, far]; intrinsics (3x3) and cam2world (4x4) are HOST row-major.
  * *bad_rays (device int32) counts rays whose sphere determinant is negative (the reference asserts). */
