@@ -15,27 +15,26 @@ namespace clift {
 namespace {
 
 constexpr int kTcRows = 128;            // records per tile = UMMA M
-constexpr int kTcParts = 4;             // threads per record (each takes every kTcParts-th column chunk)
+constexpr int kTcParts = 3;             // threads per record (each takes every kTcParts-th column chunk)
 constexpr int kTcRowThreads = kTcRows * kTcParts;
 constexpr int kTcThreads = 64 + kTcRowThreads;
 constexpr int kTcMaxK = 256;
-constexpr int kTcStages = 4;
+constexpr int kTcStages = 5;
 constexpr int kTcSlabK = 8;             // K rows per weight stage = one tcgen05.mma k-step
 constexpr int kTcStageFloats = 2 * kTcSlabK * 256;   // hi + lo, N up to 256
-constexpr int kTcFeatRows = 32;
 constexpr int kTcMaxGemms = 24;
-constexpr int kTcBiasFloats = 17 * 256;
+constexpr int kTcBiasFloats = 16 * 256;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemALo = 256;      // column offset of A_lo
 
 struct TcSmem {
     float* a_hi;        // [kTcMaxK/4][128][4]   (also the [c][128] scratch of the final epilogues)
     float* w;           // [kTcStages][kTcStageFloats]
-    float* feat;        // [32][128] appearance features of the tile (rgb input construction)
     float* bias;        // [kTcBiasFloats] all biases of the schedule, loaded once per CTA
     int* ray;           // [128]
     int* runs;          // [129]
     int* n_runs;        // [1]
+    int* code;          // [kTcMaxK] decode table of the rgb MLP input rows (kind | base << 2 | doublings << 10)
     uint64_t* full;     // [kTcStages]
     uint64_t* empty;    // [kTcStages]
     uint64_t* bar_a;    // A operand ready (row threads -> MMA)
@@ -44,19 +43,19 @@ struct TcSmem {
 };
 
 constexpr size_t kTcSmemBytes = (size_t)kTcMaxK * kTcRows * 4 + (size_t)kTcStages * kTcStageFloats * 4 +
-                                (size_t)kTcFeatRows * kTcRows * 4 + (size_t)kTcBiasFloats * 4 + (2 * kTcRows + 8) * 4 + 256;
+                                (size_t)kTcBiasFloats * 4 + (2 * kTcRows + 8) * 4 + (size_t)kTcMaxK * 4 + 256;
 static_assert(kTcSmemBytes <= 232448, "shared memory budget of one sm_100a CTA");
 
 __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
     TcSmem s;
     s.a_hi = reinterpret_cast<float*>(raw);
     s.w = s.a_hi + kTcMaxK * kTcRows;
-    s.feat = s.w + kTcStages * kTcStageFloats;
-    s.bias = s.feat + kTcFeatRows * kTcRows;
+    s.bias = s.w + kTcStages * kTcStageFloats;
     s.ray = reinterpret_cast<int*>(s.bias + kTcBiasFloats);
     s.runs = s.ray + kTcRows;
     s.n_runs = s.runs + kTcRows + 1;
-    s.full = reinterpret_cast<uint64_t*>(s.n_runs + 7);
+    s.code = s.n_runs + 7;
+    s.full = reinterpret_cast<uint64_t*>(s.code + kTcMaxK);
     s.empty = s.full + kTcStages;
     s.bar_a = s.empty + kTcStages;
     s.bar_d = s.bar_a + 1;
@@ -66,7 +65,7 @@ __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
 
 // One GEMM of the schedule: D[128 x n_pad] = A[128 x 8*k_steps] * W^T, weights packed by clift_pack_linear_tc.
 struct TcGemm {
-    const float* w;     // [k_steps][hi|lo][2][n_pad][4]
+    const float* w;     // [k_steps] slabs, see tc_issue for the two slab layouts
     int k_steps;        // ceil(K / 8)
     int n_pad;          // multiple of 32, <= 256
 };
@@ -77,36 +76,60 @@ struct PipeState {      // ring position; producer and MMA warps advance it iden
     __device__ __forceinline__ uint32_t phase() const { return (slab / kTcStages) & 1; }
 };
 
+// k-steps carried by one ring stage: small-N GEMMs pack several (their per-k-step slab is tiny, and one bulk copy +
+// barrier round trip per 2 KB would leave them latency-bound)
+__device__ __forceinline__ int tc_ksteps_per_stage(int n_pad) { return n_pad >= 256 ? 1 : 256 / n_pad; }
+
 // warp 0, one lane: stream the GEMM's weight slabs
 __device__ __forceinline__ void tc_produce(const TcSmem& s, const TcGemm& g, PipeState& ps) {
-    const uint32_t bytes = 2u * kTcSlabK * g.n_pad * 4u;
-    for (int i = 0; i < g.k_steps; ++i, ++ps.slab) {
+    const int per = tc_ksteps_per_stage(g.n_pad);
+    const uint32_t kstep_floats = 2u * kTcSlabK * g.n_pad;
+    for (int k0 = 0; k0 < g.k_steps; k0 += per, ++ps.slab) {
+        const uint32_t bytes = (uint32_t)min(per, g.k_steps - k0) * kstep_floats * 4u;
         tc::mbar_wait(&s.empty[ps.stage()], ps.phase() ^ 1);
         tc::mbar_arrive_expect_tx(&s.full[ps.stage()], bytes);
-        tc::bulk_load(s.w + (size_t)ps.stage() * kTcStageFloats, g.w + (size_t)i * (2 * kTcSlabK * g.n_pad), bytes, &s.full[ps.stage()]);
+        tc::bulk_load(s.w + (size_t)ps.stage() * kTcStageFloats, g.w + (size_t)k0 * kstep_floats, bytes, &s.full[ps.stage()]);
     }
 }
 
-// warp 1, one lane: issue the 3xTF32 MMAs of one GEMM
+// warp 1, one lane: issue the 3xTF32 MMAs of one GEMM.
+// n_pad > 128 : slab = [hi | lo][2 k-chunks][n_pad][4], three MMAs per k-step (A_hi*W_hi, A_hi*W_lo, A_lo*W_hi)
+// n_pad <= 128: slab = [2 k-chunks][hi | lo][n_pad][4]: one descriptor with 2*n_pad rows covers [W_hi ; W_lo], so
+//               A_hi*W_hi and A_hi*W_lo are ONE MMA writing D[:, 0:n_pad) and D[:, n_pad:2n_pad) (the epilogue adds
+//               the two column blocks) - small-N MMAs are latency-bound, not N-bound.
 __device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeState& ps, uint32_t tmem, uint32_t a_parity,
                                          long long* trace = nullptr) {
     const uint32_t idesc = tc::make_idesc_tf32(kTcRows, g.n_pad);
+    const uint32_t idesc2 = tc::make_idesc_tf32(kTcRows, 2 * g.n_pad);
     const uint32_t a_base = tc::smem_addr(s.a_hi);
-    const uint32_t w_lbo = (uint32_t)g.n_pad * 16u;
+    const uint32_t rows16 = (uint32_t)g.n_pad * 16u;
+    const bool stacked = g.n_pad <= 128;
+    const int per = tc_ksteps_per_stage(g.n_pad);
+    const uint32_t kstep_bytes = 2u * kTcSlabK * g.n_pad * 4u;
     tc::mbar_wait(s.bar_a, a_parity);
     tc::fence_after_sync();
     if (trace) trace[3] = clock64();
-    for (int ks = 0; ks < g.k_steps; ++ks, ++ps.slab) {
+    for (int k0 = 0; k0 < g.k_steps; k0 += per, ++ps.slab) {
         tc::mbar_wait(&s.full[ps.stage()], ps.phase());
         tc::fence_after_sync();
-        const uint32_t w_hi = tc::smem_addr(s.w + (size_t)ps.stage() * kTcStageFloats);
-        const uint32_t w_lo = w_hi + (uint32_t)kTcSlabK * g.n_pad * 4u;
-        const uint64_t a_desc = tc::make_smem_desc(a_base + (uint32_t)ks * 2u * (kTcRows * 16u), kTcRows * 16u, 128u);
-        const uint64_t bh = tc::make_smem_desc(w_hi, w_lbo, 128u);
-        const uint64_t bl = tc::make_smem_desc(w_lo, w_lbo, 128u);
-        tc::mma_ss(tmem, a_desc, bh, idesc, ks > 0 ? 1u : 0u);
-        tc::mma_ss(tmem, a_desc, bl, idesc, 1u);
-        tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
+        const uint32_t w_stage = tc::smem_addr(s.w + (size_t)ps.stage() * kTcStageFloats);
+        const int n_here = min(per, g.k_steps - k0);
+        for (int j = 0; j < n_here; ++j) {
+            const int ks = k0 + j;
+            const uint32_t w0 = w_stage + (uint32_t)j * kstep_bytes;
+            const uint64_t a_desc = tc::make_smem_desc(a_base + (uint32_t)ks * 2u * (kTcRows * 16u), kTcRows * 16u, 128u);
+            if (stacked) {
+                const uint64_t bh = tc::make_smem_desc(w0, 2u * rows16, 128u);
+                tc::mma_ss(tmem, a_desc, bh, idesc2, ks > 0 ? 1u : 0u);
+                tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
+            } else {
+                const uint64_t bh = tc::make_smem_desc(w0, rows16, 128u);
+                const uint64_t bl = tc::make_smem_desc(w0 + 2u * rows16, rows16, 128u);
+                tc::mma_ss(tmem, a_desc, bh, idesc, ks > 0 ? 1u : 0u);
+                tc::mma_ss(tmem, a_desc, bl, idesc, 1u);
+                tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
+            }
+        }
         tc::mma_commit(&s.empty[ps.stage()]);
     }
     tc::mma_commit(s.bar_d);
@@ -147,6 +170,20 @@ __device__ __forceinline__ RowId make_row_id(uint32_t tmem) {
     r.rt = threadIdx.x - 64;
     r.lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
     return r;
+}
+
+// 16 accumulator columns of this thread's record; stacked GEMMs (n_pad <= 128) keep A_hi*W_lo in columns [n_pad, 2 n_pad)
+__device__ __forceinline__ void tc_ld_acc16(const RowId& r, int c0, int n_pad, float* v) {
+    tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
+    if (n_pad <= 128) {
+        float u[16];
+        tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c0), u);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += u[i];
+    } else {
+        tc::tmem_wait_ld();
+    }
 }
 
 __device__ __forceinline__ void tc_init(const TcSmem& s) {
@@ -197,8 +234,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_gemm_test_kernel(const float
         tc::fence_after_sync();
         for (int c0 = r.half * 16; c0 < g.n_pad; c0 += 16 * kTcParts) {
             float v[16];
-            tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
-            tc::tmem_wait_ld();
+            tc_ld_acc16(r, c0, g.n_pad, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) out[(size_t)r.row * g.n_pad + c0 + i] = v[i];
         }
@@ -242,14 +278,19 @@ __device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, const RowId&
     constexpr int kStride = 16 * kTcParts;
     const int c_begin = r.half * 16;
     if (c_begin >= n_pad) return;
-    float nxt[16];
+    const bool stacked = n_pad <= 128;
+    float nxt[16], nxt2[16];
     tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, nxt);
+    if (stacked) tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c_begin), nxt2);
     for (int c0 = c_begin; c0 < n_pad; c0 += kStride) {
         float v[16];
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = nxt[i];
-        if (c0 + kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), nxt);
+        for (int i = 0; i < 16; ++i) v[i] = stacked ? nxt[i] + nxt2[i] : nxt[i];
+        if (c0 + kStride < n_pad) {
+            tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), nxt);
+            if (stacked) tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c0 + kStride), nxt2);
+        }
         if (bias_off >= 0) {
             const float4* b4 = reinterpret_cast<const float4*>(s.bias + bias_off + c0);
 #pragma unroll
@@ -268,17 +309,53 @@ __device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, const RowId&
     }
 }
 
-// final-layer epilogue (half 0 threads): D (+bias) -> scratch[c][row] for c < n_out (scratch = a_hi region)
-__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, const RowId& r, int n_out, int bias_off) {
+// final-layer epilogue (part 0 threads): D (+bias) -> scratch[c][row] for c < n_out (scratch = a_hi region)
+__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, const RowId& r, int n_out, int n_pad, int bias_off) {
     if (r.half != 0) return;
     for (int c0 = 0; c0 < n_out; c0 += 16) {
         float v[16];
-        tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
-        tc::tmem_wait_ld();
+        tc_ld_acc16(r, c0, n_pad, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if (c0 + i < n_out) s.a_hi[(size_t)(c0 + i) * kTcRows + r.row] = v[i] + (bias_off >= 0 ? s.bias[bias_off + c0 + i] : 0.0f);
     }
+}
+
+// semantic final layer for n_cls <= 32: logits stay in registers -> (+bias) -> softmax -> * w -> scratch[c][row]
+__device__ __forceinline__ void tc_epilogue_semantic32(const TcSmem& s, const RowId& r, int n_cls, int n_pad, int bias_off, int softmax,
+                                                       float w) {
+    if (r.half != 0) return;
+    float v[32];
+    tc_ld_acc16(r, 0, n_pad, v);
+    if (n_cls > 16) {
+        tc_ld_acc16(r, 16, n_pad, v + 16);
+    } else {
+#pragma unroll
+        for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += (bias_off >= 0 && i < n_cls) ? s.bias[bias_off + i] : 0.0f;
+    if (softmax) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < n_cls) mx = fmaxf(mx, v[i]);
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            v[i] = i < n_cls ? expf(v[i] - mx) : 0.0f;
+            tot += v[i];
+        }
+        const float sc = w / tot;            // one division per record (the FMA kernel divides per class: 1 ulp apart)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= sc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= w;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < n_cls) s.a_hi[(size_t)i * kTcRows + r.row] = v[i];
 }
 
 // xyz (+ sin/cos PE, dimension-major frequency-minor) -> A operand, zero padded to a multiple of 8
@@ -305,16 +382,29 @@ __device__ __forceinline__ void tc_build_xyz(const TcSmem& s, const RowId& r, co
     }
 }
 
-// row threads: sum rows [0,nch) of scratch over each ray run (fixed order) and add into dst[ray*stride + col0 + c]
+// row threads: sum rows [0,nch) of scratch over each ray run and add into dst[ray*stride + col0 + c].  Four adjacent
+// lanes share one (run, channel) item: each sums a contiguous quarter of the run, then a fixed-order shuffle tree
+// combines them (bit-reproducible), so the dependent-add chain is a quarter of the run length.
 __device__ __forceinline__ void tc_reduce_runs(const TcSmem& s, int rt, int nch, float* __restrict__ dst, int stride, int col0) {
     tc::named_bar_sync(1, kTcRowThreads);
     const int n_runs = *s.n_runs;
-    for (int idx = rt; idx < n_runs * nch; idx += kTcRowThreads) {
-        const int r = idx / nch, c = idx - r * nch;
-        const int m0 = s.runs[r], m1 = s.runs[r + 1];
+    const int items = n_runs * nch, sub = rt & 3;
+    for (int base = 0; base < items; base += kTcRowThreads / 4) {
+        const int idx = base + (rt >> 2);
         float acc = 0.0f;
-        for (int m = m0; m < m1; ++m) acc += s.a_hi[(size_t)c * kTcRows + m];
-        atomicAdd(dst + (int64_t)s.ray[m0] * stride + col0 + c, acc);
+        int ray = 0, c = 0;
+        if (idx < items) {
+            const int rr = idx / nch;
+            c = idx - rr * nch;
+            const int m0 = s.runs[rr], m1 = s.runs[rr + 1];
+            const int len = m1 - m0, q = (len + 3) >> 2;
+            const int a = m0 + min(sub * q, len), b = m0 + min((sub + 1) * q, len);
+            for (int m = a; m < b; ++m) acc += s.a_hi[(size_t)c * kTcRows + m];
+            ray = s.ray[m0];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (idx < items && sub == 0) atomicAdd(dst + (int64_t)ray * stride + col0 + c, acc);
     }
     tc::named_bar_sync(1, kTcRowThreads);
 }
@@ -327,6 +417,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
     for (int gi = 0; gi < P.n_gemms; ++gi)
         if (P.bias_off[gi] >= 0)
             for (int i = threadIdx.x; i < P.g[gi].n_pad; i += kTcThreads) s.bias[P.bias_off[gi] + i] = P.bias[gi][i];
+    if (P.n_rgb > 0) {   // decode table of the rgb MLP input rows
+        const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
+        const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
+        for (int q = threadIdx.x; q < kTcMaxK; q += kTcThreads) {
+            int kind = 3, b = 0, f = 0;
+            if (q < o_sf) {
+                kind = 0, b = q;
+            } else if (q < o_sd) {
+                const int j = (q < o_cf) ? q - o_sf : q - o_cf;
+                kind = q < o_cf ? 1 : 2, b = j / pf, f = j % pf;
+            } else if (q < n_in) {
+                const int j = (q < o_cd) ? q - o_sd : q - o_cd;
+                kind = q < o_cd ? 1 : 2, b = A + j / pv, f = j % pv;
+            }
+            s.code[q] = kind | (b << 2) | (f << 10);
+        }
+    }
     tc_init(s);
     const uint32_t tmem = *s.tmem_base;
     const long long n_act = min((long long)P.stats[0], P.cap);
@@ -400,11 +507,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     if (l + 1 < P.n_sem) {
                         tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
                         publish(gi + 1);
+                    } else if (P.n_cls <= 32) {
+                        tc_epilogue_semantic32(s, r, P.n_cls, P.g[gi].n_pad, P.bias_off[gi], P.softmax, p.w);
                     } else {
-                        tc_epilogue_final(s, r, P.n_cls, P.bias_off[gi]);
+                        tc_epilogue_final(s, r, P.n_cls, P.g[gi].n_pad, P.bias_off[gi]);
                     }
                 }
-                if (r.half == 0) {   // softmax over the thread's own column of the scratch, then the compositing weight
+                if (r.half == 0 && P.n_cls > 32) {   // wide heads: softmax over the thread's own column of the scratch
                     if (P.softmax) {
                         float mx = -INFINITY;
                         for (int c = 0; c < P.n_cls; ++c) mx = fmaxf(mx, s.a_hi[(size_t)c * kTcRows + row]);
@@ -433,7 +542,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                             tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
                             publish(gi + 1);
                         } else {
-                            tc_epilogue_final(s, r, P.d_ins, P.bias_off[gi]);
+                            tc_epilogue_final(s, r, P.d_ins, P.g[gi].n_pad, P.bias_off[gi]);
                         }
                     }
                     if (r.half == 0)
@@ -466,45 +575,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 publish(gi);
                 wait_d();   // basis GEMM: features in D columns [0, dim_app)
                 const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
+                const int n_base = A + 3;
+                // staging behind the K rows of the first rgb GEMM: base values x_b (A features + 3 direction
+                // components), then sin x_b, then cos x_b, each [n_base][128]
+                float* xb = s.a_hi + (size_t)P.g[gi + 1].k_steps * 8 * kTcRows;
+                float* sb = xb + (size_t)n_base * kTcRows;
+                float* cb = sb + (size_t)n_base * kTcRows;
                 if (r.half == 0) {
                     for (int c0 = 0; c0 < A; c0 += 16) {
                         float v[16];
-                        tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
-                        tc::tmem_wait_ld();
+                        tc_ld_acc16(r, c0, P.g[gi].n_pad, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c0 + i < A) s.feat[(size_t)(c0 + i) * kTcRows + row] = v[i];
+                            if (c0 + i < A) xb[(size_t)(c0 + i) * kTcRows + row] = v[i];
                     }
+                } else if (r.half == 1 && ray >= 0) {
+                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kTcRows + row] = __ldg(P.rays + (int64_t)ray * 8 + 3 + k);
+                } else if (r.half == 1) {
+                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kTcRows + row] = k == 2 ? 1.0f : 0.0f;
                 }
                 ++gi;
                 tc::named_bar_sync(1, kTcRowThreads);
-                float dir[3] = {0.f, 0.f, 1.f};
-                if (ray >= 0) {
-                    dir[0] = __ldg(P.rays + (int64_t)ray * 8 + 3);
-                    dir[1] = __ldg(P.rays + (int64_t)ray * 8 + 4);
-                    dir[2] = __ldg(P.rays + (int64_t)ray * 8 + 5);
+                // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418):
+                // one sincosf per base value, higher frequencies by angle doubling
+                for (int b = r.half; b < n_base; b += kTcParts) {
+                    float sv, cv;
+                    sincosf(xb[(size_t)b * kTcRows + row], &sv, &cv);
+                    sb[(size_t)b * kTcRows + row] = sv;
+                    cb[(size_t)b * kTcRows + row] = cv;
                 }
-                // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418)
-                const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
+                tc::named_bar_sync(1, kTcRowThreads);
+                const int n_in = A * (1 + 2 * pf) + 3 * (1 + 2 * pv);
                 for (int k0 = r.half * 8; k0 < n_in; k0 += 8 * kTcParts) {
                     float v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int q = k0 + i;
+                        const int code = s.code[k0 + i];       // kind | base << 2 | doublings << 10 ; kind 3 = zero pad
+                        const int kind = code & 3, b = (code >> 2) & 255, f = code >> 10;
                         float x = 0.0f;
-                        if (q < A) {
-                            x = s.feat[(size_t)q * kTcRows + row];
-                        } else if (q < o_sf) {
-                            x = q - A == 0 ? dir[0] : (q - A == 1 ? dir[1] : dir[2]);
-                        } else if (q < o_sd) {
-                            const int j = (q < o_cf) ? q - o_sf : q - o_cf;
-                            const float arg = s.feat[(size_t)(j / pf) * kTcRows + row] * (float)(1 << (j % pf));
-                            x = (q < o_cf) ? sinf(arg) : cosf(arg);
-                        } else if (q < n_in) {
-                            const int j = (q < o_cd) ? q - o_sd : q - o_cd;
-                            const int d = j / pv;
-                            const float arg = (d == 0 ? dir[0] : (d == 1 ? dir[1] : dir[2])) * (float)(1 << (j % pv));
-                            x = (q < o_cd) ? sinf(arg) : cosf(arg);
+                        if (kind == 0) {
+                            x = xb[(size_t)b * kTcRows + row];
+                        } else if (kind != 3) {
+                            float sv = sb[(size_t)b * kTcRows + row], cv = cb[(size_t)b * kTcRows + row];
+                            for (int d = 0; d < f; ++d) {   // (sin, cos)(2t) from (sin, cos)(t)
+                                const float s2 = 2.0f * sv * cv, c2 = 1.0f - 2.0f * sv * sv;
+                                sv = s2;
+                                cv = c2;
+                            }
+                            x = kind == 1 ? sv : cv;
                         }
                         v[i] = x;
                     }
@@ -517,7 +635,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                         tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
                         publish(gi + 1);
                     } else {
-                        tc_epilogue_final(s, r, 3, P.bias_off[gi]);
+                        tc_epilogue_final(s, r, 3, P.g[gi].n_pad, P.bias_off[gi]);
                     }
                 }
                 if (r.half == 0)
@@ -534,7 +652,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
     if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
 }
 
-// W [out][in] -> [k-step][hi|lo][2 k-chunks][n_pad][4]  (zero padded; hi/lo tf32-exact)
+// W [out][in] -> per k-step slab, [hi|lo][2 k-chunks][n_pad][4] for n_pad > 128 else [2 k-chunks][hi|lo][n_pad][4]
+// (zero padded; hi/lo tf32-exact)
 __global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, int n_in, float* __restrict__ dst, int n_pad, int slabs) {
     const int64_t total = (int64_t)slabs * kTcSlabK * n_pad;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -545,9 +664,15 @@ __global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, in
     tc::split_tf32(x, hi, lo);
     const int slab = k / kTcSlabK, kc = (k % kTcSlabK) / 4, ki = k & 3;   // kc in {0,1}
     float* base = dst + (size_t)slab * (2 * kTcSlabK * n_pad);
-    const size_t off = ((size_t)kc * n_pad + n) * 4 + ki;
-    base[off] = hi;
-    base[(size_t)kTcSlabK * n_pad + off] = lo;
+    if (n_pad <= 128) {   // [k chunk][hi | lo][n_pad][4]
+        const size_t off = ((size_t)(kc * 2) * n_pad + n) * 4 + ki;
+        base[off] = hi;
+        base[(size_t)n_pad * 4 + off] = lo;
+    } else {              // [hi | lo][k chunk][n_pad][4]
+        const size_t off = ((size_t)kc * n_pad + n) * 4 + ki;
+        base[off] = hi;
+        base[(size_t)kTcSlabK * n_pad + off] = lo;
+    }
 }
 
 }  // namespace
@@ -578,7 +703,11 @@ bool heads_tc_available(const clift_field* f, int heads) {
     };
     if ((heads & CLIFT_HEAD_SEMANTIC) && !ok(f->semantic)) return false;
     if ((heads & CLIFT_HEAD_INSTANCE) && (!ok(f->instance_fast) || (f->slow_fast && !ok(f->instance_slow)))) return false;
-    if ((heads & CLIFT_HEAD_RGB) && (!ok(f->rgb) || !f->basis_tc || f->dim_appearance > kTcFeatRows || f->appearance_comps % 8)) return false;
+    if (heads & CLIFT_HEAD_RGB) {
+        if (!ok(f->rgb) || !f->basis_tc || f->dim_appearance > 64 || f->appearance_comps % 8) return false;
+        // the base/sin/cos staging of the rgb input lives behind the K rows of the first rgb GEMM
+        if ((int)round_up(f->rgb.dims[0], 8) + 3 * (f->dim_appearance + 3) > kTcMaxK) return false;
+    }
     return true;
 }
 
