@@ -62,17 +62,24 @@ class _Render(torch.autograd.Function):
         for k, v in t.items():
             setattr(out, k, L.ptr(v))
         out.save_for_backward = 1 if need_grad else 0
-        cap = renderer.max_active(B)
+        cap = renderer.max_active(B, need_grad)
         while True:
             nbytes = lib.clift_render_workspace_bytes(C.byref(cfg), C.byref(pk.field), B, cap, out.save_for_backward)
             if nbytes < 0:
                 L.check(int(nbytes))
-            ws = _workspace(dev, nbytes)
+            if need_grad:
+                # a training forward owns its workspace until its backward ran (several chunks may be in flight,
+                # trainer:105-123); the caching allocator makes this a pointer bump after the first step
+                ws = torch.empty((int(nbytes),), dtype=torch.uint8, device=dev)
+                _WORKSPACES[dev] = ws
+            else:
+                ws = _workspace(dev, nbytes)
             L.check(lib.clift_render_forward(C.byref(cfg), C.byref(pk.field), L.ptr(rays), L.ptr(jitter), B, int(add_bg),
                                              L.ptr(ws), ws.numel(), cap, C.byref(out), L.stream_ptr(dev)))
             if B == 0 or not renderer.check_overflow:
                 break
             n_act, _, overflow, _ = renderer.last_stats(dev)       # one 32-byte D2H (the reference syncs ~10x per call)
+            renderer._active_per_ray = max(1.0, n_act / max(B, 1))
             if not overflow:
                 break
             cap = (n_act + 127) // 128 * 128                          # rerun with the exact active-sample count
@@ -84,7 +91,6 @@ class _Render(torch.autograd.Function):
             ctx.t = {k: t[k] for k in ("rgb_raw", "semantic_raw", "opacity") if k in t}
             ctx.ws = ws
             ctx.param_names = [n for n, _ in model.named_parameters()]
-            renderer._live_ctx = ctx
         empty = rays.new_zeros((0,))
         res = (t.get("rgb", empty), t.get("semantic", empty), t.get("instance", empty), t["depth"],
                t["dist_reg"].reshape(()) if "dist_reg" in t else empty, t.get("points", empty))
@@ -97,9 +103,8 @@ class _Render(torch.autograd.Function):
         if not ctx.need_grad:
             raise L.CliftError("backward through a render that was run without need_grad")
         renderer, model, pk = ctx.renderer, ctx.model, ctx.pk
-        if renderer._live_ctx is not ctx:
-            raise L.CliftError("the render workspace was overwritten by a later render call before backward ran: "
-                               "call backward before the next training-mode render on this renderer")
+        if ctx.ws is None:
+            raise L.CliftError("backward called twice on the same render (its saved state was consumed)")
         lib = L.load()
         dev = ctx.rays.device
         heads = ctx.heads
@@ -119,7 +124,7 @@ class _Render(torch.autograd.Function):
                                           int(ctx.add_bg), L.ptr(ctx.ws), ctx.ws.numel(), ctx.cap,
                                           C.byref(saved), L.ptr(g_rgb), L.ptr(g_sem), L.ptr(g_ins), L.ptr(g_dist),
                                           C.byref(fg), L.stream_ptr(dev)))
-        renderer._live_ctx = None
+        ctx.ws = None        # consumed
         st = L.stream_ptr(dev)
         grads = {}
         if want_density:
@@ -185,7 +190,7 @@ class TensoRFRenderer(nn.Module):
         self.check_overflow = True
         # lib.HEADS_AUTO: tcgen05 tensor-core heads for inference, FP32-FMA heads for training forwards
         self.head_path = L.HEADS_AUTO
-        self._live_ctx = None
+        self._active_per_ray = None
         self._host = None
         self.last_opacity = None
         self.update_step_size(self.grid_dim)
@@ -225,11 +230,16 @@ class TensoRFRenderer(nn.Module):
         target_res = ((xyz_max - xyz_min) / voxel_size).long().tolist()
         return tuple(max(x, 1) for x in target_res)
 
-    def max_active(self, n_rays: int) -> int:
-        """<= 0 means worst case (every sample active) to the C ABI."""
+    def max_active(self, n_rays: int, training: bool = False) -> int:
+        """<= 0 means worst case (every sample active) to the C ABI.  Training forwards size their activation stash
+        by this capacity, so they follow the measured active count of the previous call (x1.5) instead of the
+        static per-ray bound; an overflow still repeats the call at the exact size."""
         if self.max_active_per_ray <= 0:
             return 0
-        return max(128, int(n_rays) * min(int(self.max_active_per_ray), int(self.n_samples)))
+        per_ray = min(int(self.max_active_per_ray), int(self.n_samples))
+        if training and self.check_overflow and self._active_per_ray is not None:
+            per_ray = min(per_ray, int(self._active_per_ray * 1.5) + 8)
+        return max(128, int(n_rays) * per_ray)
 
     # ---- descriptor for the C ABI -----------------------------------------------------------------
     def _cfg(self, model: TensorVMSplit, heads: int) -> L.RenderCfg:

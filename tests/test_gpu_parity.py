@@ -347,3 +347,27 @@ def test_full_size_properties(path):
     assert gpu.rel_err(ins[pick.cuda()], ref[2]) < REL
     assert gpu.rel_err(depth[pick.cuda()], ref[3]) < REL
     assert gpu.rel_err(sem[pick.cuda()].exp(), ref[1].exp()) < REL
+
+
+def test_chunked_training_forward_then_one_backward():
+    """TensoRFTrainer.forward renders the batch in chunks and backpropagates once (trainer:105-123)."""
+    fx, params, cfg, rays, model, rend = case("render_a")
+    r = rays.cuda()
+    w = torch.linspace(0.2, 1.0, r.shape[0] * 3, device="cuda").view(-1, 3)
+
+    def run(chunks):
+        model.zero_grad(set_to_none=True)
+        outs = [rend(model, r[b:e].contiguous(), 0.0, True, True) for b, e in chunks]
+        rgb = torch.cat([o[0] for o in outs])
+        sem = torch.cat([o[1] for o in outs])
+        dist = torch.stack([o[5] for o in outs]).mean()          # trainer:116,122 averages dist_reg over chunks
+        ((rgb * w).sum() / r.shape[0] + 0.3 * dist - 0.01 * sem[:, 1].mean()).backward()
+        return {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    n = r.shape[0]
+    whole = run([(0, n)])
+    split = run([(0, n // 2), (n // 2, n)])
+    for k in whole:
+        if k.startswith(("density", "appearance", "render_appearance", "render_semantic")):
+            # dist_reg is a per-chunk mean, so equal chunks reproduce the single-call value (n is even)
+            assert gpu.rel_err(split[k], whole[k]) < 2e-3, k
