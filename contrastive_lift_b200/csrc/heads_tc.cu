@@ -23,14 +23,14 @@ constexpr int kTcStages = 5;
 constexpr int kTcSlabK = 8;             // K rows per weight stage = one tcgen05.mma k-step
 constexpr int kTcStageFloats = 2 * kTcSlabK * 256;   // hi + lo, N up to 256
 constexpr int kTcMaxGemms = 24;
-constexpr int kTcBiasFloats = 16 * 256;
+constexpr int kTcOnesFloats = 2 * kTcRows * 4;   // A chunk [2 k-chunks][128][4] with column 0 = 1 (bias k-step)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kTmemALo = 256;      // column offset of A_lo
 
 struct TcSmem {
     float* a_hi;        // [kTcMaxK/4][128][4]   (also the [c][128] scratch of the final epilogues)
     float* w;           // [kTcStages][kTcStageFloats]
-    float* bias;        // [kTcBiasFloats] all biases of the schedule, loaded once per CTA
+    float* ones;        // [kTcOnesFloats] constant A operand of the bias k-step: A[m][0] = 1, A[m][1..7] = 0
     int* ray;           // [128]
     int* runs;          // [129]
     int* n_runs;        // [1]
@@ -43,15 +43,15 @@ struct TcSmem {
 };
 
 constexpr size_t kTcSmemBytes = (size_t)kTcMaxK * kTcRows * 4 + (size_t)kTcStages * kTcStageFloats * 4 +
-                                (size_t)kTcBiasFloats * 4 + (2 * kTcRows + 8) * 4 + (size_t)kTcMaxK * 4 + 256;
+                                (size_t)kTcOnesFloats * 4 + (2 * kTcRows + 8) * 4 + (size_t)kTcMaxK * 4 + 256;
 static_assert(kTcSmemBytes <= 232448, "shared memory budget of one sm_100a CTA");
 
 __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
     TcSmem s;
     s.a_hi = reinterpret_cast<float*>(raw);
     s.w = s.a_hi + kTcMaxK * kTcRows;
-    s.bias = s.w + kTcStages * kTcStageFloats;
-    s.ray = reinterpret_cast<int*>(s.bias + kTcBiasFloats);
+    s.ones = s.w + kTcStages * kTcStageFloats;
+    s.ray = reinterpret_cast<int*>(s.ones + kTcOnesFloats);
     s.runs = s.ray + kTcRows;
     s.n_runs = s.runs + kTcRows + 1;
     s.code = s.n_runs + 7;
@@ -68,12 +68,19 @@ struct TcGemm {
     const float* w;     // [k_steps] slabs, see tc_issue for the two slab layouts
     int k_steps;        // ceil(K / 8)
     int n_pad;          // multiple of 32, <= 256
+    int has_bias;       // 1: one more slab follows whose k row 0 is the bias; its A operand is the constant ones chunk,
+                        //    so the bias add is one extra MMA k-step instead of an add per accumulator element
 };
 
 struct PipeState {      // ring position; producer and MMA warps advance it identically
-    uint32_t slab = 0;
-    __device__ __forceinline__ int stage() const { return slab % kTcStages; }
-    __device__ __forceinline__ uint32_t phase() const { return (slab / kTcStages) & 1; }
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == kTcStages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
 };
 
 // k-steps carried by one ring stage: small-N GEMMs pack several (their per-k-step slab is tiny, and one bulk copy +
@@ -84,53 +91,66 @@ __device__ __forceinline__ int tc_ksteps_per_stage(int n_pad) { return n_pad >= 
 __device__ __forceinline__ void tc_produce(const TcSmem& s, const TcGemm& g, PipeState& ps) {
     const int per = tc_ksteps_per_stage(g.n_pad);
     const uint32_t kstep_floats = 2u * kTcSlabK * g.n_pad;
-    for (int k0 = 0; k0 < g.k_steps; k0 += per, ++ps.slab) {
-        const uint32_t bytes = (uint32_t)min(per, g.k_steps - k0) * kstep_floats * 4u;
-        tc::mbar_wait(&s.empty[ps.stage()], ps.phase() ^ 1);
-        tc::mbar_arrive_expect_tx(&s.full[ps.stage()], bytes);
-        tc::bulk_load(s.w + (size_t)ps.stage() * kTcStageFloats, g.w + (size_t)k0 * kstep_floats, bytes, &s.full[ps.stage()]);
+    const int steps = g.k_steps + g.has_bias;
+    for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
+        const uint32_t bytes = (uint32_t)min(per, steps - k0) * kstep_floats * 4u;
+        tc::mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+        tc::mbar_arrive_expect_tx(&s.full[ps.stage], bytes);
+        tc::bulk_load(s.w + (size_t)ps.stage * kTcStageFloats, g.w + (size_t)k0 * kstep_floats, bytes, &s.full[ps.stage]);
     }
 }
 
-// warp 1, one lane: issue the 3xTF32 MMAs of one GEMM.
+// warp 1, one lane: issue the 3xTF32 MMAs of one GEMM.  The issuing thread has ~384 cycles per k-step before it, not
+// the tensor pipe, becomes the limiter, so descriptors are running values updated by adds (low word = address >> 4).
 // n_pad > 128 : slab = [hi | lo][2 k-chunks][n_pad][4], three MMAs per k-step (A_hi*W_hi, A_hi*W_lo, A_lo*W_hi)
 // n_pad <= 128: slab = [2 k-chunks][hi | lo][n_pad][4]: one descriptor with 2*n_pad rows covers [W_hi ; W_lo], so
 //               A_hi*W_hi and A_hi*W_lo are ONE MMA writing D[:, 0:n_pad) and D[:, n_pad:2n_pad) (the epilogue adds
 //               the two column blocks) - small-N MMAs are latency-bound, not N-bound.
+// bias        : the slab after the last K slab carries the bias in its k row 0; its A operand is the constant ones
+//               chunk (exact in tf32, so no A_lo term).
 __device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeState& ps, uint32_t tmem, uint32_t a_parity,
                                          long long* trace = nullptr) {
     const uint32_t idesc = tc::make_idesc_tf32(kTcRows, g.n_pad);
-    const uint32_t idesc2 = tc::make_idesc_tf32(kTcRows, 2 * g.n_pad);
-    const uint32_t a_base = tc::smem_addr(s.a_hi);
-    const uint32_t rows16 = (uint32_t)g.n_pad * 16u;
+    const uint32_t rows16 = (uint32_t)g.n_pad;                          // n_pad*16 bytes >> 4
     const bool stacked = g.n_pad <= 128;
+    const uint32_t idesc_ss = stacked ? tc::make_idesc_tf32(kTcRows, 2 * g.n_pad) : idesc;
     const int per = tc_ksteps_per_stage(g.n_pad);
-    const uint32_t kstep_bytes = 2u * kTcSlabK * g.n_pad * 4u;
+    const uint32_t kstep16 = 2u * kTcSlabK * g.n_pad * 4u >> 4;         // bytes of one k-step slab >> 4
+    constexpr uint32_t kStage16 = kTcStageFloats * 4u >> 4;
+    // descriptor words: high = SBO (128 B) | version 1 ; low = address>>4 | LBO<<16
+    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo = (kTcRows * 16u >> 4) << 16;
+    const uint32_t b_lbo = (stacked ? 2u * rows16 : rows16) << 16;
+    uint32_t a_lo = (tc::smem_addr(s.a_hi) >> 4) | a_lbo;
+    const uint32_t ones_lo = (tc::smem_addr(s.ones) >> 4) | a_lbo;
+    const uint32_t w_lo0 = (tc::smem_addr(s.w) >> 4) | b_lbo;
+    const uint32_t lo_off = stacked ? 0u : 2u * rows16;                 // W_lo block inside a non-stacked slab
+    uint32_t a_tmem = tmem + kTmemALo;
+    auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+
     tc::mbar_wait(s.bar_a, a_parity);
     tc::fence_after_sync();
     if (trace) trace[3] = clock64();
-    for (int k0 = 0; k0 < g.k_steps; k0 += per, ++ps.slab) {
-        tc::mbar_wait(&s.full[ps.stage()], ps.phase());
+    const int steps = g.k_steps + g.has_bias;
+    uint32_t acc = 0u;
+    for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
+        tc::mbar_wait(&s.full[ps.stage], ps.phase);
         tc::fence_after_sync();
-        const uint32_t w_stage = tc::smem_addr(s.w + (size_t)ps.stage() * kTcStageFloats);
-        const int n_here = min(per, g.k_steps - k0);
-        for (int j = 0; j < n_here; ++j) {
-            const int ks = k0 + j;
-            const uint32_t w0 = w_stage + (uint32_t)j * kstep_bytes;
-            const uint64_t a_desc = tc::make_smem_desc(a_base + (uint32_t)ks * 2u * (kTcRows * 16u), kTcRows * 16u, 128u);
-            if (stacked) {
-                const uint64_t bh = tc::make_smem_desc(w0, 2u * rows16, 128u);
-                tc::mma_ss(tmem, a_desc, bh, idesc2, ks > 0 ? 1u : 0u);
-                tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
-            } else {
-                const uint64_t bh = tc::make_smem_desc(w0, rows16, 128u);
-                const uint64_t bl = tc::make_smem_desc(w0 + 2u * rows16, rows16, 128u);
-                tc::mma_ss(tmem, a_desc, bh, idesc, ks > 0 ? 1u : 0u);
-                tc::mma_ss(tmem, a_desc, bl, idesc, 1u);
-                tc::mma_ts(tmem, tmem + kTmemALo + (uint32_t)ks * 8u, bh, idesc, 1u);
-            }
+        if (trace && k0 == 0) trace[5] = clock64();
+        uint32_t w_lo = w_lo0 + (uint32_t)ps.stage * kStage16;
+        const int n_here = min(per, steps - k0);
+        for (int j = 0; j < n_here; ++j, w_lo += kstep16) {
+            const bool bias_step = k0 + j >= g.k_steps;
+            const uint64_t a_desc = desc(bias_step ? ones_lo : a_lo);
+            const uint64_t bh = desc(w_lo);
+            tc::mma_ss(tmem, a_desc, bh, idesc_ss, acc);
+            acc = 1u;
+            if (!stacked) tc::mma_ss(tmem, a_desc, desc(w_lo + lo_off), idesc, 1u);
+            if (!bias_step) tc::mma_ts(tmem, a_tmem, bh, idesc, 1u);
+            a_lo += 2u * (kTcRows * 16u >> 4);
+            a_tmem += 8u;
         }
-        tc::mma_commit(&s.empty[ps.stage()]);
+        tc::mma_commit(&s.empty[ps.stage]);
     }
     tc::mma_commit(s.bar_d);
     if (trace) trace[4] = clock64();
@@ -140,7 +160,10 @@ __device__ __forceinline__ void tc_issue(const TcSmem& s, const TcGemm& g, PipeS
 __device__ __forceinline__ void tc_put8(const TcSmem& s, uint32_t lane_base, int row, int k0, const float* v) {
     float hi[8], lo[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tc::split_tf32(v[i], hi[i], lo[i]);
+    for (int i = 0; i < 8; ++i) {   // hi is tf32-exact; lo = v - hi is exact in fp32 and is read as tf32 by the tensor core
+        hi[i] = __uint_as_float(__float_as_uint(v[i]) & 0xffffe000u);
+        lo[i] = v[i] - hi[i];
+    }
     float4* dst = reinterpret_cast<float4*>(s.a_hi + ((size_t)(k0 >> 2) * kTcRows + row) * 4);
     dst[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
     dst[kTcRows] = make_float4(hi[4], hi[5], hi[6], hi[7]);
@@ -187,6 +210,8 @@ __device__ __forceinline__ void tc_ld_acc16(const RowId& r, int c0, int n_pad, f
 }
 
 __device__ __forceinline__ void tc_init(const TcSmem& s) {
+    for (int i = threadIdx.x; i < kTcOnesFloats; i += kTcThreads) s.ones[i] = (i < kTcRows * 4 && (i & 3) == 0) ? 1.0f : 0.0f;
+    tc::fence_proxy_async_smem();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kTcStages; ++i) {
             tc::mbar_init(&s.full[i], 1);
@@ -259,8 +284,6 @@ struct TcHeadsParams {
     // GEMM schedule of one tile, in issue order: semantic | instance fast | instance slow | basis | rgb
     int n_gemms;
     TcGemm g[kTcMaxGemms];
-    const float* bias[kTcMaxGemms];   // [>= n_pad] or null
-    int bias_off[kTcMaxGemms];        // offset into the shared-memory bias table, -1 = no bias
     int n_sem, n_ins, n_rgb;          // layers per stack (0 = head off)
     float* rgb_raw;
     float* sem_raw;
@@ -272,58 +295,55 @@ __device__ __forceinline__ void tc_stamp(const TcHeadsParams& P, long long tile_
     if (P.trace && blockIdx.x == 0 && tile_local < 4) P.trace[(tile_local * kTcMaxGemms + gi) * 6 + slot] = clock64();
 }
 
-// hidden-layer epilogue: D -> +bias -> ReLU -> next layer's A operand.  A record's kTcParts threads take the 16-column
-// chunks round-robin; the next TMEM load is in flight while the current chunk is processed.
-__device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, const RowId& r, int n_pad, int bias_off) {
+// hidden-layer epilogue: D (bias already accumulated by the bias k-step) -> ReLU -> next layer's A operand.  A record's
+// kTcParts threads take the 16-column chunks round-robin; the next TMEM load is in flight while a chunk is processed.
+__device__ __forceinline__ void tc_relu_put16(const TcSmem& s, const RowId& r, int c0, float* v) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+    tc_put8(s, r.lane_base, r.row, c0, v);
+    tc_put8(s, r.lane_base, r.row, c0 + 8, v + 8);
+}
+
+__device__ __forceinline__ void tc_epilogue_hidden(const TcSmem& s, const RowId& r, int n_pad) {
     constexpr int kStride = 16 * kTcParts;
     const int c_begin = r.half * 16;
     if (c_begin >= n_pad) return;
-    const bool stacked = n_pad <= 128;
-    float nxt[16], nxt2[16];
-    tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, nxt);
-    if (stacked) tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c_begin), nxt2);
-    for (int c0 = c_begin; c0 < n_pad; c0 += kStride) {
-        float v[16];
+    if (n_pad <= 128) {   // stacked accumulator: columns [n_pad, 2 n_pad) hold A_hi * W_lo
+        for (int c0 = c_begin; c0 < n_pad; c0 += kStride) {
+            float v[16];
+            tc_ld_acc16(r, c0, n_pad, v);
+            tc_relu_put16(s, r, c0, v);
+        }
+        return;
+    }
+    float a[16], b[16];
+    tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, a);
+    for (int c0 = c_begin; c0 < n_pad; c0 += 2 * kStride) {
         tc::tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = stacked ? nxt[i] + nxt2[i] : nxt[i];
+        if (c0 + kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), b);
+        tc_relu_put16(s, r, c0, a);
         if (c0 + kStride < n_pad) {
-            tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), nxt);
-            if (stacked) tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c0 + kStride), nxt2);
+            tc::tmem_wait_ld();
+            if (c0 + 2 * kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + 2 * kStride), a);
+            tc_relu_put16(s, r, c0 + kStride, b);
         }
-        if (bias_off >= 0) {
-            const float4* b4 = reinterpret_cast<const float4*>(s.bias + bias_off + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 b = b4[i];
-                v[4 * i + 0] += b.x;
-                v[4 * i + 1] += b.y;
-                v[4 * i + 2] += b.z;
-                v[4 * i + 3] += b.w;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
-        tc_put8(s, r.lane_base, r.row, c0, v);
-        tc_put8(s, r.lane_base, r.row, c0 + 8, v + 8);
     }
 }
 
-// final-layer epilogue (part 0 threads): D (+bias) -> scratch[c][row] for c < n_out (scratch = a_hi region)
-__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, const RowId& r, int n_out, int n_pad, int bias_off) {
+// final-layer epilogue (part 0 threads): D -> scratch[c][row] for c < n_out (scratch = a_hi region)
+__device__ __forceinline__ void tc_epilogue_final(const TcSmem& s, const RowId& r, int n_out, int n_pad) {
     if (r.half != 0) return;
     for (int c0 = 0; c0 < n_out; c0 += 16) {
         float v[16];
         tc_ld_acc16(r, c0, n_pad, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (c0 + i < n_out) s.a_hi[(size_t)(c0 + i) * kTcRows + r.row] = v[i] + (bias_off >= 0 ? s.bias[bias_off + c0 + i] : 0.0f);
+            if (c0 + i < n_out) s.a_hi[(size_t)(c0 + i) * kTcRows + r.row] = v[i];
     }
 }
 
-// semantic final layer for n_cls <= 32: logits stay in registers -> (+bias) -> softmax -> * w -> scratch[c][row]
-__device__ __forceinline__ void tc_epilogue_semantic32(const TcSmem& s, const RowId& r, int n_cls, int n_pad, int bias_off, int softmax,
-                                                       float w) {
+// semantic final layer for n_cls <= 32: logits stay in registers -> softmax -> * w -> scratch[c][row]
+__device__ __forceinline__ void tc_epilogue_semantic32(const TcSmem& s, const RowId& r, int n_cls, int n_pad, int softmax, float w) {
     if (r.half != 0) return;
     float v[32];
     tc_ld_acc16(r, 0, n_pad, v);
@@ -333,8 +353,6 @@ __device__ __forceinline__ void tc_epilogue_semantic32(const TcSmem& s, const Ro
 #pragma unroll
         for (int i = 16; i < 32; ++i) v[i] = 0.0f;
     }
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] += (bias_off >= 0 && i < n_cls) ? s.bias[bias_off + i] : 0.0f;
     if (softmax) {
         float mx = -INFINITY;
 #pragma unroll
@@ -414,9 +432,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem s = carve_tc_smem(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int gi = 0; gi < P.n_gemms; ++gi)
-        if (P.bias_off[gi] >= 0)
-            for (int i = threadIdx.x; i < P.g[gi].n_pad; i += kTcThreads) s.bias[P.bias_off[gi] + i] = P.bias[gi][i];
     if (P.n_rgb > 0) {   // decode table of the rgb MLP input rows
         const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
         const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
@@ -505,12 +520,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 for (int l = 0; l < P.n_sem; ++l, ++gi) {
                     wait_d();
                     if (l + 1 < P.n_sem) {
-                        tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
+                        tc_epilogue_hidden(s, r, P.g[gi].n_pad);
                         publish(gi + 1);
                     } else if (P.n_cls <= 32) {
-                        tc_epilogue_semantic32(s, r, P.n_cls, P.g[gi].n_pad, P.bias_off[gi], P.softmax, p.w);
+                        tc_epilogue_semantic32(s, r, P.n_cls, P.g[gi].n_pad, P.softmax, p.w);
                     } else {
-                        tc_epilogue_final(s, r, P.n_cls, P.g[gi].n_pad, P.bias_off[gi]);
+                        tc_epilogue_final(s, r, P.n_cls, P.g[gi].n_pad);
                     }
                 }
                 if (r.half == 0 && P.n_cls > 32) {   // wide heads: softmax over the thread's own column of the scratch
@@ -539,10 +554,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     for (int l = 0; l < P.n_ins; ++l, ++gi) {
                         wait_d();
                         if (l + 1 < P.n_ins) {
-                            tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
+                            tc_epilogue_hidden(s, r, P.g[gi].n_pad);
                             publish(gi + 1);
                         } else {
-                            tc_epilogue_final(s, r, P.d_ins, P.g[gi].n_pad, P.bias_off[gi]);
+                            tc_epilogue_final(s, r, P.d_ins, P.g[gi].n_pad);
                         }
                     }
                     if (r.half == 0)
@@ -632,10 +647,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 for (int l = 0; l < P.n_rgb; ++l, ++gi) {
                     wait_d();
                     if (l + 1 < P.n_rgb) {
-                        tc_epilogue_hidden(s, r, P.g[gi].n_pad, P.bias_off[gi]);
+                        tc_epilogue_hidden(s, r, P.g[gi].n_pad);
                         publish(gi + 1);
                     } else {
-                        tc_epilogue_final(s, r, 3, P.g[gi].n_pad, P.bias_off[gi]);
+                        tc_epilogue_final(s, r, 3, P.g[gi].n_pad);
                     }
                 }
                 if (r.half == 0)
@@ -654,12 +669,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
 
 // W [out][in] -> per k-step slab, [hi|lo][2 k-chunks][n_pad][4] for n_pad > 128 else [2 k-chunks][hi|lo][n_pad][4]
 // (zero padded; hi/lo tf32-exact)
-__global__ void pack_linear_tc_kernel(const float* __restrict__ w, int n_out, int n_in, float* __restrict__ dst, int n_pad, int slabs) {
+__global__ void pack_linear_tc_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out, int n_in,
+                                      float* __restrict__ dst, int n_pad, int slabs) {
     const int64_t total = (int64_t)slabs * kTcSlabK * n_pad;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int k = (int)(idx / n_pad), n = (int)(idx % n_pad);
-    const float x = (k < n_in && n < n_out) ? w[(size_t)n * n_in + k] : 0.0f;
+    const int k_bias = (n_in + kTcSlabK - 1) / kTcSlabK * kTcSlabK;      // row 0 of the extra slab
+    float x = (k < n_in && n < n_out) ? w[(size_t)n * n_in + k] : 0.0f;
+    if (bias && k == k_bias && n < n_out) x = bias[n];
     float hi, lo;
     tc::split_tf32(x, hi, lo);
     const int slab = k / kTcSlabK, kc = (k % kTcSlabK) / 4, ki = k & 3;   // kc in {0,1}
@@ -688,9 +706,9 @@ static bool tc_add_stack(TcHeadsParams& P, const clift_mlp& m) {
         g.w = m.w_tc[l];
         g.k_steps = (int)ceil_div(m.dims[l], 8);
         g.n_pad = (int)round_up(m.dims[l + 1], 32);
+        g.has_bias = 1;        // clift_pack_linear_tc was given the layer's bias (all MLP layers have one)
         if (m.dims[l] > kTcMaxK || g.n_pad > 256) return false;
-        P.bias[P.n_gemms] = m.bias[l];
-        ++P.n_gemms;   // bias_off is assigned in launch_heads_forward_tc
+        ++P.n_gemms;
     }
     return true;
 }
@@ -754,7 +772,7 @@ int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* fiel
             g.w = field->basis_tc;
             g.k_steps = (int)ceil_div(3 * field->appearance_comps, 8);
             g.n_pad = (int)round_up(field->dim_appearance, 32);
-            P.bias[P.n_gemms] = nullptr;
+            g.has_bias = 0;    // appearance_basis_mat has bias=False (tensoRF.py:65)
             ++P.n_gemms;
         } else {
             ok = false;
@@ -766,15 +784,6 @@ int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* fiel
         return CLIFT_ERR_UNSUPPORTED;
     }
     if (P.n_gemms == 0 || n_rays <= 0) return CLIFT_OK;
-    int bias_floats = 0;
-    for (int gi = 0; gi < P.n_gemms; ++gi) {
-        P.bias_off[gi] = P.bias[gi] ? bias_floats : -1;
-        if (P.bias[gi]) bias_floats += P.g[gi].n_pad;
-    }
-    if (bias_floats > kTcBiasFloats) {
-        set_error("launch_heads_forward_tc: bias table of %d floats exceeds the shared-memory budget", bias_floats);
-        return CLIFT_ERR_UNSUPPORTED;
-    }
     const int grid = sm_count();
 #define CLIFT_TC_CASE(NV)                                                                                              \
     case NV: {                                                                                                         \
@@ -806,29 +815,31 @@ extern "C" int32_t clift_debug_tc_trace(long long* device_buf) {
     return CLIFT_OK;
 }
 
-extern "C" int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in) {
+extern "C" int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in, int32_t has_bias) {
     if (n_out <= 0 || n_in <= 0 || n_out > 256 || n_in > kTcMaxK) return CLIFT_ERR_UNSUPPORTED;
-    const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kTcSlabK);
+    const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kTcSlabK) + (has_bias ? 1 : 0);
     return (int64_t)slabs * 2 * kTcSlabK * n_pad;
 }
 
-extern "C" int32_t clift_pack_linear_tc(const float* w, float* dst, int32_t n_out, int32_t n_in, void* stream) {
+extern "C" int32_t clift_pack_linear_tc(const float* w, const float* bias, float* dst, int32_t n_out, int32_t n_in, void* stream) {
     CLIFT_CHECK_ARG(w && dst, "null pointer");
     CLIFT_CHECK_SUPPORTED(n_out > 0 && n_in > 0 && n_out <= 256 && n_in <= kTcMaxK, "layer wider than 256");
-    const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kTcSlabK);
+    const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kTcSlabK) + (bias ? 1 : 0);
     const int64_t total = (int64_t)slabs * kTcSlabK * n_pad;
-    pack_linear_tc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, n_out, n_in, dst, n_pad, slabs);
+    pack_linear_tc_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, bias, n_out, n_in, dst, n_pad, slabs);
     CLIFT_AFTER_LAUNCH("pack_linear_tc_kernel");
     return CLIFT_OK;
 }
 
-extern "C" int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, void* stream) {
+extern "C" int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, int32_t has_bias,
+                                       void* stream) {
     CLIFT_CHECK_ARG(a && w_tc && out, "null pointer");
     CLIFT_CHECK_SUPPORTED(n_out > 0 && k > 0 && n_out <= 256 && k <= kTcMaxK, "layer wider than 256");
     TcGemm g;
     g.w = w_tc;
     g.k_steps = (int)ceil_div(k, 8);
     g.n_pad = (int)round_up(n_out, 32);
+    g.has_bias = has_bias ? 1 : 0;
     CLIFT_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes));
     tc_gemm_test_kernel<<<1, kTcThreads, kTcSmemBytes, (cudaStream_t)stream>>>(a, k, g, out);
     CLIFT_AFTER_LAUNCH("tc_gemm_test_kernel");

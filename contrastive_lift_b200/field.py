@@ -110,11 +110,12 @@ class _PackedMlp:
         for i, l in enumerate(self.linears):
             L.check(lib.clift_pack_linear(L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None,
                                           L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
-            nf = lib.clift_tc_weight_floats(l.out_features, l.in_features)
+            nf = lib.clift_tc_weight_floats(l.out_features, l.in_features, 1 if l.bias is not None else 0)
             if nf > 0:      # inside the tensor-core envelope: keep the tf32 hi/lo operand current as well
                 if self.w_tc[i] is None:
                     self.w_tc[i] = torch.zeros((nf,), device=self.wt[i].device)
-                L.check(lib.clift_pack_linear_tc(L.ptr(l.weight.data), L.ptr(self.w_tc[i]), l.out_features, l.in_features, stream))
+                L.check(lib.clift_pack_linear_tc(L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None,
+                                                 L.ptr(self.w_tc[i]), l.out_features, l.in_features, stream))
             if training:
                 if self.w_dgrad[i] is None:
                     self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR = 0, 1, 2
@@ -79,9 +79,9 @@ SIGNATURES = {
     "clift_pack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_unpack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_pack_linear_dgrad": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
-    "clift_tc_weight_floats": (C.c_int64, [C.c_int32, C.c_int32]),
-    "clift_pack_linear_tc": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
-    "clift_debug_tc_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_tc_weight_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "clift_pack_linear_tc": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_debug_tc_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_debug_tc_trace": (C.c_int32, [_vp]),
     "clift_gen_rays": (C.c_int32, [_fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "clift_sample_points": (C.c_int32, [C.POINTER(RenderCfg), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 3
+#define CLIFT_ABI_VERSION 4
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -164,14 +164,16 @@ int32_t clift_unpack_linear(const float* wt, const float* bias_pad, float* w, fl
 /* nn.Linear weight [out][in] -> zero padded copy [round_up(out,16)][dgrad_pad(in)] (data-gradient operand). */
 int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32_t n_out, int32_t n_in, void* stream);
 
-/* Tensor-core operand of one nn.Linear for the tcgen05 head kernels: W [out][in] -> tf32-exact (hi, lo) pairs in
- * 8-row K slabs (one tcgen05.mma k-step), each slab [hi|lo][2 k-chunks][n_pad=round_up(out,32)][4];
- * clift_tc_weight_floats() sizes it. */
-int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in);
-int32_t clift_pack_linear_tc(const float* w, float* dst, int32_t n_out, int32_t n_in, void* stream);
-/* Bring-up / parity entry for the tensor-core GEMM core: out[128][round_up(n_out,32)] = a[128][k] * W^T with the
- * 3xTF32 split (one CTA).  Used by tests only. */
-int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, void* stream);
+/* Tensor-core operand of one nn.Linear for the tcgen05 head kernels: W [out][in] (+ bias[out] or null) -> tf32-exact
+ * (hi, lo) pairs in 8-row K slabs (one tcgen05.mma k-step each), n_pad = round_up(out, 32); with a bias one more slab
+ * follows whose first K row is the bias (the kernels multiply it with a constant-one operand column).
+ * clift_tc_weight_floats() sizes the buffer. */
+int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in, int32_t has_bias);
+int32_t clift_pack_linear_tc(const float* w, const float* bias, float* dst, int32_t n_out, int32_t n_in, void* stream);
+/* Bring-up / parity entry for the tensor-core GEMM core: out[128][round_up(n_out,32)] = a[128][k] * W^T (+ bias) with
+ * the 3xTF32 split (one CTA).  Used by tests only. */
+int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, int32_t has_bias,
+                            void* stream);
 
 /* Debug: device buffer of 4*24*6 int64 that CTA 0 of the tensor-core head kernel fills with clock64() stamps per
  * (tile, GEMM): 0 accumulator seen, 1 next operand written, 2 operand published, 3 MMA thread saw operand,
