@@ -49,6 +49,20 @@ def peaks():
     return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sust=1400.0, src="fallback")
 
 
+def ncu_traffic(name: str, frame: int, samples: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` summary
+    (profiles/<name>.json, written by scripts/ncu_summary.py for the default 800x800 x 512 workload), else None."""
+    p = os.path.join(ROOT, "profiles", name + ".json")
+    if frame != 800 or samples != 512 or not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        return sum(d[k] * scale[d[k + "__unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except KeyError:
+        return None
+
+
 def head_flops_per_sample(params) -> float:
     """2*MACs of every Linear the heads evaluate per active sample (~1.016 MFLOP at C=21, d=3)."""
     macs = 0
@@ -131,7 +145,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    per_step = max(256, min(2048, 4096 // max(1, steps)))
+    per_step = 2048          # one reference chunk (config.chunk, render_panopli.py:114) per step: ~0.5 s of host work
     vals = []
     for i in range(warm + steps):
         v, n, dt = cpu_reference_rate(args.frame, args.samples, 60.0, per_step)
@@ -294,17 +308,20 @@ def run_ours(args):
         "stage_ms": {"march": stage[0], "compact": stage[1], "heads": stage[2], "epilogue": stage[3]},
         "roofline": {"kernel": "heads_tc_forward_kernel (tcgen05 3xTF32)" if tensor_heads else "heads_forward_kernel (FP32 FMA)",
                      "bound": "tensor", "achieved": heads_tflops, "peak": pk["bf16_sust"],
-                     "unit": "TFLOP/s", "frac": heads_tflops / pk["bf16_sust"], "traffic": None,
+                     "unit": "TFLOP/s", "frac": heads_tflops / pk["bf16_sust"],
+                     "traffic": ncu_traffic("r01_ncu_heads_tc" if tensor_heads else "r01_ncu_heads_fma", args.frame, args.samples),
+                     "algorithmic_flops_per_launch": flops,
                      "note": f"algorithmic 2*MAC FLOPs of the head Linears x active samples; peak = {pk['src']} sustained bf16 "
                              "(fp32-faithful heads issue 3 tf32 MMAs per product = 6x the bf16 cost, so the reachable "
                              "fraction of this peak is 1/6 by construction)"},
         "roofline_march": {"kernel": "march_kernel", "bound": "hbm", "achieved": march_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                           "frac": march_gbs / pk["hbm"], "traffic": None,
+                           "frac": march_gbs / pk["hbm"], "traffic": ncu_traffic("r01_ncu_march", args.frame, args.samples),
+                           "algorithmic_bytes_per_launch": march_bytes,
                            "note": "algorithmic gather bytes (1152 B per in-box sample) + ray/weight streams; factors are "
                                    "L2-resident so DRAM traffic is far below this by design"},
     }
     if world == 1 and not args.no_cpu:
-        v, n, dt = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 8192)
+        v, n, dt = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 131072)
         line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"{n} rays strided from the same {H}x{W} frame, S={args.samples}, chunk=2048, all heads, {dt:.1f} s"}
     print(json.dumps(line), flush=True)

@@ -1,13 +1,29 @@
-// Tensor-core (tcgen05 / TMEM) implementation of the MLP-head GEMMs (tensoRF.py:383-418, 462-511, 565-594).
+// Tensor-core (tcgen05 / TMEM) implementation of the MLP heads on the compacted active samples
+// (tensoRF.py:127-137, 383-418, 462-511, 565-594; renderer:103-131, 137-156) - the inference path.
 //
-// fp32-faithful arithmetic on the tf32 tensor pipe: every operand x is split into tf32-exact hi + lo and
-//     A*W ~= A_hi*W_hi + A_hi*W_lo + A_lo*W_hi        (error ~2^-21 per product, fp32 accumulation in TMEM)
-// A_hi lives in shared memory ([K/4][128][4] floats, canonical K-major/no-swizzle UMMA layout), A_lo in tensor memory
-// (128 lanes x K columns, read by the .ts form of tcgen05.mma), the accumulator D in tensor memory (128 lanes x N
-// columns), and the pre-split weights stream through a bulk-TMA + mbarrier ring in 16-row K slabs.
+// fp32-faithful arithmetic on the tf32 tensor pipe: every operand x is split into a tf32-exact hi part and the
+// remainder lo = x - hi, and
+//     A*W ~= A_hi*W_hi + A_hi*W_lo + A_lo*W_hi        (error ~2^-21 per product, fp32 accumulation in tensor memory)
+// measured 1e-6..3e-6 relative against fp64 (tests/test_gpu_tc.py), i.e. inside the 1e-4 budget with two orders to spare.
 //
-// Roles (192 threads): warp 0 weight producer, warp 1 MMA issuer (one elected lane), warps 2-5 = 128 "row" threads
-// (thread <-> record <-> TMEM lane) that build layer inputs, run epilogues (bias, ReLU, split, write next A) and reduce.
+// Per CTA (one per SM, persistent over 128-record tiles):
+//   shared memory : A_hi [K/4][128][4] fp32 (128 KB, canonical K-major / no-swizzle UMMA layout: 8-row x 16-byte core
+//                   matrices, SBO 128 B, LBO 2 KB), a 5-stage x 16 KB weight ring fed by 1-D bulk TMA + mbarriers, a
+//                   constant "ones" operand chunk, record positions / ray ids / run table
+//   tensor memory : D = 128 lanes x 256 columns (accumulator), A_lo = 128 lanes x 256 columns (read by the .ts MMA form)
+//   warp 0        : weight producer (one lane)       warp 1 : MMA issuer (one lane, running descriptors)
+//   warps 2..13   : 384 "row" threads, three per record (thread <-> TMEM lane quarter of its warp): build layer inputs,
+//                   run epilogues (TMEM -> ReLU -> hi to smem / lo to TMEM), softmax / sigmoid, per-ray run sums
+// One tile runs 17 dependent GEMMs (semantic 5, instance fast 4 + slow 4, basis 1, rgb 3).  Choices that the
+// clock64 traces under profiles/ drove:
+//   * the bias is one more MMA k-step against the ones chunk instead of an add per accumulator element;
+//   * for N <= 128 the hi and lo weight blocks are one stacked B operand (one MMA, epilogue adds the two column blocks):
+//     small-N MMAs are latency-bound (~76 cycles each), not N-bound;
+//   * ring stages carry several k-steps for small N, so short GEMMs are not bulk-copy round-trip bound;
+//   * the appearance gather runs in quad layout (64-byte coalesced texel segments), writes raw products into the A rows,
+//     and the row threads split them in place; the rgb MLP input is built the same way from one SFU sincos per base value.
+// MMA and epilogue of a tile are serial by data dependence (one A buffer fills the SM), so the tensor pipe is busy
+// ~55-60 % of the kernel; DESIGN.md has the cycle budget.
 #include "launchers.h"
 #include "tcgen05.cuh"
 
@@ -31,10 +47,10 @@ struct TcSmem {
     float* a_hi;        // [kTcMaxK/4][128][4]   (also the [c][128] scratch of the final epilogues)
     float* w;           // [kTcStages][kTcStageFloats]
     float* ones;        // [kTcOnesFloats] constant A operand of the bias k-step: A[m][0] = 1, A[m][1..7] = 0
+    float4* pos;        // [128] record positions (x, y, z normalised, w) of the tile
     int* ray;           // [128]
     int* runs;          // [129]
     int* n_runs;        // [1]
-    int* code;          // [kTcMaxK] decode table of the rgb MLP input rows (kind | base << 2 | doublings << 10)
     uint64_t* full;     // [kTcStages]
     uint64_t* empty;    // [kTcStages]
     uint64_t* bar_a;    // A operand ready (row threads -> MMA)
@@ -43,7 +59,7 @@ struct TcSmem {
 };
 
 constexpr size_t kTcSmemBytes = (size_t)kTcMaxK * kTcRows * 4 + (size_t)kTcStages * kTcStageFloats * 4 +
-                                (size_t)kTcOnesFloats * 4 + (2 * kTcRows + 8) * 4 + (size_t)kTcMaxK * 4 + 256;
+                                (size_t)kTcOnesFloats * 4 + (size_t)kTcRows * 16 + (2 * kTcRows + 8) * 4 + 256;
 static_assert(kTcSmemBytes <= 232448, "shared memory budget of one sm_100a CTA");
 
 __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
@@ -51,11 +67,11 @@ __device__ __forceinline__ TcSmem carve_tc_smem(unsigned char* raw) {
     s.a_hi = reinterpret_cast<float*>(raw);
     s.w = s.a_hi + kTcMaxK * kTcRows;
     s.ones = s.w + kTcStages * kTcStageFloats;
-    s.ray = reinterpret_cast<int*>(s.ones + kTcOnesFloats);
+    s.pos = reinterpret_cast<float4*>(s.ones + kTcOnesFloats);
+    s.ray = reinterpret_cast<int*>(s.pos + kTcRows);
     s.runs = s.ray + kTcRows;
     s.n_runs = s.runs + kTcRows + 1;
-    s.code = s.n_runs + 7;
-    s.full = reinterpret_cast<uint64_t*>(s.code + kTcMaxK);
+    s.full = reinterpret_cast<uint64_t*>(s.n_runs + 7);
     s.empty = s.full + kTcStages;
     s.bar_a = s.empty + kTcStages;
     s.bar_d = s.bar_a + 1;
@@ -168,6 +184,17 @@ __device__ __forceinline__ void tc_put8(const TcSmem& s, uint32_t lane_base, int
     dst[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
     dst[kTcRows] = make_float4(hi[4], hi[5], hi[6], hi[7]);
     tc::tmem_st8(lane_base + kTmemALo + (uint32_t)k0, lo);
+}
+
+// row threads: the A operand region holds RAW fp32 values for K rows [0, k_rows) (written by any thread); convert them in
+// place to the tf32-exact hi part and move the lo part to tensor memory.  A record's threads alternate over 8-row chunks.
+__device__ __forceinline__ void tc_split_rows(const TcSmem& s, uint32_t lane_base, int row, int part, int k_rows) {
+    for (int k0 = part * 8; k0 < k_rows; k0 += 8 * kTcParts) {
+        const float4* src = reinterpret_cast<const float4*>(s.a_hi + ((size_t)(k0 >> 2) * kTcRows + row) * 4);
+        const float4 a = src[0], b = src[kTcRows];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        tc_put8(s, lane_base, row, k0, v);
+    }
 }
 
 // row threads: publish the A operand they just wrote
@@ -288,11 +315,11 @@ struct TcHeadsParams {
     float* rgb_raw;
     float* sem_raw;
     float* ins;
-    long long* trace;                 // debug: [4 tiles][kTcMaxGemms][6] clock64 stamps of CTA 0, or null
+    long long* trace;                 // debug: [4 tiles][kTcMaxGemms][10] clock64 stamps of CTA 0, or null
 };
 
 __device__ __forceinline__ void tc_stamp(const TcHeadsParams& P, long long tile_local, int gi, int slot) {
-    if (P.trace && blockIdx.x == 0 && tile_local < 4) P.trace[(tile_local * kTcMaxGemms + gi) * 6 + slot] = clock64();
+    if (P.trace && blockIdx.x == 0 && tile_local < 4) P.trace[(tile_local * kTcMaxGemms + gi) * 10 + slot] = clock64();
 }
 
 // hidden-layer epilogue: D (bias already accumulated by the bias k-step) -> ReLU -> next layer's A operand.  A record's
@@ -378,6 +405,13 @@ __device__ __forceinline__ void tc_epilogue_semantic32(const TcSmem& s, const Ro
 
 // xyz (+ sin/cos PE, dimension-major frequency-minor) -> A operand, zero padded to a multiple of 8
 __device__ __forceinline__ void tc_build_xyz(const TcSmem& s, const RowId& r, const float4& p, int pe) {
+    if (pe == 0) {   // the shipped configuration (pe_sem = pe_ins = 0): one chunk, no decode
+        if (r.half == 0) {
+            const float v[8] = {p.x, p.y, p.z, 0.f, 0.f, 0.f, 0.f, 0.f};
+            tc_put8(s, r.lane_base, r.row, 0, v);
+        }
+        return;
+    }
     const int n_in = 3 + 6 * pe;
     const float xyz[3] = {p.x, p.y, p.z};
     for (int k0 = r.half * 8; k0 < n_in; k0 += 8 * kTcParts) {
@@ -432,27 +466,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem s = carve_tc_smem(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (P.n_rgb > 0) {   // decode table of the rgb MLP input rows
-        const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
-        const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
-        for (int q = threadIdx.x; q < kTcMaxK; q += kTcThreads) {
-            int kind = 3, b = 0, f = 0;
-            if (q < o_sf) {
-                kind = 0, b = q;
-            } else if (q < o_sd) {
-                const int j = (q < o_cf) ? q - o_sf : q - o_cf;
-                kind = q < o_cf ? 1 : 2, b = j / pf, f = j % pf;
-            } else if (q < n_in) {
-                const int j = (q < o_cd) ? q - o_sd : q - o_cd;
-                kind = q < o_cd ? 1 : 2, b = A + j / pv, f = j % pv;
-            }
-            s.code[q] = kind | (b << 2) | (f << 10);
-        }
-    }
     tc_init(s);
     const uint32_t tmem = *s.tmem_base;
     const long long n_act = min((long long)P.stats[0], P.cap);
     const long long n_tiles = (n_act + kTcRows - 1) / kTcRows;
+    // (Measured: offsetting CTAs in time so their appearance gathers do not coincide is SLOWER - a gather then competes
+    // with the other CTAs' weight streams for L2; in lockstep nobody streams weights while everybody gathers.)
 
     if (warp == 0) {
         if (tc::elect_one()) {
@@ -467,7 +486,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
             long long tl = 0;
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl)
                 for (int gi = 0; gi < P.n_gemms; ++gi, ++count) {
-                    tc_issue(s, P.g[gi], ps, tmem, count & 1, P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kTcMaxGemms + gi) * 6 : nullptr);
+                    tc_issue(s, P.g[gi], ps, tmem, count & 1, P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kTcMaxGemms + gi) * 10 : nullptr);
                 }
         }
     } else {
@@ -487,17 +506,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
             tc_publish_a(s);
             if (threadIdx.x == 64) tc_stamp(P, tl, g_next, 2);
         };
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ray_next = -1;
+        auto fetch = [&](long long tile) {   // record of this thread's row in `tile` (issued early: ~1 us of latency)
+            p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            ray_next = -1;
+            if (tile < n_tiles && tile * kTcRows + row < n_act) {
+                p_next = P.rec_pos[tile * kTcRows + row];
+                ray_next = P.rec_ray[tile * kTcRows + row];
+            }
+        };
+        fetch(blockIdx.x);
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             ++tl;
             const long long base = tile * kTcRows;
             const int nv = (int)min((long long)kTcRows, n_act - base);
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            int ray = -1;
-            if (row < nv) {
-                p = P.rec_pos[base + row];
-                ray = P.rec_ray[base + row];
+            const float4 p = p_next;
+            const int ray = ray_next;
+            fetch(tile + gridDim.x);
+            if (r.half == 0) {
+                s.ray[row] = ray;
+                s.pos[row] = p;
             }
-            if (r.half == 0) s.ray[row] = ray;
             tc::named_bar_sync(1, kTcRowThreads);
             if (warp == 2) {   // run starts, in record order
                 int n = 0;
@@ -562,40 +592,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                     }
                     if (r.half == 0)
                         for (int c = 0; c < P.d_ins; ++c) s.a_hi[(size_t)c * kTcRows + row] *= p.w;
+                    if (threadIdx.x == 64) tc_stamp(P, tl, gi, 6);
                     tc_reduce_runs(s, r.rt, P.d_ins, P.ins, width, net * P.d_ins);
+                    if (threadIdx.x == 64) tc_stamp(P, tl, gi, 7);
                 }
             }
             if (P.n_rgb > 0) {
                 const FactorParams& f = P.app;
-                // appearance gather: 18 taps x comps channels -> plane*line products; the record's two threads
-                // alternate over the 8-channel groups
-                const float xs[3] = {p.x, p.y, p.z};
-#pragma unroll 1
-                for (int mode = 0; mode < 3; ++mode) {
-                    const Tap2 t2 = make_tap2(xs[mode_a(mode)], xs[mode_b(mode)], f.pw[mode], f.ph[mode]);
-                    const Tap1 t1 = make_tap1(xs[mode_v(mode)], f.ll[mode]);
+                // appearance gather in quad layout (4 lanes x float4 = one 64-byte texel segment per tap, fully
+                // coalesced): plane*line products go RAW into the A operand rows, then the row-mapped threads split them
+                {
+                    const int q = r.rt & 3;
+                    // one (record, mode) item per quad and step: 128 x 3 items over 96 quads, perfectly balanced
+                    for (int item = r.rt >> 2; item < 3 * kTcRows; item += kTcRowThreads / 4) {
+                        const int m = item / 3, mode = item - m * 3;
+                        const float4 pm = s.pos[m];
+                        const float ca = mode == 2 ? pm.y : pm.x, cb = mode == 0 ? pm.y : pm.z;
+                        const float cv = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
+                        const int W = f.pw[mode];
+                        const Tap2 t2 = make_tap2(ca, cb, W, f.ph[mode]);
+                        const Tap1 t1 = make_tap1(cv, f.ll[mode]);
+                        const float* plane = f.plane[mode];
+                        const float* line = f.line[mode];
 #pragma unroll
-                    for (int v8 = 0; v8 < NV * 2; ++v8) {
-                        if (((mode * NV * 2 + v8) % kTcParts) != r.half) continue;   // warp-uniform
-                        const int ch = v8 * 8;
-                        const float4 pa = plane_tap(f.plane[mode], t2, f.pw[mode], f.comps, ch);
-                        const float4 la = line_tap(f.line[mode], t1, f.comps, ch);
-                        const float4 pb = plane_tap(f.plane[mode], t2, f.pw[mode], f.comps, ch + 4);
-                        const float4 lb = line_tap(f.line[mode], t1, f.comps, ch + 4);
-                        const float v[8] = {pa.x * la.x, pa.y * la.y, pa.z * la.z, pa.w * la.w,
-                                            pb.x * lb.x, pb.y * lb.y, pb.z * lb.z, pb.w * lb.w};
-                        tc_put8(s, r.lane_base, row, mode * f.comps + ch, v);
+                        for (int v = 0; v < NV; ++v) {
+                            const int ch = v * 16 + q * 4;
+                            const float4 pv4 = plane_tap(plane, t2, W, f.comps, ch);
+                            const float4 lv4 = line_tap(line, t1, f.comps, ch);
+                            const int k = mode * f.comps + ch;
+                            *reinterpret_cast<float4*>(s.a_hi + ((size_t)(k >> 2) * kTcRows + m) * 4) =
+                                make_float4(pv4.x * lv4.x, pv4.y * lv4.y, pv4.z * lv4.z, pv4.w * lv4.w);
+                        }
                     }
                 }
+                tc::named_bar_sync(1, kTcRowThreads);
+                tc_split_rows(s, r.lane_base, row, r.half, 3 * f.comps);
                 publish(gi);
                 wait_d();   // basis GEMM: features in D columns [0, dim_app)
                 const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
                 const int n_base = A + 3;
-                // staging behind the K rows of the first rgb GEMM: base values x_b (A features + 3 direction
-                // components), then sin x_b, then cos x_b, each [n_base][128]
-                float* xb = s.a_hi + (size_t)P.g[gi + 1].k_steps * 8 * kTcRows;
-                float* sb = xb + (size_t)n_base * kTcRows;
-                float* cb = sb + (size_t)n_base * kTcRows;
+                // staging behind the K rows of the first rgb GEMM: base values x_b (A features, 3 direction components)
+                const int k_rows = P.g[gi + 1].k_steps * 8;
+                float* xb = s.a_hi + (size_t)k_rows * kTcRows;
                 if (r.half == 0) {
                     for (int c0 = 0; c0 < A; c0 += 16) {
                         float v[16];
@@ -611,38 +649,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) heads_tc_forward_kernel(const _
                 }
                 ++gi;
                 tc::named_bar_sync(1, kTcRowThreads);
+                if (threadIdx.x == 64) tc_stamp(P, tl, gi, 6);
                 // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418):
-                // one sincosf per base value, higher frequencies by angle doubling
-                for (int b = r.half; b < n_base; b += kTcParts) {
-                    float sv, cv;
-                    sincosf(xb[(size_t)b * kTcRows + row], &sv, &cv);
-                    sb[(size_t)b * kTcRows + row] = sv;
-                    cb[(size_t)b * kTcRows + row] = cv;
+                // one (record, base value) item per thread and step - SFU sincos (|error| < 4e-7 on these O(1) arguments,
+                // far inside the 1e-4 budget; the FP32-FMA kernel keeps libm), higher frequencies by angle doubling -
+                // written RAW to their K rows, then split like the gather.
+                {
+                    const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
+                    auto put = [&](int k, int m, float x) { s.a_hi[((size_t)(k >> 2) * kTcRows + m) * 4 + (k & 3)] = x; };
+                    for (int item = r.rt; item < n_base * kTcRows; item += kTcRowThreads) {
+                        const int b = item / kTcRows, m = item - b * kTcRows;     // b is warp-uniform
+                        const float x = xb[(size_t)b * kTcRows + m];
+                        const bool is_feat = b < A;
+                        const int nf = is_feat ? pf : pv;
+                        const int ks = is_feat ? o_sf + b * pf : o_sd + (b - A) * pv;
+                        const int kc = is_feat ? o_cf + b * pf : o_cd + (b - A) * pv;
+                        put(b, m, x);                                               // feat rows [0,A), dir rows [A,A+3)
+                        float sv, cv;
+                        __sincosf(x, &sv, &cv);
+                        for (int j = 0; j < nf; ++j) {
+                            put(ks + j, m, sv);
+                            put(kc + j, m, cv);
+                            const float s2 = 2.0f * sv * cv, c2 = 1.0f - 2.0f * sv * sv;   // (sin, cos)(2t)
+                            sv = s2;
+                            cv = c2;
+                        }
+                    }
+                    for (int item = r.rt; item < (k_rows - n_in) * kTcRows; item += kTcRowThreads)
+                        put(n_in + item / kTcRows, item % kTcRows, 0.0f);           // zero pad rows
                 }
                 tc::named_bar_sync(1, kTcRowThreads);
-                const int n_in = A * (1 + 2 * pf) + 3 * (1 + 2 * pv);
-                for (int k0 = r.half * 8; k0 < n_in; k0 += 8 * kTcParts) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int code = s.code[k0 + i];       // kind | base << 2 | doublings << 10 ; kind 3 = zero pad
-                        const int kind = code & 3, b = (code >> 2) & 255, f = code >> 10;
-                        float x = 0.0f;
-                        if (kind == 0) {
-                            x = xb[(size_t)b * kTcRows + row];
-                        } else if (kind != 3) {
-                            float sv = sb[(size_t)b * kTcRows + row], cv = cb[(size_t)b * kTcRows + row];
-                            for (int d = 0; d < f; ++d) {   // (sin, cos)(2t) from (sin, cos)(t)
-                                const float s2 = 2.0f * sv * cv, c2 = 1.0f - 2.0f * sv * sv;
-                                sv = s2;
-                                cv = c2;
-                            }
-                            x = kind == 1 ? sv : cv;
-                        }
-                        v[i] = x;
-                    }
-                    tc_put8(s, r.lane_base, row, k0, v);
-                }
+                if (threadIdx.x == 64) tc_stamp(P, tl, gi, 7);
+                tc_split_rows(s, r.lane_base, row, r.half, k_rows);
                 publish(gi);
                 for (int l = 0; l < P.n_rgb; ++l, ++gi) {
                     wait_d();
@@ -724,7 +762,7 @@ bool heads_tc_available(const clift_field* f, int heads) {
     if (heads & CLIFT_HEAD_RGB) {
         if (!ok(f->rgb) || !f->basis_tc || f->dim_appearance > 64 || f->appearance_comps % 8) return false;
         // the base/sin/cos staging of the rgb input lives behind the K rows of the first rgb GEMM
-        if ((int)round_up(f->rgb.dims[0], 8) + 3 * (f->dim_appearance + 3) > kTcMaxK) return false;
+        if ((int)round_up(f->rgb.dims[0], 8) + (f->dim_appearance + 3) > kTcMaxK) return false;
     }
     return true;
 }

@@ -279,7 +279,21 @@ class TensoRFRenderer(nn.Module):
         rays = rays.detach().contiguous().float()
         params = [p for _, p in tensorf.named_parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        return _Render.apply(self, tensorf, rays, jitter, add_bg, heads, want_points, need_grad, *params)
+        limit = ((1 << 31) - 1) // max(int(self.n_samples), 1)        # one C call handles n_rays*n_samples < 2^31
+        if rays.shape[0] <= limit:
+            return _Render.apply(self, tensorf, rays, jitter, add_bg, heads, want_points, need_grad, *params)
+        # very large frames (e.g. 1600x1600 at 1024 samples/ray): split into ray ranges, concatenate the per-ray maps,
+        # and recombine the per-call distortion means into the mean over all rays
+        outs, sizes = [], []
+        for b in range(0, rays.shape[0], limit):
+            e = min(b + limit, rays.shape[0])
+            outs.append(_Render.apply(self, tensorf, rays[b:e].contiguous(), None if jitter is None else jitter[b:e].contiguous(),
+                                      add_bg, heads, want_points, need_grad, *params))
+            sizes.append(e - b)
+        cat = lambda i: torch.cat([o[i] for o in outs]) if outs[0][i].numel() else outs[0][i]
+        wts = torch.tensor(sizes, device=rays.device, dtype=torch.float32) / float(rays.shape[0])
+        dist = (torch.stack([o[4] for o in outs]) * wts).sum() if outs[0][4].numel() else outs[0][4]
+        return cat(0), cat(1), cat(2), cat(3), dist, cat(5)
 
     # ---- renderer:80-176 --------------------------------------------------------------------------
     def forward(self, tensorf, rays, perturb, white_bg, is_train):

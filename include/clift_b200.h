@@ -175,9 +175,9 @@ int32_t clift_pack_linear_tc(const float* w, const float* bias, float* dst, int3
 int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, int32_t has_bias,
                             void* stream);
 
-/* Debug: device buffer of 4*24*6 int64 that CTA 0 of the tensor-core head kernel fills with clock64() stamps per
+/* Debug: device buffer of 4*24*10 int64 that CTA 0 of the tensor-core head kernel fills with clock64() stamps per
  * (tile, GEMM): 0 accumulator seen, 1 next operand written, 2 operand published, 3 MMA thread saw operand,
- * 4 MMAs issued.  null disables. */
+ * 4 MMAs issued, 5 first weight slab seen, 6-7 phase marks inside the operand build.  null disables. */
 int32_t clift_debug_tc_trace(long long* device_buf);
 
 /* ---- R1-R4: util/ray.py:8-12,25-31,46-54,81-99 + dataset/base.py:211-219 ------------------------

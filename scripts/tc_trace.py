@@ -21,7 +21,7 @@ rays = cl.get_rays_checked(200, 200, k.numpy(), c2w.numpy())
 lib = L.load()
 with torch.no_grad():
     rend(model, rays, 1.0, False, False)
-    buf = torch.zeros((4, 24, 6), dtype=torch.int64, device="cuda")
+    buf = torch.zeros((4, 24, 10), dtype=torch.int64, device="cuda")
     lib.clift_debug_tc_trace(L.ptr(buf))
     rend(model, rays, 1.0, False, False)
     torch.cuda.synchronize()
@@ -39,5 +39,7 @@ for tile in (1, 2):
         w_wait = int(t[tile, g, 5]) - t0 - saw
         print(f"{n:6s} {a_w:10d} {pub:10d} {saw:10d} {iss:10d} {d:10d} | {epi:9d} {pub - a_w:8d} {saw - pub:8d} {iss - saw:7d} {d - iss:9d} {w_wait:7d}")
         prev_d = d
+        if int(t[tile, g, 6]) or int(t[tile, g, 7]):
+            print(f"       marks: {int(t[tile, g, 6]) - t0:10d} {int(t[tile, g, 7]) - t0:10d}")
     nxt = int(t[tile + 1, 0, 1]) - t0
     print(f"next tile's first operand written at {nxt}")
