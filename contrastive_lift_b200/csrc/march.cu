@@ -19,6 +19,7 @@ namespace clift {
 namespace {
 
 constexpr int kWarpsPerCta = 8;
+constexpr int kFullLaneMin = 12;   // in-box samples per 32-sample chunk from which the lane-per-sample lookup wins
 
 template <int NV>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_constant__ MarchParams P) {
@@ -86,19 +87,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
             if (inm != 0u) {
                 n_in += __popc(inm);
                 float feat = 0.0f;
+                if (__popc(inm) >= kFullLaneMin) {
+                    // mostly in-box chunk: every lane evaluates its own sample
+                    if (in) feat = vm_dot_full<NV>(P.f, lines_s, x[0], x[1], x[2]);
+                } else {
+                    // sparse chunk: quads (4 lanes x 4 channels) walk only the 8-sample groups that have work
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (((inm >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
-                    const int src = j * 8 + (lane >> 2);
-                    const float sx = __shfl_sync(0xffffffffu, x[0], src);
-                    const float sy = __shfl_sync(0xffffffffu, x[1], src);
-                    const float sz = __shfl_sync(0xffffffffu, x[2], src);
-                    float acc = 0.0f;
-                    if ((inm >> src) & 1u) acc = vm_dot_partial<NV>(P.f, lines_s, sx, sy, sz, q);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                    const float v = __shfl_sync(0xffffffffu, acc, (lane & 7) * 4);
-                    if ((lane >> 3) == j) feat = v;
+                    for (int j = 0; j < 4; ++j) {
+                        if (((inm >> (8 * j)) & 0xffu) == 0u) continue;   // warp-uniform
+                        const int src = j * 8 + (lane >> 2);
+                        const float sx = __shfl_sync(0xffffffffu, x[0], src);
+                        const float sy = __shfl_sync(0xffffffffu, x[1], src);
+                        const float sz = __shfl_sync(0xffffffffu, x[2], src);
+                        float acc = 0.0f;
+                        if ((inm >> src) & 1u) acc = vm_dot_partial<NV>(P.f, lines_s, sx, sy, sz, q);
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                        const float v = __shfl_sync(0xffffffffu, acc, (lane & 7) * 4);
+                        if ((lane >> 3) == j) feat = v;
+                    }
                 }
                 const float sigma = in ? softplus_f(feat + P.shift) : 0.0f;
                 const float tn = sample_t(g, G.step, i + 1);

@@ -92,6 +92,33 @@ __device__ __forceinline__ float vm_dot_partial(const FactorParams& f, const flo
     return acc;
 }
 
+// One lane's FULL sum_modes sum_c P_c(x_a,x_b) * L_c(x_v): the lane reads each tap's whole texel (comps x 4 B
+// contiguous) as float4 pieces.  Half the instructions of the quad form above (taps are set up once per sample, no
+// shuffles), at the price of idle lanes for out-of-box samples of a partially in-box chunk.
+template <int NV>
+__device__ __forceinline__ float vm_dot_full(const FactorParams& f, const float* lines_s, float x0, float x1, float x2) {
+    const float xs[3] = {x0, x1, x2};
+    float acc = 0.0f;
+    int soff = 0;
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const Tap2 t2 = make_tap2(xs[mode_a(m)], xs[mode_b(m)], f.pw[m], f.ph[m]);
+        const Tap1 t1 = make_tap1(xs[mode_v(m)], f.ll[m]);
+        const float* line = lines_s ? lines_s + soff : f.line[m];
+        soff += f.ll[m] * f.comps;
+#pragma unroll
+        for (int v = 0; v < NV * 4; ++v) {
+            const float4 p = plane_tap(f.plane[m], t2, f.pw[m], f.comps, v * 4);
+            const float4 l = line_tap(line, t1, f.comps, v * 4);
+            acc = fmaf(p.x, l.x, acc);
+            acc = fmaf(p.y, l.y, acc);
+            acc = fmaf(p.z, l.z, acc);
+            acc = fmaf(p.w, l.w, acc);
+        }
+    }
+    return acc;
+}
+
 __device__ __forceinline__ float softplus_f(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
 #endif
 
