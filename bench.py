@@ -207,8 +207,9 @@ def run_ours(args):
     model, rend = model.to(dev), rend.to(dev)
     rend.max_active_per_ray = MAX_ACTIVE_PER_RAY
     rend.check_overflow = False       # checked once after warm-up below; keeps the timed call free of host syncs
-    rend.head_path = {"auto": L.HEADS_AUTO, "fma": L.HEADS_FMA, "tensor": L.HEADS_TENSOR}[args.heads]
+    rend.head_path = {"auto": L.HEADS_AUTO, "fma": L.HEADS_FMA, "tensor": L.HEADS_TENSOR, "tensor16": L.HEADS_TENSOR16}[args.heads]
     tensor_heads = args.heads != "fma"
+    f16_heads = args.heads in ("auto", "tensor16")
     H = W = args.frame
     n_rays = H * W
     k, c2w = syn.camera(H, W, yaw_deg=7.0 * rank)
@@ -306,14 +307,18 @@ def run_ours(args):
         "clocks": clocks,
         "scene": {"n_inbox_per_ray": n_in / n_rays, "n_active_per_ray": n_act / n_rays, "head_tiles": n_tiles},
         "stage_ms": {"march": stage[0], "compact": stage[1], "heads": stage[2], "epilogue": stage[3]},
-        "roofline": {"kernel": "heads_tc_forward_kernel (tcgen05 3xTF32)" if tensor_heads else "heads_forward_kernel (FP32 FMA)",
+        "roofline": {"kernel": ("heads_tc16_forward_kernel (tcgen05 kind::f16, 3-product fp16 split)" if f16_heads else
+                                "heads_tc_forward_kernel (tcgen05 3xTF32)") if tensor_heads else "heads_forward_kernel (FP32 FMA)",
                      "bound": "tensor", "achieved": heads_tflops, "peak": pk["bf16_sust"],
                      "unit": "TFLOP/s", "frac": heads_tflops / pk["bf16_sust"],
-                     "traffic": ncu_traffic("r01_ncu_heads_tc" if tensor_heads else "r01_ncu_heads_fma", args.frame, args.samples),
+                     "traffic": ncu_traffic(("r01_ncu_heads_tc16" if f16_heads else "r01_ncu_heads_tc") if tensor_heads else "r01_ncu_heads_fma",
+                                            args.frame, args.samples),
                      "algorithmic_flops_per_launch": flops,
                      "note": f"algorithmic 2*MAC FLOPs of the head Linears x active samples; peak = {pk['src']} sustained bf16 "
-                             "(fp32-faithful heads issue 3 tf32 MMAs per product = 6x the bf16 cost, so the reachable "
-                             "fraction of this peak is 1/6 by construction)"},
+                             + ("(fp32-faithful heads issue 3 kind::f16 MMAs per product = 3x the bf16 cost, so the reachable "
+                                "fraction of this peak is 1/3 by construction)" if f16_heads else
+                                "(fp32-faithful heads issue 3 tf32 MMAs per product = 6x the bf16 cost, so the reachable "
+                                "fraction of this peak is 1/6 by construction)")},
         "roofline_march": {"kernel": "march_kernel", "bound": "hbm", "achieved": march_gbs, "peak": pk["hbm"], "unit": "GB/s",
                            "frac": march_gbs / pk["hbm"], "traffic": ncu_traffic("r01_ncu_march", args.frame, args.samples),
                            "algorithmic_bytes_per_launch": march_bytes,
@@ -339,7 +344,7 @@ def main():
     ap.add_argument("--samples", type=int, default=512)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--heads", default="auto", choices=["auto", "fma", "tensor"], help="MLP-head kernel family")
+    ap.add_argument("--heads", default="auto", choices=["auto", "fma", "tensor", "tensor16"], help="MLP-head kernel family")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

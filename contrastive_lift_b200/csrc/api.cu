@@ -207,14 +207,19 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         float* o_rgb = (heads & CLIFT_HEAD_RGB) ? out->rgb_raw : nullptr;
         float* o_sem = (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr;
         float* o_ins = (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr;
-        bool use_tc = false;
-        if (cfg->head_path == CLIFT_HEADS_TENSOR) {
-            CLIFT_CHECK_SUPPORTED(!save, "the tensor-core head path does not record the training stash (use CLIFT_HEADS_AUTO/FMA)");
-            use_tc = true;
-        } else if (cfg->head_path == CLIFT_HEADS_AUTO) {
-            use_tc = !save && heads_tc_available(field, heads);
+        int path = CLIFT_HEADS_FMA;
+        if (cfg->head_path == CLIFT_HEADS_TENSOR || cfg->head_path == CLIFT_HEADS_TENSOR16) {
+            CLIFT_CHECK_SUPPORTED(!save, "the tensor-core head paths do not record the training stash (use CLIFT_HEADS_AUTO/FMA)");
+            path = cfg->head_path;
+        } else if (cfg->head_path == CLIFT_HEADS_AUTO && !save) {
+            if (heads_tc16_available(field, heads))
+                path = CLIFT_HEADS_TENSOR16;
+            else if (heads_tc_available(field, heads))
+                path = CLIFT_HEADS_TENSOR;
         }
-        if (use_tc)
+        if (path == CLIFT_HEADS_TENSOR16)
+            rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream);
+        else if (path == CLIFT_HEADS_TENSOR)
             rc = launch_heads_forward_tc(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream);
         else
             rc = launch_heads_forward(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, save ? &lay : nullptr, stream);

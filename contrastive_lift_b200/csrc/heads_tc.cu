@@ -769,6 +769,7 @@ bool heads_tc_available(const clift_field* f, int heads) {
 
 static long long* g_tc_trace = nullptr;
 void set_tc_trace(long long* p) { g_tc_trace = p; }
+long long* get_tc_trace() { return g_tc_trace; }
 
 int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
                             int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream) {

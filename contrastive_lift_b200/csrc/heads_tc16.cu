@@ -1,0 +1,992 @@
+// Tensor-core (tcgen05 / TMEM) MLP heads on the compacted active samples, fp16-split variant - the default inference path
+// (tensoRF.py:127-137, 383-418, 462-511, 565-594; renderer:103-131, 137-156).
+//
+// fp32-faithful arithmetic at the kind::f16 rate (K = 16 per MMA, twice the tf32 rate): every operand x is scaled by a
+// power of two s (exact) and split into two fp16 numbers, hi = fp16(s x), lo = fp16(s x - hi), and
+//     (s_a A)(s_w W) ~= A_hi*W_hi + A_hi*W_lo + A_lo*W_hi        (22 significant bits per operand, fp32 accumulation in TMEM)
+// The scales come from a pack-time bound chain (clift_pack_linear_tc16): with |input| <= B_in, every activation of a layer is
+// bounded by B_out = B_in * max_n sum_k |W_nk| + max|b|; s_a = 2^floor(log2(2^14 / B_in)) keeps every scaled activation below
+// 2^14 (fp16 overflows at 65504), s_w does the same for the weights and the bias row.  The bound is loose (it ignores
+// cancellation) but fp16 keeps 22 bits for any value above 2^-3 of... the scaled range [2^-3, 2^14], i.e. the bound may be
+// 2^17 times the actual activation before precision starts to degrade (gracefully: absolute error 2^-25 scaled).  The
+// un-scaling (one FMUL per accumulator element) rides in the epilogues.  Measured against fp64: same 1e-6 class as 3xTF32
+// (tests/test_gpu_tc.py).
+//
+// Per CTA (one per SM, persistent over 128-record tiles):
+//   shared memory : A_hi, A_lo  [K/8][128][8] fp16 each (64 KB + 64 KB, canonical K-major / no-swizzle UMMA layout: 8-row x
+//                   16-byte core matrices, SBO 128 B, LBO 2 KB), a 5-stage x 16 KB weight ring fed by 1-D bulk TMA + mbarriers,
+//                   a constant "ones" operand chunk (bias k-step), record positions / ray ids / run table / scale table
+//   tensor memory : D = 128 lanes x 256 columns (fp32 accumulator)
+//   warp 0        : weight producer (one lane)       warp 1 : MMA issuer (one lane, running descriptors)
+//   warps 2..13   : 384 "row" threads, three per record (thread <-> TMEM lane quarter of its warp): build layer inputs,
+//                   run epilogues (TMEM -> ReLU -> rescale -> fp16 split -> smem), softmax / sigmoid, per-ray run sums
+// Both operand halves live in shared memory, so any thread may write any record's operand row: the appearance gather
+// (quad layout) and the rgb-input builder write the final fp16 pairs directly - no staging pass.
+#include <cuda_fp16.h>
+
+#include "launchers.h"
+#include "tcgen05.cuh"
+
+namespace clift {
+
+long long* get_tc_trace();   // heads_tc.cu (clift_debug_tc_trace)
+
+namespace {
+
+constexpr int kRows = 128;              // records per tile = UMMA M
+constexpr int kParts = 3;               // threads per record
+constexpr int kRowThreads = kRows * kParts;
+constexpr int kThreads = 64 + kRowThreads;
+constexpr int kMaxK = 256;
+constexpr int kStages = 5;
+constexpr int kStepK = 16;              // K per tcgen05.mma kind::f16
+constexpr int kStageBytes = 2 * kStepK * 256 * 2;    // hi + lo, N up to 256
+constexpr int kABytes = kMaxK * kRows * 2;           // one operand half
+constexpr int kOnesBytes = 2 * kRows * 16;
+constexpr int kMaxGemms = 24;
+constexpr int kHeaderFloats = 16;       // per packed layer: ca, cw, 1/(ca cw), out bound, in bound, L, max|W|, max|b|
+constexpr uint32_t kTmemCols = 256;
+
+struct Smem {
+    unsigned char* a_hi;   // [kMaxK/8][128][8] fp16  (also the [c][128] float scratch of the final epilogues)
+    unsigned char* a_lo;
+    unsigned char* w;      // [kStages][kStageBytes]
+    unsigned char* ones;   // A chunk pair [2][128][8] fp16 with element 0 of chunk 0 = 1
+    float4* pos;           // [128]
+    int* ray;              // [128]
+    int* runs;             // [129]
+    int* n_runs;
+    float2* sc;            // [kMaxGemms] (ca, 1/(ca cw)) per GEMM
+    uint64_t* full;
+    uint64_t* empty;
+    uint64_t* bar_a;
+    uint64_t* bar_d;
+    uint32_t* tmem_base;
+};
+
+constexpr size_t kSmemBytes = 2 * (size_t)kABytes + (size_t)kStages * kStageBytes + kOnesBytes + (size_t)kRows * 16 +
+                              (2 * kRows + 8) * 4 + kMaxGemms * 8 + 256;
+static_assert(kSmemBytes <= 232448, "shared memory budget of one sm_100a CTA");
+
+__device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
+    Smem s;
+    s.a_hi = raw;
+    s.a_lo = s.a_hi + kABytes;
+    s.w = s.a_lo + kABytes;
+    s.ones = s.w + (size_t)kStages * kStageBytes;
+    s.pos = reinterpret_cast<float4*>(s.ones + kOnesBytes);
+    s.ray = reinterpret_cast<int*>(s.pos + kRows);
+    s.runs = s.ray + kRows;
+    s.n_runs = s.runs + kRows + 1;
+    s.sc = reinterpret_cast<float2*>(s.n_runs + 7);
+    s.full = reinterpret_cast<uint64_t*>(s.sc + kMaxGemms);
+    s.empty = s.full + kStages;
+    s.bar_a = s.empty + kStages;
+    s.bar_d = s.bar_a + 1;
+    s.tmem_base = reinterpret_cast<uint32_t*>(s.bar_d + 1);
+    return s;
+}
+
+// One GEMM of the schedule: D[128 x n_pad] = A[128 x 16*k_steps] * W^T (+ bias row), weights packed by clift_pack_linear_tc16
+struct Gemm {
+    const __half* w;    // slabs (after the header)
+    const float* meta;  // header of the packed layer
+    int k_steps;        // ceil(K / 16)
+    int n_pad;          // multiple of 32, <= 256
+    int has_bias;
+};
+
+struct PipeState {
+    int stage = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance() {
+        if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
+__device__ __forceinline__ int ksteps_per_stage(int n_pad) { return n_pad >= 256 ? 1 : 256 / n_pad; }
+
+// warp 0, one lane: stream the GEMM's weight slabs (64 * n_pad bytes per k-step)
+__device__ __forceinline__ void produce(const Smem& s, const Gemm& g, PipeState& ps) {
+    const int per = ksteps_per_stage(g.n_pad);
+    const uint32_t kstep_bytes = 64u * g.n_pad;
+    const int steps = g.k_steps + g.has_bias;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(g.w);
+    for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
+        const uint32_t bytes = (uint32_t)min(per, steps - k0) * kstep_bytes;
+        tc::mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
+        tc::mbar_arrive_expect_tx(&s.full[ps.stage], bytes);
+        tc::bulk_load(s.w + (size_t)ps.stage * kStageBytes, src + (size_t)k0 * kstep_bytes, bytes, &s.full[ps.stage]);
+    }
+}
+
+// warp 1, one lane: issue the three fp16 MMAs per k-step.
+// n_pad > 128 : slab = [hi | lo][2 k-chunks][n_pad][8]: A_hi*W_hi, A_hi*W_lo, A_lo*W_hi
+// n_pad <= 128: slab = [2 k-chunks][hi | lo][n_pad][8]: A_hi*[W_hi ; W_lo] is ONE MMA writing D[:, 0:n_pad) and
+//               D[:, n_pad:2n_pad) (the epilogue adds the two column blocks), then A_lo*W_hi
+// bias        : the slab after the last K slab carries the scaled bias in its k row 0; its A operand is the ones chunk.
+__device__ __forceinline__ void issue(const Smem& s, const Gemm& g, PipeState& ps, uint32_t tmem, uint32_t a_parity,
+                                      long long* trace = nullptr) {
+    const uint32_t idesc = tc::make_idesc_f16(kRows, g.n_pad);
+    const uint32_t rows16 = (uint32_t)g.n_pad;
+    const bool stacked = g.n_pad <= 128;
+    const uint32_t idesc_ss = stacked ? tc::make_idesc_f16(kRows, 2 * g.n_pad) : idesc;
+    const int per = ksteps_per_stage(g.n_pad);
+    const uint32_t kstep16 = 64u * g.n_pad >> 4;
+    constexpr uint32_t kStage16 = kStageBytes >> 4;
+    constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);     // SBO 128 B, descriptor version 1
+    const uint32_t a_lbo = (kRows * 16u >> 4) << 16;
+    const uint32_t b_lbo = (stacked ? 2u * rows16 : rows16) << 16;
+    uint32_t ah = (tc::smem_addr(s.a_hi) >> 4) | a_lbo;
+    uint32_t al = (tc::smem_addr(s.a_lo) >> 4) | a_lbo;
+    const uint32_t ones_lo = (tc::smem_addr(s.ones) >> 4) | a_lbo;
+    const uint32_t w_lo0 = (tc::smem_addr(s.w) >> 4) | b_lbo;
+    const uint32_t lo_off = stacked ? 0u : 2u * rows16;
+    auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+
+    tc::mbar_wait(s.bar_a, a_parity);
+    tc::fence_after_sync();
+    if (trace) trace[3] = clock64();
+    const int steps = g.k_steps + g.has_bias;
+    uint32_t acc = 0u;
+    for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
+        tc::mbar_wait(&s.full[ps.stage], ps.phase);
+        tc::fence_after_sync();
+        if (trace && k0 == 0) trace[5] = clock64();
+        uint32_t w_lo = w_lo0 + (uint32_t)ps.stage * kStage16;
+        const int n_here = min(per, steps - k0);
+        for (int j = 0; j < n_here; ++j, w_lo += kstep16) {
+            const bool bias_step = k0 + j >= g.k_steps;
+            const uint64_t a_desc = desc(bias_step ? ones_lo : ah);
+            const uint64_t bh = desc(w_lo);
+            tc::mma_ss_f16(tmem, a_desc, bh, idesc_ss, acc);
+            acc = 1u;
+            if (!stacked) tc::mma_ss_f16(tmem, a_desc, desc(w_lo + lo_off), idesc, 1u);
+            if (!bias_step) tc::mma_ss_f16(tmem, desc(al), bh, idesc, 1u);
+            ah += 2u * (kRows * 16u >> 4);
+            al += 2u * (kRows * 16u >> 4);
+        }
+        tc::mma_commit(&s.empty[ps.stage]);
+    }
+    tc::mma_commit(s.bar_d);
+    if (trace) trace[4] = clock64();
+}
+
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// (x, y) -> fp16 pair of the values and of their remainders
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 b = __half22float2(h);
+    hi = h2_bits(h);
+    lo = h2_bits(__floats2half2_rn(x - b.x, y - b.y));
+}
+
+// 16 consecutive K values (k0 multiple of 16, already scaled) of record `row` -> A_hi / A_lo
+__device__ __forceinline__ void put16(const Smem& s, int row, int k0, const float* v) {
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    const size_t off = ((size_t)(k0 >> 3) * kRows + row) * 16;
+    uint4* dh = reinterpret_cast<uint4*>(s.a_hi + off);
+    uint4* dl = reinterpret_cast<uint4*>(s.a_lo + off);
+    dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
+    dh[kRows] = make_uint4(h[4], h[5], h[6], h[7]);
+    dl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+    dl[kRows] = make_uint4(l[4], l[5], l[6], l[7]);
+}
+
+// one K value of one record (any thread)
+__device__ __forceinline__ void put1(const Smem& s, int row, int k, float x) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    const size_t off = ((size_t)(k >> 3) * kRows + row) * 16 + (size_t)(k & 7) * 2;
+    *reinterpret_cast<__half*>(s.a_hi + off) = h;
+    *reinterpret_cast<__half*>(s.a_lo + off) = l;
+}
+
+__device__ __forceinline__ void publish_a(const Smem& s) {
+    tc::fence_proxy_async_smem();
+    tc::fence_before_sync();
+    tc::named_bar_sync(1, kRowThreads);
+    if (threadIdx.x == 64) tc::mbar_arrive(s.bar_a);
+}
+
+struct RowId {
+    int row, part, rt;
+    uint32_t lane_base;
+};
+
+__device__ __forceinline__ RowId make_row_id(uint32_t tmem) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    RowId r;
+    const int quarter = warp & 3;           // the TMEM lane quarter a warp may touch is warp_id % 4
+    r.row = quarter * 32 + lane;
+    r.part = (warp - 2) >> 2;
+    r.rt = threadIdx.x - 64;
+    r.lane_base = tmem + ((uint32_t)(quarter * 32) << 16);
+    return r;
+}
+
+// 16 accumulator columns of this thread's record; stacked GEMMs keep A_hi*W_lo in columns [n_pad, 2 n_pad)
+__device__ __forceinline__ void ld_acc16(const RowId& r, int c0, int n_pad, float* v) {
+    tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
+    if (n_pad <= 128) {
+        float u[16];
+        tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c0), u);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += u[i];
+    } else {
+        tc::tmem_wait_ld();
+    }
+}
+
+__device__ __forceinline__ void tc16_init(const Smem& s) {
+    for (int i = threadIdx.x; i < kOnesBytes / 2; i += kThreads)
+        reinterpret_cast<__half*>(s.ones)[i] = __float2half_rn((i < kRows * 8 && (i & 7) == 0) ? 1.0f : 0.0f);
+    tc::fence_proxy_async_smem();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            tc::mbar_init(&s.full[i], 1);
+            tc::mbar_init(&s.empty[i], 1);
+        }
+        tc::mbar_init(s.bar_a, 1);
+        tc::mbar_init(s.bar_d, 1);
+        tc::fence_barrier_init();
+    }
+    if ((threadIdx.x >> 5) == 1) tc::tmem_alloc(s.tmem_base, kTmemCols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// parity / bring-up kernel: out[128][n_pad] = a[128][K] * W^T (+ bias), one CTA
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) tc16_gemm_test_kernel(const float* __restrict__ a, int K, Gemm g, float* __restrict__ out) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem s = carve_smem(smem_raw);
+    const int warp = threadIdx.x >> 5;
+    tc16_init(s);
+    const uint32_t tmem = *s.tmem_base;
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            PipeState ps;
+            produce(s, g, ps);
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            PipeState ps;
+            issue(s, g, ps, tmem, 0);
+        }
+    } else {
+        const RowId r = make_row_id(tmem);
+        const float ca = g.meta[0], inv = g.meta[2];
+        for (int k0 = r.part * 16; k0 < g.k_steps * 16; k0 += 16 * kParts) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (k0 + i < K) ? a[(size_t)r.row * K + k0 + i] * ca : 0.0f;
+            put16(s, r.row, k0, v);
+        }
+        publish_a(s);
+        tc::mbar_wait(s.bar_d, 0);
+        tc::fence_after_sync();
+        for (int c0 = r.part * 16; c0 < g.n_pad; c0 += 16 * kParts) {
+            float v[16];
+            ld_acc16(r, c0, g.n_pad, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) out[(size_t)r.row * g.n_pad + c0 + i] = v[i] * inv;
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// production kernel
+// ---------------------------------------------------------------------------------------------------------
+struct HeadsParams {
+    const float4* rec_pos;
+    const int32_t* rec_ray;
+    const unsigned long long* stats;
+    long long cap;
+    const float* rays;
+    FactorParams app;
+    int dim_app, pe_view, pe_feat, pe_sem, pe_ins;
+    int n_cls, d_ins, slow_fast, softmax, heads;
+    int n_gemms;
+    Gemm g[kMaxGemms];          // semantic | instance fast | instance slow | basis | rgb
+    int n_sem, n_ins, n_rgb;
+    float* rgb_raw;
+    float* sem_raw;
+    float* ins;
+    long long* trace;
+};
+
+__device__ __forceinline__ void stamp(const HeadsParams& P, long long tile_local, int gi, int slot) {
+    if (P.trace && blockIdx.x == 0 && tile_local < 4) P.trace[(tile_local * kMaxGemms + gi) * 10 + slot] = clock64();
+}
+
+// hidden-layer epilogue: D (bias included) -> ReLU -> * e (rescale to the next layer's operand scale) -> fp16 pairs
+__device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0, float* v, float e) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f) * e;
+    put16(s, r.row, c0, v);
+}
+
+__device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, int n_pad, float e) {
+    constexpr int kStride = 16 * kParts;
+    const int c_begin = r.part * 16;
+    if (c_begin >= n_pad) return;
+    if (n_pad <= 128) {
+        for (int c0 = c_begin; c0 < n_pad; c0 += kStride) {
+            float v[16];
+            ld_acc16(r, c0, n_pad, v);
+            relu_put16(s, r, c0, v, e);
+        }
+        return;
+    }
+    float a[16], b[16];
+    tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, a);
+    for (int c0 = c_begin; c0 < n_pad; c0 += 2 * kStride) {
+        tc::tmem_wait_ld();
+        if (c0 + kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), b);
+        relu_put16(s, r, c0, a, e);
+        if (c0 + kStride < n_pad) {
+            tc::tmem_wait_ld();
+            if (c0 + 2 * kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + 2 * kStride), a);
+            relu_put16(s, r, c0 + kStride, b, e);
+        }
+    }
+}
+
+// final-layer epilogue (part 0 threads): D * inv -> scratch[c][row] for c < n_out (scratch = A_hi region as floats)
+__device__ __forceinline__ void epilogue_final(const Smem& s, const RowId& r, int n_out, int n_pad, float inv) {
+    if (r.part != 0) return;
+    float* scratch = reinterpret_cast<float*>(s.a_hi);
+    for (int c0 = 0; c0 < n_out; c0 += 16) {
+        float v[16];
+        ld_acc16(r, c0, n_pad, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < n_out) scratch[(size_t)(c0 + i) * kRows + r.row] = v[i] * inv;
+    }
+}
+
+// semantic final layer for n_cls <= 32: logits in registers -> softmax -> * w -> scratch[c][row]
+__device__ __forceinline__ void epilogue_semantic32(const Smem& s, const RowId& r, int n_cls, int n_pad, int softmax, float w,
+                                                    float inv) {
+    if (r.part != 0) return;
+    float* scratch = reinterpret_cast<float*>(s.a_hi);
+    float v[32];
+    ld_acc16(r, 0, n_pad, v);
+    if (n_cls > 16) {
+        ld_acc16(r, 16, n_pad, v + 16);
+    } else {
+#pragma unroll
+        for (int i = 16; i < 32; ++i) v[i] = 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= inv;
+    if (softmax) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < n_cls) mx = fmaxf(mx, v[i]);
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            v[i] = i < n_cls ? expf(v[i] - mx) : 0.0f;
+            tot += v[i];
+        }
+        const float sc = w / tot;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= sc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= w;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+        if (i < n_cls) scratch[(size_t)i * kRows + r.row] = v[i];
+}
+
+// xyz (+ sin/cos PE, dimension-major frequency-minor) * ca -> A operand, zero padded to a multiple of 16
+__device__ __forceinline__ void build_xyz(const Smem& s, const RowId& r, const float4& p, int pe, float ca) {
+    if (pe == 0) {   // the shipped configuration (pe_sem = pe_ins = 0): one k-step, no decode
+        if (r.part == 0) {
+            const float v[16] = {p.x * ca, p.y * ca, p.z * ca, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            put16(s, r.row, 0, v);
+        }
+        return;
+    }
+    const int n_in = 3 + 6 * pe;
+    const float xyz[3] = {p.x, p.y, p.z};
+    for (int k0 = r.part * 16; k0 < n_in; k0 += 16 * kParts) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int q = k0 + i;
+            float x = 0.0f;
+            if (q < 3) {
+                x = q == 0 ? xyz[0] : (q == 1 ? xyz[1] : xyz[2]);
+            } else if (q < n_in) {
+                const int j = (q - 3) % (3 * pe);
+                const int d = j / pe;
+                const float arg = (d == 0 ? xyz[0] : (d == 1 ? xyz[1] : xyz[2])) * (float)(1 << (j % pe));
+                x = (q - 3 < 3 * pe) ? sinf(arg) : cosf(arg);
+            }
+            v[i] = x * ca;
+        }
+        put16(s, r.row, k0, v);
+    }
+}
+
+// row threads: sum rows [0,nch) of the float scratch over each ray run and add into dst[ray*stride + col0 + c].  Four adjacent
+// lanes share one (run, channel) item: each sums a contiguous quarter of the run, then a fixed-order shuffle tree combines
+// them (bit-reproducible).
+__device__ __forceinline__ void reduce_runs(const Smem& s, int rt, int nch, float* __restrict__ dst, int stride, int col0) {
+    const float* scratch = reinterpret_cast<const float*>(s.a_hi);
+    tc::named_bar_sync(1, kRowThreads);
+    const int n_runs = *s.n_runs;
+    const int items = n_runs * nch, sub = rt & 3;
+    for (int base = 0; base < items; base += kRowThreads / 4) {
+        const int idx = base + (rt >> 2);
+        float acc = 0.0f;
+        int ray = 0, c = 0;
+        if (idx < items) {
+            const int rr = idx / nch;
+            c = idx - rr * nch;
+            const int m0 = s.runs[rr], m1 = s.runs[rr + 1];
+            const int len = m1 - m0, q = (len + 3) >> 2;
+            const int a = m0 + min(sub * q, len), b = m0 + min((sub + 1) * q, len);
+            for (int m = a; m < b; ++m) acc += scratch[(size_t)c * kRows + m];
+            ray = s.ray[m0];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (idx < items && sub == 0) atomicAdd(dst + (int64_t)ray * stride + col0 + c, acc);
+    }
+    tc::named_bar_sync(1, kRowThreads);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const __grid_constant__ HeadsParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Smem s = carve_smem(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < P.n_gemms) s.sc[threadIdx.x] = make_float2(P.g[threadIdx.x].meta[0], P.g[threadIdx.x].meta[2]);
+    tc16_init(s);
+    const uint32_t tmem = *s.tmem_base;
+    const long long n_act = min((long long)P.stats[0], P.cap);
+    const long long n_tiles = (n_act + kRows - 1) / kRows;
+
+    if (warp == 0) {
+        if (tc::elect_one()) {
+            PipeState ps;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+                for (int gi = 0; gi < P.n_gemms; ++gi) produce(s, P.g[gi], ps);
+        }
+    } else if (warp == 1) {
+        if (tc::elect_one()) {
+            PipeState ps;
+            uint32_t count = 0;
+            long long tl = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl)
+                for (int gi = 0; gi < P.n_gemms; ++gi, ++count)
+                    issue(s, P.g[gi], ps, tmem, count & 1,
+                          P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kMaxGemms + gi) * 10 : nullptr);
+        }
+    } else {
+        const RowId r = make_row_id(tmem);
+        const int row = r.row;
+        float* scratch = reinterpret_cast<float*>(s.a_hi);
+        uint32_t count = 0;
+        long long tl = -1;
+        int gi = 0;
+        auto wait_d = [&]() {
+            tc::mbar_wait(s.bar_d, count & 1);
+            ++count;
+            tc::fence_after_sync();
+            if (threadIdx.x == 64) stamp(P, tl, gi, 0);
+        };
+        auto publish = [&](int g_next) {
+            if (threadIdx.x == 64) stamp(P, tl, g_next, 1);
+            publish_a(s);
+            if (threadIdx.x == 64) stamp(P, tl, g_next, 2);
+        };
+        // one MLP stack whose first operand is already published: hidden epilogues feed the next layer in place
+        auto run_hidden = [&](int n_layers) {
+            for (int l = 0; l + 1 < n_layers; ++l, ++gi) {
+                wait_d();
+                epilogue_hidden(s, r, P.g[gi].n_pad, s.sc[gi + 1].x * s.sc[gi].y);
+                publish(gi + 1);
+            }
+            wait_d();   // final layer: the caller reads D, then advances gi
+        };
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ray_next = -1;
+        auto fetch = [&](long long tile) {
+            p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            ray_next = -1;
+            if (tile < n_tiles && tile * kRows + row < n_act) {
+                p_next = P.rec_pos[tile * kRows + row];
+                ray_next = P.rec_ray[tile * kRows + row];
+            }
+        };
+        fetch(blockIdx.x);
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ++tl;
+            const long long base = tile * kRows;
+            const int nv = (int)min((long long)kRows, n_act - base);
+            const float4 p = p_next;
+            const int ray = ray_next;
+            fetch(tile + gridDim.x);
+            if (r.part == 0) {
+                s.ray[row] = ray;
+                s.pos[row] = p;
+            }
+            tc::named_bar_sync(1, kRowThreads);
+            if (warp == 2) {   // run starts, in record order
+                int n = 0;
+                for (int w4 = 0; w4 < kRows / 32; ++w4) {
+                    const int m = w4 * 32 + lane;
+                    const bool start = m < nv && (m == 0 || s.ray[m] != s.ray[m - 1]);
+                    const unsigned bits = __ballot_sync(0xffffffffu, start);
+                    if (start) s.runs[n + __popc(bits & ((1u << lane) - 1u))] = m;
+                    n += __popc(bits);
+                }
+                if (lane == 0) {
+                    s.runs[n] = nv;
+                    *s.n_runs = n;
+                }
+            }
+            gi = 0;
+            if (P.n_sem > 0) {
+                build_xyz(s, r, p, P.pe_sem, s.sc[gi].x);
+                publish(gi);
+                run_hidden(P.n_sem);
+                if (P.n_cls <= 32) {
+                    epilogue_semantic32(s, r, P.n_cls, P.g[gi].n_pad, P.softmax, p.w, s.sc[gi].y);
+                } else {
+                    epilogue_final(s, r, P.n_cls, P.g[gi].n_pad, s.sc[gi].y);
+                    if (r.part == 0) {   // wide heads: softmax over the thread's own column of the scratch
+                        if (P.softmax) {
+                            float mx = -INFINITY;
+                            for (int c = 0; c < P.n_cls; ++c) mx = fmaxf(mx, scratch[(size_t)c * kRows + row]);
+                            float tot = 0.0f;
+                            for (int c = 0; c < P.n_cls; ++c) {
+                                const float e = expf(scratch[(size_t)c * kRows + row] - mx);
+                                scratch[(size_t)c * kRows + row] = e;
+                                tot += e;
+                            }
+                            for (int c = 0; c < P.n_cls; ++c)
+                                scratch[(size_t)c * kRows + row] = (scratch[(size_t)c * kRows + row] / tot) * p.w;
+                        } else {
+                            for (int c = 0; c < P.n_cls; ++c) scratch[(size_t)c * kRows + row] *= p.w;
+                        }
+                    }
+                }
+                ++gi;
+                reduce_runs(s, r.rt, P.n_cls, P.sem_raw, P.n_cls, 0);
+            }
+            if (P.n_ins > 0) {
+                const int width = P.d_ins * (P.slow_fast ? 2 : 1);
+                for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
+                    build_xyz(s, r, p, P.pe_ins, s.sc[gi].x);
+                    publish(gi);
+                    run_hidden(P.n_ins);
+                    epilogue_final(s, r, P.d_ins, P.g[gi].n_pad, s.sc[gi].y * p.w);
+                    ++gi;
+                    if (threadIdx.x == 64) stamp(P, tl, gi, 6);
+                    reduce_runs(s, r.rt, P.d_ins, P.ins, width, net * P.d_ins);
+                    if (threadIdx.x == 64) stamp(P, tl, gi, 7);
+                }
+            }
+            if (P.n_rgb > 0) {
+                const FactorParams& f = P.app;
+                // appearance gather in quad layout (4 lanes x float4 = one 64-byte texel segment per tap, fully coalesced):
+                // scaled plane*line products go straight into the operand rows as fp16 pairs
+                {
+                    const int q = r.rt & 3;
+                    const float ca = s.sc[gi].x;
+                    for (int item = r.rt >> 2; item < 3 * kRows; item += kRowThreads / 4) {
+                        const int m = item / 3, mode = item - m * 3;
+                        const float4 pm = s.pos[m];
+                        const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
+                        const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
+                        const int W = f.pw[mode];
+                        const Tap2 t2 = make_tap2(c_a, c_b, W, f.ph[mode]);
+                        const Tap1 t1 = make_tap1(c_v, f.ll[mode]);
+                        const float* plane = f.plane[mode];
+                        const float* line = f.line[mode];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            const int ch = v * 16 + q * 4;
+                            const float4 pv4 = plane_tap(plane, t2, W, f.comps, ch);
+                            const float4 lv4 = line_tap(line, t1, f.comps, ch);
+                            const int k = mode * f.comps + ch;      // multiple of 4
+                            uint32_t h0, l0, h1, l1;
+                            split2(pv4.x * lv4.x * ca, pv4.y * lv4.y * ca, h0, l0);
+                            split2(pv4.z * lv4.z * ca, pv4.w * lv4.w * ca, h1, l1);
+                            const size_t off = ((size_t)(k >> 3) * kRows + m) * 16 + (size_t)(k & 4) * 2;
+                            *reinterpret_cast<uint2*>(s.a_hi + off) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2*>(s.a_lo + off) = make_uint2(l0, l1);
+                        }
+                    }
+                }
+                publish(gi);
+                wait_d();   // basis GEMM: features in D columns [0, dim_app)
+                const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
+                const int n_base = A + 3;
+                // staging behind the K rows of the first rgb GEMM (inside the A_hi region): base values x_b
+                const int k_rows = P.g[gi + 1].k_steps * kStepK;
+                float* xb = reinterpret_cast<float*>(s.a_hi + (size_t)(k_rows >> 3) * kRows * 16);
+                if (r.part == 0) {
+                    const float inv = s.sc[gi].y;
+                    for (int c0 = 0; c0 < A; c0 += 16) {
+                        float v[16];
+                        ld_acc16(r, c0, P.g[gi].n_pad, v);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (c0 + i < A) xb[(size_t)(c0 + i) * kRows + row] = v[i] * inv;
+                    }
+                } else if (r.part == 1 && ray >= 0) {
+                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kRows + row] = __ldg(P.rays + (int64_t)ray * 8 + 3 + k);
+                } else if (r.part == 1) {
+                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kRows + row] = k == 2 ? 1.0f : 0.0f;
+                }
+                ++gi;
+                tc::fence_before_sync();
+                tc::named_bar_sync(1, kRowThreads);
+                if (threadIdx.x == 64) stamp(P, tl, gi, 6);
+                // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418): one
+                // (record, base value) item per thread and step - SFU sincos (|error| < 4e-7 on these O(1) arguments),
+                // higher frequencies by angle doubling - written as fp16 pairs at the first rgb layer's operand scale.
+                {
+                    const float ca = s.sc[gi].x;
+                    const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
+                    for (int item = r.rt; item < n_base * kRows; item += kRowThreads) {
+                        const int b = item / kRows, m = item - b * kRows;     // b is warp-uniform
+                        const float x = xb[(size_t)b * kRows + m];
+                        const bool is_feat = b < A;
+                        const int nf = is_feat ? pf : pv;
+                        const int ks = is_feat ? o_sf + b * pf : o_sd + (b - A) * pv;
+                        const int kc = is_feat ? o_cf + b * pf : o_cd + (b - A) * pv;
+                        put1(s, m, b, x * ca);
+                        float sv, cv;
+                        __sincosf(x, &sv, &cv);
+                        for (int j = 0; j < nf; ++j) {
+                            put1(s, m, ks + j, sv * ca);
+                            put1(s, m, kc + j, cv * ca);
+                            const float s2 = 2.0f * sv * cv, c2 = 1.0f - 2.0f * sv * sv;
+                            sv = s2;
+                            cv = c2;
+                        }
+                    }
+                    for (int item = r.rt; item < (k_rows - n_in) * kRows; item += kRowThreads)
+                        put1(s, item % kRows, n_in + item / kRows, 0.0f);
+                }
+                if (threadIdx.x == 64) stamp(P, tl, gi, 7);
+                publish(gi);
+                run_hidden(P.n_rgb);
+                epilogue_final(s, r, 3, P.g[gi].n_pad, s.sc[gi].y);
+                ++gi;
+                if (r.part == 0)
+                    for (int c = 0; c < 3; ++c) {
+                        const float x = scratch[(size_t)c * kRows + row];
+                        scratch[(size_t)c * kRows + row] = (1.0f / (1.0f + expf(-x))) * p.w;
+                    }
+                reduce_runs(s, r.rt, 3, P.rgb_raw, 3, 0);
+            }
+        }
+        tc::fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pack-time kernels
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float pow2_floor_ratio(float num_log2, float x) {   // 2^floor(num_log2 - log2(x)), exponent clamped
+    int e = 0;
+    frexpf(x, &e);                        // x = m * 2^e, m in [0.5, 1)  =>  2^(e-1) <= x < 2^e
+    int k = (int)num_log2 - e;            // 2^num / x > 2^(num - e)
+    k = max(-60, min(60, k));
+    return ldexpf(1.0f, k);
+}
+
+// header[0..7] = ca, cw, 1/(ca cw), out bound, in bound, L = max_n sum_k |W_nk|, max|W|, max|b|
+__global__ void __launch_bounds__(256) tc16_plan_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out,
+                                                        int n_in, const float* __restrict__ in_bound_dev, float in_floor,
+                                                        float* __restrict__ header) {
+    __shared__ float red[3][256];
+    float l1 = 0.0f, wm = 0.0f, bm = 0.0f;
+    for (int n = threadIdx.x; n < n_out; n += 256) {
+        float sum = 0.0f;
+        for (int k = 0; k < n_in; ++k) {
+            const float a = fabsf(w[(size_t)n * n_in + k]);
+            sum += a;
+            wm = fmaxf(wm, a);
+        }
+        l1 = fmaxf(l1, sum);
+        if (bias) bm = fmaxf(bm, fabsf(bias[n]));
+    }
+    red[0][threadIdx.x] = l1;
+    red[1][threadIdx.x] = wm;
+    red[2][threadIdx.x] = bm;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+            for (int j = 0; j < 3; ++j) red[j][threadIdx.x] = fmaxf(red[j][threadIdx.x], red[j][threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        l1 = red[0][0] * 1.0001f;    // rounding slack of the fp32 sums
+        wm = red[1][0];
+        bm = red[2][0];
+        float in_bound = in_floor;
+        if (in_bound_dev) in_bound = fmaxf(in_bound, *in_bound_dev);
+        in_bound = fminf(fmaxf(in_bound, 1e-30f), 1e30f);
+        const float ca = pow2_floor_ratio(14.0f, in_bound);
+        float cw = pow2_floor_ratio(14.0f, fmaxf(wm, 1e-30f));
+        if (bm > 0.0f) cw = fminf(cw, pow2_floor_ratio(14.0f, fminf(bm * ca, 1e30f)));
+        header[0] = ca;
+        header[1] = cw;
+        header[2] = 1.0f / (ca * cw);
+        header[3] = in_bound * l1 + bm;
+        header[4] = in_bound;
+        header[5] = l1;
+        header[6] = wm;
+        header[7] = bm;
+    }
+}
+
+// W [out][in] * cw (+ bias * ca * cw in k row 0 of one more slab) -> per k-step slab of fp16 (hi, lo) pairs:
+// [hi|lo][2 k-chunks][n_pad][8] for n_pad > 128 else [2 k-chunks][hi|lo][n_pad][8]; zero padded
+__global__ void pack_linear_tc16_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out, int n_in,
+                                        const float* __restrict__ header, __half* __restrict__ dst, int n_pad, int slabs) {
+    const int64_t total = (int64_t)slabs * kStepK * n_pad;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const float ca = header[0], cw = header[1];
+    const int k = (int)(idx / n_pad), n = (int)(idx % n_pad);
+    const int k_bias = (n_in + kStepK - 1) / kStepK * kStepK;
+    float x = (k < n_in && n < n_out) ? w[(size_t)n * n_in + k] * cw : 0.0f;
+    if (bias && k == k_bias && n < n_out) x = bias[n] * (ca * cw);
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    const int slab = k / kStepK, kc = (k % kStepK) / 8, ki = k & 7;
+    __half* base = dst + (size_t)slab * (2 * kStepK * n_pad);
+    if (n_pad <= 128) {
+        const size_t off = ((size_t)(kc * 2) * n_pad + n) * 8 + ki;
+        base[off] = hi;
+        base[(size_t)n_pad * 8 + off] = lo;
+    } else {
+        const size_t off = ((size_t)kc * n_pad + n) * 8 + ki;
+        base[off] = hi;
+        base[(size_t)kStepK * n_pad + off] = lo;
+    }
+}
+
+// dst[slot] = max |x| (dst zeroed by the caller; |x| >= 0 so the uint order of the bits is the float order)
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ dst) {
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));
+}
+
+__global__ void factor_bound_kernel(float* __restrict__ scratch8) {   // [0..2] plane maxima, [3..5] line maxima -> [6]
+    float b = 0.0f;
+    for (int m = 0; m < 3; ++m) b = fmaxf(b, scratch8[m] * scratch8[3 + m]);
+    scratch8[6] = b * 1.0001f;
+}
+
+}  // namespace
+}  // namespace clift
+
+
+namespace clift {
+
+static bool tc16_add_stack(HeadsParams& P, const clift_mlp& m) {
+    for (int l = 0; l < m.n_layers; ++l) {
+        if (!m.w_tc16[l] || P.n_gemms >= kMaxGemms) return false;
+        Gemm& g = P.g[P.n_gemms];
+        g.meta = reinterpret_cast<const float*>(m.w_tc16[l]);
+        g.w = reinterpret_cast<const __half*>(g.meta + kHeaderFloats);
+        g.k_steps = (int)ceil_div(m.dims[l], kStepK);
+        g.n_pad = (int)round_up(m.dims[l + 1], 32);
+        g.has_bias = 1;
+        if (m.dims[l] > kMaxK || g.n_pad > 256) return false;
+        ++P.n_gemms;
+    }
+    return true;
+}
+
+bool heads_tc16_available(const clift_field* f, int heads) {
+    auto ok = [](const clift_mlp& m) {
+        for (int l = 0; l < m.n_layers; ++l)
+            if (!m.w_tc16[l] || m.dims[l] > kMaxK || m.dims[l + 1] > 256) return false;
+        return m.n_layers >= 1;
+    };
+    if (f->num_classes > CLIFT_MAX_HEAD_OUT || f->dim_instance > CLIFT_MAX_HEAD_OUT) return false;
+    if ((heads & CLIFT_HEAD_SEMANTIC) && !ok(f->semantic)) return false;
+    if ((heads & CLIFT_HEAD_INSTANCE) && (!ok(f->instance_fast) || (f->slow_fast && !ok(f->instance_slow)))) return false;
+    if (heads & CLIFT_HEAD_RGB) {
+        if (!ok(f->rgb) || !f->basis_tc16 || f->dim_appearance > 64 || f->appearance_comps % 16 || 3 * f->appearance_comps > kMaxK)
+            return false;
+        // the base-value staging of the rgb input lives behind the K rows of the first rgb GEMM, inside the A_hi region
+        if (round_up(f->rgb.dims[0], kStepK) * kRows * 2 + (int64_t)(f->dim_appearance + 3) * kRows * 4 > kABytes) return false;
+    }
+    return true;
+}
+
+int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
+                              int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream) {
+    HeadsParams P;
+    memset(&P, 0, sizeof(P));
+    P.rec_pos = ws.rec_pos;
+    P.rec_ray = ws.rec_ray;
+    P.stats = reinterpret_cast<const unsigned long long*>(ws.stats);
+    P.cap = cap;
+    P.rays = rays;
+    P.app = make_factors(field, true);
+    P.dim_app = field->dim_appearance;
+    P.pe_view = field->pe_view;
+    P.pe_feat = field->pe_feat;
+    P.pe_sem = field->pe_sem;
+    P.pe_ins = field->pe_ins;
+    P.n_cls = field->num_classes;
+    P.d_ins = field->dim_instance;
+    P.slow_fast = field->slow_fast;
+    P.softmax = cfg->semantic_softmax;
+    P.rgb_raw = rgb_raw;
+    P.sem_raw = sem_raw;
+    P.ins = ins;
+    P.trace = get_tc_trace();
+    int heads = (sem_raw ? CLIFT_HEAD_SEMANTIC : 0) | (ins ? CLIFT_HEAD_INSTANCE : 0) | (rgb_raw ? CLIFT_HEAD_RGB : 0);
+    bool ok = heads_tc16_available(field, heads);
+    if (ok && sem_raw) {
+        P.n_sem = field->semantic.n_layers;
+        ok = ok && tc16_add_stack(P, field->semantic);
+    }
+    if (ok && ins) {
+        P.n_ins = field->instance_fast.n_layers;
+        ok = ok && tc16_add_stack(P, field->instance_fast);
+        if (field->slow_fast) ok = ok && tc16_add_stack(P, field->instance_slow);
+    }
+    if (ok && rgb_raw) {
+        P.n_rgb = field->rgb.n_layers;
+        if (P.n_gemms < kMaxGemms) {
+            Gemm& g = P.g[P.n_gemms];
+            g.meta = reinterpret_cast<const float*>(field->basis_tc16);
+            g.w = reinterpret_cast<const __half*>(g.meta + kHeaderFloats);
+            g.k_steps = (int)ceil_div(3 * field->appearance_comps, kStepK);
+            g.n_pad = (int)round_up(field->dim_appearance, 32);
+            g.has_bias = 0;    // appearance_basis_mat has bias=False (tensoRF.py:65)
+            ++P.n_gemms;
+        } else {
+            ok = false;
+        }
+        ok = ok && tc16_add_stack(P, field->rgb);
+    }
+    if (!ok) {
+        set_error("launch_heads_forward_tc16: field lacks fp16 tensor-core operands (clift_pack_linear_tc16) or exceeds the envelope");
+        return CLIFT_ERR_UNSUPPORTED;
+    }
+    if (P.n_gemms == 0 || n_rays <= 0) return CLIFT_OK;
+    const int grid = sm_count();
+#define CLIFT_TC16_CASE(NV)                                                                                            \
+    case NV: {                                                                                                         \
+        CLIFT_CUDA(cudaFuncSetAttribute(heads_tc16_forward_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        (int)kSmemBytes));                                                             \
+        heads_tc16_forward_kernel<NV><<<grid, kThreads, kSmemBytes, stream>>>(P);                                      \
+        break;                                                                                                         \
+    }
+    switch (P.app.comps / 16) {
+        CLIFT_TC16_CASE(1)
+        CLIFT_TC16_CASE(2)
+        CLIFT_TC16_CASE(3)
+        CLIFT_TC16_CASE(4)
+        default:
+            set_error("launch_heads_forward_tc16: appearance_comps %d not in {16,32,48,64}", P.app.comps);
+            return CLIFT_ERR_UNSUPPORTED;
+    }
+#undef CLIFT_TC16_CASE
+    CLIFT_AFTER_LAUNCH("heads_tc16_forward_kernel");
+    return CLIFT_OK;
+}
+
+}  // namespace clift
+
+using namespace clift;
+
+extern "C" int64_t clift_tc16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias) {
+    if (n_out <= 0 || n_in <= 0 || n_out > 256 || n_in > kMaxK) return CLIFT_ERR_UNSUPPORTED;
+    const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kStepK) + (has_bias ? 1 : 0);
+    return (int64_t)kHeaderFloats * 4 + (int64_t)slabs * 2 * kStepK * n_pad * 2;
+}
+
+extern "C" int32_t clift_pack_linear_tc16(const float* w, const float* bias, void* dst, int32_t n_out, int32_t n_in,
+                                          const float* in_bound, float in_bound_floor, void* stream) {
+    CLIFT_CHECK_ARG(w && dst, "null pointer");
+    CLIFT_CHECK_ARG(((uintptr_t)dst & 15) == 0, "dst must be 16-byte aligned");
+    CLIFT_CHECK_ARG(in_bound || in_bound_floor > 0.0f, "an input bound is required (device scalar and/or a positive floor)");
+    CLIFT_CHECK_SUPPORTED(n_out > 0 && n_in > 0 && n_out <= 256 && n_in <= kMaxK, "layer wider than 256");
+    const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kStepK) + (bias ? 1 : 0);
+    float* header = reinterpret_cast<float*>(dst);
+    tc16_plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, bias, n_out, n_in, in_bound, in_bound_floor, header);
+    CLIFT_AFTER_LAUNCH("tc16_plan_kernel");
+    const int64_t total = (int64_t)slabs * kStepK * n_pad;
+    pack_linear_tc16_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        w, bias, n_out, n_in, header, reinterpret_cast<__half*>(header + kHeaderFloats), n_pad, slabs);
+    CLIFT_AFTER_LAUNCH("pack_linear_tc16_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_tc16_factor_bound(const float* const* planes3, const float* const* lines3, const int64_t* plane_elems3,
+                                           const int64_t* line_elems3, float* scratch8, void* stream) {
+    CLIFT_CHECK_ARG(planes3 && lines3 && plane_elems3 && line_elems3 && scratch8, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CLIFT_CUDA(cudaMemsetAsync(scratch8, 0, 8 * sizeof(float), st));
+    for (int m = 0; m < 3; ++m) {
+        CLIFT_CHECK_ARG(planes3[m] && lines3[m] && plane_elems3[m] > 0 && line_elems3[m] > 0, "null factor or empty factor");
+        const int grid_p = (int)std::min<int64_t>(ceil_div(plane_elems3[m], 256 * 8), 4 * sm_count());
+        absmax_kernel<<<std::max(grid_p, 1), 256, 0, st>>>(planes3[m], plane_elems3[m], scratch8 + m);
+        CLIFT_AFTER_LAUNCH("absmax_kernel");
+        const int grid_l = (int)std::min<int64_t>(ceil_div(line_elems3[m], 256 * 8), 4 * sm_count());
+        absmax_kernel<<<std::max(grid_l, 1), 256, 0, st>>>(lines3[m], line_elems3[m], scratch8 + 3 + m);
+        CLIFT_AFTER_LAUNCH("absmax_kernel");
+    }
+    factor_bound_kernel<<<1, 1, 0, st>>>(scratch8);
+    CLIFT_AFTER_LAUNCH("factor_bound_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_debug_tc16_gemm(const float* a, const void* w_tc16, float* out, int32_t k, int32_t n_out,
+                                         int32_t has_bias, void* stream) {
+    CLIFT_CHECK_ARG(a && w_tc16 && out, "null pointer");
+    CLIFT_CHECK_SUPPORTED(n_out > 0 && k > 0 && n_out <= 256 && k <= kMaxK, "layer wider than 256");
+    Gemm g;
+    g.meta = reinterpret_cast<const float*>(w_tc16);
+    g.w = reinterpret_cast<const __half*>(g.meta + kHeaderFloats);
+    g.k_steps = (int)ceil_div(k, kStepK);
+    g.n_pad = (int)round_up(n_out, 32);
+    g.has_bias = has_bias ? 1 : 0;
+    CLIFT_CUDA(cudaFuncSetAttribute(tc16_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    tc16_gemm_test_kernel<<<1, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, k, g, out);
+    CLIFT_AFTER_LAUNCH("tc16_gemm_test_kernel");
+    return CLIFT_OK;
+}

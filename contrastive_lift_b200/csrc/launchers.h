@@ -36,6 +36,11 @@ bool heads_tc_available(const clift_field* f, int heads);
 int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
                             int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream);
 
+// heads_tc16.cu
+bool heads_tc16_available(const clift_field* f, int heads);
+int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
+                              int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream);
+
 // pack.cu
 int launch_transpose(const float* src, float* dst, int rows, int cols, int dst_rows_pad, int dst_cols_pad, cudaStream_t stream);
 

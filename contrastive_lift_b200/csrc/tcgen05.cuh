@@ -1,4 +1,4 @@
-// Thin inline-PTX wrappers for the Blackwell tensor-core path (sm_100a): tcgen05.mma (kind::tf32) with accumulators in
+// Thin inline-PTX wrappers for the Blackwell tensor-core path (sm_100a): tcgen05.mma (kind::tf32, kind::f16) with accumulators in
 // tensor memory, TMEM allocation / load / store, mbarrier pipelines and 1-D bulk TMA copies.
 //
 // Operand conventions used by heads_tc.cu (all "K-major, no swizzle" canonical UMMA layouts):
@@ -106,6 +106,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 //   [4,6) c_format = 1 (F32)  [7,10) a_format = 2 (TF32)  [10,13) b_format = 2  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int m, int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// kind::f16 with fp16 operands, fp32 accumulate: a_format = b_format = 0 (F16); one MMA consumes K = 16 (two 16-byte chunks)
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands
+__device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T   (single thread)

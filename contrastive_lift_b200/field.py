@@ -103,19 +103,40 @@ class _PackedMlp:
         self.bias = [torch.zeros((L.n_pad(l.out_features),), device=device) for l in self.linears]
         self.w_dgrad: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.w_tc: List[Optional[torch.Tensor]] = [None] * len(self.linears)
+        self.w_tc16: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.g_wt: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.g_bias: List[Optional[torch.Tensor]] = [None] * len(self.linears)
 
-    def pack(self, lib, stream, training: bool):
+    def out_bound_ptr(self) -> int:
+        """Device address of the bound on |output| of the last layer (header word 3 of its fp16-split operand);
+        -1 = no such operand (a stack chained to it stays off the fp16 path)."""
+        t = self.w_tc16[-1]
+        return -1 if t is None else t.data_ptr() + 12
+
+    def pack(self, lib, stream, training: bool, in_bound_ptr: Optional[int] = None, in_bound_floor: float = 1.0):
+        """``in_bound_ptr`` / ``in_bound_floor``: bound on |input| of the first layer for the fp16-split operand chain
+        (device scalar and/or constant; xyz, sin/cos and unit directions are bounded by 1)."""
+        bound_ptr, floor = in_bound_ptr, in_bound_floor
         for i, l in enumerate(self.linears):
-            L.check(lib.clift_pack_linear(L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None,
-                                          L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
-            nf = lib.clift_tc_weight_floats(l.out_features, l.in_features, 1 if l.bias is not None else 0)
-            if nf > 0:      # inside the tensor-core envelope: keep the tf32 hi/lo operand current as well
-                if self.w_tc[i] is None:
-                    self.w_tc[i] = torch.zeros((nf,), device=self.wt[i].device)
-                L.check(lib.clift_pack_linear_tc(L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None,
-                                                 L.ptr(self.w_tc[i]), l.out_features, l.in_features, stream))
+            has_bias = 1 if l.bias is not None else 0
+            w, b = L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None
+            L.check(lib.clift_pack_linear(w, b, L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
+            if not training:    # tensor-core operands serve inference only (PackedField.refresh tracks their staleness)
+                nf = lib.clift_tc_weight_floats(l.out_features, l.in_features, has_bias)
+                if nf > 0:      # inside the tensor-core envelope: tf32 hi/lo operand
+                    if self.w_tc[i] is None:
+                        self.w_tc[i] = torch.zeros((nf,), device=self.wt[i].device)
+                    L.check(lib.clift_pack_linear_tc(w, b, L.ptr(self.w_tc[i]), l.out_features, l.in_features, stream))
+                nb = lib.clift_tc16_weight_bytes(l.out_features, l.in_features, has_bias)
+                if nb > 0 and bound_ptr != -1:   # fp16-split operand, scales chained layer to layer
+                    if self.w_tc16[i] is None:
+                        self.w_tc16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
+                    L.check(lib.clift_pack_linear_tc16(w, b, L.ptr(self.w_tc16[i]), l.out_features, l.in_features, bound_ptr,
+                                                       float(floor), stream))
+                    bound_ptr, floor = self.w_tc16[i].data_ptr() + 12, 0.0
+                else:
+                    bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
+                    self.w_tc16[i] = None
             if training:
                 if self.w_dgrad[i] is None:
                     self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
@@ -131,6 +152,7 @@ class _PackedMlp:
             m.bias[i] = L.ptr(self.bias[i])
             m.w_dgrad[i] = L.ptr(self.w_dgrad[i])
             m.w_tc[i] = L.ptr(self.w_tc[i])
+            m.w_tc16[i] = L.ptr(self.w_tc16[i])
 
     def grad_buffers(self, g: L.MlpGrad, want: bool):
         for i in range(len(self.linears)):
@@ -356,6 +378,7 @@ class PackedField:
         self.grid = model.grid_dim()
         self.ids = self._ids(model)
         self.versions: Optional[Tuple[int, ...]] = None
+        self.tc_stale = True
         self.trained = False
         self.model_params = list(model.parameters())
         mk = lambda plist: [torch.empty((p.shape[2], p.shape[3], p.shape[1]), device=dev) for p in plist]
@@ -365,6 +388,7 @@ class PackedField:
         self.src = {"density": (model.density_plane, model.density_line),
                     "appearance": (model.appearance_plane, model.appearance_line)}
         self.basis = _PackedMlp([model.appearance_basis_mat], dev)
+        self.tc16_scratch = torch.zeros((8,), device=dev)
         self.rgb = _PackedMlp(_linears(model.render_appearance_mlp.mlp), dev)
         self.sem = _PackedMlp(_linears(model.render_semantic_mlp.mlp), dev)
         self.insf = _PackedMlp(_linears(model.render_instance_mlp.mlp), dev) if model.render_instance_mlp is not None else None
@@ -401,7 +425,7 @@ class PackedField:
         # Inference renders reuse the packed copy while no parameter version moved.  Training renders always
         # repack: the reference's EMA writes through ``.data`` (trainer:325-329), which version counters miss.
         versions = tuple(p._version for p in self.model_params) + (L.param_epoch(),)
-        if not training and versions == self.versions:
+        if not training and versions == self.versions and not self.tc_stale:
             return
         lib, st = self.lib, L.stream_ptr(self.device)
         for name in ("density", "appearance"):
@@ -410,13 +434,23 @@ class PackedField:
                 p, l = planes[i].data, lines[i].data
                 L.check(lib.clift_pack_plane(L.ptr(p), L.ptr(self.planes[name][i]), p.shape[1], p.shape[2], p.shape[3], st))
                 L.check(lib.clift_pack_plane(L.ptr(l), L.ptr(self.lines[name][i]), l.shape[1], l.shape[2], 1, st))
-        for m in (self.basis, self.rgb, self.sem, self.insf, self.inss):
+        # fp16-split operand chain: |plane*line| bound -> basis -> (features, dirs, sin/cos) -> rgb stack
+        vp3, i3 = C.c_void_p * 3, C.c_int64 * 3
+        ap, al = self.planes["appearance"], self.lines["appearance"]
+        if not training:
+            L.check(lib.clift_tc16_factor_bound(vp3(*[L.ptr(t) for t in ap]), vp3(*[L.ptr(t) for t in al]),
+                                                i3(*[t.numel() for t in ap]), i3(*[t.numel() for t in al]),
+                                                L.ptr(self.tc16_scratch), st))
+        self.basis.pack(lib, st, training, self.tc16_scratch.data_ptr() + 24, 0.0)
+        self.rgb.pack(lib, st, training, self.basis.out_bound_ptr(), 1.0)
+        for m in (self.sem, self.insf, self.inss):
             if m is not None:
                 m.pack(lib, st, training)
         f = self.field
         f.basis = L.ptr(self.basis.wt[0])
         f.basis_dgrad = L.ptr(self.basis.w_dgrad[0])
         f.basis_tc = L.ptr(self.basis.w_tc[0])
+        f.basis_tc16 = L.ptr(self.basis.w_tc16[0])
         self.rgb.fill(f.rgb)
         self.sem.fill(f.semantic)
         if self.insf is not None:
@@ -424,6 +458,7 @@ class PackedField:
         if self.inss is not None:
             self.inss.fill(f.instance_slow)
         self.versions = versions
+        self.tc_stale = training        # training refreshes skip the tensor-core operands
         self.trained = self.trained or training
 
     # ---- gradient side ---------------------------------------------------------------------------

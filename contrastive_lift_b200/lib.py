@@ -13,10 +13,10 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
-HEADS_AUTO, HEADS_FMA, HEADS_TENSOR = 0, 1, 2
+HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
 
 _fp = C.POINTER(C.c_float)
 _vp = C.c_void_p
@@ -24,7 +24,8 @@ _vp = C.c_void_p
 
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)),
-                ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS), ("w_tc", _vp * MAX_LAYERS)]
+                ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS), ("w_tc", _vp * MAX_LAYERS),
+                ("w_tc16", _vp * MAX_LAYERS)]
 
 
 class MlpGrad(C.Structure):
@@ -38,6 +39,7 @@ class Field(C.Structure):
                 ("dim_instance", C.c_int32), ("slow_fast", C.c_int32), ("density_shift", C.c_float),
                 ("density_plane", _vp * 3), ("density_line", _vp * 3),
                 ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp), ("basis_dgrad", _vp), ("basis_tc", _vp),
+                ("basis_tc16", _vp),
                 ("rgb", Mlp), ("semantic", Mlp), ("instance_fast", Mlp), ("instance_slow", Mlp)]
 
 
@@ -82,6 +84,10 @@ SIGNATURES = {
     "clift_tc_weight_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "clift_pack_linear_tc": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_debug_tc_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "clift_tc16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "clift_pack_linear_tc16": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_float, _vp]),
+    "clift_tc16_factor_bound": (C.c_int32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp]),
+    "clift_debug_tc16_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_debug_tc_trace": (C.c_int32, [_vp]),
     "clift_gen_rays": (C.c_int32, [_fp, _fp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp]),
     "clift_sample_points": (C.c_int32, [C.POINTER(RenderCfg), _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp]),

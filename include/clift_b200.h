@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 4
+#define CLIFT_ABI_VERSION 5
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -53,6 +53,8 @@ typedef struct {
     const float* w_dgrad[CLIFT_MAX_LAYERS];
     /* tensor-core operand written by clift_pack_linear_tc() (null = the FP32-FMA head kernel is used) */
     const float* w_tc[CLIFT_MAX_LAYERS];
+    /* fp16-split tensor-core operand written by clift_pack_linear_tc16() (null = not available) */
+    const void* w_tc16[CLIFT_MAX_LAYERS];
 } clift_mlp;
 
 /* Gradient mirror of clift_mlp (same packed shapes); null pointers = do not accumulate. */
@@ -82,6 +84,7 @@ typedef struct {
     const float* basis;              /* appearance_basis_mat packed as a 1-layer clift_mlp weight */
     const float* basis_dgrad;        /* ... and in clift_pack_linear_dgrad() layout (training only, else null) */
     const float* basis_tc;           /* ... and in clift_pack_linear_tc() layout (tensor-core heads, else null) */
+    const void* basis_tc16;          /* ... and in clift_pack_linear_tc16() layout (fp16-split tensor-core heads, else null) */
     clift_mlp rgb;                   /* render_appearance_mlp.mlp       (H1) */
     clift_mlp semantic;              /* render_semantic_mlp.mlp         (H2) */
     clift_mlp instance_fast;         /* render_instance_mlp.mlp         (H3) */
@@ -107,14 +110,16 @@ typedef struct {
     float weight_thres;              /* raymarch_weight_thres 1e-4 */
     int32_t semantic_softmax;        /* semantic_weight_mode == "softmax" */
     int32_t heads;                   /* bit mask of CLIFT_HEAD_* to evaluate */
-    int32_t head_path;               /* CLIFT_HEADS_AUTO / _FMA / _TENSOR */
+    int32_t head_path;               /* CLIFT_HEADS_AUTO / _FMA / _TENSOR / _TENSOR16 */
 } clift_render_cfg;
 
-/* MLP-head implementation: AUTO = tcgen05 tensor cores (3xTF32, fp32-faithful) for inference when the field carries
- * w_tc operands, FP32 FMA otherwise and always for save_for_backward forwards (they record the training stash). */
+/* MLP-head implementation.  AUTO = tcgen05 tensor cores for inference - the fp16-split path (3 kind::f16 MMAs per
+ * product, scaled operands, fp32-faithful) when the field carries w_tc16 operands, else the 3xTF32 path (w_tc) -
+ * and FP32 FMA otherwise and always for save_for_backward forwards (they record the training stash). */
 #define CLIFT_HEADS_AUTO 0
 #define CLIFT_HEADS_FMA 1
 #define CLIFT_HEADS_TENSOR 2
+#define CLIFT_HEADS_TENSOR16 3
 
 #define CLIFT_HEAD_RGB 1
 #define CLIFT_HEAD_SEMANTIC 2
@@ -174,6 +179,26 @@ int32_t clift_pack_linear_tc(const float* w, const float* bias, float* dst, int3
  * the 3xTF32 split (one CTA).  Used by tests only. */
 int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, int32_t has_bias,
                             void* stream);
+
+/* fp16-split tensor-core operand of one nn.Linear (heads_tc16): a 64-byte header of fp32 scalars
+ *   [0] ca = power-of-two scale of the layer's input   [1] cw = scale of the weights   [2] 1/(ca*cw)
+ *   [3] bound on |output| = in_bound * max_n sum_k |W_nk| + max|b|   [4] in_bound   [5..7] the three norms
+ * followed by fp16 (hi, lo) pairs of cw*W in 16-row K slabs (one kind::f16 MMA k-step each), n_pad = round_up(out, 32);
+ * with a bias one more slab follows whose first K row is ca*cw*b.  The input bound is max(in_bound_floor, *in_bound)
+ * (`in_bound` = device scalar or null): pass the previous layer's header + 3 to chain a stack, 1.0 as the floor for inputs
+ * that contain coordinates / sin / cos / unit directions.  Everything is computed on the device, stream-ordered.
+ * clift_tc16_weight_bytes() sizes the buffer (16-byte aligned). */
+int64_t clift_tc16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias);
+int32_t clift_pack_linear_tc16(const float* w, const float* bias, void* dst, int32_t n_out, int32_t n_in,
+                               const float* in_bound, float in_bound_floor, void* stream);
+/* Bound on |plane * line| products of a VM factor set for the chain above: scratch8[6] = max_mode max|plane| * max|line|
+ * (scratch8 = 8 device floats; packed or unpacked factors, only the element counts matter). */
+int32_t clift_tc16_factor_bound(const float* const* planes3, const float* const* lines3, const int64_t* plane_elems3,
+                                const int64_t* line_elems3, float* scratch8, void* stream);
+/* Bring-up / parity entry: out[128][round_up(n_out,32)] = a[128][k] * W^T (+ bias) through the fp16-split core (one CTA);
+ * |a| must respect the input bound the operand was packed with.  Used by tests only. */
+int32_t clift_debug_tc16_gemm(const float* a, const void* w_tc16, float* out, int32_t k, int32_t n_out, int32_t has_bias,
+                              void* stream);
 
 /* Debug: device buffer of 4*24*10 int64 that CTA 0 of the tensor-core head kernel fills with clock64() stamps per
  * (tile, GEMM): 0 accumulator seen, 1 next operand written, 2 operand published, 3 MMA thread saw operand,

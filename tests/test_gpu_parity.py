@@ -92,7 +92,7 @@ def test_density_matches_reference(name):
     assert torch.allclose(sigma, ref, rtol=REL, atol=1e-7), float((sigma - ref).abs().max())
 
 
-@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR], ids=["fma", "tcgen05"])
+@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR, L.HEADS_TENSOR16], ids=["fma", "tcgen05", "tcgen05_f16"])
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
 def test_render_inference_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
@@ -155,7 +155,7 @@ def test_render_training_forward_rng_parity(name, tag, seed):
     assert gpu.rel_err(sem.exp() if bool(fx["softmax"]) else sem, ref_sem.exp() if bool(fx["softmax"]) else ref_sem) < REL
 
 
-@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR], ids=["fma", "tcgen05"])
+@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR, L.HEADS_TENSOR16], ids=["fma", "tcgen05", "tcgen05_f16"])
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
 def test_instance_and_segment_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
@@ -308,7 +308,7 @@ def test_active_list_overflow_is_reported():
     assert gpu.rel_err(out[0], tn(fx["inf_rgb"])) < REL
 
 
-@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR], ids=["fma", "tcgen05"])
+@pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR, L.HEADS_TENSOR16], ids=["fma", "tcgen05", "tcgen05_f16"])
 def test_full_size_properties(path):
     """BASELINE-size frame (400x400, S=512, all heads): properties that need no CPU oracle run."""
     grid = (128, 128, 128)
