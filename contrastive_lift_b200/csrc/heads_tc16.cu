@@ -45,7 +45,10 @@ constexpr int kABytes = kMaxK * kRows * 2;           // one operand half
 constexpr int kOnesBytes = 2 * kRows * 16;
 constexpr int kMaxGemms = 24;
 constexpr int kHeaderFloats = 16;       // per packed layer: ca, cw, 1/(ca cw), out bound, in bound, L, max|W|, max|b|
-constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kTmemCols = 512;     // two 256-column accumulators: GEMM g accumulates in buffer g & 1
+constexpr int kRoundCols = 16 * kParts; // accumulator columns (= next layer's K rows) finished per epilogue round
+constexpr int kMaxRounds = 8;
+constexpr int kXbStride = kRows + 8;    // row stride of the rgb base-value staging (bank-conflict-free for 4 bases x 8 rows)
 
 struct Smem {
     unsigned char* a_hi;   // [kMaxK/8][128][8] fp16  (also the [c][128] float scratch of the final epilogues)
@@ -59,8 +62,8 @@ struct Smem {
     float2* sc;            // [kMaxGemms] (ca, 1/(ca cw)) per GEMM
     uint64_t* full;
     uint64_t* empty;
-    uint64_t* bar_a;
-    uint64_t* bar_d;
+    uint64_t* bar_a;       // [kMaxRounds] operand rounds ready (every row thread arrives), one phase per GEMM and round
+    uint64_t* bar_d;       // accumulator ready (MMA -> row threads)
     uint32_t* tmem_base;
 };
 
@@ -82,7 +85,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
     s.full = reinterpret_cast<uint64_t*>(s.sc + kMaxGemms);
     s.empty = s.full + kStages;
     s.bar_a = s.empty + kStages;
-    s.bar_d = s.bar_a + 1;
+    s.bar_d = s.bar_a + kMaxRounds;
     s.tmem_base = reinterpret_cast<uint32_t*>(s.bar_d + 1);
     return s;
 }
@@ -94,6 +97,10 @@ struct Gemm {
     int k_steps;        // ceil(K / 16)
     int n_pad;          // multiple of 32, <= 256
     int has_bias;
+    int n_sets;         // stacked small-N GEMMs (n_pad <= 64) spread their k-steps round-robin over n_sets accumulator column sets
+                        //    (2 n_pad columns each; the epilogue adds them): the dependent chain of latency-bound MMAs shortens
+    int a_rounds;       // 1: the A operand is published whole; else ceil(previous n_pad / 48): it streams out of the previous
+                        //    layer's epilogue 48 K rows (3 k-steps) per round
 };
 
 struct PipeState {
@@ -128,16 +135,23 @@ __device__ __forceinline__ void produce(const Smem& s, const Gemm& g, PipeState&
 // n_pad <= 128: slab = [2 k-chunks][hi | lo][n_pad][8]: A_hi*[W_hi ; W_lo] is ONE MMA writing D[:, 0:n_pad) and
 //               D[:, n_pad:2n_pad) (the epilogue adds the two column blocks), then A_lo*W_hi
 // bias        : the slab after the last K slab carries the scaled bias in its k row 0; its A operand is the ones chunk.
-__device__ __forceinline__ void issue(const Smem& s, const Gemm& g, PipeState& ps, uint32_t tmem, uint32_t a_parity,
+// The issuing thread runs ~1 dependent instruction per 4-6 cycles, so the per-k-step body must stay a few dozen instructions
+// (budget 384 cycles per N=256 k-step): descriptors are running values, GEMM fields are copied to registers, and the operand
+// round logic exists only in the kStream instantiation.
+template <bool kStream>
+__device__ __forceinline__ void issue(const Smem& s, const Gemm& gm, PipeState& ps, uint32_t d_tmem, uint32_t& a_parity,
                                       long long* trace = nullptr) {
-    const uint32_t idesc = tc::make_idesc_f16(kRows, g.n_pad);
-    const uint32_t rows16 = (uint32_t)g.n_pad;
-    const bool stacked = g.n_pad <= 128;
-    const uint32_t idesc_ss = stacked ? tc::make_idesc_f16(kRows, 2 * g.n_pad) : idesc;
-    const int per = ksteps_per_stage(g.n_pad);
-    const uint32_t kstep16 = 64u * g.n_pad >> 4;
+    const int n_pad = gm.n_pad, k_steps = gm.k_steps, n_sets = gm.n_sets, a_rounds = gm.a_rounds;
+    const int steps = k_steps + gm.has_bias;
+    const uint32_t idesc = tc::make_idesc_f16(kRows, n_pad);
+    const uint32_t rows16 = (uint32_t)n_pad;
+    const bool stacked = n_pad <= 128;
+    const uint32_t idesc_ss = stacked ? tc::make_idesc_f16(kRows, 2 * n_pad) : idesc;
+    const int per = ksteps_per_stage(n_pad);
+    const uint32_t kstep16 = 64u * n_pad >> 4;
     constexpr uint32_t kStage16 = kStageBytes >> 4;
     constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);     // SBO 128 B, descriptor version 1
+    constexpr uint32_t kAStep = 2u * (kRows * 16u >> 4);       // two k-chunks per MMA
     const uint32_t a_lbo = (kRows * 16u >> 4) << 16;
     const uint32_t b_lbo = (stacked ? 2u * rows16 : rows16) << 16;
     uint32_t ah = (tc::smem_addr(s.a_hi) >> 4) | a_lbo;
@@ -145,32 +159,46 @@ __device__ __forceinline__ void issue(const Smem& s, const Gemm& g, PipeState& p
     const uint32_t ones_lo = (tc::smem_addr(s.ones) >> 4) | a_lbo;
     const uint32_t w_lo0 = (tc::smem_addr(s.w) >> 4) | b_lbo;
     const uint32_t lo_off = stacked ? 0u : 2u * rows16;
+    const uint32_t set_stride = n_sets > 1 ? 2u * n_pad : 0u;
     auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
 
-    tc::mbar_wait(s.bar_a, a_parity);
-    tc::fence_after_sync();
+    int rounds_seen = 0;
+    auto need_round = [&](int r) {     // operand rounds 0..r written and published by every row thread
+        while (rounds_seen <= r) {
+            tc::mbar_wait(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
+            a_parity ^= 1u << rounds_seen;
+            ++rounds_seen;
+            tc::fence_after_sync();
+        }
+    };
+    if (!kStream) need_round(a_rounds - 1);
     if (trace) trace[3] = clock64();
-    const int steps = g.k_steps + g.has_bias;
-    uint32_t acc = 0u;
+    int kk = 0, set = 0;
+    uint32_t set_off = 0u;
     for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
         tc::mbar_wait(&s.full[ps.stage], ps.phase);
         tc::fence_after_sync();
         if (trace && k0 == 0) trace[5] = clock64();
         uint32_t w_lo = w_lo0 + (uint32_t)ps.stage * kStage16;
         const int n_here = min(per, steps - k0);
-        for (int j = 0; j < n_here; ++j, w_lo += kstep16) {
-            const bool bias_step = k0 + j >= g.k_steps;
+        for (int j = 0; j < n_here; ++j, ++kk, w_lo += kstep16, ah += kAStep, al += kAStep) {
+            if (kStream) need_round(min(kk * kStepK / kRoundCols, a_rounds - 1));
+            const bool bias_step = kk >= k_steps;
             const uint64_t a_desc = desc(bias_step ? ones_lo : ah);
             const uint64_t bh = desc(w_lo);
-            tc::mma_ss_f16(tmem, a_desc, bh, idesc_ss, acc);
-            acc = 1u;
-            if (!stacked) tc::mma_ss_f16(tmem, a_desc, desc(w_lo + lo_off), idesc, 1u);
-            if (!bias_step) tc::mma_ss_f16(tmem, desc(al), bh, idesc, 1u);
-            ah += 2u * (kRows * 16u >> 4);
-            al += 2u * (kRows * 16u >> 4);
+            const uint32_t dt = d_tmem + set_off;
+            tc::mma_ss_f16(dt, a_desc, bh, idesc_ss, kk >= n_sets ? 1u : 0u);   // the first MMA into a column set overwrites
+            if (!stacked) tc::mma_ss_f16(dt, a_desc, desc(w_lo + lo_off), idesc, 1u);
+            if (!bias_step) tc::mma_ss_f16(dt, desc(al), bh, idesc, 1u);
+            set_off += set_stride;
+            if (++set == n_sets) {
+                set = 0;
+                set_off = 0u;
+            }
         }
         tc::mma_commit(&s.empty[ps.stage]);
     }
+    if (kStream) need_round(a_rounds - 1);   // keep the round barriers' parities in step when K ends before the last round
     tc::mma_commit(s.bar_d);
     if (trace) trace[4] = clock64();
 }
@@ -208,11 +236,11 @@ __device__ __forceinline__ void put1(const Smem& s, int row, int k, float x) {
     *reinterpret_cast<__half*>(s.a_lo + off) = l;
 }
 
-__device__ __forceinline__ void publish_a(const Smem& s) {
+// every row thread: the operand rows it wrote for round `r` of the next GEMM are visible to the tensor core
+__device__ __forceinline__ void arrive_round(const Smem& s, int r) {
     tc::fence_proxy_async_smem();
     tc::fence_before_sync();
-    tc::named_bar_sync(1, kRowThreads);
-    if (threadIdx.x == 64) tc::mbar_arrive(s.bar_a);
+    tc::mbar_arrive(&s.bar_a[r]);
 }
 
 struct RowId {
@@ -231,15 +259,18 @@ __device__ __forceinline__ RowId make_row_id(uint32_t tmem) {
     return r;
 }
 
-// 16 accumulator columns of this thread's record; stacked GEMMs keep A_hi*W_lo in columns [n_pad, 2 n_pad)
-__device__ __forceinline__ void ld_acc16(const RowId& r, int c0, int n_pad, float* v) {
-    tc::tmem_ld16(r.lane_base + (uint32_t)c0, v);
+// 16 accumulator columns of this thread's record; stacked GEMMs keep A_hi*W_lo in columns [n_pad, 2 n_pad) and may spread
+// their k-steps over n_sets such column sets
+__device__ __forceinline__ void ld_acc16(uint32_t d, int c0, int n_pad, int n_sets, float* v) {
+    tc::tmem_ld16(d + (uint32_t)c0, v);
     if (n_pad <= 128) {
-        float u[16];
-        tc::tmem_ld16(r.lane_base + (uint32_t)(n_pad + c0), u);
-        tc::tmem_wait_ld();
+        for (int b = 1; b < 2 * n_sets; ++b) {
+            float u[16];
+            tc::tmem_ld16(d + (uint32_t)(b * n_pad + c0), u);
+            tc::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += u[i];
+            for (int i = 0; i < 16; ++i) v[i] += u[i];
+        }
     } else {
         tc::tmem_wait_ld();
     }
@@ -254,7 +285,7 @@ __device__ __forceinline__ void tc16_init(const Smem& s) {
             tc::mbar_init(&s.full[i], 1);
             tc::mbar_init(&s.empty[i], 1);
         }
-        tc::mbar_init(s.bar_a, 1);
+        for (int i = 0; i < kMaxRounds; ++i) tc::mbar_init(&s.bar_a[i], kRowThreads);
         tc::mbar_init(s.bar_d, 1);
         tc::fence_barrier_init();
     }
@@ -281,7 +312,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc16_gemm_test_kernel(const float
     } else if (warp == 1) {
         if (tc::elect_one()) {
             PipeState ps;
-            issue(s, g, ps, tmem, 0);
+            uint32_t a_parity = 0;
+            issue<false>(s, g, ps, tmem, a_parity);
         }
     } else {
         const RowId r = make_row_id(tmem);
@@ -292,12 +324,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc16_gemm_test_kernel(const float
             for (int i = 0; i < 16; ++i) v[i] = (k0 + i < K) ? a[(size_t)r.row * K + k0 + i] * ca : 0.0f;
             put16(s, r.row, k0, v);
         }
-        publish_a(s);
+        arrive_round(s, 0);
         tc::mbar_wait(s.bar_d, 0);
         tc::fence_after_sync();
         for (int c0 = r.part * 16; c0 < g.n_pad; c0 += 16 * kParts) {
             float v[16];
-            ld_acc16(r, c0, g.n_pad, v);
+            ld_acc16(r.lane_base, c0, g.n_pad, g.n_sets, v);
 #pragma unroll
             for (int i = 0; i < 16; ++i) out[(size_t)r.row * g.n_pad + c0 + i] = v[i] * inv;
         }
@@ -318,7 +350,7 @@ struct HeadsParams {
     const float* rays;
     FactorParams app;
     int dim_app, pe_view, pe_feat, pe_sem, pe_ins;
-    int n_cls, d_ins, slow_fast, softmax, heads;
+    int n_cls, d_ins, slow_fast, softmax, use_sets;
     int n_gemms;
     Gemm g[kMaxGemms];          // semantic | instance fast | instance slow | basis | rgb
     int n_sem, n_ins, n_rgb;
@@ -326,9 +358,14 @@ struct HeadsParams {
     float* sem_raw;
     float* ins;
     long long* trace;
+    int stream;                 // 1: hidden-layer operands stream out of the epilogues in rounds, accumulators ping-pong
+    int park;                   // 1: the appearance gather runs row-mapped inside the MMA phases of the xyz stacks and parks
+                                //    its fp16 pairs in spare tensor-memory columns (requires !stream: one accumulator buffer)
 };
 
-__device__ __forceinline__ void stamp(const HeadsParams& P, long long tile_local, int gi, int slot) {
+constexpr uint32_t kParkCol = 256;      // first tensor-memory column of the parked appearance products
+
+__device__ __forceinline__ void stamp(const HeadsParams& P, int tile_local, int gi, int slot) {
     if (P.trace && blockIdx.x == 0 && tile_local < 4) P.trace[(tile_local * kMaxGemms + gi) * 10 + slot] = clock64();
 }
 
@@ -339,39 +376,44 @@ __device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0
     put16(s, r.row, c0, v);
 }
 
-__device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, int n_pad, float e) {
-    constexpr int kStride = 16 * kParts;
+// Streams the next layer's operand: round j = this thread's chunk of accumulator columns [48 j, 48 j + 48), i.e. K rows
+// (3 k-steps) of the next GEMM, which the MMA thread issues as soon as all 384 row threads have arrived on bar_a[j] - the
+// next layer's MMAs (into the other accumulator buffer) overlap the rest of this epilogue.
+__device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, uint32_t d, const Gemm& g, float e, bool stream) {
+    const int n_pad = g.n_pad;
+    const int rounds = (n_pad + kRoundCols - 1) / kRoundCols;
     const int c_begin = r.part * 16;
-    if (c_begin >= n_pad) return;
     if (n_pad <= 128) {
-        for (int c0 = c_begin; c0 < n_pad; c0 += kStride) {
-            float v[16];
-            ld_acc16(r, c0, n_pad, v);
-            relu_put16(s, r, c0, v, e);
+        for (int j = 0, c0 = c_begin; j < rounds; ++j, c0 += kRoundCols) {
+            if (c0 < n_pad) {
+                float v[16];
+                ld_acc16(d, c0, n_pad, g.n_sets, v);
+                relu_put16(s, r, c0, v, e);
+            }
+            if (stream) arrive_round(s, j);
         }
+        if (!stream) arrive_round(s, 0);
         return;
     }
-    float a[16], b[16];
-    tc::tmem_ld16(r.lane_base + (uint32_t)c_begin, a);
-    for (int c0 = c_begin; c0 < n_pad; c0 += 2 * kStride) {
-        tc::tmem_wait_ld();
-        if (c0 + kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + kStride), b);
-        relu_put16(s, r, c0, a, e);
-        if (c0 + kStride < n_pad) {
+    for (int j = 0, c0 = c_begin; j < rounds; ++j, c0 += kRoundCols) {
+        if (c0 < n_pad) {
+            float v[16];
+            tc::tmem_ld16(d + (uint32_t)c0, v);
             tc::tmem_wait_ld();
-            if (c0 + 2 * kStride < n_pad) tc::tmem_ld16(r.lane_base + (uint32_t)(c0 + 2 * kStride), a);
-            relu_put16(s, r, c0 + kStride, b, e);
+            relu_put16(s, r, c0, v, e);
         }
+        if (stream) arrive_round(s, j);
     }
+    if (!stream) arrive_round(s, 0);
 }
 
 // final-layer epilogue (part 0 threads): D * inv -> scratch[c][row] for c < n_out (scratch = A_hi region as floats)
-__device__ __forceinline__ void epilogue_final(const Smem& s, const RowId& r, int n_out, int n_pad, float inv) {
+__device__ __forceinline__ void epilogue_final(const Smem& s, const RowId& r, uint32_t d, int n_out, const Gemm& g, float inv) {
     if (r.part != 0) return;
     float* scratch = reinterpret_cast<float*>(s.a_hi);
     for (int c0 = 0; c0 < n_out; c0 += 16) {
         float v[16];
-        ld_acc16(r, c0, n_pad, v);
+        ld_acc16(d, c0, g.n_pad, g.n_sets, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if (c0 + i < n_out) scratch[(size_t)(c0 + i) * kRows + r.row] = v[i] * inv;
@@ -379,14 +421,14 @@ __device__ __forceinline__ void epilogue_final(const Smem& s, const RowId& r, in
 }
 
 // semantic final layer for n_cls <= 32: logits in registers -> softmax -> * w -> scratch[c][row]
-__device__ __forceinline__ void epilogue_semantic32(const Smem& s, const RowId& r, int n_cls, int n_pad, int softmax, float w,
-                                                    float inv) {
+__device__ __forceinline__ void epilogue_semantic32(const Smem& s, const RowId& r, uint32_t d, int n_cls, const Gemm& g, int softmax,
+                                                    float w, float inv) {
     if (r.part != 0) return;
     float* scratch = reinterpret_cast<float*>(s.a_hi);
     float v[32];
-    ld_acc16(r, 0, n_pad, v);
+    ld_acc16(d, 0, g.n_pad, g.n_sets, v);
     if (n_cls > 16) {
-        ld_acc16(r, 16, n_pad, v + 16);
+        ld_acc16(d, 16, g.n_pad, g.n_sets, v + 16);
     } else {
 #pragma unroll
         for (int i = 16; i < 32; ++i) v[i] = 0.0f;
@@ -475,6 +517,102 @@ __device__ __forceinline__ void reduce_runs(const Smem& s, int rt, int nch, floa
     tc::named_bar_sync(1, kRowThreads);
 }
 
+// all tap loads of one (record, mode) gather item in flight at once: NV x 4 plane taps (L2, the long latency) first, then
+// the line taps (L1-resident); out-of-range taps carry weight 0 and read a clamped (valid) texel
+template <int NV>
+__device__ __forceinline__ void gather_item(const FactorParams& f, int mode, const float4& pm, int q, float ca, const Smem& s,
+                                            int m) {
+    const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
+    const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
+    const int W = f.pw[mode], H = f.ph[mode], Ln = f.ll[mode], C = f.comps;
+    const Tap2 t2 = make_tap2(c_a, c_b, W, H);
+    const Tap1 t1 = make_tap1(c_v, Ln);
+    const int x0 = min(max(t2.x0, 0), W - 1), x1 = min(max(t2.x0 + 1, 0), W - 1);
+    const int y0 = min(max(t2.y0, 0), H - 1), y1 = min(max(t2.y0 + 1, 0), H - 1);
+    const int z0 = min(max(t1.z0, 0), Ln - 1), z1 = min(max(t1.z0 + 1, 0), Ln - 1);
+    const float* p00 = f.plane[mode] + ((int64_t)y0 * W + x0) * C + q * 4;
+    const float* p10 = f.plane[mode] + ((int64_t)y0 * W + x1) * C + q * 4;
+    const float* p01 = f.plane[mode] + ((int64_t)y1 * W + x0) * C + q * 4;
+    const float* p11 = f.plane[mode] + ((int64_t)y1 * W + x1) * C + q * 4;
+    const float* l0 = f.line[mode] + (int64_t)z0 * C + q * 4;
+    const float* l1 = f.line[mode] + (int64_t)z1 * C + q * 4;
+    float4 a[NV], b[NV], c[NV], d[NV], u[NV], w[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        a[v] = ldg4(p00 + v * 16);
+        b[v] = ldg4(p10 + v * 16);
+        c[v] = ldg4(p01 + v * 16);
+        d[v] = ldg4(p11 + v * 16);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        u[v] = ldg4(l0 + v * 16);
+        w[v] = ldg4(l1 + v * 16);
+    }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), lv = make_float4(0.f, 0.f, 0.f, 0.f);
+        fma4(pv, a[v], t2.w00);
+        fma4(pv, b[v], t2.w10);
+        fma4(pv, c[v], t2.w01);
+        fma4(pv, d[v], t2.w11);
+        fma4(lv, u[v], t1.w0);
+        fma4(lv, w[v], t1.w1);
+        const int k = mode * C + v * 16 + q * 4;      // multiple of 4
+        uint32_t h0, lo0, h1, lo1;
+        split2(pv.x * lv.x * ca, pv.y * lv.y * ca, h0, lo0);
+        split2(pv.z * lv.z * ca, pv.w * lv.w * ca, h1, lo1);
+        const size_t off = ((size_t)(k >> 3) * kRows + m) * 16 + (size_t)(k & 4) * 2;
+        *reinterpret_cast<uint2*>(s.a_hi + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(s.a_lo + off) = make_uint2(lo0, lo1);
+    }
+}
+
+// Row-mapped gather slice: channels [8 slice, 8 slice + 8) of mode `mode` at this thread's own record, 12 16-byte loads in
+// flight (one 32-byte sector per tap), products scaled and split to fp16 pairs, parked in 8 tensor-memory columns of the
+// record's lane as [4 words hi | 4 words lo] - the image of one 16-byte A_hi chunk and one A_lo chunk.
+__device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, const float4& pm, int slice, float ca, uint32_t park) {
+    const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
+    const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
+    const int W = f.pw[mode], H = f.ph[mode], Ln = f.ll[mode], C = f.comps;
+    const Tap2 t2 = make_tap2(c_a, c_b, W, H);
+    const Tap1 t1 = make_tap1(c_v, Ln);
+    const int x0 = min(max(t2.x0, 0), W - 1), x1 = min(max(t2.x0 + 1, 0), W - 1);
+    const int y0 = min(max(t2.y0, 0), H - 1), y1 = min(max(t2.y0 + 1, 0), H - 1);
+    const int z0 = min(max(t1.z0, 0), Ln - 1), z1 = min(max(t1.z0 + 1, 0), Ln - 1);
+    const int ch = slice * 8;
+    const float* p00 = f.plane[mode] + ((int64_t)y0 * W + x0) * C + ch;
+    const float* p10 = f.plane[mode] + ((int64_t)y0 * W + x1) * C + ch;
+    const float* p01 = f.plane[mode] + ((int64_t)y1 * W + x0) * C + ch;
+    const float* p11 = f.plane[mode] + ((int64_t)y1 * W + x1) * C + ch;
+    const float* l0 = f.line[mode] + (int64_t)z0 * C + ch;
+    const float* l1 = f.line[mode] + (int64_t)z1 * C + ch;
+    float4 a[2], b[2], c[2], d[2], u[2], w[2];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        a[v] = ldg4(p00 + v * 4);
+        b[v] = ldg4(p10 + v * 4);
+        c[v] = ldg4(p01 + v * 4);
+        d[v] = ldg4(p11 + v * 4);
+        u[v] = ldg4(l0 + v * 4);
+        w[v] = ldg4(l1 + v * 4);
+    }
+    uint32_t words[8];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f), lv = make_float4(0.f, 0.f, 0.f, 0.f);
+        fma4(pv, a[v], t2.w00);
+        fma4(pv, b[v], t2.w10);
+        fma4(pv, c[v], t2.w01);
+        fma4(pv, d[v], t2.w11);
+        fma4(lv, u[v], t1.w0);
+        fma4(lv, w[v], t1.w1);
+        split2(pv.x * lv.x * ca, pv.y * lv.y * ca, words[2 * v], words[4 + 2 * v]);
+        split2(pv.z * lv.z * ca, pv.w * lv.w * ca, words[2 * v + 1], words[4 + 2 * v + 1]);
+    }
+    tc::tmem_st8u(park + (uint32_t)(slice * 8), words);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const __grid_constant__ HeadsParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -484,69 +622,85 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
     tc16_init(s);
     const uint32_t tmem = *s.tmem_base;
     const long long n_act = min((long long)P.stats[0], P.cap);
-    const long long n_tiles = (n_act + kRows - 1) / kRows;
+    const int n_tiles = (int)((n_act + kRows - 1) / kRows);    // < 2^24: one call handles n_rays * n_samples < 2^31
 
     if (warp == 0) {
         if (tc::elect_one()) {
             PipeState ps;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
                 for (int gi = 0; gi < P.n_gemms; ++gi) produce(s, P.g[gi], ps);
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             PipeState ps;
-            uint32_t count = 0;
-            long long tl = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl)
-                for (int gi = 0; gi < P.n_gemms; ++gi, ++count)
-                    issue(s, P.g[gi], ps, tmem, count & 1,
-                          P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kMaxGemms + gi) * 10 : nullptr);
+            uint32_t count = 0, a_parity = 0;
+            int tl = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl)
+                for (int gi = 0; gi < P.n_gemms; ++gi, ++count) {
+                    long long* tr = P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kMaxGemms + gi) * 10 : nullptr;
+                    if (P.stream)
+                        issue<true>(s, P.g[gi], ps, tmem + ((count & 1u) ? 256u : 0u), a_parity, tr);
+                    else
+                        issue<false>(s, P.g[gi], ps, tmem, a_parity, tr);
+                }
         }
     } else {
         const RowId r = make_row_id(tmem);
         const int row = r.row;
         float* scratch = reinterpret_cast<float*>(s.a_hi);
-        uint32_t count = 0;
-        long long tl = -1;
+        uint32_t count = 0;                                    // GEMMs consumed so far (bar_d parity, accumulator buffer)
+        uint32_t d = r.lane_base;                              // accumulator of the GEMM waited for last
+        int tl = -1;
         int gi = 0;
         auto wait_d = [&]() {
             tc::mbar_wait(s.bar_d, count & 1);
+            d = r.lane_base + ((P.stream && (count & 1u)) ? 256u : 0u);
             ++count;
             tc::fence_after_sync();
             if (threadIdx.x == 64) stamp(P, tl, gi, 0);
         };
-        auto publish = [&](int g_next) {
+        auto publish = [&](int g_next) {                       // whole operand written by this thread: round 0
             if (threadIdx.x == 64) stamp(P, tl, g_next, 1);
-            publish_a(s);
-            if (threadIdx.x == 64) stamp(P, tl, g_next, 2);
+            arrive_round(s, 0);
         };
-        // one MLP stack whose first operand is already published: hidden epilogues feed the next layer in place
+        // one MLP stack whose first operand is already published: hidden epilogues stream the next layer's operand in place
+        // parked appearance gather: this thread's record, mode = its part; one 8-channel slice per long MMA phase
+        const int g_basis = P.n_gemms - P.n_rgb - 1;
+        const uint32_t park = r.lane_base + kParkCol + (uint32_t)(r.part * 16 * NV);
+        int park_next = 2 * NV;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto park_slice = [&]() {
+            gather_slice(P.app, r.part, p, park_next, s.sc[g_basis].x, park);
+            ++park_next;
+        };
         auto run_hidden = [&](int n_layers) {
             for (int l = 0; l + 1 < n_layers; ++l, ++gi) {
                 wait_d();
-                epilogue_hidden(s, r, P.g[gi].n_pad, s.sc[gi + 1].x * s.sc[gi].y);
-                publish(gi + 1);
+                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0);
+                if (threadIdx.x == 64) stamp(P, tl, gi + 1, 1);
+                if (park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice();   // hides under that GEMM
             }
             wait_d();   // final layer: the caller reads D, then advances gi
         };
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
         int ray_next = -1;
-        auto fetch = [&](long long tile) {
+        auto fetch = [&](int tile) {
             p_next = make_float4(0.f, 0.f, 0.f, 0.f);
             ray_next = -1;
-            if (tile < n_tiles && tile * kRows + row < n_act) {
-                p_next = P.rec_pos[tile * kRows + row];
-                ray_next = P.rec_ray[tile * kRows + row];
+            const long long rec = (long long)tile * kRows + row;
+            if (tile < n_tiles && rec < n_act) {
+                p_next = P.rec_pos[rec];
+                ray_next = P.rec_ray[rec];
             }
         };
         fetch(blockIdx.x);
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             ++tl;
-            const long long base = tile * kRows;
-            const int nv = (int)min((long long)kRows, n_act - base);
-            const float4 p = p_next;
+            const int nv = (int)min((long long)kRows, n_act - (long long)tile * kRows);
+            p = p_next;
             const int ray = ray_next;
             fetch(tile + gridDim.x);
+            park_next = (P.park && P.n_rgb > 0) ? 0 : 2 * NV;
             if (r.part == 0) {
                 s.ray[row] = ray;
                 s.pos[row] = p;
@@ -572,9 +726,9 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 publish(gi);
                 run_hidden(P.n_sem);
                 if (P.n_cls <= 32) {
-                    epilogue_semantic32(s, r, P.n_cls, P.g[gi].n_pad, P.softmax, p.w, s.sc[gi].y);
+                    epilogue_semantic32(s, r, d, P.n_cls, P.g[gi], P.softmax, p.w, s.sc[gi].y);
                 } else {
-                    epilogue_final(s, r, P.n_cls, P.g[gi].n_pad, s.sc[gi].y);
+                    epilogue_final(s, r, d, P.n_cls, P.g[gi], s.sc[gi].y);
                     if (r.part == 0) {   // wide heads: softmax over the thread's own column of the scratch
                         if (P.softmax) {
                             float mx = -INFINITY;
@@ -601,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                     build_xyz(s, r, p, P.pe_ins, s.sc[gi].x);
                     publish(gi);
                     run_hidden(P.n_ins);
-                    epilogue_final(s, r, P.d_ins, P.g[gi].n_pad, s.sc[gi].y * p.w);
+                    epilogue_final(s, r, d, P.d_ins, P.g[gi], s.sc[gi].y * p.w);
                     ++gi;
                     if (threadIdx.x == 64) stamp(P, tl, gi, 6);
                     reduce_runs(s, r.rt, P.d_ins, P.ins, width, net * P.d_ins);
@@ -610,56 +764,53 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             }
             if (P.n_rgb > 0) {
                 const FactorParams& f = P.app;
-                // appearance gather in quad layout (4 lanes x float4 = one 64-byte texel segment per tap, fully coalesced):
-                // scaled plane*line products go straight into the operand rows as fp16 pairs
-                {
+                if (P.park) {
+                    // the products were gathered slice by slice under the xyz stacks' MMAs (leftover slices now) and wait in
+                    // tensor memory as chunk images: copy them into the operand rows
+                    while (park_next < 2 * NV) park_slice();
+                    tc::tmem_wait_st();
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        uint32_t v[16];
+                        tc::tmem_ld16u(park + (uint32_t)(16 * j), v);
+                        tc::tmem_wait_ld();
+                        const size_t off = ((size_t)(r.part * 2 * NV + 2 * j) * kRows + row) * 16;
+                        *reinterpret_cast<uint4*>(s.a_hi + off) = make_uint4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<uint4*>(s.a_lo + off) = make_uint4(v[4], v[5], v[6], v[7]);
+                        *reinterpret_cast<uint4*>(s.a_hi + off + kRows * 16) = make_uint4(v[8], v[9], v[10], v[11]);
+                        *reinterpret_cast<uint4*>(s.a_lo + off + kRows * 16) = make_uint4(v[12], v[13], v[14], v[15]);
+                    }
+                } else {
+                    // appearance gather in quad layout (4 lanes x float4 = one 64-byte texel segment per tap, fully
+                    // coalesced): scaled plane*line products go straight into the operand rows as fp16 pairs.  One
+                    // (record, mode) item per quad and step: 128 x 3 items over 96 quads.
                     const int q = r.rt & 3;
                     const float ca = s.sc[gi].x;
                     for (int item = r.rt >> 2; item < 3 * kRows; item += kRowThreads / 4) {
                         const int m = item / 3, mode = item - m * 3;
-                        const float4 pm = s.pos[m];
-                        const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
-                        const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
-                        const int W = f.pw[mode];
-                        const Tap2 t2 = make_tap2(c_a, c_b, W, f.ph[mode]);
-                        const Tap1 t1 = make_tap1(c_v, f.ll[mode]);
-                        const float* plane = f.plane[mode];
-                        const float* line = f.line[mode];
-#pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            const int ch = v * 16 + q * 4;
-                            const float4 pv4 = plane_tap(plane, t2, W, f.comps, ch);
-                            const float4 lv4 = line_tap(line, t1, f.comps, ch);
-                            const int k = mode * f.comps + ch;      // multiple of 4
-                            uint32_t h0, l0, h1, l1;
-                            split2(pv4.x * lv4.x * ca, pv4.y * lv4.y * ca, h0, l0);
-                            split2(pv4.z * lv4.z * ca, pv4.w * lv4.w * ca, h1, l1);
-                            const size_t off = ((size_t)(k >> 3) * kRows + m) * 16 + (size_t)(k & 4) * 2;
-                            *reinterpret_cast<uint2*>(s.a_hi + off) = make_uint2(h0, h1);
-                            *reinterpret_cast<uint2*>(s.a_lo + off) = make_uint2(l0, l1);
-                        }
+                        gather_item<NV>(f, mode, s.pos[m], q, ca, s, m);
                     }
                 }
                 publish(gi);
                 wait_d();   // basis GEMM: features in D columns [0, dim_app)
                 const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
                 const int n_base = A + 3;
-                // staging behind the K rows of the first rgb GEMM (inside the A_hi region): base values x_b
+                // staging behind the K rows of the first rgb GEMM (inside the A_hi region): base values x_b [b][kXbStride]
                 const int k_rows = P.g[gi + 1].k_steps * kStepK;
                 float* xb = reinterpret_cast<float*>(s.a_hi + (size_t)(k_rows >> 3) * kRows * 16);
                 if (r.part == 0) {
                     const float inv = s.sc[gi].y;
                     for (int c0 = 0; c0 < A; c0 += 16) {
                         float v[16];
-                        ld_acc16(r, c0, P.g[gi].n_pad, v);
+                        ld_acc16(d, c0, P.g[gi].n_pad, P.g[gi].n_sets, v);
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
-                            if (c0 + i < A) xb[(size_t)(c0 + i) * kRows + row] = v[i] * inv;
+                            if (c0 + i < A) xb[(size_t)(c0 + i) * kXbStride + row] = v[i] * inv;
                     }
                 } else if (r.part == 1 && ray >= 0) {
-                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kRows + row] = __ldg(P.rays + (int64_t)ray * 8 + 3 + k);
+                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kXbStride + row] = __ldg(P.rays + (int64_t)ray * 8 + 3 + k);
                 } else if (r.part == 1) {
-                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kRows + row] = k == 2 ? 1.0f : 0.0f;
+                    for (int k = 0; k < 3; ++k) xb[(size_t)(A + k) * kXbStride + row] = k == 2 ? 1.0f : 0.0f;
                 }
                 ++gi;
                 tc::fence_before_sync();
@@ -668,12 +819,15 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 // MLP input [feat, dir, sin(feat 2^j), cos(feat 2^j), sin(dir 2^j), cos(dir 2^j)] (tensoRF.py:400-418): one
                 // (record, base value) item per thread and step - SFU sincos (|error| < 4e-7 on these O(1) arguments),
                 // higher frequencies by angle doubling - written as fp16 pairs at the first rgb layer's operand scale.
+                // A warp covers 8 records x 4 consecutive base values, which spreads its 2-byte operand stores over all banks.
                 {
                     const float ca = s.sc[gi].x;
                     const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
-                    for (int item = r.rt; item < n_base * kRows; item += kRowThreads) {
-                        const int b = item / kRows, m = item - b * kRows;     // b is warp-uniform
-                        const float x = xb[(size_t)b * kRows + m];
+                    const int n_items = ((n_base + 3) >> 2) * 4 * kRows;
+                    for (int item = r.rt; item < n_items; item += kRowThreads) {
+                        const int b = ((item >> 9) << 2) | (item & 3), m = (item >> 2) & (kRows - 1);
+                        if (b >= n_base) continue;
+                        const float x = xb[(size_t)b * kXbStride + m];
                         const bool is_feat = b < A;
                         const int nf = is_feat ? pf : pv;
                         const int ks = is_feat ? o_sf + b * pf : o_sd + (b - A) * pv;
@@ -695,7 +849,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 if (threadIdx.x == 64) stamp(P, tl, gi, 7);
                 publish(gi);
                 run_hidden(P.n_rgb);
-                epilogue_final(s, r, 3, P.g[gi].n_pad, s.sc[gi].y);
+                epilogue_final(s, r, d, 3, P.g[gi], s.sc[gi].y);
                 ++gi;
                 if (r.part == 0)
                     for (int c = 0; c < 3; ++c) {
@@ -829,6 +983,8 @@ static bool tc16_add_stack(HeadsParams& P, const clift_mlp& m) {
         g.k_steps = (int)ceil_div(m.dims[l], kStepK);
         g.n_pad = (int)round_up(m.dims[l + 1], 32);
         g.has_bias = 1;
+        g.a_rounds = (l == 0 || !P.stream) ? 1 : (int)ceil_div(P.g[P.n_gemms - 1].n_pad, kRoundCols);
+        g.n_sets = P.use_sets ? std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps + g.has_bias)) : 1;
         if (m.dims[l] > kMaxK || g.n_pad > 256) return false;
         ++P.n_gemms;
     }
@@ -848,7 +1004,7 @@ bool heads_tc16_available(const clift_field* f, int heads) {
         if (!ok(f->rgb) || !f->basis_tc16 || f->dim_appearance > 64 || f->appearance_comps % 16 || 3 * f->appearance_comps > kMaxK)
             return false;
         // the base-value staging of the rgb input lives behind the K rows of the first rgb GEMM, inside the A_hi region
-        if (round_up(f->rgb.dims[0], kStepK) * kRows * 2 + (int64_t)(f->dim_appearance + 3) * kRows * 4 > kABytes) return false;
+        if (round_up(f->rgb.dims[0], kStepK) * kRows * 2 + (int64_t)(f->dim_appearance + 3) * kXbStride * 4 > kABytes) return false;
     }
     return true;
 }
@@ -876,6 +1032,18 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
     P.sem_raw = sem_raw;
     P.ins = ins;
     P.trace = get_tc_trace();
+    {   // development switches; the defaults are the measured best on B200 (profiles/r01_tc16_ab.md):
+        //   CLIFT_TC16_STREAM=1  stream hidden-layer operands out of the epilogues + ping-pong accumulators (slower: the MMA
+        //                        phase is shared-memory-bandwidth bound, the epilogue's operand stores stretch it)
+        //   CLIFT_TC16_PARK=0    gather the appearance products in one burst before the basis GEMM instead of under the MMAs
+        //   CLIFT_TC16_SETS=1    spread small-N GEMMs over several accumulator column sets (no gain: they are issue-bound)
+        const char* e_stream = getenv("CLIFT_TC16_STREAM");
+        const char* e_park = getenv("CLIFT_TC16_PARK");
+        const char* e_sets = getenv("CLIFT_TC16_SETS");
+        P.stream = e_stream && atoi(e_stream) != 0;
+        P.park = !P.stream && !(e_park && atoi(e_park) == 0);
+        P.use_sets = (e_sets && atoi(e_sets) != 0) ? 1 : 0;
+    }
     int heads = (sem_raw ? CLIFT_HEAD_SEMANTIC : 0) | (ins ? CLIFT_HEAD_INSTANCE : 0) | (rgb_raw ? CLIFT_HEAD_RGB : 0);
     bool ok = heads_tc16_available(field, heads);
     if (ok && sem_raw) {
@@ -896,6 +1064,8 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
             g.k_steps = (int)ceil_div(3 * field->appearance_comps, kStepK);
             g.n_pad = (int)round_up(field->dim_appearance, 32);
             g.has_bias = 0;    // appearance_basis_mat has bias=False (tensoRF.py:65)
+            g.a_rounds = 1;
+            g.n_sets = P.use_sets ? std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps)) : 1;
             ++P.n_gemms;
         } else {
             ok = false;
@@ -985,6 +1155,8 @@ extern "C" int32_t clift_debug_tc16_gemm(const float* a, const void* w_tc16, flo
     g.k_steps = (int)ceil_div(k, kStepK);
     g.n_pad = (int)round_up(n_out, 32);
     g.has_bias = has_bias ? 1 : 0;
+    g.a_rounds = 1;
+    g.n_sets = std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps + g.has_bias));
     CLIFT_CUDA(cudaFuncSetAttribute(tc16_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     tc16_gemm_test_kernel<<<1, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, k, g, out);
     CLIFT_AFTER_LAUNCH("tc16_gemm_test_kernel");

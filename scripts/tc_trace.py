@@ -34,7 +34,7 @@ for tile in (1, 2):
     print(f"{'gemm':6s} {'A_written':>10s} {'published':>10s} {'mma_saw_A':>10s} {'mma_issued':>10s} {'D_seen':>10s} | {'build/epi':>9s} {'publish':>8s} {'handoff':>8s} {'issue':>7s} {'mma+wake':>9s} {'w_wait':>7s}")
     prev_d = None
     for g, n in enumerate(names):
-        a_w, pub, saw, iss, d = (int(t[tile, g, i]) - t0 for i in (1, 2, 3, 4, 0))
+        a_w, pub, saw, iss, d = (int(t[tile, g, i]) - t0 for i in (1, 1, 3, 4, 0))   # streamed operands: written == published
         epi = a_w - prev_d if prev_d is not None else 0
         w_wait = int(t[tile, g, 5]) - t0 - saw
         print(f"{n:6s} {a_w:10d} {pub:10d} {saw:10d} {iss:10d} {d:10d} | {epi:9d} {pub - a_w:8d} {saw - pub:8d} {iss - saw:7d} {d - iss:9d} {w_wait:7d}")
