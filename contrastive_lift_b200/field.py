@@ -308,14 +308,23 @@ class TensorVMSplit(nn.Module):
 
     @torch.no_grad()
     def upsample_plane_line(self, plane_coef, line_coef, res_target):
-        # epoch-boundary utility: stock bilinear resize, not on the per-step path
+        # tensoRF.py:190-197: F.interpolate(bilinear, align_corners=True) -> clift_upsample_bilinear
+        lib = L.load()
+
+        def resize(t: torch.Tensor, h2: int, w2: int) -> torch.Tensor:
+            src = t.data.contiguous()
+            if not src.is_cuda:
+                raise L.CliftError("upsample_volume_grid needs the model on a CUDA device (no CPU path)")
+            dst = torch.empty((1, src.shape[1], h2, w2), device=src.device)
+            L.check(lib.clift_upsample_bilinear(L.ptr(src), L.ptr(dst), src.shape[1], src.shape[2], src.shape[3], h2, w2,
+                                                L.stream_ptr(src.device)))
+            return dst
+
         for i in range(3):
             v = VECTOR_MODE[i]
             m0, m1 = MATRIX_MODE[i]
-            plane_coef[i] = nn.Parameter(F.interpolate(plane_coef[i].data, size=(res_target[m1], res_target[m0]),
-                                                       mode="bilinear", align_corners=True))
-            line_coef[i] = nn.Parameter(F.interpolate(line_coef[i].data, size=(res_target[v], 1), mode="bilinear",
-                                                      align_corners=True))
+            plane_coef[i] = nn.Parameter(resize(plane_coef[i], int(res_target[m1]), int(res_target[m0])))
+            line_coef[i] = nn.Parameter(resize(line_coef[i], int(res_target[v]), 1))
         return plane_coef, line_coef
 
     # ---- optimizer groups (tensoRF.py:199-246) --------------------------------------------------

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -62,6 +62,10 @@ class RenderOut(C.Structure):
                 ("points", _vp), ("weights", _vp), ("save_for_backward", C.c_int32)]
 
 
+class AdamTensor(C.Structure):
+    _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_int64)]
+
+
 class CliftError(RuntimeError):
     pass
 
@@ -104,6 +108,12 @@ SIGNATURES = {
     "clift_ema_update": (C.c_int32, [_vp, _vp, C.c_int64, C.c_double, _vp]),
     "clift_contrastive_loss": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp]),
     "clift_tv_loss": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_float, _vp]),
+    "clift_adam_step": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,
+                                    C.c_float, _vp]),
+    "clift_dense_alpha": (C.c_int32, [C.POINTER(RenderCfg), C.POINTER(Field), _vp, _vp, _vp, _vp, _vp]),
+    "clift_alpha_bbox": (C.c_int32, [_vp, C.POINTER(C.c_int32), _vp, _vp, _vp, _fp, _fp, C.c_float, _vp, _vp, _vp, _vp]),
+    "clift_upsample_bilinear": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "clift_assign_centroids": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp]),
 }
 
 

@@ -1,0 +1,82 @@
+"""Fused Adam over a parameter group.
+
+Drop-in for the ``torch.optim.Adam`` the reference builds in ``get_optimizer_and_scheduler``
+(trainer/__init__.py:134-139; groups from tensoRF.py:199-246, betas trainer:98-103): same constructor
+arguments, same ``param_groups`` keys and the same per-parameter state (``step``, ``exp_avg``, ``exp_avg_sq``),
+so ``state_dict()`` / ``load_state_dict()`` and LR schedulers are interchangeable with the stock optimizer
+and checkpoints keep their format.  ``step()`` issues ONE ``clift_adam_step`` launch per param group
+instead of a dozen ATen kernels per tensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List
+
+import torch
+
+from . import lib as L
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, amsgrad=False, *, maximize=False,
+                 grad_scale: float = 1.0):
+        if amsgrad or maximize:
+            raise L.CliftError("FusedAdam: amsgrad / maximize are not built (the reference uses neither)")
+        if betas is None:
+            betas = (0.9, 0.999)
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                        foreach=None, capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        self.grad_scale = float(grad_scale)   # e.g. 1/world_size after a SUM all-reduce of the gradient arena
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.load()
+        for group in self.param_groups:
+            entries: List[L.AdamTensor] = []
+            step = None
+            device = None
+            max_n = 0
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda:
+                    raise L.CliftError("FusedAdam: parameters must live on a CUDA device (no CPU path)")
+                if p.grad.is_sparse or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise L.CliftError("FusedAdam: dense contiguous fp32 parameters only")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                t = int(st["step"].item()) if st["step"].device.type == "cpu" else int(st["step"])
+                if step is None:
+                    step, device = t, p.device
+                elif t != step or p.device != device:      # mixed histories: flush what we have, start a new launch
+                    self._launch(lib, entries, max_n, group, step, device)
+                    entries, max_n, step, device = [], 0, t, p.device
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                e = L.AdamTensor()
+                e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.n = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), \
+                    st["exp_avg_sq"].data_ptr(), p.numel()
+                entries.append(e)
+                max_n = max(max_n, p.numel())
+            self._launch(lib, entries, max_n, group, step, device)
+        return loss
+
+    def _launch(self, lib, entries, max_n, group, step, device):
+        if not entries:
+            return
+        raw = bytes((L.AdamTensor * len(entries))(*entries))
+        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
+        b1, b2 = group["betas"]
+        L.check(lib.clift_adam_step(L.ptr(table), len(entries), int(max_n), float(group["lr"]), float(b1), float(b2),
+                                    float(group["eps"]), float(group["weight_decay"]), int(step), self.grad_scale,
+                                    L.stream_ptr(device)))
+        # the caching allocator may not hand the table's block to another stream-ordered tensor before the launch ran:
+        # same stream, so ordering holds without a record_stream

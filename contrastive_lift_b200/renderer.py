@@ -329,5 +329,75 @@ class TensoRFRenderer(nn.Module):
         L.check(L.load().clift_render_stats(L.ptr(ws), L.ptr(st), L.stream_ptr(ws.device)))
         return tuple(int(v) for v in st.cpu().tolist())
 
+    # ---- renderer:668-729: epoch-boundary dense-alpha sweep, bounding box, factor shrink ------------------
+    def _lattice(self, device):
+        g = self.grid_dim.tolist()
+        return [torch.linspace(0, 1, int(n)).to(device).contiguous() for n in g]     # the reference's own linspace values
+
+    @torch.no_grad()
+    def get_dense_alpha(self, tensorf):
+        """-> (alpha [G0,G1,G2], dense_xyz [G0,G1,G2,3]) as renderer:717-729; alpha comes from clift_dense_alpha."""
+        dev = tensorf.density_line[0].device
+        pk = tensorf.packed(False)
+        cfg = self._cfg(tensorf, 0)
+        sx, sy, sz = self._lattice(dev)
+        g = [int(v) for v in self.grid_dim.tolist()]
+        alpha = torch.empty(g, device=dev)
+        L.check(L.load().clift_dense_alpha(C.byref(cfg), C.byref(pk.field), L.ptr(sx), L.ptr(sy), L.ptr(sz), L.ptr(alpha),
+                                           L.stream_ptr(dev)))
+        samples = torch.stack(torch.meshgrid(sx, sy, sz, indexing="ij"), -1)
+        dense_xyz = self.bbox_aabb[0] * (1 - samples) + self.bbox_aabb[1] * samples
+        return alpha, dense_xyz
+
+    @torch.no_grad()
+    def alpha_bbox(self, tensorf):
+        """(xyz_min, xyz_max, n_valid) of the lattice voxels whose 3x3x3-max-pooled alpha reaches alpha_mask_threshold
+        (renderer:668-681): clift_dense_alpha + clift_alpha_bbox, one 7-number readback."""
+        dev = tensorf.density_line[0].device
+        lib, st = L.load(), L.stream_ptr(dev)
+        pk = tensorf.packed(False)
+        cfg = self._cfg(tensorf, 0)
+        sx, sy, sz = self._lattice(dev)
+        g = [int(v) for v in self.grid_dim.tolist()]
+        alpha = torch.empty(g, device=dev)
+        L.check(lib.clift_dense_alpha(C.byref(cfg), C.byref(pk.field), L.ptr(sx), L.ptr(sy), L.ptr(sz), L.ptr(alpha), st))
+        out = torch.zeros((8,), device=dev)
+        scratch = torch.zeros((8,), dtype=torch.int32, device=dev)
+        aabb = self._host[0]
+        L.check(lib.clift_alpha_bbox(L.ptr(alpha), (C.c_int32 * 3)(*g), L.ptr(sx), L.ptr(sy), L.ptr(sz), (C.c_float * 3)(*aabb[0]),
+                                     (C.c_float * 3)(*aabb[1]), float(self.alpha_mask_threshold), L.ptr(out),
+                                     out.data_ptr() + 24, L.ptr(scratch), st))
+        host = out.cpu()
+        n_valid = int(host[6:7].view(torch.int32).item())
+        return host[0:3].to(dev), host[3:6].to(dev), n_valid
+
+    @torch.no_grad()
     def update_bbox_aabb_and_shrink(self, tensorf, fractional_lenience=1.0):
-        raise L.CliftError("update_bbox_aabb_and_shrink (epoch-boundary dense-alpha sweep, SURVEY 8f rank 3) is not built yet")
+        xyz_min, xyz_max, n_valid = self.alpha_bbox(tensorf)
+        total_voxels = int(self.grid_dim[0] * self.grid_dim[1] * self.grid_dim[2])
+        if n_valid == 0:
+            print(f"[{self.instance_id:02d}] no valid voxels found ...")
+            return
+        # renderer:683-713 on 3-vectors (host-side bookkeeping, same operations in the same order)
+        extent = xyz_max - xyz_min
+        position = (xyz_min + xyz_max) / 2
+        xyz_min_fl = position - (extent * fractional_lenience) / 2
+        xyz_max_fl = position + (extent * fractional_lenience) / 2
+        box_min, box_max = self.bbox_aabb[0], self.bbox_aabb[1]
+        xyz_min = torch.maximum(box_min, xyz_min_fl)
+        xyz_max = torch.minimum(box_max, xyz_max_fl)
+        if self.parent_renderer_ref is not None:
+            box_min, box_max = self.parent_renderer_ref.bbox_aabb[0], self.parent_renderer_ref.bbox_aabb[1]
+            xyz_min = torch.maximum(box_min, xyz_min)
+            xyz_max = torch.minimum(box_max, xyz_max)
+        new_bbox_aabb = torch.stack((xyz_min, xyz_max))
+        if self.verbose:
+            print(f"[{self.instance_id:02d}] bbox: {xyz_min, xyz_max} alpha rest %%%f" % (n_valid / total_voxels * 100))
+        t_l, b_r = (xyz_min - self.bbox_aabb[0]) / self.units, (xyz_max - self.bbox_aabb[0]) / self.units
+        t_l, b_r = torch.round(torch.round(t_l)).long(), torch.round(b_r).long() + 1
+        b_r = torch.stack([b_r, self.grid_dim]).amin(0)
+        new_size = b_r - t_l
+        if new_size[0] > 0 and new_size[1] > 0 and new_size[2] > 0:
+            tensorf.shrink(t_l, b_r)
+            self.bbox_aabb.data = new_bbox_aabb
+            self.update_step_size((int(new_size[0]), int(new_size[1]), int(new_size[2])))

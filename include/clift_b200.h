@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 5
+#define CLIFT_ABI_VERSION 6
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -262,6 +262,41 @@ int32_t clift_contrastive_loss(const float* features, const int64_t* labels, int
 /* ---- TV: model/loss/loss.py:9-26 on a packed plane [H][W][C]; adds scale*dTV/dplane into grad (may be null). */
 int32_t clift_tv_loss(const float* plane_hwc, int32_t comps, int32_t h, int32_t w, float* loss,
                       float* grad_hwc, float grad_scale, void* stream);
+
+/* ---- torch.optim.Adam step (trainer/__init__.py:134-139; trainer:98-103,199,221), fused over a table
+ * of tensors: ONE launch updates every parameter of a param group (amsgrad=False, maximize=False - the reference's use).
+ * `table` is a DEVICE array of n_tensors entries; max_n = the largest entry's n (sizes the grid); step = the 1-based step
+ * count AFTER this update; grad_scale multiplies every gradient first (1.0, or 1/world_size after a SUM all-reduce). */
+typedef struct {
+    float* param;
+    const float* grad;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int64_t n;
+} clift_adam_tensor;
+int32_t clift_adam_step(const clift_adam_tensor* table, int32_t n_tensors, int64_t max_n, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+
+/* ---- epoch-boundary volume operations.
+ * clift_dense_alpha  (renderer:717-729,744-748): alpha[i][j][k] = 1 - exp(-sigma(p_ijk) * cfg->step_size) at the lattice
+ *   p = aabb_min*(1-s) + aabb_max*s, s = the caller's torch.linspace(0,1,grid[c]) per axis (device arrays sx, sy, sz).
+ * clift_alpha_bbox   (renderer:671-681): clamp -> 3x3x3 max-pool (stride 1, padding 1) -> >= threshold; bbox6 = min xyz,
+ *   max xyz of the surviving lattice positions, *count their number (bbox6 = 0 when none).  scratch8: 8 device uint32;
+ *   grid3, aabb_min3, aabb_max3 are HOST arrays (the renderer's grid_dim / bbox_aabb).
+ * clift_upsample_bilinear (tensoRF.py:179-197): F.interpolate(bilinear, align_corners=True) of (1,C,H,W) -> (1,C,H2,W2). */
+int32_t clift_dense_alpha(const clift_render_cfg* cfg, const clift_field* field, const float* sx, const float* sy,
+                          const float* sz, float* alpha, void* stream);
+int32_t clift_alpha_bbox(const float* alpha, const int32_t* grid3, const float* sx, const float* sy, const float* sz,
+                         const float* aabb_min3, const float* aabb_max3, float threshold, float* bbox6, int32_t* count,
+                         uint32_t* scratch8, void* stream);
+int32_t clift_upsample_bilinear(const float* src, float* dst, int32_t channels, int32_t h, int32_t w, int32_t h2, int32_t w2,
+                                void* stream);
+
+/* ---- nearest-centroid assignment of rendered embeddings (inference/render_panopli.py:389-396:
+ * torch.cdist(p=2) + argmin, ties to the lowest index).  features [n][feature_stride] (first `dim` columns used, dim <= 16),
+ * centroids [k][dim]; labels int32 [n]; distances [n] (Euclidean, to the chosen centroid) or null. */
+int32_t clift_assign_centroids(const float* features, int64_t n, int32_t dim, int32_t feature_stride, const float* centroids,
+                               int32_t k, int32_t* labels, float* distances, void* stream);
 
 #ifdef __cplusplus
 }

@@ -270,12 +270,78 @@ def distloss_case():
     print("distloss: ok")
 
 
+def epoch_cases():
+    """the reference's update_bbox_aabb_and_shrink / upsample_volume_grid / get_target_resolution
+    on a ball scene vs the oracle restatement; rank 2: restated Adam vs torch.optim.Adam."""
+    import contextlib
+    import io
+    out = {}
+    for tag, grid, seed, lenience in (("a", (20, 24, 18), 61, 1.0), ("b", (26, 22, 30), 62, 1.2)):
+        params = syn.make_field_params(seed, grid, 4, 3, ball=0.3, ball_gain=3.5)
+        aabb = syn.default_aabb()
+        model = refload.build_model(params, grid, 4, 3)
+        rend = refload.build_renderer(aabb, grid)
+        cfg = orc.RenderConfig(aabb=aabb.clone(), grid_dim=grid).refresh()
+        alpha_ref, xyz_ref = rend.get_dense_alpha(model)
+        alpha, xyz = orc.dense_alpha(params, cfg)
+        assert torch.equal(xyz, xyz_ref) and torch.allclose(alpha, alpha_ref, rtol=1e-6, atol=1e-9), tag
+        lo, hi, n_valid = orc.alpha_bbox(alpha_ref, xyz_ref, rend.alpha_mask_threshold)
+        new_aabb, t_l, b_r = orc.shrink_plan(cfg, lo, hi, lenience)
+        with contextlib.redirect_stdout(io.StringIO()):
+            rend.update_bbox_aabb_and_shrink(model, lenience)
+        assert torch.equal(rend.bbox_aabb, new_aabb), (tag, rend.bbox_aabb, new_aabb)
+        assert rend.grid_dim.tolist() == (b_r - t_l).tolist(), tag
+        shr = orc.shrink_params(params, t_l, b_r)
+        sd = model.state_dict()
+        for k in shr:
+            assert torch.equal(sd[k], shr[k]), (tag, k)
+        n_vox = int(grid[0] * grid[1] * grid[2] * 2.5)
+        res = rend.get_target_resolution(n_vox)
+        assert tuple(res) == orc.target_resolution(new_aabb, n_vox), tag
+        model.upsample_volume_grid(res)
+        ups = orc.upsample_params(shr, res)
+        sd = model.state_dict()
+        for k in ups:
+            assert torch.equal(sd[k], ups[k]), (tag, k)
+        out.update({f"{tag}_grid": np.array(grid), f"{tag}_seed": np.array(seed), f"{tag}_lenience": np.array(lenience),
+                    f"{tag}_alpha": t2n(alpha_ref), f"{tag}_bbox_lo": t2n(lo), f"{tag}_bbox_hi": t2n(hi),
+                    f"{tag}_n_valid": np.array(n_valid), f"{tag}_new_aabb": t2n(new_aabb), f"{tag}_t_l": t2n(t_l),
+                    f"{tag}_b_r": t2n(b_r), f"{tag}_res": np.array(res),
+                    f"{tag}_up_digest": np.array([float(ups[k].double().sum()) for k in sorted(ups) if "plane" in k or "line" in k]),
+                    f"{tag}_up_plane0": t2n(ups["density_plane.0"])})
+    # Adam: restatement vs torch.optim.Adam, 5 steps, two groups (weight decay on / off)
+    gen = torch.Generator().manual_seed(77)
+    ps = [torch.randn(37, 5, generator=gen), torch.randn(130, generator=gen)]
+    ref_p = [torch.nn.Parameter(p.clone()) for p in ps]
+    opt = torch.optim.Adam([{"params": [ref_p[0]], "lr": 0.02, "weight_decay": 1e-2}, {"params": [ref_p[1]], "lr": 0.001}],
+                           betas=(0.9, 0.99))
+    mine = [p.clone() for p in ps]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    grads = []
+    for step in range(1, 6):
+        gs = [torch.randn(p.shape, generator=gen) * (0.5 ** step) for p in ps]
+        grads.append(gs)
+        for rp, g in zip(ref_p, gs):
+            rp.grad = g.clone()
+        opt.step()
+        orc.adam_step(mine[0], gs[0], ms[0], vs[0], step, 0.02, (0.9, 0.99), 1e-8, 1e-2)
+        orc.adam_step(mine[1], gs[1], ms[1], vs[1], step, 0.001, (0.9, 0.99), 1e-8, 0.0)
+    for a, b in zip(mine, ref_p):
+        assert torch.allclose(a, b.data, rtol=1e-6, atol=1e-8), float((a - b.data).abs().max())
+    out.update({"adam_p0": t2n(ps[0]), "adam_p1": t2n(ps[1]), "adam_out0": t2n(ref_p[0].data), "adam_out1": t2n(ref_p[1].data),
+                "adam_g0": np.stack([t2n(g[0]) for g in grads]), "adam_g1": np.stack([t2n(g[1]) for g in grads])})
+    np.savez_compressed(os.path.join(OUT, "epoch.npz"), **out)
+    print("epoch (bbox / shrink / upsample / adam): ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ray_cases()
     distloss_case()
     loss_cases()
+    epoch_cases()
     for i, (name, grid, c, d, s, sm, sf) in enumerate(RENDER_CASES):
         render_case(name, grid, c, d, s, sm, sf, seed=40 + i)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))

@@ -150,3 +150,76 @@ def test_oracle_against_live_reference_random_config():
         got = orc.render_forward(params, cfg, rays)
     for a, b in zip(ref, got):
         assert torch.equal(a, b)
+
+
+# ---- epoch-boundary volume operations, Adam, nearest centroid -------------------------------
+EPOCH_CASES = {"a": 4, "b": 4}
+
+
+def epoch_inputs(fx, tag):
+    grid = tuple(int(v) for v in fx[f"{tag}_grid"])
+    params = syn.make_field_params(int(fx[f"{tag}_seed"]), grid, 4, 3, ball=0.3, ball_gain=3.5)
+    cfg = orc.RenderConfig(aabb=syn.default_aabb(), grid_dim=grid).refresh()
+    return params, cfg
+
+
+@pytest.mark.parametrize("tag", sorted(EPOCH_CASES))
+def test_bbox_shrink_upsample_golden(tag):
+    fx = gu.load("epoch")
+    params, cfg = epoch_inputs(fx, tag)
+    alpha, xyz = orc.dense_alpha(params, cfg)
+    assert torch.allclose(alpha, tn(fx[f"{tag}_alpha"]), rtol=1e-6, atol=1e-9)
+    lo, hi, n_valid = orc.alpha_bbox(tn(fx[f"{tag}_alpha"]), xyz)
+    assert torch.equal(lo, tn(fx[f"{tag}_bbox_lo"])) and torch.equal(hi, tn(fx[f"{tag}_bbox_hi"]))
+    assert n_valid == int(fx[f"{tag}_n_valid"])
+    new_aabb, t_l, b_r = orc.shrink_plan(cfg, lo, hi, float(fx[f"{tag}_lenience"]))
+    assert torch.equal(new_aabb, tn(fx[f"{tag}_new_aabb"]))
+    assert torch.equal(t_l, tn(fx[f"{tag}_t_l"])) and torch.equal(b_r, tn(fx[f"{tag}_b_r"]))
+    res = orc.target_resolution(new_aabb, int(cfg.grid_dim[0] * cfg.grid_dim[1] * cfg.grid_dim[2] * 2.5))
+    assert list(res) == [int(v) for v in fx[f"{tag}_res"]]
+    ups = orc.upsample_params(orc.shrink_params(params, t_l, b_r), res)
+    assert torch.equal(ups["density_plane.0"], tn(fx[f"{tag}_up_plane0"]))
+    digest = np.array([float(ups[k].double().sum()) for k in sorted(ups) if "plane" in k or "line" in k])
+    assert np.allclose(digest, fx[f"{tag}_up_digest"], rtol=1e-12)
+
+
+def test_adam_restatement_golden():
+    fx = gu.load("epoch")
+    for i, (lr, wd) in enumerate(((0.02, 1e-2), (0.001, 0.0))):
+        p = tn(fx[f"adam_p{i}"]).clone()
+        m, v = torch.zeros_like(p), torch.zeros_like(p)
+        for step in range(1, 6):
+            orc.adam_step(p, tn(fx[f"adam_g{i}"][step - 1]), m, v, step, lr, (0.9, 0.99), 1e-8, wd)
+        assert torch.allclose(p, tn(fx[f"adam_out{i}"]), rtol=1e-6, atol=1e-8)
+
+
+def test_fused_adam_state_layout_matches_torch_adam():
+    """The drop-in keeps torch.optim.Adam's param_group keys and per-parameter state names (checkpoint format)."""
+    import contrastive_lift_b200 as cl
+    p = [torch.nn.Parameter(torch.zeros(3))]
+    a = torch.optim.Adam(p, lr=0.1, betas=(0.9, 0.99), weight_decay=0.5)
+    b = cl.FusedAdam(p, lr=0.1, betas=(0.9, 0.99), weight_decay=0.5)
+    assert set(a.param_groups[0]) <= set(b.param_groups[0]) | {"decoupled_weight_decay"}
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize"):
+        assert a.param_groups[0][k] == b.param_groups[0][k], k
+    p[0].grad = torch.ones(3)
+    with pytest.raises(cl.lib.CliftError):      # no CPU path
+        b.step()
+
+
+@pytest.mark.skipif(not refload.available(), reason="/root/reference not present")
+def test_bbox_shrink_live_reference():
+    import contextlib
+    import io
+    grid = (18, 20, 22)
+    params = syn.make_field_params(91, grid, 3, 2, ball=0.4, ball_gain=3.0)
+    model = refload.build_model(params, grid, 3, 2)
+    rend = refload.build_renderer(syn.default_aabb(), grid)
+    cfg = orc.RenderConfig(aabb=syn.default_aabb(), grid_dim=grid).refresh()
+    alpha, xyz = orc.dense_alpha(params, cfg)
+    lo, hi, _ = orc.alpha_bbox(alpha, xyz, rend.alpha_mask_threshold)
+    new_aabb, t_l, b_r = orc.shrink_plan(cfg, lo, hi, 1.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rend.update_bbox_aabb_and_shrink(model)
+    assert torch.equal(rend.bbox_aabb, new_aabb)
+    assert rend.grid_dim.tolist() == (b_r - t_l).tolist()
