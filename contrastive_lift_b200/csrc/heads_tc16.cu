@@ -64,6 +64,7 @@ struct Smem {
     uint64_t* empty;
     uint64_t* bar_a;       // [kMaxRounds] operand rounds ready (every row thread arrives), one phase per GEMM and round
     uint64_t* bar_d;       // accumulator ready (MMA -> row threads)
+    uint64_t* full_peer;   // [kStages] CTA pairs: the peer's half of the weight stage has landed (leader's copy is used)
     uint32_t* tmem_base;
 };
 
@@ -86,13 +87,15 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
     s.empty = s.full + kStages;
     s.bar_a = s.empty + kStages;
     s.bar_d = s.bar_a + kMaxRounds;
-    s.tmem_base = reinterpret_cast<uint32_t*>(s.bar_d + 1);
+    s.full_peer = s.bar_d + 1;
+    s.tmem_base = reinterpret_cast<uint32_t*>(s.full_peer + kStages);
     return s;
 }
 
 // One GEMM of the schedule: D[128 x n_pad] = A[128 x 16*k_steps] * W^T (+ bias row), weights packed by clift_pack_linear_tc16
 struct Gemm {
     const __half* w;    // slabs (after the header)
+    const __half* w_pair;   // the same weights in CTA-pair layout: [rank][k-step][per-CTA slab], see pack_linear_tc16_kernel
     const float* meta;  // header of the packed layer
     int k_steps;        // ceil(K / 16)
     int n_pad;          // multiple of 32, <= 256
@@ -115,18 +118,33 @@ struct PipeState {
 };
 
 __device__ __forceinline__ int ksteps_per_stage(int n_pad) { return n_pad >= 256 ? 1 : 256 / n_pad; }
+// CTA pairs: bytes of one k-step's slab in ONE CTA, and k-steps per 16 KB ring stage
+__device__ __host__ __forceinline__ uint32_t pair_slab_bytes(int n_pad) { return (n_pad > 128 ? 32u : 48u) * (uint32_t)n_pad; }
+__device__ __forceinline__ int pair_ksteps_per_stage(int n_pad) { return min(8, (int)(kStageBytes / pair_slab_bytes(n_pad))); }
 
-// warp 0, one lane: stream the GEMM's weight slabs (64 * n_pad bytes per k-step)
-__device__ __forceinline__ void produce(const Smem& s, const Gemm& g, PipeState& ps) {
-    const int per = ksteps_per_stage(g.n_pad);
-    const uint32_t kstep_bytes = 64u * g.n_pad;
+// warp 0, one lane: stream the GEMM's weight slabs (64 * n_pad bytes per k-step; CTA pairs: this CTA's half)
+template <bool kPair>
+__device__ __forceinline__ void produce(const Smem& s, const Gemm& g, PipeState& ps, uint32_t rank) {
+    const int per = kPair ? pair_ksteps_per_stage(g.n_pad) : ksteps_per_stage(g.n_pad);
+    const uint32_t kstep_bytes = kPair ? pair_slab_bytes(g.n_pad) : 64u * g.n_pad;
     const int steps = g.k_steps + g.has_bias;
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(g.w);
+    const unsigned char* src = kPair ? reinterpret_cast<const unsigned char*>(g.w_pair) + (size_t)rank * steps * kstep_bytes
+                                     : reinterpret_cast<const unsigned char*>(g.w);
     for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
         const uint32_t bytes = (uint32_t)min(per, steps - k0) * kstep_bytes;
         tc::mbar_wait(&s.empty[ps.stage], ps.phase ^ 1);
         tc::mbar_arrive_expect_tx(&s.full[ps.stage], bytes);
         tc::bulk_load(s.w + (size_t)ps.stage * kStageBytes, src + (size_t)k0 * kstep_bytes, bytes, &s.full[ps.stage]);
+    }
+}
+
+// CTA pairs, peer CTA's warp 1, one lane: tell the leader's MMA thread when this CTA's half of a weight stage has landed
+__device__ __forceinline__ void relay(const Smem& s, const Gemm& g, PipeState& ps, uint32_t leader_full_peer) {
+    const int per = pair_ksteps_per_stage(g.n_pad);
+    const int steps = g.k_steps + g.has_bias;
+    for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
+        tc::mbar_wait(&s.full[ps.stage], ps.phase);
+        tc::mbar_arrive_cluster(leader_full_peer + 8u * (uint32_t)ps.stage);
     }
 }
 
@@ -138,34 +156,50 @@ __device__ __forceinline__ void produce(const Smem& s, const Gemm& g, PipeState&
 // The issuing thread runs ~1 dependent instruction per 4-6 cycles, so the per-k-step body must stay a few dozen instructions
 // (budget 384 cycles per N=256 k-step): descriptors are running values, GEMM fields are copied to registers, and the operand
 // round logic exists only in the kStream instantiation.
-template <bool kStream>
+// CTA pairs (kPair): M = 256 over both CTAs, each CTA's shared memory holds half of B's rows at the descriptor address:
+//   n_pad > 128 : per-CTA slab = [hi | lo][2 k-chunks][n_pad/2][8]; the same three MMAs with N = n_pad split over the pair
+//   n_pad <= 128: per-CTA slab = [Y: 2 k-chunks x n_pad rows][X: 2 k-chunks x n_pad/2 rows]; Y = W_hi in the leader and W_lo
+//                 in the peer, so A_hi*[W_hi ; W_lo] (N = 2 n_pad) is one MMA; X = the CTA's half of W_hi for A_lo*W_hi
+template <bool kStream, bool kPair>
 __device__ __forceinline__ void issue(const Smem& s, const Gemm& gm, PipeState& ps, uint32_t d_tmem, uint32_t& a_parity,
                                       long long* trace = nullptr) {
     const int n_pad = gm.n_pad, k_steps = gm.k_steps, n_sets = gm.n_sets, a_rounds = gm.a_rounds;
     const int steps = k_steps + gm.has_bias;
-    const uint32_t idesc = tc::make_idesc_f16(kRows, n_pad);
-    const uint32_t rows16 = (uint32_t)n_pad;
+    const int m_rows = kPair ? 2 * kRows : kRows;
+    const uint32_t idesc = tc::make_idesc_f16(m_rows, n_pad);
     const bool stacked = n_pad <= 128;
-    const uint32_t idesc_ss = stacked ? tc::make_idesc_f16(kRows, 2 * n_pad) : idesc;
-    const int per = ksteps_per_stage(n_pad);
-    const uint32_t kstep16 = 64u * n_pad >> 4;
+    const uint32_t idesc_ss = stacked ? tc::make_idesc_f16(m_rows, 2 * n_pad) : idesc;
+    const int per = kPair ? pair_ksteps_per_stage(n_pad) : ksteps_per_stage(n_pad);
+    const uint32_t kstep16 = (kPair ? pair_slab_bytes(n_pad) : 64u * n_pad) >> 4;
     constexpr uint32_t kStage16 = kStageBytes >> 4;
     constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);     // SBO 128 B, descriptor version 1
     constexpr uint32_t kAStep = 2u * (kRows * 16u >> 4);       // two k-chunks per MMA
     const uint32_t a_lbo = (kRows * 16u >> 4) << 16;
-    const uint32_t b_lbo = (stacked ? 2u * rows16 : rows16) << 16;
+    // first B operand (W_hi, or the stacked [W_hi ; W_lo]): rows per k-chunk in this CTA's shared memory
+    const uint32_t rows1 = kPair ? (stacked ? (uint32_t)n_pad : (uint32_t)n_pad / 2) : (stacked ? 2u * n_pad : (uint32_t)n_pad);
+    // second B operand: W_lo (not stacked) / the W_hi copy for A_lo*W_hi (stacked): offset from the first, rows per k-chunk
+    const uint32_t off2 = 2u * rows1;
+    const uint32_t rows2 = kPair ? (uint32_t)n_pad / 2 : rows1;
     uint32_t ah = (tc::smem_addr(s.a_hi) >> 4) | a_lbo;
     uint32_t al = (tc::smem_addr(s.a_lo) >> 4) | a_lbo;
     const uint32_t ones_lo = (tc::smem_addr(s.ones) >> 4) | a_lbo;
-    const uint32_t w_lo0 = (tc::smem_addr(s.w) >> 4) | b_lbo;
-    const uint32_t lo_off = stacked ? 0u : 2u * rows16;
+    const uint32_t w_base = tc::smem_addr(s.w) >> 4;
     const uint32_t set_stride = n_sets > 1 ? 2u * n_pad : 0u;
     auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+    auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
+        if (kPair)
+            tc::mma_ss_f16_pair(d, a, b, id, acc);
+        else
+            tc::mma_ss_f16(d, a, b, id, acc);
+    };
 
     int rounds_seen = 0;
     auto need_round = [&](int r) {     // operand rounds 0..r written and published by every row thread
         while (rounds_seen <= r) {
-            tc::mbar_wait(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
+            if (kPair)
+                tc::mbar_wait_cluster(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
+            else
+                tc::mbar_wait(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
             a_parity ^= 1u << rounds_seen;
             ++rounds_seen;
             tc::fence_after_sync();
@@ -177,29 +211,40 @@ __device__ __forceinline__ void issue(const Smem& s, const Gemm& gm, PipeState& 
     uint32_t set_off = 0u;
     for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
         tc::mbar_wait(&s.full[ps.stage], ps.phase);
+        if (kPair) tc::mbar_wait_cluster(&s.full_peer[ps.stage], ps.phase);
         tc::fence_after_sync();
         if (trace && k0 == 0) trace[5] = clock64();
-        uint32_t w_lo = w_lo0 + (uint32_t)ps.stage * kStage16;
+        uint32_t w_lo = w_base + (uint32_t)ps.stage * kStage16;
         const int n_here = min(per, steps - k0);
         for (int j = 0; j < n_here; ++j, ++kk, w_lo += kstep16, ah += kAStep, al += kAStep) {
             if (kStream) need_round(min(kk * kStepK / kRoundCols, a_rounds - 1));
             const bool bias_step = kk >= k_steps;
             const uint64_t a_desc = desc(bias_step ? ones_lo : ah);
-            const uint64_t bh = desc(w_lo);
+            const uint64_t b1 = desc(w_lo | (rows1 << 16));
             const uint32_t dt = d_tmem + set_off;
-            tc::mma_ss_f16(dt, a_desc, bh, idesc_ss, kk >= n_sets ? 1u : 0u);   // the first MMA into a column set overwrites
-            if (!stacked) tc::mma_ss_f16(dt, a_desc, desc(w_lo + lo_off), idesc, 1u);
-            if (!bias_step) tc::mma_ss_f16(dt, desc(al), bh, idesc, 1u);
+            mma(dt, a_desc, b1, idesc_ss, kk >= n_sets ? 1u : 0u);   // the first MMA into a column set overwrites
+            if (stacked) {
+                if (!bias_step) mma(dt, desc(al), kPair ? desc((w_lo + off2) | (rows2 << 16)) : desc(w_lo | (rows1 << 16)), idesc, 1u);
+            } else {
+                mma(dt, a_desc, desc((w_lo + off2) | (rows2 << 16)), idesc, 1u);
+                if (!bias_step) mma(dt, desc(al), b1, idesc, 1u);
+            }
             set_off += set_stride;
             if (++set == n_sets) {
                 set = 0;
                 set_off = 0u;
             }
         }
-        tc::mma_commit(&s.empty[ps.stage]);
+        if (kPair)
+            tc::mma_commit_pair(&s.empty[ps.stage], 3);
+        else
+            tc::mma_commit(&s.empty[ps.stage]);
     }
     if (kStream) need_round(a_rounds - 1);   // keep the round barriers' parities in step when K ends before the last round
-    tc::mma_commit(s.bar_d);
+    if (kPair)
+        tc::mma_commit_pair(s.bar_d, 3);
+    else
+        tc::mma_commit(s.bar_d);
     if (trace) trace[4] = clock64();
 }
 
@@ -236,11 +281,24 @@ __device__ __forceinline__ void put1(const Smem& s, int row, int k, float x) {
     *reinterpret_cast<__half*>(s.a_lo + off) = l;
 }
 
+// two adjacent K values (k even) of one record
+__device__ __forceinline__ void put2(const Smem& s, int row, int k, float x, float y) {
+    uint32_t hi, lo;
+    split2(x, y, hi, lo);
+    const size_t off = ((size_t)(k >> 3) * kRows + row) * 16 + (size_t)(k & 7) * 2;
+    *reinterpret_cast<uint32_t*>(s.a_hi + off) = hi;
+    *reinterpret_cast<uint32_t*>(s.a_lo + off) = lo;
+}
+
 // every row thread: the operand rows it wrote for round `r` of the next GEMM are visible to the tensor core
-__device__ __forceinline__ void arrive_round(const Smem& s, int r) {
+// (CTA pairs: the barrier lives in the leader CTA; `leader_bar_a` is its shared::cluster address, 0 = single-CTA mode)
+__device__ __forceinline__ void arrive_round(const Smem& s, int r, uint32_t leader_bar_a = 0u) {
     tc::fence_proxy_async_smem();
     tc::fence_before_sync();
-    tc::mbar_arrive(&s.bar_a[r]);
+    if (leader_bar_a)
+        tc::mbar_arrive_cluster(leader_bar_a + 8u * (uint32_t)r);
+    else
+        tc::mbar_arrive(&s.bar_a[r]);
 }
 
 struct RowId {
@@ -276,6 +334,7 @@ __device__ __forceinline__ void ld_acc16(uint32_t d, int c0, int n_pad, int n_se
     }
 }
 
+template <bool kPair = false>
 __device__ __forceinline__ void tc16_init(const Smem& s) {
     for (int i = threadIdx.x; i < kOnesBytes / 2; i += kThreads)
         reinterpret_cast<__half*>(s.ones)[i] = __float2half_rn((i < kRows * 8 && (i & 7) == 0) ? 1.0f : 0.0f);
@@ -285,13 +344,20 @@ __device__ __forceinline__ void tc16_init(const Smem& s) {
             tc::mbar_init(&s.full[i], 1);
             tc::mbar_init(&s.empty[i], 1);
         }
-        for (int i = 0; i < kMaxRounds; ++i) tc::mbar_init(&s.bar_a[i], kRowThreads);
+        for (int i = 0; i < kMaxRounds; ++i) tc::mbar_init(&s.bar_a[i], kPair ? 2 * kRowThreads : kRowThreads);
+        for (int i = 0; i < kStages; ++i) tc::mbar_init(&s.full_peer[i], 1);
         tc::mbar_init(s.bar_d, 1);
         tc::fence_barrier_init();
     }
-    if ((threadIdx.x >> 5) == 1) tc::tmem_alloc(s.tmem_base, kTmemCols);
+    if ((threadIdx.x >> 5) == 1) {
+        if (kPair)
+            tc::tmem_alloc_pair(s.tmem_base, kTmemCols);
+        else
+            tc::tmem_alloc(s.tmem_base, kTmemCols);
+    }
     tc::fence_before_sync();
     __syncthreads();
+    if (kPair) tc::cluster_sync();     // the peer's barriers exist before anyone arrives on them remotely
     tc::fence_after_sync();
 }
 
@@ -307,13 +373,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc16_gemm_test_kernel(const float
     if (warp == 0) {
         if (tc::elect_one()) {
             PipeState ps;
-            produce(s, g, ps);
+            produce<false>(s, g, ps, 0);
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             PipeState ps;
             uint32_t a_parity = 0;
-            issue<false>(s, g, ps, tmem, a_parity);
+            issue<false, false>(s, g, ps, tmem, a_parity);
         }
     } else {
         const RowId r = make_row_id(tmem);
@@ -359,6 +425,7 @@ struct HeadsParams {
     float* ins;
     long long* trace;
     int stream;                 // 1: hidden-layer operands stream out of the epilogues in rounds, accumulators ping-pong
+    int pair;                   // 1: CTA pairs (clusters of 2, cta_group::2 MMAs with M = 256): each SM stages half of every weight slab
     int park;                   // 1: the appearance gather runs row-mapped inside the MMA phases of the xyz stacks and parks
                                 //    its fp16 pairs in spare tensor-memory columns (requires !stream: one accumulator buffer)
 };
@@ -379,7 +446,8 @@ __device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0
 // Streams the next layer's operand: round j = this thread's chunk of accumulator columns [48 j, 48 j + 48), i.e. K rows
 // (3 k-steps) of the next GEMM, which the MMA thread issues as soon as all 384 row threads have arrived on bar_a[j] - the
 // next layer's MMAs (into the other accumulator buffer) overlap the rest of this epilogue.
-__device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, uint32_t d, const Gemm& g, float e, bool stream) {
+__device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, uint32_t d, const Gemm& g, float e, bool stream,
+                                                uint32_t leader_bar_a) {
     const int n_pad = g.n_pad;
     const int rounds = (n_pad + kRoundCols - 1) / kRoundCols;
     const int c_begin = r.part * 16;
@@ -390,9 +458,9 @@ __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, u
                 ld_acc16(d, c0, n_pad, g.n_sets, v);
                 relu_put16(s, r, c0, v, e);
             }
-            if (stream) arrive_round(s, j);
+            if (stream) arrive_round(s, j, leader_bar_a);
         }
-        if (!stream) arrive_round(s, 0);
+        if (!stream) arrive_round(s, 0, leader_bar_a);
         return;
     }
     for (int j = 0, c0 = c_begin; j < rounds; ++j, c0 += kRoundCols) {
@@ -402,9 +470,9 @@ __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, u
             tc::tmem_wait_ld();
             relu_put16(s, r, c0, v, e);
         }
-        if (stream) arrive_round(s, j);
+        if (stream) arrive_round(s, j, leader_bar_a);
     }
-    if (!stream) arrive_round(s, 0);
+    if (!stream) arrive_round(s, 0, leader_bar_a);
 }
 
 // final-layer epilogue (part 0 threads): D * inv -> scratch[c][row] for c < n_out (scratch = A_hi region as floats)
@@ -568,6 +636,13 @@ __device__ __forceinline__ void gather_item(const FactorParams& f, int mode, con
     }
 }
 
+// one 32-byte sector, not allocated in L1 (the L1 array is the shared-memory array the MMAs are reading their operands from)
+__device__ __forceinline__ void ldg8_na(const float* p, float4& lo, float4& hi) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+                 : "l"(p));
+}
+
 // Row-mapped gather slice: channels [8 slice, 8 slice + 8) of mode `mode` at this thread's own record, 12 16-byte loads in
 // flight (one 32-byte sector per tap), products scaled and split to fp16 pairs, parked in 8 tensor-memory columns of the
 // record's lane as [4 words hi | 4 words lo] - the image of one 16-byte A_hi chunk and one A_lo chunk.
@@ -588,15 +663,12 @@ __device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, co
     const float* l0 = f.line[mode] + (int64_t)z0 * C + ch;
     const float* l1 = f.line[mode] + (int64_t)z1 * C + ch;
     float4 a[2], b[2], c[2], d[2], u[2], w[2];
-#pragma unroll
-    for (int v = 0; v < 2; ++v) {
-        a[v] = ldg4(p00 + v * 4);
-        b[v] = ldg4(p10 + v * 4);
-        c[v] = ldg4(p01 + v * 4);
-        d[v] = ldg4(p11 + v * 4);
-        u[v] = ldg4(l0 + v * 4);
-        w[v] = ldg4(l1 + v * 4);
-    }
+    ldg8_na(p00, a[0], a[1]);
+    ldg8_na(p10, b[0], b[1]);
+    ldg8_na(p01, c[0], c[1]);
+    ldg8_na(p11, d[0], d[1]);
+    ldg8_na(l0, u[0], u[1]);
+    ldg8_na(l1, w[0], w[1]);
     uint32_t words[8];
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
@@ -613,36 +685,51 @@ __device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, co
     tc::tmem_st8u(park + (uint32_t)(slice * 8), words);
 }
 
-template <int NV>
+// kPair: launched as clusters of two CTAs; the pair works on two tiles at once with M = 256 MMAs issued by the leader
+// (cluster rank 0) - see issue().  Every CTA of a pair runs the same number of iterations (a CTA whose tile index is past the
+// end carries an empty tile through the same schedule).
+template <int NV, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const __grid_constant__ HeadsParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem s = carve_smem(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < P.n_gemms) s.sc[threadIdx.x] = make_float2(P.g[threadIdx.x].meta[0], P.g[threadIdx.x].meta[2]);
-    tc16_init(s);
+    tc16_init<kPair>(s);
     const uint32_t tmem = *s.tmem_base;
     const long long n_act = min((long long)P.stats[0], P.cap);
     const int n_tiles = (int)((n_act + kRows - 1) / kRows);    // < 2^24: one call handles n_rays * n_samples < 2^31
+    const uint32_t rank = kPair ? tc::cluster_ctarank() : 0u;
+    // tiles of this CTA: tile_first, tile_first + tile_step, ... while the PAIR's (even) tile index is in range
+    const int tile_step = kPair ? (int)gridDim.x : (int)gridDim.x;
+    const int tile_first = kPair ? (int)(blockIdx.x & ~1u) : (int)blockIdx.x;     // iteration key (pairs: the leader's tile)
+    const int tile_mine = kPair ? (int)rank : 0;                                   // + this CTA's offset inside the pair
+    const uint32_t leader_bar_a = kPair ? tc::map_to_rank(&s.bar_a[0], 0) : 0u;
 
     if (warp == 0) {
         if (tc::elect_one()) {
             PipeState ps;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-                for (int gi = 0; gi < P.n_gemms; ++gi) produce(s, P.g[gi], ps);
+            for (int tile = tile_first; tile < n_tiles; tile += tile_step)
+                for (int gi = 0; gi < P.n_gemms; ++gi) produce<kPair>(s, P.g[gi], ps, rank);
         }
     } else if (warp == 1) {
         if (tc::elect_one()) {
             PipeState ps;
-            uint32_t count = 0, a_parity = 0;
-            int tl = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl)
-                for (int gi = 0; gi < P.n_gemms; ++gi, ++count) {
-                    long long* tr = P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kMaxGemms + gi) * 10 : nullptr;
-                    if (P.stream)
-                        issue<true>(s, P.g[gi], ps, tmem + ((count & 1u) ? 256u : 0u), a_parity, tr);
-                    else
-                        issue<false>(s, P.g[gi], ps, tmem, a_parity, tr);
-                }
+            if (kPair && rank != 0) {
+                const uint32_t leader_full_peer = tc::map_to_rank(&s.full_peer[0], 0);
+                for (int tile = tile_first; tile < n_tiles; tile += tile_step)
+                    for (int gi = 0; gi < P.n_gemms; ++gi) relay(s, P.g[gi], ps, leader_full_peer);
+            } else {
+                uint32_t count = 0, a_parity = 0;
+                int tl = 0;
+                for (int tile = tile_first; tile < n_tiles; tile += tile_step, ++tl)
+                    for (int gi = 0; gi < P.n_gemms; ++gi, ++count) {
+                        long long* tr = P.trace && blockIdx.x == 0 && tl < 4 ? P.trace + (tl * kMaxGemms + gi) * 10 : nullptr;
+                        if (P.stream)
+                            issue<true, kPair>(s, P.g[gi], ps, tmem + ((count & 1u) ? 256u : 0u), a_parity, tr);
+                        else
+                            issue<false, kPair>(s, P.g[gi], ps, tmem, a_parity, tr);
+                    }
+            }
         }
     } else {
         const RowId r = make_row_id(tmem);
@@ -661,7 +748,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         };
         auto publish = [&](int g_next) {                       // whole operand written by this thread: round 0
             if (threadIdx.x == 64) stamp(P, tl, g_next, 1);
-            arrive_round(s, 0);
+            arrive_round(s, 0, leader_bar_a);
         };
         // one MLP stack whose first operand is already published: hidden epilogues stream the next layer's operand in place
         // parked appearance gather: this thread's record, mode = its part; one 8-channel slice per long MMA phase
@@ -676,7 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         auto run_hidden = [&](int n_layers) {
             for (int l = 0; l + 1 < n_layers; ++l, ++gi) {
                 wait_d();
-                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0);
+                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a);
                 if (threadIdx.x == 64) stamp(P, tl, gi + 1, 1);
                 if (park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice();   // hides under that GEMM
             }
@@ -693,13 +780,14 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 ray_next = P.rec_ray[rec];
             }
         };
-        fetch(blockIdx.x);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        fetch(tile_first + tile_mine);
+        for (int tile_key = tile_first; tile_key < n_tiles; tile_key += tile_step) {
             ++tl;
-            const int nv = (int)min((long long)kRows, n_act - (long long)tile * kRows);
+            const int tile = tile_key + tile_mine;
+            const int nv = (int)max(0ll, min((long long)kRows, n_act - (long long)tile * kRows));
             p = p_next;
             const int ray = ray_next;
-            fetch(tile + gridDim.x);
+            fetch(tile + tile_step);
             park_next = (P.park && P.n_rgb > 0) ? 0 : 2 * NV;
             if (r.part == 0) {
                 s.ray[row] = ray;
@@ -835,6 +923,11 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                         put1(s, m, b, x * ca);
                         float sv, cv;
                         __sincosf(x, &sv, &cv);
+                        if (nf == 2 && !((ks | kc) & 1)) {      // the shipped pe_feat = pe_view = 2: (f, 2f) pairs are aligned
+                            put2(s, m, ks, sv * ca, 2.0f * sv * cv * ca);
+                            put2(s, m, kc, cv * ca, (1.0f - 2.0f * sv * sv) * ca);
+                            continue;
+                        }
                         for (int j = 0; j < nf; ++j) {
                             put1(s, m, ks + j, sv * ca);
                             put1(s, m, kc + j, cv * ca);
@@ -862,7 +955,13 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         tc::fence_before_sync();
     }
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, kTmemCols);
+    if (kPair) tc::cluster_sync();     // nobody leaves while the peer may still signal its barriers / read its operands
+    if (warp == 1) {
+        if (kPair)
+            tc::tmem_dealloc_pair(tmem, kTmemCols);
+        else
+            tc::tmem_dealloc(tmem, kTmemCols);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -923,9 +1022,14 @@ __global__ void __launch_bounds__(256) tc16_plan_kernel(const float* __restrict_
 }
 
 // W [out][in] * cw (+ bias * ca * cw in k row 0 of one more slab) -> per k-step slab of fp16 (hi, lo) pairs:
-// [hi|lo][2 k-chunks][n_pad][8] for n_pad > 128 else [2 k-chunks][hi|lo][n_pad][8]; zero padded
+// [hi|lo][2 k-chunks][n_pad][8] for n_pad > 128 else [2 k-chunks][hi|lo][n_pad][8]; zero padded.
+// `pair` (the CTA-pair copy, [rank][k-step][per-CTA slab], h = n_pad / 2):
+//   n_pad > 128 : CTA r holds rows [r h, r h + h): [hi | lo][2 k-chunks][h][8]
+//   n_pad <= 128: [Y: 2 k-chunks x n_pad rows][X: 2 k-chunks x h rows]; Y = hi (rank 0) / lo (rank 1) of all rows,
+//                 X = hi of rows [r h, r h + h)
 __global__ void pack_linear_tc16_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out, int n_in,
-                                        const float* __restrict__ header, __half* __restrict__ dst, int n_pad, int slabs) {
+                                        const float* __restrict__ header, __half* __restrict__ dst, __half* __restrict__ pair,
+                                        int n_pad, int slabs) {
     const int64_t total = (int64_t)slabs * kStepK * n_pad;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -946,6 +1050,23 @@ __global__ void pack_linear_tc16_kernel(const float* __restrict__ w, const float
         const size_t off = ((size_t)kc * n_pad + n) * 8 + ki;
         base[off] = hi;
         base[(size_t)kStepK * n_pad + off] = lo;
+    }
+    // CTA-pair copy
+    const int h = n_pad / 2;
+    const size_t pb = pair_slab_bytes(n_pad) / 2;                       // halves per k-step slab of one CTA
+    __half* r0 = pair + (size_t)slab * pb;
+    __half* r1 = pair + ((size_t)slabs + slab) * pb;
+    if (n_pad > 128) {
+        __half* b = (n < h ? r0 : r1);
+        const size_t off = ((size_t)kc * h + (n % h)) * 8 + ki;
+        b[off] = hi;
+        b[(size_t)2 * h * 8 + off] = lo;
+    } else {
+        const size_t off_y = ((size_t)kc * n_pad + n) * 8 + ki;
+        r0[off_y] = hi;
+        r1[off_y] = lo;
+        __half* b = (n < h ? r0 : r1) + (size_t)2 * n_pad * 8;
+        b[((size_t)kc * h + (n % h)) * 8 + ki] = hi;
     }
 }
 
@@ -983,6 +1104,7 @@ static bool tc16_add_stack(HeadsParams& P, const clift_mlp& m) {
         g.k_steps = (int)ceil_div(m.dims[l], kStepK);
         g.n_pad = (int)round_up(m.dims[l + 1], 32);
         g.has_bias = 1;
+        g.w_pair = g.w + (size_t)(g.k_steps + 1) * 2 * kStepK * g.n_pad;
         g.a_rounds = (l == 0 || !P.stream) ? 1 : (int)ceil_div(P.g[P.n_gemms - 1].n_pad, kRoundCols);
         g.n_sets = P.use_sets ? std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps + g.has_bias)) : 1;
         if (m.dims[l] > kMaxK || g.n_pad > 256) return false;
@@ -1040,6 +1162,8 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
         const char* e_stream = getenv("CLIFT_TC16_STREAM");
         const char* e_park = getenv("CLIFT_TC16_PARK");
         const char* e_sets = getenv("CLIFT_TC16_SETS");
+        const char* e_pair = getenv("CLIFT_TC16_PAIR");
+        P.pair = e_pair && atoi(e_pair) != 0;
         P.stream = e_stream && atoi(e_stream) != 0;
         P.park = !P.stream && !(e_park && atoi(e_park) == 0);
         P.use_sets = (e_sets && atoi(e_sets) != 0) ? 1 : 0;
@@ -1064,6 +1188,7 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
             g.k_steps = (int)ceil_div(3 * field->appearance_comps, kStepK);
             g.n_pad = (int)round_up(field->dim_appearance, 32);
             g.has_bias = 0;    // appearance_basis_mat has bias=False (tensoRF.py:65)
+            g.w_pair = g.w + (size_t)g.k_steps * 2 * kStepK * g.n_pad;
             g.a_rounds = 1;
             g.n_sets = P.use_sets ? std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps)) : 1;
             ++P.n_gemms;
@@ -1077,12 +1202,27 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
         return CLIFT_ERR_UNSUPPORTED;
     }
     if (P.n_gemms == 0 || n_rays <= 0) return CLIFT_OK;
-    const int grid = sm_count();
+    const int grid = P.pair ? (sm_count() & ~1) : sm_count();
+    auto launch = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return e;
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)grid);
+        lc.blockDim = dim3(kThreads);
+        lc.dynamicSmemBytes = kSmemBytes;
+        lc.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = P.pair ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        return cudaLaunchKernelEx(&lc, kernel, P);
+    };
 #define CLIFT_TC16_CASE(NV)                                                                                            \
     case NV: {                                                                                                         \
-        CLIFT_CUDA(cudaFuncSetAttribute(heads_tc16_forward_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                        (int)kSmemBytes));                                                             \
-        heads_tc16_forward_kernel<NV><<<grid, kThreads, kSmemBytes, stream>>>(P);                                      \
+        CLIFT_CUDA(P.pair ? launch(heads_tc16_forward_kernel<NV, true>) : launch(heads_tc16_forward_kernel<NV, false>)); \
         break;                                                                                                         \
     }
     switch (P.app.comps / 16) {
@@ -1106,7 +1246,7 @@ using namespace clift;
 extern "C" int64_t clift_tc16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias) {
     if (n_out <= 0 || n_in <= 0 || n_out > 256 || n_in > kMaxK) return CLIFT_ERR_UNSUPPORTED;
     const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kStepK) + (has_bias ? 1 : 0);
-    return (int64_t)kHeaderFloats * 4 + (int64_t)slabs * 2 * kStepK * n_pad * 2;
+    return (int64_t)kHeaderFloats * 4 + (int64_t)slabs * 2 * kStepK * n_pad * 2 + (int64_t)2 * slabs * pair_slab_bytes(n_pad);
 }
 
 extern "C" int32_t clift_pack_linear_tc16(const float* w, const float* bias, void* dst, int32_t n_out, int32_t n_in,
@@ -1120,8 +1260,9 @@ extern "C" int32_t clift_pack_linear_tc16(const float* w, const float* bias, voi
     tc16_plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, bias, n_out, n_in, in_bound, in_bound_floor, header);
     CLIFT_AFTER_LAUNCH("tc16_plan_kernel");
     const int64_t total = (int64_t)slabs * kStepK * n_pad;
+    __half* single = reinterpret_cast<__half*>(header + kHeaderFloats);
     pack_linear_tc16_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        w, bias, n_out, n_in, header, reinterpret_cast<__half*>(header + kHeaderFloats), n_pad, slabs);
+        w, bias, n_out, n_in, header, single, single + (size_t)slabs * 2 * kStepK * n_pad, n_pad, slabs);
     CLIFT_AFTER_LAUNCH("pack_linear_tc16_kernel");
     return CLIFT_OK;
 }
@@ -1155,6 +1296,7 @@ extern "C" int32_t clift_debug_tc16_gemm(const float* a, const void* w_tc16, flo
     g.k_steps = (int)ceil_div(k, kStepK);
     g.n_pad = (int)round_up(n_out, 32);
     g.has_bias = has_bias ? 1 : 0;
+    g.w_pair = nullptr;
     g.a_rounds = 1;
     g.n_sets = std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps + g.has_bias));
     CLIFT_CUDA(cudaFuncSetAttribute(tc16_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));

@@ -78,8 +78,9 @@ def main():
     batch = (rays, torch.rand(B, 3, generator=g).to(dev), torch.softmax(torch.randn(B, C, generator=g), -1).to(dev),
              torch.rand(B, generator=g).to(dev), ins_rays, torch.randint(1, 8, (N_INS,), generator=g).to(dev),
              torch.rand(N_INS, generator=g).to(dev))
-    opt_main = torch.optim.Adam(model.get_optimizable_parameters(0.02, 0.001, 1e-8), betas=(0.9, 0.99))
-    opt_ins = torch.optim.Adam(model.get_optimizable_instance_parameters(0.02, 0.001, using_DINO=True), betas=(0.9, 0.999))
+    adam = torch.optim.Adam if "--torch-adam" in sys.argv else cl.FusedAdam      # one launch per param group
+    opt_main = adam(model.get_optimizable_parameters(0.02, 0.001, 1e-8), betas=(0.9, 0.99))
+    opt_ins = adam(model.get_optimizable_instance_parameters(0.02, 0.001, using_DINO=True), betas=(0.9, 0.999))
     torch.manual_seed(123)
     for _ in range(3):
         gpu_step(model, rend, opt_main, opt_ins, batch)
@@ -104,7 +105,7 @@ def main():
     print(json.dumps({"workload": "training step: 4096-ray main pass (2 chunks, MSE+TV+dist+CE, Adam) + 1024-ray instance pass "
                                   "(slow-fast loss, EMA, Adam), S=%d, G=128^3, C=21, d=3+3" % rend.n_samples,
                       "ms_per_step": ms, "train_Mrays_per_s": (B + N_INS) / ms / 1e3, "clift_launches_per_step": launches,
-                      "loss_main": float(losses[0]), "loss_slow_fast": float(losses[1]),
+                      "optimizer": adam.__name__, "loss_main": float(losses[0]), "loss_slow_fast": float(losses[1]),
                       "cpu_oracle_s_per_step": cpu_s, "cpu_cores": os.cpu_count(), "speedup_vs_cpu": cpu_s * 1e3 / ms,
                       "gpu_mem_peak_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
 
