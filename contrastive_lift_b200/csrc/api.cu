@@ -62,6 +62,27 @@ static int check_mlp(const clift_mlp& m, const char* name, int expect_out) {
     return CLIFT_OK;
 }
 
+static int check_grid_head(const clift_grid_head& g, const char* name) {
+    if (g.comps % 16 != 0 || g.comps < 16 || g.comps > 64) {
+        set_error("%s grid: comps %d not in {16,32,48,64}", name, g.comps);
+        return CLIFT_ERR_UNSUPPORTED;
+    }
+    if (g.dim < 1 || g.dim > 64) {
+        set_error("%s grid: basis width %d outside [1,64]", name, g.dim);
+        return CLIFT_ERR_UNSUPPORTED;
+    }
+    for (int m = 0; m < 3; ++m)
+        if (!g.plane[m] || !g.line[m]) {
+            set_error("%s grid: null factor pointer", name);
+            return CLIFT_ERR_ARG;
+        }
+    if (!g.basis) {
+        set_error("%s grid: null basis", name);
+        return CLIFT_ERR_ARG;
+    }
+    return CLIFT_OK;
+}
+
 static int check_field(const clift_field* f, int heads) {
     CLIFT_CHECK_ARG(f != nullptr, "null field");
     for (int k = 0; k < 3; ++k) CLIFT_CHECK_ARG(f->grid[k] >= 2, "grid dimension < 2");
@@ -84,13 +105,25 @@ static int check_field(const clift_field* f, int heads) {
         CLIFT_CHECK_SUPPORTED(f->num_classes >= 1 && f->num_classes <= CLIFT_MAX_HEAD_OUT, "num_classes outside [1,64]");
         int rc = check_mlp(f->semantic, "semantic mlp", f->num_classes);
         if (rc) return rc;
-        CLIFT_CHECK_ARG(f->semantic.dims[0] == 3 + 6 * f->pe_sem, "semantic mlp input width != 3+6*pe_sem");
+        if (f->semantic_grid.comps) {
+            rc = check_grid_head(f->semantic_grid, "semantic");
+            if (rc) return rc;
+            CLIFT_CHECK_ARG(f->semantic.dims[0] == f->semantic_grid.dim, "semantic mlp input width != semantic_grid.dim");
+        } else {
+            CLIFT_CHECK_ARG(f->semantic.dims[0] == 3 + 6 * f->pe_sem, "semantic mlp input width != 3+6*pe_sem");
+        }
     }
     if (heads & CLIFT_HEAD_INSTANCE) {
         CLIFT_CHECK_SUPPORTED(f->dim_instance >= 1 && f->dim_instance <= CLIFT_MAX_HEAD_OUT, "dim_instance outside [1,64]");
         int rc = check_mlp(f->instance_fast, "instance mlp", f->dim_instance);
         if (rc) return rc;
-        CLIFT_CHECK_ARG(f->instance_fast.dims[0] == 3 + 6 * f->pe_ins, "instance mlp input width != 3+6*pe_ins");
+        if (f->instance_grid.comps) {
+            rc = check_grid_head(f->instance_grid, "instance");
+            if (rc) return rc;
+            CLIFT_CHECK_ARG(f->instance_fast.dims[0] == f->instance_grid.dim, "instance mlp input width != instance_grid.dim");
+        } else {
+            CLIFT_CHECK_ARG(f->instance_fast.dims[0] == 3 + 6 * f->pe_ins, "instance mlp input width != 3+6*pe_ins");
+        }
         if (f->slow_fast) {
             rc = check_mlp(f->instance_slow, "instance slow mlp", f->dim_instance);
             if (rc) return rc;
@@ -208,10 +241,13 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         float* o_sem = (heads & CLIFT_HEAD_SEMANTIC) ? out->semantic_raw : nullptr;
         float* o_ins = (heads & CLIFT_HEAD_INSTANCE) ? out->instance : nullptr;
         int path = CLIFT_HEADS_FMA;
+        const bool grid_heads = ((heads & CLIFT_HEAD_SEMANTIC) && field->semantic_grid.comps) ||
+                                ((heads & CLIFT_HEAD_INSTANCE) && field->instance_grid.comps);
         if (cfg->head_path == CLIFT_HEADS_TENSOR || cfg->head_path == CLIFT_HEADS_TENSOR16) {
             CLIFT_CHECK_SUPPORTED(!save, "the tensor-core head paths do not record the training stash (use CLIFT_HEADS_AUTO/FMA)");
+            CLIFT_CHECK_SUPPORTED(!grid_heads, "grid-mode semantic/instance heads run on the FP32-FMA kernels (use CLIFT_HEADS_AUTO/FMA)");
             path = cfg->head_path;
-        } else if (cfg->head_path == CLIFT_HEADS_AUTO && !save) {
+        } else if (cfg->head_path == CLIFT_HEADS_AUTO && !save && !grid_heads) {
             if (heads_tc16_available(field, heads))
                 path = CLIFT_HEADS_TENSOR16;
             else if (heads_tc_available(field, heads))

@@ -65,9 +65,12 @@ __host__ __device__ __forceinline__ int mode_v(int m) { return 2 - m; }
 //   a_off[id][l] : rows holding the INPUT of layer l (k_pad(dims[l]) rows, zero padded)
 //   z_off[id][l] : rows holding dL/d(pre-activation OUTPUT of layer l) (n_pad(dims[l+1]) rows, zero padded)
 //   prob_off     : softmax probabilities of the semantic head (n_pad(C) rows)
+// stack ids: 0 semantic mlp, 1 instance fast, 2 instance slow, 3 rgb mlp, 4 appearance basis,
+//            5 semantic-grid basis, 6 instance-grid basis (grid-mode heads only)
+constexpr int kStashIds = 7;
 struct StashLayout {
-    int a_off[5][CLIFT_MAX_LAYERS];
-    int z_off[5][CLIFT_MAX_LAYERS];
+    int a_off[kStashIds][CLIFT_MAX_LAYERS];
+    int z_off[kStashIds][CLIFT_MAX_LAYERS];
     int prob_off;
     int a_rows, z_rows;   // rows per tile in the A / Z stash
 };
@@ -78,7 +81,7 @@ inline const clift_mlp* field_mlp(const clift_field* f, int id, clift_mlp* basis
         case 1: return &f->instance_fast;
         case 2: return &f->instance_slow;
         case 3: return &f->rgb;
-        default:
+        case 4:
             memset(basis_tmp, 0, sizeof(*basis_tmp));
             basis_tmp->n_layers = 1;
             basis_tmp->dims[0] = 3 * f->appearance_comps;
@@ -86,6 +89,16 @@ inline const clift_mlp* field_mlp(const clift_field* f, int id, clift_mlp* basis
             basis_tmp->wt[0] = f->basis;
             basis_tmp->w_dgrad[0] = f->basis_dgrad;
             return basis_tmp;
+        default: {
+            const clift_grid_head& g = id == 5 ? f->semantic_grid : f->instance_grid;
+            memset(basis_tmp, 0, sizeof(*basis_tmp));
+            basis_tmp->n_layers = 1;
+            basis_tmp->dims[0] = 3 * g.comps;
+            basis_tmp->dims[1] = g.dim;
+            basis_tmp->wt[0] = g.basis;
+            basis_tmp->w_dgrad[0] = g.basis_dgrad;
+            return basis_tmp;
+        }
     }
 }
 
@@ -93,9 +106,12 @@ inline StashLayout make_stash_layout(const clift_field* f, int heads) {
     StashLayout L;
     memset(&L, 0, sizeof(L));
     int a = 0, z = 0;
-    for (int id = 0; id < 5; ++id) {
+    for (int id = 0; id < kStashIds; ++id) {
         const bool on = (id == 0 && (heads & CLIFT_HEAD_SEMANTIC)) || (id == 1 && (heads & CLIFT_HEAD_INSTANCE)) ||
-                        (id == 2 && (heads & CLIFT_HEAD_INSTANCE) && f->slow_fast) || (id >= 3 && (heads & CLIFT_HEAD_RGB));
+                        (id == 2 && (heads & CLIFT_HEAD_INSTANCE) && f->slow_fast) ||
+                        ((id == 3 || id == 4) && (heads & CLIFT_HEAD_RGB)) ||
+                        (id == 5 && (heads & CLIFT_HEAD_SEMANTIC) && f->semantic_grid.comps > 0) ||
+                        (id == 6 && (heads & CLIFT_HEAD_INSTANCE) && f->instance_grid.comps > 0);
         if (!on) continue;
         clift_mlp tmp;
         const clift_mlp* m = field_mlp(f, id, &tmp);

@@ -35,6 +35,10 @@ struct HeadsParams {
     FactorParams app;
     const float* basis_wt;
     int dim_app, pe_view, pe_feat, pe_sem, pe_ins;
+    FactorParams semg, insg;          // grid-mode semantic / instance heads (comps == 0: MLP mode, input = xyz)
+    const float* semg_basis;
+    const float* insg_basis;
+    int semg_dim, insg_dim;
     clift_mlp rgb, sem, insf, inss;
     int n_cls, d_ins, slow_fast, softmax, heads;
     float* rgb_raw;
@@ -209,6 +213,21 @@ __device__ __forceinline__ void gather_appearance(const Smem& sm, const FactorPa
     __syncthreads();
 }
 
+// Grid-mode head input (tensoRF.py:127-134, 142-156): plane*line products of the head's own VM factor set (rows
+// [0, 3*comps), saved to `stash_rows` for the basis weight gradient) -> bias-free basis Linear -> act rows [0, 64)
+// (rows >= dim are exact zeros: the packed weight is zero padded).
+__device__ __forceinline__ void grid_head_input(const Smem& sm, const FactorParams& f, const float* basis_wt, int dim,
+                                                float* stash_rows) {
+    switch (f.comps >> 4) {
+        case 1: gather_appearance<1>(sm, f); break;
+        case 2: gather_appearance<2>(sm, f); break;
+        case 3: gather_appearance<3>(sm, f); break;
+        default: gather_appearance<4>(sm, f); break;
+    }
+    if (stash_rows) store_rows(sm, stash_rows, 3 * f.comps);
+    run_layer(sm, basis_wt, nullptr, 3 * f.comps, dim, false);
+}
+
 // rows [A, in) of the RGB MLP input: viewdir, sin/cos PE of the 27 features, sin/cos PE of the viewdir
 __device__ __forceinline__ void build_rgb_input(const Smem& sm, int A, int pf, int pv) {
     const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
@@ -288,7 +307,10 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
 
         float* stash = P.stash_a ? P.stash_a + (size_t)tile * P.lay.a_rows * kTile : nullptr;
         if (P.heads & CLIFT_HEAD_SEMANTIC) {
-            build_xyz_input(sm, P.pe_sem);
+            if (P.semg.comps)
+                grid_head_input(sm, P.semg, P.semg_basis, P.semg_dim, stash ? stash + (size_t)P.lay.a_off[5][0] * kTile : nullptr);
+            else
+                build_xyz_input(sm, P.pe_sem);
             run_mlp(sm, P.sem, stash, P.lay.a_off[0]);
             if (P.softmax) {
                 if (tid < kTile) {
@@ -315,7 +337,11 @@ __global__ void __launch_bounds__(kThreads, 1) heads_forward_kernel(const __grid
         if (P.heads & CLIFT_HEAD_INSTANCE) {
             const int width = P.d_ins * (P.slow_fast ? 2 : 1);
             for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
-                build_xyz_input(sm, P.pe_ins);
+                if (P.insg.comps)     // both nets read the same basis feature (tensoRF.py:497-511); re-gathered per net
+                    grid_head_input(sm, P.insg, P.insg_basis, P.insg_dim,
+                                    stash && net == 0 ? stash + (size_t)P.lay.a_off[6][0] * kTile : nullptr);
+                else
+                    build_xyz_input(sm, P.pe_ins);
                 run_mlp(sm, net == 0 ? P.insf : P.inss, stash, P.lay.a_off[1 + net]);
                 for (int idx = tid; idx < P.d_ins * kTile; idx += kThreads) sm.act[idx] *= sm.pos[idx % kTile].w;
                 __syncthreads();
@@ -362,6 +388,14 @@ struct HeadsBwdParams {
     float* g_app_line[3];
     const float* basis_dgrad;
     int dim_app, pe_view, pe_feat;
+    FactorParams semg, insg;          // grid-mode semantic / instance heads (comps == 0: MLP mode)
+    float* g_semg_plane[3];
+    float* g_semg_line[3];
+    float* g_insg_plane[3];
+    float* g_insg_line[3];
+    const float* semg_basis_dgrad;
+    const float* insg_basis_dgrad;
+    int semg_dim, insg_dim;
     clift_mlp rgb, sem, insf, inss;
     clift_mlp_grad g_rgb_mlp, g_sem_mlp, g_insf_mlp, g_inss_mlp;
     int n_cls, d_ins, slow_fast, softmax;
@@ -432,9 +466,10 @@ __device__ __forceinline__ void mlp_backward(const Smem& sm, const clift_mlp& ml
     __syncthreads();
 }
 
+// act rows [0, 3*comps) = dL/d(plane*line product) of the tile's records -> factor gradients of the set `f`
 template <int NV>
-__device__ __forceinline__ void scatter_appearance(const Smem& sm, const HeadsBwdParams& P, int nv) {
-    const FactorParams& f = P.app;
+__device__ __forceinline__ void scatter_factors(const Smem& sm, const FactorParams& f, float* const* g_plane, float* const* g_line,
+                                                int nv) {
     const int q = threadIdx.x & 3;
 #pragma unroll 1
     for (int pass = 0; pass < kTile / 64; ++pass) {
@@ -457,19 +492,33 @@ __device__ __forceinline__ void scatter_appearance(const Smem& sm, const HeadsBw
                 const float g0 = g[0], g1 = g[kTile], g2 = g[2 * kTile], g3 = g[3 * kTile];
                 // d plane = g * L * bilinear weight ; d line = g * P * linear weight
                 const float a0 = g0 * lv.x, a1 = g1 * lv.y, a2 = g2 * lv.z, a3 = g3 * lv.w;
-                float* gp = P.g_app_plane[mode];
+                float* gp = g_plane[mode];
                 if (t2.w00 != 0.0f) red_add4(gp + (row0 + t2.x0) * f.comps + ch, a0 * t2.w00, a1 * t2.w00, a2 * t2.w00, a3 * t2.w00);
                 if (t2.w10 != 0.0f) red_add4(gp + (row0 + t2.x0 + 1) * f.comps + ch, a0 * t2.w10, a1 * t2.w10, a2 * t2.w10, a3 * t2.w10);
                 if (t2.w01 != 0.0f) red_add4(gp + (row1 + t2.x0) * f.comps + ch, a0 * t2.w01, a1 * t2.w01, a2 * t2.w01, a3 * t2.w01);
                 if (t2.w11 != 0.0f) red_add4(gp + (row1 + t2.x0 + 1) * f.comps + ch, a0 * t2.w11, a1 * t2.w11, a2 * t2.w11, a3 * t2.w11);
                 const float b0 = g0 * pv.x, b1 = g1 * pv.y, b2 = g2 * pv.z, b3 = g3 * pv.w;
-                float* gl = P.g_app_line[mode];
+                float* gl = g_line[mode];
                 if (t1.w0 != 0.0f) red_add4(gl + (int64_t)t1.z0 * f.comps + ch, b0 * t1.w0, b1 * t1.w0, b2 * t1.w0, b3 * t1.w0);
                 if (t1.w1 != 0.0f) red_add4(gl + (int64_t)(t1.z0 + 1) * f.comps + ch, b0 * t1.w1, b1 * t1.w1, b2 * t1.w1, b3 * t1.w1);
             }
         }
     }
     __syncthreads();
+}
+
+// Grid-mode head input backward: act rows [0, 64) = dL/d(basis feature) -> Z-stash (basis weight gradient) -> products
+// gradient through basis^T -> scatter into the head's own factor gradients.
+__device__ __forceinline__ void grid_head_backward(const Smem& sm, const FactorParams& f, const float* basis_dgrad, int dim,
+                                                   float* z_rows, float* const* g_plane, float* const* g_line, int nv) {
+    store_rows(sm, z_rows, 64);
+    run_dgrad(sm, basis_dgrad, dim, 3 * f.comps);
+    switch (f.comps >> 4) {
+        case 1: scatter_factors<1>(sm, f, g_plane, g_line, nv); break;
+        case 2: scatter_factors<2>(sm, f, g_plane, g_line, nv); break;
+        case 3: scatter_factors<3>(sm, f, g_plane, g_line, nv); break;
+        default: scatter_factors<4>(sm, f, g_plane, g_line, nv); break;
+    }
 }
 
 template <int NV>
@@ -534,7 +583,10 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                 for (int c = P.n_cls; c < rows; ++c) sm.act[(size_t)c * kTile + tid] = 0.0f;
             }
             __syncthreads();
-            mlp_backward(sm, P.sem, P.g_sem_mlp, sa, sz, P.lay.a_off[0], P.lay.z_off[0], false);
+            mlp_backward(sm, P.sem, P.g_sem_mlp, sa, sz, P.lay.a_off[0], P.lay.z_off[0], P.semg.comps != 0);
+            if (P.semg.comps)
+                grid_head_backward(sm, P.semg, P.semg_basis_dgrad, P.semg_dim, sz + (size_t)P.lay.z_off[5][0] * kTile,
+                                   P.g_semg_plane, P.g_semg_line, nv);
         }
         if (P.do_ins) {
             for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
@@ -548,7 +600,30 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                 }
                 __syncthreads();
                 mlp_backward(sm, net == 0 ? P.insf : P.inss, net == 0 ? P.g_insf_mlp : P.g_inss_mlp, sa, sz,
-                             P.lay.a_off[1 + net], P.lay.z_off[1 + net], false);
+                             P.lay.a_off[1 + net], P.lay.z_off[1 + net], P.insg.comps != 0);
+                if (P.insg.comps) {
+                    // the fast and the slow net read the same basis feature: its gradient is their sum.  The fast net's
+                    // share is parked in the basis Z-stash rows (same thread <-> element mapping as store_rows) and added
+                    // back after the slow net's backward.
+                    float* zrow = sz + (size_t)P.lay.z_off[6][0] * kTile;
+                    if (P.slow_fast && net == 0) {
+                        store_rows(sm, zrow, 64);
+                        __syncthreads();
+                        continue;
+                    }
+                    if (P.slow_fast) {
+                        const float4* z4 = reinterpret_cast<const float4*>(zrow);
+                        float4* d4 = reinterpret_cast<float4*>(sm.act);
+                        for (int i = tid; i < 64 * (kTile / 4); i += kThreads) {
+                            const float4 z = z4[i];
+                            float4 d = d4[i];
+                            d.x += z.x, d.y += z.y, d.z += z.z, d.w += z.w;
+                            d4[i] = d;
+                        }
+                        __syncthreads();
+                    }
+                    grid_head_backward(sm, P.insg, P.insg_basis_dgrad, P.insg_dim, zrow, P.g_insg_plane, P.g_insg_line, nv);
+                }
             }
         }
         if (P.do_rgb) {
@@ -590,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
             // basis layer: dZ = dfeat (64 rows, zero padded) -> Z-stash, then dprod = basis^T dfeat
             store_rows(sm, sz + (size_t)P.lay.z_off[4][0] * kTile, 64);
             run_dgrad(sm, P.basis_dgrad, A, 3 * P.app.comps);
-            scatter_appearance<NV>(sm, P, nv);
+            scatter_factors<NV>(sm, P.app, P.g_app_plane, P.g_app_line, nv);
         }
     }
 }
@@ -754,6 +829,12 @@ int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, 
     P.pe_feat = field->pe_feat;
     P.pe_sem = field->pe_sem;
     P.pe_ins = field->pe_ins;
+    P.semg = make_grid_factors(field, field->semantic_grid);
+    P.insg = make_grid_factors(field, field->instance_grid);
+    P.semg_basis = field->semantic_grid.basis;
+    P.insg_basis = field->instance_grid.basis;
+    P.semg_dim = field->semantic_grid.dim;
+    P.insg_dim = field->instance_grid.dim;
     P.rgb = field->rgb;
     P.sem = field->semantic;
     P.insf = field->instance_fast;
@@ -871,6 +952,36 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
     P.dim_app = field->dim_appearance;
     P.pe_view = field->pe_view;
     P.pe_feat = field->pe_feat;
+    P.semg = make_grid_factors(field, field->semantic_grid);
+    P.insg = make_grid_factors(field, field->instance_grid);
+    if (!do_sem) P.semg.comps = 0;
+    if (!do_ins) P.insg.comps = 0;
+    for (int m = 0; m < 3; ++m) {
+        P.g_semg_plane[m] = grad->semantic_grid.plane[m];
+        P.g_semg_line[m] = grad->semantic_grid.line[m];
+        P.g_insg_plane[m] = grad->instance_grid.plane[m];
+        P.g_insg_line[m] = grad->instance_grid.line[m];
+    }
+    P.semg_basis_dgrad = field->semantic_grid.basis_dgrad;
+    P.insg_basis_dgrad = field->instance_grid.basis_dgrad;
+    P.semg_dim = field->semantic_grid.dim;
+    P.insg_dim = field->instance_grid.dim;
+    for (int h = 0; h < 2; ++h) {
+        const FactorParams& gf = h == 0 ? P.semg : P.insg;
+        if (!gf.comps) continue;
+        const clift_grid_head_grad& gg = h == 0 ? grad->semantic_grid : grad->instance_grid;
+        const clift_grid_head& gh = h == 0 ? field->semantic_grid : field->instance_grid;
+        for (int m = 0; m < 3; ++m)
+            if (!gg.plane[m] || !gg.line[m]) {
+                set_error("clift_render_backward: grid-mode %s head without factor gradient buffers", h == 0 ? "semantic" : "instance");
+                return CLIFT_ERR_ARG;
+            }
+        if (!gg.basis || !gh.basis_dgrad) {
+            set_error("clift_render_backward: grid-mode %s head without basis dgrad operand / gradient buffer",
+                      h == 0 ? "semantic" : "instance");
+            return CLIFT_ERR_ARG;
+        }
+    }
     P.rgb = field->rgb;
     P.sem = field->semantic;
     P.insf = field->instance_fast;
@@ -915,8 +1026,9 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
             if (!m.w_dgrad[l]) return false;
         return true;
     };
-    if ((do_rgb && !need_dgrad(field->rgb, true)) || (do_sem && !need_dgrad(field->semantic, false)) ||
-        (do_ins && (!need_dgrad(field->instance_fast, false) || (field->slow_fast && !need_dgrad(field->instance_slow, false))))) {
+    const bool sg = P.semg.comps != 0, ig = P.insg.comps != 0;
+    if ((do_rgb && !need_dgrad(field->rgb, true)) || (do_sem && !need_dgrad(field->semantic, sg)) ||
+        (do_ins && (!need_dgrad(field->instance_fast, ig) || (field->slow_fast && !need_dgrad(field->instance_slow, ig))))) {
         set_error("clift_render_backward: field lacks the w_dgrad operands (pack with clift_pack_linear_dgrad)");
         return CLIFT_ERR_ARG;
     }
@@ -942,9 +1054,13 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
     // weight gradients, one split-K GEMM per layer
     int rc;
     clift_mlp tmp;
-    if (do_sem)
+    if (do_sem) {
         for (int l = 0; l < field->semantic.n_layers; ++l)
             if ((rc = launch_wgrad(ws, lay, 0, l, &field->semantic, grad->semantic.wt[l], cap, stream))) return rc;
+        if (sg && (rc = launch_wgrad(ws, lay, 5, 0, field_mlp(field, 5, &tmp), grad->semantic_grid.basis, cap, stream))) return rc;
+    }
+    if (do_ins && ig)
+        if ((rc = launch_wgrad(ws, lay, 6, 0, field_mlp(field, 6, &tmp), grad->instance_grid.basis, cap, stream))) return rc;
     if (do_ins) {
         for (int l = 0; l < field->instance_fast.n_layers; ++l)
             if ((rc = launch_wgrad(ws, lay, 1, l, &field->instance_fast, grad->instance_fast.wt[l], cap, stream))) return rc;

@@ -63,6 +63,20 @@ inline FactorParams make_factors(const clift_field* f, bool appearance) {
     return p;
 }
 
+// factor set of a grid-mode semantic / instance head (comps == 0: the head is in MLP mode)
+inline FactorParams make_grid_factors(const clift_field* f, const clift_grid_head& g) {
+    FactorParams p;
+    for (int m = 0; m < 3; ++m) {
+        p.plane[m] = g.plane[m];
+        p.line[m] = g.line[m];
+        p.pw[m] = f->grid[mode_a(m)];
+        p.ph[m] = f->grid[mode_b(m)];
+        p.ll[m] = f->grid[mode_v(m)];
+    }
+    p.comps = g.comps;
+    return p;
+}
+
 #ifdef __CUDACC__
 // One quad lane's share (channels ch, ch+16, ...) of  sum_modes sum_c P_c(x_a,x_b) * L_c(x_v).
 // `lines_s` != null: density line factors staged in shared memory, modes back to back.

@@ -198,13 +198,17 @@ class TensorVMSplit(nn.Module):
             raise L.CliftError("distilled-feature grids are outside the B200 hot path (off in every shipped contrastive config)")
         if use_proj:
             raise L.CliftError("use_proj (SlowFastProjLayer) is outside the B200 hot path (off in every shipped config)")
-        if not use_semantic_mlp or (dim_feature_instance is not None and not use_instance_mlp):
-            raise L.CliftError("grid-mode semantic/instance heads (allgrid.yaml) are not built yet: "
-                               "use_mlp_for_semantics/use_mlp_for_instances must be True")
         if use_feature_reg:
             raise L.CliftError("use_feature_regularization is not reachable from shipped configs and is not built")
-        if len(set(num_density_comps)) != 1 or len(set(num_appearance_comps)) != 1:
-            raise L.CliftError("per-mode component counts must be equal")
+        sem_grid = num_semantics_comps is not None and not use_semantic_mlp
+        ins_grid = dim_feature_instance is not None and num_instance_comps is not None and not use_instance_mlp
+        if not sem_grid and not use_semantic_mlp:
+            raise L.CliftError("TensorVMSplit without a semantic head (use_semantic_mlp=False and no num_semantics_comps) "
+                               "is not a configuration the reference's trainer or render scripts build")
+        for comps in (num_density_comps, num_appearance_comps) + ((num_semantics_comps,) if sem_grid else ()) + \
+                ((num_instance_comps,) if ins_grid else ()):
+            if len(set(comps)) != 1:
+                raise L.CliftError("per-mode component counts must be equal")
         self.num_density_comps = num_density_comps
         self.num_appearance_comps = num_appearance_comps
         self.num_semantics_comps = num_semantics_comps
@@ -233,12 +237,26 @@ class TensorVMSplit(nn.Module):
         self.semantic_plane = self.semantic_line = self.semantic_basis_mat = None
         self.instance_plane = self.instance_line = self.instance_basis_mat = None
         self.render_semantic_mlp = self.render_instance_mlp = None
+        # tensoRF.py:72-85: a grid-mode head owns a VM factor set + bias-free basis and a 3-layer MLP on the basis feature
         if dim_feature_instance is not None:
-            self.render_instance_mlp = MLPRenderInstanceFeature(3, ins_out_channels, pe_feat=pe_ins, num_mlp_layers=4,
-                                                                dim_mlp=dim_mlp_instance, output_activation=nn.Identity(),
-                                                                slow_fast_mode=slow_fast_mode)
-        self.render_semantic_mlp = MLPRenderSemanticFeature(3, num_semantic_classes, pe_feat=pe_sem,
-                                                            output_activation=output_mlp_semantics)
+            if ins_grid:
+                self.instance_plane, self.instance_line = self.init_one_svd(num_instance_comps, grid_dim, 0.1)
+                self.instance_basis_mat = nn.Linear(sum(num_instance_comps), dim_instances, bias=False)
+                self.render_instance_mlp = MLPRenderInstanceFeature(dim_instances, ins_out_channels, num_mlp_layers=3,
+                                                                    dim_mlp=dim_mlp_instance, output_activation=nn.Identity(),
+                                                                    slow_fast_mode=slow_fast_mode)
+            elif use_instance_mlp:
+                self.render_instance_mlp = MLPRenderInstanceFeature(3, ins_out_channels, pe_feat=pe_ins, num_mlp_layers=4,
+                                                                    dim_mlp=dim_mlp_instance, output_activation=nn.Identity(),
+                                                                    slow_fast_mode=slow_fast_mode)
+        if sem_grid:
+            self.semantic_plane, self.semantic_line = self.init_one_svd(num_semantics_comps, grid_dim, 0.1)
+            self.semantic_basis_mat = nn.Linear(sum(num_semantics_comps), dim_semantics, bias=False)
+            self.render_semantic_mlp = MLPRenderSemanticFeature(dim_semantics, num_semantic_classes, num_mlp_layers=3,
+                                                                dim_mlp=dim_mlp_semantics, output_activation=output_mlp_semantics)
+        else:
+            self.render_semantic_mlp = MLPRenderSemanticFeature(3, num_semantic_classes, pe_feat=pe_sem,
+                                                                output_activation=output_mlp_semantics)
         self.use_distilled_features_semantic = False
         self.use_distilled_features_instance = False
         self.num_feature_comps = num_feature_comps
@@ -289,21 +307,33 @@ class TensorVMSplit(nn.Module):
         return sigma.view(xyz_sampled.shape[:-1])
 
     # ---- grid surgery (tensoRF.py:158-197): parameter objects are replaced, packed view dropped --
+    def _factor_sets(self):
+        """(plane list, line list) of every VM factor set this model owns (grid-mode heads add theirs)."""
+        sets = [(self.density_plane, self.density_line), (self.appearance_plane, self.appearance_line)]
+        if self.semantic_plane is not None:
+            sets.append((self.semantic_plane, self.semantic_line))
+        if self.instance_plane is not None:
+            sets.append((self.instance_plane, self.instance_line))
+        return sets
+
     @torch.no_grad()
     def shrink(self, t_l, b_r):
-        for i in range(3):
-            v = VECTOR_MODE[i]
-            self.density_line[i] = nn.Parameter(self.density_line[i].data[..., t_l[v]:b_r[v], :].contiguous())
-            self.appearance_line[i] = nn.Parameter(self.appearance_line[i].data[..., t_l[v]:b_r[v], :].contiguous())
-            m0, m1 = MATRIX_MODE[i]
-            self.density_plane[i] = nn.Parameter(self.density_plane[i].data[..., t_l[m1]:b_r[m1], t_l[m0]:b_r[m0]].contiguous())
-            self.appearance_plane[i] = nn.Parameter(self.appearance_plane[i].data[..., t_l[m1]:b_r[m1], t_l[m0]:b_r[m0]].contiguous())
+        for planes, lines in self._factor_sets():
+            for i in range(3):
+                v = VECTOR_MODE[i]
+                m0, m1 = MATRIX_MODE[i]
+                lines[i] = nn.Parameter(lines[i].data[..., t_l[v]:b_r[v], :].contiguous())
+                planes[i] = nn.Parameter(planes[i].data[..., t_l[m1]:b_r[m1], t_l[m0]:b_r[m0]].contiguous())
         self._packed = None
 
     @torch.no_grad()
     def upsample_volume_grid(self, res_target):
         self.appearance_plane, self.appearance_line = self.upsample_plane_line(self.appearance_plane, self.appearance_line, res_target)
         self.density_plane, self.density_line = self.upsample_plane_line(self.density_plane, self.density_line, res_target)
+        if self.semantic_plane is not None:
+            self.semantic_plane, self.semantic_line = self.upsample_plane_line(self.semantic_plane, self.semantic_line, res_target)
+        if self.instance_plane is not None:
+            self.instance_plane, self.instance_line = self.upsample_plane_line(self.instance_plane, self.instance_line, res_target)
         self._packed = None
 
     @torch.no_grad()
@@ -335,7 +365,11 @@ class TensorVMSplit(nn.Module):
                      {'params': self.appearance_plane, 'lr': lr_grid},
                      {'params': self.appearance_basis_mat.parameters(), 'lr': lr_net},
                      {'params': self.render_appearance_mlp.parameters(), 'lr': lr_net}]
-        if self.render_semantic_mlp is not None:
+        if self.semantic_plane is not None:
+            grad_vars.extend([{'params': self.semantic_plane, 'lr': lr_grid}, {'params': self.semantic_line, 'lr': lr_grid},
+                              {'params': self.semantic_basis_mat.parameters(), 'lr': lr_net},
+                              {'params': self.render_semantic_mlp.parameters(), 'lr': lr_net}])
+        elif self.render_semantic_mlp is not None:
             grad_vars.append({'params': self.render_semantic_mlp.parameters(), 'lr': lr_net})
         return grad_vars
 
@@ -343,11 +377,19 @@ class TensorVMSplit(nn.Module):
         return [{'params': self.density_line, 'lr': lr_grid}, {'params': self.density_plane, 'lr': lr_grid}]
 
     def get_optimizable_segment_parameters(self, lr_grid, lr_net, _weight_decay=0):
+        if self.semantic_plane is not None:
+            return [{'params': self.semantic_plane, 'lr': lr_grid}, {'params': self.semantic_line, 'lr': lr_grid},
+                    {'params': self.semantic_basis_mat.parameters(), 'lr': lr_net},
+                    {'params': self.render_semantic_mlp.parameters(), 'lr': lr_net}]
         return [{'params': self.render_semantic_mlp.parameters(), 'lr': lr_net}] if self.render_semantic_mlp is not None else []
 
     def get_optimizable_instance_parameters(self, lr_grid, lr_net, using_DINO=False):
         grad_vars = []
-        if self.render_instance_mlp is not None:
+        if self.instance_plane is not None:
+            grad_vars.extend([{'params': self.instance_plane, 'lr': lr_grid}, {'params': self.instance_line, 'lr': lr_grid},
+                              {'params': self.instance_basis_mat.parameters(), 'lr': lr_net},
+                              {'params': self.render_instance_mlp.mlp.parameters(), 'lr': lr_net}])
+        elif self.render_instance_mlp is not None:
             grad_vars.append({'params': self.render_instance_mlp.mlp.parameters(), 'lr': lr_net})
         if self.slow_fast_mode and not using_DINO:
             grad_vars.append({'params': self.render_instance_mlp.slow_mlp.parameters(), 'lr': lr_net})
@@ -363,16 +405,27 @@ class TensorVMSplit(nn.Module):
         return sum(plane_tv(p) * 1e-2 for p in self.appearance_plane)
 
     def tv_loss_semantics(self, regularizer=None):
-        return 0
+        from .loss import plane_tv
+        if self.semantic_plane is None:
+            return 0
+        return sum(plane_tv(p) * 1e-2 + plane_tv(l) * 1e-3 for p, l in zip(self.semantic_plane, self.semantic_line))
 
     def tv_loss_instances(self, regularizer=None):
-        return 0
+        from .loss import plane_tv
+        if self.instance_plane is None:
+            return 0
+        return sum(plane_tv(p) * 1e-2 + plane_tv(l) * 1e-3 for p, l in zip(self.instance_plane, self.instance_line))
 
     def total_tv_loss(self, regularizer, config, current_epoch):
         """Same signature as tensoRF.py:281-290.  ``regularizer`` (the reference's TVLoss module) is
-        accepted and ignored: the stencil runs in clift_tv_loss.  Semantic/instance planes do not exist
-        in MLP-head mode, so their terms are zero as in the reference."""
-        return self.tv_loss_density() * config.lambda_tv_density + self.tv_loss_appearance() * config.lambda_tv_appearance
+        accepted and ignored: the stencil runs in clift_tv_loss.  Semantic/instance planes exist only in
+        grid-head mode; their terms switch on at the reference's epochs and are zero otherwise."""
+        tot = self.tv_loss_density() * config.lambda_tv_density + self.tv_loss_appearance() * config.lambda_tv_appearance
+        if self.semantic_plane is not None and current_epoch >= config.late_semantic_optimization:
+            tot = tot + self.tv_loss_semantics() * config.lambda_tv_semantics
+        if self.instance_plane is not None and current_epoch >= config.instance_optimization_epoch:
+            tot = tot + self.tv_loss_instances() * config.lambda_tv_instances
+        return tot
 
 
 class PackedField:
@@ -396,6 +449,15 @@ class PackedField:
         self.lines = {"density": mkl(model.density_line), "appearance": mkl(model.appearance_line)}
         self.src = {"density": (model.density_plane, model.density_line),
                     "appearance": (model.appearance_plane, model.appearance_line)}
+        # grid-mode heads (tensoRF.py:72-85): their own factor set + basis, same packed layouts as the appearance set
+        self.grid_basis: Dict[str, _PackedMlp] = {}
+        for name in ("semantic", "instance"):
+            planes, lines = getattr(model, f"{name}_plane"), getattr(model, f"{name}_line")
+            if planes is None:
+                continue
+            self.planes[name], self.lines[name] = mk(planes), mkl(lines)
+            self.src[name] = (planes, lines)
+            self.grid_basis[name] = _PackedMlp([getattr(model, f"{name}_basis_mat")], dev)
         self.basis = _PackedMlp([model.appearance_basis_mat], dev)
         self.tc16_scratch = torch.zeros((8,), device=dev)
         self.rgb = _PackedMlp(_linears(model.render_appearance_mlp.mlp), dev)
@@ -418,10 +480,19 @@ class PackedField:
             f.density_line[i] = L.ptr(self.lines["density"][i])
             f.appearance_plane[i] = L.ptr(self.planes["appearance"][i])
             f.appearance_line[i] = L.ptr(self.lines["appearance"][i])
+        for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
+            if name not in self.grid_basis:
+                gh.comps = 0
+                continue
+            gh.comps = self.src[name][0][0].shape[1]
+            gh.dim = self.grid_basis[name].dims[1]
+            for i in range(3):
+                gh.plane[i] = L.ptr(self.planes[name][i])
+                gh.line[i] = L.ptr(self.lines[name][i])
         self.field = f
         self.grad = L.FieldGrad()
-        self.g_planes: Dict[str, List[Optional[torch.Tensor]]] = {"density": [None] * 3, "appearance": [None] * 3}
-        self.g_lines: Dict[str, List[Optional[torch.Tensor]]] = {"density": [None] * 3, "appearance": [None] * 3}
+        self.g_planes: Dict[str, List[Optional[torch.Tensor]]] = {k: [None] * 3 for k in self.planes}
+        self.g_lines: Dict[str, List[Optional[torch.Tensor]]] = {k: [None] * 3 for k in self.planes}
 
     @staticmethod
     def _ids(model) -> Tuple[int, ...]:
@@ -437,7 +508,7 @@ class PackedField:
         if not training and versions == self.versions and not self.tc_stale:
             return
         lib, st = self.lib, L.stream_ptr(self.device)
-        for name in ("density", "appearance"):
+        for name in self.src:
             planes, lines = self.src[name]
             for i in range(3):
                 p, l = planes[i].data, lines[i].data
@@ -452,10 +523,17 @@ class PackedField:
                                                 L.ptr(self.tc16_scratch), st))
         self.basis.pack(lib, st, training, self.tc16_scratch.data_ptr() + 24, 0.0)
         self.rgb.pack(lib, st, training, self.basis.out_bound_ptr(), 1.0)
-        for m in (self.sem, self.insf, self.inss):
+        for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
             if m is not None:
-                m.pack(lib, st, training)
+                # a grid-mode head's stack stays off the fp16-split operand chain (bound pointer -1): it runs on the FMA kernels
+                m.pack(lib, st, training, -1 if name in self.grid_basis else None)
         f = self.field
+        for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
+            if name in self.grid_basis:
+                gb = self.grid_basis[name]
+                gb.pack(lib, st, training, -1)
+                gh.basis = L.ptr(gb.wt[0])
+                gh.basis_dgrad = L.ptr(gb.w_dgrad[0])
         f.basis = L.ptr(self.basis.wt[0])
         f.basis_dgrad = L.ptr(self.basis.w_dgrad[0])
         f.basis_tc = L.ptr(self.basis.w_tc[0])
@@ -473,7 +551,10 @@ class PackedField:
     # ---- gradient side ---------------------------------------------------------------------------
     def prepare_grads(self, want_density: bool, want_rgb: bool, want_sem: bool, want_ins: bool) -> L.FieldGrad:
         g = self.grad
-        for name, want in (("density", want_density), ("appearance", want_rgb)):
+        wants = {"density": want_density, "appearance": want_rgb, "semantic": want_sem, "instance": want_ins}
+        for name in self.planes:
+            want = wants[name]
+            gh = {"semantic": g.semantic_grid, "instance": g.instance_grid}.get(name)
             for i in range(3):
                 if want:
                     if self.g_planes[name][i] is None:
@@ -486,8 +567,14 @@ class PackedField:
                 gl = L.ptr(self.g_lines[name][i]) if want else None
                 if name == "density":
                     g.density_plane[i], g.density_line[i] = gp, gl
-                else:
+                elif name == "appearance":
                     g.appearance_plane[i], g.appearance_line[i] = gp, gl
+                else:
+                    gh.plane[i], gh.line[i] = gp, gl
+            if gh is not None:
+                dummy = L.MlpGrad()
+                self.grid_basis[name].grad_buffers(dummy, want)
+                gh.basis = dummy.wt[0]
         dummy = L.MlpGrad()
         self.basis.grad_buffers(dummy, want_rgb)
         g.basis = dummy.wt[0]

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -32,6 +32,15 @@ class MlpGrad(C.Structure):
     _fields_ = [("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS)]
 
 
+class GridHead(C.Structure):
+    _fields_ = [("comps", C.c_int32), ("dim", C.c_int32), ("plane", _vp * 3), ("line", _vp * 3), ("basis", _vp),
+                ("basis_dgrad", _vp)]
+
+
+class GridHeadGrad(C.Structure):
+    _fields_ = [("plane", _vp * 3), ("line", _vp * 3), ("basis", _vp)]
+
+
 class Field(C.Structure):
     _fields_ = [("grid", C.c_int32 * 3), ("density_comps", C.c_int32), ("appearance_comps", C.c_int32),
                 ("dim_appearance", C.c_int32), ("pe_view", C.c_int32), ("pe_feat", C.c_int32),
@@ -40,13 +49,15 @@ class Field(C.Structure):
                 ("density_plane", _vp * 3), ("density_line", _vp * 3),
                 ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp), ("basis_dgrad", _vp), ("basis_tc", _vp),
                 ("basis_tc16", _vp),
-                ("rgb", Mlp), ("semantic", Mlp), ("instance_fast", Mlp), ("instance_slow", Mlp)]
+                ("rgb", Mlp), ("semantic", Mlp), ("instance_fast", Mlp), ("instance_slow", Mlp),
+                ("semantic_grid", GridHead), ("instance_grid", GridHead)]
 
 
 class FieldGrad(C.Structure):
     _fields_ = [("density_plane", _vp * 3), ("density_line", _vp * 3),
                 ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp),
-                ("rgb", MlpGrad), ("semantic", MlpGrad), ("instance_fast", MlpGrad), ("instance_slow", MlpGrad)]
+                ("rgb", MlpGrad), ("semantic", MlpGrad), ("instance_fast", MlpGrad), ("instance_slow", MlpGrad),
+                ("semantic_grid", GridHeadGrad), ("instance_grid", GridHeadGrad)]
 
 
 class RenderCfg(C.Structure):

@@ -138,6 +138,12 @@ class _Render(torch.autograd.Function):
             grads["appearance_basis_mat.weight"] = pk.basis.unpack_grads(lib, st)[0]
             for n, g in zip(_mlp_names("render_appearance_mlp.mlp", pk.rgb), pk.rgb.unpack_grads(lib, st)):
                 grads[n] = g
+        for name, gout in (("semantic", g_sem), ("instance", g_ins)):      # grid-mode heads: their own factors + basis
+            if gout is not None and name in pk.grid_basis:
+                gp, gl = pk.unpack_factor_grads(name)
+                for i in range(3):
+                    grads[f"{name}_plane.{i}"], grads[f"{name}_line.{i}"] = gp[i], gl[i]
+                grads[f"{name}_basis_mat.weight"] = pk.grid_basis[name].unpack_grads(lib, st)[0]
         if g_sem is not None:
             for n, g in zip(_mlp_names("render_semantic_mlp.mlp", pk.sem), pk.sem.unpack_grads(lib, st)):
                 grads[n] = g

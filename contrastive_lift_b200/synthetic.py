@@ -43,8 +43,13 @@ def make_field_params(seed: int, grid_dim: Sequence[int], num_classes: int = 21,
                       dim_appearance: int = 27, pe_view: int = 2, pe_feat: int = 2, pe_sem: int = 0,
                       pe_ins: int = 0, width_rgb: int = 128, width_sem: int = 256, width_ins: int = 256,
                       ball: Optional[float] = 0.35, ball_gain: float = 3.0,
-                      factor_scale: float = 0.1) -> Dict[str, torch.Tensor]:
-    """Parameter dict of the default contrastive_lift configuration (MLP heads on xyz)."""
+                      factor_scale: float = 0.1, sem_grid_comps: Optional[int] = None,
+                      ins_grid_comps: Optional[int] = None, dim_semantics: int = 27, dim_instances: int = 27,
+                      width_sem_grid: int = 128) -> Dict[str, torch.Tensor]:
+    """Parameter dict of the default contrastive_lift configuration (MLP heads on xyz).  ``sem_grid_comps`` /
+    ``ins_grid_comps`` (e.g. 32) switch that head to grid mode (allgrid.yaml, tensoRF.py:72-84): a VM factor set +
+    bias-free basis Linear feeding a 3-layer MLP; their draws come after the default ones, so the default stream is
+    unchanged."""
     rng = np.random.default_rng(seed)
     g = list(grid_dim)
     p: Dict[str, torch.Tensor] = {}
@@ -67,11 +72,27 @@ def make_field_params(seed: int, grid_dim: Sequence[int], num_classes: int = 21,
     in_rgb = dim_appearance + 3 + 2 * pe_feat * dim_appearance + 2 * pe_view * 3
     _mlp(rng, p, "render_appearance_mlp.mlp", [in_rgb, width_rgb, width_rgb, 3], zero_last_bias=True)
     in_ins = 3 + 2 * pe_ins * 3
-    _mlp(rng, p, "render_instance_mlp.mlp", [in_ins, width_ins, width_ins, width_ins, max_instances])
+    ins_dims = [in_ins, width_ins, width_ins, width_ins, max_instances]
+    if ins_grid_comps:       # tensoRF.py:75-77: 3 layers on the 27 basis features
+        ins_dims = [dim_instances, width_ins, width_ins, max_instances]
+    _mlp(rng, p, "render_instance_mlp.mlp", ins_dims)
     if slow_fast:
-        _mlp(rng, p, "render_instance_mlp.slow_mlp", [in_ins, width_ins, width_ins, width_ins, max_instances])
+        _mlp(rng, p, "render_instance_mlp.slow_mlp", ins_dims)
     in_sem = 3 + 2 * pe_sem * 3
-    _mlp(rng, p, "render_semantic_mlp.mlp", [in_sem, width_sem, width_sem, width_sem, width_sem, num_classes])
+    sem_dims = [in_sem, width_sem, width_sem, width_sem, width_sem, num_classes]
+    if sem_grid_comps:       # tensoRF.py:81-85: 3 layers of dim_mlp_semantics
+        sem_dims = [dim_semantics, width_sem_grid, width_sem_grid, num_classes]
+    _mlp(rng, p, "render_semantic_mlp.mlp", sem_dims)
+    for name, comps, dim in (("semantic", sem_grid_comps, dim_semantics), ("instance", ins_grid_comps, dim_instances)):
+        if not comps:
+            continue
+        for i in range(3):
+            a, b = MATRIX_MODE[i]
+            v = VECTOR_MODE[i]
+            p[f"{name}_plane.{i}"] = torch.from_numpy((factor_scale * rng.standard_normal((1, comps, g[b], g[a]))).astype(np.float32))
+            p[f"{name}_line.{i}"] = torch.from_numpy((factor_scale * rng.standard_normal((1, comps, g[v], 1))).astype(np.float32))
+        w, _ = _linear(rng, dim, 3 * comps, bias=False)
+        p[f"{name}_basis_mat.weight"] = torch.from_numpy(w)
     return p
 
 

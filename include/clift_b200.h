@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 6
+#define CLIFT_ABI_VERSION 7
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -63,6 +63,25 @@ typedef struct {
     float* bias[CLIFT_MAX_LAYERS];
 } clift_mlp_grad;
 
+/* Grid-mode semantic / instance head input (use_mlp_for_semantics / use_mlp_for_instances = False: allgrid.yaml,
+ * instGRIDsemMLP.yaml, onlyRGBsegGRID.yaml; tensoRF.py:72-85, 127-156): a VM factor set in the same packed layout as the
+ * appearance factors, reduced by a bias-free basis Linear (3*comps -> dim) whose output is the head MLP's input
+ * (dims[0] of that clift_mlp == dim).  comps == 0: MLP mode, the head reads xyz (+ positional encoding). */
+typedef struct {
+    int32_t comps;               /* 0 = off, else 16, 32, 48 or 64 per mode (the reference builds 32) */
+    int32_t dim;                 /* dim_semantics / dim_instances = 27 (<= 64) */
+    const float* plane[3];
+    const float* line[3];
+    const float* basis;          /* clift_pack_linear() of the basis weight */
+    const float* basis_dgrad;    /* clift_pack_linear_dgrad() of it (training only, else null) */
+} clift_grid_head;
+
+typedef struct {
+    float* plane[3];
+    float* line[3];
+    float* basis;
+} clift_grid_head_grad;
+
 /* TensorVMSplit parameters (tensoRF.py:32-106) in the kernels' HBM layout.
  * plane i: channel-last [H=grid[b]][W=grid[a]][comps] with (a,b)=matrix_mode[i] in {(0,1),(0,2),(1,2)}
  * line  i: [grid[v]][comps] with v=vector_mode[i] in {2,1,0};  written by clift_pack_plane/line(). */
@@ -89,6 +108,8 @@ typedef struct {
     clift_mlp semantic;              /* render_semantic_mlp.mlp         (H2) */
     clift_mlp instance_fast;         /* render_instance_mlp.mlp         (H3) */
     clift_mlp instance_slow;         /* render_instance_mlp.slow_mlp    (H3) */
+    clift_grid_head semantic_grid;   /* semantic_plane/line/basis_mat   (F3; comps 0 in MLP mode) */
+    clift_grid_head instance_grid;   /* instance_plane/line/basis_mat   (F3; fast and slow nets share the feature) */
 } clift_field;
 
 typedef struct {
@@ -98,6 +119,7 @@ typedef struct {
     float* appearance_line[3];
     float* basis;
     clift_mlp_grad rgb, semantic, instance_fast, instance_slow;
+    clift_grid_head_grad semantic_grid, instance_grid;   /* required when the matching head is in grid mode */
 } clift_field_grad;
 
 /* TensoRFRenderer constants (renderer:39-78). */
@@ -115,7 +137,9 @@ typedef struct {
 
 /* MLP-head implementation.  AUTO = tcgen05 tensor cores for inference - the fp16-split path (3 kind::f16 MMAs per
  * product, scaled operands, fp32-faithful) when the field carries w_tc16 operands, else the 3xTF32 path (w_tc) -
- * and FP32 FMA otherwise and always for save_for_backward forwards (they record the training stash). */
+ * and FP32 FMA otherwise and always for save_for_backward forwards (they record the training stash).  Grid-mode
+ * semantic / instance heads (clift_grid_head.comps > 0) run on the FP32-FMA kernels; asking for a tensor path
+ * explicitly with such a head evaluated returns CLIFT_ERR_UNSUPPORTED. */
 #define CLIFT_HEADS_AUTO 0
 #define CLIFT_HEADS_FMA 1
 #define CLIFT_HEADS_TENSOR 2

@@ -506,11 +506,23 @@ def tv_loss(x: Tensor) -> Tensor:
     return 2 * (tv_h / cnt_h + tv_w / cnt_w) / n
 
 
-def total_tv_loss(params: Params, lambda_density: float = 0.1, lambda_appearance: float = 0.01) -> Tensor:
-    """tensoRF.py:248-290 for the MLP-head configuration (no semantic/instance planes)."""
+def total_tv_loss(params: Params, lambda_density: float = 0.1, lambda_appearance: float = 0.01,
+                  lambda_semantics: float = 0.02, lambda_instances: float = 0.02) -> Tensor:
+    """tensoRF.py:248-290 (past the late_semantic / instance_optimization epochs).  Semantic / instance factor sets
+    exist only in grid-head mode; their lines are regularised too (tensoRF.py:264,271)."""
     td = sum(tv_loss(params[f"density_plane.{i}"]) * 1e-2 for i in range(3))
     ta = sum(tv_loss(params[f"appearance_plane.{i}"]) * 1e-2 for i in range(3))
-    return td * lambda_density + ta * lambda_appearance
+    tot = td * lambda_density + ta * lambda_appearance
+    for name, lam in (("semantic", lambda_semantics), ("instance", lambda_instances)):
+        if f"{name}_plane.0" in params:
+            tot = tot + lam * sum(tv_loss(params[f"{name}_plane.{i}"]) * 1e-2 + tv_loss(params[f"{name}_line.{i}"]) * 1e-3
+                                  for i in range(3))
+    return tot
+
+
+def factor_sets(params: Params) -> List[str]:
+    """Names of the VM factor sets present in a parameter dict (grid-mode heads add semantic / instance)."""
+    return [n for n in ("density", "appearance", "semantic", "instance") if f"{n}_plane.0" in params]
 
 
 # --------------------------------------------------------------------------------------
@@ -552,9 +564,9 @@ def shrink_plan(cfg: RenderConfig, xyz_min: Tensor, xyz_max: Tensor, fractional_
 
 
 def shrink_params(params: Params, t_l: Tensor, b_r: Tensor) -> Params:
-    """tensoRF.py:158-177 on the parameter dict (density + appearance factors; heads untouched)."""
+    """tensoRF.py:158-177 on the parameter dict (every factor set present; heads untouched)."""
     out = dict(params)
-    for name in ("density", "appearance"):
+    for name in factor_sets(params):
         for i in range(3):
             v = VECTOR_MODE[i]
             m0, m1 = MATRIX_MODE[i]
@@ -566,7 +578,7 @@ def shrink_params(params: Params, t_l: Tensor, b_r: Tensor) -> Params:
 def upsample_params(params: Params, res_target: Sequence[int]) -> Params:
     """tensoRF.py:179-197: bilinear align_corners resize of every plane / line factor."""
     out = dict(params)
-    for name in ("density", "appearance"):
+    for name in factor_sets(params):
         for i in range(3):
             v = VECTOR_MODE[i]
             m0, m1 = MATRIX_MODE[i]

@@ -29,6 +29,18 @@ RENDER_CASES = [
     ("render_b", (16, 16, 16), 2, 3, 37, True, True),      # MOS-like: C=2, S not a multiple of 32
     ("render_c", (24, 18, 20), 5, 4, 64, False, False),    # semantic_weight_mode none, no slow net
 ]
+# grid-mode heads (allgrid.yaml / instGRIDsemMLP.yaml / onlyRGBsegGRID.yaml; tensoRF.py:72-85, 142-156):
+# name -> (semantic grid comps, instance grid comps); None = that head stays an MLP on xyz
+GRID_CASES = {
+    "render_d": (32, 32),      # both heads on VM grids, slow-fast instance nets sharing one feature
+    "render_e": (16, None),    # semantic grid (16 comps), instance MLP, no slow net, semantic_weight_mode none
+    "render_f": (None, 32),    # instGRIDsemMLP: semantic MLP, instance grid
+}
+RENDER_CASES += [
+    ("render_d", (18, 20, 16), 5, 3, 40, True, True),
+    ("render_e", (16, 18, 20), 4, 4, 48, False, False),
+    ("render_f", (20, 16, 18), 3, 3, 33, True, False),
+]
 
 
 def case_rays(seed: int) -> torch.Tensor:
@@ -56,12 +68,15 @@ def grad_digest(g: torch.Tensor) -> np.ndarray:
 
 def render_case(name, grid, n_cls, n_ins, n_samples, softmax, slow_fast, seed):
     ref = refload.load()
-    params = syn.make_field_params(seed, grid, n_cls, n_ins, slow_fast=slow_fast)
+    sem_grid, ins_grid = GRID_CASES.get(name, (None, None))
+    params = syn.make_field_params(seed, grid, n_cls, n_ins, slow_fast=slow_fast, sem_grid_comps=sem_grid,
+                                   ins_grid_comps=ins_grid)
     aabb = syn.default_aabb()
     if name == "render_c":
         aabb = torch.tensor([[-0.9, -0.8, -1.0], [1.0, 0.7, 0.85]])
     ratio = orc.ratio_for_samples(aabb, grid, n_samples)
-    model = refload.build_model(params, grid, n_cls, n_ins, slow_fast, softmax)
+    model = refload.build_model(params, grid, n_cls, n_ins, slow_fast, softmax, sem_grid_comps=sem_grid,
+                                ins_grid_comps=ins_grid)
     rend = refload.build_renderer(aabb, grid, softmax, True, 0.5)
     rend.update_step_ratio(ratio)
     assert rend.n_samples == n_samples, (rend.n_samples, n_samples)
@@ -70,7 +85,8 @@ def render_case(name, grid, n_cls, n_ins, n_samples, softmax, slow_fast, seed):
     assert cfg.n_samples == n_samples and torch.equal(cfg.step_size, rend.step_size)
     rays = case_rays(seed + 1)
     fx = dict(seed=seed, grid=np.array(grid), n_cls=n_cls, n_ins=n_ins, n_samples=n_samples,
-              softmax=int(softmax), slow_fast=int(slow_fast), aabb=t2n(aabb), step_ratio=ratio,
+              softmax=int(softmax), slow_fast=int(slow_fast), sem_grid=int(sem_grid or 0), ins_grid=int(ins_grid or 0),
+              aabb=t2n(aabb), step_ratio=ratio,
               step_size=t2n(rend.step_size), inv_extent=t2n(rend.inv_box_extent), units=t2n(rend.units),
               params_checksum=syn.params_checksum(params), rays=t2n(rays))
 
@@ -335,15 +351,65 @@ def epoch_cases():
     print("epoch (bbox / shrink / upsample / adam): ok")
 
 
+def grid_epoch_case():
+    """Grid-mode heads through the parameter-only paths: total_tv_loss with semantic / instance planes AND lines
+    (tensoRF.py:260-290), shrink and upsample_volume_grid of all four factor sets (tensoRF.py:158-197)."""
+    ref = refload.load()
+    grid, seed = (12, 16, 14), 71
+    params = syn.make_field_params(seed, grid, 4, 3, sem_grid_comps=32, ins_grid_comps=32)
+    model = refload.build_model(params, grid, 4, 3, sem_grid_comps=32, ins_grid_comps=32)
+    tv = ref.loss.TVLoss()
+    cfgns = type("C", (), dict(late_semantic_optimization=1, instance_optimization_epoch=4, lambda_tv_density=0.1,
+                               lambda_tv_appearance=0.01, lambda_tv_semantics=0.02, lambda_tv_instances=0.02))()
+    tot = model.total_tv_loss(tv, cfgns, 5)
+    tot.backward()
+    pq = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    tot_o = orc.total_tv_loss(pq)
+    tot_o.backward()
+    assert torch.allclose(tot.detach(), tot_o.detach(), rtol=1e-6)
+    fx = dict(seed=seed, grid=np.array(grid), tv_total=t2n(tot), tv_early=t2n(model.total_tv_loss(tv, cfgns, 2)))
+    for k in ("semantic_plane.1", "semantic_line.0", "instance_plane.2", "instance_line.1"):
+        g = dict(model.named_parameters())[k].grad
+        assert torch.allclose(g, pq[k].grad, rtol=1e-5, atol=1e-10), k
+        fx[f"tv_grad/{k}"] = t2n(g)
+    t_l, b_r = torch.tensor([1, 2, 0]), torch.tensor([11, 15, 13])
+    with torch.no_grad():
+        model.shrink(t_l, b_r)
+    shr = orc.shrink_params(params, t_l, b_r)
+    sd = model.state_dict()
+    for k in shr:
+        assert torch.equal(sd[k], shr[k]), k
+    res = (17, 21, 19)
+    model.upsample_volume_grid(res)
+    ups = orc.upsample_params(shr, res)
+    sd = model.state_dict()
+    for k in ups:
+        assert torch.equal(sd[k], ups[k]), k
+    fx.update(t_l=t2n(t_l), b_r=t2n(b_r), res=np.array(res),
+              up_digest=np.array([float(ups[k].double().sum()) for k in sorted(ups) if "plane" in k or "line" in k]),
+              up_semantic_plane0=t2n(ups["semantic_plane.0"][:, :4]), up_instance_line2=t2n(ups["instance_line.2"]))
+    np.savez_compressed(os.path.join(OUT, "grid_epoch.npz"), **fx)
+    print("grid_epoch (tv / shrink / upsample with semantic + instance grids): ok")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    ray_cases()
-    distloss_case()
-    loss_cases()
-    epoch_cases()
+    only = set(sys.argv[1:])          # e.g. `python -m oracle.make_golden render_d grid_epoch`: regenerate just these
+    want = lambda n: not only or n in only
+    if want("rays"):
+        ray_cases()
+    if want("distloss"):
+        distloss_case()
+    if want("losses"):
+        loss_cases()
+    if want("epoch"):
+        epoch_cases()
+    if want("grid_epoch"):
+        grid_epoch_case()
     for i, (name, grid, c, d, s, sm, sf) in enumerate(RENDER_CASES):
-        render_case(name, grid, c, d, s, sm, sf, seed=40 + i)
+        if want(name):
+            render_case(name, grid, c, d, s, sm, sf, seed=40 + i)
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"fixtures: {tot / 1e6:.2f} MB in {OUT}")
 

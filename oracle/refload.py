@@ -93,15 +93,15 @@ def load():
 
 
 def build_model(params, grid_dim, num_classes, max_instances, slow_fast=True, semantic_softmax=True,
-                pe_sem=0, pe_ins=0):
+                pe_sem=0, pe_ins=0, sem_grid_comps=None, ins_grid_comps=None):
     """Reference TensorVMSplit built like trainer/train_panopli_tensorf.py:55-65, weights from ``params``."""
     ref = load()
     model = ref.tensorf.TensorVMSplit(
-        list(grid_dim), num_semantics_comps=(32, 32, 32), num_instance_comps=(32, 32, 32),
+        list(grid_dim), num_semantics_comps=(sem_grid_comps or 32,) * 3, num_instance_comps=(ins_grid_comps or 32,) * 3,
         num_semantic_classes=num_classes,
         dim_feature_instance=2 * max_instances if slow_fast else max_instances,
         output_mlp_semantics=torch.nn.Softmax(dim=-1) if semantic_softmax else torch.nn.Identity(),
-        use_semantic_mlp=True, use_instance_mlp=True, use_feature_reg=False,
+        use_semantic_mlp=not sem_grid_comps, use_instance_mlp=not ins_grid_comps, use_feature_reg=False,
         use_distilled_features_semantic=False, use_distilled_features_instance=False,
         pe_sem=pe_sem, pe_ins=pe_ins, slow_fast_mode=slow_fast, use_proj=False)
     missing, unexpected = model.load_state_dict({k: v.clone() for k, v in params.items()}, strict=True)

@@ -8,7 +8,15 @@ from contrastive_lift_b200 import synthetic as syn
 from oracle import clift_oracle as orc
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-RENDER_CASES = ("render_a", "render_b", "render_c")
+MLP_CASES = ("render_a", "render_b", "render_c")
+GRID_CASES = ("render_d", "render_e", "render_f")      # grid-mode semantic / instance heads (allgrid.yaml family)
+RENDER_CASES = MLP_CASES + GRID_CASES
+
+
+def grid_comps(fx):
+    """(semantic grid comps, instance grid comps) of a fixture; None = that head is an MLP on xyz."""
+    g = lambda k: (int(fx[k]) or None) if k in fx.files else None
+    return g("sem_grid"), g("ins_grid")
 
 
 def load(name):
@@ -17,8 +25,9 @@ def load(name):
 
 def render_inputs(fx):
     grid = tuple(int(v) for v in fx["grid"])
+    sem_grid, ins_grid = grid_comps(fx)
     params = syn.make_field_params(int(fx["seed"]), grid, int(fx["n_cls"]), int(fx["n_ins"]),
-                                   slow_fast=bool(fx["slow_fast"]))
+                                   slow_fast=bool(fx["slow_fast"]), sem_grid_comps=sem_grid, ins_grid_comps=ins_grid)
     chk = syn.params_checksum(params)
     assert abs(chk - float(fx["params_checksum"])) <= 1e-9 * abs(chk), "numpy RNG stream drifted; regenerate fixtures"
     aabb = torch.from_numpy(fx["aabb"])

@@ -192,3 +192,41 @@ def test_assign_clusters_matches_reference_bookkeeping():
     labels += 1
     assert got.shape == (n_img, n_pix, labels.max() + 1)
     assert float((got.argmax(-1).view(-1).numpy() != labels).mean()) < 5e-3
+
+
+def test_grid_heads_tv_shrink_upsample_golden():
+    """Grid-mode heads (allgrid.yaml family): TV over semantic / instance planes AND lines, shrink and upsample of all
+    four factor sets, against the reference-generated fixture."""
+    fx = gu.load("grid_epoch")
+    grid = tuple(int(v) for v in fx["grid"])
+    params = syn.make_field_params(int(fx["seed"]), grid, 4, 3, sem_grid_comps=32, ins_grid_comps=32)
+    model, rend = gpu.build(params, grid, 4, 3, True, True, syn.default_aabb(), 0.5, sem_grid=32, ins_grid=32)
+
+    class Cfg:
+        late_semantic_optimization, instance_optimization_epoch = 1, 4
+        lambda_tv_density, lambda_tv_appearance, lambda_tv_semantics, lambda_tv_instances = 0.1, 0.01, 0.02, 0.02
+
+    early = model.total_tv_loss(None, Cfg, 2)
+    assert abs(float(early) - float(fx["tv_early"])) < 1e-5 * abs(float(fx["tv_early"]))
+    tot = model.total_tv_loss(None, Cfg, 5)
+    assert abs(float(tot) - float(fx["tv_total"])) < 1e-5 * abs(float(fx["tv_total"]))
+    tot.backward()
+    named = dict(model.named_parameters())
+    for k in ("semantic_plane.1", "semantic_line.0", "instance_plane.2", "instance_line.1"):
+        assert gpu.rel_err(named[k].grad, tn(fx[f"tv_grad/{k}"])) < 1e-5, k
+    t_l, b_r, res = tn(fx["t_l"]), tn(fx["b_r"]), [int(v) for v in fx["res"]]
+    model.shrink(t_l, b_r)
+    shr = orc.shrink_params(params, t_l, b_r)
+    sd = model.state_dict()
+    for k in ("semantic_plane.2", "semantic_line.1", "instance_plane.0", "instance_line.2"):
+        assert torch.equal(sd[k].cpu(), shr[k]), k
+    model.upsample_volume_grid(res)
+    ups = orc.upsample_params(shr, res)
+    sd = model.state_dict()
+    worst = max(gpu.rel_err(sd[k], ups[k]) for k in ups if "plane" in k or "line" in k)
+    assert worst < 1e-6, worst
+    # the resized grid-mode model renders
+    rend.update_step_size(tuple(res))
+    with torch.no_grad():
+        out = rend(model, syn.random_rays(3, 64).cuda(), 1.0, False, False)
+    assert all(torch.isfinite(o).all() for o in out[:4])

@@ -27,8 +27,9 @@ def tn(x):
 def case(name):
     fx = gu.load(name)
     params, cfg, rays = gu.render_inputs(fx)
+    sem_grid, ins_grid = gu.grid_comps(fx)
     model, rend = gpu.build(params, cfg.grid_dim, int(fx["n_cls"]), int(fx["n_ins"]), bool(fx["slow_fast"]),
-                            bool(fx["softmax"]), cfg.aabb, float(fx["step_ratio"]))
+                            bool(fx["softmax"]), cfg.aabb, float(fx["step_ratio"]), sem_grid=sem_grid, ins_grid=ins_grid)
     assert rend.n_samples == int(fx["n_samples"])
     assert float(rend.step_size) == float(fx["step_size"])
     return fx, params, cfg, rays, model, rend
@@ -97,6 +98,11 @@ def test_density_matches_reference(name):
 def test_render_inference_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
     rend.head_path = path
+    if name in gu.GRID_CASES and path != L.HEADS_FMA:
+        # grid-mode heads run on the FP32-FMA kernels: an explicit tensor path is refused, AUTO picks FMA
+        with pytest.raises(L.CliftError), torch.no_grad():
+            rend(model, rays.cuda(), 1.0, False, False)
+        rend.head_path = L.HEADS_AUTO
     with torch.no_grad():
         rgb, sem, ins, depth, feats, dist = rend(model, rays.cuda(), 1.0, False, False)
     assert feats.shape == (1, 1) and rgb.grad_fn is None
@@ -159,7 +165,7 @@ def test_render_training_forward_rng_parity(name, tag, seed):
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
 def test_instance_and_segment_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
-    rend.head_path = path
+    rend.head_path = L.HEADS_AUTO if name in gu.GRID_CASES and path != L.HEADS_FMA else path
     with torch.no_grad():
         torch.manual_seed(11)
         ins, pts = rend.forward_instance_feature(model, rays.cuda(), 1.0, True)
@@ -213,7 +219,7 @@ def test_instance_pass_gradients_reach_only_instance_head(name):
     oi, _ = orc.render_instance_feature(p, cfg, rays, tn(fx["insf_jitter"]))
     (oi * w.cpu()).sum().backward()
     for k, prm in model.named_parameters():
-        if k.startswith("render_instance_mlp"):
+        if k.startswith(("render_instance_mlp", "instance_plane", "instance_line", "instance_basis_mat")):
             assert gpu.rel_err(prm.grad, p[k].grad) < 2e-3, k
         else:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k

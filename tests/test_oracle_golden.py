@@ -223,3 +223,44 @@ def test_bbox_shrink_live_reference():
         rend.update_bbox_aabb_and_shrink(model)
     assert torch.equal(rend.bbox_aabb, new_aabb)
     assert rend.grid_dim.tolist() == (b_r - t_l).tolist()
+
+
+# ---- grid-mode heads (allgrid.yaml family): parameter-only paths ------------------------------------------
+def test_grid_heads_tv_shrink_upsample_golden():
+    fx = gu.load("grid_epoch")
+    grid = tuple(int(v) for v in fx["grid"])
+    params = syn.make_field_params(int(fx["seed"]), grid, 4, 3, sem_grid_comps=32, ins_grid_comps=32)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    tot = orc.total_tv_loss(p)
+    assert torch.allclose(tot.detach(), tn(fx["tv_total"]), rtol=1e-6)
+    # epoch 2 of the fixture: past late_semantic_optimization (1), before instance_optimization_epoch (4)
+    early = orc.total_tv_loss(params, lambda_instances=0.0)
+    assert torch.allclose(early, tn(fx["tv_early"]), rtol=1e-6)
+    tot.backward()
+    for k in ("semantic_plane.1", "semantic_line.0", "instance_plane.2", "instance_line.1"):
+        assert torch.allclose(p[k].grad, tn(fx[f"tv_grad/{k}"]), rtol=1e-5, atol=1e-10), k
+    shr = orc.shrink_params(params, tn(fx["t_l"]), tn(fx["b_r"]))
+    ups = orc.upsample_params(shr, [int(v) for v in fx["res"]])
+    digest = np.array([float(ups[k].double().sum()) for k in sorted(ups) if "plane" in k or "line" in k])
+    assert np.allclose(digest, fx["up_digest"], rtol=1e-12)
+    assert torch.equal(ups["semantic_plane.0"][:, :4], tn(fx["up_semantic_plane0"]))
+    assert torch.equal(ups["instance_line.2"], tn(fx["up_instance_line2"]))
+
+
+def test_grid_head_model_mirrors_reference_layout():
+    """Host mirror in grid mode: same state_dict keys / shapes as the parameter dict the reference loads (no GPU needed)."""
+    import contrastive_lift_b200 as cl
+    grid = (8, 10, 12)
+    for sem_grid, ins_grid, slow_fast in ((32, 32, True), (16, None, False), (None, 32, False)):
+        params = syn.make_field_params(5, grid, 4, 3, slow_fast=slow_fast, sem_grid_comps=sem_grid, ins_grid_comps=ins_grid)
+        model = cl.TensorVMSplit(list(grid), num_semantics_comps=(sem_grid or 32,) * 3, num_instance_comps=(ins_grid or 32,) * 3,
+                                 num_semantic_classes=4, dim_feature_instance=6 if slow_fast else 3,
+                                 use_semantic_mlp=not sem_grid, use_instance_mlp=not ins_grid, slow_fast_mode=slow_fast)
+        res = model.load_state_dict(params, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        names = {n for g in model.get_optimizable_parameters(1e-2, 1e-3) for p in g["params"]
+                 for n, q in model.named_parameters() if q is p}
+        assert ("semantic_plane.0" in names) == bool(sem_grid) and "render_semantic_mlp.mlp.0.weight" in names
+        ins_names = {n for g in model.get_optimizable_instance_parameters(1e-2, 1e-3) for p in g["params"]
+                     for n, q in model.named_parameters() if q is p}
+        assert ("instance_basis_mat.weight" in ins_names) == bool(ins_grid)
