@@ -38,13 +38,16 @@ def render_inputs(fx):
     return params, cfg, rays
 
 
-def train_loss(out, fx, tag):
-    """The scalar the fixtures' gradients were taken of (oracle/make_golden.py: loss_fn)."""
+def train_loss(out, fx, tag, keep=None):
+    """The scalar the fixtures' gradients were taken of (oracle/make_golden.py: loss_fn).  ``keep`` (bool per ray)
+    drops the per-ray terms of the other rays (the distortion term, which has no activity threshold, stays whole)."""
     tgt = torch.from_numpy(fx[f"{tag}_tgt_rgb"]).to(out[0].device)
     probs = torch.from_numpy(fx[f"{tag}_probs"]).to(out[0].device)
     w_ins = torch.from_numpy(fx[f"{tag}_w_ins"]).to(out[0].device)
-    ce = -(probs * torch.log_softmax(out[1], -1)).sum(-1).mean()
-    return ((out[0] - tgt) ** 2).mean() + 0.37 * out[5] + 0.1 * ce + 0.05 * (out[2] * w_ins).sum(-1).mean()
+    k = torch.ones(out[0].shape[0], device=out[0].device) if keep is None else keep.to(out[0].device).float()
+    ce = (-(probs * torch.log_softmax(out[1], -1)).sum(-1) * k).mean()
+    return ((((out[0] - tgt) ** 2) * k[:, None]).mean() + 0.37 * out[5] + 0.1 * ce
+            + 0.05 * ((out[2] * w_ins).sum(-1) * k).mean())
 
 
 def grad_digest(g):

@@ -23,3 +23,24 @@ def rel_err(got, ref):
     ref = ref.to(got.device)
     denom = ref.abs().max().clamp_min(1e-12)
     return float((got - ref).abs().max() / denom)
+
+
+def flip_risk(params, cfg, rays, jitter, margin=2e-3):
+    """Per-ray count of samples whose reference weight sits within `margin` (relative) of raymarch_weight_thres.
+    Such a sample may land on the other side of `weight > thres` (renderer:103) under fp32 reassociation of the
+    density sum; the head outputs of its ray then differ by up to thres * |head output| per flipped sample.  Tests
+    compare those rays with that explicit allowance instead of the plain 1e-4 bound."""
+    from oracle import clift_oracle as orc
+    with torch.no_grad():
+        w = orc._march(params, cfg, rays, jitter)[6]
+    return ((w - cfg.weight_thres).abs() < margin * cfg.weight_thres).sum(-1)
+
+
+def rel_err_rows(got, ref, rows):
+    """rel_err restricted to the rays selected by the bool mask `rows` (scale = max |ref| over ALL rays)."""
+    ref = ref.to(got.device)
+    denom = ref.abs().max().clamp_min(1e-12)
+    rows = rows.to(got.device)
+    if not bool(rows.any()):
+        return 0.0
+    return float((got[rows] - ref[rows]).abs().max() / denom)

@@ -153,12 +153,22 @@ def test_render_training_forward_rng_parity(name, tag, seed):
     torch.manual_seed(seed)
     with torch.no_grad():
         rgb, sem, ins, depth, _, dist = rend(model, rays.cuda(), 1.0, False, True)
-    assert gpu.rel_err(rgb, tn(fx[f"{tag}_rgb"])) < REL
-    assert gpu.rel_err(ins, tn(fx[f"{tag}_ins"])) < REL
-    assert gpu.rel_err(depth, tn(fx[f"{tag}_depth"])) < REL
-    assert gpu.rel_err(dist, tn(fx[f"{tag}_dist"])) < REL
+    # rays with a sample sitting on the activity threshold (|w - 1e-4| < 2e-7) may flip it: they get the explicit
+    # allowance of thres * |head output| per such sample, every other ray the plain 1e-4 bound
+    risk = gpu.flip_risk(params, cfg, rays, tn(fx[f"{tag}_jitter"]))
+    safe, n_risky = risk == 0, int((risk > 0).sum())
+    assert n_risky <= 4, n_risky
+    softmax = bool(fx["softmax"])
     ref_sem = tn(fx[f"{tag}_sem"])
-    assert gpu.rel_err(sem.exp() if bool(fx["softmax"]) else sem, ref_sem.exp() if bool(fx["softmax"]) else ref_sem) < REL
+    pairs = [(rgb, tn(fx[f"{tag}_rgb"])), (ins, tn(fx[f"{tag}_ins"])),
+             (sem.exp() if softmax else sem, ref_sem.exp() if softmax else ref_sem)]
+    for got, ref in pairs:
+        assert gpu.rel_err_rows(got, ref, safe) < REL
+        if n_risky:
+            allow = REL + float(risk.max()) * cfg.weight_thres * 4.0      # head outputs of these fixtures stay below 4
+            assert gpu.rel_err_rows(got, ref, ~safe) < allow
+    assert gpu.rel_err(depth, tn(fx[f"{tag}_depth"])) < REL            # depth / dist-reg sum every weight: no threshold
+    assert gpu.rel_err(dist, tn(fx[f"{tag}_dist"])) < REL
 
 
 @pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR, L.HEADS_TENSOR16], ids=["fma", "tcgen05", "tcgen05_f16"])
@@ -184,6 +194,23 @@ def test_render_training_gradients_golden(name, tag, seed):
     torch.manual_seed(seed)
     out = rend(model, rays.cuda(), 1.0, False, True)
     assert out[0].grad_fn is not None and out[3].grad_fn is None       # depth carries no grad (renderer:173)
+    risk = gpu.flip_risk(params, cfg, rays, tn(fx[f"{tag}_jitter"]))
+    if int((risk > 0).sum()) > 0:
+        # A sample sitting on the activity threshold (|w - 1e-4| < 2e-7) may flip; in softmax mode its ray's semantic
+        # gradient carries a 1/opacity factor, so one flip moves factor gradients by percents.  Those rays' per-ray loss
+        # terms are dropped on both sides and the reference gradient comes from the reference-pinned oracle instead of
+        # the stored digest (same scalar otherwise).
+        keep = risk == 0
+        assert int((~keep).sum()) <= 4
+        gu.train_loss(out, fx, tag, keep).backward()
+        p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+        o2 = orc.render_forward(p, cfg, rays, tn(fx[f"{tag}_jitter"]), bool(fx[f"{tag}_coin"]))
+        gu.train_loss(o2, fx, tag, keep).backward()
+        for k, prm in model.named_parameters():
+            g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+            ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
+            assert gpu.rel_err(g, ref) < 2e-3, k
+        return
     loss = gu.train_loss(out, fx, tag)
     assert abs(float(loss) - float(fx[f"{tag}_loss"])) < 1e-3 * abs(float(fx[f"{tag}_loss"]))
     loss.backward()
