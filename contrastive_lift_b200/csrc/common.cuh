@@ -60,11 +60,22 @@ __host__ __device__ __forceinline__ int mode_a(int m) { return m == 2 ? 1 : 0; }
 __host__ __device__ __forceinline__ int mode_b(int m) { return m == 0 ? 1 : 2; }
 __host__ __device__ __forceinline__ int mode_v(int m) { return 2 - m; }
 
-// Per-tile activation stash of the training path.  Every row is CLIFT_TILE floats (one value per record of
-// the tile); a tile's rows are contiguous.  MLP ids: 0 semantic, 1 instance fast, 2 instance slow, 3 rgb, 4 basis.
-//   a_off[id][l] : rows holding the INPUT of layer l (k_pad(dims[l]) rows, zero padded)
-//   z_off[id][l] : rows holding dL/d(pre-activation OUTPUT of layer l) (n_pad(dims[l+1]) rows, zero padded)
-//   prob_off     : softmax probabilities of the semantic head (n_pad(C) rows)
+// Per-tile activation stash of the training path: blocks of rows x CLIFT_TILE floats (one value per record of the tile),
+// a tile's blocks back to back.  MLP ids below.
+//   a_off[id][l] : first row of the block holding the INPUT of layer l (k_pad(dims[l]) rows, zero padded)
+//   z_off[id][l] : first row of the block holding dL/d(pre-activation OUTPUT of layer l) (n_pad(dims[l+1]) rows, zero padded)
+//   prob_off     : softmax probabilities of the semantic head (n_pad(C) rows reserved, C written)
+// Block layout: R rows x 128 records are stored as 8 groups of 16 records, each group row-major [R][16 floats], so the
+// tensor-core weight-gradient kernel (wgrad_tc.cu) streams one 16-record group of ALL rows as one contiguous R*64-byte
+// piece (sequential DRAM reads instead of 64-byte pieces at a 512-byte stride).
+// stash_idx = float offset of element (row, record m) inside a block; stash_idx4 = float4 offset of the q-th float4 of a row.
+__host__ __device__ __forceinline__ size_t stash_idx(int R, int row, int m) {
+    return ((size_t)(m >> 4) * R + row) * 16 + (m & 15);
+}
+__host__ __device__ __forceinline__ size_t stash_idx4(int R, int row, int q) {
+    return ((size_t)(q >> 2) * R + row) * 4 + (q & 3);
+}
+
 // stack ids: 0 semantic mlp, 1 instance fast, 2 instance slow, 3 rgb mlp, 4 appearance basis,
 //            5 semantic-grid basis, 6 instance-grid basis (grid-mode heads only)
 constexpr int kStashIds = 7;

@@ -137,11 +137,11 @@ __device__ __forceinline__ void run_layer(const Smem& sm, const float* wt, const
         mlp_layer<4>(sm, wt, bias, kp, relu);
 }
 
-// rows [0,rows) of act -> global rows (coalesced: one row = kTile consecutive floats)
+// rows [0,rows) of act -> a stash block of `rows` rows (stash_idx layout: a warp writes one row as 8 pieces of 64 bytes)
 __device__ __forceinline__ void store_rows(const Smem& sm, float* __restrict__ dst, int rows) {
     float4* d4 = reinterpret_cast<float4*>(dst);
     const float4* s4 = reinterpret_cast<const float4*>(sm.act);
-    for (int i = threadIdx.x; i < rows * (kTile / 4); i += kThreads) d4[i] = s4[i];
+    for (int i = threadIdx.x; i < rows * (kTile / 4); i += kThreads) d4[stash_idx4(rows, i >> 5, i & 31)] = s4[i];
 }
 
 // `stash` (may be null) = this tile's A-stash base; a_off = the MLP's row offsets: the INPUT of every layer is saved.
@@ -451,7 +451,7 @@ __device__ __forceinline__ void mlp_backward(const Smem& sm, const clift_mlp& ml
             float4* d4 = reinterpret_cast<float4*>(sm.act);
             const int rows = (n_in + 15) & ~15;
             for (int i = threadIdx.x; i < rows * (kTile / 4); i += kThreads) {
-                const float4 a = a4[i];
+                const float4 a = a4[stash_idx4(rows, i >> 5, i & 31)];
                 float4 d = d4[i];
                 d.x = a.x > 0.0f ? d.x : 0.0f;
                 d.y = a.y > 0.0f ? d.y : 0.0f;
@@ -570,12 +570,12 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                 const float w = sm.pos[tid].w;
                 const float* g = P.g_ray + (int64_t)max(ray, 0) * P.ray_stride + P.off_sem;
                 if (P.softmax) {
-                    const float* pr = sa + (size_t)P.lay.prob_off * kTile + tid;
+                    const float* pr = sa + (size_t)P.lay.prob_off * kTile;      // block of n_cls rows (store_rows in the forward)
                     float dot = 0.0f;
-                    for (int c = 0; c < P.n_cls; ++c) dot += (ray >= 0 ? w * g[c] : 0.0f) * pr[(size_t)c * kTile];
+                    for (int c = 0; c < P.n_cls; ++c) dot += (ray >= 0 ? w * g[c] : 0.0f) * pr[stash_idx(P.n_cls, c, tid)];
                     for (int c = 0; c < P.n_cls; ++c) {
                         const float d = ray >= 0 ? w * g[c] : 0.0f;
-                        sm.act[(size_t)c * kTile + tid] = pr[(size_t)c * kTile] * (d - dot);
+                        sm.act[(size_t)c * kTile + tid] = pr[stash_idx(P.n_cls, c, tid)] * (d - dot);
                     }
                 } else {
                     for (int c = 0; c < P.n_cls; ++c) sm.act[(size_t)c * kTile + tid] = ray >= 0 ? w * g[c] : 0.0f;
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                         const float4* z4 = reinterpret_cast<const float4*>(zrow);
                         float4* d4 = reinterpret_cast<float4*>(sm.act);
                         for (int i = tid; i < 64 * (kTile / 4); i += kThreads) {
-                            const float4 z = z4[i];
+                            const float4 z = z4[stash_idx4(64, i >> 5, i & 31)];
                             float4 d = d4[i];
                             d.x += z.x, d.y += z.y, d.z += z.z, d.w += z.w;
                             d4[i] = d;
@@ -647,6 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
             const int A = P.dim_app, pf = P.pe_feat;
             const int o_sf = A + 3, o_cf = o_sf + A * pf;
             const float* in = sa + (size_t)P.lay.a_off[3][0] * kTile;
+            const int in_rows = (P.rgb.dims[0] + 15) & ~15;      // rows of that stash block
             // dfeat goes to the spare rows [192, 192+A) first (the MLP input occupies rows < 192), then down to [0, A)
             float* spare = sm.act + (size_t)192 * kTile;
             for (int idx = tid; idx < A * kTile; idx += kThreads) {
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                 float v = sm.act[(size_t)a * kTile + m];
                 for (int j = 0; j < pf; ++j) {
                     const int rs = o_sf + a * pf + j, rc = o_cf + a * pf + j;
-                    const float sv = in[(size_t)rs * kTile + m], cv = in[(size_t)rc * kTile + m];
+                    const float sv = in[stash_idx(in_rows, rs, m)], cv = in[stash_idx(in_rows, rc, m)];
                     v += (float)(1 << j) * (cv * sm.act[(size_t)rs * kTile + m] - sv * sm.act[(size_t)rc * kTile + m]);
                 }
                 spare[idx] = v;
@@ -706,13 +707,13 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const __grid_constant__ Wgra
         const long long tile = split + (s / (kTile / kWgSlab)) * P.splits;
         const int m0 = (int)(s % (kTile / kWgSlab)) * kWgSlab;
         const int buf = (int)(s & 1);
-        const float* ga = P.a + tile * P.a_tile_stride + m0;
-        const float* gz = P.z + tile * P.z_tile_stride + m0;
+        const float* ga = P.a + tile * P.a_tile_stride;      // stash blocks of K / N rows (stash_idx layout)
+        const float* gz = P.z + tile * P.z_tile_stride;
         // 64 rows x 8 chunks of 16 B per operand = 512 chunks; 256 threads -> 2 each per operand
         for (int c = tid; c < 64 * (kWgSlab / 4); c += 256) {
             const int r = c / (kWgSlab / 4), q = c % (kWgSlab / 4);
-            if (kb + r < P.K) cp_async16(&sA[buf][r * kWgPitch + q * 4], ga + (size_t)(kb + r) * kTile + q * 4);
-            if (nb + r < P.N) cp_async16(&sZ[buf][r * kWgPitch + q * 4], gz + (size_t)(nb + r) * kTile + q * 4);
+            if (kb + r < P.K) cp_async16(&sA[buf][r * kWgPitch + q * 4], ga + stash_idx(P.K, kb + r, m0 + q * 4));
+            if (nb + r < P.N) cp_async16(&sZ[buf][r * kWgPitch + q * 4], gz + stash_idx(P.N, nb + r, m0 + q * 4));
         }
         cp_async_commit();
     };
@@ -880,16 +881,34 @@ int launch_heads_forward(const clift_render_cfg* cfg, const clift_field* field, 
 
 namespace clift {
 
+// weight gradient of layer l of stack `id`: queued for the tensor-core kernel (wgrad_tc.cu) when its shape qualifies, else
+// one FP32-FMA split-K launch (the K = 16 xyz input layers)
+struct WgradQueue {
+    WgradTcItem items[kWgradTcMaxLayers];
+    int n = 0;
+    bool use_tc = true;
+};
+
 static int launch_wgrad(const Workspace& ws, const StashLayout& lay, int id, int l, const clift_mlp* m, float* out, int64_t cap,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, WgradQueue* q = nullptr) {
     if (!out) return CLIFT_OK;
+    const int K = k_pad(m->dims[l]), N = n_pad(m->dims[l + 1]);
+    if (q && q->use_tc && q->n < kWgradTcMaxLayers && wgrad_tc_eligible(K, N)) {
+        WgradTcItem& it = q->items[q->n++];
+        it.a_row = lay.a_off[id][l];
+        it.z_row = lay.z_off[id][l];
+        it.K = K;
+        it.N = N;
+        it.out = out;
+        return CLIFT_OK;
+    }
     WgradParams W;
     W.a = ws.stash_a + (size_t)lay.a_off[id][l] * kTile;
     W.z = ws.stash_z + (size_t)lay.z_off[id][l] * kTile;
     W.a_tile_stride = (long long)lay.a_rows * kTile;
     W.z_tile_stride = (long long)lay.z_rows * kTile;
-    W.K = k_pad(m->dims[l]);
-    W.N = n_pad(m->dims[l + 1]);
+    W.K = K;
+    W.N = N;
     W.out = out;
     W.stats = reinterpret_cast<const unsigned long long*>(ws.stats);
     W.cap = cap;
@@ -1051,29 +1070,35 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
     }
 #undef CLIFT_HEADS_BWD_CASE
     CLIFT_AFTER_LAUNCH("heads_backward_kernel");
-    // weight gradients, one split-K GEMM per layer
+    // weight gradients: one tensor-core launch for every layer with K >= 64 (CLIFT_WGRAD_FMA=1: the FP32-FMA kernel for all)
     int rc;
     clift_mlp tmp;
+    WgradQueue queue;
+    {
+        const char* e = getenv("CLIFT_WGRAD_FMA");
+        queue.use_tc = !(e && atoi(e) != 0);
+    }
+    WgradQueue* q = &queue;
     if (do_sem) {
         for (int l = 0; l < field->semantic.n_layers; ++l)
-            if ((rc = launch_wgrad(ws, lay, 0, l, &field->semantic, grad->semantic.wt[l], cap, stream))) return rc;
-        if (sg && (rc = launch_wgrad(ws, lay, 5, 0, field_mlp(field, 5, &tmp), grad->semantic_grid.basis, cap, stream))) return rc;
+            if ((rc = launch_wgrad(ws, lay, 0, l, &field->semantic, grad->semantic.wt[l], cap, stream, q))) return rc;
+        if (sg && (rc = launch_wgrad(ws, lay, 5, 0, field_mlp(field, 5, &tmp), grad->semantic_grid.basis, cap, stream, q))) return rc;
     }
     if (do_ins && ig)
-        if ((rc = launch_wgrad(ws, lay, 6, 0, field_mlp(field, 6, &tmp), grad->instance_grid.basis, cap, stream))) return rc;
+        if ((rc = launch_wgrad(ws, lay, 6, 0, field_mlp(field, 6, &tmp), grad->instance_grid.basis, cap, stream, q))) return rc;
     if (do_ins) {
         for (int l = 0; l < field->instance_fast.n_layers; ++l)
-            if ((rc = launch_wgrad(ws, lay, 1, l, &field->instance_fast, grad->instance_fast.wt[l], cap, stream))) return rc;
+            if ((rc = launch_wgrad(ws, lay, 1, l, &field->instance_fast, grad->instance_fast.wt[l], cap, stream, q))) return rc;
         if (field->slow_fast)
             for (int l = 0; l < field->instance_slow.n_layers; ++l)
-                if ((rc = launch_wgrad(ws, lay, 2, l, &field->instance_slow, grad->instance_slow.wt[l], cap, stream))) return rc;
+                if ((rc = launch_wgrad(ws, lay, 2, l, &field->instance_slow, grad->instance_slow.wt[l], cap, stream, q))) return rc;
     }
     if (do_rgb) {
         for (int l = 0; l < field->rgb.n_layers; ++l)
-            if ((rc = launch_wgrad(ws, lay, 3, l, &field->rgb, grad->rgb.wt[l], cap, stream))) return rc;
-        if ((rc = launch_wgrad(ws, lay, 4, 0, field_mlp(field, 4, &tmp), grad->basis, cap, stream))) return rc;
+            if ((rc = launch_wgrad(ws, lay, 3, l, &field->rgb, grad->rgb.wt[l], cap, stream, q))) return rc;
+        if ((rc = launch_wgrad(ws, lay, 4, 0, field_mlp(field, 4, &tmp), grad->basis, cap, stream, q))) return rc;
     }
-    return CLIFT_OK;
+    return launch_wgrad_tc(ws, lay, queue.items, queue.n, cap, stream);
 }
 
 }  // namespace clift

@@ -41,6 +41,17 @@ bool heads_tc16_available(const clift_field* f, int heads);
 int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
                               int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream);
 
+// wgrad_tc.cu: tensor-core (tcgen05 3xTF32) weight gradients over the training stashes, all layers in one launch
+constexpr int kWgradTcMaxLayers = 24;
+struct WgradTcItem {
+    int a_row, z_row;   // first row of the layer's input / dZ inside a tile's A- / Z-stash
+    int K, N;           // k_pad(in), n_pad(out)
+    float* out;         // packed dW^T [K][N]
+};
+bool wgrad_tc_eligible(int K, int N);
+int launch_wgrad_tc(const Workspace& ws, const StashLayout& lay, const WgradTcItem* items, int n_items, int64_t cap,
+                    cudaStream_t stream);
+
 // pack.cu
 int launch_transpose(const float* src, float* dst, int rows, int cols, int dst_rows_pad, int dst_cols_pad, cudaStream_t stream);
 

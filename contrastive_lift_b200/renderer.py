@@ -43,6 +43,9 @@ class _Render(torch.autograd.Function):
     def forward(ctx, renderer, model, rays, jitter, add_bg, heads, want_points, need_grad, *params):
         lib = L.load()
         dev = rays.device
+        # outputs no loss consumes arrive as None in backward (not as zero tensors): the main training pass never uses
+        # instance_map (trainer:154), so its backward skips the instance head like the reference's autograd does
+        ctx.set_materialize_grads(False)
         pk = model.packed(need_grad)
         cfg = renderer._cfg(model, heads)
         B = rays.shape[0]

@@ -82,6 +82,11 @@ def main():
     opt_main = adam(model.get_optimizable_parameters(0.02, 0.001, 1e-8), betas=(0.9, 0.99))
     opt_ins = adam(model.get_optimizable_instance_parameters(0.02, 0.001, using_DINO=True), betas=(0.9, 0.999))
     torch.manual_seed(123)
+    if "--profile-steps" in sys.argv:       # under ncu: a few bare steps, no timing, no CPU leg
+        for _ in range(int(sys.argv[sys.argv.index("--profile-steps") + 1])):
+            gpu_step(model, rend, opt_main, opt_ins, batch)
+        torch.cuda.synchronize()
+        return
     for _ in range(3):
         gpu_step(model, rend, opt_main, opt_ins, batch)
     torch.cuda.synchronize()

@@ -91,3 +91,27 @@ def test_tc16_bound_chain_covers_a_stack():
             assert float(hdr[4]) == float(prev[3].cpu())
         x = x.clamp_min(0)
         prev = buf
+
+
+def test_wgrad_tensor_core_matches_fma_kernel(monkeypatch):
+    """wgrad_tc_kernel (tcgen05 3xTF32 over the training stashes) against the FP32-FMA wgrad kernel on the same forward /
+    backward: every Linear weight gradient within 2e-5 scale-relative (both are fp32-faithful; they differ by summation order)."""
+    import golden_util as gu
+    import gpu_util as gpu
+    for name in ("render_a", "render_d"):
+        fx = gu.load(name)
+        params, cfg, rays = gu.render_inputs(fx)
+        sem_grid, ins_grid = gu.grid_comps(fx)
+        grads = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("CLIFT_WGRAD_FMA", mode)
+            model, rend = gpu.build(params, cfg.grid_dim, int(fx["n_cls"]), int(fx["n_ins"]), bool(fx["slow_fast"]),
+                                    bool(fx["softmax"]), cfg.aabb, float(fx["step_ratio"]), sem_grid=sem_grid, ins_grid=ins_grid)
+            torch.manual_seed(7)
+            out = rend(model, rays.cuda(), 1.0, False, True)
+            gu.train_loss(out, fx, "trn").backward()
+            grads[mode] = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        for k, g in grads["1"].items():
+            if k.endswith(".weight"):
+                err = gpu.rel_err(grads["0"][k], g.cpu())
+                assert err < 2e-5, (name, k, err)
