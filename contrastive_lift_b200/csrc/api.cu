@@ -243,18 +243,22 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         int path = CLIFT_HEADS_FMA;
         const bool grid_heads = ((heads & CLIFT_HEAD_SEMANTIC) && field->semantic_grid.comps) ||
                                 ((heads & CLIFT_HEAD_INSTANCE) && field->instance_grid.comps);
+        const bool tc16_train = save && !grid_heads && heads_tc16_available(field, heads) && heads_tc16_stash_ok(field, heads);
         if (cfg->head_path == CLIFT_HEADS_TENSOR || cfg->head_path == CLIFT_HEADS_TENSOR16) {
-            CLIFT_CHECK_SUPPORTED(!save, "the tensor-core head paths do not record the training stash (use CLIFT_HEADS_AUTO/FMA)");
+            CLIFT_CHECK_SUPPORTED(!save || (cfg->head_path == CLIFT_HEADS_TENSOR16 && tc16_train),
+                                  "this tensor-core head path cannot record the training stash for this field (use CLIFT_HEADS_AUTO/FMA)");
             CLIFT_CHECK_SUPPORTED(!grid_heads, "grid-mode semantic/instance heads run on the FP32-FMA kernels (use CLIFT_HEADS_AUTO/FMA)");
             path = cfg->head_path;
-        } else if (cfg->head_path == CLIFT_HEADS_AUTO && !save && !grid_heads) {
+        } else if (cfg->head_path == CLIFT_HEADS_AUTO && save) {
+            if (tc16_train) path = CLIFT_HEADS_TENSOR16;
+        } else if (cfg->head_path == CLIFT_HEADS_AUTO && !grid_heads) {
             if (heads_tc16_available(field, heads))
                 path = CLIFT_HEADS_TENSOR16;
             else if (heads_tc_available(field, heads))
                 path = CLIFT_HEADS_TENSOR;
         }
         if (path == CLIFT_HEADS_TENSOR16)
-            rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream);
+            rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream, save ? &lay : nullptr);
         else if (path == CLIFT_HEADS_TENSOR)
             rc = launch_heads_forward_tc(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream);
         else

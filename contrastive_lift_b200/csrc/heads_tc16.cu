@@ -428,6 +428,11 @@ struct HeadsParams {
     int pair;                   // 1: CTA pairs (clusters of 2, cta_group::2 MMAs with M = 256): each SM stages half of every weight slab
     int park;                   // 1: the appearance gather runs row-mapped inside the MMA phases of the xyz stacks and parks
                                 //    its fp16 pairs in spare tensor-memory columns (requires !stream: one accumulator buffer)
+    // training forwards (save_for_backward): every layer input is also written, unscaled fp32, to the A-stash the backward
+    // kernels read (heads.cu: StashLayout / stash_idx), the per-record rgb to rec_rgb; null = inference
+    float* stash_a;
+    float* rec_rgb;
+    StashLayout lay;
 };
 
 constexpr uint32_t kParkCol = 256;      // first tensor-memory column of the parked appearance products
@@ -437,9 +442,17 @@ __device__ __forceinline__ void stamp(const HeadsParams& P, int tile_local, int 
 }
 
 // hidden-layer epilogue: D (bias included) -> ReLU -> * e (rescale to the next layer's operand scale) -> fp16 pairs
-__device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0, float* v, float e) {
+// `st_blk` (training): the stash block of the NEXT layer's input (st_rows rows); it gets the unscaled activation D * inv
+__device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0, float* v, float e, float* st_blk, int st_rows,
+                                           float inv) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f) * e;
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+    if (st_blk) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st_blk[stash_idx(st_rows, c0 + i, r.row)] = v[i] * inv;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= e;
     put16(s, r.row, c0, v);
 }
 
@@ -447,7 +460,7 @@ __device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0
 // (3 k-steps) of the next GEMM, which the MMA thread issues as soon as all 384 row threads have arrived on bar_a[j] - the
 // next layer's MMAs (into the other accumulator buffer) overlap the rest of this epilogue.
 __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, uint32_t d, const Gemm& g, float e, bool stream,
-                                                uint32_t leader_bar_a) {
+                                                uint32_t leader_bar_a, float* st_blk = nullptr, int st_rows = 0, float inv = 0.0f) {
     const int n_pad = g.n_pad;
     const int rounds = (n_pad + kRoundCols - 1) / kRoundCols;
     const int c_begin = r.part * 16;
@@ -456,7 +469,7 @@ __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, u
             if (c0 < n_pad) {
                 float v[16];
                 ld_acc16(d, c0, n_pad, g.n_sets, v);
-                relu_put16(s, r, c0, v, e);
+                relu_put16(s, r, c0, v, e, st_blk, st_rows, inv);
             }
             if (stream) arrive_round(s, j, leader_bar_a);
         }
@@ -468,7 +481,7 @@ __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, u
             float v[16];
             tc::tmem_ld16(d + (uint32_t)c0, v);
             tc::tmem_wait_ld();
-            relu_put16(s, r, c0, v, e);
+            relu_put16(s, r, c0, v, e, st_blk, st_rows, inv);
         }
         if (stream) arrive_round(s, j, leader_bar_a);
     }
@@ -490,7 +503,7 @@ __device__ __forceinline__ void epilogue_final(const Smem& s, const RowId& r, ui
 
 // semantic final layer for n_cls <= 32: logits in registers -> softmax -> * w -> scratch[c][row]
 __device__ __forceinline__ void epilogue_semantic32(const Smem& s, const RowId& r, uint32_t d, int n_cls, const Gemm& g, int softmax,
-                                                    float w, float inv) {
+                                                    float w, float inv, float* st_prob = nullptr) {
     if (r.part != 0) return;
     float* scratch = reinterpret_cast<float*>(s.a_hi);
     float v[32];
@@ -513,6 +526,12 @@ __device__ __forceinline__ void epilogue_semantic32(const Smem& s, const RowId& 
         for (int i = 0; i < 32; ++i) {
             v[i] = i < n_cls ? expf(v[i] - mx) : 0.0f;
             tot += v[i];
+        }
+        if (st_prob) {      // training: the softmax backward needs the probabilities
+            const float it = 1.0f / tot;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < n_cls) st_prob[stash_idx(n_cls, i, r.row)] = v[i] * it;
         }
         const float sc = w / tot;
 #pragma unroll
@@ -646,7 +665,8 @@ __device__ __forceinline__ void ldg8_na(const float* p, float4& lo, float4& hi) 
 // Row-mapped gather slice: channels [8 slice, 8 slice + 8) of mode `mode` at this thread's own record, 12 16-byte loads in
 // flight (one 32-byte sector per tap), products scaled and split to fp16 pairs, parked in 8 tensor-memory columns of the
 // record's lane as [4 words hi | 4 words lo] - the image of one 16-byte A_hi chunk and one A_lo chunk.
-__device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, const float4& pm, int slice, float ca, uint32_t park) {
+__device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, const float4& pm, int slice, float ca, uint32_t park,
+                                             float* st_app = nullptr, int row = 0) {
     const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
     const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
     const int W = f.pw[mode], H = f.ph[mode], Ln = f.ll[mode], C = f.comps;
@@ -681,6 +701,13 @@ __device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, co
         fma4(lv, w[v], t1.w1);
         split2(pv.x * lv.x * ca, pv.y * lv.y * ca, words[2 * v], words[4 + 2 * v]);
         split2(pv.z * lv.z * ca, pv.w * lv.w * ca, words[2 * v + 1], words[4 + 2 * v + 1]);
+        if (st_app) {       // training: the basis weight gradient needs the plane*line products (block of 3*C rows)
+            const int k = mode * C + ch + 4 * v, R = 3 * C;
+            st_app[stash_idx(R, k, row)] = pv.x * lv.x;
+            st_app[stash_idx(R, k + 1, row)] = pv.y * lv.y;
+            st_app[stash_idx(R, k + 2, row)] = pv.z * lv.z;
+            st_app[stash_idx(R, k + 3, row)] = pv.w * lv.w;
+        }
     }
     tc::tmem_st8u(park + (uint32_t)(slice * 8), words);
 }
@@ -756,14 +783,26 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         const uint32_t park = r.lane_base + kParkCol + (uint32_t)(r.part * 16 * NV);
         int park_next = 2 * NV;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* st = nullptr;                                   // training: this tile's A-stash
+        auto st_block = [&](int id, int l) { return st ? st + (size_t)P.lay.a_off[id][l] * kRows : nullptr; };
         auto park_slice = [&]() {
-            gather_slice(P.app, r.part, p, park_next, s.sc[g_basis].x, park);
+            gather_slice(P.app, r.part, p, park_next, s.sc[g_basis].x, park, st_block(4, 0), row);
             ++park_next;
         };
-        auto run_hidden = [&](int n_layers) {
+        auto stash_xyz = [&](int id) {                         // layer-0 input of an xyz stack (pe = 0): 16 rows, 3 valid
+            if (st && r.part == 0) {
+                float* b = st_block(id, 0);
+                b[stash_idx(16, 0, row)] = p.x;
+                b[stash_idx(16, 1, row)] = p.y;
+                b[stash_idx(16, 2, row)] = p.z;
+                for (int k = 3; k < 16; ++k) b[stash_idx(16, k, row)] = 0.0f;
+            }
+        };
+        auto run_hidden = [&](int n_layers, int id) {
             for (int l = 0; l + 1 < n_layers; ++l, ++gi) {
                 wait_d();
-                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a);
+                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a, st_block(id, l + 1),
+                                P.g[gi].n_pad, s.sc[gi].y);
                 if (threadIdx.x == 64) stamp(P, tl, gi + 1, 1);
                 if (park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice();   // hides under that GEMM
             }
@@ -788,6 +827,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             p = p_next;
             const int ray = ray_next;
             fetch(tile + tile_step);
+            st = P.stash_a ? P.stash_a + (size_t)tile * P.lay.a_rows * kRows : nullptr;
             park_next = (P.park && P.n_rgb > 0) ? 0 : 2 * NV;
             if (r.part == 0) {
                 s.ray[row] = ray;
@@ -811,10 +851,12 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             gi = 0;
             if (P.n_sem > 0) {
                 build_xyz(s, r, p, P.pe_sem, s.sc[gi].x);
+                stash_xyz(0);
                 publish(gi);
-                run_hidden(P.n_sem);
+                run_hidden(P.n_sem, 0);
                 if (P.n_cls <= 32) {
-                    epilogue_semantic32(s, r, d, P.n_cls, P.g[gi], P.softmax, p.w, s.sc[gi].y);
+                    epilogue_semantic32(s, r, d, P.n_cls, P.g[gi], P.softmax, p.w, s.sc[gi].y,
+                                        st ? st + (size_t)P.lay.prob_off * kRows : nullptr);
                 } else {
                     epilogue_final(s, r, d, P.n_cls, P.g[gi], s.sc[gi].y);
                     if (r.part == 0) {   // wide heads: softmax over the thread's own column of the scratch
@@ -841,8 +883,9 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 const int width = P.d_ins * (P.slow_fast ? 2 : 1);
                 for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
                     build_xyz(s, r, p, P.pe_ins, s.sc[gi].x);
+                    stash_xyz(1 + net);
                     publish(gi);
-                    run_hidden(P.n_ins);
+                    run_hidden(P.n_ins, 1 + net);
                     epilogue_final(s, r, d, P.d_ins, P.g[gi], s.sc[gi].y * p.w);
                     ++gi;
                     if (threadIdx.x == 64) stamp(P, tl, gi, 6);
@@ -910,6 +953,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 // A warp covers 8 records x 4 consecutive base values, which spreads its 2-byte operand stores over all banks.
                 {
                     const float ca = s.sc[gi].x;
+                    float* st_in = st_block(3, 0);             // training: the rgb MLP input (k_rows rows)
                     const int o_sf = A + 3, o_cf = o_sf + A * pf, o_sd = o_cf + A * pf, o_cd = o_sd + 3 * pv, n_in = o_cd + 3 * pv;
                     const int n_items = ((n_base + 3) >> 2) * 4 * kRows;
                     for (int item = r.rt; item < n_items; item += kRowThreads) {
@@ -923,31 +967,46 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                         put1(s, m, b, x * ca);
                         float sv, cv;
                         __sincosf(x, &sv, &cv);
+                        if (st_in) st_in[stash_idx(k_rows, b, m)] = x;
                         if (nf == 2 && !((ks | kc) & 1)) {      // the shipped pe_feat = pe_view = 2: (f, 2f) pairs are aligned
                             put2(s, m, ks, sv * ca, 2.0f * sv * cv * ca);
                             put2(s, m, kc, cv * ca, (1.0f - 2.0f * sv * sv) * ca);
+                            if (st_in) {
+                                st_in[stash_idx(k_rows, ks, m)] = sv;
+                                st_in[stash_idx(k_rows, ks + 1, m)] = 2.0f * sv * cv;
+                                st_in[stash_idx(k_rows, kc, m)] = cv;
+                                st_in[stash_idx(k_rows, kc + 1, m)] = 1.0f - 2.0f * sv * sv;
+                            }
                             continue;
                         }
                         for (int j = 0; j < nf; ++j) {
                             put1(s, m, ks + j, sv * ca);
                             put1(s, m, kc + j, cv * ca);
+                            if (st_in) {
+                                st_in[stash_idx(k_rows, ks + j, m)] = sv;
+                                st_in[stash_idx(k_rows, kc + j, m)] = cv;
+                            }
                             const float s2 = 2.0f * sv * cv, c2 = 1.0f - 2.0f * sv * sv;
                             sv = s2;
                             cv = c2;
                         }
                     }
-                    for (int item = r.rt; item < (k_rows - n_in) * kRows; item += kRowThreads)
+                    for (int item = r.rt; item < (k_rows - n_in) * kRows; item += kRowThreads) {
                         put1(s, item % kRows, n_in + item / kRows, 0.0f);
+                        if (st_in) st_in[stash_idx(k_rows, n_in + item / kRows, item % kRows)] = 0.0f;
+                    }
                 }
                 if (threadIdx.x == 64) stamp(P, tl, gi, 7);
                 publish(gi);
-                run_hidden(P.n_rgb);
+                run_hidden(P.n_rgb, 3);
                 epilogue_final(s, r, d, 3, P.g[gi], s.sc[gi].y);
                 ++gi;
                 if (r.part == 0)
                     for (int c = 0; c < 3; ++c) {
                         const float x = scratch[(size_t)c * kRows + row];
-                        scratch[(size_t)c * kRows + row] = (1.0f / (1.0f + expf(-x))) * p.w;
+                        const float sig = 1.0f / (1.0f + expf(-x));
+                        if (P.rec_rgb && row < nv) P.rec_rgb[((long long)tile * kRows + row) * 4 + c] = sig;
+                        scratch[(size_t)c * kRows + row] = sig * p.w;
                     }
                 reduce_runs(s, r.rt, 3, P.rgb_raw, 3, 0);
             }
@@ -1131,8 +1190,26 @@ bool heads_tc16_available(const clift_field* f, int heads) {
     return true;
 }
 
+// Training forwards through the tensor-core kernel: possible when every stash block has a writer there - xyz stacks without
+// positional encoding, hidden widths that are multiples of 32 (accumulator columns = stash rows), <= 32 classes.
+bool heads_tc16_stash_ok(const clift_field* f, int heads) {
+    auto hidden_ok = [](const clift_mlp& m) {
+        for (int l = 1; l < m.n_layers; ++l)
+            if (m.dims[l] % 32) return false;
+        return true;
+    };
+    if ((heads & CLIFT_HEAD_SEMANTIC) && (f->pe_sem != 0 || f->num_classes > 32 || !hidden_ok(f->semantic))) return false;
+    if ((heads & CLIFT_HEAD_INSTANCE) &&
+        (f->pe_ins != 0 || !hidden_ok(f->instance_fast) || (f->slow_fast && !hidden_ok(f->instance_slow))))
+        return false;
+    if ((heads & CLIFT_HEAD_RGB) && !hidden_ok(f->rgb)) return false;
+    const char* e = getenv("CLIFT_TRAIN_FWD_FMA");       // development switch: training forwards on the FP32-FMA kernel
+    return !(e && atoi(e) != 0);
+}
+
 int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
-                              int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream) {
+                              int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream,
+                              const StashLayout* lay) {
     HeadsParams P;
     memset(&P, 0, sizeof(P));
     P.rec_pos = ws.rec_pos;
@@ -1168,8 +1245,17 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
         P.park = !P.stream && !(e_park && atoi(e_park) == 0);
         P.use_sets = (e_sets && atoi(e_sets) != 0) ? 1 : 0;
     }
+    if (lay) {      // training forward: record the stash; only the default schedule has the writers
+        P.pair = 0;
+        P.stream = 0;
+        P.park = 1;
+        P.use_sets = 0;
+        P.stash_a = ws.stash_a;
+        P.rec_rgb = ws.rec_rgb;
+        P.lay = *lay;
+    }
     int heads = (sem_raw ? CLIFT_HEAD_SEMANTIC : 0) | (ins ? CLIFT_HEAD_INSTANCE : 0) | (rgb_raw ? CLIFT_HEAD_RGB : 0);
-    bool ok = heads_tc16_available(field, heads);
+    bool ok = heads_tc16_available(field, heads) && (!lay || heads_tc16_stash_ok(field, heads));
     if (ok && sem_raw) {
         P.n_sem = field->semantic.n_layers;
         ok = ok && tc16_add_stack(P, field->semantic);

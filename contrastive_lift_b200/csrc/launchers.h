@@ -38,8 +38,10 @@ int launch_heads_forward_tc(const clift_render_cfg* cfg, const clift_field* fiel
 
 // heads_tc16.cu
 bool heads_tc16_available(const clift_field* f, int heads);
+bool heads_tc16_stash_ok(const clift_field* f, int heads);     // the tensor-core forward can record the training stash
 int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* field, const float* rays, const Workspace& ws,
-                              int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream);
+                              int64_t cap, int64_t n_rays, float* rgb_raw, float* sem_raw, float* ins, cudaStream_t stream,
+                              const StashLayout* lay = nullptr);
 
 // wgrad_tc.cu: tensor-core (tcgen05 3xTF32) weight gradients over the training stashes, all layers in one launch
 constexpr int kWgradTcMaxLayers = 24;

@@ -121,22 +121,23 @@ class _PackedMlp:
             has_bias = 1 if l.bias is not None else 0
             w, b = L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None
             L.check(lib.clift_pack_linear(w, b, L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
-            if not training:    # tensor-core operands serve inference only (PackedField.refresh tracks their staleness)
+            if not training:    # the 3xTF32 operands serve inference only (PackedField.refresh tracks their staleness)
                 nf = lib.clift_tc_weight_floats(l.out_features, l.in_features, has_bias)
                 if nf > 0:      # inside the tensor-core envelope: tf32 hi/lo operand
                     if self.w_tc[i] is None:
                         self.w_tc[i] = torch.zeros((nf,), device=self.wt[i].device)
                     L.check(lib.clift_pack_linear_tc(w, b, L.ptr(self.w_tc[i]), l.out_features, l.in_features, stream))
-                nb = lib.clift_tc16_weight_bytes(l.out_features, l.in_features, has_bias)
-                if nb > 0 and bound_ptr != -1:   # fp16-split operand, scales chained layer to layer
-                    if self.w_tc16[i] is None:
-                        self.w_tc16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
-                    L.check(lib.clift_pack_linear_tc16(w, b, L.ptr(self.w_tc16[i]), l.out_features, l.in_features, bound_ptr,
-                                                       float(floor), stream))
-                    bound_ptr, floor = self.w_tc16[i].data_ptr() + 12, 0.0
-                else:
-                    bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
-                    self.w_tc16[i] = None
+            # fp16-split operand (inference heads AND the training forward, which records the stash from the same kernel)
+            nb = lib.clift_tc16_weight_bytes(l.out_features, l.in_features, has_bias)
+            if nb > 0 and bound_ptr != -1:   # scales chained layer to layer
+                if self.w_tc16[i] is None:
+                    self.w_tc16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
+                L.check(lib.clift_pack_linear_tc16(w, b, L.ptr(self.w_tc16[i]), l.out_features, l.in_features, bound_ptr,
+                                                   float(floor), stream))
+                bound_ptr, floor = self.w_tc16[i].data_ptr() + 12, 0.0
+            else:
+                bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
+                self.w_tc16[i] = None
             if training:
                 if self.w_dgrad[i] is None:
                     self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
@@ -517,10 +518,9 @@ class PackedField:
         # fp16-split operand chain: |plane*line| bound -> basis -> (features, dirs, sin/cos) -> rgb stack
         vp3, i3 = C.c_void_p * 3, C.c_int64 * 3
         ap, al = self.planes["appearance"], self.lines["appearance"]
-        if not training:
-            L.check(lib.clift_tc16_factor_bound(vp3(*[L.ptr(t) for t in ap]), vp3(*[L.ptr(t) for t in al]),
-                                                i3(*[t.numel() for t in ap]), i3(*[t.numel() for t in al]),
-                                                L.ptr(self.tc16_scratch), st))
+        L.check(lib.clift_tc16_factor_bound(vp3(*[L.ptr(t) for t in ap]), vp3(*[L.ptr(t) for t in al]),
+                                            i3(*[t.numel() for t in ap]), i3(*[t.numel() for t in al]),
+                                            L.ptr(self.tc16_scratch), st))
         self.basis.pack(lib, st, training, self.tc16_scratch.data_ptr() + 24, 0.0)
         self.rgb.pack(lib, st, training, self.basis.out_bound_ptr(), 1.0)
         for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
@@ -545,7 +545,7 @@ class PackedField:
         if self.inss is not None:
             self.inss.fill(f.instance_slow)
         self.versions = versions
-        self.tc_stale = training        # training refreshes skip the tensor-core operands
+        self.tc_stale = training        # training refreshes skip the 3xTF32 operands
         self.trained = self.trained or training
 
     # ---- gradient side ---------------------------------------------------------------------------

@@ -187,9 +187,13 @@ def test_instance_and_segment_golden(name, path):
     assert gpu.rel_err(seg.exp() if bool(fx["softmax"]) else seg, ref.exp() if bool(fx["softmax"]) else ref) < REL
 
 
+@pytest.mark.parametrize("fwd", ["tc16", "fma"])
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
 @pytest.mark.parametrize("tag,seed", [("trn", 7), ("trn2", 8)])
-def test_render_training_gradients_golden(name, tag, seed):
+def test_render_training_gradients_golden(name, tag, seed, fwd, monkeypatch):
+    """fwd: which kernel runs the training forward and records the stash (tcgen05 fp16-split by default, FP32 FMA with
+    CLIFT_TRAIN_FWD_FMA=1; grid-mode heads always FMA) - see gpu_util.grad_close for the two tolerances."""
+    monkeypatch.setenv("CLIFT_TRAIN_FWD_FMA", "1" if fwd == "fma" else "0")
     fx, params, cfg, rays, model, rend = case(name)
     torch.manual_seed(seed)
     out = rend(model, rays.cuda(), 1.0, False, True)
@@ -209,7 +213,7 @@ def test_render_training_gradients_golden(name, tag, seed):
         for k, prm in model.named_parameters():
             g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
             ref = p[k].grad if p[k].grad is not None else torch.zeros_like(p[k])
-            assert gpu.rel_err(g, ref) < 2e-3, k
+            assert gpu.grad_close(g, ref, fwd), k
         return
     loss = gu.train_loss(out, fx, tag)
     assert abs(float(loss) - float(fx[f"{tag}_loss"])) < 1e-3 * abs(float(fx[f"{tag}_loss"]))
@@ -225,16 +229,18 @@ def test_render_training_gradients_golden(name, tag, seed):
         assert abs(dig[2] - ref[2]) <= 4e-3 * max(ref[2], 1e-20), (k, dig[:3], ref[:3])
         err = float(np.abs(dig[3:] - ref[3:]).max()) / scale
         worst[k] = err
-        assert err < 2e-3, (k, err)
+        assert err < (2e-3 if fwd == "fma" else 3e-2), (k, err)
         if f"{tag}_grad/{k}" in fx.files:
             full = tn(fx[f"{tag}_grad/{k}"])
-            assert gpu.rel_err(g, full) < 2e-3, k
+            assert gpu.grad_close(g, full, fwd), k
     # instance head gets gradient only because this test's loss touches instance_map
     assert model.render_instance_mlp.mlp[0].weight.grad.abs().sum() > 0
 
 
+@pytest.mark.parametrize("fwd", ["tc16", "fma"])
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
-def test_instance_pass_gradients_reach_only_instance_head(name):
+def test_instance_pass_gradients_reach_only_instance_head(name, fwd, monkeypatch):
+    monkeypatch.setenv("CLIFT_TRAIN_FWD_FMA", "1" if fwd == "fma" else "0")
     fx, params, cfg, rays, model, rend = case(name)
     torch.manual_seed(11)
     ins, pts = rend.forward_instance_feature(model, rays.cuda(), 1.0, True)
@@ -247,7 +253,7 @@ def test_instance_pass_gradients_reach_only_instance_head(name):
     (oi * w.cpu()).sum().backward()
     for k, prm in model.named_parameters():
         if k.startswith(("render_instance_mlp", "instance_plane", "instance_line", "instance_basis_mat")):
-            assert gpu.rel_err(prm.grad, p[k].grad) < 2e-3, k
+            assert gpu.grad_close(prm.grad, p[k].grad, fwd), k
         else:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
 

@@ -115,3 +115,29 @@ def test_wgrad_tensor_core_matches_fma_kernel(monkeypatch):
             if k.endswith(".weight"):
                 err = gpu.rel_err(grads["0"][k], g.cpu())
                 assert err < 2e-5, (name, k, err)
+
+
+def test_training_forward_tensor_core_stash_matches_fma_forward(monkeypatch):
+    """Training forwards run on the tcgen05 fp16-split kernel and record the backward's stash from there; with
+    CLIFT_TRAIN_FWD_FMA=1 the FP32-FMA kernel does both.  Same outputs (1e-5) and same parameter gradients
+    (gpu_util.grad_close: 2e-3 relative L2, single elements may carry a ReLU-mask flip)."""
+    import golden_util as gu
+    import gpu_util as gpu
+    for name in ("render_a", "render_b", "render_c"):
+        fx = gu.load(name)
+        params, cfg, rays = gu.render_inputs(fx)
+        res = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("CLIFT_TRAIN_FWD_FMA", mode)
+            model, rend = gpu.build(params, cfg.grid_dim, int(fx["n_cls"]), int(fx["n_ins"]), bool(fx["slow_fast"]),
+                                    bool(fx["softmax"]), cfg.aabb, float(fx["step_ratio"]))
+            torch.manual_seed(7)
+            out = rend(model, rays.cuda(), 1.0, False, True)
+            gu.train_loss(out, fx, "trn").backward()
+            res[mode] = ([o.detach().clone() for o in out[:3]],
+                         {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+        for a, b in zip(res["0"][0], res["1"][0]):
+            assert gpu.rel_err(a, b.cpu()) < 1e-5, name
+        assert set(res["0"][1]) == set(res["1"][1])
+        for k, g in res["1"][1].items():
+            assert gpu.grad_close(res["0"][1][k], g.cpu(), "tc16"), (name, k)
