@@ -715,7 +715,9 @@ __device__ __forceinline__ void gather_slice(const FactorParams& f, int mode, co
 // kPair: launched as clusters of two CTAs; the pair works on two tiles at once with M = 256 MMAs issued by the leader
 // (cluster rank 0) - see issue().  Every CTA of a pair runs the same number of iterations (a CTA whose tile index is past the
 // end carries an empty tile through the same schedule).
-template <int NV, bool kPair>
+// kStash: training forward - every layer input is also written to the A-stash (compiled out of the inference instantiation:
+// the extra predicates and address math in the epilogues cost it 6 %).
+template <int NV, bool kPair, bool kStash>
 __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const __grid_constant__ HeadsParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem s = carve_smem(smem_raw);
@@ -784,13 +786,16 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         int park_next = 2 * NV;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         float* st = nullptr;                                   // training: this tile's A-stash
-        auto st_block = [&](int id, int l) { return st ? st + (size_t)P.lay.a_off[id][l] * kRows : nullptr; };
+        auto st_block = [&](int id, int l) -> float* {
+            if (!kStash) return nullptr;
+            return st + (size_t)P.lay.a_off[id][l] * kRows;
+        };
         auto park_slice = [&]() {
             gather_slice(P.app, r.part, p, park_next, s.sc[g_basis].x, park, st_block(4, 0), row);
             ++park_next;
         };
         auto stash_xyz = [&](int id) {                         // layer-0 input of an xyz stack (pe = 0): 16 rows, 3 valid
-            if (st && r.part == 0) {
+            if (kStash && r.part == 0) {
                 float* b = st_block(id, 0);
                 b[stash_idx(16, 0, row)] = p.x;
                 b[stash_idx(16, 1, row)] = p.y;
@@ -827,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             p = p_next;
             const int ray = ray_next;
             fetch(tile + tile_step);
-            st = P.stash_a ? P.stash_a + (size_t)tile * P.lay.a_rows * kRows : nullptr;
+            if (kStash) st = P.stash_a + (size_t)tile * P.lay.a_rows * kRows;
             park_next = (P.park && P.n_rgb > 0) ? 0 : 2 * NV;
             if (r.part == 0) {
                 s.ray[row] = ray;
@@ -856,7 +861,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 run_hidden(P.n_sem, 0);
                 if (P.n_cls <= 32) {
                     epilogue_semantic32(s, r, d, P.n_cls, P.g[gi], P.softmax, p.w, s.sc[gi].y,
-                                        st ? st + (size_t)P.lay.prob_off * kRows : nullptr);
+                                        kStash ? st + (size_t)P.lay.prob_off * kRows : nullptr);
                 } else {
                     epilogue_final(s, r, d, P.n_cls, P.g[gi], s.sc[gi].y);
                     if (r.part == 0) {   // wide heads: softmax over the thread's own column of the scratch
@@ -1005,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                     for (int c = 0; c < 3; ++c) {
                         const float x = scratch[(size_t)c * kRows + row];
                         const float sig = 1.0f / (1.0f + expf(-x));
-                        if (P.rec_rgb && row < nv) P.rec_rgb[((long long)tile * kRows + row) * 4 + c] = sig;
+                        if (kStash && row < nv) P.rec_rgb[((long long)tile * kRows + row) * 4 + c] = sig;
                         scratch[(size_t)c * kRows + row] = sig * p.w;
                     }
                 reduce_runs(s, r.rt, 3, P.rgb_raw, 3, 0);
@@ -1035,30 +1040,36 @@ __device__ __forceinline__ float pow2_floor_ratio(float num_log2, float x) {   /
 }
 
 // header[0..7] = ca, cw, 1/(ca cw), out bound, in bound, L = max_n sum_k |W_nk|, max|W|, max|b|
-__global__ void __launch_bounds__(256) tc16_plan_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out,
-                                                        int n_in, const float* __restrict__ in_bound_dev, float in_floor,
-                                                        float* __restrict__ header) {
-    __shared__ float red[3][256];
+__global__ void __launch_bounds__(1024) tc16_plan_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out,
+                                                         int n_in, const float* __restrict__ in_bound_dev, float in_floor,
+                                                         float* __restrict__ header) {
+    // one warp per weight row (coalesced reads, fixed-order lane tree): it runs before every training forward
+    __shared__ float red[3][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float l1 = 0.0f, wm = 0.0f, bm = 0.0f;
-    for (int n = threadIdx.x; n < n_out; n += 256) {
+    for (int n = warp; n < n_out; n += 32) {
         float sum = 0.0f;
-        for (int k = 0; k < n_in; ++k) {
+        for (int k = lane; k < n_in; k += 32) {
             const float a = fabsf(w[(size_t)n * n_in + k]);
             sum += a;
             wm = fmaxf(wm, a);
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         l1 = fmaxf(l1, sum);
         if (bias) bm = fmaxf(bm, fabsf(bias[n]));
     }
-    red[0][threadIdx.x] = l1;
-    red[1][threadIdx.x] = wm;
-    red[2][threadIdx.x] = bm;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-            for (int j = 0; j < 3; ++j) red[j][threadIdx.x] = fmaxf(red[j][threadIdx.x], red[j][threadIdx.x + o]);
-        __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    if (lane == 0) {
+        red[0][warp] = l1;
+        red[1][warp] = wm;
+        red[2][warp] = bm;
     }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 1; i < 32; ++i)
+            for (int j = 0; j < 3; ++j) red[j][0] = fmaxf(red[j][0], red[j][i]);
     if (threadIdx.x == 0) {
         l1 = red[0][0] * 1.0001f;    // rounding slack of the fp32 sums
         wm = red[1][0];
@@ -1308,7 +1319,9 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
     };
 #define CLIFT_TC16_CASE(NV)                                                                                            \
     case NV: {                                                                                                         \
-        CLIFT_CUDA(P.pair ? launch(heads_tc16_forward_kernel<NV, true>) : launch(heads_tc16_forward_kernel<NV, false>)); \
+        CLIFT_CUDA(lay ? launch(heads_tc16_forward_kernel<NV, false, true>)                                            \
+                       : (P.pair ? launch(heads_tc16_forward_kernel<NV, true, false>)                                  \
+                                 : launch(heads_tc16_forward_kernel<NV, false, false>)));                              \
         break;                                                                                                         \
     }
     switch (P.app.comps / 16) {
@@ -1343,7 +1356,7 @@ extern "C" int32_t clift_pack_linear_tc16(const float* w, const float* bias, voi
     CLIFT_CHECK_SUPPORTED(n_out > 0 && n_in > 0 && n_out <= 256 && n_in <= kMaxK, "layer wider than 256");
     const int n_pad = (int)round_up(n_out, 32), slabs = (int)ceil_div(n_in, kStepK) + (bias ? 1 : 0);
     float* header = reinterpret_cast<float*>(dst);
-    tc16_plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(w, bias, n_out, n_in, in_bound, in_bound_floor, header);
+    tc16_plan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w, bias, n_out, n_in, in_bound, in_bound_floor, header);
     CLIFT_AFTER_LAUNCH("tc16_plan_kernel");
     const int64_t total = (int64_t)slabs * kStepK * n_pad;
     __half* single = reinterpret_cast<__half*>(header + kHeaderFloats);
