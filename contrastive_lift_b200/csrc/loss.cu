@@ -4,8 +4,8 @@
 //   vanilla loss    : model/loss/loss.py:62-82
 //   TV regulariser  : model/loss/loss.py:9-26 (tensoRF.py:248-290 supplies the 1e-2*lambda scale)
 // The reference needs torch.unique, per-label Python loops, boolean-mask indexing (host syncs) and an
-// (N/2)^2 cdist; here one CTA keeps features/labels in shared memory, resolves label groups by
-// first-occurrence scans, and all reductions use a fixed tree so the result is run-to-run identical.
+// (N/2)^2 cdist; here every CTA (the slow-fast loss: of one thread-block cluster) keeps features/labels in shared memory,
+// resolves label groups by first-occurrence scans, and all reductions use a fixed tree so the result is run-to-run identical.
 #include "launchers.h"
 
 namespace clift {
@@ -54,12 +54,26 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 // ----------------------------------------------------------------------------------------------
 // slow-fast
 // ----------------------------------------------------------------------------------------------
+// One thread-block cluster (1, 8 or 16 CTAs by problem size); every CTA holds all features / labels in shared memory and
+// owns the fast samples i = rank*32 + warp, + 32*cluster size, ...: ONE WARP per fast sample, its lanes split the slow
+// samples j (lane, lane + 32, ...) and combine with a fixed xor tree, so the N/2 x N/2 pair loop that a single CTA walked in
+// 512-long dependent chains is 16 x 32 = 512 warps wide.  The four loss sums are combined in rank order through distributed
+// shared memory (fixed order: run-to-run identical), after which every CTA knows the totals the gradient needs.
+__device__ __forceinline__ float warp_sum_xor(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 __global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __restrict__ feats, const long long* __restrict__ labels,
                                                                 const float* __restrict__ conf, int n, int d,
                                                                 float* __restrict__ loss_out, float* __restrict__ grad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float s_red[33];
+    __shared__ float s_part[4];
     const int nf = n / 2, ns = n - nf, w2 = 2 * d;
+    const unsigned rank = cluster_ctarank(), csize = cluster_nctarank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     long long* s_lab = reinterpret_cast<long long*>(smem_raw);      // [n]
     float* s_feat = reinterpret_cast<float*>(s_lab + n);              // [n][2d]
     float* s_cent = s_feat + (size_t)n * w2;                          // [ns][d] centroid of slow sample j's label group
@@ -70,11 +84,13 @@ __global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __r
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_lab[i] = labels[i];
     for (int i = threadIdx.x; i < n * w2; i += blockDim.x) s_feat[i] = feats[i];
-    if (grad)
-        for (int i = threadIdx.x; i < n * w2; i += blockDim.x) grad[i] = 0.0f;
+    if (grad)      // slow rows carry no gradient (trainer:267: the slow half is detached); fast rows are written whole below
+        for (int i = nf * w2 + (int)rank * (int)blockDim.x + threadIdx.x; i < n * w2; i += (int)csize * blockDim.x) grad[i] = 0.0f;
     __syncthreads();
     if (nf == 0 || ns == 0) {   // trainer:285-288
-        if (threadIdx.x == 0) loss_out[0] = 0.0f;
+        if (rank == 0 && threadIdx.x == 0) loss_out[0] = 0.0f;
+        if (grad)
+            for (int i = (int)rank * (int)blockDim.x + threadIdx.x; i < nf * w2; i += (int)csize * blockDim.x) grad[i] = 0.0f;
         return;
     }
     // slow centroids: every slow sample gets the mean of its label group (members summed in index order)
@@ -90,22 +106,29 @@ __global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __r
         for (int k = 0; k < d; ++k) s_cent[j * d + k] /= (float)cnt;
     }
     __syncthreads();
-    float my_conc = 0.0f, my_logp = 0.0f, my_valid = 0.0f, my_first = 0.0f;
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+    float my_conc = 0.0f, my_logp = 0.0f, my_valid = 0.0f, my_first = 0.0f;      // lane 0 of each warp accumulates
+    for (int i = (int)rank * n_warps + warp; i < nf; i += (int)csize * n_warps) {
         const long long l = s_lab[i];
-        int rep = -1;
-        for (int j = 0; j < ns; ++j)
+        int rep = 0x7fffffff;
+        for (int j = lane; j < ns; j += 32)
             if (s_lab[nf + j] == l) {
                 rep = j;
                 break;
             }
-        int n_l = 0;
-        bool first = true;
-        for (int ii = 0; ii < nf; ++ii)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) rep = min(rep, __shfl_xor_sync(0xffffffffu, rep, o));
+        if (rep == 0x7fffffff) rep = -1;
+        int n_l = 0, earlier = 0;
+        for (int ii = lane; ii < nf; ii += 32)
             if (s_lab[ii] == l) {
                 ++n_l;
-                if (ii < i) first = false;
+                if (ii < i) earlier = 1;
             }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_l += __shfl_xor_sync(0xffffffffu, n_l, o);
+            earlier |= __shfl_xor_sync(0xffffffffu, earlier, o);
+        }
         float cw = 0.0f;
         if (rep >= 0) {
             float dsq = 0.0f;
@@ -114,13 +137,13 @@ __global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __r
                 dsq += df * df;
             }
             cw = expf(-dsq) * conf[i] / (float)n_l;
-            my_conc += cw;
-            if (first) my_first += 1.0f;
+            if (lane == 0) {
+                my_conc += cw;
+                if (!earlier) my_first += 1.0f;
+            }
         }
-        s_cw[i] = cw;
-        s_rep[i] = rep;
         float num = 0.0f, den = 0.0f;
-        for (int j = 0; j < ns; ++j) {
+        for (int j = lane; j < ns; j += 32) {
             float dsq = 0.0f;
             for (int k = 0; k < d; ++k) {
                 const float df = s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k];
@@ -130,46 +153,71 @@ __global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __r
             den += e;
             if (s_lab[nf + j] == l) num += e;
         }
-        s_num[i] = num;
-        s_den[i] = den;
-        const float prob = num / den;
-        if (prob != 0.0f) {
-            my_logp += logf(prob);
-            my_valid += 1.0f;
+        num = warp_sum_xor(num);
+        den = warp_sum_xor(den);
+        if (lane == 0) {
+            s_cw[i] = cw;
+            s_rep[i] = rep;
+            s_num[i] = num;
+            s_den[i] = den;
+            const float prob = num / den;
+            if (prob != 0.0f) {
+                my_logp += logf(prob);
+                my_valid += 1.0f;
+            }
         }
     }
-    const float conc = block_sum(my_conc, s_red);
-    const float n_int = block_sum(my_first, s_red);
-    const float logp = block_sum(my_logp, s_red);
-    const float n_valid = block_sum(my_valid, s_red);
+    const float b_conc = block_sum(my_conc, s_red);
+    const float b_first = block_sum(my_first, s_red);
+    const float b_logp = block_sum(my_logp, s_red);
+    const float b_valid = block_sum(my_valid, s_red);
     if (threadIdx.x == 0) {
+        s_part[0] = b_conc;
+        s_part[1] = b_first;
+        s_part[2] = b_logp;
+        s_part[3] = b_valid;
+    }
+    cluster_sync_all();
+    float conc = 0.0f, n_int = 0.0f, logp = 0.0f, n_valid = 0.0f;
+    for (unsigned r = 0; r < csize; ++r) {        // rank order: the same totals, bit for bit, in every CTA
+        conc += ld_dsmem_f32(&s_part[0], r);
+        n_int += ld_dsmem_f32(&s_part[1], r);
+        logp += ld_dsmem_f32(&s_part[2], r);
+        n_valid += ld_dsmem_f32(&s_part[3], r);
+    }
+    cluster_sync_all();                            // peers' partials stay alive until everybody has read them
+    if (rank == 0 && threadIdx.x == 0) {
         float l = 0.0f;
         if (n_int > 0.0f) l = -conc / n_int;
         l += -(logp / n_valid);      // 0/0 -> NaN like mean() of an empty selection
         loss_out[0] = l;
     }
     if (!grad) return;
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+    for (int i = (int)rank * n_warps + warp; i < nf; i += (int)csize * n_warps) {
         const long long l = s_lab[i];
         const float num = s_num[i], den = s_den[i];
         const bool valid = (num / den) != 0.0f;
         for (int k = 0; k < d; ++k) {
             float g = 0.0f;
-            if (s_rep[i] >= 0) g += 2.0f * s_cw[i] / n_int * (s_feat[i * w2 + k] - s_cent[s_rep[i] * d + k]);
-            grad[i * w2 + k] = g;
-        }
-        if (!valid) continue;
-        for (int j = 0; j < ns; ++j) {
-            float dsq = 0.0f;
-            for (int k = 0; k < d; ++k) {
-                const float df = s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k];
-                dsq += df * df;
+            if (valid)
+                for (int j = lane; j < ns; j += 32) {
+                    float dsq = 0.0f;
+                    for (int kk = 0; kk < d; ++kk) {
+                        const float df = s_feat[i * w2 + kk] - s_feat[(nf + j) * w2 + d + kk];
+                        dsq += df * df;
+                    }
+                    const float dist = sqrtf(dsq);
+                    if (dist == 0.0f) continue;   // cdist backward yields 0 at coincident points
+                    const float sx = expf(-dist), e = expf(sx);
+                    const float c = ((s_lab[nf + j] == l ? 1.0f / num : 0.0f) - 1.0f / den) * e * sx / (dist * n_valid);
+                    g += c * (s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k]);
+                }
+            g = warp_sum_xor(g);
+            if (lane == 0) {
+                if (s_rep[i] >= 0) g += 2.0f * s_cw[i] / n_int * (s_feat[i * w2 + k] - s_cent[s_rep[i] * d + k]);
+                grad[i * w2 + k] = g;
+                grad[i * w2 + d + k] = 0.0f;
             }
-            const float dist = sqrtf(dsq);
-            if (dist == 0.0f) continue;   // cdist backward yields 0 at coincident points
-            const float s = expf(-dist), e = expf(s);
-            const float c = ((s_lab[nf + j] == l ? 1.0f / num : 0.0f) - 1.0f / den) * e * s / (dist * n_valid);
-            for (int k = 0; k < d; ++k) grad[i * w2 + k] += c * (s_feat[i * w2 + k] - s_feat[(nf + j) * w2 + d + k]);
         }
     }
 }
@@ -316,8 +364,22 @@ extern "C" int32_t clift_slowfast_loss(const float* features, const int64_t* lab
     const size_t smem = (size_t)n * 8 + (size_t)n * 2 * d * 4 + (size_t)ns * d * 4 + (size_t)nf * 4 * 4 + 64;
     CLIFT_CHECK_SUPPORTED(smem <= 200 * 1024, "slow-fast loss: N*d too large for one CTA's shared memory");
     CLIFT_CUDA(cudaFuncSetAttribute(slowfast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    slowfast_kernel<<<1, kLossThreads, smem, (cudaStream_t)stream>>>(features, (const long long*)labels, confidences, n, d, loss,
-                                                                     grad_features);
+    CLIFT_CUDA(cudaFuncSetAttribute(slowfast_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const int cluster = nf >= 512 ? 16 : (nf >= 64 ? 8 : 1);      // one warp per fast sample: 32 warps per CTA
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)cluster);
+    lc.blockDim = dim3(kLossThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CLIFT_CUDA(cudaLaunchKernelEx(&lc, slowfast_kernel, features, (const long long*)labels, confidences, (int)n, (int)d, loss,
+                                  grad_features));
     CLIFT_AFTER_LAUNCH("slowfast_kernel");
     return CLIFT_OK;
 }
