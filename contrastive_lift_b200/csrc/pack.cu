@@ -37,6 +37,44 @@ __global__ void copy2d_pad_kernel(const float* __restrict__ src, int s_rows, int
     dst[i] = (r < s_rows && c < s_cols) ? src[(int64_t)r * s_cols + c] : 0.0f;
 }
 
+// One launch for a table of transpose / copy jobs (clift_pack_batch): CTA b finds its job by binary search over the jobs'
+// first-tile prefix and handles one 32 x 32 destination tile of it.
+__global__ void __launch_bounds__(256) pack_batch_kernel(const clift_pack_job* __restrict__ jobs, int n_jobs) {
+    __shared__ float tile[32][33];
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first_tile <= (int)blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const clift_pack_job J = jobs[lo];
+    const int t = (int)blockIdx.x - J.first_tile;
+    const int tiles_x = (J.d_cols + 31) >> 5;
+    const int bi = (t / tiles_x) * 32, bj = (t % tiles_x) * 32;   // dst tile origin (row, col)
+    if (bi >= J.d_rows) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (J.kind == 0) {
+        for (int r = ty; r < 32; r += 8) {
+            const int sj = bj + r, si = bi + tx;   // src row = dst col, src col = dst row
+            tile[r][tx] = (J.src && sj < J.s_rows && si < J.s_cols) ? J.src[(int64_t)sj * J.s_pitch + si] : 0.0f;
+        }
+        __syncthreads();
+        for (int r = ty; r < 32; r += 8) {
+            const int di = bi + r, dj = bj + tx;
+            if (di < J.d_rows && dj < J.d_cols) J.dst[(int64_t)di * J.d_cols + dj] = tile[tx][r];
+        }
+    } else {
+        for (int r = ty; r < 32; r += 8) {
+            const int di = bi + r, dj = bj + tx;
+            if (di < J.d_rows && dj < J.d_cols)
+                J.dst[(int64_t)di * J.d_cols + dj] =
+                    (J.src && di < J.s_rows && dj < J.s_cols) ? J.src[(int64_t)di * J.s_pitch + dj] : 0.0f;
+        }
+    }
+}
+
 }  // namespace
 
 static int transpose_pad(const float* src, int s_pitch, int s_rows, int s_cols, float* dst, int d_rows, int d_cols,
@@ -94,5 +132,13 @@ extern "C" int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32
     const int rows = k_pad(n_out), cols = dgrad_pad(n_in);
     copy2d_pad_kernel<<<(unsigned)ceil_div((int64_t)rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(w, n_out, n_in, w_dgrad, rows, cols);
     CLIFT_AFTER_LAUNCH("copy2d_pad_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_pack_batch(const clift_pack_job* jobs, int32_t n_jobs, int32_t total_tiles, void* stream) {
+    CLIFT_CHECK_ARG(n_jobs >= 0 && total_tiles >= 0 && (n_jobs == 0 || jobs), "null table or negative size");
+    if (n_jobs == 0 || total_tiles == 0) return CLIFT_OK;
+    pack_batch_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, n_jobs);
+    CLIFT_AFTER_LAUNCH("pack_batch_kernel");
     return CLIFT_OK;
 }

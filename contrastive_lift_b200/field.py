@@ -113,14 +113,24 @@ class _PackedMlp:
         t = self.w_tc16[-1]
         return -1 if t is None else t.data_ptr() + 12
 
+    def collect(self, batch: "L.PackBatch", training: bool):
+        """Queue the fp32 layout jobs of this stack (W^T + bias, and the data-gradient copy in training) on ``batch``."""
+        for i, l in enumerate(self.linears):
+            batch.linear(l.weight.data, l.bias.data if l.bias is not None else None, self.wt[i], self.bias[i],
+                         l.out_features, l.in_features)
+            if training:
+                if self.w_dgrad[i] is None:
+                    self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
+                batch.dgrad(l.weight.data, self.w_dgrad[i], l.out_features, l.in_features)
+
     def pack(self, lib, stream, training: bool, in_bound_ptr: Optional[int] = None, in_bound_floor: float = 1.0):
-        """``in_bound_ptr`` / ``in_bound_floor``: bound on |input| of the first layer for the fp16-split operand chain
+        """Tensor-core operands of this stack (the fp32 layouts travel through ``collect``).
+        ``in_bound_ptr`` / ``in_bound_floor``: bound on |input| of the first layer for the fp16-split operand chain
         (device scalar and/or constant; xyz, sin/cos and unit directions are bounded by 1)."""
         bound_ptr, floor = in_bound_ptr, in_bound_floor
         for i, l in enumerate(self.linears):
             has_bias = 1 if l.bias is not None else 0
             w, b = L.ptr(l.weight.data), L.ptr(l.bias.data) if l.bias is not None else None
-            L.check(lib.clift_pack_linear(w, b, L.ptr(self.wt[i]), L.ptr(self.bias[i]), l.out_features, l.in_features, stream))
             if not training:    # the 3xTF32 operands serve inference only (PackedField.refresh tracks their staleness)
                 nf = lib.clift_tc_weight_floats(l.out_features, l.in_features, has_bias)
                 if nf > 0:      # inside the tensor-core envelope: tf32 hi/lo operand
@@ -138,11 +148,6 @@ class _PackedMlp:
             else:
                 bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
                 self.w_tc16[i] = None
-            if training:
-                if self.w_dgrad[i] is None:
-                    self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
-                L.check(lib.clift_pack_linear_dgrad(L.ptr(l.weight.data), L.ptr(self.w_dgrad[i]), l.out_features,
-                                                    l.in_features, stream))
 
     def fill(self, m: L.Mlp):
         m.n_layers = len(self.linears)
@@ -155,12 +160,15 @@ class _PackedMlp:
             m.w_tc[i] = L.ptr(self.w_tc[i])
             m.w_tc16[i] = L.ptr(self.w_tc16[i])
 
-    def grad_buffers(self, g: L.MlpGrad, want: bool):
+    def grad_buffers(self, g: L.MlpGrad, want: bool, to_zero: Optional[List[torch.Tensor]] = None):
+        """``to_zero``: list the caller clears with one multi-tensor launch (else each buffer is cleared here)."""
         for i in range(len(self.linears)):
             if want:
                 if self.g_wt[i] is None:
                     self.g_wt[i] = torch.zeros_like(self.wt[i])
                     self.g_bias[i] = torch.zeros_like(self.bias[i])
+                elif to_zero is not None:
+                    to_zero += [self.g_wt[i], self.g_bias[i]]
                 else:
                     self.g_wt[i].zero_()
                     self.g_bias[i].zero_()
@@ -170,14 +178,17 @@ class _PackedMlp:
                 g.wt[i] = None
                 g.bias[i] = None
 
-    def unpack_grads(self, lib, stream) -> List[torch.Tensor]:
-        """-> [dW0, db0, dW1, db1, ...] in nn.Linear layout."""
+    def unpack_grads(self, lib, stream, batch: Optional["L.PackBatch"] = None) -> List[torch.Tensor]:
+        """-> [dW0, db0, dW1, db1, ...] in nn.Linear layout (``batch``: queued there, valid after batch.run())."""
         out = []
         for i, l in enumerate(self.linears):
             gw = torch.empty_like(l.weight)
             gb = torch.empty_like(l.bias) if l.bias is not None else None
-            L.check(lib.clift_unpack_linear(L.ptr(self.g_wt[i]), L.ptr(self.g_bias[i]), L.ptr(gw), L.ptr(gb),
-                                            l.out_features, l.in_features, stream))
+            if batch is not None:
+                batch.unlinear(self.g_wt[i], self.g_bias[i], gw, gb, l.out_features, l.in_features)
+            else:
+                L.check(lib.clift_unpack_linear(L.ptr(self.g_wt[i]), L.ptr(self.g_bias[i]), L.ptr(gw), L.ptr(gb),
+                                                l.out_features, l.in_features, stream))
             out.append(gw)
             if gb is not None:
                 out.append(gb)
@@ -509,12 +520,18 @@ class PackedField:
         if not training and versions == self.versions and not self.tc_stale:
             return
         lib, st = self.lib, L.stream_ptr(self.device)
+        # every fp32 layout job of the model (factor transposes, W^T + bias, data-gradient copies) in ONE launch
+        batch = L.PackBatch()
         for name in self.src:
             planes, lines = self.src[name]
             for i in range(3):
                 p, l = planes[i].data, lines[i].data
-                L.check(lib.clift_pack_plane(L.ptr(p), L.ptr(self.planes[name][i]), p.shape[1], p.shape[2], p.shape[3], st))
-                L.check(lib.clift_pack_plane(L.ptr(l), L.ptr(self.lines[name][i]), l.shape[1], l.shape[2], 1, st))
+                batch.plane(p, self.planes[name][i], p.shape[1], p.shape[2], p.shape[3])
+                batch.plane(l, self.lines[name][i], l.shape[1], l.shape[2], 1)
+        for m in [self.basis, self.rgb, self.sem, self.insf, self.inss] + list(self.grid_basis.values()):
+            if m is not None:
+                m.collect(batch, training)
+        batch.run(lib, self.device)
         # fp16-split operand chain: |plane*line| bound -> basis -> (features, dirs, sin/cos) -> rgb stack
         vp3, i3 = C.c_void_p * 3, C.c_int64 * 3
         ap, al = self.planes["appearance"], self.lines["appearance"]
@@ -551,6 +568,7 @@ class PackedField:
     # ---- gradient side ---------------------------------------------------------------------------
     def prepare_grads(self, want_density: bool, want_rgb: bool, want_sem: bool, want_ins: bool) -> L.FieldGrad:
         g = self.grad
+        to_zero: List[torch.Tensor] = []            # cleared with one multi-tensor launch at the end
         wants = {"density": want_density, "appearance": want_rgb, "semantic": want_sem, "instance": want_ins}
         for name in self.planes:
             want = wants[name]
@@ -561,8 +579,7 @@ class PackedField:
                         self.g_planes[name][i] = torch.zeros_like(self.planes[name][i])
                         self.g_lines[name][i] = torch.zeros_like(self.lines[name][i])
                     else:
-                        self.g_planes[name][i].zero_()
-                        self.g_lines[name][i].zero_()
+                        to_zero += [self.g_planes[name][i], self.g_lines[name][i]]
                 gp = L.ptr(self.g_planes[name][i]) if want else None
                 gl = L.ptr(self.g_lines[name][i]) if want else None
                 if name == "density":
@@ -573,20 +590,22 @@ class PackedField:
                     gh.plane[i], gh.line[i] = gp, gl
             if gh is not None:
                 dummy = L.MlpGrad()
-                self.grid_basis[name].grad_buffers(dummy, want)
+                self.grid_basis[name].grad_buffers(dummy, want, to_zero)
                 gh.basis = dummy.wt[0]
         dummy = L.MlpGrad()
-        self.basis.grad_buffers(dummy, want_rgb)
+        self.basis.grad_buffers(dummy, want_rgb, to_zero)
         g.basis = dummy.wt[0]
-        self.rgb.grad_buffers(g.rgb, want_rgb)
-        self.sem.grad_buffers(g.semantic, want_sem)
+        self.rgb.grad_buffers(g.rgb, want_rgb, to_zero)
+        self.sem.grad_buffers(g.semantic, want_sem, to_zero)
         if self.insf is not None:
-            self.insf.grad_buffers(g.instance_fast, want_ins)
+            self.insf.grad_buffers(g.instance_fast, want_ins, to_zero)
         if self.inss is not None:
-            self.inss.grad_buffers(g.instance_slow, want_ins)
+            self.inss.grad_buffers(g.instance_slow, want_ins, to_zero)
+        if to_zero:
+            torch._foreach_zero_(to_zero)
         return g
 
-    def unpack_factor_grads(self, name: str) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
+    def unpack_factor_grads(self, name: str, batch: Optional["L.PackBatch"] = None) -> Tuple[List[torch.Tensor], List[torch.Tensor]]:
         lib, st = self.lib, L.stream_ptr(self.device)
         planes, lines = self.src[name]
         gp, gl = [], []
@@ -594,8 +613,12 @@ class PackedField:
             p, l = planes[i], lines[i]
             a = torch.empty_like(p.data)
             b = torch.empty_like(l.data)
-            L.check(lib.clift_unpack_plane(L.ptr(self.g_planes[name][i]), L.ptr(a), p.shape[1], p.shape[2], p.shape[3], st))
-            L.check(lib.clift_unpack_plane(L.ptr(self.g_lines[name][i]), L.ptr(b), l.shape[1], l.shape[2], 1, st))
+            if batch is not None:
+                batch.unplane(self.g_planes[name][i], a, p.shape[1], p.shape[2], p.shape[3])
+                batch.unplane(self.g_lines[name][i], b, l.shape[1], l.shape[2], 1)
+            else:
+                L.check(lib.clift_unpack_plane(L.ptr(self.g_planes[name][i]), L.ptr(a), p.shape[1], p.shape[2], p.shape[3], st))
+                L.check(lib.clift_unpack_plane(L.ptr(self.g_lines[name][i]), L.ptr(b), l.shape[1], l.shape[2], 1, st))
             gp.append(a)
             gl.append(b)
         return gp, gl

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -73,6 +73,12 @@ class RenderOut(C.Structure):
                 ("points", _vp), ("weights", _vp), ("save_for_backward", C.c_int32)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("src", _vp), ("dst", _vp), ("s_pitch", C.c_int32), ("s_rows", C.c_int32), ("s_cols", C.c_int32),
+                ("d_rows", C.c_int32), ("d_cols", C.c_int32), ("kind", C.c_int32), ("first_tile", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_int64)]
 
@@ -92,6 +98,7 @@ SIGNATURES = {
     "clift_profile_enable": (C.c_int32, [C.c_int32]),
     "clift_profile_stage_ms": (C.c_int32, [_fp]),
     "clift_pack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "clift_pack_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "clift_unpack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_pack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_unpack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
@@ -201,3 +208,48 @@ def param_epoch() -> int:
 def fill3(arr, values: Sequence) -> None:
     for i in range(3):
         arr[i] = values[i]
+
+
+class PackBatch:
+    """Collects layout jobs (clift_pack_job) and runs them as ONE clift_pack_batch launch: the batched form of
+    clift_pack_plane / clift_unpack_plane / clift_pack_linear / clift_unpack_linear / clift_pack_linear_dgrad."""
+
+    def __init__(self):
+        self.jobs = []
+        self.tiles = 0
+
+    def _add(self, src, dst, s_pitch, s_rows, s_cols, d_rows, d_cols, kind):
+        if d_rows <= 0 or d_cols <= 0:
+            return
+        j = PackJob()
+        j.src, j.dst = ptr(src), ptr(dst)
+        j.s_pitch, j.s_rows, j.s_cols, j.d_rows, j.d_cols, j.kind = s_pitch, s_rows, s_cols, d_rows, d_cols, kind
+        j.first_tile = self.tiles
+        self.tiles += ((d_rows + 31) // 32) * ((d_cols + 31) // 32)
+        self.jobs.append(j)
+
+    def plane(self, nchw, hwc, comps, h, w):
+        self._add(nchw, hwc, h * w, comps, h * w, h * w, comps, 0)
+
+    def unplane(self, hwc, nchw, comps, h, w):
+        self._add(hwc, nchw, comps, h * w, comps, comps, h * w, 0)
+
+    def linear(self, w, b, wt, bias_pad, n_out, n_in):
+        self._add(w, wt, n_in, n_out, n_in, k_pad(n_in), n_pad(n_out), 0)
+        self._add(b, bias_pad, n_out, 1, n_out, 1, n_pad(n_out), 1)
+
+    def unlinear(self, wt, bias_pad, w, b, n_out, n_in):
+        self._add(wt, w, n_pad(n_out), n_in, n_out, n_out, n_in, 0)
+        if b is not None:
+            self._add(bias_pad, b, n_out, 1, n_out, 1, n_out, 1)
+
+    def dgrad(self, w, w_dgrad, n_out, n_in):
+        self._add(w, w_dgrad, n_in, n_out, n_in, k_pad(n_out), dgrad_pad(n_in), 1)
+
+    def run(self, lib, device):
+        if not self.jobs:
+            return
+        raw = bytes((PackJob * len(self.jobs))(*self.jobs))
+        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
+        check(lib.clift_pack_batch(ptr(table), len(self.jobs), int(self.tiles), stream_ptr(device)))
+        self.jobs, self.tiles = [], 0

@@ -129,33 +129,35 @@ class _Render(torch.autograd.Function):
                                           C.byref(fg), L.stream_ptr(dev)))
         ctx.ws = None        # consumed
         st = L.stream_ptr(dev)
+        batch = L.PackBatch()        # every gradient goes back to checkpoint layout in one launch
         grads = {}
         if want_density:
-            gp, gl = pk.unpack_factor_grads("density")
+            gp, gl = pk.unpack_factor_grads("density", batch)
             for i in range(3):
                 grads[f"density_plane.{i}"], grads[f"density_line.{i}"] = gp[i], gl[i]
         if g_rgb is not None:
-            gp, gl = pk.unpack_factor_grads("appearance")
+            gp, gl = pk.unpack_factor_grads("appearance", batch)
             for i in range(3):
                 grads[f"appearance_plane.{i}"], grads[f"appearance_line.{i}"] = gp[i], gl[i]
-            grads["appearance_basis_mat.weight"] = pk.basis.unpack_grads(lib, st)[0]
-            for n, g in zip(_mlp_names("render_appearance_mlp.mlp", pk.rgb), pk.rgb.unpack_grads(lib, st)):
+            grads["appearance_basis_mat.weight"] = pk.basis.unpack_grads(lib, st, batch)[0]
+            for n, g in zip(_mlp_names("render_appearance_mlp.mlp", pk.rgb), pk.rgb.unpack_grads(lib, st, batch)):
                 grads[n] = g
         for name, gout in (("semantic", g_sem), ("instance", g_ins)):      # grid-mode heads: their own factors + basis
             if gout is not None and name in pk.grid_basis:
-                gp, gl = pk.unpack_factor_grads(name)
+                gp, gl = pk.unpack_factor_grads(name, batch)
                 for i in range(3):
                     grads[f"{name}_plane.{i}"], grads[f"{name}_line.{i}"] = gp[i], gl[i]
-                grads[f"{name}_basis_mat.weight"] = pk.grid_basis[name].unpack_grads(lib, st)[0]
+                grads[f"{name}_basis_mat.weight"] = pk.grid_basis[name].unpack_grads(lib, st, batch)[0]
         if g_sem is not None:
-            for n, g in zip(_mlp_names("render_semantic_mlp.mlp", pk.sem), pk.sem.unpack_grads(lib, st)):
+            for n, g in zip(_mlp_names("render_semantic_mlp.mlp", pk.sem), pk.sem.unpack_grads(lib, st, batch)):
                 grads[n] = g
         if g_ins is not None and pk.insf is not None:
-            for n, g in zip(_mlp_names("render_instance_mlp.mlp", pk.insf), pk.insf.unpack_grads(lib, st)):
+            for n, g in zip(_mlp_names("render_instance_mlp.mlp", pk.insf), pk.insf.unpack_grads(lib, st, batch)):
                 grads[n] = g
             if pk.inss is not None:
-                for n, g in zip(_mlp_names("render_instance_mlp.slow_mlp", pk.inss), pk.inss.unpack_grads(lib, st)):
+                for n, g in zip(_mlp_names("render_instance_mlp.slow_mlp", pk.inss), pk.inss.unpack_grads(lib, st, batch)):
                     grads[n] = g
+        batch.run(lib, dev)
         return (None,) * 8 + tuple(grads.get(n) for n in ctx.param_names)
 
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 7
+#define CLIFT_ABI_VERSION 8
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -192,6 +192,26 @@ int32_t clift_unpack_linear(const float* wt, const float* bias_pad, float* w, fl
                             int32_t n_out, int32_t n_in, void* stream);
 /* nn.Linear weight [out][in] -> zero padded copy [round_up(out,16)][dgrad_pad(in)] (data-gradient operand). */
 int32_t clift_pack_linear_dgrad(const float* w, float* w_dgrad, int32_t n_out, int32_t n_in, void* stream);
+
+/* All of the above for a whole model in ONE launch (a training step repacks every parameter before each render and unpacks
+ * every gradient after each backward: ~150 tiny launches otherwise).  `jobs` is a DEVICE array; job i covers the 32x32
+ * destination tiles [first_tile, first_tile + ceil(d_rows/32)*ceil(d_cols/32)) of the launch, first_tile being the running
+ * sum over the jobs before it; total_tiles = the sum over all jobs.
+ *   kind 0: dst[i][j] = src[j*s_pitch + i]  (transpose)     kind 1: dst[i][j] = src[i*s_pitch + j]  (copy)
+ * for i < d_rows, j < d_cols, zero where the source index is outside s_rows x s_cols or src is null.
+ *   clift_pack_plane   = kind 0, src (comps x h*w, pitch h*w) -> dst (h*w x comps);  clift_unpack_plane the inverse
+ *   clift_pack_linear  = kind 0, src (n_out x n_in, pitch n_in) -> dst (k_pad x n_pad), + kind 1 for the bias (1 x n_pad)
+ *   clift_pack_linear_dgrad = kind 1, src (n_out x n_in) -> dst (round_up(out,16) x dgrad_pad(in)) */
+typedef struct {
+    const float* src;
+    float* dst;
+    int32_t s_pitch, s_rows, s_cols;
+    int32_t d_rows, d_cols;
+    int32_t kind;
+    int32_t first_tile;
+    int32_t reserved;
+} clift_pack_job;
+int32_t clift_pack_batch(const clift_pack_job* jobs, int32_t n_jobs, int32_t total_tiles, void* stream);
 
 /* Tensor-core operand of one nn.Linear for the tcgen05 head kernels: W [out][in] (+ bias[out] or null) -> tf32-exact
  * (hi, lo) pairs in 8-row K slabs (one tcgen05.mma k-step each), n_pad = round_up(out, 32); with a bias one more slab
