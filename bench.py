@@ -6,8 +6,10 @@
 One *step* = one pass of the render hot path over one synthetic frame: ray generation (R1-R4), ray march with
 TensoRF density lookup + transmittance scan (S1-C1), the RGB / semantic / instance heads on the active samples
 (F2-H3) and compositing + per-ray epilogue (C3), all heads on (C=21 classes, 3+3 slow-fast embedding dims).
-N>1: one process per GPU (torchrun), every rank renders its own frame (different camera yaw) with replicated
-parameters - rays shard with no data-path collective, so scaling is "weak" and `value` = all ranks' rays / max time.
+N>1: one process per GPU (torchrun), every rank renders its own frame with replicated parameters - the camera of rank r
+is rolled by 90 degrees x r about its optical axis, a different ray set of exactly the same cost (the cube and the ball are
+symmetric under that roll), so per-GPU work is fixed: rays shard with no data-path collective, scaling is "weak" and
+`value` = all ranks' rays / max time.
 
 `value`   : device-resident inputs (camera pose -> rays generated on the GPU), CUDA-event time per step, L2
             flushed between steps outside the timed spans.
@@ -170,7 +172,8 @@ def workload_config(args, world):
     return {"workload": f"synthetic {args.frame}x{args.frame} frame (solid-ball TensoRF scene, G=128^3), {args.samples} samples/ray, "
                         f"all heads (RGB + semantic C={N_CLS} + slow-fast instance d={N_INS}+{N_INS}), inference",
             "frame": args.frame, "samples_per_ray": args.samples, "grid": list(GRID), "rays_per_step_per_gpu": args.frame ** 2,
-            "parallelism": f"rays sharded, parameters replicated, {world} GPU(s), no data-path collective",
+            "parallelism": f"rays sharded, parameters replicated, {world} GPU(s), no data-path collective; rank r renders the "
+                           "frame of the camera rolled by 90 deg x r (same cost by symmetry: fixed per-GPU work)",
             "l2": "256 MB scratch write between timed steps (outside the timed spans); per-step working set ~1.5 GB >> 126 MB L2"}
 
 
@@ -212,7 +215,9 @@ def run_ours(args):
     f16_heads = args.heads in ("auto", "tensor16")
     H = W = args.frame
     n_rays = H * W
-    k, c2w = syn.camera(H, W, yaw_deg=7.0 * rank)
+    k, c2w = syn.camera(H, W)
+    roll = [(1.0, 0.0), (0.0, 1.0), (-1.0, 0.0), (0.0, -1.0)][rank % 4]            # (cos, sin) of 90 degrees x rank
+    c2w[:3, :3] = c2w[:3, :3] @ torch.tensor([[roll[0], -roll[1], 0.0], [roll[1], roll[0], 0.0], [0.0, 0.0, 1.0]])
     k_np, c2w_np = k.numpy(), c2w.numpy()
     flush = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
 
