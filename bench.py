@@ -17,6 +17,7 @@ symmetric under that roll), so per-GPU work is fixed: rays shard with no data-pa
             (as the reference's dataset produces them): H2D of the rays, render, D2H of the four output maps.
 `roofline`: the dominant kernel (MLP heads, compute-bound) and, as `roofline_march`, the HBM/L2-gather-bound
             march kernel, both from CUDA events recorded inside libclift_b200.so around those launches.
+`train_step`: (N=1) BASELINE config 3 through the same public classes - ms per training step (scripts/train_step_bench.py).
 `cpu_baseline` / `--impl reference`: the reference's algorithm on the host cores.  The reference is pure Python
             on PyTorch and /root/reference does not travel to the GPU box, so this is the reference-pinned
             port in oracle/ (kind "port"), replaying render_panopli.py's chunk loop (chunk=2048) on a bounded
@@ -330,6 +331,17 @@ def run_ours(args):
                            "note": "algorithmic gather bytes (1152 B per in-box sample) + ray/weight streams; factors are "
                                    "L2-resident so DRAM traffic is far below this by design"},
     }
+    if world == 1 and not args.no_train:
+        # BASELINE config 3 next to the headline: one training step (4096-ray main pass + 1024-ray instance pass with the
+        # slow-fast loss, both backwards, two fused Adam steps) through the same public classes; reported, not the metric
+        try:
+            flush = d_rays = None        # release the render bench's buffers first
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import train_step_bench
+            line["train_step"] = train_step_bench.measure(steps=10, warmup=3, device_index=local, with_cpu=False)
+        except Exception as e:      # never lose the bench line over the extra figure
+            line["train_step"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu:
         v, n, dt = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 131072)
         line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
@@ -349,6 +361,7 @@ def main():
     ap.add_argument("--samples", type=int, default=512)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the extra training-step figure (N=1 only)")
     ap.add_argument("--heads", default="auto", choices=["auto", "fma", "tensor", "tensor16"], help="MLP-head kernel family")
     args = ap.parse_args()
     if args.impl == "reference":

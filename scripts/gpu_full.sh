@@ -13,11 +13,11 @@ timeout 300 python scripts/tc_trace.py 2>&1 | head -26 > gpurun_out/tc_trace.txt
 timeout 300 python scripts/wgrad_trace.py 2>&1 | tail -150 > gpurun_out/wgrad_trace.txt
 timeout 900 python scripts/sweep.py > gpurun_out/sweep.md 2> gpurun_out/sweep.err; tail -20 gpurun_out/sweep.md
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_tc16.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_launch_tc16.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_launch_tc16.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:heads_tc16_forward -s 3 -c 1 -o gpurun_out/prof_heads_tc16 -f \
-    python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_heads_tc16.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_heads_tc16.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 3 -c 1 -o gpurun_out/prof_march -f \
-    python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_march.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu --no-train > gpurun_out/ncu_march.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 3 -c 1 -o gpurun_out/prof_wgrad_tc -f \
     python scripts/train_step_bench.py --profile-steps 2 > gpurun_out/ncu_wgrad_tc.log 2>&1
 ls -la gpurun_out/*.ncu-rep

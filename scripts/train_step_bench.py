@@ -60,8 +60,9 @@ def cpu_step(params, cfg, batch):
     orc.slow_fast_loss(feats, labels, ins_conf).backward()
 
 
-def main():
-    dev = torch.device("cuda", 0)
+def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False, profile_steps=0):
+    """One training-step measurement -> dict (bench.py reports it next to the render metric)."""
+    dev = torch.device("cuda", device_index)
     params = syn.make_field_params(0, GRID, C, D)
     aabb = syn.default_aabb()
     model = cl.TensorVMSplit(list(GRID), num_semantic_classes=C, dim_feature_instance=2 * D, use_semantic_mlp=True,
@@ -78,19 +79,18 @@ def main():
     batch = (rays, torch.rand(B, 3, generator=g).to(dev), torch.softmax(torch.randn(B, C, generator=g), -1).to(dev),
              torch.rand(B, generator=g).to(dev), ins_rays, torch.randint(1, 8, (N_INS,), generator=g).to(dev),
              torch.rand(N_INS, generator=g).to(dev))
-    adam = torch.optim.Adam if "--torch-adam" in sys.argv else cl.FusedAdam      # one launch per param group
+    adam = torch.optim.Adam if torch_adam else cl.FusedAdam      # one launch per param group
     opt_main = adam(model.get_optimizable_parameters(0.02, 0.001, 1e-8), betas=(0.9, 0.99))
     opt_ins = adam(model.get_optimizable_instance_parameters(0.02, 0.001, using_DINO=True), betas=(0.9, 0.999))
     torch.manual_seed(123)
-    if "--profile-steps" in sys.argv:       # under ncu: a few bare steps, no timing, no CPU leg
-        for _ in range(int(sys.argv[sys.argv.index("--profile-steps") + 1])):
+    if profile_steps:       # under ncu: a few bare steps, no timing, no CPU leg
+        for _ in range(profile_steps):
             gpu_step(model, rend, opt_main, opt_ins, batch)
-        torch.cuda.synchronize()
-        return
-    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        return None
+    for _ in range(warmup):
         gpu_step(model, rend, opt_main, opt_ins, batch)
-    torch.cuda.synchronize()
-    steps = 10
+    torch.cuda.synchronize(dev)
     l0 = L.launch_count()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -98,21 +98,29 @@ def main():
     for _ in range(steps):
         losses = gpu_step(model, rend, opt_main, opt_ins, batch)
     t1.record()
-    torch.cuda.synchronize()
+    torch.cuda.synchronize(dev)
     ms = t0.elapsed_time(t1) / steps
     launches = (L.launch_count() - l0) / steps
-    n_act, n_in, _, _ = rend.last_stats(dev)
-    cfg = orc.RenderConfig(aabb=aabb, grid_dim=GRID).refresh()
-    torch.set_num_threads(os.cpu_count() or 1)
-    c0 = time.perf_counter()
-    cpu_step(params, cfg, batch)
-    cpu_s = time.perf_counter() - c0
-    print(json.dumps({"workload": "training step: 4096-ray main pass (2 chunks, MSE+TV+dist+CE, Adam) + 1024-ray instance pass "
-                                  "(slow-fast loss, EMA, Adam), S=%d, G=128^3, C=21, d=3+3" % rend.n_samples,
-                      "ms_per_step": ms, "train_Mrays_per_s": (B + N_INS) / ms / 1e3, "clift_launches_per_step": launches,
-                      "optimizer": adam.__name__, "loss_main": float(losses[0]), "loss_slow_fast": float(losses[1]),
-                      "cpu_oracle_s_per_step": cpu_s, "cpu_cores": os.cpu_count(), "speedup_vs_cpu": cpu_s * 1e3 / ms,
-                      "gpu_mem_peak_GB": torch.cuda.max_memory_allocated() / 2 ** 30}))
+    out = {"workload": "training step: 4096-ray main pass (2 chunks, MSE+TV+dist+CE, Adam) + 1024-ray instance pass "
+                       "(slow-fast loss, EMA, Adam), S=%d, G=128^3, C=21, d=3+3" % rend.n_samples,
+           "ms_per_step": ms, "train_Mrays_per_s": (B + N_INS) / ms / 1e3, "clift_launches_per_step": launches,
+           "optimizer": adam.__name__, "loss_main": float(losses[0]), "loss_slow_fast": float(losses[1])}
+    if with_cpu:
+        cfg = orc.RenderConfig(aabb=aabb, grid_dim=GRID).refresh()
+        torch.set_num_threads(os.cpu_count() or 1)
+        c0 = time.perf_counter()
+        cpu_step(params, cfg, batch)
+        cpu_s = time.perf_counter() - c0
+        out.update({"cpu_oracle_s_per_step": cpu_s, "cpu_cores": os.cpu_count(), "speedup_vs_cpu": cpu_s * 1e3 / ms})
+    out["gpu_mem_peak_GB"] = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    return out
+
+
+def main():
+    prof = int(sys.argv[sys.argv.index("--profile-steps") + 1]) if "--profile-steps" in sys.argv else 0
+    out = measure(with_cpu=True, torch_adam="--torch-adam" in sys.argv, profile_steps=prof)
+    if out is not None:
+        print(json.dumps(out))
 
 
 if __name__ == "__main__":
