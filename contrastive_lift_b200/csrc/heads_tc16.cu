@@ -1040,11 +1040,11 @@ __device__ __forceinline__ float pow2_floor_ratio(float num_log2, float x) {   /
 }
 
 // header[0..7] = ca, cw, 1/(ca cw), out bound, in bound, L = max_n sum_k |W_nk|, max|W|, max|b|
-__global__ void __launch_bounds__(1024) tc16_plan_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out,
-                                                         int n_in, const float* __restrict__ in_bound_dev, float in_floor,
-                                                         float* __restrict__ header) {
+// body of the plan kernels (whole CTA of 1024 threads; `red` = 96 floats of shared memory)
+__device__ __forceinline__ void tc16_plan_body(const float* __restrict__ w, const float* __restrict__ bias, int n_out, int n_in,
+                                               const float* in_bound_dev, float in_floor, float* __restrict__ header,
+                                               float (*red)[32]) {
     // one warp per weight row (coalesced reads, fixed-order lane tree): it runs before every training forward
-    __shared__ float red[3][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float l1 = 0.0f, wm = 0.0f, bm = 0.0f;
     for (int n = warp; n < n_out; n += 32) {
@@ -1091,17 +1091,36 @@ __global__ void __launch_bounds__(1024) tc16_plan_kernel(const float* __restrict
     }
 }
 
+__global__ void __launch_bounds__(1024) tc16_plan_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out,
+                                                         int n_in, const float* __restrict__ in_bound_dev, float in_floor,
+                                                         float* __restrict__ header) {
+    __shared__ float red[3][32];
+    tc16_plan_body(w, bias, n_out, n_in, in_bound_dev, in_floor, header, red);
+}
+
+// clift_pack_linear_tc16_batch, launch 1: CTA c plans the jobs of chain c in table order - a chain is a stack of layers whose
+// input bound is the previous layer's output bound (read back from the header that layer's plan has just written)
+__global__ void __launch_bounds__(1024) tc16_plan_batch_kernel(const clift_tc16_job* __restrict__ jobs, int n_jobs) {
+    __shared__ float red[3][32];
+    for (int j = 0; j < n_jobs; ++j) {
+        if (jobs[j].chain != (int)blockIdx.x) continue;
+        const clift_tc16_job J = jobs[j];
+        tc16_plan_body(J.w, J.bias, J.n_out, J.n_in, J.in_bound, J.in_bound_floor, reinterpret_cast<float*>(J.dst), red);
+        __threadfence();
+        __syncthreads();
+    }
+}
+
 // W [out][in] * cw (+ bias * ca * cw in k row 0 of one more slab) -> per k-step slab of fp16 (hi, lo) pairs:
 // [hi|lo][2 k-chunks][n_pad][8] for n_pad > 128 else [2 k-chunks][hi|lo][n_pad][8]; zero padded.
 // `pair` (the CTA-pair copy, [rank][k-step][per-CTA slab], h = n_pad / 2):
 //   n_pad > 128 : CTA r holds rows [r h, r h + h): [hi | lo][2 k-chunks][h][8]
 //   n_pad <= 128: [Y: 2 k-chunks x n_pad rows][X: 2 k-chunks x h rows]; Y = hi (rank 0) / lo (rank 1) of all rows,
 //                 X = hi of rows [r h, r h + h)
-__global__ void pack_linear_tc16_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out, int n_in,
-                                        const float* __restrict__ header, __half* __restrict__ dst, __half* __restrict__ pair,
-                                        int n_pad, int slabs) {
+__device__ __forceinline__ void pack_linear_tc16_body(const float* __restrict__ w, const float* __restrict__ bias, int n_out,
+                                                      int n_in, const float* __restrict__ header, __half* __restrict__ dst,
+                                                      __half* __restrict__ pair, int n_pad, int slabs, int64_t idx) {
     const int64_t total = (int64_t)slabs * kStepK * n_pad;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const float ca = header[0], cw = header[1];
     const int k = (int)(idx / n_pad), n = (int)(idx % n_pad);
@@ -1138,6 +1157,30 @@ __global__ void pack_linear_tc16_kernel(const float* __restrict__ w, const float
         __half* b = (n < h ? r0 : r1) + (size_t)2 * n_pad * 8;
         b[((size_t)kc * h + (n % h)) * 8 + ki] = hi;
     }
+}
+
+__global__ void pack_linear_tc16_kernel(const float* __restrict__ w, const float* __restrict__ bias, int n_out, int n_in,
+                                        const float* __restrict__ header, __half* __restrict__ dst, __half* __restrict__ pair,
+                                        int n_pad, int slabs) {
+    pack_linear_tc16_body(w, bias, n_out, n_in, header, dst, pair, n_pad, slabs, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// clift_pack_linear_tc16_batch, launch 2: block b finds its job by binary search over the jobs' first-block prefix
+__global__ void __launch_bounds__(256) pack_linear_tc16_batch_kernel(const clift_tc16_job* __restrict__ jobs, int n_jobs) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first_block <= (int)blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const clift_tc16_job J = jobs[lo];
+    const int n_pad = (J.n_out + 31) & ~31, slabs = (J.n_in + kStepK - 1) / kStepK + (J.bias ? 1 : 0);
+    const float* header = reinterpret_cast<const float*>(J.dst);
+    __half* single = reinterpret_cast<__half*>(reinterpret_cast<float*>(J.dst) + kHeaderFloats);
+    pack_linear_tc16_body(J.w, J.bias, J.n_out, J.n_in, header, single, single + (size_t)slabs * 2 * kStepK * n_pad, n_pad, slabs,
+                          (int64_t)((int)blockIdx.x - J.first_block) * 256 + threadIdx.x);
 }
 
 // dst[slot] = max |x| (dst zeroed by the caller; |x| >= 0 so the uint order of the bits is the float order)
@@ -1363,6 +1406,17 @@ extern "C" int32_t clift_pack_linear_tc16(const float* w, const float* bias, voi
     pack_linear_tc16_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
         w, bias, n_out, n_in, header, single, single + (size_t)slabs * 2 * kStepK * n_pad, n_pad, slabs);
     CLIFT_AFTER_LAUNCH("pack_linear_tc16_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_pack_linear_tc16_batch(const clift_tc16_job* jobs, int32_t n_jobs, int32_t n_chains, int32_t total_blocks,
+                                                void* stream) {
+    CLIFT_CHECK_ARG(n_jobs >= 0 && n_chains >= 0 && total_blocks >= 0 && (n_jobs == 0 || jobs), "null table or negative size");
+    if (n_jobs == 0 || n_chains == 0 || total_blocks == 0) return CLIFT_OK;
+    tc16_plan_batch_kernel<<<(unsigned)n_chains, 1024, 0, (cudaStream_t)stream>>>(jobs, n_jobs);
+    CLIFT_AFTER_LAUNCH("tc16_plan_batch_kernel");
+    pack_linear_tc16_batch_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs, n_jobs);
+    CLIFT_AFTER_LAUNCH("pack_linear_tc16_batch_kernel");
     return CLIFT_OK;
 }
 

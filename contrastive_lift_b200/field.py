@@ -123,7 +123,8 @@ class _PackedMlp:
                     self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
                 batch.dgrad(l.weight.data, self.w_dgrad[i], l.out_features, l.in_features)
 
-    def pack(self, lib, stream, training: bool, in_bound_ptr: Optional[int] = None, in_bound_floor: float = 1.0):
+    def pack(self, lib, stream, training: bool, in_bound_ptr: Optional[int] = None, in_bound_floor: float = 1.0,
+             tc16: Optional["L.Tc16Batch"] = None, chain: int = 0):
         """Tensor-core operands of this stack (the fp32 layouts travel through ``collect``).
         ``in_bound_ptr`` / ``in_bound_floor``: bound on |input| of the first layer for the fp16-split operand chain
         (device scalar and/or constant; xyz, sin/cos and unit directions are bounded by 1)."""
@@ -142,8 +143,12 @@ class _PackedMlp:
             if nb > 0 and bound_ptr != -1:   # scales chained layer to layer
                 if self.w_tc16[i] is None:
                     self.w_tc16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
-                L.check(lib.clift_pack_linear_tc16(w, b, L.ptr(self.w_tc16[i]), l.out_features, l.in_features, bound_ptr,
-                                                   float(floor), stream))
+                if tc16 is not None:       # queued: the whole model's operands go out as one batched call
+                    tc16.add(l.weight.data, l.bias.data if l.bias is not None else None, self.w_tc16[i], l.out_features,
+                             l.in_features, bound_ptr, floor, chain)
+                else:
+                    L.check(lib.clift_pack_linear_tc16(w, b, L.ptr(self.w_tc16[i]), l.out_features, l.in_features, bound_ptr,
+                                                       float(floor), stream))
                 bound_ptr, floor = self.w_tc16[i].data_ptr() + 12, 0.0
             else:
                 bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
@@ -538,12 +543,14 @@ class PackedField:
         L.check(lib.clift_tc16_factor_bound(vp3(*[L.ptr(t) for t in ap]), vp3(*[L.ptr(t) for t in al]),
                                             i3(*[t.numel() for t in ap]), i3(*[t.numel() for t in al]),
                                             L.ptr(self.tc16_scratch), st))
-        self.basis.pack(lib, st, training, self.tc16_scratch.data_ptr() + 24, 0.0)
-        self.rgb.pack(lib, st, training, self.basis.out_bound_ptr(), 1.0)
-        for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
+        tc16 = L.Tc16Batch()          # chain 0: basis -> rgb stack; chains 1-3: the xyz stacks
+        self.basis.pack(lib, st, training, self.tc16_scratch.data_ptr() + 24, 0.0, tc16, 0)
+        self.rgb.pack(lib, st, training, self.basis.out_bound_ptr(), 1.0, tc16, 0)
+        for chain, (name, m) in enumerate((("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)), start=1):
             if m is not None:
                 # a grid-mode head's stack stays off the fp16-split operand chain (bound pointer -1): it runs on the FMA kernels
-                m.pack(lib, st, training, -1 if name in self.grid_basis else None)
+                m.pack(lib, st, training, -1 if name in self.grid_basis else None, 1.0, tc16, chain)
+        tc16.run(lib, self.device)
         f = self.field
         for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
             if name in self.grid_basis:

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -79,6 +79,12 @@ class PackJob(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class Tc16Job(C.Structure):
+    _fields_ = [("w", _vp), ("bias", _vp), ("dst", _vp), ("in_bound", _vp), ("in_bound_floor", C.c_float),
+                ("n_out", C.c_int32), ("n_in", C.c_int32), ("chain", C.c_int32), ("first_block", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_int64)]
 
@@ -99,6 +105,7 @@ SIGNATURES = {
     "clift_profile_stage_ms": (C.c_int32, [_fp]),
     "clift_pack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_pack_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
+    "clift_pack_linear_tc16_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_unpack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_pack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_unpack_linear": (C.c_int32, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
@@ -253,3 +260,34 @@ class PackBatch:
         table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
         check(lib.clift_pack_batch(ptr(table), len(self.jobs), int(self.tiles), stream_ptr(device)))
         self.jobs, self.tiles = [], 0
+
+
+class Tc16Batch:
+    """Collects fp16-split operand jobs (clift_tc16_job) of a model and runs them as ONE clift_pack_linear_tc16_batch call
+    (two launches).  ``chain``: layers whose input bound chains through the previous layer's header share a chain id."""
+
+    def __init__(self):
+        self.jobs = []
+        self.blocks = 0
+        self.chains = 0
+
+    def add(self, w, bias, dst, n_out, n_in, in_bound_ptr, floor, chain):
+        j = Tc16Job()
+        j.w, j.bias, j.dst = ptr(w), ptr(bias), ptr(dst)
+        j.in_bound = in_bound_ptr
+        j.in_bound_floor = float(floor)
+        j.n_out, j.n_in, j.chain = int(n_out), int(n_in), int(chain)
+        j.first_block = self.blocks
+        n_pad = (n_out + 31) // 32 * 32
+        slabs = (n_in + 15) // 16 + (1 if bias is not None else 0)
+        self.blocks += (slabs * 16 * n_pad + 255) // 256
+        self.chains = max(self.chains, chain + 1)
+        self.jobs.append(j)
+
+    def run(self, lib, device):
+        if not self.jobs:
+            return
+        raw = bytes((Tc16Job * len(self.jobs))(*self.jobs))
+        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
+        check(lib.clift_pack_linear_tc16_batch(ptr(table), len(self.jobs), int(self.chains), int(self.blocks), stream_ptr(device)))
+        self.jobs, self.blocks, self.chains = [], 0, 0

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 8
+#define CLIFT_ABI_VERSION 9
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -235,6 +235,24 @@ int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32
 int64_t clift_tc16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias);
 int32_t clift_pack_linear_tc16(const float* w, const float* bias, void* dst, int32_t n_out, int32_t n_in,
                                const float* in_bound, float in_bound_floor, void* stream);
+/* The same for a whole model in two launches.  `jobs` is a DEVICE array in dependency order; jobs with the same `chain`
+ * (0 .. n_chains-1) are one stack of layers planned one after the other by one CTA, so a job's `in_bound` may point at
+ * header word 3 of the previous job of its chain.  Job i owns the pack blocks [first_block, first_block + ceil(slabs*16*n_pad
+ * / 256)) of the second launch (running sum, n_pad = round_up(n_out,32), slabs = ceil(n_in/16) + (bias != null));
+ * total_blocks = the sum.  Same argument rules as clift_pack_linear_tc16 (not re-checked per job). */
+typedef struct {
+    const float* w;
+    const float* bias;
+    void* dst;
+    const float* in_bound;
+    float in_bound_floor;
+    int32_t n_out, n_in;
+    int32_t chain;
+    int32_t first_block;
+    int32_t reserved;
+} clift_tc16_job;
+int32_t clift_pack_linear_tc16_batch(const clift_tc16_job* jobs, int32_t n_jobs, int32_t n_chains, int32_t total_blocks,
+                                     void* stream);
 /* Bound on |plane * line| products of a VM factor set for the chain above: scratch8[6] = max_mode max|plane| * max|line|
  * (scratch8 = 8 device floats; packed or unpacked factors, only the element counts matter). */
 int32_t clift_tc16_factor_bound(const float* const* planes3, const float* const* lines3, const int64_t* plane_elems3,
