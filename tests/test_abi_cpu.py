@@ -92,3 +92,46 @@ def test_unsupported_configurations_fail_loudly():
         cl.TensorVMSplit([8, 8, 8], num_semantic_classes=4, dim_feature_instance=6, use_semantic_mlp=False)
     with pytest.raises(L.CliftError):
         cl.TensoRFRenderer(syn.default_aabb(), [8, 8, 8], stop_semantic_grad=False)
+
+
+def test_ctypes_structs_match_the_compiled_header(tmp_path):
+    """Every struct of include/clift_b200.h, compiled as plain C by gcc, has the size of its ctypes mirror in lib.py."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = [("clift_mlp", L.Mlp), ("clift_mlp_grad", L.MlpGrad), ("clift_grid_head", L.GridHead),
+             ("clift_grid_head_grad", L.GridHeadGrad), ("clift_field", L.Field), ("clift_field_grad", L.FieldGrad),
+             ("clift_render_cfg", L.RenderCfg), ("clift_render_out", L.RenderOut), ("clift_adam_tensor", L.AdamTensor),
+             ("clift_pack_job", L.PackJob), ("clift_tc16_job", L.Tc16Job)]
+    body = "".join(f'printf("%zu\\n", sizeof({c}));' for c, _ in pairs)
+    src = tmp_path / "sizes.c"
+    src.write_text(f'#include <stdio.h>\n#include "clift_b200.h"\nint main(void) {{ {body} return 0; }}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    for (cname, ctype), size in zip(pairs, sizes):
+        assert C.sizeof(ctype) == size, (cname, C.sizeof(ctype), size)
+
+
+def test_batched_pack_job_tables(monkeypatch):
+    """Host side of clift_pack_batch / clift_pack_linear_tc16_batch: tile and block prefixes, job shapes (no GPU needed)."""
+    monkeypatch.setattr(L, "ptr", lambda t: None if t is None else 0x1000)
+    b = L.PackBatch()
+    x = torch.zeros(1)
+    b.plane(x, x, 48, 20, 24)              # (1,48,20,24) -> [480][48]
+    b.linear(x, x, x, x, 21, 256)          # W [21][256] -> W^T [256][64] + bias [64]
+    b.dgrad(x, x, 21, 256)                 # -> [32][256]
+    b.unlinear(x, x, x, None, 3, 150)      # packed grad [160][64] -> [3][150], no bias
+    j = b.jobs
+    assert [(q.d_rows, q.d_cols, q.kind) for q in j] == [(480, 48, 0), (256, 64, 0), (1, 64, 1), (32, 256, 1), (3, 150, 0)]
+    tiles = [15 * 2, 8 * 2, 1 * 2, 1 * 8, 1 * 5]
+    assert [q.first_tile for q in j] == [sum(tiles[:i]) for i in range(5)] and b.tiles == sum(tiles)
+    assert (j[1].s_pitch, j[1].s_rows, j[1].s_cols) == (256, 21, 256) and (j[4].s_pitch, j[4].s_rows, j[4].s_cols) == (64, 150, 3)
+    t = L.Tc16Batch()
+    t.add(x, None, x, 27, 144, 0x2000, 0.0, 0)       # basis: no bias, 9 slabs x 16 x 32
+    t.add(x, x, x, 128, 150, 0x3000, 1.0, 0)         # rgb layer 0: 10 + 1 slabs x 16 x 128
+    t.add(x, x, x, 256, 3, None, 1.0, 1)             # xyz layer 0 of another chain: 1 + 1 slabs x 16 x 256
+    assert [q.first_block for q in t.jobs] == [0, 18, 18 + 88] and t.blocks == 18 + 88 + 32 and t.chains == 2
