@@ -195,12 +195,11 @@ def run_ours(args):
     import contrastive_lift_b200 as cl
     from contrastive_lift_b200 import lib as L
     from contrastive_lift_b200 import synthetic as syn
-    from oracle import clift_oracle as orc   # cpu_baseline leg + geometry helper only
 
     lib = L.load()
     params = syn.make_field_params(0, GRID, N_CLS, N_INS)
     aabb = syn.default_aabb()
-    ratio = orc.ratio_for_samples(aabb, GRID, args.samples)
+    ratio = syn.ratio_for_samples(aabb, GRID, args.samples)
     model = cl.TensorVMSplit(list(GRID), num_semantics_comps=(32, 32, 32), num_instance_comps=(32, 32, 32),
                              num_semantic_classes=N_CLS, dim_feature_instance=2 * N_INS, use_semantic_mlp=True,
                              use_instance_mlp=True, slow_fast_mode=True)

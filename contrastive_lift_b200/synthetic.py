@@ -105,6 +105,16 @@ def params_checksum(params: Dict[str, torch.Tensor]) -> float:
     return tot
 
 
+def ratio_for_samples(aabb: torch.Tensor, grid_dim: Sequence[int], n_samples: int) -> float:
+    """the ``step_ratio`` that makes ``TensoRFRenderer.update_step_ratio`` (renderer:59-78) yield ``n_samples``
+    samples per ray: n = int(|extent| / (mean(extent / (G - 1 + 1e-3)) * ratio)) + 1."""
+    extent = aabb[1] - aabb[0]
+    g = torch.as_tensor(list(grid_dim), dtype=torch.long)
+    units = extent / (g - 1 + 1e-3)
+    diag = torch.sqrt(torch.sum(torch.square(extent)))
+    return float(diag / ((n_samples - 0.5) * torch.mean(units)))
+
+
 def default_aabb() -> torch.Tensor:
     return torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]], dtype=torch.float32)
 

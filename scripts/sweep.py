@@ -12,7 +12,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import contrastive_lift_b200 as cl  # noqa: E402
 from contrastive_lift_b200 import lib as L, synthetic as syn  # noqa: E402
-from oracle import clift_oracle as orc  # noqa: E402  (step-ratio helper only)
 import bench  # noqa: E402
 
 GRID = (128, 128, 128)
@@ -33,7 +32,7 @@ def main():
     for frame in (256, 400, 800, 1600):
         for S in (128, 256, 512, 1024):
             rend = cl.TensoRFRenderer(aabb, list(GRID), semantic_weight_mode="softmax").to(dev)
-            rend.update_step_ratio(orc.ratio_for_samples(aabb, GRID, S))
+            rend.update_step_ratio(syn.ratio_for_samples(aabb, GRID, S))
             assert rend.n_samples == S
             rend.max_active_per_ray = 192
             k, c2w = syn.camera(frame, frame)

@@ -4,12 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import contrastive_lift_b200 as cl
 from contrastive_lift_b200 import lib as L, synthetic as syn
-from oracle import clift_oracle as orc
 
 grid = (128, 128, 128)
 params = syn.make_field_params(0, grid, 21, 3)
 aabb = syn.default_aabb()
-ratio = orc.ratio_for_samples(aabb, grid, 512)
+ratio = syn.ratio_for_samples(aabb, grid, 512)
 model = cl.TensorVMSplit(list(grid), num_semantic_classes=21, dim_feature_instance=6, use_semantic_mlp=True,
                          use_instance_mlp=True, slow_fast_mode=True)
 model.load_state_dict(params)

@@ -15,7 +15,6 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import contrastive_lift_b200 as cl  # noqa: E402
 from contrastive_lift_b200 import lib as L, synthetic as syn  # noqa: E402
-from oracle import clift_oracle as orc  # noqa: E402  (cpu baseline leg only)
 
 GRID, C, D = (128, 128, 128), 21, 3
 B, CHUNK, N_INS = 4096, 2048, 1024
@@ -47,6 +46,7 @@ def gpu_step(model, rend, opt_main, opt_ins, batch):
 
 
 def cpu_step(params, cfg, batch):
+    from oracle import clift_oracle as orc      # the CPU leg is the only user of the oracle
     rays, rgbs, probs, confs, ins_rays, labels, ins_conf = (t.cpu() for t in batch)
     p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     g = torch.Generator().manual_seed(0)
@@ -106,6 +106,7 @@ def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False
            "ms_per_step": ms, "train_Mrays_per_s": (B + N_INS) / ms / 1e3, "clift_launches_per_step": launches,
            "optimizer": adam.__name__, "loss_main": float(losses[0]), "loss_slow_fast": float(losses[1])}
     if with_cpu:
+        from oracle import clift_oracle as orc
         cfg = orc.RenderConfig(aabb=aabb, grid_dim=GRID).refresh()
         torch.set_num_threads(os.cpu_count() or 1)
         c0 = time.perf_counter()
