@@ -60,8 +60,14 @@ def cpu_step(params, cfg, batch):
     orc.slow_fast_loss(feats, labels, ins_conf).backward()
 
 
-def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False, profile_steps=0):
-    """One training-step measurement -> dict (bench.py reports it next to the render metric)."""
+def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False, profile_steps=0, rays=None, classes=None):
+    """One training-step measurement -> dict (bench.py reports it next to the render metric).  ``rays`` / ``classes``
+    override the main-pass batch and the class count (BASELINE config 4 per-GPU share: 1024 rays, C = 2)."""
+    global B, C
+    if rays:
+        B = int(rays)
+    if classes:
+        C = int(classes)
     dev = torch.device("cuda", device_index)
     params = syn.make_field_params(0, GRID, C, D)
     aabb = syn.default_aabb()
@@ -101,8 +107,8 @@ def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False
     torch.cuda.synchronize(dev)
     ms = t0.elapsed_time(t1) / steps
     launches = (L.launch_count() - l0) / steps
-    out = {"workload": "training step: 4096-ray main pass (2 chunks, MSE+TV+dist+CE, Adam) + 1024-ray instance pass "
-                       "(slow-fast loss, EMA, Adam), S=%d, G=128^3, C=21, d=3+3" % rend.n_samples,
+    out = {"workload": "training step: %d-ray main pass (%d chunk(s), MSE+TV+dist+CE, Adam) + 1024-ray instance pass "
+                       "(slow-fast loss, EMA, Adam), S=%d, G=128^3, C=%d, d=3+3" % (B, (B + CHUNK - 1) // CHUNK, rend.n_samples, C),
            "ms_per_step": ms, "train_Mrays_per_s": (B + N_INS) / ms / 1e3, "clift_launches_per_step": launches,
            "optimizer": adam.__name__, "loss_main": float(losses[0]), "loss_slow_fast": float(losses[1])}
     if with_cpu:
@@ -119,7 +125,9 @@ def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False
 
 def main():
     prof = int(sys.argv[sys.argv.index("--profile-steps") + 1]) if "--profile-steps" in sys.argv else 0
-    out = measure(with_cpu=True, torch_adam="--torch-adam" in sys.argv, profile_steps=prof)
+    arg = lambda k: int(sys.argv[sys.argv.index(k) + 1]) if k in sys.argv else None
+    out = measure(with_cpu="--no-cpu" not in sys.argv, torch_adam="--torch-adam" in sys.argv, profile_steps=prof,
+                  rays=arg("--rays"), classes=arg("--classes"))
     if out is not None:
         print(json.dumps(out))
 
