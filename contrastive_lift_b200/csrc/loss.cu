@@ -410,11 +410,8 @@ extern "C" int32_t clift_tv_loss(const float* plane_hwc, int32_t comps, int32_t 
                                  float grad_scale, void* stream) {
     CLIFT_CHECK_ARG(plane_hwc && comps > 0 && h > 0 && w > 0, "null pointer or bad size");
     if (loss) {
-        static bool attr_set = false;
-        if (!attr_set) {     // 16 CTAs per cluster is above the portable 8: opt in once
-            CLIFT_CUDA(cudaFuncSetAttribute(tv_value_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            attr_set = true;
-        }
+        // 16 CTAs per cluster is above the portable 8: opt in (per device, so on every call - it is a host-side table write)
+        CLIFT_CUDA(cudaFuncSetAttribute(tv_value_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(kTvCluster);
         lc.blockDim = dim3(1024);
