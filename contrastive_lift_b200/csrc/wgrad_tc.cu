@@ -8,11 +8,11 @@
 // One launch covers all layers.  A CTA owns (layer, split): it walks tiles split, split + n_splits, ... and accumulates the
 // whole K x N gradient block in tensor memory (ceil(K/128) accumulators of 128 lanes x N fp32 columns, <= 512 columns),
 // then adds it to the packed gradient with vector reductions - one flush per CTA instead of one per tile.
-//   warps 1..8 (256 loader threads): per 16-record stage, 16-byte cp.async copies of the A and dZ row pieces straight into
+//   warps 1..8 (256 loader threads): per ring stage (one 16-record group, two for small layers), 16-byte cp.async copies of the A and dZ row pieces straight into
 //       the canonical no-swizzle K-major layout [record chunk of 4][row][4 floats], then the 3xTF32 split in place
 //       (hi = x with the low 13 mantissa bits cleared, lo = x - hi); a ring of 3 (256 x 256 layer) to 8 (small layers)
 //       stages with full/empty mbarriers keeps ring-depth - 1 stages of loads in flight
-//   warp 0, one lane: per stage 2 k-steps x ceil(K/128) row blocks x 3 products (A_hi*Z_hi, A_hi*Z_lo, A_lo*Z_hi) of
+//   warp 0, one lane: per 16-record group 2 k-steps x ceil(K/128) row blocks x 3 products (A_hi*Z_hi, A_hi*Z_lo, A_lo*Z_hi) of
 //       tcgen05.mma kind::tf32 (M = 128, N = n_pad, K = 8), fp32 accumulation; tcgen05.commit releases the stage
 // fp32-faithful like the 3xTF32 forward heads: products carry 21+ significant bits per operand.
 #include "launchers.h"
@@ -25,7 +25,7 @@ long long* get_tc_trace();   // heads_tc.cu (clift_debug_tc_trace): here 4 int64
 namespace {
 
 constexpr int kTile = CLIFT_TILE;
-constexpr int kWtChunkM = 16;                    // records per ring stage = two kind::tf32 k-steps
+constexpr int kWtChunkM = 16;                    // records per stash group = two kind::tf32 k-steps
 constexpr int kWtLoaders = 256;
 constexpr int kWtThreads = 32 + kWtLoaders;
 constexpr int kWtMaxStages = 8;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
     }
 }
 
-// Stage layout (part = (K + N) * 64 bytes): [A_hi: 4 chunks x K rows x 16 B][Z_hi: 4 x N x 16 B][A_lo][Z_lo].
+// Stage layout (part = groups * (K + N) * 64 bytes): [A_hi: 4*groups chunks x K rows x 16 B][Z_hi: 4*groups x N x 16 B][A_lo][Z_lo].
 // The loaders cp.async the RAW fp32 pieces into the hi half (no register staging: register-destination loads of two stages
 // end up sharing hardware scoreboards and serialise), then every thread splits exactly the pieces it copied itself, in
 // place (hi) and into the lo half, and publishes the stage to the tensor core.
