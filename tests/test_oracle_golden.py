@@ -152,6 +152,40 @@ def test_oracle_against_live_reference_random_config():
         assert torch.equal(a, b)
 
 
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("sem_grid,ins_grid,slow_fast", [(32, 32, False), (48, None, True), (None, 16, True)])
+def test_oracle_against_live_reference_grid_heads(sem_grid, ins_grid, slow_fast):
+    """Grid-mode semantic / instance heads (allgrid.yaml family): forward, instance pass and gradients against the
+    imported reference on a fresh configuration (build container only)."""
+    grid = (10, 12, 9)
+    params = syn.make_field_params(81, grid, 5, 3, slow_fast=slow_fast, sem_grid_comps=sem_grid, ins_grid_comps=ins_grid)
+    aabb = syn.default_aabb()
+    model = refload.build_model(params, grid, 5, 3, slow_fast, True, sem_grid_comps=sem_grid, ins_grid_comps=ins_grid)
+    rend = refload.build_renderer(aabb, grid)
+    cfg = orc.RenderConfig(aabb=aabb, grid_dim=grid, slow_fast=slow_fast).refresh()
+    rays = syn.random_rays(6, 48)
+    torch.manual_seed(3)
+    ref = rend(model, rays, 1.0, False, True)
+    torch.manual_seed(3)
+    jitter = 1.0 * torch.rand(rays.shape[0], 1)
+    coin = bool(torch.rand((1,)) < 0.5)
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    got = orc.render_forward(p, cfg, rays, jitter, coin)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    (ref[0].sum() + ref[1].exp().sum() + (ref[2] ** 2).sum()).backward()
+    (got[0].sum() + got[1].exp().sum() + (got[2] ** 2).sum()).backward()
+    for k, prm in model.named_parameters():
+        g_ref = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        g = p[k].grad if p[k].grad is not None else torch.zeros_like(prm)
+        assert torch.allclose(g_ref, g, rtol=1e-5, atol=1e-9), k
+    torch.manual_seed(4)
+    ins_ref, pts_ref = rend.forward_instance_feature(model, rays, 1.0, True)
+    torch.manual_seed(4)
+    ins, pts = orc.render_instance_feature(params, cfg, rays, 1.0 * torch.rand(rays.shape[0], 1))
+    assert torch.equal(ins_ref, ins) and torch.equal(pts_ref, pts)
+
+
 # ---- SURVEY 8(f): epoch-boundary volume operations, Adam, nearest centroid -------------------------------
 EPOCH_CASES = {"a": 4, "b": 4}
 
