@@ -225,11 +225,17 @@ __global__ void __launch_bounds__(kLossThreads) slowfast_kernel(const float* __r
 // ----------------------------------------------------------------------------------------------
 // vanilla contrastive (loss.py:62-82)
 // ----------------------------------------------------------------------------------------------
+// Same organisation as the slow-fast kernel: one thread-block cluster, every CTA holds all features / labels, one warp per
+// sample i with its lanes splitting the partners j.  The gradient of sample i needs 1/p_j and 1/Z_j of every partner, so after
+// the first pass the CTAs all-gather those two vectors through distributed shared memory (each reads the entries its peers own).
 __global__ void __launch_bounds__(kLossThreads) contrastive_kernel(const float* __restrict__ feats, const long long* __restrict__ labels,
                                                                    int n, int d, float temperature, float* __restrict__ loss_out,
                                                                    float* __restrict__ grad) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float s_red[33];
+    __shared__ float s_part[1];
+    const unsigned rank = cluster_ctarank(), csize = cluster_nctarank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     long long* s_lab = reinterpret_cast<long long*>(smem_raw);   // [n]
     float* s_feat = reinterpret_cast<float*>(s_lab + n);           // [n][d]
     float* s_a = s_feat + (size_t)n * d;                           // [n] 1/p_i if i contributes else 0
@@ -237,11 +243,11 @@ __global__ void __launch_bounds__(kLossThreads) contrastive_kernel(const float* 
     for (int i = threadIdx.x; i < n; i += blockDim.x) s_lab[i] = labels[i];
     for (int i = threadIdx.x; i < n * d; i += blockDim.x) s_feat[i] = feats[i];
     __syncthreads();
-    float my_log = 0.0f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float my_log = 0.0f;                                           // lane 0 of each warp accumulates
+    for (int i = (int)rank * n_warps + warp; i < n; i += (int)csize * n_warps) {
         const long long l = s_lab[i];
         float p = 0.0f, z = 0.0f;
-        for (int j = 0; j < n; ++j) {
+        for (int j = lane; j < n; j += 32) {
             float dsq = 0.0f;
             for (int k = 0; k < d; ++k) {
                 const float df = s_feat[i * d + k] - s_feat[j * d + k];
@@ -252,31 +258,52 @@ __global__ void __launch_bounds__(kLossThreads) contrastive_kernel(const float* 
             z += e;
             if (pos) p += e;
         }
-        const float prob = p / z;
-        const bool valid = prob != 0.0f;
-        if (valid) my_log += logf(prob);
-        s_a[i] = valid ? 1.0f / p : 0.0f;
-        s_b[i] = valid ? 1.0f / z : 0.0f;
+        p = warp_sum_xor(p);
+        z = warp_sum_xor(z);
+        if (lane == 0) {
+            const float prob = p / z;
+            const bool valid = prob != 0.0f;
+            if (valid) my_log += logf(prob);
+            s_a[i] = valid ? 1.0f / p : 0.0f;
+            s_b[i] = valid ? 1.0f / z : 0.0f;
+        }
     }
-    const float tot = block_sum(my_log, s_red);
-    if (threadIdx.x == 0) loss_out[0] = -tot / (float)n;
-    if (!grad) return;
+    const float b_log = block_sum(my_log, s_red);
+    if (threadIdx.x == 0) s_part[0] = b_log;
+    cluster_sync_all();
+    // all-gather 1/p and 1/Z: sample i belongs to CTA (i / n_warps) % csize
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned owner = (unsigned)(i / n_warps) % csize;
+        if (owner != rank) {
+            s_a[i] = ld_dsmem_f32(&s_a[i], owner);
+            s_b[i] = ld_dsmem_f32(&s_b[i], owner);
+        }
+    }
+    float tot = 0.0f;
+    for (unsigned r = 0; r < csize; ++r) tot += ld_dsmem_f32(&s_part[0], r);      // rank order: fixed
+    cluster_sync_all();                                            // peers' vectors stay alive until everybody has read them
+    if (rank == 0 && threadIdx.x == 0) loss_out[0] = -tot / (float)n;
+    if (!grad) return;
+    for (int i = (int)rank * n_warps + warp; i < n; i += (int)csize * n_warps) {
         const long long l = s_lab[i];
-        for (int k = 0; k < d; ++k) grad[i * d + k] = 0.0f;
-        for (int j = 0; j < n; ++j) {
-            if (j == i) continue;
-            float dsq = 0.0f;
-            for (int k = 0; k < d; ++k) {
-                const float df = s_feat[i * d + k] - s_feat[j * d + k];
-                dsq += df * df;
+        for (int k = 0; k < d; ++k) {
+            float g = 0.0f;
+            for (int j = lane; j < n; j += 32) {
+                if (j == i) continue;
+                float dsq = 0.0f;
+                for (int kk = 0; kk < d; ++kk) {
+                    const float df = s_feat[i * d + kk] - s_feat[j * d + kk];
+                    dsq += df * df;
+                }
+                const bool pos = s_lab[j] == l;
+                const float temp = pos ? temperature : 1.0f;
+                const float sx = expf(-dsq / temp), e = expf(sx);
+                const float m = pos ? 1.0f : 0.0f;
+                const float c = e * sx * (2.0f / temp) * ((m * s_a[i] - s_b[i]) + (m * s_a[j] - s_b[j])) / (float)n;
+                g += c * (s_feat[i * d + k] - s_feat[j * d + k]);
             }
-            const bool pos = s_lab[j] == l;
-            const float temp = pos ? temperature : 1.0f;
-            const float s = expf(-dsq / temp), e = expf(s);
-            const float m = pos ? 1.0f : 0.0f;
-            const float c = e * s * (2.0f / temp) * ((m * s_a[i] - s_b[i]) + (m * s_a[j] - s_b[j])) / (float)n;
-            for (int k = 0; k < d; ++k) grad[i * d + k] += c * (s_feat[i * d + k] - s_feat[j * d + k]);
+            g = warp_sum_xor(g);
+            if (lane == 0) grad[i * d + k] = g;
         }
     }
 }
@@ -390,8 +417,22 @@ extern "C" int32_t clift_contrastive_loss(const float* features, const int64_t* 
     const size_t smem = (size_t)n * 8 + (size_t)n * dim * 4 + (size_t)n * 8 + 64;
     CLIFT_CHECK_SUPPORTED(smem <= 200 * 1024, "contrastive loss: N*D too large for one CTA's shared memory");
     CLIFT_CUDA(cudaFuncSetAttribute(contrastive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    contrastive_kernel<<<1, kLossThreads, smem, (cudaStream_t)stream>>>(features, (const long long*)labels, n, dim, temperature,
-                                                                        loss, grad_features);
+    CLIFT_CUDA(cudaFuncSetAttribute(contrastive_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    const int cluster = n >= 512 ? 16 : (n >= 64 ? 8 : 1);        // one warp per sample: 32 warps per CTA
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)cluster);
+    lc.blockDim = dim3(kLossThreads);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CLIFT_CUDA(cudaLaunchKernelEx(&lc, contrastive_kernel, features, (const long long*)labels, (int)n, (int)dim, temperature, loss,
+                                  grad_features));
     CLIFT_AFTER_LAUNCH("contrastive_kernel");
     return CLIFT_OK;
 }
