@@ -98,3 +98,45 @@ def test_oracle_forward_is_bit_equal_to_the_live_reference(seed, n_samples, n_cl
         assert torch.equal(a, b)
     if empty_scene and n_samples >= 56:      # sigma = softplus(-10 +- 0.1): alpha = sigma * delta * 25 stays below the 1e-4 threshold
         assert int(det["active"].sum()) == 0
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(1, 90), d=st.integers(1, 4), n_labels=st.integers(1, 9), seed=st.integers(0, 10_000))
+def test_slow_fast_loss_oracle_matches_the_live_reference(n, d, n_labels, seed):
+    """trainer:256-310 on random batches: odd N, N = 1, a single label, labels missing from one half."""
+    gen = torch.Generator().manual_seed(seed)
+    params = syn.make_field_params(3, (8, 8, 8), 4, 3)
+    model = refload.build_model(params, (8, 8, 8), 4, 3)
+    model.dim_feature_instance = 2 * d
+    feats = torch.randn(n, 2 * d, generator=gen).requires_grad_(True)
+    labels = torch.randint(1, n_labels + 1, (n,), generator=gen)
+    conf = torch.rand(n, generator=gen)
+    l_ref = refload.slow_fast_loss(model, labels, feats, conf, use_ema=False)
+    f2 = feats.detach().clone().requires_grad_(True)
+    l_orc = orc.slow_fast_loss(f2, labels, conf)
+    assert torch.equal(l_ref.detach(), l_orc.detach()) or (torch.isnan(l_ref) and torch.isnan(l_orc))
+    if l_ref.requires_grad and not torch.isnan(l_ref):
+        l_ref.backward()
+        l_orc.backward()
+        assert torch.allclose(feats.grad, f2.grad, rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@settings(max_examples=25, deadline=None)
+@given(n=st.integers(2, 70), d=st.integers(1, 6), n_labels=st.integers(1, 8), temp=st.sampled_from([1.0, 10.0, 100.0]),
+       seed=st.integers(0, 10_000))
+def test_contrastive_loss_oracle_matches_the_live_reference(n, d, n_labels, temp, seed):
+    """model/loss/loss.py:62-82 on random batches."""
+    ref = refload.load()
+    gen = torch.Generator().manual_seed(seed)
+    feats = torch.randn(n, d, generator=gen).requires_grad_(True)
+    labels = torch.randint(1, n_labels + 1, (n,), generator=gen)
+    l_ref = ref.loss.contrastive_loss(feats, labels, temp)
+    f2 = feats.detach().clone().requires_grad_(True)
+    l_orc = orc.contrastive_loss(f2, labels, temp)
+    assert torch.equal(l_ref.detach(), l_orc.detach()) or (torch.isnan(l_ref) and torch.isnan(l_orc))
+    if not torch.isnan(l_ref):
+        l_ref.backward()
+        l_orc.backward()
+        assert torch.allclose(feats.grad, f2.grad, rtol=1e-6, atol=1e-10)
