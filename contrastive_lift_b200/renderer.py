@@ -204,6 +204,9 @@ class TensoRFRenderer(nn.Module):
         self._active_per_ray = None
         self._host = None
         self.last_opacity = None
+        # None: the C ABI's own bound (n_rays * n_samples < 2^31 per call); a smaller value forces the ray-range split
+        # of _run (tests use it to cover the path 1600x1600 frames at inference sample counts take)
+        self.max_rays_per_call = None
         self.update_step_size(self.grid_dim)
 
     # ---- renderer:59-78 ---------------------------------------------------------------------------
@@ -291,6 +294,8 @@ class TensoRFRenderer(nn.Module):
         params = [p for _, p in tensorf.named_parameters()]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         limit = ((1 << 31) - 1) // max(int(self.n_samples), 1)        # one C call handles n_rays*n_samples < 2^31
+        if self.max_rays_per_call is not None:
+            limit = max(1, min(limit, int(self.max_rays_per_call)))
         if rays.shape[0] <= limit:
             return _Render.apply(self, tensorf, rays, jitter, add_bg, heads, want_points, need_grad, *params)
         # very large frames (e.g. 1600x1600 at 1024 samples/ray): split into ray ranges, concatenate the per-ray maps,

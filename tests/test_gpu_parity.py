@@ -410,3 +410,43 @@ def test_chunked_training_forward_then_one_backward():
         if k.startswith(("density", "appearance", "render_appearance", "render_semantic")):
             # dist_reg is a per-chunk mean, so equal chunks reproduce the single-call value (n is even)
             assert gpu.rel_err(split[k], whole[k]) < 2e-3, k
+
+
+def test_ray_range_split_of_very_large_calls():
+    """Frames with n_rays * n_samples >= 2^31 (1600x1600 at inference sample counts) are rendered as several C calls over
+    ray ranges; `max_rays_per_call` forces that path on a small batch.  Per-ray maps must agree with the single call
+    (rays are independent) and the distortion term must be the mean over ALL rays, for ragged ranges too."""
+    fx, params, cfg, rays, model, rend = case("render_a")
+    r = rays.cuda()
+    n = r.shape[0]
+    with torch.no_grad():
+        whole = rend(model, r, 1.0, False, False)
+        rend.max_rays_per_call = n // 3 + 1                       # three ranges, the last one shorter
+        split = rend(model, r, 1.0, False, False)
+        for a, b in zip(whole[:4], split[:4]):
+            assert a.shape == b.shape and torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+        assert abs(float(split[5]) - float(whole[5])) <= 1e-5 * abs(float(whole[5])) + 1e-9
+        ins_w, pts_w = rend.forward_instance_feature(model, r, 1.0, False)
+        rend.max_rays_per_call = None
+        ins_1, pts_1 = rend.forward_instance_feature(model, r, 1.0, False)
+        assert torch.allclose(ins_w, ins_1, rtol=1e-5, atol=1e-6) and torch.allclose(pts_w, pts_1, rtol=1e-5, atol=1e-6)
+
+    # training: one backward through the concatenated ranges reproduces the single-call gradients (jitter and the
+    # background choice are drawn once per forward() call, before the split, as the reference does per call)
+    w = torch.linspace(0.2, 1.0, n * 3, device="cuda").view(-1, 3)
+
+    def grads(limit):
+        rend.max_rays_per_call = limit
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(5)
+        rgb, sem, _, _, _, dist = rend(model, r, 1.0, True, True)
+        ((rgb * w).sum() / n + 0.3 * dist - 0.01 * sem[:, 1].mean()).backward()
+        rend.max_rays_per_call = None
+        return float(dist), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    d1, g1 = grads(None)
+    d3, g3 = grads(n // 3 + 1)
+    assert abs(d3 - d1) <= 1e-5 * abs(d1) + 1e-9
+    assert set(g1) == set(g3)
+    for k in g1:
+        assert gpu.rel_err(g3[k], g1[k]) < 2e-3, k
