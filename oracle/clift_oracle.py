@@ -252,7 +252,7 @@ def run_mlp(x: Tensor, layers: Sequence[Tuple[Tensor, Tensor]]) -> Tensor:
     for i, (w, b) in enumerate(layers):
         x = F.linear(x, w, b)
         if i + 1 < len(layers):
-            x = torch.relu(x)
+            x = torch.relu_(x)          # nn.ReLU(inplace=True), tensoRF.py:395,479,575: same values, no second activation buffer
     return x
 
 
