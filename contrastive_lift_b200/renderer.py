@@ -179,6 +179,7 @@ class TensoRFRenderer(nn.Module):
         super().__init__()
         if not stop_semantic_grad:
             raise L.CliftError("stop_semantic_grad=False is not built (every shipped config uses True, panopli_paper.yaml:35)")
+        self._check_weight_mode(semantic_weight_mode)
         self.register_buffer("bbox_aabb", torch.as_tensor(bbox_aabb, dtype=torch.float32).clone())
         self.register_buffer("grid_dim", torch.LongTensor(list(grid_dim)))
         self.register_buffer("inv_box_extent", torch.zeros([3]))
@@ -255,8 +256,30 @@ class TensoRFRenderer(nn.Module):
             per_ray = min(per_ray, int(self._active_per_ray * 1.5) + 8)
         return max(128, int(n_rays) * per_ray)
 
+    @staticmethod
+    def _check_weight_mode(mode) -> None:
+        # renderer:142-143 composites the semantic / instance maps from the single arg-max sample in this mode; the kernels
+        # composite over all active samples only ("softmax" and every other string, which the reference treats as "none")
+        if mode == "argmax":
+            raise L.CliftError('semantic_weight_mode="argmax" is not built (shipped configs use "softmax", panopli_paper.yaml:19)')
+
     # ---- descriptor for the C ABI -----------------------------------------------------------------
     def _cfg(self, model: TensorVMSplit, heads: int) -> L.RenderCfg:
+        self._check_weight_mode(self.semantic_weight_mode)           # the attribute may have been changed after construction
+        if heads & L.HEAD_SEMANTIC:
+            # One flag (clift_render_cfg.semantic_softmax) switches both the per-sample Softmax of the semantic MLP
+            # (tensoRF.py:594, the model's output_mlp_semantics) and the renderer's log-normalisation (renderer:160-162).
+            # Every caller derives both from config.semantic_weight_mode (trainer:54,67; render_panopli.py:76,89); a pair that
+            # disagrees would be computed differently from the reference, so it is refused instead.
+            act = model.render_semantic_mlp.output_activation
+            if not isinstance(act, (nn.Softmax, nn.Identity)):
+                raise L.CliftError(f"output_mlp_semantics must be nn.Softmax(dim=-1) or nn.Identity(), got {type(act).__name__}")
+            if isinstance(act, nn.Softmax) and act.dim not in (-1, 1):
+                raise L.CliftError(f"output_mlp_semantics=nn.Softmax(dim={act.dim}): the class axis is the last one")
+            if isinstance(act, nn.Softmax) != (self.semantic_weight_mode == "softmax"):
+                raise L.CliftError(f'semantic_weight_mode="{self.semantic_weight_mode}" with output_mlp_semantics='
+                                   f"{type(act).__name__}: the reference's callers build Softmax <-> \"softmax\" and Identity <-> "
+                                   "anything else together (trainer:54,67), and the kernels switch both with one flag")
         if self._host is None:       # one D2H of 10 floats per geometry change, not per call
             self._host = (self.bbox_aabb.detach().cpu().tolist(), self.inv_box_extent.detach().cpu().tolist(),
                           float(self.step_size))

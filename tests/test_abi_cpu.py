@@ -135,3 +135,33 @@ def test_batched_pack_job_tables(monkeypatch):
     t.add(x, x, x, 128, 150, 0x3000, 1.0, 0)         # rgb layer 0: 10 + 1 slabs x 16 x 128
     t.add(x, x, x, 256, 3, None, 1.0, 1)             # xyz layer 0 of another chain: 1 + 1 slabs x 16 x 256
     assert [q.first_block for q in t.jobs] == [0, 18, 18 + 88] and t.blocks == 18 + 88 + 32 and t.chains == 2
+
+
+def test_semantic_weight_mode_and_output_activation_must_agree():
+    """One C-ABI flag switches the per-sample Softmax of the semantic MLP (tensoRF.py:594) and the renderer's
+    log-normalisation (renderer:160-162); the reference's callers always build them together (trainer:54,67).  A pair that
+    disagrees, or the arg-max compositing mode (renderer:142-143), is refused instead of being computed differently."""
+    import gpu_util as gpu
+    grid = (8, 8, 8)
+    for softmax in (True, False):
+        for sem_grid, ins_grid in ((None, None), (32, 32)):
+            params = syn.make_field_params(0, grid, 4, 3, sem_grid_comps=sem_grid, ins_grid_comps=ins_grid) \
+                if sem_grid else syn.make_field_params(0, grid, 4, 3)
+            model, rend = gpu.build(params, grid, 4, 3, True, softmax, syn.default_aabb(), 0.5, device="cpu",
+                                    sem_grid=sem_grid, ins_grid=ins_grid)
+            for heads in (L.HEAD_ALL, L.HEAD_INSTANCE, L.HEAD_SEMANTIC, 0):      # what the GPU tests / bench / smoke build
+                assert rend._cfg(model, heads).semantic_softmax == int(softmax)
+    model, rend = gpu.build(syn.make_field_params(0, grid, 4, 3), grid, 4, 3, True, True, syn.default_aabb(), 0.5, device="cpu")
+    rend.semantic_weight_mode = "none"
+    with pytest.raises(L.CliftError, match="output_mlp_semantics"):
+        rend._cfg(model, L.HEAD_ALL)
+    rend._cfg(model, L.HEAD_INSTANCE)                   # the instance pass never evaluates the semantic head
+    rend.semantic_weight_mode = "softmax"
+    model.render_semantic_mlp.output_activation = torch.nn.Sigmoid()
+    with pytest.raises(L.CliftError, match="Softmax"):
+        rend._cfg(model, L.HEAD_SEMANTIC)
+    with pytest.raises(L.CliftError, match="argmax"):
+        cl.TensoRFRenderer(syn.default_aabb(), list(grid), semantic_weight_mode="argmax")
+    rend.semantic_weight_mode = "argmax"                # changed after construction: caught at the next call
+    with pytest.raises(L.CliftError, match="argmax"):
+        rend._cfg(model, 0)
