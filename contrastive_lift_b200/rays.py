@@ -4,6 +4,7 @@ the dataset worker and ships 32 B/ray over PCIe (inference/render_panopli.py:110
 from __future__ import annotations
 
 import ctypes as C
+from typing import Tuple
 
 import numpy as np
 import torch
@@ -12,9 +13,10 @@ from . import lib as L
 
 
 def get_rays(height: int, width: int, intrinsics, cam2world, near: float = 0.01, radius: float = 1.0,
-             device="cuda") -> torch.Tensor:
-    """-> rays [H*W, 8] = [o(3), d(3), near, far] on ``device``; ray index = row*W + col.
-    Raises AssertionError when a ray's origin lies outside the scene sphere (the reference asserts, ray.py:96-98)."""
+             device="cuda") -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (rays [H*W, 8] = [o(3), d(3), near, far] on ``device``, ray index = row*W + col; bad int32 [1] device flag).
+    ``bad`` != 0 when a ray's origin lies outside the scene sphere (the reference asserts, ray.py:96-98); reading it is a
+    device sync, so it is left to the caller - ``get_rays_checked`` reads it and raises AssertionError like the reference."""
     lib = L.load()
     dev = torch.device(device)
     k = np.ascontiguousarray(np.asarray(intrinsics, dtype=np.float32).reshape(3, 3))
