@@ -280,10 +280,14 @@ class TensoRFRenderer(nn.Module):
                 raise L.CliftError(f'semantic_weight_mode="{self.semantic_weight_mode}" with output_mlp_semantics='
                                    f"{type(act).__name__}: the reference's callers build Softmax <-> \"softmax\" and Identity <-> "
                                    "anything else together (trainer:54,67), and the kernels switch both with one flag")
-        if self._host is None:       # one D2H of 10 floats per geometry change, not per call
+        # one D2H of 10 floats per geometry change, not per call.  The key also catches buffers replaced or written behind
+        # update_step_size's back (on_load_checkpoint assigns renderer.bbox_aabb directly, trainer:463)
+        key = (self.bbox_aabb.data_ptr(), self.bbox_aabb._version, self.inv_box_extent.data_ptr(), self.inv_box_extent._version,
+               id(self.step_size))
+        if self._host is None or self._host[3] != key:
             self._host = (self.bbox_aabb.detach().cpu().tolist(), self.inv_box_extent.detach().cpu().tolist(),
-                          float(self.step_size))
-        aabb, inv, step = self._host
+                          float(self.step_size), key)
+        aabb, inv, step, _ = self._host
         cfg = L.RenderCfg()
         L.fill3(cfg.aabb_min, aabb[0])
         L.fill3(cfg.aabb_max, aabb[1])

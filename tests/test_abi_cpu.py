@@ -165,3 +165,21 @@ def test_semantic_weight_mode_and_output_activation_must_agree():
     rend.semantic_weight_mode = "argmax"                # changed after construction: caught at the next call
     with pytest.raises(L.CliftError, match="argmax"):
         rend._cfg(model, 0)
+
+
+def test_renderer_descriptor_follows_buffers_replaced_behind_its_back():
+    """on_load_checkpoint assigns renderer.bbox_aabb directly (trainer:463); in-place edits and .data swaps happen in
+    user code too.  The cached host copy of the geometry must follow all of them."""
+    import gpu_util as gpu
+    grid = (8, 8, 8)
+    model, rend = gpu.build(syn.make_field_params(0, grid, 4, 3), grid, 4, 3, True, True, syn.default_aabb(), 0.5, device="cpu")
+    assert list(rend._cfg(model, 0).aabb_max) == [1.0, 1.0, 1.0]
+    rend.bbox_aabb = torch.tensor([[-1.0, -1.0, -1.0], [0.5, 0.75, 1.0]])          # buffer replaced
+    assert list(rend._cfg(model, 0).aabb_max) == [0.5, 0.75, 1.0]
+    rend.bbox_aabb[1, 0] = 0.25                                                     # written in place
+    assert list(rend._cfg(model, 0).aabb_max) == [0.25, 0.75, 1.0]
+    rend.bbox_aabb.data = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 0.5]])       # storage swapped
+    assert list(rend._cfg(model, 0).aabb_max) == [1.0, 1.0, 0.5]
+    rend.update_step_size(rend.grid_dim)
+    c = rend._cfg(model, 0)
+    assert abs(c.inv_extent[2] - 2.0 / 1.5) < 1e-7 and c.step_size == float(rend.step_size) and c.n_samples == rend.n_samples
