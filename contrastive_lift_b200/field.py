@@ -360,12 +360,19 @@ class TensorVMSplit(nn.Module):
 
         def resize(t: torch.Tensor, h2: int, w2: int) -> torch.Tensor:
             src = t.data.contiguous()
+            home = src.device
             if not src.is_cuda:
-                raise L.CliftError("upsample_volume_grid needs the model on a CUDA device (no CPU path)")
+                # Lightning restores checkpoints before it moves the module to its device, so on_load_checkpoint
+                # (trainer:460-466) resizes a CPU-resident model.  There is still no CPU arithmetic: the factors are staged
+                # through the current CUDA device, resized by the same kernel, and returned to where they lived.
+                if not torch.cuda.is_available():
+                    raise L.CliftError("upsample_volume_grid needs a CUDA device (CPU-resident parameters are staged "
+                                       "through it; there is no CPU path)")
+                src = src.cuda()
             dst = torch.empty((1, src.shape[1], h2, w2), device=src.device)
             L.check(lib.clift_upsample_bilinear(L.ptr(src), L.ptr(dst), src.shape[1], src.shape[2], src.shape[3], h2, w2,
                                                 L.stream_ptr(src.device)))
-            return dst
+            return dst if home == dst.device else dst.to(home)
 
         for i in range(3):
             v = VECTOR_MODE[i]

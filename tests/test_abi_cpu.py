@@ -183,3 +183,16 @@ def test_renderer_descriptor_follows_buffers_replaced_behind_its_back():
     rend.update_step_size(rend.grid_dim)
     c = rend._cfg(model, 0)
     assert abs(c.inv_extent[2] - 2.0 / 1.5) < 1e-7 and c.step_size == float(rend.step_size) and c.n_samples == rend.n_samples
+
+
+def test_upsample_of_a_cpu_model_without_a_gpu_fails_loudly():
+    """on_load_checkpoint (trainer:460-466) resizes the factors while Lightning still holds the module on the CPU: the
+    mirror stages them through the CUDA device; with no device there is no silent CPU resize."""
+    if torch.cuda.is_available():
+        pytest.skip("covered by the -m gpu test of the staged path")
+    import gpu_util as gpu
+    grid = (8, 8, 8)
+    model, _ = gpu.build(syn.make_field_params(0, grid, 4, 3), grid, 4, 3, True, True, syn.default_aabb(), 0.5, device="cpu")
+    with pytest.raises(L.CliftError, match="CUDA device"):
+        model.upsample_volume_grid((12, 10, 14))
+    assert list(model.grid_dim()) == [8, 8, 8]                  # nothing was replaced

@@ -230,3 +230,19 @@ def test_grid_heads_tv_shrink_upsample_golden():
     with torch.no_grad():
         out = rend(model, syn.random_rays(3, 64).cuda(), 1.0, False, False)
     assert all(torch.isfinite(o).all() for o in out[:4])
+
+
+def test_upsample_of_a_cpu_resident_model_is_staged_through_the_gpu():
+    """Checkpoint resume: on_load_checkpoint (trainer:460-466) calls upsample_volume_grid with the CPU LongTensor
+    renderer.grid_dim while Lightning still holds the module on the CPU.  Same kernel, parameters stay on the CPU."""
+    grid = (8, 8, 8)
+    params = syn.make_field_params(0, grid, 4, 3)
+    on_gpu, _ = gpu.build(params, grid, 4, 3, True, True, syn.default_aabb(), 0.5)
+    on_cpu, _ = gpu.build(params, grid, 4, 3, True, True, syn.default_aabb(), 0.5, device="cpu")
+    on_gpu.upsample_volume_grid((12, 10, 14))
+    on_cpu.upsample_volume_grid(torch.tensor([12, 10, 14]))
+    assert list(on_cpu.grid_dim()) == [12, 10, 14]
+    a, b = on_gpu.state_dict(), on_cpu.state_dict()
+    for k in a:
+        assert not b[k].is_cuda and a[k].shape == b[k].shape, k
+        assert torch.equal(a[k].cpu(), b[k]), k
