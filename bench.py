@@ -118,8 +118,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_rate(frame: int, samples: int, budget_s: float, max_rays: int, rank_yaw: float = 0.0):
-    """Reference algorithm (oracle port) on the host cores: render_panopli.py:114-120 chunk loop, chunk=2048."""
+def cpu_reference_rate(frame: int, samples: int, budget_s: float, max_rays: int, rank_yaw: float = 0.0, keep: bool = False):
+    """Reference algorithm (oracle port) on the host cores: render_panopli.py:114-120 chunk loop, chunk=2048.
+    ``keep``: also return the rays that were rendered and their rgb / depth maps (for the PSNR-match figure)."""
     from contrastive_lift_b200 import synthetic as syn
     from oracle import clift_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
@@ -133,14 +134,31 @@ def cpu_reference_rate(frame: int, samples: int, budget_s: float, max_rays: int,
     stride = max(1, rays.shape[0] // max_rays)
     sub = rays[::stride][:max_rays].contiguous()            # strided: same in-box/active statistics as the frame
     orc.render_chunked(params, cfg, sub[:256], chunk=2048)  # warm-up (thread pools, allocator)
-    done, t0 = 0, time.perf_counter()
+    done, t0, kept = 0, time.perf_counter(), []
     while done < sub.shape[0]:
-        orc.render_chunked(params, cfg, sub[done:done + 2048], chunk=2048)
+        out = orc.render_chunked(params, cfg, sub[done:done + 2048], chunk=2048)
+        if keep:
+            kept.append((out[0], out[3]))
         done += min(2048, sub.shape[0] - done)
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    if keep:
+        return done / dt / 1e6, done, dt, sub[:done], torch.cat([k[0] for k in kept]), torch.cat([k[1] for k in kept])
     return done / dt / 1e6, done, dt
+
+
+def psnr_match(rend, model, cpu_rays, cpu_rgb, cpu_depth, dev):
+    """CUDA render of ``cpu_rays`` against the CPU reference's maps of the same rays."""
+    import math
+    with torch.no_grad():
+        out = rend(model, cpu_rays.to(dev).contiguous(), 1.0, False, False)
+    rgb, depth = out[0].float().cpu(), out[3].float().cpu()
+    mse = float(((rgb - cpu_rgb) ** 2).mean())
+    return {"psnr_db": min(200.0, -10.0 * math.log10(mse)) if mse > 0.0 else 200.0, "cap_db": 200.0,
+            "rgb_max_abs_err": float((rgb - cpu_rgb).abs().max()),
+            "depth_max_rel_err": float((depth - cpu_depth).abs().max() / cpu_depth.abs().max().clamp_min(1e-12)),
+            "rays": int(cpu_rays.shape[0]), "against": "CPU reference port, same rays (cpu_baseline sample)"}
 
 
 def run_reference(args):
@@ -342,9 +360,15 @@ def run_ours(args):
         except Exception as e:      # never lose the bench line over the extra figure
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"}
     if world == 1 and not args.no_cpu:
-        v, n, dt = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 131072)
+        v, n, dt, cpu_rays, cpu_rgb, cpu_depth = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 131072, keep=True)
         line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": f"{n} rays strided from the same {H}x{W} frame, S={args.samples}, chunk=2048, all heads, {dt:.1f} s"}
+        # "PSNR match" of BASELINE.json's metric: the rays the CPU reference just rendered, rendered again by the CUDA path,
+        # PSNR = -10 log10(mse) of the two rgb maps (util/metrics.py:25-26); identical images give +inf, reported capped
+        try:
+            line["psnr_match"] = psnr_match(rend, model, cpu_rays, cpu_rgb, cpu_depth, dev)
+        except Exception as e:      # never lose the bench line over the extra figure
+            line["psnr_match"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
