@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Static evidence from the built library (no GPU needed): per-kernel registers / stack / static shared memory from
+`cuobjdump --dump-resource-usage`, and the count of Blackwell-specific SASS mnemonics per kernel from `cuobjdump -sass`
+(B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, bulk TMA -> UBLKCP/UTMALDG, cp.async -> LDGSTS,
+red.global -> REDG).  Writes profiles/r01_static_sass.md.
+
+    python scripts/static_evidence.py
+"""
+import collections
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "contrastive_lift_b200", "libclift_b200.so")
+OUT = os.path.join(ROOT, "profiles", "r01_static_sass.md")
+MNEMONICS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "LDGSTS", "REDG", "HMMA"]
+
+
+def demangle(names):
+    out = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.strip().split("\n")
+    clean = []
+    for d in out:
+        d = d.replace("clift::(anonymous namespace)::", "").replace("clift::", "").replace("void ", "")
+        clean.append(re.sub(r"\(.*", "", d))
+    return clean
+
+
+def main():
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", LIB], capture_output=True, text=True).stdout
+    items = re.findall(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", res)
+    usage = {n: (int(r), int(st), int(sh), int(lo)) for n, r, st, sh, lo in items}
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    counts = collections.defaultdict(collections.Counter)
+    pat = re.compile(r"\b(" + "|".join(MNEMONICS) + r")\b")
+    fn = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            continue
+        if fn:
+            for t in pat.findall(line):
+                counts[fn][t] += 1
+    names = sorted(usage)
+    nice = dict(zip(names, demangle(names)))
+    rows = sorted((nice[n], n) for n in names)
+    with open(OUT, "w") as f:
+        f.write("# Round 1 - static evidence from libclift_b200.so (sm_100a cubin, `scripts/static_evidence.py`, no GPU involved)\n\n")
+        f.write("Registers / stack bytes / static shared bytes per kernel (`cuobjdump --dump-resource-usage`; dynamic shared memory is set "
+                "at launch) and counts of the SASS mnemonics that identify the Blackwell paths (`cuobjdump -sass`): `UTCHMMA` = tcgen05.mma, "
+                "`UTCBAR` = tcgen05.commit, `LDTM`/`STTM` = tcgen05.ld/st (tensor memory), `UBLKCP` = bulk TMA copy (cp.async.bulk), "
+                "`SYNCS` = mbarrier ops, `LDGSTS` = cp.async, `REDG` = red.global. `HMMA` (legacy mma.sync) appears nowhere.\n\n")
+        f.write("| kernel | regs | stack B | static smem B | " + " | ".join(MNEMONICS) + " |\n")
+        f.write("|---|---|---|---|" + "---|" * len(MNEMONICS) + "\n")
+        for label, n in rows:
+            r, st, sh, _ = usage[n]
+            c = counts.get(n, {})
+            f.write(f"| `{label}` | {r} | {st} | {sh} | " + " | ".join(str(c.get(k, 0) or "") for k in MNEMONICS) + " |\n")
+        spills = [(nice[n], usage[n][1]) for n in names if usage[n][1] > 0]
+        f.write(f"\n{len(names)} kernels; kernels with a non-zero stack frame (local arrays or spills): "
+                + (", ".join(f"`{a}` ({b} B)" for a, b in sorted(spills)) if spills else "none") + ".\n")
+    print(OUT, len(names), "kernels")
+
+
+if __name__ == "__main__":
+    main()
