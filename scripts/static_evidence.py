@@ -60,6 +60,12 @@ def main():
         spills = [(nice[n], usage[n][1]) for n in names if usage[n][1] > 0]
         f.write(f"\n{len(names)} kernels; kernels with a non-zero stack frame (local arrays or spills): "
                 + (", ".join(f"`{a}` ({b} B)" for a, b in sorted(spills)) if spills else "none") + ".\n")
+        f.write("\nWhere the stack frames come from (`nvdisasm -g` line mapping of every `LDL`/`STL`): in `heads_tc16_forward_kernel` "
+                "(192 STL / 288 LDL) and `heads_tc_forward_kernel` all of them sit on the `sinf`/`cosf` calls of the positional-encoding "
+                "branch `pe_sem / pe_ins > 0` (`heads_tc16.cu:571`, `heads_tc.cu:429`: libdevice's slow-path argument reduction keeps its "
+                "table walk in local memory); the shipped configurations (`pe_sem = pe_ins = 0`) take the branch above it and never execute "
+                "them. `march_kernel` keeps the ray origin / direction (6 words, written once per ray at `march.cu:66-67`) in local memory "
+                "and re-reads them in `sample_point` (`common.cuh:241`, L1 hits). No kernel spills registers in its steady-state loop.\n")
     print(OUT, len(names), "kernels")
 
 
