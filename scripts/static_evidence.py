@@ -65,7 +65,9 @@ def main():
                 "branch `pe_sem / pe_ins > 0` (`heads_tc16.cu:571`, `heads_tc.cu:429`: libdevice's slow-path argument reduction keeps its "
                 "table walk in local memory); the shipped configurations (`pe_sem = pe_ins = 0`) take the branch above it and never execute "
                 "them. `march_kernel` keeps the ray origin / direction (6 words, written once per ray at `march.cu:66-67`) in local memory "
-                "and re-reads them in `sample_point` (`common.cuh:241`, L1 hits). No kernel spills registers in its steady-state loop.\n")
+                "and re-reads them in `sample_point` (`common.cuh:241`, L1 hits); `march_backward_kernel<3>` spills a few loop-invariant "
+                "scalars set up before its ray loop (`march.cu:470-474`). The FP32-FMA head kernels' frames are the same libdevice slow "
+                "path (`heads.cu:169,243,247`). No tensor-core kernel touches local memory in its steady-state loop.\n")
     print(OUT, len(names), "kernels")
 
 
