@@ -442,7 +442,7 @@ def test_ray_range_split_of_very_large_calls():
         rgb, sem, _, _, _, dist = rend(model, r, 1.0, True, True)
         ((rgb * w).sum() / n + 0.3 * dist - 0.01 * sem[:, 1].mean()).backward()
         rend.max_rays_per_call = None
-        return float(dist), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+        return float(dist.detach()), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
 
     d1, g1 = grads(None)
     d3, g3 = grads(n // 3 + 1)
