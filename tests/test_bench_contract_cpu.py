@@ -36,3 +36,26 @@ def test_gpu_arm_has_no_cpu_fallback():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=300, cwd=ROOT)
     assert out.returncode != 0 and "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_roofline_flop_basis_matches_the_survey_figure():
+    """roofline.achieved = algorithmic FLOPs / kernel time: the per-active-sample figure is SURVEY 8(d)'s
+    2 x (3888 + 35968 + 202752 + 265216) MACs = 1.016 MFLOP at C = 21, d = 3 (basis + rgb + semantic + fast/slow instance)."""
+    import bench
+    from contrastive_lift_b200 import synthetic as syn
+    params = syn.make_field_params(0, (8, 8, 8), bench.N_CLS, bench.N_INS)
+    assert bench.head_flops_per_sample(params) == 2 * (3888 + 35968 + 202752 + 265216)
+
+
+def test_cpu_baseline_leg_keeps_what_the_psnr_match_needs():
+    import bench
+    rate, n, dt, rays, rgb, depth = bench.cpu_reference_rate(16, 32, 5.0, 256, keep=True)
+    assert rate > 0 and n == 256 == rays.shape[0] and rgb.shape == (256, 3) and depth.shape == (256,)
+
+    class SameMaps:                                   # stands in for the CUDA renderer: returns the reference's own maps
+        def __call__(self, model, r, *a):
+            return rgb + 1e-6, None, None, depth
+    out = bench.psnr_match(SameMaps(), None, rays, rgb, depth, "cpu")
+    assert 110.0 < out["psnr_db"] <= 200.0 and out["rays"] == 256 and out["depth_max_rel_err"] == 0.0
+    assert bench.psnr_match(type("Z", (), {"__call__": lambda s, m, r, *a: (rgb, None, None, depth)})(), None, rays, rgb, depth,
+                            "cpu")["psnr_db"] == 200.0      # identical images: capped, never inf (the line must stay JSON)
