@@ -184,3 +184,41 @@ def test_oracle_training_pass_matches_the_live_reference(seed, n_samples, n_cls,
         g_got = p[k].grad if p[k].grad is not None else torch.zeros_like(v)
         scale = float(g_ref.abs().max())
         assert torch.allclose(g_got, g_ref, rtol=1e-4, atol=1e-6 * max(scale, 1e-12) + 1e-12), k
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference tree not present (GPU box)")
+@settings(max_examples=8, deadline=None)
+@given(seed=st.integers(0, 10_000), n_samples=st.integers(12, 60), n_cls=st.integers(2, 6), slow_fast=st.booleans(),
+       softmax=st.booleans(), train=st.booleans())
+def test_oracle_instance_and_segment_passes_match_the_live_reference(seed, n_samples, n_cls, slow_fast, softmax, train):
+    """forward_instance_feature / forward_segment_feature (renderer:178-217, 259-300): maps bit-equal, gradients reach only
+    the instance (resp. semantic) head - density is evaluated under no_grad there."""
+    grid = (8 + seed % 4, 9 + seed % 5, 8 + seed % 3)
+    params = syn.make_field_params(seed, grid, n_cls, 2, slow_fast=slow_fast, ball=0.45)
+    aabb = syn.default_aabb()
+    ratio = syn.ratio_for_samples(aabb, grid, n_samples)
+    model = refload.build_model(params, grid, n_cls, 2, slow_fast, softmax)
+    rend = refload.build_renderer(aabb, grid, softmax)
+    rend.update_step_ratio(ratio)
+    cfg = orc.RenderConfig(aabb=aabb, grid_dim=grid, step_ratio=ratio, semantic_softmax=softmax, slow_fast=slow_fast).refresh()
+    rays = syn.random_rays(seed + 5, 18)
+    torch.manual_seed(seed + 11)
+    ref_ins, ref_pts = rend.forward_instance_feature(model, rays, 1.0, train)
+    ref_seg = rend.forward_segment_feature(model, rays, 1.0, train)
+    torch.manual_seed(seed + 11)
+    j1 = torch.rand((rays.shape[0], 1)) if train else None
+    j2 = torch.rand((rays.shape[0], 1)) if train else None
+    p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    ins, pts = orc.render_instance_feature(p, cfg, rays, j1)
+    seg = orc.render_segment_feature(p, cfg, rays, j2)
+    assert torch.equal(ins, ref_ins) and torch.equal(pts, ref_pts) and torch.equal(seg, ref_seg)
+    (ref_ins.sum() + 0.5 * ref_seg.mean()).backward()
+    (ins.sum() + 0.5 * seg.mean()).backward()
+    for k, v in model.named_parameters():
+        head = k.startswith(("render_instance_mlp", "render_semantic_mlp"))
+        if not head:
+            assert v.grad is None and p[k].grad is None, k
+            continue
+        g_ref = v.grad if v.grad is not None else torch.zeros_like(v)
+        g_got = p[k].grad if p[k].grad is not None else torch.zeros_like(v)
+        assert torch.allclose(g_got, g_ref, rtol=1e-4, atol=1e-6 * max(float(g_ref.abs().max()), 1e-12) + 1e-12), k
