@@ -29,12 +29,21 @@ def shard_rays(rays: torch.Tensor, rank: Optional[int] = None, world: Optional[i
 
 
 def gather_rays_output(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
-    """Inverse of shard_rays for an output map [n_local, K]: all-gather with the shard sizes of shard_range()."""
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sizes = [shard_range(n_total, r, world) for r in range(world)]
-    parts = [local.new_empty((e - b,) + tuple(local.shape[1:])) for b, e in sizes]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts, 0)
+    """Inverse of shard_rays for an output map [n_local, K]: all-gather with the shard sizes of shard_range().
+    Shards differ by at most one ray; the collective itself runs on equal-size buffers (gloo refuses uneven all_gather
+    lists, NCCL falls back to one broadcast per rank for them), the padding row is dropped afterwards."""
+    world = dist.get_world_size(group)
+    sizes = [e - b for b, e in (shard_range(n_total, r, world) for r in range(world))]
+    rows = max(sizes) if sizes else 0
+    if local.shape[0] != sizes[dist.get_rank(group)]:
+        raise ValueError(f"gather_rays_output: this rank holds {local.shape[0]} rays, shard_range() assigns it "
+                         f"{sizes[dist.get_rank(group)]} of {n_total}")
+    send = local.contiguous()
+    if send.shape[0] < rows:
+        send = torch.cat([send, send.new_zeros((rows - send.shape[0],) + tuple(send.shape[1:]))], 0)
+    parts = [send.new_empty(send.shape) for _ in range(world)]
+    dist.all_gather(parts, send, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
 
 
 @torch.no_grad()

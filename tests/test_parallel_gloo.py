@@ -43,10 +43,17 @@ def _worker(rank, world, port, out):
         for p in net[:3].parameters():
             p.grad.fill_(float(rank + 1))
         par.allreduce_gradients(net.parameters(), average=True)
-        assert all(torch.allclose(p.grad, torch.full_like(p.grad, 1.5)) for p in net[:3].parameters())
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, (world + 1) / 2.0)) for p in net[:3].parameters())
         # output maps gather back in ray order
         full = par.gather_rays_output(xs * 2.0, x.shape[0])
         assert torch.equal(full, x * 2.0)
+        # ragged shards (ray counts that do not divide by the world size), 1-D maps (depth) and an empty frame
+        for n in (7, 1, 0, 5 * world + 3):
+            m = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+            assert torch.equal(par.gather_rays_output(par.shard_rays(m) + 1.0, n), m + 1.0), n
+            assert torch.equal(par.gather_rays_output(par.shard_rays(m[:, 0]), n), m[:, 0]), n
+        with pytest.raises(ValueError):
+            par.gather_rays_output(x, x.shape[0])          # the whole frame is not this rank's shard
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
@@ -63,15 +70,16 @@ def test_shard_range_covers_everything_in_order():
             assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
 
 
-@pytest.mark.timeout(120)
-def test_flat_arena_allreduce_matches_single_process_gradient():
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("world", [2, 3])
+def test_flat_arena_allreduce_matches_single_process_gradient(world):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [out.get(timeout=100) for _ in procs]
+    res = [out.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=30)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
