@@ -59,19 +59,15 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, averag
     dev = plist[0].device
     total = sum(p.numel() for p in plist)
     flat = torch.zeros((total,), dtype=torch.float32, device=dev)
-    off = 0
-    for p in plist:
-        if p.grad is not None:
-            flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
-        off += p.numel()
+    slots = flat.split([p.numel() for p in plist])                    # views into the arena, one per parameter
+    live = [(s, p.grad) for s, p in zip(slots, plist) if p.grad is not None]
+    if live:      # one multi-tensor copy in, one out (instead of a launch per parameter and direction)
+        torch._foreach_copy_([s.view_as(g) for s, g in live], [g for _, g in live])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat.mul_(1.0 / dist.get_world_size(group))
-    off = 0
-    for p in plist:
-        if p.grad is not None:
-            p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-        off += p.numel()
+    if live:
+        torch._foreach_copy_([g for _, g in live], [s.view_as(g) for s, g in live])
     return total * 4
 
 
