@@ -196,3 +196,23 @@ def test_upsample_of_a_cpu_model_without_a_gpu_fails_loudly():
     with pytest.raises(L.CliftError, match="CUDA device"):
         model.upsample_volume_grid((12, 10, 14))
     assert list(model.grid_dim()) == [8, 8, 8]                  # nothing was replaced
+
+
+def test_missing_or_stale_library_fails_loudly(monkeypatch, tmp_path):
+    """No extension, no product: a missing libclift_b200.so (or one built from another header revision) raises at the first
+    compute call - nothing falls back to PyTorch or to the oracle."""
+    monkeypatch.setattr(L, "_LIB", None)
+    monkeypatch.setattr(L, "LIB_PATH", str(tmp_path / "libclift_b200.so"))
+    with pytest.raises(L.CliftError, match="is missing"):
+        L.load()
+    with pytest.raises(L.CliftError, match="is missing"):
+        cl.contrastive_loss(torch.zeros(4, 3), torch.zeros(4, dtype=torch.long), 100.0)
+    # a library of another ABI revision is refused too
+    monkeypatch.undo()
+    real = L.load()
+    monkeypatch.setattr(L, "_LIB", None)
+    monkeypatch.setattr(L, "ABI_VERSION", real.clift_abi_version() + 1)
+    with pytest.raises(L.CliftError, match="rebuild"):
+        L.load()
+    monkeypatch.undo()
+    assert L.load().clift_abi_version() == L.ABI_VERSION
