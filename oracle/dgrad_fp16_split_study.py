@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """Design study for the next kernel (tcgen05 data-gradient chain), CPU only.
+TEST / DESIGN INFRASTRUCTURE ONLY (lives under oracle/ because it runs the oracle; nothing in the product imports it).
+
 
 Question: is the forward's operand format - power-of-two scale, fp16 (hi, lo) split, three products accumulated in fp32 -
 accurate enough for the BACKWARD data-gradient GEMMs dA = dZ . W, whose operand dZ has a runtime, wide dynamic range, when the
@@ -89,7 +91,7 @@ def main():
     loss.backward()
 
     # incoming ray gradients: their absmax starts the bound chain (one small reduction kernel in the plan)
-    lines = ["# Round 1 - design study: fp16-split operands for the data-gradient GEMMs (CPU emulation, `scripts/dgrad_fp16_split_study.py`)\n",
+    lines = ["# Round 1 - design study: fp16-split operands for the data-gradient GEMMs (CPU emulation, `oracle/dgrad_fp16_split_study.py`)\n",
              f"One oracle training pass, {rays.shape[0]} rays, S = {cfg.n_samples}, G = 64^3, C = {N_CLS}: true dZ of every Linear captured by "
              "autograd hooks; `dA = dZ . W` re-evaluated with the forward kernel's operand format and a scale from an a-priori bound "
              "chain. Errors are against the fp64 product, `max` = max |err| / max |dA| (the scale-relative measure of the parity tests), "

@@ -1,5 +1,7 @@
 #!/usr/bin/env python
 """Build-container check (needs /root/reference): is the oracle port a FAIR stand-in for the reference on the CPU?
+TEST INFRASTRUCTURE ONLY (lives under oracle/ because it runs the oracle and the imported reference; nothing in the product imports it).
+
 
 Times the unmodified reference renderer (imported through oracle/refload.py) and the oracle port
 (oracle/clift_oracle.py, what `bench.py --impl reference` and `cpu_baseline` run on the GPU box) on the same bench
