@@ -59,3 +59,27 @@ def test_cpu_baseline_leg_keeps_what_the_psnr_match_needs():
     assert 110.0 < out["psnr_db"] <= 200.0 and out["rays"] == 256 and out["depth_max_rel_err"] == 0.0
     assert bench.psnr_match(type("Z", (), {"__call__": lambda s, m, r, *a: (rgb, None, None, depth)})(), None, rays, rgb, depth,
                             "cpu")["psnr_db"] == 200.0      # identical images: capped, never inf (the line must stay JSON)
+
+
+def test_oracle_is_only_reachable_from_the_allowed_places():
+    """oracle/ is test infrastructure: the product package never imports it; outside tests/ and oracle/ itself only
+    __graft_entry__.smoke()/build(), bench.py's CPU legs (cpu_baseline, --impl reference) and the CPU leg of the
+    training-step bench (its cpu_baseline analogue) do."""
+    import re
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    users = {}
+    for base, _, files in os.walk(ROOT):
+        rel = os.path.relpath(base, ROOT)
+        if rel.split(os.sep)[0] in ("tests", "oracle", ".git", "gpurun_out", "baseline"):
+            continue
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(base, f)).read()
+                if pat.search(src):
+                    users[os.path.normpath(os.path.join(rel, f))] = src
+    assert sorted(users) == ["__graft_entry__.py", "bench.py", os.path.join("scripts", "train_step_bench.py")], sorted(users)
+    assert not any(k.startswith("contrastive_lift_b200") for k in users)
+    # bench.py: the GPU arm (run_ours) reaches the oracle only through cpu_reference_rate (the cpu_baseline leg)
+    bench_src = users["bench.py"]
+    body = bench_src[bench_src.index("def run_ours"):bench_src.index("def main")]
+    assert "oracle" not in body.replace("cpu_reference_rate", "")
