@@ -216,3 +216,17 @@ def test_missing_or_stale_library_fails_loudly(monkeypatch, tmp_path):
         L.load()
     monkeypatch.undo()
     assert L.load().clift_abi_version() == L.ABI_VERSION
+
+
+def test_integration_doc_binding_matches_the_library():
+    """INTEGRATION.md shows the ctypes stub a maintainer would write; its struct fields, ABI number and the entry points it
+    calls must be the library's."""
+    import re
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class RenderCfg\(C\.Structure\):.*?_fields_ = \[(.*?)\]\s*#", doc, re.S)
+    assert m, "RenderCfg stub not found in INTEGRATION.md"
+    names = re.findall(r'\("(\w+)"', m.group(1))
+    assert names == [n for n, _ in L.RenderCfg._fields_]
+    assert f"clift_abi_version() == {L.ABI_VERSION}" in doc
+    for fn in set(re.findall(r"lib\.(clift_\w+)", doc)):
+        assert fn in L.SIGNATURES, fn
