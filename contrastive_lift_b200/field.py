@@ -363,7 +363,7 @@ class TensorVMSplit(nn.Module):
             home = src.device
             if not src.is_cuda:
                 # Lightning restores checkpoints before it moves the module to its device, so on_load_checkpoint
-                # (trainer:460-466) resizes a CPU-resident model.  There is still no CPU arithmetic: the factors are staged
+                # (trainer:461-469) resizes a CPU-resident model.  There is still no CPU arithmetic: the factors are staged
                 # through the current CUDA device, resized by the same kernel, and returned to where they lived.
                 if not torch.cuda.is_available():
                     raise L.CliftError("upsample_volume_grid needs a CUDA device (CPU-resident parameters are staged "

@@ -281,7 +281,7 @@ class TensoRFRenderer(nn.Module):
                                    f"{type(act).__name__}: the reference's callers build Softmax <-> \"softmax\" and Identity <-> "
                                    "anything else together (trainer:54,67), and the kernels switch both with one flag")
         # one D2H of 10 floats per geometry change, not per call.  The key also catches buffers replaced or written behind
-        # update_step_size's back (on_load_checkpoint assigns renderer.bbox_aabb directly, trainer:463)
+        # update_step_size's back (on_load_checkpoint assigns renderer.bbox_aabb directly, trainer:466)
         key = (self.bbox_aabb.data_ptr(), self.bbox_aabb._version, self.inv_box_extent.data_ptr(), self.inv_box_extent._version,
                id(self.step_size))
         if self._host is None or self._host[3] != key:

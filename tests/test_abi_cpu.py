@@ -168,7 +168,7 @@ def test_semantic_weight_mode_and_output_activation_must_agree():
 
 
 def test_renderer_descriptor_follows_buffers_replaced_behind_its_back():
-    """on_load_checkpoint assigns renderer.bbox_aabb directly (trainer:463); in-place edits and .data swaps happen in
+    """on_load_checkpoint assigns renderer.bbox_aabb directly (trainer:466); in-place edits and .data swaps happen in
     user code too.  The cached host copy of the geometry must follow all of them."""
     import gpu_util as gpu
     grid = (8, 8, 8)
@@ -186,7 +186,7 @@ def test_renderer_descriptor_follows_buffers_replaced_behind_its_back():
 
 
 def test_upsample_of_a_cpu_model_without_a_gpu_fails_loudly():
-    """on_load_checkpoint (trainer:460-466) resizes the factors while Lightning still holds the module on the CPU: the
+    """on_load_checkpoint (trainer:461-469) resizes the factors while Lightning still holds the module on the CPU: the
     mirror stages them through the CUDA device; with no device there is no silent CPU resize."""
     if torch.cuda.is_available():
         pytest.skip("covered by the -m gpu test of the staged path")

@@ -233,7 +233,7 @@ def test_grid_heads_tv_shrink_upsample_golden():
 
 
 def test_upsample_of_a_cpu_resident_model_is_staged_through_the_gpu():
-    """Checkpoint resume: on_load_checkpoint (trainer:460-466) calls upsample_volume_grid with the CPU LongTensor
+    """Checkpoint resume: on_load_checkpoint (trainer:461-469) calls upsample_volume_grid with the CPU LongTensor
     renderer.grid_dim while Lightning still holds the module on the CPU.  Same kernel, parameters stay on the CPU."""
     grid = (8, 8, 8)
     params = syn.make_field_params(0, grid, 4, 3)
