@@ -43,3 +43,50 @@ def test_every_attribute_the_reference_callers_use_exists():
     assert not missing, f"reference callers use attributes the mirrors lack: {sorted(missing)}"
     # the nested ones the EMA reads (trainer:259)
     assert hasattr(model.render_instance_mlp, "mlp") and hasattr(model.render_instance_mlp, "slow_mlp")
+
+
+def _params(fn):
+    import inspect
+    return [(n, p.default) for n, p in inspect.signature(fn).parameters.items() if n != "self"]
+
+
+def _same_default(a, b):
+    import inspect
+    import torch
+    if a is inspect._empty or b is inspect._empty:
+        return a is b
+    if isinstance(a, torch.nn.Module) or isinstance(b, torch.nn.Module):
+        return type(a) is type(b) and getattr(a, "dim", None) == getattr(b, "dim", None)
+    if callable(a) and callable(b):
+        return getattr(a, "__name__", None) == getattr(b, "__name__", None)
+    return a == b
+
+
+def test_constructor_and_function_signatures_match_the_reference():
+    """Same parameter names, order and defaults as the reference's definitions: positional and keyword call sites
+    both keep working.  The mirrors may append keyword-only conveniences after the reference's parameters."""
+    from oracle import refload
+    ref = refload.load()
+    pairs = [
+        (ref.tensorf.TensorVMSplit.__init__, cl.TensorVMSplit.__init__, 0),
+        (ref.renderer.TensoRFRenderer.__init__, cl.TensoRFRenderer.__init__, 1),          # + verbose
+        (ref.renderer.TensoRFRenderer.forward, cl.TensoRFRenderer.forward, 0),
+        (ref.renderer.TensoRFRenderer.forward_instance_feature, cl.TensoRFRenderer.forward_instance_feature, 0),
+        (ref.renderer.TensoRFRenderer.forward_segment_feature, cl.TensoRFRenderer.forward_segment_feature, 0),
+        (ref.renderer.TensoRFRenderer.update_step_size, cl.TensoRFRenderer.update_step_size, 0),
+        (ref.renderer.TensoRFRenderer.update_step_ratio, cl.TensoRFRenderer.update_step_ratio, 0),
+        (ref.renderer.TensoRFRenderer.get_target_resolution, cl.TensoRFRenderer.get_target_resolution, 0),
+        (ref.renderer.TensoRFRenderer.update_bbox_aabb_and_shrink, cl.TensoRFRenderer.update_bbox_aabb_and_shrink, 0),
+        (ref.tensorf.TensorVMSplit.get_optimizable_parameters, cl.TensorVMSplit.get_optimizable_parameters, 0),
+        (ref.tensorf.TensorVMSplit.get_optimizable_instance_parameters, cl.TensorVMSplit.get_optimizable_instance_parameters, 0),
+        (ref.tensorf.TensorVMSplit.upsample_volume_grid, cl.TensorVMSplit.upsample_volume_grid, 0),
+        (ref.tensorf.TensorVMSplit.total_tv_loss, cl.TensorVMSplit.total_tv_loss, 0),
+        (ref.loss.contrastive_loss, cl.contrastive_loss, 0),
+        (ref.loss.TVLoss.__init__, cl.TVLoss.__init__, 1),                                  # + weight (default 1: TVLoss() is the reference's)
+    ]
+    for theirs, ours, extra in pairs:
+        a, b = _params(theirs), _params(ours)
+        assert len(b) == len(a) + extra, (theirs.__qualname__, a, b)
+        for (na, da), (nb, db) in zip(a, b):
+            assert na == nb, (theirs.__qualname__, na, nb)
+            assert _same_default(da, db), (theirs.__qualname__, na, da, db)
