@@ -90,3 +90,32 @@ def test_constructor_and_function_signatures_match_the_reference():
         for (na, da), (nb, db) in zip(a, b):
             assert na == nb, (theirs.__qualname__, na, nb)
             assert _same_default(da, db), (theirs.__qualname__, na, da, db)
+
+
+def test_instances_carry_the_reference_objects_attributes_and_module_tree():
+    """Every plain (non-tensor, non-module) attribute a reference instance carries exists on the mirror with the same value,
+    and the two module trees have the same names - for the MLP-head and the grid-head configurations."""
+    import torch
+    from oracle import refload
+    ref = refload.load()
+
+    def plain(o):
+        return {k: v for k, v in vars(o).items() if not k.startswith("_") and not isinstance(v, (torch.nn.Module, torch.Tensor))}
+
+    for mlp_heads in (True, False):
+        kw = dict(num_semantics_comps=(32, 32, 32), num_instance_comps=(32, 32, 32), num_semantic_classes=5, dim_feature_instance=6,
+                  output_mlp_semantics=torch.nn.Softmax(dim=-1), use_semantic_mlp=mlp_heads, use_instance_mlp=mlp_heads,
+                  slow_fast_mode=True)
+        theirs, ours = ref.tensorf.TensorVMSplit([8, 9, 10], **kw), cl.TensorVMSplit([8, 9, 10], **kw)
+        a, b = plain(theirs), plain(ours)
+        assert set(a) <= set(b), sorted(set(a) - set(b))
+        assert {k: b[k] for k in a} == a
+        assert set(dict(theirs.named_modules())) == set(dict(ours.named_modules()))
+        assert [n for n, _ in theirs.named_parameters()] == [n for n, _ in ours.named_parameters()]      # optimizer / DDP order
+    theirs = refload.build_renderer(syn.default_aabb(), [8, 9, 10])
+    ours = cl.TensoRFRenderer(syn.default_aabb(), [8, 9, 10], semantic_weight_mode="softmax")
+    a, b = plain(theirs), plain(ours)
+    assert set(a) <= set(b), sorted(set(a) - set(b))
+    assert {k: b[k] for k in a} == a
+    assert [n for n, _ in theirs.named_buffers()] == [n for n, _ in ours.named_buffers()]
+    assert float(theirs.step_size) == float(ours.step_size) and theirs.n_samples == ours.n_samples
