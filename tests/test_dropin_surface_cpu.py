@@ -119,3 +119,22 @@ def test_instances_carry_the_reference_objects_attributes_and_module_tree():
     assert {k: b[k] for k in a} == a
     assert [n for n, _ in theirs.named_buffers()] == [n for n, _ in ours.named_buffers()]
     assert float(theirs.step_size) == float(ours.step_size) and theirs.n_samples == ours.n_samples
+
+
+def test_same_seed_gives_the_reference_initialisation():
+    """The mirrors draw their initial parameters in the reference's order (tensoRF.py:48-106): under the same torch seed a
+    freshly constructed model is bit-identical to the reference's, so seeded training runs start from the same point."""
+    import torch
+    from oracle import refload
+    ref = refload.load()
+    for mlp_heads, slow_fast in ((True, True), (False, True), (True, False)):
+        kw = dict(num_semantics_comps=(32, 32, 32), num_instance_comps=(32, 32, 32), num_semantic_classes=5,
+                  dim_feature_instance=6 if slow_fast else 3, output_mlp_semantics=torch.nn.Softmax(dim=-1),
+                  use_semantic_mlp=mlp_heads, use_instance_mlp=mlp_heads, slow_fast_mode=slow_fast)
+        torch.manual_seed(11)
+        theirs = ref.tensorf.TensorVMSplit([8, 9, 10], **kw).state_dict()
+        torch.manual_seed(11)
+        ours = cl.TensorVMSplit([8, 9, 10], **kw).state_dict()
+        assert list(theirs) == list(ours)
+        for k in theirs:
+            assert torch.equal(theirs[k], ours[k]), k
