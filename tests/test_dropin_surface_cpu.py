@@ -138,3 +138,28 @@ def test_same_seed_gives_the_reference_initialisation():
         assert list(theirs) == list(ours)
         for k in theirs:
             assert torch.equal(theirs[k], ours[k]), k
+
+
+def test_shrink_matches_the_reference_on_every_factor_set():
+    """TensorVMSplit.shrink (tensoRF.py:158-177) is pure slicing of the plane / line factors; the mirror's must select the same
+    window in every factor set (grid-mode heads included) and leave trainable Parameters behind."""
+    import torch
+    from oracle import refload
+    ref = refload.load()
+    for mlp_heads in (True, False):
+        kw = dict(num_semantics_comps=(32, 32, 32), num_instance_comps=(32, 32, 32), num_semantic_classes=5, dim_feature_instance=6,
+                  output_mlp_semantics=torch.nn.Softmax(dim=-1), use_semantic_mlp=mlp_heads, use_instance_mlp=mlp_heads,
+                  slow_fast_mode=True)
+        torch.manual_seed(3)
+        theirs = ref.tensorf.TensorVMSplit([12, 10, 14], **kw)
+        torch.manual_seed(3)
+        ours = cl.TensorVMSplit([12, 10, 14], **kw)
+        t_l, b_r = torch.tensor([2, 1, 3]), torch.tensor([11, 9, 12])
+        theirs.shrink(t_l, b_r)
+        ours.shrink(t_l, b_r)
+        a, b = theirs.state_dict(), ours.state_dict()
+        assert list(a) == list(b)
+        for k in a:
+            assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+        assert list(ours.grid_dim()) == [9, 8, 9]
+        assert all(isinstance(p, torch.nn.Parameter) and p.requires_grad for p in ours.parameters())
