@@ -309,6 +309,13 @@ class TensorVMSplit(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **k)
 
+    def __getstate__(self):
+        # copy.deepcopy / pickle / torch.save(model) (ddp_spawn, EMA copies): the packed view is a cache full of raw device
+        # pointers (ctypes) - it is rebuilt on the next render, never copied
+        state = self.__dict__.copy()
+        state["_packed"] = None
+        return state
+
     def invalidate_packed(self) -> None:
         """Call after mutating parameters through ``.data`` outside a training render."""
         self._packed = None

@@ -230,3 +230,35 @@ def test_integration_doc_binding_matches_the_library():
     assert f"clift_abi_version() == {L.ABI_VERSION}" in doc
     for fn in set(re.findall(r"lib\.(clift_\w+)", doc)):
         assert fn in L.SIGNATURES, fn
+
+
+def test_models_survive_deepcopy_and_pickle_with_a_live_packed_view():
+    """ddp_spawn, EMA copies and torch.save(model) copy the module; the packed parameter view (ctypes structs full of raw
+    device pointers) is a cache and must not travel."""
+    import copy
+    import io
+    import pickle
+
+    class FakePacked:                     # stands in for the PackedField a CUDA render leaves behind
+        def __init__(self):
+            self.field = L.Field()
+            self.field.basis = 0x1000
+
+    model = cl.TensorVMSplit([8, 8, 8], num_semantic_classes=4, dim_feature_instance=6, use_semantic_mlp=True,
+                             use_instance_mlp=True, slow_fast_mode=True)
+    model._packed = FakePacked()
+    with pytest.raises(ValueError):
+        pickle.dumps(model._packed.field)     # the hazard: ctypes objects with pointers do not pickle
+    for clone in (copy.deepcopy(model), pickle.loads(pickle.dumps(model))):
+        assert clone._packed is None and model._packed is not None
+        for (ka, a), (kb, b) in zip(model.state_dict().items(), clone.state_dict().items()):
+            assert ka == kb and torch.equal(a, b) and a.data_ptr() != b.data_ptr()
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    assert torch.load(buf, weights_only=False)._packed is None
+    rend = cl.TensoRFRenderer(syn.default_aabb(), [8, 8, 8], semantic_weight_mode="softmax")
+    rend._cfg(model, 0)                   # fills the host geometry cache
+    twin = copy.deepcopy(rend)
+    twin.bbox_aabb[1, 2] = 0.5            # the copy owns its buffers and its cache follows them
+    assert list(twin._cfg(model, 0).aabb_max) == [1.0, 1.0, 0.5] and list(rend._cfg(model, 0).aabb_max) == [1.0, 1.0, 1.0]
