@@ -89,6 +89,15 @@ class MLPRenderSemanticFeature(_HeadBase):
         self.mlp = _sequential(self.in_feat_mlp, dim_mlp, out_channels, num_mlp_layers)
 
 
+def _param_version(p: torch.Tensor) -> Optional[int]:
+    """Autograd version counter of a parameter; None for a tensor created under torch.inference_mode() (it keeps none), which
+    makes PackedField.refresh repack on every call instead of trusting a cache it cannot validate."""
+    try:
+        return p._version
+    except RuntimeError:
+        return None
+
+
 def _linears(seq: nn.Sequential) -> List[nn.Linear]:
     return [m for m in seq if isinstance(m, nn.Linear)]
 
@@ -535,8 +544,8 @@ class PackedField:
     def refresh(self, training: bool) -> None:
         # Inference renders reuse the packed copy while no parameter version moved.  Training renders always
         # repack: the reference's EMA writes through ``.data`` (trainer:325-329), which version counters miss.
-        versions = tuple(p._version for p in self.model_params) + (L.param_epoch(),)
-        if not training and versions == self.versions and not self.tc_stale:
+        versions = tuple(_param_version(p) for p in self.model_params) + (L.param_epoch(),)
+        if not training and versions == self.versions and not self.tc_stale and None not in versions:
             return
         lib, st = self.lib, L.stream_ptr(self.device)
         # every fp32 layout job of the model (factor transposes, W^T + bias, data-gradient copies) in ONE launch

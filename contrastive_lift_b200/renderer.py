@@ -161,6 +161,15 @@ class _Render(torch.autograd.Function):
         return (None,) * 8 + tuple(grads.get(n) for n in ctx.param_names)
 
 
+def _tensor_key(t: torch.Tensor):
+    """(storage address, version) of a buffer; version None = a tensor created under torch.inference_mode(), which keeps no
+    version counter - such a buffer is re-read on every call instead of cached."""
+    try:
+        return t.data_ptr(), t._version
+    except RuntimeError:
+        return t.data_ptr(), None
+
+
 def _mlp_names(prefix: str, pm) -> List[str]:
     names = []
     for i, l in enumerate(pm.linears):
@@ -282,9 +291,8 @@ class TensoRFRenderer(nn.Module):
                                    "anything else together (trainer:54,67), and the kernels switch both with one flag")
         # one D2H of 10 floats per geometry change, not per call.  The key also catches buffers replaced or written behind
         # update_step_size's back (on_load_checkpoint assigns renderer.bbox_aabb directly, trainer:466)
-        key = (self.bbox_aabb.data_ptr(), self.bbox_aabb._version, self.inv_box_extent.data_ptr(), self.inv_box_extent._version,
-               id(self.step_size))
-        if self._host is None or self._host[3] != key:
+        key = (_tensor_key(self.bbox_aabb), _tensor_key(self.inv_box_extent), id(self.step_size))
+        if self._host is None or self._host[3] != key or key[0][1] is None or key[1][1] is None:
             self._host = (self.bbox_aabb.detach().cpu().tolist(), self.inv_box_extent.detach().cpu().tolist(),
                           float(self.step_size), key)
         aabb, inv, step, _ = self._host

@@ -262,3 +262,42 @@ def test_models_survive_deepcopy_and_pickle_with_a_live_packed_view():
     twin = copy.deepcopy(rend)
     twin.bbox_aabb[1, 2] = 0.5            # the copy owns its buffers and its cache follows them
     assert list(twin._cfg(model, 0).aabb_max) == [1.0, 1.0, 0.5] and list(rend._cfg(model, 0).aabb_max) == [1.0, 1.0, 1.0]
+
+
+def test_packed_view_cache_validation_handles_inference_tensors():
+    """PackedField.refresh trusts its packed copy only while every parameter's version counter is unchanged.  Parameters
+    created under torch.inference_mode() keep no counter: the cache is then never trusted (repack on every call) instead of
+    raising 'Inference tensors do not track version counter'."""
+    from contrastive_lift_b200 import field as F
+    normal = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.ones(2))]
+    with torch.inference_mode():
+        frozen = [torch.nn.Parameter(torch.zeros(3))]
+    assert F._param_version(normal[0]) == 0 and F._param_version(frozen[0]) is None
+
+    def stub(params):
+        pk = object.__new__(F.PackedField)          # no device work: only the cache check at the top of refresh() runs
+        pk.model_params, pk.tc_stale = params, False
+        pk.versions = tuple(F._param_version(p) for p in params) + (L.param_epoch(),)
+        return pk
+
+    assert stub(normal).refresh(False) is None      # valid cache: returns before touching the library
+    with torch.no_grad():
+        normal[1].add_(1.0)                         # a version moved: the early return must not happen
+    pk = stub(normal)
+    pk.versions = (0, 0, L.param_epoch())
+    with pytest.raises(AttributeError):             # falls through to the repack (this stub has no library handle)
+        pk.refresh(False)
+    with pytest.raises(AttributeError):             # inference tensors: never trusted, even with an "equal" version tuple
+        stub(frozen).refresh(False)
+    with pytest.raises(AttributeError):             # training renders always repack
+        stub([torch.nn.Parameter(torch.zeros(1))]).refresh(True)
+
+
+def test_renderer_built_under_inference_mode_still_describes_itself():
+    with torch.inference_mode():
+        rend = cl.TensoRFRenderer(syn.default_aabb(), [8, 8, 8], semantic_weight_mode="softmax")
+        model = cl.TensorVMSplit([8, 8, 8], num_semantic_classes=4, dim_feature_instance=6, use_semantic_mlp=True,
+                                 use_instance_mlp=True, slow_fast_mode=True)
+        assert rend._cfg(model, L.HEAD_ALL).n_samples == rend.n_samples
+    rend.update_step_ratio(0.3)
+    assert rend._cfg(model, 0).n_samples == rend.n_samples and list(rend._cfg(model, 0).aabb_min) == [-1.0, -1.0, -1.0]
