@@ -29,44 +29,58 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def _digest() -> str:
+def _headers_digest() -> "hashlib._Hash":
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "clift_b200.h")]
-    for f in files:
-        p = os.path.join(CSRC, f)
-        if os.path.isfile(p) and (f.endswith((".cu", ".cuh", ".h"))):
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cuh", ".h")):
             h.update(f.encode())
-            h.update(open(p, "rb").read())
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "include", "clift_b200.h"), "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    return h
+
+
+def _source_digest(src: str, headers) -> str:
+    h = headers.copy()
+    h.update(open(os.path.join(CSRC, src), "rb").read())
     return h.hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    want = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == want:
+    """Recompiles only the sources whose text (or any header, or the flags) changed since their object was built."""
+    headers = _headers_digest()
+    want = {src: _source_digest(src, headers) for src in SOURCES}
+    stamp = {}
+    if os.path.exists(STAMP) and not force:
+        for line in open(STAMP).read().splitlines():
+            k, _, v = line.partition(" ")
+            stamp[k] = v
+    obj_of = lambda src: os.path.join(CSRC, src.replace(".cu", ".o"))
+    todo = [src for src in SOURCES if stamp.get(src) != want[src] or not os.path.exists(obj_of(src))]
+    if not todo and os.path.exists(LIB):
         return LIB
     nvcc = _nvcc()
-    objs = []
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    for src in todo:
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj_of(src)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose:
             print(f"--- {src}\n{out}", flush=True)
-        failed |= p.returncode != 0
+        if p.returncode != 0:
+            failed = True
+        else:
+            stamp[src] = want[src]
+    open(STAMP, "w").write("".join(f"{k} {v}\n" for k, v in stamp.items() if k in want))
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *[obj_of(src) for src in SOURCES]]
     subprocess.run(cmd, check=True)
-    open(STAMP, "w").write(want)
     return LIB
 
 

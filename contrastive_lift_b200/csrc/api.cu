@@ -19,17 +19,16 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+int sm_count() {     // of the CURRENT device (callers run under a device guard); cached per device ordinal
+    static std::atomic<int> cached[64];
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    n = cached[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
     }
-    return cached;
+    return n;
 }
 
 static bool g_profile = false;

@@ -214,10 +214,131 @@ __global__ void __launch_bounds__(256) centroid_kernel(const float* __restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// panoptic instance labels from rendered embeddings (the device form of render_panopli.py:371-419): every "thing" point
+// takes the nearest centroid of ITS semantic class; classes present in the data get consecutive label ranges in ascending
+// class order, each range as long as the highest centroid index any point of the class chose, + 1; stuff points get label 0.
+//   pass 1: class = argmax of the semantic scores (first maximum), nearest centroid inside the class's table slice,
+//           code = class << 20 | local index (-1 = stuff), atomicMax of local + 1 per class
+//   pass 2: one thread walks the classes: first label of each present class (exclusive running sum), total label count
+//   pass 3: label = first[class] + local + 1; optional one-hot rows (fp64, as the reference's numpy one-hot)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cluster_local_kernel(const float* __restrict__ feats, int64_t n, int d, int feat_stride,
+                                                            const float* __restrict__ scores, int n_cls,
+                                                            const float* __restrict__ centroids,
+                                                            const int32_t* __restrict__ cls_first,
+                                                            const int32_t* __restrict__ cls_count, int32_t* __restrict__ code,
+                                                            uint32_t* __restrict__ cls_top, int32_t* __restrict__ missing) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const float* row = feats + p * feat_stride;
+        if (!(row[0] == -INFINITY)) {        // column 0 marks thing points with -inf (create_instances_from_semantics)
+            code[p] = -1;
+            continue;
+        }
+        int c = 0;
+        float top = scores[p * n_cls];
+        for (int j = 1; j < n_cls; ++j) {
+            const float s = scores[p * n_cls + j];
+            if (s > top) {
+                top = s;
+                c = j;
+            }
+        }
+        const int k = cls_count[c];
+        if (k <= 0) {                         // the reference raises KeyError here; reported through `missing`
+            atomicMax(missing, c + 1);
+            code[p] = -1;
+            continue;
+        }
+        float f[16];
+        for (int i = 0; i < d; ++i) f[i] = row[1 + i];
+        const float* cs = centroids + (int64_t)cls_first[c] * d;
+        float best = INFINITY;
+        int arg = 0;
+        for (int j = 0; j < k; ++j) {
+            float acc = 0.0f;
+            for (int i = 0; i < d; ++i) {
+                const float diff = f[i] - __ldg(cs + j * d + i);
+                acc = fmaf(diff, diff, acc);
+            }
+            if (acc < best) {
+                best = acc;
+                arg = j;
+            }
+        }
+        code[p] = (c << 20) | arg;
+        atomicMax(cls_top + c, (uint32_t)arg + 1u);
+    }
+}
+
+__global__ void cluster_ranges_kernel(uint32_t* __restrict__ cls_top, int n_cls, int32_t* __restrict__ n_labels) {
+    uint32_t run = 0;
+    for (int c = 0; c < n_cls; ++c) {         // cls_top[c]: range length in, first label of the class out
+        const uint32_t len = cls_top[c];
+        cls_top[c] = run;
+        run += len;
+    }
+    *n_labels = (int32_t)run + 1;             // + the stuff label 0
+}
+
+__global__ void __launch_bounds__(256) cluster_label_kernel(const int32_t* __restrict__ code, int64_t n,
+                                                            const uint32_t* __restrict__ cls_first_label,
+                                                            int32_t* __restrict__ labels) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = code[p];
+        labels[p] = v < 0 ? 0 : (int32_t)cls_first_label[v >> 20] + (v & 0xfffff) + 1;
+    }
+}
+
+__global__ void __launch_bounds__(256) onehot_kernel(const int32_t* __restrict__ labels, int64_t n, int width,
+                                                     double* __restrict__ out) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t l = labels[p];
+        if (l >= 0 && l < width) out[p * width + l] = 1.0;
+    }
+}
+
 }  // namespace
 }  // namespace clift
 
 using namespace clift;
+
+extern "C" int32_t clift_assign_clusters(const float* features, int64_t n, int32_t dim, int32_t feature_stride,
+                                         const float* scores, int32_t n_classes, const float* centroids,
+                                         const int32_t* class_first, const int32_t* class_count, int32_t* labels,
+                                         uint32_t* class_scratch, int32_t* stats2, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CLIFT_CHECK_ARG(n >= 0 && dim > 0 && feature_stride >= dim + 1 && n_classes > 0, "bad size");
+    CLIFT_CHECK_ARG(class_first && class_count && class_scratch && stats2, "null pointer");
+    CLIFT_CHECK_SUPPORTED(dim <= 16 && n_classes <= 2048, "embedding wider than 16 or more than 2048 classes");
+    CLIFT_CUDA(cudaMemsetAsync(class_scratch, 0, (size_t)n_classes * sizeof(uint32_t), stream));
+    CLIFT_CUDA(cudaMemsetAsync(stats2, 0, 2 * sizeof(int32_t), stream));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), 8 * sm_count()));
+    if (n > 0) {
+        CLIFT_CHECK_ARG(features && scores && centroids && labels, "null pointer");
+        cluster_local_kernel<<<grid, 256, 0, stream>>>(features, n, dim, feature_stride, scores, n_classes, centroids, class_first,
+                                                       class_count, labels, class_scratch, stats2 + 1);
+        CLIFT_AFTER_LAUNCH("cluster_local_kernel");
+    }
+    cluster_ranges_kernel<<<1, 1, 0, stream>>>(class_scratch, n_classes, stats2);
+    CLIFT_AFTER_LAUNCH("cluster_ranges_kernel");
+    if (n > 0) {
+        cluster_label_kernel<<<grid, 256, 0, stream>>>(labels, n, class_scratch, labels);
+        CLIFT_AFTER_LAUNCH("cluster_label_kernel");
+    }
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_labels_onehot(const int32_t* labels, int64_t n, int32_t width, double* onehot, void* stream) {
+    CLIFT_CHECK_ARG(n >= 0 && width > 0, "bad size");
+    if (n == 0) return CLIFT_OK;
+    CLIFT_CHECK_ARG(labels && onehot, "null pointer");
+    CLIFT_CUDA(cudaMemsetAsync(onehot, 0, (size_t)n * width * sizeof(double), (cudaStream_t)stream));
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), 8 * sm_count()));
+    onehot_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, n, width, onehot);
+    CLIFT_AFTER_LAUNCH("onehot_kernel");
+    return CLIFT_OK;
+}
 
 extern "C" int32_t clift_adam_step(const clift_adam_tensor* table_dev, int32_t n_tensors, int64_t max_n, float lr, float beta1,
                                    float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {

@@ -336,7 +336,8 @@ class TensorVMSplit(nn.Module):
         pk = self.packed(False)
         xyz = xyz_sampled.detach().reshape(-1, 3).contiguous().float()
         sigma = torch.empty((xyz.shape[0],), device=xyz.device)
-        L.check(lib.clift_density(C.byref(pk.field), L.ptr(xyz), xyz.shape[0], L.ptr(sigma), L.stream_ptr(xyz.device)))
+        with L.on(xyz.device):
+            L.check(lib.clift_density(C.byref(pk.field), L.ptr(xyz), xyz.shape[0], L.ptr(sigma), L.stream_ptr(xyz.device)))
         return sigma.view(xyz_sampled.shape[:-1])
 
     # ---- grid surgery (tensoRF.py:158-197): parameter objects are replaced, packed view dropped --
@@ -386,8 +387,9 @@ class TensorVMSplit(nn.Module):
                                        "through it; there is no CPU path)")
                 src = src.cuda()
             dst = torch.empty((1, src.shape[1], h2, w2), device=src.device)
-            L.check(lib.clift_upsample_bilinear(L.ptr(src), L.ptr(dst), src.shape[1], src.shape[2], src.shape[3], h2, w2,
-                                                L.stream_ptr(src.device)))
+            with L.on(src.device):
+                L.check(lib.clift_upsample_bilinear(L.ptr(src), L.ptr(dst), src.shape[1], src.shape[2], src.shape[3], h2, w2,
+                                                    L.stream_ptr(src.device)))
             return dst if home == dst.device else dst.to(home)
 
         for i in range(3):
@@ -547,6 +549,10 @@ class PackedField:
         versions = tuple(_param_version(p) for p in self.model_params) + (L.param_epoch(),)
         if not training and versions == self.versions and not self.tc_stale and None not in versions:
             return
+        with L.on(self.device):
+            self._refresh(training, versions)
+
+    def _refresh(self, training: bool, versions) -> None:
         lib, st = self.lib, L.stream_ptr(self.device)
         # every fp32 layout job of the model (factor transposes, W^T + bias, data-gradient copies) in ONE launch
         batch = L.PackBatch()

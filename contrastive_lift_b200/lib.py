@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -139,6 +139,8 @@ SIGNATURES = {
     "clift_alpha_bbox": (C.c_int32, [_vp, C.POINTER(C.c_int32), _vp, _vp, _vp, _fp, _fp, C.c_float, _vp, _vp, _vp, _vp]),
     "clift_upsample_bilinear": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_assign_centroids": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp]),
+    "clift_assign_clusters": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "clift_labels_onehot": (C.c_int32, [_vp, C.c_int64, C.c_int32, _vp, _vp]),
 }
 
 
@@ -181,6 +183,16 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def on(device) -> "torch.cuda.device":
+    """Context manager every libclift call site runs under: kernels, cudaFuncSetAttribute and the default-stream pointer all
+    refer to the CURRENT device, so it must be the device that owns the tensors (a model on cuda:1 with cuda:0 current
+    would otherwise launch on the wrong GPU)."""
+    dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+    if dev.type != "cuda":
+        raise CliftError(f"libclift_b200 runs on CUDA devices only: got a tensor on {dev} (no CPU fallback exists)")
+    return torch.cuda.device(dev)
 
 
 def launch_count() -> int:
@@ -257,8 +269,9 @@ class PackBatch:
         if not self.jobs:
             return
         raw = bytes((PackJob * len(self.jobs))(*self.jobs))
-        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
-        check(lib.clift_pack_batch(ptr(table), len(self.jobs), int(self.tiles), stream_ptr(device)))
+        with on(device):
+            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
+            check(lib.clift_pack_batch(ptr(table), len(self.jobs), int(self.tiles), stream_ptr(device)))
         self.jobs, self.tiles = [], 0
 
 
@@ -288,6 +301,7 @@ class Tc16Batch:
         if not self.jobs:
             return
         raw = bytes((Tc16Job * len(self.jobs))(*self.jobs))
-        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
-        check(lib.clift_pack_linear_tc16_batch(ptr(table), len(self.jobs), int(self.chains), int(self.blocks), stream_ptr(device)))
+        with on(device):
+            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
+            check(lib.clift_pack_linear_tc16_batch(ptr(table), len(self.jobs), int(self.chains), int(self.blocks), stream_ptr(device)))
         self.jobs, self.blocks, self.chains = [], 0, 0

@@ -25,8 +25,13 @@ class _SlowFast(torch.autograd.Function):
         n, w = f.shape
         loss = torch.empty((1,), device=f.device)
         grad = torch.empty_like(f)
-        L.check(lib.clift_slowfast_loss(L.ptr(f), L.ptr(labels.contiguous().long()), L.ptr(confidences.contiguous().float()),
-                                        n, w // 2, L.ptr(loss), L.ptr(grad), L.stream_ptr(f.device)))
+        # converted copies stay bound until the launch is enqueued: a temporary released earlier could hand its block to the
+        # next conversion and alias the two arguments
+        lab = labels.to(f.device).contiguous().long()
+        conf = confidences.to(f.device).contiguous().float()
+        with L.on(f.device):
+            L.check(lib.clift_slowfast_loss(L.ptr(f), L.ptr(lab), L.ptr(conf), n, w // 2, L.ptr(loss), L.ptr(grad),
+                                            L.stream_ptr(f.device)))
         ctx.save_for_backward(grad)
         return loss.reshape(())
 
@@ -51,8 +56,10 @@ class _Contrastive(torch.autograd.Function):
         f = features.detach().contiguous().float()
         loss = torch.empty((1,), device=f.device)
         grad = torch.empty_like(f)
-        L.check(lib.clift_contrastive_loss(L.ptr(f), L.ptr(labels.contiguous().long()), f.shape[0], f.shape[1],
-                                           float(temperature), L.ptr(loss), L.ptr(grad), L.stream_ptr(f.device)))
+        lab = labels.to(f.device).contiguous().long()       # bound until the launch is enqueued
+        with L.on(f.device):
+            L.check(lib.clift_contrastive_loss(L.ptr(f), L.ptr(lab), f.shape[0], f.shape[1], float(temperature), L.ptr(loss),
+                                               L.ptr(grad), L.stream_ptr(f.device)))
         ctx.save_for_backward(grad)
         return loss.reshape(())
 
@@ -72,7 +79,8 @@ def ema_update(slow_params: Iterable[torch.Tensor], fast_params: Iterable[torch.
     """param_k = param_k * momentum + (1 - momentum) * param_q for every pair (trainer:325-329)."""
     lib = L.load()
     for q, k in zip(fast_params, slow_params):
-        L.check(lib.clift_ema_update(L.ptr(k.data), L.ptr(q.data), k.numel(), float(momentum), L.stream_ptr(k.device)))
+        with L.on(k.device):
+            L.check(lib.clift_ema_update(L.ptr(k.data), L.ptr(q.data), k.numel(), float(momentum), L.stream_ptr(k.device)))
     L.bump_param_epoch()     # parameters were mutated through raw pointers: packed copies are stale
 
 
@@ -89,12 +97,14 @@ class _PlaneTV(torch.autograd.Function):
         _, c, h, w = p.shape
         st = L.stream_ptr(p.device)
         hwc = torch.empty((h, w, c), device=p.device)
-        L.check(lib.clift_pack_plane(L.ptr(p.contiguous()), L.ptr(hwc), c, h, w, st))
+        src = p.contiguous()                                 # bound until the launches are enqueued
         loss = torch.empty((1,), device=p.device)
         g_hwc = torch.zeros_like(hwc)
-        L.check(lib.clift_tv_loss(L.ptr(hwc), c, h, w, L.ptr(loss), L.ptr(g_hwc), 1.0, st))
-        g = torch.empty_like(p)
-        L.check(lib.clift_unpack_plane(L.ptr(g_hwc), L.ptr(g), c, h, w, st))
+        g = torch.empty_like(src)
+        with L.on(p.device):
+            L.check(lib.clift_pack_plane(L.ptr(src), L.ptr(hwc), c, h, w, st))
+            L.check(lib.clift_tv_loss(L.ptr(hwc), c, h, w, L.ptr(loss), L.ptr(g_hwc), 1.0, st))
+            L.check(lib.clift_unpack_plane(L.ptr(g_hwc), L.ptr(g), c, h, w, st))
         ctx.save_for_backward(g)
         return loss.reshape(())
 

@@ -36,6 +36,7 @@ class FusedAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = L.load()
+        keep: List[torch.Tensor] = []      # contiguous gradient copies stay alive until every launch of this step is enqueued
         for group in self.param_groups:
             entries: List[L.AdamTensor] = []
             step = None
@@ -61,22 +62,27 @@ class FusedAdam(torch.optim.Optimizer):
                     self._launch(lib, entries, max_n, group, step, device)
                     entries, max_n, step, device = [], 0, t, p.device
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                keep.append(g)
                 e = L.AdamTensor()
                 e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.n = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), \
                     st["exp_avg_sq"].data_ptr(), p.numel()
                 entries.append(e)
                 max_n = max(max_n, p.numel())
             self._launch(lib, entries, max_n, group, step, device)
+        # parameters were rewritten through raw pointers: autograd's version counters did not move, so cached packed copies
+        # (PackedField.refresh) must be told (ema_update does the same)
+        L.bump_param_epoch()
         return loss
 
     def _launch(self, lib, entries, max_n, group, step, device):
         if not entries:
             return
         raw = bytes((L.AdamTensor * len(entries))(*entries))
-        table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
         b1, b2 = group["betas"]
-        L.check(lib.clift_adam_step(L.ptr(table), len(entries), int(max_n), float(group["lr"]), float(b1), float(b2),
-                                    float(group["eps"]), float(group["weight_decay"]), int(step), self.grad_scale,
-                                    L.stream_ptr(device)))
+        with L.on(device):
+            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
+            L.check(lib.clift_adam_step(L.ptr(table), len(entries), int(max_n), float(group["lr"]), float(b1), float(b2),
+                                        float(group["eps"]), float(group["weight_decay"]), int(step), self.grad_scale,
+                                        L.stream_ptr(device)))
         # the caching allocator may not hand the table's block to another stream-ordered tensor before the launch ran:
         # same stream, so ordering holds without a record_stream

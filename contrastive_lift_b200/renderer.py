@@ -41,6 +41,11 @@ class _Render(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, renderer, model, rays, jitter, add_bg, heads, want_points, need_grad, *params):
+        with L.on(rays.device):         # every launch below targets the device that owns the rays / the model
+            return _Render._forward(ctx, renderer, model, rays, jitter, add_bg, heads, want_points, need_grad, *params)
+
+    @staticmethod
+    def _forward(ctx, renderer, model, rays, jitter, add_bg, heads, want_points, need_grad, *params):
         lib = L.load()
         dev = rays.device
         # outputs no loss consumes arrive as None in backward (not as zero tensors): the main training pass never uses
@@ -103,6 +108,11 @@ class _Render(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rgb, g_sem, g_ins, _g_depth, g_dist, _g_pts):
+        with L.on(ctx.rays.device if ctx.need_grad else torch.cuda.current_device()):
+            return _Render._backward(ctx, g_rgb, g_sem, g_ins, _g_depth, g_dist, _g_pts)
+
+    @staticmethod
+    def _backward(ctx, g_rgb, g_sem, g_ins, _g_depth, g_dist, _g_pts):
         if not ctx.need_grad:
             raise L.CliftError("backward through a render that was run without need_grad")
         renderer, model, pk = ctx.renderer, ctx.model, ctx.pk
@@ -377,7 +387,8 @@ class TensoRFRenderer(nn.Module):
         """(n_active, n_inbox, overflow, n_tiles) of the last render on ``device`` (one small D2H)."""
         ws = _WORKSPACES[torch.device(device) if not isinstance(device, torch.device) else device]
         st = torch.empty((4,), dtype=torch.int64, device=ws.device)
-        L.check(L.load().clift_render_stats(L.ptr(ws), L.ptr(st), L.stream_ptr(ws.device)))
+        with L.on(ws.device):
+            L.check(L.load().clift_render_stats(L.ptr(ws), L.ptr(st), L.stream_ptr(ws.device)))
         return tuple(int(v) for v in st.cpu().tolist())
 
     # ---- renderer:668-729: epoch-boundary dense-alpha sweep, bounding box, factor shrink ------------------
@@ -394,8 +405,9 @@ class TensoRFRenderer(nn.Module):
         sx, sy, sz = self._lattice(dev)
         g = [int(v) for v in self.grid_dim.tolist()]
         alpha = torch.empty(g, device=dev)
-        L.check(L.load().clift_dense_alpha(C.byref(cfg), C.byref(pk.field), L.ptr(sx), L.ptr(sy), L.ptr(sz), L.ptr(alpha),
-                                           L.stream_ptr(dev)))
+        with L.on(dev):
+            L.check(L.load().clift_dense_alpha(C.byref(cfg), C.byref(pk.field), L.ptr(sx), L.ptr(sy), L.ptr(sz), L.ptr(alpha),
+                                               L.stream_ptr(dev)))
         samples = torch.stack(torch.meshgrid(sx, sy, sz, indexing="ij"), -1)
         dense_xyz = self.bbox_aabb[0] * (1 - samples) + self.bbox_aabb[1] * samples
         return alpha, dense_xyz
@@ -411,13 +423,14 @@ class TensoRFRenderer(nn.Module):
         sx, sy, sz = self._lattice(dev)
         g = [int(v) for v in self.grid_dim.tolist()]
         alpha = torch.empty(g, device=dev)
-        L.check(lib.clift_dense_alpha(C.byref(cfg), C.byref(pk.field), L.ptr(sx), L.ptr(sy), L.ptr(sz), L.ptr(alpha), st))
         out = torch.zeros((8,), device=dev)
         scratch = torch.zeros((8,), dtype=torch.int32, device=dev)
         aabb = self._host[0]
-        L.check(lib.clift_alpha_bbox(L.ptr(alpha), (C.c_int32 * 3)(*g), L.ptr(sx), L.ptr(sy), L.ptr(sz), (C.c_float * 3)(*aabb[0]),
-                                     (C.c_float * 3)(*aabb[1]), float(self.alpha_mask_threshold), L.ptr(out),
-                                     out.data_ptr() + 24, L.ptr(scratch), st))
+        with L.on(dev):
+            L.check(lib.clift_dense_alpha(C.byref(cfg), C.byref(pk.field), L.ptr(sx), L.ptr(sy), L.ptr(sz), L.ptr(alpha), st))
+            L.check(lib.clift_alpha_bbox(L.ptr(alpha), (C.c_int32 * 3)(*g), L.ptr(sx), L.ptr(sy), L.ptr(sz),
+                                         (C.c_float * 3)(*aabb[0]), (C.c_float * 3)(*aabb[1]), float(self.alpha_mask_threshold),
+                                         L.ptr(out), out.data_ptr() + 24, L.ptr(scratch), st))
         host = out.cpu()
         n_valid = int(host[6:7].view(torch.int32).item())
         return host[0:3].to(dev), host[3:6].to(dev), n_valid

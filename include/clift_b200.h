@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 9
+#define CLIFT_ABI_VERSION 10
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -359,6 +359,20 @@ int32_t clift_upsample_bilinear(const float* src, float* dst, int32_t channels, 
  * centroids [k][dim]; labels int32 [n]; distances [n] (Euclidean, to the chosen centroid) or null. */
 int32_t clift_assign_centroids(const float* features, int64_t n, int32_t dim, int32_t feature_stride, const float* centroids,
                                int32_t k, int32_t* labels, float* distances, void* stream);
+
+/* Panoptic instance labels on the device (the whole of inference/render_panopli.py:371-419 assign_clusters): point p is a
+ * "thing" when features[p][0] == -inf (create_instances_from_semantics, render_panopli.py:422-427); its embedding is
+ * features[p][1 .. dim]; its class is the first argmax of scores[p][0 .. n_classes); it takes the nearest centroid among
+ * centroids[class_first[c] .. + class_count[c]) ([K][dim] table of all classes).  Classes present in the data receive
+ * consecutive label ranges in ascending class order, each as long as the highest chosen centroid index + 1 (the reference's
+ * `max_label = labels.max() + 1`); labels[p] = 0 for stuff, first_label(class) + centroid + 1 for things.
+ * class_scratch: n_classes device uint32 (out: first label of each class); stats2: device int32[2] = {label count including
+ * label 0, 1 + highest class id that had points but no centroids (0 = none; the reference raises KeyError there)}.
+ * clift_labels_onehot writes the fp64 one-hot rows [n][width] the reference returns. */
+int32_t clift_assign_clusters(const float* features, int64_t n, int32_t dim, int32_t feature_stride, const float* scores,
+                              int32_t n_classes, const float* centroids, const int32_t* class_first, const int32_t* class_count,
+                              int32_t* labels, uint32_t* class_scratch, int32_t* stats2, void* stream);
+int32_t clift_labels_onehot(const int32_t* labels, int64_t n, int32_t width, double* onehot, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,5 @@
-"""Import the UNMODIFIED reference from /root/reference on CPU (build container only).
+"""Import the UNMODIFIED reference on CPU: from /root/reference in the build container, from its staged copy oracle/_ref/
+(oracle/vendor_reference.py) on the GPU box.
 
 TEST INFRASTRUCTURE ONLY - used by oracle/make_golden.py and tests that cross-check the oracle
 against the live reference; those tests skip when /root/reference is absent (the GPU box).
@@ -19,7 +20,21 @@ from types import SimpleNamespace
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("CLIFT_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/vendor_reference.py (git-ignored)
+
+
+def _resolve_root() -> str:
+    """CLIFT_REFERENCE_ROOT, else /root/reference (build container), else the byte-for-byte staged copy of the path's
+    modules under oracle/_ref/ (what travels to the GPU box)."""
+    env = os.environ.get("CLIFT_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/model/renderer"):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _resolve_root()
 
 _STUB_MODULES = [
     "transforms3d", "transforms3d.euler", "transforms3d.axangles", "transforms3d.quaternions",

@@ -170,3 +170,14 @@ def test_loss_ray_and_epoch_entries_validate_before_touching_the_device():
     assert lib.clift_upsample_bilinear(FAKE, FAKE, 16, 8, 8, 0, 12, None) == ERR_ARG
     assert lib.clift_pack_plane(None, FAKE, 16, 8, 8, None) == ERR_ARG
     assert lib.clift_pack_linear_dgrad(FAKE, FAKE, 4096, 16, None) == ERR_UNSUPPORTED
+
+
+def test_fused_adam_step_bumps_the_packed_parameter_epoch():
+    """FusedAdam rewrites parameters through raw pointers; cached packed copies are keyed on lib.param_epoch()."""
+    import torch
+    import contrastive_lift_b200 as cl
+    p = torch.nn.Parameter(torch.zeros(3))          # no .grad: nothing to launch, the epoch must still move
+    opt = cl.FusedAdam([p], lr=0.1)
+    e0 = L.param_epoch()
+    opt.step()
+    assert L.param_epoch() == e0 + 1

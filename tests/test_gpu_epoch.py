@@ -246,3 +246,69 @@ def test_upsample_of_a_cpu_resident_model_is_staged_through_the_gpu():
     for k in a:
         assert not b[k].is_cuda and a[k].shape == b[k].shape, k
         assert torch.equal(a[k].cpu(), b[k]), k
+
+
+def test_assign_clusters_missing_centroids_raise_keyerror_and_empty_input():
+    """A thing class with points but no centroid table is the reference's KeyError (render_panopli.py:389); classes without
+    points consume no labels; zero points give an empty one-hot with only the stuff column."""
+    d, C = 3, 4
+    sem = [torch.eye(C)[[1, 1, 2, 3]]]
+    pad = np.full((4, d + 1), -np.inf, dtype=np.float32)
+    pad[:, 1:] = np.arange(12, dtype=np.float32).reshape(4, 3)
+    pad[3, 0] = np.inf                                            # last point is stuff
+    cents = {1: np.array([[0, 1, 2], [3, 4, 5]], np.float32), 2: np.array([[100, 100, 100], [6, 7, 8]], np.float32),
+             0: np.zeros((5, 3), np.float32)}                     # class 0 has centroids but no points: no labels consumed
+    got = cl.assign_clusters(pad, sem, cents, "cuda", num_images=1).cpu()
+    # class 1: points 0,1 -> centroids 0,1 -> labels 1,2; class 2: point 2 -> centroid 1 -> label 2 + 1 + 1 = 4 (range length 2)
+    assert got.dtype == torch.float64 and got.shape == (1, 4, 5)
+    assert got[0].argmax(-1).tolist() == [1, 2, 4, 0]
+    with pytest.raises(KeyError):
+        cl.assign_clusters(pad, sem, {1: cents[1]}, "cuda", num_images=1)
+    empty = cl.assign_clusters(np.zeros((0, d + 1), np.float32), [torch.zeros(0, C)], cents, "cuda", num_images=None)
+    assert empty.shape == (0, 1)
+
+
+def test_fused_adam_step_invalidates_cached_packed_parameters():
+    """render(no_grad) -> FusedAdam.step -> render(no_grad): the optimizer rewrites parameters through raw pointers (no
+    autograd version bump), so it must bump the packed-parameter epoch or the second render reuses stale packed weights."""
+    grid = (16, 16, 16)
+    params = syn.make_field_params(2, grid, 4, 3)
+    aabb = syn.default_aabb()
+    model, rend = gpu.build(params, grid, 4, 3, True, True, aabb, 0.5)
+    rays = syn.random_rays(4, 64).cuda()
+    with torch.no_grad():
+        before = rend(model, rays, 0.0, False, False)[0].clone()
+    opt = cl.FusedAdam(model.get_optimizable_parameters(0.05, 0.05), betas=(0.9, 0.99))
+    for p in model.parameters():
+        p.grad = torch.ones_like(p)
+    e0 = L.param_epoch()
+    opt.step()
+    assert L.param_epoch() > e0
+    with torch.no_grad():
+        after = rend(model, rays, 0.0, False, False)[0]
+        model.invalidate_packed()
+        fresh = rend(model, rays, 0.0, False, False)[0]
+    assert not torch.equal(before, after)
+    assert torch.equal(after, fresh)
+
+
+def test_calls_target_the_tensors_device_not_the_current_one():
+    """A model on cuda:1 while cuda:0 is current must launch on cuda:1 (every call site runs under lib.on(device))."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    grid = (16, 16, 16)
+    params = syn.make_field_params(2, grid, 4, 3)
+    aabb = syn.default_aabb()
+    m0, r0 = gpu.build(params, grid, 4, 3, True, True, aabb, 0.5, device="cuda:0")
+    m1, r1 = gpu.build(params, grid, 4, 3, True, True, aabb, 0.5, device="cuda:1")
+    rays = syn.random_rays(4, 64)
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        a = r0(m0, rays.to("cuda:0"), 0.0, False, False)
+        b = r1(m1, rays.to("cuda:1"), 0.0, False, False)
+    for x, y in zip(a[:4], b[:4]):
+        assert y.device == torch.device("cuda:1") and torch.equal(x.cpu(), y.cpu())
+    f = torch.randn(64, 6, device="cuda:1", requires_grad=True)
+    loss = cl.slow_fast_loss(f, torch.randint(1, 4, (64,), device="cuda:1"), torch.rand(64, device="cuda:1"))
+    loss.backward()
+    assert f.grad.device == torch.device("cuda:1") and torch.isfinite(loss)

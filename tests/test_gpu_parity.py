@@ -452,9 +452,6 @@ def test_ray_range_split_of_very_large_calls():
         assert gpu.rel_err(g3[k], g1[k]) < 2e-3, k
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CLIFT_RUN_UNVERIFIED") != "1",
-                    reason="written after round 1's GPU budget was spent and never run on a B200; enable with "
-                           "CLIFT_RUN_UNVERIFIED=1 under a timeout (first item of the next GPU call)")
 @pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR16], ids=["fma", "tcgen05_f16"])
 def test_config1_density_rgb_heads_only(path):
     """BASELINE config 1: 64x64 frame, 64 samples/ray, G=128^3, heads = RGB alone through the C ABI (the Python face never
