@@ -118,47 +118,86 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_rate(frame: int, samples: int, budget_s: float, max_rays: int, rank_yaw: float = 0.0, keep: bool = False):
-    """Reference algorithm (oracle port) on the host cores: render_panopli.py:114-120 chunk loop, chunk=2048.
-    ``keep``: also return the rays that were rendered and their rgb / depth maps (for the PSNR-match figure)."""
+def cpu_renderer(frame: int, samples: int, rank_yaw: float = 0.0):
+    """The reference's CPU implementation of the path for the bench scene -> (render(rays)->(rgb, sem, ins, depth), rays, kind).
+    kind "reference": the UNMODIFIED reference modules (TensoRFRenderer.forward on TensorVMSplit) from /root/reference or
+    their staged copy oracle/_ref (oracle/vendor_reference.py); kind "port": the reference-pinned restatement in
+    oracle/clift_oracle.py when neither is present.  Both replay render_panopli.py:114-120 (no_grad, chunk = 2048)."""
     from contrastive_lift_b200 import synthetic as syn
     from oracle import clift_oracle as orc
+    from oracle import refload
     torch.set_num_threads(os.cpu_count() or 1)
     params = syn.make_field_params(0, GRID, N_CLS, N_INS)
     aabb = syn.default_aabb()
     ratio = orc.ratio_for_samples(aabb, GRID, samples)
+    k, c2w = syn.camera(frame, frame, yaw_deg=rank_yaw)
+    if refload.available() and os.environ.get("CLIFT_BENCH_CPU_PORT") != "1":
+        ref = refload.load()
+        model = refload.build_model(params, GRID, N_CLS, N_INS, slow_fast=True, semantic_softmax=True)
+        rend = refload.build_renderer(aabb, GRID, semantic_softmax=True)
+        rend.update_step_ratio(ratio)
+        assert rend.n_samples == samples, (rend.n_samples, samples)
+        dirs = ref.ray.get_ray_directions_with_intrinsics(frame, frame, k.numpy())
+        o, d = ref.ray.get_rays(dirs, c2w)
+        far = ref.ray.rays_intersect_sphere(o, d, r=1)
+        rays = torch.cat([o, d, 0.01 * torch.ones_like(o[:, :1]), far[:, None]], 1).float().contiguous()   # dataset/base.py:216-219
+
+        def render(r):
+            outs = []
+            with torch.no_grad():
+                for i in range(0, r.shape[0], 2048):
+                    outs.append(rend(model, r[i:i + 2048], 1.0, False, False)[:4])
+            return tuple(torch.cat([o[j] for o in outs]) for j in range(4))
+        return render, rays, "reference"
     cfg = orc.RenderConfig(aabb=aabb, grid_dim=GRID, step_ratio=ratio).refresh()
     assert cfg.n_samples == samples
-    k, c2w = syn.camera(frame, frame, yaw_deg=rank_yaw)
     rays = orc.make_rays(frame, frame, k, c2w)
+    return (lambda r: tuple(orc.render_chunked(params, cfg, r, chunk=2048)[:4])), rays, "port"
+
+
+def cpu_reference_rate(frame: int, samples: int, budget_s: float, max_rays: int, rank_yaw: float = 0.0, keep: bool = False):
+    """Reference CPU path on the host cores: render_panopli.py:114-120 chunk loop, chunk=2048, on a strided ray sample.
+    -> (Mrays/s, rays done, seconds, kind[, rays, rgb, semantic, instance, depth])"""
+    render, rays, kind = cpu_renderer(frame, samples, rank_yaw)
     stride = max(1, rays.shape[0] // max_rays)
     sub = rays[::stride][:max_rays].contiguous()            # strided: same in-box/active statistics as the frame
-    orc.render_chunked(params, cfg, sub[:256], chunk=2048)  # warm-up (thread pools, allocator)
+    render(sub[:256])                                       # warm-up (thread pools, allocator)
     done, t0, kept = 0, time.perf_counter(), []
     while done < sub.shape[0]:
-        out = orc.render_chunked(params, cfg, sub[done:done + 2048], chunk=2048)
+        out = render(sub[done:done + 2048])
         if keep:
-            kept.append((out[0], out[3]))
+            kept.append(out)
         done += min(2048, sub.shape[0] - done)
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
     if keep:
-        return done / dt / 1e6, done, dt, sub[:done], torch.cat([k[0] for k in kept]), torch.cat([k[1] for k in kept])
-    return done / dt / 1e6, done, dt
+        return (done / dt / 1e6, done, dt, kind, sub[:done]) + tuple(torch.cat([k[j] for k in kept]) for j in range(4))
+    return done / dt / 1e6, done, dt, kind
 
 
-def psnr_match(rend, model, cpu_rays, cpu_rgb, cpu_depth, dev):
-    """CUDA render of ``cpu_rays`` against the CPU reference's maps of the same rays."""
+def psnr_match(rend, model, cpu_rays, cpu_maps, dev):
+    """CUDA render of ``cpu_rays`` against the CPU reference's maps of the same rays: PSNR of the rgb map
+    (util/metrics.py:25-26) + worst deviations of every map (semantic compared in probability space)."""
     import math
+    cpu_rgb, cpu_sem, cpu_ins, cpu_depth = cpu_maps
     with torch.no_grad():
         out = rend(model, cpu_rays.to(dev).contiguous(), 1.0, False, False)
     rgb, depth = out[0].float().cpu(), out[3].float().cpu()
     mse = float(((rgb - cpu_rgb) ** 2).mean())
-    return {"psnr_db": min(200.0, -10.0 * math.log10(mse)) if mse > 0.0 else 200.0, "cap_db": 200.0,
-            "rgb_max_abs_err": float((rgb - cpu_rgb).abs().max()),
-            "depth_max_rel_err": float((depth - cpu_depth).abs().max() / cpu_depth.abs().max().clamp_min(1e-12)),
-            "rays": int(cpu_rays.shape[0]), "against": "CPU reference port, same rays (cpu_baseline sample)"}
+    res = {"psnr_db": min(200.0, -10.0 * math.log10(mse)) if mse > 0.0 else 200.0, "cap_db": 200.0,
+           "rgb_max_abs_err": float((rgb - cpu_rgb).abs().max()),
+           "depth_max_rel_err": float((depth - cpu_depth).abs().max() / cpu_depth.abs().max().clamp_min(1e-12)),
+           "rays": int(cpu_rays.shape[0]), "against": "CPU reference, same rays (cpu_baseline sample)"}
+    if out[1] is not None and cpu_sem is not None:
+        res["semantic_prob_max_abs_err"] = float((out[1].float().cpu().exp() - cpu_sem.exp()).abs().max())
+    if out[2] is not None and cpu_ins is not None:
+        ins = out[2].float().cpu()
+        res["instance_max_rel_err"] = float((ins - cpu_ins).abs().max() / cpu_ins.abs().max().clamp_min(1e-12))
+    res["tolerance"] = "1e-4 scale-relative (max |diff| / max |reference|) per map; semantic in probability space"
+    res["ok"] = bool(res["rgb_max_abs_err"] < 1e-4 and res["depth_max_rel_err"] < 1e-4 and
+                     res.get("semantic_prob_max_abs_err", 0.0) < 1e-4 and res.get("instance_max_rel_err", 0.0) < 1e-4)
+    return res
 
 
 def run_reference(args):
@@ -168,20 +207,26 @@ def run_reference(args):
     steps, warm = max(1, args.steps), max(0, args.warmup)
     per_step = 2048          # one reference chunk (config.chunk, render_panopli.py:114) per step: ~0.5 s of host work
     vals = []
+    kind = "port"
     for i in range(warm + steps):
-        v, n, dt = cpu_reference_rate(args.frame, args.samples, 60.0, per_step)
+        v, n, dt, kind = cpu_reference_rate(args.frame, args.samples, 60.0, per_step)
         if i >= warm:
             vals.append((v, n, dt))
     rays = sum(n for _, n, _ in vals)
     secs = sum(dt for _, _, dt in vals)
     value = rays / secs / 1e6
     cores = os.cpu_count() or 1
-    sample = f"{per_step} rays/step strided from the {args.frame}x{args.frame} frame, S={args.samples}, chunk=2048, all heads"
+    sample = (f"{per_step} rays/step strided from the {args.frame}x{args.frame} frame, S={args.samples}, chunk=2048, all heads; "
+              + ("the unmodified reference modules (TensoRFRenderer.forward)" if kind == "reference" else "oracle port"))
+    cfg = workload_config(args, 1)
+    cfg["rays_per_step_per_gpu"] = 0
+    cfg["rays_per_step_on_host"] = per_step      # what this arm times per step (a bounded sample of the frame; per-ray rate)
+    cfg["parallelism"] = f"host cores only ({cores} threads), no GPU"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": secs / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, 1),
-            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": cfg,
+            "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -309,6 +354,57 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = (float(v) for v in total_ms.cpu())
+    multi = {}
+    if dist is not None and not args.no_train:
+        # The exchange steps of the path, on every rank: (0) N-GPU == 1-GPU equivalence before anything is timed,
+        # (1) ONE frame split over the ranks + all-gather of the output maps (strong scaling of inference),
+        # (2) BASELINE config 4: one 8192-ray batch sharded over the ranks, gradient all-reduce inside the timed step
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import ddp_check
+        import train_step_bench
+        from contrastive_lift_b200 import parallel as par
+        try:
+            multi["ddp_check"] = ddp_check.check(dev, verbose=False)
+        except Exception as e:
+            multi["ddp_check"] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
+        c2w0 = syn.camera(H, W)[1].numpy()
+        b0, b1 = par.shard_range(n_rays, rank, world)
+
+        def step_split():
+            rays, _bad = cl.get_rays(H, W, k_np, c2w0, device=dev)          # every rank: the same frame, its own ray range
+            out = rend(model, rays[b0:b1].contiguous(), 1.0, False, False)
+            maps = torch.cat([out[0], out[1], out[2], out[3][:, None]], 1)
+            return par.gather_rays_output(maps, n_rays)
+
+        with torch.no_grad():
+            for _ in range(3):
+                full = step_split()
+            barrier()
+            ms_split = timed(step_split, args.steps)
+            barrier()
+            single = None
+            if rank == 0:       # the gathered frame against the same frame rendered whole on this GPU
+                rays, _bad = cl.get_rays(H, W, k_np, c2w0, device=dev)
+                o = rend(model, rays, 1.0, False, False)
+                single = torch.cat([o[0], o[1], o[2], o[3][:, None]], 1)
+                split_equal = bool(torch.equal(full, single))
+                split_err = float((full - single).abs().max())
+            del full, single
+        t = torch.tensor([sum(ms_split)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        multi["frame_split"] = {"workload": f"ONE {H}x{W} frame, ray ranges sharded over {world} GPUs, maps all-gathered "
+                                            f"({(3 + N_CLS + 2 * N_INS + 1) * 4} B/ray) to every rank, inside the timed region",
+                                "ms_per_frame": float(t) / args.steps, "Mrays_per_s": n_rays * args.steps / (float(t) * 1e-3) / 1e6,
+                                "scaling": "strong"}
+        if rank == 0:
+            multi["frame_split"].update({"equals_single_gpu_frame": split_equal, "max_abs_diff": split_err})
+        flush = d_rays = None
+        torch.cuda.empty_cache()
+        try:
+            multi["train_step_cfg4"] = train_step_bench.measure(steps=10, warmup=3, device_index=local, rays=8192, classes=2,
+                                                                distributed=True)
+        except Exception as e:
+            multi["train_step_cfg4"] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -356,17 +452,21 @@ def run_ours(args):
             torch.cuda.empty_cache()
             sys.path.insert(0, os.path.join(ROOT, "scripts"))
             import train_step_bench
-            line["train_step"] = train_step_bench.measure(steps=10, warmup=3, device_index=local, with_cpu=False)
+            line["train_step"] = train_step_bench.measure(steps=10, warmup=3, device_index=local, with_cpu=False, parity=True)
+            # BASELINE config 4 on ONE GPU: the N = 1 point of the strong-scaling training figure the N > 1 lines carry
+            line["train_step_cfg4"] = train_step_bench.measure(steps=10, warmup=3, device_index=local, rays=8192, classes=2)
         except Exception as e:      # never lose the bench line over the extra figure
             line["train_step"] = {"error": f"{type(e).__name__}: {e}"}
+    line.update(multi)
     if world == 1 and not args.no_cpu:
-        v, n, dt, cpu_rays, cpu_rgb, cpu_depth = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 131072, keep=True)
-        line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": f"{n} rays strided from the same {H}x{W} frame, S={args.samples}, chunk=2048, all heads, {dt:.1f} s"}
+        v, n, dt, kind, cpu_rays, *cpu_maps = cpu_reference_rate(args.frame, args.samples, args.cpu_seconds, 131072, keep=True)
+        line["cpu_baseline"] = {"value": v, "unit": "Mrays/s", "cores": os.cpu_count() or 1, "kind": kind,
+                                "sample": f"{n} rays strided from the same {H}x{W} frame, S={args.samples}, chunk=2048, all heads, {dt:.1f} s"
+                                          + ("; the unmodified reference modules" if kind == "reference" else "; reference-pinned port")}
         # "PSNR match" of BASELINE.json's metric: the rays the CPU reference just rendered, rendered again by the CUDA path,
         # PSNR = -10 log10(mse) of the two rgb maps (util/metrics.py:25-26); identical images give +inf, reported capped
         try:
-            line["psnr_match"] = psnr_match(rend, model, cpu_rays, cpu_rgb, cpu_depth, dev)
+            line["psnr_match"] = psnr_match(rend, model, cpu_rays, cpu_maps, dev)
         except Exception as e:      # never lose the bench line over the extra figure
             line["psnr_match"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)

@@ -1,5 +1,5 @@
 """Data-parallel plumbing for the render path: one process per GPU, parameters replicated,
-rays sharded, gradients mean-all-reduced once per backward over a flat fp32 arena.
+rays sharded, gradients sum-all-reduced once per backward over a persistent flat fp32 arena (the 1/N rides in the optimizer).
 
 This reproduces what the reference gets from Lightning's DDPStrategy (trainer/__init__.py:95-108): each rank renders
 its own rays, every ``manual_backward`` (trainer:198, :220) is followed by a mean of the gradients over ranks.  The
@@ -46,29 +46,104 @@ def gather_rays_output(local: torch.Tensor, n_total: int, group=None) -> torch.T
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
 
 
+class GradientArena:
+    """Persistent flat fp32 arena for the gradient all-reduce of one optimizer's parameters (DDP's bucket, kept across steps).
+
+    ``reduce()`` gathers the live ``.grad``s into the arena with one multi-tensor copy, issues ONE ``all_reduce(SUM)`` on
+    the arena (+ one presence flag per parameter, see below) and scatters the sums back with one multi-tensor copy; the 1/N
+    of the mean is left to the optimizer (``FusedAdam(grad_scale=1/N)`` folds it into the update) unless ``average=True``.
+    Nothing is allocated after the first call.  ``drain_ms()`` is the summed device time of the ``timed`` reduces since the last
+    drain (CUDA events read after the fact, so timing never stalls the host inside a step).
+
+    Presence flags: a parameter whose grad is None here (head not evaluated in this pass - the reason the reference needs
+    ``find_unused_parameters=True``, trainer/__init__.py:95-108) contributes zeros and stays None.  DDP would hand every rank
+    the reduced gradient if ANY rank had one; here the passes are the same on every rank by construction, so a differing
+    None pattern is a bug: the summed flags are checked one call later (no sync on the hot path) and raise."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        if not self.params:
+            raise ValueError("GradientArena: no trainable parameters")
+        dev = self.params[0].device
+        self.sizes = [p.numel() for p in self.params]
+        self.total = sum(self.sizes)
+        self.flat = torch.zeros((self.total + len(self.params),), dtype=torch.float32, device=dev)
+        self.slots = [s.view_as(p) for s, p in zip(self.flat[:self.total].split(self.sizes), self.params)]
+        self.flags = self.flat[self.total:]
+        self._events: List[tuple] = []
+        self._pending_flags = None
+        self._host_flags = torch.zeros((len(self.params),), dtype=torch.float32).pin_memory() if dev.type == "cuda" else \
+            torch.zeros((len(self.params),), dtype=torch.float32)
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def check_patterns(self) -> None:
+        """Raise if, in the previous reduce, some ranks had a gradient for a parameter and others did not."""
+        if self._pending_flags is None:
+            return
+        flags, world = self._pending_flags
+        self._pending_flags = None
+        bad = [i for i, v in enumerate(flags.tolist()) if v not in (0.0, float(world))]
+        if bad:
+            raise RuntimeError(f"GradientArena: gradient None-pattern differs across ranks for parameter slots {bad[:8]} "
+                               "(every rank must run the same passes; DDP's find_unused_parameters semantics are not emulated)")
+
+    @torch.no_grad()
+    def reduce(self, average: bool = False, timed: bool = False) -> int:
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return 0
+        self.check_patterns()
+        world = dist.get_world_size(self.group)
+        live = [(s, p.grad) for s, p in zip(self.slots, self.params) if p.grad is not None]
+        dead = [s for s, p in zip(self.slots, self.params) if p.grad is None]
+        ev = None
+        if timed and self.flat.is_cuda:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        if dead:
+            torch._foreach_zero_(dead)
+        if live:
+            torch._foreach_copy_([s for s, _ in live], [g for _, g in live])
+        self._host_flags.copy_(torch.tensor([0.0 if p.grad is None else 1.0 for p in self.params]))
+        self.flags.copy_(self._host_flags, non_blocking=True)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        if average:
+            self.flat[:self.total].mul_(1.0 / world)
+        if live:
+            torch._foreach_copy_([g for _, g in live], [s for s, _ in live])
+        if ev is not None:
+            ev[1].record()
+            self._events.append(ev)
+        self._pending_flags = (self.flags.to("cpu", non_blocking=True) if self.flat.is_cuda else self.flags.clone(), world)
+        return self.total * 4
+
+    def drain_ms(self) -> float:
+        total = 0.0
+        for a, b in self._events:
+            b.synchronize()
+            total += a.elapsed_time(b)
+        self._events = []
+        return total
+
+
+_ARENAS = {}
+
+
 @torch.no_grad()
 def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, average: bool = True) -> int:
-    """Sum (then 1/world) every parameter's ``.grad`` across ranks through ONE flat buffer / one collective.
-
-    Parameters whose grad is None on this rank (heads not evaluated in this pass - the reference needs
-    ``find_unused_parameters=True`` for the same reason) contribute zeros and stay None.  Returns the number of
-    bytes reduced."""
+    """Sum (then 1/world) every parameter's ``.grad`` across ranks through ONE flat buffer / one collective
+    (``GradientArena``, cached per parameter set, so repeated calls allocate nothing).  Returns the bytes reduced."""
     plist: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
     if not plist or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 0
-    dev = plist[0].device
-    total = sum(p.numel() for p in plist)
-    flat = torch.zeros((total,), dtype=torch.float32, device=dev)
-    slots = flat.split([p.numel() for p in plist])                    # views into the arena, one per parameter
-    live = [(s, p.grad) for s, p in zip(slots, plist) if p.grad is not None]
-    if live:      # one multi-tensor copy in, one out (instead of a launch per parameter and direction)
-        torch._foreach_copy_([s.view_as(g) for s, g in live], [g for _, g in live])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    if average:
-        flat.mul_(1.0 / dist.get_world_size(group))
-    if live:
-        torch._foreach_copy_([g for _, g in live], [s.view_as(g) for s, g in live])
-    return total * 4
+    key = (tuple(id(p) for p in plist), id(group))
+    arena = _ARENAS.get(key)
+    if arena is None or any(a is not b for a, b in zip(arena.params, plist)):
+        arena = _ARENAS[key] = GradientArena(plist, group)
+    return arena.reduce(average=average)
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

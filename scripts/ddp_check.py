@@ -33,11 +33,10 @@ def loss_of(out, tgt, n_total):
     return ((rgb - tgt) ** 2).sum() / (3 * n_total) + 0.1 * (-sem[:, 1]).sum() / n_total + 0.05 * ins.sum() / n_total
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def check(dev, verbose=True):
+    """Runs on every rank of an initialised NCCL process group -> dict (identical on all ranks): sharded training gradients
+    after the arena all-reduce vs the whole batch on rank 0, and sharded inference gathered back vs the single-GPU frame."""
+    rank, world = dist.get_rank(), dist.get_world_size()
     model, rend = build(dev)
     par.broadcast_parameters(model)
     rays = syn.random_rays(9, 1024).to(dev)
@@ -50,8 +49,9 @@ def main():
     with torch.no_grad():
         inf = rend(model, rays[b:e].contiguous(), 0.0, True, False)
         full_rgb = par.gather_rays_output(inf[0], rays.shape[0])
-    ok = True
+    res = torch.zeros(3, device=dev, dtype=torch.float64)            # ok, worst gradient error, inference equal
     if rank == 0:
+        ok = True
         model.zero_grad(set_to_none=True)
         out = rend(model, rays, 0.0, True, True)
         loss_of(out, tgt, rays.shape[0]).backward()
@@ -64,17 +64,31 @@ def main():
             worst = max(worst, err)
             if err > 2e-3:
                 ok = False
-                print(f"MISMATCH {k}: {err:.3e}")
+                if verbose:
+                    print(f"MISMATCH {k}: {err:.3e}")
         with torch.no_grad():
             single = rend(model, rays, 0.0, True, False)[0]
         same = bool(torch.allclose(single, full_rgb, rtol=1e-5, atol=1e-6))
         ok = ok and same
-        print(f"ddp_check world={world}: all-reduced {nbytes} B, worst relative gradient error {worst:.2e}, "
-              f"sharded inference == single-GPU frame: {same} -> {'OK' if ok else 'FAIL'}")
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
+        res = torch.tensor([1.0 if ok else 0.0, worst, 1.0 if same else 0.0], device=dev, dtype=torch.float64)
+    dist.broadcast(res, 0)
+    ok, worst, same = (float(v) for v in res.cpu())
+    return {"ok": bool(ok), "world": world, "allreduced_bytes": int(nbytes), "worst_rel_grad_err": worst,
+            "sharded_inference_equals_single_gpu": bool(same), "tolerance": 2e-3}
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    r = check(dev)
+    if rank == 0:
+        print(f"ddp_check world={world}: all-reduced {r['allreduced_bytes']} B, worst relative gradient error "
+              f"{r['worst_rel_grad_err']:.2e}, sharded inference == single-GPU frame: {r['sharded_inference_equals_single_gpu']} "
+              f"-> {'OK' if r['ok'] else 'FAIL'}")
     dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) else 1)
+    sys.exit(0 if r["ok"] else 1)
 
 
 if __name__ == "__main__":

@@ -18,7 +18,10 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import refload
+    assert d["cpu_baseline"]["kind"] == ("reference" if refload.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["rays_per_step_on_host"] == 2048 and d["config"]["rays_per_step_per_gpu"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None and "workload" in d["config"]
 
@@ -49,16 +52,34 @@ def test_roofline_flop_basis_matches_the_survey_figure():
 
 def test_cpu_baseline_leg_keeps_what_the_psnr_match_needs():
     import bench
-    rate, n, dt, rays, rgb, depth = bench.cpu_reference_rate(16, 32, 5.0, 256, keep=True)
+    rate, n, dt, kind, rays, rgb, sem, ins, depth = bench.cpu_reference_rate(16, 32, 5.0, 256, keep=True)
     assert rate > 0 and n == 256 == rays.shape[0] and rgb.shape == (256, 3) and depth.shape == (256,)
+    assert sem.shape == (256, bench.N_CLS) and ins.shape == (256, 2 * bench.N_INS) and kind in ("reference", "port")
 
     class SameMaps:                                   # stands in for the CUDA renderer: returns the reference's own maps
         def __call__(self, model, r, *a):
-            return rgb + 1e-6, None, None, depth
-    out = bench.psnr_match(SameMaps(), None, rays, rgb, depth, "cpu")
+            return rgb + 1e-6, sem, ins, depth
+    out = bench.psnr_match(SameMaps(), None, rays, (rgb, sem, ins, depth), "cpu")
     assert 110.0 < out["psnr_db"] <= 200.0 and out["rays"] == 256 and out["depth_max_rel_err"] == 0.0
-    assert bench.psnr_match(type("Z", (), {"__call__": lambda s, m, r, *a: (rgb, None, None, depth)})(), None, rays, rgb, depth,
-                            "cpu")["psnr_db"] == 200.0      # identical images: capped, never inf (the line must stay JSON)
+    assert out["semantic_prob_max_abs_err"] == 0.0 and out["instance_max_rel_err"] == 0.0 and out["ok"]
+    same = type("Z", (), {"__call__": lambda s, m, r, *a: (rgb, sem, ins, depth)})()
+    assert bench.psnr_match(same, None, rays, (rgb, sem, ins, depth), "cpu")["psnr_db"] == 200.0   # capped, never inf (JSON)
+
+
+def test_reference_and_port_cpu_legs_agree_bit_for_bit(monkeypatch):
+    """The staged / live reference modules and the oracle port render the bench scene's rays identically (when the reference
+    is reachable), so either is a valid cpu_baseline and psnr_match checker."""
+    import bench
+    from oracle import refload
+    if not refload.available():
+        return
+    render_ref, rays_ref, kind = bench.cpu_renderer(24, 48)
+    assert kind == "reference"
+    monkeypatch.setenv("CLIFT_BENCH_CPU_PORT", "1")
+    render_port, rays_port, kind2 = bench.cpu_renderer(24, 48)
+    assert kind2 == "port" and torch.equal(rays_ref, rays_port)
+    for a, b in zip(render_ref(rays_ref[:300]), render_port(rays_port[:300])):
+        assert torch.equal(a, b)
 
 
 def test_oracle_is_only_reachable_from_the_allowed_places():

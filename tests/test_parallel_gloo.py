@@ -54,6 +54,16 @@ def _worker(rank, world, port, out):
             assert torch.equal(par.gather_rays_output(par.shard_rays(m[:, 0]), n), m[:, 0]), n
         with pytest.raises(ValueError):
             par.gather_rays_output(x, x.shape[0])          # the whole frame is not this rank's shard
+        # a None pattern that differs across ranks (one rank skipped a head) is reported by the next reduce
+        arena = par.GradientArena(net.parameters())
+        for p in net.parameters():
+            p.grad = torch.ones_like(p)
+        if rank == 0:
+            net[3].bias.grad = None
+        arena.reduce()
+        with pytest.raises(RuntimeError, match="None-pattern"):
+            arena.reduce()
+        arena.reduce()                                     # the flags of the call that raised were consumed
         out.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         out.put((rank, repr(e)))
