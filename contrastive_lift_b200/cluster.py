@@ -58,7 +58,7 @@ def assign_clusters(all_thing_features, all_points_semantics, all_centroids: Dic
     scratch = torch.empty((n_cls,), dtype=torch.int32, device=dev)
     stats = torch.empty((2,), dtype=torch.int32, device=dev)
     with L.on(dev):
-        L.check(lib.clift_assign_clusters(L.ptr(feats), n, d, feats.stride(0), L.ptr(scores), n_cls, L.ptr(cents), L.ptr(d_first),
+        L.check(lib.clift_assign_clusters(L.ptr(feats), n, d, feats.stride(0) if n else d + 1, L.ptr(scores), n_cls, L.ptr(cents), L.ptr(d_first),
                                           L.ptr(d_count), L.ptr(labels), L.ptr(scratch), L.ptr(stats), L.stream_ptr(dev)))
         width, missing = (int(v) for v in stats.cpu().tolist())
         if missing:
