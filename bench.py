@@ -435,7 +435,8 @@ def run_ours(args):
                 rays, _bad = cl.get_rays(H, W, k_np, c2w0, device=dev)
                 o = rend(model, rays, 1.0, False, False)
                 single = torch.cat([o[0], o[1], o[2], o[3][:, None]], 1)
-                split_equal = bool(torch.equal(full, single))
+                # per-ray sums of a ray whose samples straddle two head tiles are combined with atomics: last-bit differences
+                split_equal = bool(torch.allclose(full, single, rtol=1e-5, atol=2e-6))
                 split_err = float((full - single).abs().max())
             del full, single
         t = torch.tensor([sum(ms_split)], device=dev, dtype=torch.float64)
@@ -445,7 +446,8 @@ def run_ours(args):
                                 "ms_per_frame": float(t) / args.steps, "Mrays_per_s": n_rays * args.steps / (float(t) * 1e-3) / 1e6,
                                 "scaling": "strong"}
         if rank == 0:
-            multi["frame_split"].update({"equals_single_gpu_frame": split_equal, "max_abs_diff": split_err})
+            multi["frame_split"].update({"matches_single_gpu_frame": split_equal, "max_abs_diff": split_err,
+                                         "tolerance": "allclose(rtol 1e-5, atol 2e-6)"})
         flush = d_rays = None
         torch.cuda.empty_cache()
         try:
