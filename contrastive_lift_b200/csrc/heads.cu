@@ -15,7 +15,10 @@
 //
 // This file is the fp32 CUDA-core (FFMA) implementation: exact fp32 products/accumulation like the
 // reference's sgemm path (TF32 is off in the reference, trainer:33-35).
+#include <cuda_fp16.h>
+
 #include "launchers.h"
+#include "tcgen05.cuh"
 
 namespace clift {
 
@@ -25,6 +28,16 @@ constexpr int kTile = CLIFT_TILE;
 constexpr int kThreads = 256;
 constexpr int kActRows = CLIFT_MAX_WIDTH;
 constexpr int kSlabRows = 16;
+
+// ---- tensor-core data-gradient engine of the backward kernel (tcgen05 kind::f16, 3-product fp16 split) ----------------
+// dA[n][m] = sum_k W[k][n] dZ[k][m] for one 128-record tile: the M = 128 records are the MMA rows, the dZ rows of `act` are
+// converted k-step by k-step (16 K rows) into a double-buffered fp16 (hi, lo) operand chunk, the weights are the
+// clift_pack_linear_tc16() slabs of W^T streamed by bulk TMA through a small ring, the accumulator lives in tensor memory.
+constexpr int kDgStages = 3;                 // weight ring depth (16 KB slabs: one k-step at N = 256)
+constexpr int kDgStageBytes = 16384;
+constexpr int kDgABytes = 8192;              // one operand chunk: [hi | lo][2 k-chunks][128 rows][8 halves]
+constexpr uint32_t kDgTmemCols = 256;
+constexpr int kDgHeaderFloats = 16;          // header of a clift_pack_linear_tc16() operand
 
 struct HeadsParams {
     const float4* rec_pos;
@@ -57,6 +70,26 @@ struct Smem {
     int* runs;       // [kTile + 1]
     float* dir;      // [3][kTile]
 };
+
+// state of the tensor-core dgrad engine; the counters are identical in every thread (uniform control flow)
+struct DgEngine {
+    unsigned char* a_op;     // [2][kDgABytes]
+    unsigned char* w_ring;   // [kDgStages][kDgStageBytes]
+    uint64_t* w_full;        // [kDgStages]
+    uint64_t* w_empty;       // [kDgStages]
+    uint64_t* a_free;        // [2]
+    uint64_t* d_done;
+    float* red;              // [8]
+    uint32_t tmem;
+    uint32_t a_fills[2];     // fills of each operand chunk buffer so far
+    uint32_t w_loads;        // weight slabs loaded so far (stage = w_loads % kDgStages)
+    uint32_t w_used;         // weight slabs consumed so far
+    uint32_t d_count;        // GEMMs completed so far
+    bool on;
+};
+// the weight ring aliases the FMA path's two 16 KB cp.async slabs (the two engines never run at the same time) + one more
+constexpr size_t kDgExtraBytes = 1024 + (size_t)(kDgStages - 2) * kDgStageBytes + 2 * kDgABytes + (2 * kDgStages + 3) * 8 + 64;
+static_assert(kDgStageBytes == kSlabRows * 256 * 4, "ring stage = one FMA weight slab");
 
 constexpr size_t kSmemBytes = (size_t)kActRows * kTile * 4 + 2 * kSlabRows * 256 * 4 + kTile * 16 + kTile * 4 +
                               (kTile + 4) * 4 + 3 * kTile * 4;
@@ -387,6 +420,8 @@ struct HeadsBwdParams {
     float* g_app_plane[3];
     float* g_app_line[3];
     const float* basis_dgrad;
+    const void* basis_dg16;           // tensor-core operand of the basis data gradient (null: FP32 FMA)
+    int use_tc;                       // 1: data gradients with a w_dg16 operand run on tcgen05
     int dim_app, pe_view, pe_feat;
     FactorParams semg, insg;          // grid-mode semantic / instance heads (comps == 0: MLP mode)
     float* g_semg_plane[3];
@@ -437,15 +472,151 @@ __device__ __forceinline__ void run_dgrad(const Smem& sm, const float* w_dgrad, 
         mlp_layer<4>(sm, w_dgrad, nullptr, kp, false);
 }
 
+__device__ __forceinline__ uint32_t dg_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+// thread 0: slab `idx` of the running GEMM -> next ring stage (waits until the MMAs that read that stage have completed)
+__device__ __forceinline__ void dg_load(const DgEngine& E, const unsigned char* slabs, uint32_t slab_bytes, int idx) {
+    const uint32_t st = E.w_loads % kDgStages, round = E.w_loads / kDgStages;
+    if (round > 0) tc::mbar_wait(&E.w_empty[st], (round - 1) & 1u);
+    tc::mbar_arrive_expect_tx(&E.w_full[st], slab_bytes);
+    tc::bulk_load(E.w_ring + (size_t)st * kDgStageBytes, slabs + (size_t)idx * slab_bytes, slab_bytes, &E.w_full[st]);
+}
+
+// Tensor-core form of run_dgrad: act rows [0, round16(K)) = dZ[k][m] (rows >= K zero) -> act rows [0, out_rows) = dA[n][m]
+// (rows >= n_in zero).  `w16` = clift_pack_linear_tc16() operand of W^T (K = the layer's out width, N = its in width).
+// The operand scale is dynamic: s = 2^floor(log2(2^14 / max|dZ|)) over the tile (exact power of two), so every scaled
+// dZ is below 2^14 and splits into fp16 (hi, lo) with 22 significant bits; the weight scale is the pack-time one.
+__device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const void* w16, int K, int n_in, int out_rows) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k_steps = (K + 15) >> 4, kp = k_steps * 16;
+    const int n_pad = (n_in + 31) & ~31;
+    float mx = 0.0f;
+    {
+        const float4* a4 = reinterpret_cast<const float4*>(sm.act);
+        for (int i = tid; i < kp * (kTile / 4); i += kThreads) {
+            const float4 v = a4[i];
+            mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) E.red[warp] = mx;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) mx = fmaxf(mx, E.red[w]);
+    }
+    if (mx == 0.0f) {       // nothing flows back through this layer for this tile (e.g. the detached slow net): dA = 0
+        float4* d4 = reinterpret_cast<float4*>(sm.act);
+        for (int i = tid; i < out_rows * (kTile / 4); i += kThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+        return;
+    }
+    int ex = 0;
+    frexpf(mx, &ex);                                   // mx < 2^ex
+    const float sa = ldexpf(1.0f, max(-60, min(60, 14 - ex)));
+    const float* meta = reinterpret_cast<const float*>(w16);
+    const float inv = 1.0f / (sa * meta[1]);
+    const unsigned char* slabs = reinterpret_cast<const unsigned char*>(meta + kDgHeaderFloats);
+    const uint32_t slab_bytes = 64u * (uint32_t)n_pad;
+    const bool stacked = n_pad <= 128;
+    const int n_pre = min(kDgStages, k_steps);
+    for (int i = 0; i < n_pre; ++i) {
+        if (tid == 0) dg_load(E, slabs, slab_bytes, i);
+        ++E.w_loads;
+    }
+    const int m = tid & (kTile - 1), c = tid >> 7;
+    for (int ks = 0; ks < k_steps; ++ks) {
+        const int b = ks & 1;
+        if (E.a_fills[b] > 0) tc::mbar_wait(&E.a_free[b], (E.a_fills[b] - 1) & 1u);
+        ++E.a_fills[b];
+        {   // records m, K rows [16 ks + 8 c, + 8) -> one 16-byte row of the hi chunk and one of the lo chunk
+            const float* src = sm.act + (size_t)(ks * 16 + c * 8) * kTile + m;
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x = src[(2 * i) * kTile] * sa, y = src[(2 * i + 1) * kTile] * sa;
+                const __half2 hh = __floats2half2_rn(x, y);
+                const float2 back = __half22float2(hh);
+                h[i] = dg_bits(hh);
+                l[i] = dg_bits(__floats2half2_rn(x - back.x, y - back.y));
+            }
+            unsigned char* dst = E.a_op + (size_t)b * kDgABytes + ((size_t)c * kTile + m) * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(dst + kDgABytes / 2) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t st = E.w_used % kDgStages;
+            tc::mbar_wait(&E.w_full[st], (E.w_used / kDgStages) & 1u);
+            tc::fence_after_sync();
+            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO 128 B, descriptor version 1
+            auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+            const uint32_t a_lbo = (kTile * 16u >> 4) << 16;
+            const uint32_t ah = (tc::smem_addr(E.a_op + (size_t)b * kDgABytes) >> 4) | a_lbo;
+            const uint32_t al = (tc::smem_addr(E.a_op + (size_t)b * kDgABytes + kDgABytes / 2) >> 4) | a_lbo;
+            const uint32_t w_lo = tc::smem_addr(E.w_ring + (size_t)st * kDgStageBytes) >> 4;
+            const uint32_t rows1 = stacked ? 2u * n_pad : (uint32_t)n_pad;
+            const uint32_t idesc = tc::make_idesc_f16(kTile, n_pad);
+            const uint64_t b1 = desc(w_lo | (rows1 << 16));
+            const uint32_t acc = ks > 0 ? 1u : 0u;
+            if (stacked) {      // slab = [2 k-chunks][hi | lo][n_pad][8]: A_hi*[W_hi ; W_lo] in one MMA, then A_lo*W_hi
+                tc::mma_ss_f16(E.tmem, desc(ah), b1, tc::make_idesc_f16(kTile, 2 * n_pad), acc);
+                tc::mma_ss_f16(E.tmem, desc(al), b1, idesc, 1u);
+            } else {            // slab = [hi | lo][2 k-chunks][n_pad][8]
+                tc::mma_ss_f16(E.tmem, desc(ah), b1, idesc, acc);
+                tc::mma_ss_f16(E.tmem, desc(ah), desc((w_lo + 2u * rows1) | (rows1 << 16)), idesc, 1u);
+                tc::mma_ss_f16(E.tmem, desc(al), b1, idesc, 1u);
+            }
+            tc::mma_commit(&E.w_empty[st]);
+            tc::mma_commit(&E.a_free[b]);
+            if (ks == k_steps - 1) tc::mma_commit(E.d_done);
+            // refill one k-step late: the stage of slab ks - 1 is free (or about to be) while this k-step's MMAs run
+            if (ks >= 1 && ks - 1 + n_pre < k_steps) dg_load(E, slabs, slab_bytes, ks - 1 + n_pre);
+        }
+        ++E.w_used;
+        if (ks >= 1 && ks - 1 + n_pre < k_steps) ++E.w_loads;
+    }
+    tc::mbar_wait(E.d_done, E.d_count & 1u);
+    ++E.d_count;
+    tc::fence_after_sync();
+    {   // accumulator (lane = record, column = n) -> act[n][m]; warps w and w + 4 share a lane quarter and split the columns
+        const int q = warp & 3, mrow = q * 32 + lane;
+        const uint32_t taddr = E.tmem + ((uint32_t)(q * 32) << 16);
+        for (int c0 = (warp >> 2) * 16; c0 < n_pad; c0 += 32) {
+            float v[16];
+            tc::tmem_ld16(taddr + (uint32_t)c0, v);
+            if (stacked) {
+                float u[16];
+                tc::tmem_ld16(taddr + (uint32_t)(n_pad + c0), u);
+                tc::tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += u[i];
+            } else {
+                tc::tmem_wait_ld();
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sm.act[(size_t)(c0 + i) * kTile + mrow] = v[i] * inv;
+        }
+        float4* d4 = reinterpret_cast<float4*>(sm.act + (size_t)n_pad * kTile);
+        for (int i = tid; i < (out_rows - n_pad) * (kTile / 4); i += kThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+}
+
 // act rows [0, n_pad(out)) hold dZ of the LAST layer (pad rows zero).  Walks the stack backwards.
 // On return (need_input_grad) act rows [0, dgrad_pad(dims[0])) hold dL/d(input of layer 0).
-__device__ __forceinline__ void mlp_backward(const Smem& sm, const clift_mlp& mlp, const clift_mlp_grad& g, const float* stash_a,
-                                             float* stash_z, const int* a_off, const int* z_off, bool need_input_grad) {
+__device__ __forceinline__ void mlp_backward(const Smem& sm, DgEngine& E, const clift_mlp& mlp, const clift_mlp_grad& g,
+                                             const float* stash_a, float* stash_z, const int* a_off, const int* z_off,
+                                             bool need_input_grad) {
     for (int l = mlp.n_layers - 1; l >= 0; --l) {
         const int n_out = mlp.dims[l + 1], n_in = mlp.dims[l];
         emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
         if (l == 0 && !need_input_grad) break;
-        run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
+        if (E.on && mlp.w_dg16[l])
+            run_dgrad_tc(sm, E, mlp.w_dg16[l], n_out, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256));
+        else
+            run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
         if (l > 0) {   // ReLU mask from the saved input of layer l (= post-ReLU output of layer l-1)
             const float4* a4 = reinterpret_cast<const float4*>(stash_a + (size_t)a_off[l] * kTile);
             float4* d4 = reinterpret_cast<float4*>(sm.act);
@@ -523,18 +694,59 @@ __device__ __forceinline__ void grid_head_backward(const Smem& sm, const FactorP
 
 template <int NV>
 __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __grid_constant__ HeadsBwdParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem sm;
     sm.act = reinterpret_cast<float*>(smem_raw);
     sm.wslab = sm.act + kActRows * kTile;
-    sm.pos = reinterpret_cast<float4*>(sm.wslab + 2 * kSlabRows * 256);
+    sm.pos = reinterpret_cast<float4*>(sm.wslab + kDgStages * kSlabRows * 256);   // 3 slabs here: the dgrad weight ring
     sm.ray = reinterpret_cast<int*>(sm.pos + kTile);
     sm.runs = sm.ray + kTile;
     sm.dir = reinterpret_cast<float*>(sm.runs + kTile + 4);   // here: [3][kTile] saved rgb of the records
+    const int tid = threadIdx.x;
+
+    // tensor-core dgrad engine: weight ring = the FMA path's cp.async slabs + one more 16 KB stage (the two engines never
+    // run at the same time), operand chunks, barriers, tensor memory
+    DgEngine E;
+    E.on = P.use_tc != 0;
+    E.w_ring = reinterpret_cast<unsigned char*>(sm.wslab);
+    {
+        // layout after the FMA regions: [pos | ray | runs | dir] stay where they are; the engine's extra stage, operand
+        // chunks and barriers follow them, 1 KB aligned
+        uintptr_t p = reinterpret_cast<uintptr_t>(sm.dir + 3 * kTile);
+        p = (p + 1023) & ~(uintptr_t)1023;
+        unsigned char* q = reinterpret_cast<unsigned char*>(p);
+        E.a_op = q;
+        q += 2 * kDgABytes;
+        E.w_full = reinterpret_cast<uint64_t*>(q);
+        E.w_empty = E.w_full + kDgStages;
+        E.a_free = E.w_empty + kDgStages;
+        E.d_done = E.a_free + 2;
+        E.red = reinterpret_cast<float*>(E.d_done + 1);
+    }
+    E.a_fills[0] = E.a_fills[1] = 0;
+    E.w_loads = E.w_used = E.d_count = 0;
+    E.tmem = 0;
+    if (E.on) {
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(E.red + 8);
+        if (tid == 0) {
+            for (int i = 0; i < kDgStages; ++i) {
+                tc::mbar_init(&E.w_full[i], 1);
+                tc::mbar_init(&E.w_empty[i], 1);
+            }
+            tc::mbar_init(&E.a_free[0], 1);
+            tc::mbar_init(&E.a_free[1], 1);
+            tc::mbar_init(E.d_done, 1);
+            tc::fence_barrier_init();
+        }
+        if ((tid >> 5) == 0) tc::tmem_alloc(tmem_slot, kDgTmemCols);
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        E.tmem = *tmem_slot;
+    }
 
     const long long n_act = min((long long)P.stats[0], P.cap);
     const long long n_tiles = (n_act + kTile - 1) / kTile;
-    const int tid = threadIdx.x;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long base = tile * kTile;
@@ -583,7 +795,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                 for (int c = P.n_cls; c < rows; ++c) sm.act[(size_t)c * kTile + tid] = 0.0f;
             }
             __syncthreads();
-            mlp_backward(sm, P.sem, P.g_sem_mlp, sa, sz, P.lay.a_off[0], P.lay.z_off[0], P.semg.comps != 0);
+            mlp_backward(sm, E, P.sem, P.g_sem_mlp, sa, sz, P.lay.a_off[0], P.lay.z_off[0], P.semg.comps != 0);
             if (P.semg.comps)
                 grid_head_backward(sm, P.semg, P.semg_basis_dgrad, P.semg_dim, sz + (size_t)P.lay.z_off[5][0] * kTile,
                                    P.g_semg_plane, P.g_semg_line, nv);
@@ -599,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                     for (int c = P.d_ins; c < rows; ++c) sm.act[(size_t)c * kTile + tid] = 0.0f;
                 }
                 __syncthreads();
-                mlp_backward(sm, net == 0 ? P.insf : P.inss, net == 0 ? P.g_insf_mlp : P.g_inss_mlp, sa, sz,
+                mlp_backward(sm, E, net == 0 ? P.insf : P.inss, net == 0 ? P.g_insf_mlp : P.g_inss_mlp, sa, sz,
                              P.lay.a_off[1 + net], P.lay.z_off[1 + net], P.insg.comps != 0);
                 if (P.insg.comps) {
                     // the fast and the slow net read the same basis feature: its gradient is their sum.  The fast net's
@@ -642,7 +854,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
                 if (ray >= 0) P.g_w[(int64_t)ray * P.S + P.rec_idx[base + tid]] = gw;
             }
             __syncthreads();
-            mlp_backward(sm, P.rgb, P.g_rgb_mlp, sa, sz, P.lay.a_off[3], P.lay.z_off[3], true);
+            mlp_backward(sm, E, P.rgb, P.g_rgb_mlp, sa, sz, P.lay.a_off[3], P.lay.z_off[3], true);
             // positional-encoding backward: dfeat_a = dIn[a] + sum_j 2^j (cos_aj * dIn[sin_aj] - sin_aj * dIn[cos_aj])
             const int A = P.dim_app, pf = P.pe_feat;
             const int o_sf = A + 3, o_cf = o_sf + A * pf;
@@ -665,9 +877,19 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
             __syncthreads();
             // basis layer: dZ = dfeat (64 rows, zero padded) -> Z-stash, then dprod = basis^T dfeat
             store_rows(sm, sz + (size_t)P.lay.z_off[4][0] * kTile, 64);
-            run_dgrad(sm, P.basis_dgrad, A, 3 * P.app.comps);
+            if (E.on && P.basis_dg16) {
+                const int n_in = 3 * P.app.comps;
+                run_dgrad_tc(sm, E, P.basis_dg16, A, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256));
+            } else {
+                run_dgrad(sm, P.basis_dgrad, A, 3 * P.app.comps);
+            }
             scatter_factors<NV>(sm, P.app, P.g_app_plane, P.g_app_line, nv);
         }
+    }
+    if (E.on) {
+        tc::fence_before_sync();
+        __syncthreads();
+        if ((tid >> 5) == 0) tc::tmem_dealloc(E.tmem, kDgTmemCols);
     }
 }
 
@@ -968,6 +1190,11 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
         P.g_app_line[m] = grad->appearance_line[m];
     }
     P.basis_dgrad = field->basis_dgrad;
+    P.basis_dg16 = field->basis_dg16;
+    {   // development switch: CLIFT_DGRAD_FMA=1 keeps every data gradient on the FP32-FMA tile GEMM
+        const char* e = getenv("CLIFT_DGRAD_FMA");
+        P.use_tc = !(e && atoi(e) != 0);
+    }
     P.dim_app = field->dim_appearance;
     P.pe_view = field->pe_view;
     P.pe_feat = field->pe_feat;
@@ -1055,8 +1282,8 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
 #define CLIFT_HEADS_BWD_CASE(NV)                                                                                       \
     case NV: {                                                                                                         \
         CLIFT_CUDA(cudaFuncSetAttribute(heads_backward_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                        (int)kSmemBytes));                                                             \
-        heads_backward_kernel<NV><<<grid, kThreads, kSmemBytes, stream>>>(P);                                          \
+                                        (int)(kSmemBytes + kDgExtraBytes)));                                           \
+        heads_backward_kernel<NV><<<grid, kThreads, kSmemBytes + kDgExtraBytes, stream>>>(P);                          \
         break;                                                                                                         \
     }
     switch (P.app.comps / 16) {

@@ -113,6 +113,8 @@ class _PackedMlp:
         self.w_dgrad: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.w_tc: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.w_tc16: List[Optional[torch.Tensor]] = [None] * len(self.linears)
+        self.w_t: List[Optional[torch.Tensor]] = [None] * len(self.linears)        # fp32 W^T, source of w_dg16
+        self.w_dg16: List[Optional[torch.Tensor]] = [None] * len(self.linears)     # fp16-split operand of the data gradient
         self.g_wt: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.g_bias: List[Optional[torch.Tensor]] = [None] * len(self.linears)
 
@@ -131,6 +133,9 @@ class _PackedMlp:
                 if self.w_dgrad[i] is None:
                     self.w_dgrad[i] = torch.zeros((L.k_pad(l.out_features), L.dgrad_pad(l.in_features)), device=self.wt[i].device)
                 batch.dgrad(l.weight.data, self.w_dgrad[i], l.out_features, l.in_features)
+                if self.w_t[i] is None:
+                    self.w_t[i] = torch.empty((l.in_features, l.out_features), device=self.wt[i].device)
+                batch.transpose(l.weight.data, self.w_t[i], l.out_features, l.in_features)
 
     def pack(self, lib, stream, training: bool, in_bound_ptr: Optional[int] = None, in_bound_floor: float = 1.0,
              tc16: Optional["L.Tc16Batch"] = None, chain: int = 0):
@@ -163,6 +168,18 @@ class _PackedMlp:
                 bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
                 self.w_tc16[i] = None
 
+    def pack_dgrad16(self, lib, tc16: "L.Tc16Batch", chain: int):
+        """Queue the tensor-core data-gradient operands: clift_pack_linear_tc16 of W^T (no bias; the operand scale of dZ is
+        chosen per tile inside the backward kernel, so no bound chain - floor 1)."""
+        for i, l in enumerate(self.linears):
+            nb = lib.clift_tc16_weight_bytes(l.in_features, l.out_features, 0)
+            if nb <= 0 or self.w_t[i] is None:
+                self.w_dg16[i] = None
+                continue
+            if self.w_dg16[i] is None:
+                self.w_dg16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
+            tc16.add(self.w_t[i], None, self.w_dg16[i], l.in_features, l.out_features, None, 1.0, chain)
+
     def fill(self, m: L.Mlp):
         m.n_layers = len(self.linears)
         for i, d in enumerate(self.dims):
@@ -173,6 +190,7 @@ class _PackedMlp:
             m.w_dgrad[i] = L.ptr(self.w_dgrad[i])
             m.w_tc[i] = L.ptr(self.w_tc[i])
             m.w_tc16[i] = L.ptr(self.w_tc16[i])
+            m.w_dg16[i] = L.ptr(self.w_dg16[i])
 
     def grad_buffers(self, g: L.MlpGrad, want: bool, to_zero: Optional[List[torch.Tensor]] = None):
         """``to_zero``: list the caller clears with one multi-tensor launch (else each buffer is cleared here)."""
@@ -579,6 +597,10 @@ class PackedField:
             if m is not None:
                 # a grid-mode head's stack stays off the fp16-split operand chain (bound pointer -1): it runs on the FMA kernels
                 m.pack(lib, st, training, -1 if name in self.grid_basis else None, 1.0, tc16, chain)
+        if training:      # tensor-core data-gradient operands (W^T), one planning chain per stack
+            for chain, m in enumerate((self.basis, self.rgb, self.sem, self.insf, self.inss), start=4):
+                if m is not None:
+                    m.pack_dgrad16(lib, tc16, chain)
         tc16.run(lib, self.device)
         f = self.field
         for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
@@ -591,6 +613,7 @@ class PackedField:
         f.basis_dgrad = L.ptr(self.basis.w_dgrad[0])
         f.basis_tc = L.ptr(self.basis.w_tc[0])
         f.basis_tc16 = L.ptr(self.basis.w_tc16[0])
+        f.basis_dg16 = L.ptr(self.basis.w_dg16[0])
         self.rgb.fill(f.rgb)
         self.sem.fill(f.semantic)
         if self.insf is not None:

@@ -25,7 +25,7 @@ _vp = C.c_void_p
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)),
                 ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS), ("w_tc", _vp * MAX_LAYERS),
-                ("w_tc16", _vp * MAX_LAYERS)]
+                ("w_tc16", _vp * MAX_LAYERS), ("w_dg16", _vp * MAX_LAYERS)]
 
 
 class MlpGrad(C.Structure):
@@ -48,7 +48,7 @@ class Field(C.Structure):
                 ("dim_instance", C.c_int32), ("slow_fast", C.c_int32), ("density_shift", C.c_float),
                 ("density_plane", _vp * 3), ("density_line", _vp * 3),
                 ("appearance_plane", _vp * 3), ("appearance_line", _vp * 3), ("basis", _vp), ("basis_dgrad", _vp), ("basis_tc", _vp),
-                ("basis_tc16", _vp),
+                ("basis_tc16", _vp), ("basis_dg16", _vp),
                 ("rgb", Mlp), ("semantic", Mlp), ("instance_fast", Mlp), ("instance_slow", Mlp),
                 ("semantic_grid", GridHead), ("instance_grid", GridHead)]
 
@@ -264,6 +264,10 @@ class PackBatch:
 
     def dgrad(self, w, w_dgrad, n_out, n_in):
         self._add(w, w_dgrad, n_in, n_out, n_in, k_pad(n_out), dgrad_pad(n_in), 1)
+
+    def transpose(self, w, w_t, n_out, n_in):
+        """w [n_out][n_in] -> w_t [n_in][n_out] (the source of the tensor-core data-gradient operand)."""
+        self._add(w, w_t, n_in, n_out, n_in, n_in, n_out, 0)
 
     def run(self, lib, device):
         if not self.jobs:

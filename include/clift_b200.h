@@ -55,6 +55,10 @@ typedef struct {
     const float* w_tc[CLIFT_MAX_LAYERS];
     /* fp16-split tensor-core operand written by clift_pack_linear_tc16() (null = not available) */
     const void* w_tc16[CLIFT_MAX_LAYERS];
+    /* data-gradient operand for the tensor-core training backward: clift_pack_linear_tc16() of W^T ([in][out] row-major,
+     * no bias), i.e. the B operand of dA[m][i] = sum_o dZ[m][o] W[o][i] (null = that layer's data gradient runs on FP32 FMA
+     * from w_dgrad) */
+    const void* w_dg16[CLIFT_MAX_LAYERS];
 } clift_mlp;
 
 /* Gradient mirror of clift_mlp (same packed shapes); null pointers = do not accumulate. */
@@ -104,6 +108,7 @@ typedef struct {
     const float* basis_dgrad;        /* ... and in clift_pack_linear_dgrad() layout (training only, else null) */
     const float* basis_tc;           /* ... and in clift_pack_linear_tc() layout (tensor-core heads, else null) */
     const void* basis_tc16;          /* ... and in clift_pack_linear_tc16() layout (fp16-split tensor-core heads, else null) */
+    const void* basis_dg16;          /* ... and its transpose in clift_pack_linear_tc16() layout (tensor-core data gradient) */
     clift_mlp rgb;                   /* render_appearance_mlp.mlp       (H1) */
     clift_mlp semantic;              /* render_semantic_mlp.mlp         (H2) */
     clift_mlp instance_fast;         /* render_instance_mlp.mlp         (H3) */
