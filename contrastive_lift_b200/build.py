@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libclift_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "march.cu", "heads.cu", "heads_tc.cu", "heads_tc16.cu", "wgrad_tc.cu", "backward.cu", "pack.cu", "rays.cu", "loss.cu", "epoch.cu"]
+SOURCES = ["api.cu", "march.cu", "heads.cu", "heads_tc.cu", "heads_tc16.cu", "heads_x16.cu", "wgrad_tc.cu", "backward.cu", "pack.cu", "rays.cu", "loss.cu", "epoch.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -256,7 +256,12 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
             else if (heads_tc_available(field, heads))
                 path = CLIFT_HEADS_TENSOR;
         }
-        if (path == CLIFT_HEADS_TENSOR16)
+        const int xyz_heads = heads & (CLIFT_HEAD_SEMANTIC | CLIFT_HEAD_INSTANCE);
+        if (path == CLIFT_HEADS_TENSOR16 && !save && xyz_heads && heads_x16_available(field, xyz_heads)) {
+            // inference: the xyz stacks on the pipelined kernel, the rgb stack (gather, basis, encoding) on the serial one
+            rc = launch_heads_forward_x16(cfg, field, ws, max_active, n_rays, o_sem, o_ins, stream);
+            if (!rc && o_rgb) rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, nullptr, nullptr, stream, nullptr);
+        } else if (path == CLIFT_HEADS_TENSOR16)
             rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream, save ? &lay : nullptr);
         else if (path == CLIFT_HEADS_TENSOR)
             rc = launch_heads_forward_tc(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream);

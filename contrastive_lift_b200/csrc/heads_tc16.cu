@@ -785,15 +785,21 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         const uint32_t park = r.lane_base + kParkCol + (uint32_t)(r.part * 16 * NV);
         int park_next = 2 * NV;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ray_next = -1;
         float* st = nullptr;                                   // training: this tile's A-stash
         auto st_block = [&](int id, int l) -> float* {
             if (!kStash) return nullptr;
             return st + (size_t)P.lay.a_off[id][l] * kRows;
         };
-        auto park_slice = [&]() {
-            gather_slice(P.app, r.part, p, park_next, s.sc[g_basis].x, park, st_block(4, 0), row);
+        auto park_slice = [&](const float4& pp) {
+            gather_slice(P.app, r.part, pp, park_next, s.sc[g_basis].x, park, st_block(4, 0), row);
             ++park_next;
         };
+        // rgb stack alone (the xyz stacks run on heads_x16.cu): there is no long MMA phase of this tile to hide the gather
+        // under, so the slices of the NEXT tile's records are gathered under this tile's four GEMMs and wait in the parked
+        // columns across the tile boundary (the first tile of a CTA gathers in one burst)
+        const bool prefetch = !kStash && P.park && P.n_sem == 0 && P.n_ins == 0 && P.n_rgb > 0;
         auto stash_xyz = [&](int id) {                         // layer-0 input of an xyz stack (pe = 0): 16 rows, 3 valid
             if (kStash && r.part == 0) {
                 float* b = st_block(id, 0);
@@ -809,12 +815,11 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a, st_block(id, l + 1),
                                 P.g[gi].n_pad, s.sc[gi].y);
                 if (threadIdx.x == 64) stamp(P, tl, gi + 1, 1);
-                if (park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice();   // hides under that GEMM
+                if (!prefetch && park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice(p);   // hides under that GEMM
+                if (prefetch && park_next < 2 * NV) park_slice(p_next);
             }
             wait_d();   // final layer: the caller reads D, then advances gi
         };
-        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ray_next = -1;
         auto fetch = [&](int tile) {
             p_next = make_float4(0.f, 0.f, 0.f, 0.f);
             ray_next = -1;
@@ -833,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             const int ray = ray_next;
             fetch(tile + tile_step);
             if (kStash) st = P.stash_a + (size_t)tile * P.lay.a_rows * kRows;
-            park_next = (P.park && P.n_rgb > 0) ? 0 : 2 * NV;
+            if (!(prefetch && tl > 0)) park_next = (P.park && P.n_rgb > 0) ? 0 : 2 * NV;   // prefetch: slices parked so far stay
             if (r.part == 0) {
                 s.ray[row] = ray;
                 s.pos[row] = p;
@@ -903,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 if (P.park) {
                     // the products were gathered slice by slice under the xyz stacks' MMAs (leftover slices now) and wait in
                     // tensor memory as chunk images: copy them into the operand rows
-                    while (park_next < 2 * NV) park_slice();
+                    while (park_next < 2 * NV) park_slice(p);
                     tc::tmem_wait_st();
 #pragma unroll
                     for (int j = 0; j < NV; ++j) {
@@ -916,6 +921,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                         *reinterpret_cast<uint4*>(s.a_hi + off + kRows * 16) = make_uint4(v[8], v[9], v[10], v[11]);
                         *reinterpret_cast<uint4*>(s.a_lo + off + kRows * 16) = make_uint4(v[12], v[13], v[14], v[15]);
                     }
+                    if (prefetch) park_next = tile_key + tile_step < n_tiles ? 0 : 2 * NV;   // the parked columns are free again
                 } else {
                     // appearance gather in quad layout (4 lanes x float4 = one 64-byte texel segment per tap, fully
                     // coalesced): scaled plane*line products go straight into the operand rows as fp16 pairs.  One
@@ -928,6 +934,10 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                     }
                 }
                 publish(gi);
+                if (prefetch) {
+                    if (park_next < 2 * NV) park_slice(p_next);
+                    if (park_next < 2 * NV) park_slice(p_next);
+                }
                 wait_d();   // basis GEMM: features in D columns [0, dim_app)
                 const int A = P.dim_app, pf = P.pe_feat, pv = P.pe_view;
                 const int n_base = A + 3;

@@ -115,6 +115,7 @@ class _PackedMlp:
         self.w_tc16: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.w_t: List[Optional[torch.Tensor]] = [None] * len(self.linears)        # fp32 W^T, source of w_dg16
         self.w_dg16: List[Optional[torch.Tensor]] = [None] * len(self.linears)     # fp16-split operand of the data gradient
+        self.w_x16: List[Optional[torch.Tensor]] = [None] * len(self.linears)      # pipelined-kernel stages of 256-wide layers
         self.g_wt: List[Optional[torch.Tensor]] = [None] * len(self.linears)
         self.g_bias: List[Optional[torch.Tensor]] = [None] * len(self.linears)
 
@@ -168,6 +169,19 @@ class _PackedMlp:
                 bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
                 self.w_tc16[i] = None
 
+    def pack_x16(self, lib, stream):
+        """Stages of the pipelined xyz-stack kernel (inference): re-layout of the fp16-split operands just packed."""
+        for i, l in enumerate(self.linears):
+            has_bias = 1 if l.bias is not None else 0
+            nb = lib.clift_x16_weight_bytes(l.out_features, l.in_features, has_bias)
+            if nb <= 0 or self.w_tc16[i] is None or i + 1 == len(self.linears):
+                self.w_x16[i] = None
+                continue
+            if self.w_x16[i] is None:
+                self.w_x16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
+            L.check(lib.clift_pack_linear_x16(L.ptr(self.w_tc16[i]), L.ptr(self.w_x16[i]), l.out_features, l.in_features,
+                                              has_bias, stream))
+
     def pack_dgrad16(self, lib, tc16: "L.Tc16Batch", chain: int):
         """Queue the tensor-core data-gradient operands: clift_pack_linear_tc16 of W^T (no bias; the operand scale of dZ is
         chosen per tile inside the backward kernel, so no bound chain - floor 1)."""
@@ -191,6 +205,7 @@ class _PackedMlp:
             m.w_tc[i] = L.ptr(self.w_tc[i])
             m.w_tc16[i] = L.ptr(self.w_tc16[i])
             m.w_dg16[i] = L.ptr(self.w_dg16[i])
+            m.w_x16[i] = L.ptr(self.w_x16[i])
 
     def grad_buffers(self, g: L.MlpGrad, want: bool, to_zero: Optional[List[torch.Tensor]] = None):
         """``to_zero``: list the caller clears with one multi-tensor launch (else each buffer is cleared here)."""
@@ -602,6 +617,10 @@ class PackedField:
                 if m is not None:
                     m.pack_dgrad16(lib, tc16, chain)
         tc16.run(lib, self.device)
+        if not training:   # inference: stages of the pipelined kernel for the xyz stacks (MLP-mode heads)
+            for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
+                if m is not None and name not in self.grid_basis:
+                    m.pack_x16(lib, st)
         f = self.field
         for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
             if name in self.grid_basis:

@@ -25,7 +25,8 @@ _vp = C.c_void_p
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("dims", C.c_int32 * (MAX_LAYERS + 1)),
                 ("wt", _vp * MAX_LAYERS), ("bias", _vp * MAX_LAYERS), ("w_dgrad", _vp * MAX_LAYERS), ("w_tc", _vp * MAX_LAYERS),
-                ("w_tc16", _vp * MAX_LAYERS), ("w_dg16", _vp * MAX_LAYERS)]
+                ("w_tc16", _vp * MAX_LAYERS), ("w_dg16", _vp * MAX_LAYERS),
+                ("w_x16", _vp * MAX_LAYERS)]
 
 
 class MlpGrad(C.Structure):
@@ -112,6 +113,8 @@ SIGNATURES = {
     "clift_pack_linear_dgrad": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_tc_weight_floats": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "clift_pack_linear_tc": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "clift_x16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "clift_pack_linear_x16": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_debug_tc_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_tc16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "clift_pack_linear_tc16": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_float, _vp]),

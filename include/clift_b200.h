@@ -59,6 +59,9 @@ typedef struct {
      * no bias), i.e. the B operand of dA[m][i] = sum_o dZ[m][o] W[o][i] (null = that layer's data gradient runs on FP32 FMA
      * from w_dgrad) */
     const void* w_dg16[CLIFT_MAX_LAYERS];
+    /* clift_pack_linear_x16() re-layout of w_tc16 for the pipelined inference kernel of the xyz stacks (256-wide layers: one
+     * 8 KB stage per k-step and N-half; null = the layer is not 256 wide or the stack runs on the serial kernel) */
+    const void* w_x16[CLIFT_MAX_LAYERS];
 } clift_mlp;
 
 /* Gradient mirror of clift_mlp (same packed shapes); null pointers = do not accumulate. */
@@ -224,6 +227,11 @@ int32_t clift_pack_batch(const clift_pack_job* jobs, int32_t n_jobs, int32_t tot
  * clift_tc_weight_floats() sizes the buffer. */
 int64_t clift_tc_weight_floats(int32_t n_out, int32_t n_in, int32_t has_bias);
 int32_t clift_pack_linear_tc(const float* w, const float* bias, float* dst, int32_t n_out, int32_t n_in, void* stream);
+/* Pipelined xyz-stack kernel (heads_x16.cu): the fp16-split operand of a 256-wide layer re-ordered from
+ * clift_pack_linear_tc16()'s k-step slabs into one 8 KB stage per (N-half, k-step): [W_hi: 2 k-chunks x 128 rows x 16 B | W_lo],
+ * half 0's stages first, the bias step last in each half.  clift_x16_weight_bytes() sizes dst (< 0: layer not eligible). */
+int64_t clift_x16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias);
+int32_t clift_pack_linear_x16(const void* w_tc16, void* dst, int32_t n_out, int32_t n_in, int32_t has_bias, void* stream);
 /* Bring-up / parity entry for the tensor-core GEMM core: out[128][round_up(n_out,32)] = a[128][k] * W^T (+ bias) with
  * the 3xTF32 split (one CTA).  Used by tests only. */
 int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, int32_t has_bias,

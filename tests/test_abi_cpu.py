@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header_layout():
     import ctypes as C
-    assert C.sizeof(L.Mlp) == 4 + 4 * 9 + 8 * 8 * 6
+    assert C.sizeof(L.Mlp) == 4 + 4 * 9 + 8 * 8 * 7
     assert C.sizeof(L.RenderCfg) == 4 * 9 + 4 * 7
     assert C.sizeof(L.RenderOut) == 8 * 11 + 8
 
