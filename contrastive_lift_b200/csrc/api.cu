@@ -32,8 +32,9 @@ int sm_count() {     // of the CURRENT device (callers run under a device guard)
 }
 
 static bool g_profile = false;
-static cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+static cudaEvent_t g_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5]: between the two head kernels
 static bool g_ev_valid = false;
+static bool g_ev_split = false;
 
 static void profile_mark(int i, cudaStream_t stream) {
     if (g_profile && g_ev[i]) cudaEventRecord(g_ev[i], stream);
@@ -204,6 +205,7 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
     if (out->dist_reg) CLIFT_CHECK_ARG(out->dist_ray, "dist_ray is required when dist_reg is requested");
 
     CLIFT_CUDA(cudaMemsetAsync(ws.stats, 0, 16 * sizeof(int32_t), stream));
+    g_ev_split = false;
     MarchParams M;
     M.g = make_geom(cfg);
     M.f = make_factors(field, false);
@@ -260,6 +262,8 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         if (path == CLIFT_HEADS_TENSOR16 && !save && xyz_heads && heads_x16_available(field, xyz_heads)) {
             // inference: the xyz stacks on the pipelined kernel, the rgb stack (gather, basis, encoding) on the serial one
             rc = launch_heads_forward_x16(cfg, field, ws, max_active, n_rays, o_sem, o_ins, stream);
+            profile_mark(5, stream);
+            g_ev_split = g_profile;
             if (!rc && o_rgb) rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, nullptr, nullptr, stream, nullptr);
         } else if (path == CLIFT_HEADS_TENSOR16)
             rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream, save ? &lay : nullptr);
@@ -283,7 +287,7 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
 
 extern "C" int32_t clift_profile_enable(int32_t on) {
     if (on && !g_ev[0])
-        for (int i = 0; i < 5; ++i) CLIFT_CUDA(cudaEventCreate(&g_ev[i]));
+        for (int i = 0; i < 6; ++i) CLIFT_CUDA(cudaEventCreate(&g_ev[i]));
     g_profile = on != 0;
     g_ev_valid = false;
     return CLIFT_OK;
@@ -294,6 +298,17 @@ extern "C" int32_t clift_profile_stage_ms(float* ms4) {
     CLIFT_CHECK_ARG(g_ev_valid, "no profiled clift_render_forward since clift_profile_enable(1)");
     CLIFT_CUDA(cudaEventSynchronize(g_ev[4]));
     for (int i = 0; i < 4; ++i) CLIFT_CUDA(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_profile_heads_split_ms(float* ms2) {
+    CLIFT_CHECK_ARG(ms2 != nullptr, "null pointer");
+    CLIFT_CHECK_ARG(g_ev_valid, "no profiled clift_render_forward since clift_profile_enable(1)");
+    ms2[0] = ms2[1] = 0.0f;
+    if (!g_ev_split) return CLIFT_OK;          // one head kernel ran: no split
+    CLIFT_CUDA(cudaEventSynchronize(g_ev[4]));
+    CLIFT_CUDA(cudaEventElapsedTime(&ms2[0], g_ev[2], g_ev[5]));
+    CLIFT_CUDA(cudaEventElapsedTime(&ms2[1], g_ev[5], g_ev[3]));
     return CLIFT_OK;
 }
 

@@ -104,6 +104,7 @@ SIGNATURES = {
     "clift_launch_count": (C.c_int64, []),
     "clift_profile_enable": (C.c_int32, [C.c_int32]),
     "clift_profile_stage_ms": (C.c_int32, [_fp]),
+    "clift_profile_heads_split_ms": (C.c_int32, [_fp]),
     "clift_pack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_pack_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "clift_pack_linear_tc16_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]),

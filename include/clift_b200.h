@@ -188,6 +188,9 @@ int64_t clift_launch_count(void);
  * Off by default (no events, no synchronisation).  Not thread-safe: one profiled stream at a time. */
 int32_t clift_profile_enable(int32_t on);
 int32_t clift_profile_stage_ms(float* ms4);
+/* When the last profiled forward ran the heads as two kernels (pipelined xyz-stack kernel + rgb-stack kernel, the inference
+ * default): their device times {xyz, rgb} in ms; {0, 0} when one kernel evaluated all heads. */
+int32_t clift_profile_heads_split_ms(float* ms2);
 
 /* ---- layout packing (one transpose kernel; used for parameters and, inverted, for gradients) --- */
 /* (1,C,H,W) -> [H][W][C]  and back.   tensoRF.py:99-106 layouts. */
