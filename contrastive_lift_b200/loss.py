@@ -114,6 +114,60 @@ class _PlaneTV(torch.autograd.Function):
         return g * gout
 
 
+class _TotalTV(torch.autograd.Function):
+    """sum_i coef_i * TV(plane_i) over any number of (1,C,H,W) factor planes / (1,C,L,1) lines with a handful of launches:
+    one batched layout job in, one value + one gradient launch per plane (the gradient already scaled by coef_i), one
+    batched layout job out; backward is one multi-tensor scale by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, coefs, *planes):
+        lib = L.load()
+        dev = planes[0].device
+        with L.on(dev):
+            st = L.stream_ptr(dev)
+            srcs = [p.detach().contiguous() for p in planes]               # bound until the launches are enqueued
+            sizes = [p.numel() for p in srcs]
+            flat = torch.empty((sum(sizes),), device=dev)                   # packed copies (channel-last)
+            g_flat = torch.zeros((sum(sizes),), device=dev)                 # their gradients
+            hwc, g_hwc, off = [], [], 0
+            batch = L.PackBatch()
+            for p, n in zip(srcs, sizes):
+                _, c, h, w = p.shape
+                hwc.append(flat[off:off + n].view(h, w, c))
+                g_hwc.append(g_flat[off:off + n].view(h, w, c))
+                batch.plane(p, hwc[-1], c, h, w)
+                off += n
+            batch.run(lib, dev)
+            vals = torch.empty((len(srcs),), device=dev)
+            for i, (p, coef) in enumerate(zip(srcs, coefs)):
+                _, c, h, w = p.shape
+                L.check(lib.clift_tv_loss(L.ptr(hwc[i]), c, h, w, vals.data_ptr() + 4 * i, L.ptr(g_hwc[i]), float(coef), st))
+            grads = [torch.empty_like(p) for p in srcs]
+            batch = L.PackBatch()
+            for p, g, gh in zip(srcs, grads, g_hwc):
+                _, c, h, w = p.shape
+                batch.unplane(gh, g, c, h, w)
+            batch.run(lib, dev)
+            total = (vals * torch.tensor([float(c) for c in coefs], device=dev)).sum()
+        ctx.grads = grads
+        return total
+
+    @staticmethod
+    def backward(ctx, gout):
+        grads = ctx.grads
+        ctx.grads = None
+        return (None,) + tuple(torch._foreach_mul(grads, gout))
+
+
+def total_tv(planes_and_coefs) -> torch.Tensor:
+    """sum of coef * TVLoss(plane) over [(plane, coef), ...] (the terms of tensoRF.py:248-290 in one autograd node)."""
+    planes = [p for p, _ in planes_and_coefs]
+    for p in planes:
+        if p.dim() != 4 or p.shape[0] != 1:
+            raise L.CliftError("total_tv expects (1,C,H,W) factor planes / (1,C,L,1) lines")
+    return _TotalTV.apply([c for _, c in planes_and_coefs], *planes)
+
+
 def plane_tv(plane: torch.Tensor) -> torch.Tensor:
     """TVLoss.forward (loss.py:13-22) of one (1,C,H,W) plane."""
     if plane.shape[0] != 1:

@@ -265,32 +265,45 @@ def test_models_survive_deepcopy_and_pickle_with_a_live_packed_view():
 
 
 def test_packed_view_cache_validation_handles_inference_tensors():
-    """PackedField.refresh trusts its packed copy only while every parameter's version counter is unchanged.  Parameters
-    created under torch.inference_mode() keep no counter: the cache is then never trusted (repack on every call) instead of
-    raising 'Inference tensors do not track version counter'."""
+    """PackedField.refresh trusts its packed copy only while every parameter's version counter AND storage address and the
+    library's parameter epoch are unchanged, separately for training packings (data-gradient operands) and inference packings.
+    Parameters created under torch.inference_mode() keep no counter: the cache is then never trusted (repack on every call)
+    instead of raising 'Inference tensors do not track version counter'."""
     from contrastive_lift_b200 import field as F
     normal = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.ones(2))]
     with torch.inference_mode():
         frozen = [torch.nn.Parameter(torch.zeros(3))]
     assert F._param_version(normal[0]) == 0 and F._param_version(frozen[0]) is None
 
-    def stub(params):
+    def key(params):
+        return tuple(F._param_version(p) for p in params) + tuple(p.data_ptr() for p in params) + (L.param_epoch(),)
+
+    def stub(params, train=False, infer=True):
         pk = object.__new__(F.PackedField)          # no device work: only the cache check at the top of refresh() runs
         pk.model_params, pk.tc_stale = params, False
-        pk.versions = tuple(F._param_version(p) for p in params) + (L.param_epoch(),)
+        pk.has_train, pk.has_infer = train, infer
+        pk.versions = key(params)
         return pk
 
     assert stub(normal).refresh(False) is None      # valid cache: returns before touching the library
+    assert stub(normal, train=True).refresh(True) is None      # the chunk renders of one training step share a packing
+    with pytest.raises(AttributeError):             # an inference packing does not carry the training operands
+        stub(normal, train=False).refresh(True)     # (falls through to the repack: this stub has no library handle)
+    pk = stub(normal)
     with torch.no_grad():
         normal[1].add_(1.0)                         # a version moved: the early return must not happen
-    pk = stub(normal)
-    pk.versions = (0, 0, L.param_epoch())
-    with pytest.raises(AttributeError):             # falls through to the repack (this stub has no library handle)
+    with pytest.raises(AttributeError):
         pk.refresh(False)
-    with pytest.raises(AttributeError):             # inference tensors: never trusted, even with an "equal" version tuple
+    pk = stub(normal)
+    normal[0].data = torch.ones(3)                  # the reference's EMA: storage replaced, version counter untouched
+    with pytest.raises(AttributeError):
+        pk.refresh(False)
+    pk = stub(normal)
+    L.bump_param_epoch()                            # ema_update / FusedAdam: raw-pointer writes
+    with pytest.raises(AttributeError):
+        pk.refresh(False)
+    with pytest.raises(AttributeError):             # inference tensors: never trusted, even with an "equal" key
         stub(frozen).refresh(False)
-    with pytest.raises(AttributeError):             # training renders always repack
-        stub([torch.nn.Parameter(torch.zeros(1))]).refresh(True)
 
 
 def test_renderer_built_under_inference_mode_still_describes_itself():
