@@ -169,7 +169,16 @@ extern "C" int64_t clift_render_workspace_bytes(const clift_render_cfg* cfg, con
     if (!cfg || !field || n_rays < 0) return CLIFT_ERR_ARG;
     if (max_active <= 0) max_active = n_rays * cfg->n_samples;
     const StashLayout lay = make_stash_layout(field, cfg->heads);
-    return carve_workspace(nullptr, n_rays, cfg->n_samples, max_active, out_width(field), save_for_backward != 0, &lay).bytes;
+    return carve_workspace(nullptr, n_rays, cfg->n_samples, max_active, out_width(field), save_for_backward != 0, &lay,
+                           save_for_backward != 2).bytes;
+}
+
+extern "C" int64_t clift_render_stash_z_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays,
+                                              int64_t max_active) {
+    if (!cfg || !field || n_rays < 0) return CLIFT_ERR_ARG;
+    if (max_active <= 0) max_active = n_rays * cfg->n_samples;
+    const StashLayout lay = make_stash_layout(field, cfg->heads);
+    return round_up(ceil_div(max_active, CLIFT_TILE) * (int64_t)lay.z_rows * CLIFT_TILE * (int64_t)sizeof(float), 256);
 }
 
 extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
@@ -191,7 +200,8 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
     const int C = field->num_classes, DI = field->dim_instance * (field->slow_fast ? 2 : 1);
     const bool save = out->save_for_backward != 0;
     const StashLayout lay = make_stash_layout(field, cfg->heads);
-    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, out_width(field), save, &lay);
+    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, out_width(field), save, &lay,
+                                   out->save_for_backward != 2);
     if (ws.bytes > workspace_bytes) {
         set_error("clift_render_forward: workspace %lld bytes < required %lld", (long long)workspace_bytes, (long long)ws.bytes);
         return CLIFT_ERR_WORKSPACE;

@@ -22,7 +22,10 @@ extern "C" int32_t clift_render_backward(const clift_render_cfg* cfg, const clif
     if (max_active <= 0) max_active = n_rays * cfg->n_samples;
     const int C = field->num_classes, DI = field->dim_instance * (field->slow_fast ? 2 : 1);
     const StashLayout lay = make_stash_layout(field, heads);
-    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, 3 + C + DI, true, &lay);
+    const bool z_external = saved->save_for_backward == 2;
+    if (z_external) CLIFT_CHECK_ARG(saved->stash_z != nullptr, "saved->stash_z is required after a save_for_backward = 2 forward");
+    Workspace ws = carve_workspace(workspace, n_rays, cfg->n_samples, max_active, 3 + C + DI, true, &lay, !z_external);
+    if (z_external) ws.stash_z = saved->stash_z;
     if (ws.bytes > workspace_bytes) {
         set_error("clift_render_backward: workspace %lld bytes < required %lld", (long long)workspace_bytes, (long long)ws.bytes);
         return CLIFT_ERR_WORKSPACE;

@@ -167,8 +167,10 @@ struct Workspace {
 
 static const int kScanBlock = 2048;
 
+// `with_z`: the dL/dZ stash lives inside the workspace (save_for_backward = 1); false: the caller supplies it at backward
+// time (save_for_backward = 2), so forwards that wait for their backward hold only the activation stash
 inline Workspace carve_workspace(void* base, int64_t n_rays, int n_samples, int64_t cap, int out_width, bool save,
-                                 const StashLayout* layout) {
+                                 const StashLayout* layout, bool with_z = true) {
     Workspace w;
     memset(&w, 0, sizeof(w));
     char* p = (char*)base;
@@ -194,7 +196,7 @@ inline Workspace carve_workspace(void* base, int64_t n_rays, int n_samples, int6
         w.g_w = (float*)take(n_rays * n_samples * sizeof(float));
         w.g_ray = (float*)take(n_rays * (int64_t)(out_width + 2) * sizeof(float));
         w.stash_a = (float*)take(tiles * (int64_t)layout->a_rows * CLIFT_TILE * sizeof(float));
-        w.stash_z = (float*)take(tiles * (int64_t)layout->z_rows * CLIFT_TILE * sizeof(float));
+        if (with_z) w.stash_z = (float*)take(tiles * (int64_t)layout->z_rows * CLIFT_TILE * sizeof(float));
     }
     w.bytes = off;
     return w;

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -71,7 +71,7 @@ class RenderCfg(C.Structure):
 class RenderOut(C.Structure):
     _fields_ = [("rgb", _vp), ("semantic", _vp), ("instance", _vp), ("depth", _vp), ("opacity", _vp),
                 ("dist_reg", _vp), ("rgb_raw", _vp), ("semantic_raw", _vp), ("dist_ray", _vp),
-                ("points", _vp), ("weights", _vp), ("save_for_backward", C.c_int32)]
+                ("points", _vp), ("weights", _vp), ("save_for_backward", C.c_int32), ("stash_z", _vp)]
 
 
 class PackJob(C.Structure):
@@ -127,6 +127,7 @@ SIGNATURES = {
     "clift_density": (C.c_int32, [C.POINTER(Field), _vp, C.c_int64, _vp, _vp]),
     "clift_render_workspace_bytes": (C.c_int64, [C.POINTER(RenderCfg), C.POINTER(Field), C.c_int64, C.c_int64,
                                                        C.c_int32]),
+    "clift_render_stash_z_bytes": (C.c_int64, [C.POINTER(RenderCfg), C.POINTER(Field), C.c_int64, C.c_int64]),
     "clift_render_forward": (C.c_int32, [C.POINTER(RenderCfg), C.POINTER(Field), _vp, _vp, C.c_int64, C.c_int32,
                                          _vp, C.c_int64, C.c_int64, C.POINTER(RenderOut), _vp]),
     "clift_render_stats": (C.c_int32, [_vp, _vp, _vp]),

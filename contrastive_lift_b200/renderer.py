@@ -69,7 +69,7 @@ class _Render(torch.autograd.Function):
             t["points"] = new(B, 3)
         for k, v in t.items():
             setattr(out, k, L.ptr(v))
-        out.save_for_backward = 1 if need_grad else 0
+        out.save_for_backward = 2 if need_grad else 0      # 2: the backward's dL/dZ stash is allocated at backward time
         cap = renderer.max_active(B, need_grad)
         while True:
             nbytes = lib.clift_render_workspace_bytes(C.byref(cfg), C.byref(pk.field), B, cap, out.save_for_backward)
@@ -131,8 +131,15 @@ class _Render(torch.autograd.Function):
         saved = L.RenderOut()
         for k, v in ctx.t.items():
             setattr(saved, k, L.ptr(v))
-        saved.save_for_backward = 1
+        saved.save_for_backward = 2
         B = ctx.rays.shape[0]
+        # dL/dZ stash: scratch of this backward only (backwards of a step run one after the other, so the chunks of a
+        # step share one such buffer through the caching allocator instead of each forward holding its own)
+        zbytes = lib.clift_render_stash_z_bytes(C.byref(ctx.cfg), C.byref(pk.field), B, ctx.cap)
+        if zbytes < 0:
+            L.check(int(zbytes))
+        stash_z = torch.empty((int(zbytes),), dtype=torch.uint8, device=dev)
+        saved.stash_z = L.ptr(stash_z)
         L.check(lib.clift_render_backward(C.byref(ctx.cfg), C.byref(pk.field), L.ptr(ctx.rays), L.ptr(ctx.jitter), B,
                                           int(ctx.add_bg), L.ptr(ctx.ws), ctx.ws.numel(), ctx.cap,
                                           C.byref(saved), L.ptr(g_rgb), L.ptr(g_sem), L.ptr(g_ins), L.ptr(g_dist),
@@ -266,13 +273,13 @@ class TensoRFRenderer(nn.Module):
 
     def max_active(self, n_rays: int, training: bool = False) -> int:
         """<= 0 means worst case (every sample active) to the C ABI.  Training forwards size their activation stash
-        by this capacity, so they follow the measured active count of the previous call (x1.5) instead of the
+        by this capacity, so they follow the measured active count of the previous call (x1.25) instead of the
         static per-ray bound; an overflow still repeats the call at the exact size."""
         if self.max_active_per_ray <= 0:
             return 0
         per_ray = min(int(self.max_active_per_ray), int(self.n_samples))
         if training and self.check_overflow and self._active_per_ray is not None:
-            per_ray = min(per_ray, int(self._active_per_ray * 1.5) + 8)
+            per_ray = min(per_ray, int(self._active_per_ray * 1.25) + 8)
         return max(128, int(n_rays) * per_ray)
 
     @staticmethod

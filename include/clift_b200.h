@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 10
+#define CLIFT_ABI_VERSION 11
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -171,7 +171,11 @@ typedef struct {
     float* dist_ray;     /* [B]     per-ray distortion loss */
     float* points;       /* [B,3]   o + depth*d (forward_instance_feature, renderer:211-213) */
     float* weights;      /* [B,S]   dense compositing weights w_i (parity tests); null = keep in workspace */
-    int32_t save_for_backward; /* 1: keep what clift_render_backward needs in the workspace */
+    int32_t save_for_backward; /* 1: keep what clift_render_backward needs in the workspace; 2: the same, except that the
+                                  dL/dZ stash of the backward is NOT part of the workspace - the caller passes it to
+                                  clift_render_backward in `stash_z` (clift_render_stash_z_bytes), so a forward that waits
+                                  for its backward (several chunks per step) holds only its activation stash */
+    float* stash_z;            /* clift_render_backward with save_for_backward = 2: scratch of clift_render_stash_z_bytes() */
 } clift_render_out;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -305,6 +309,7 @@ int32_t clift_density(const clift_field* field, const float* xyz, int64_t n, flo
  *  handles n_rays*n_samples < 2^31 - callers split larger frames.                                */
 int64_t clift_render_workspace_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays,
                                      int64_t max_active, int32_t save_for_backward);
+int64_t clift_render_stash_z_bytes(const clift_render_cfg* cfg, const clift_field* field, int64_t n_rays, int64_t max_active);
 int32_t clift_render_forward(const clift_render_cfg* cfg, const clift_field* field, const float* rays,
                              const float* jitter, int64_t n_rays, int32_t add_background,
                              void* workspace, int64_t workspace_bytes, int64_t max_active,

@@ -33,7 +33,7 @@ def test_struct_sizes_match_header_layout():
     import ctypes as C
     assert C.sizeof(L.Mlp) == 4 + 4 * 9 + 8 * 8 * 7
     assert C.sizeof(L.RenderCfg) == 4 * 9 + 4 * 7
-    assert C.sizeof(L.RenderOut) == 8 * 11 + 8
+    assert C.sizeof(L.RenderOut) == 8 * 11 + 8 + 8
 
 
 def test_no_cpu_fallback():
