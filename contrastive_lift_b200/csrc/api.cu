@@ -233,17 +233,36 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
     M.dist_ray = out->dist_ray;
     M.points = out->points;
     M.stats = reinterpret_cast<unsigned long long*>(ws.stats);
+    M.scan_state = nullptr;
+    M.rec_pos = ws.rec_pos;
+    M.rec_ray = ws.rec_ray;
+    M.rec_idx = ws.rec_idx;
+    M.cap = max_active;
+    // inference: the march emits the active-sample records itself (no dense [B,S] weights, no scan / fill launches); the
+    // per-group scan state lives in the (then unused) offset array.  Training and callers that ask for the dense weights
+    // keep the two-pass form.  CLIFT_MARCH_FUSED=0: development switch back to the two-pass form.
+    bool fused = heads && !save && !out->weights && (int64_t)round_up(cfg->n_samples, 32) * 8 * 4 <= 96 * 1024;
+    {
+        const char* e = getenv("CLIFT_MARCH_FUSED");
+        if (e && atoi(e) == 0) fused = false;
+    }
+    if (fused) {
+        M.scan_state = reinterpret_cast<unsigned long long*>(ws.offset);
+        CLIFT_CUDA(cudaMemsetAsync(ws.offset, 0, (size_t)ceil_div(n_rays, 8) * 8, stream));
+    }
     profile_mark(0, stream);
     rc = launch_march(M, stream);
     if (rc) return rc;
     profile_mark(1, stream);
     if (heads) {
-        rc = launch_scan(ws.count, ws.offset, ws.bsum, M.stats, n_rays, max_active, stream);
-        if (rc) return rc;
-        Workspace wf = ws;
-        wf.w_dense = M.w_dense;
-        rc = launch_fill(cfg, rays, jitter, n_rays, wf, max_active, stream);
-        if (rc) return rc;
+        if (!fused) {
+            rc = launch_scan(ws.count, ws.offset, ws.bsum, M.stats, n_rays, max_active, stream);
+            if (rc) return rc;
+            Workspace wf = ws;
+            wf.w_dense = M.w_dense;
+            rc = launch_fill(cfg, rays, jitter, n_rays, wf, max_active, stream);
+            if (rc) return rc;
+        }
         if (heads & CLIFT_HEAD_RGB) CLIFT_CUDA(cudaMemsetAsync(out->rgb_raw, 0, n_rays * 3 * sizeof(float), stream));
         if (heads & CLIFT_HEAD_SEMANTIC) CLIFT_CUDA(cudaMemsetAsync(out->semantic_raw, 0, n_rays * C * sizeof(float), stream));
         if (heads & CLIFT_HEAD_INSTANCE) CLIFT_CUDA(cudaMemsetAsync(out->instance, 0, n_rays * DI * sizeof(float), stream));

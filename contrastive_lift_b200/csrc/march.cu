@@ -21,10 +21,12 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 constexpr int kFullLaneMin = 12;   // in-box samples per 32-sample chunk from which the lane-per-sample lookup wins
 
-template <int NV>
+template <int NV, bool kFused>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_constant__ MarchParams P) {
     extern __shared__ __align__(16) float s_lines[];
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ long long s_group;                 // fused: the claimed group / its exclusive record offset
+    __shared__ int s_cnt[kWarpsPerCta + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* lines_s = nullptr;
     if (P.lines_in_smem) {
@@ -56,9 +58,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
     const int n_chunks = (S + 31) >> 5;
     const int q = lane & 3;
     unsigned long long inbox_total = 0;
+    // fused: this warp's weights of the running ray, [round32(S)] floats behind the staged line factors
+    size_t line_floats = 0;
+    if (P.lines_in_smem)
+        for (int m = 0; m < 3; ++m) line_floats += (size_t)P.f.ll[m] * P.f.comps;
+    float* wst = s_lines + line_floats + (size_t)warp * (size_t)(n_chunks * 32);
+    const long long n_groups = (P.n_rays + kWarpsPerCta - 1) / kWarpsPerCta;
 
-    for (int64_t ray = (int64_t)blockIdx.x * kWarpsPerCta + warp; ray < P.n_rays;
-         ray += (int64_t)gridDim.x * kWarpsPerCta) {
+    for (int64_t it = (int64_t)blockIdx.x;; it += (int64_t)gridDim.x) {
+        int64_t ray;
+        long long group = it;
+        if (kFused) {       // groups in ticket order: every predecessor of a claimed group is running or done
+            __syncthreads();
+            if (threadIdx.x == 0) s_group = (long long)atomicAdd(P.stats + 4, 1ull);
+            __syncthreads();
+            group = s_group;
+        }
+        if (group >= n_groups) break;
+        ray = group * kWarpsPerCta + warp;
+        const bool live = ray < P.n_rays;             // fused: the last group may be ragged; its idle warps still take part
+        if (!kFused && !live) continue;
+        if (!live) ray = P.n_rays - 1;
         const float rv = lane < 8 ? __ldg(P.rays + ray * 8 + lane) : 0.0f;
         RayGeom g;
 #pragma unroll
@@ -74,9 +94,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
         float T_run = 1.0f, W_run = 0.0f, WM_run = 0.0f;
         float opa = 0.0f, dep = 0.0f, uni = 0.0f, bi = 0.0f;
         int n_act = 0, n_in = 0;
-        float* wrow = P.w_dense + ray * S;
+        float* wrow = kFused ? nullptr : P.w_dense + ray * S;
 
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = 0; c < (live ? n_chunks : 0); ++c) {
             const int i = c * 32 + lane;
             const bool valid = i < S;
             const float t = sample_t(g, G.step, i);
@@ -147,7 +167,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
                 dep += w * t;
                 n_act += __popc(__ballot_sync(0xffffffffu, w > G.thres));
             }
-            if (valid) {
+            if (kFused) {
+                wst[i] = w;
+            } else if (valid) {
                 wrow[i] = w;
                 if (P.sigma_dense) {
                     P.sigma_dense[ray * S + i] = sigma_out;
@@ -161,14 +183,83 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
             uni = warp_sum(uni);
             bi = warp_sum(bi);
         }
-        if (lane == 0) {
-            P.count[ray] = n_act;
+        if (lane == 0 && live) {
+            if (!kFused) P.count[ray] = n_act;
             P.opacity[ray] = opa;
             P.depth[ray] = dep;
             if (P.dist_ray) P.dist_ray[ray] = uni * (1.0f / 3.0f) + 2.0f * bi;
         }
-        if (P.points && lane < 3) P.points[ray * 3 + lane] = __fadd_rn(g.o[lane], __fmul_rn(dep, g.d[lane]));
+        if (P.points && lane < 3 && live) P.points[ray * 3 + lane] = __fadd_rn(g.o[lane], __fmul_rn(dep, g.d[lane]));
         inbox_total += (unsigned long long)n_in;
+        if (kFused) {
+            // ---- record offsets: intra-group exclusive scan + decoupled look-back over the groups before this one ----
+            if (lane == 0) s_cnt[warp] = live ? n_act : 0;
+            __syncthreads();
+            if (warp == 0) {
+                const int c = lane < kWarpsPerCta ? s_cnt[lane] : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < kWarpsPerCta; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const unsigned long long total = (unsigned long long)__shfl_sync(0xffffffffu, inc, kWarpsPerCta - 1);
+                constexpr unsigned long long kAgg = 1ull << 62, kInc = 2ull << 62, kVal = (1ull << 62) - 1ull;
+                volatile unsigned long long* st = P.scan_state;
+                if (lane == 0) atomicExch(P.scan_state + group, (group == 0 ? kInc : kAgg) | total);
+                unsigned long long excl = 0;
+                long long j = group - 1;
+                while (j >= 0) {        // 32 predecessors per step, nearest first in lane 0
+                    const long long jj = j - lane;
+                    unsigned long long v = 0;
+                    do {
+                        v = jj >= 0 ? st[jj] : kInc;                       // before the first group: an inclusive prefix of 0
+                    } while (__any_sync(0xffffffffu, (v >> 62) == 0ull));   // wait until every read state is published
+                    const unsigned inc_mask = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+                    const int stop = inc_mask ? __ffs(inc_mask) - 1 : 32;   // nearest lane holding an inclusive prefix
+                    unsigned long long part = lane <= stop ? (v & kVal) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                    excl += part;
+                    if (inc_mask) break;
+                    j -= 32;
+                }
+                if (lane == 0) {
+                    if (group > 0) atomicExch(P.scan_state + group, kInc | (excl + total));
+                    s_group = (long long)excl;
+                    if (group == n_groups - 1) {     // the last group knows the total
+                        const unsigned long long all = excl + total;
+                        P.stats[0] = all;
+                        P.stats[2] = (long long)all > P.cap ? 1ull : 0ull;
+                        P.stats[3] = (unsigned long long)((min((long long)all, P.cap) + CLIFT_TILE - 1) / CLIFT_TILE);
+                    }
+                }
+                if (lane < kWarpsPerCta) s_cnt[lane] = inc - c;            // exclusive offset of each ray inside the group
+            }
+            __syncthreads();
+            // ---- emit this ray's records (same arithmetic as fill_kernel: positions are recomputed, bit-exact) ----
+            if (live && n_act > 0) {
+                const long long pos = s_group + s_cnt[warp];
+                int found = 0;
+                for (int c = 0; c < n_chunks && found < n_act; ++c) {
+                    const int i = c * 32 + lane;
+                    const float w = wst[i];
+                    const bool act = i < S && w > G.thres;
+                    const unsigned m = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        const long long dst = pos + found + __popc(m & ((1u << lane) - 1u));
+                        if (dst < P.cap) {
+                            float x[3];
+                            sample_point(g, sample_t(g, G.step, i), G.amin, G.amax, G.inv, x);
+                            P.rec_pos[dst] = make_float4(x[0], x[1], x[2], w);
+                            P.rec_ray[dst] = (int32_t)ray;
+                            P.rec_idx[dst] = i;
+                        }
+                    }
+                    found += __popc(m);
+                }
+            }
+        }
     }
     if (lane == 0 && inbox_total) atomicAdd(P.stats + 1, inbox_total);
 }
@@ -590,14 +681,26 @@ int launch_march(const MarchParams& P_in, cudaStream_t stream) {
     size_t line_bytes = 0;
     for (int m = 0; m < 3; ++m) line_bytes += (size_t)P.f.ll[m] * comps * 4;
     P.lines_in_smem = line_bytes <= 96 * 1024 ? 1 : 0;
-    const size_t smem = P.lines_in_smem ? line_bytes : 0;
+    const bool fused = P.scan_state != nullptr;
+    // fused compaction: + one row of round32(S) weights per warp behind the line factors
+    const size_t stage_bytes = fused ? (size_t)kWarpsPerCta * (size_t)round_up(P.g.S, 32) * 4 : 0;
+    if (fused && (P.lines_in_smem ? line_bytes : 0) + stage_bytes > 200 * 1024) {
+        set_error("launch_march: fused compaction needs %zu bytes of shared memory", line_bytes + stage_bytes);
+        return CLIFT_ERR_UNSUPPORTED;
+    }
+    const size_t smem = (P.lines_in_smem ? line_bytes : 0) + stage_bytes;
     const int64_t want = ceil_div(P.n_rays, kWarpsPerCta);
     const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 6);
     if (grid <= 0) return CLIFT_OK;
 #define CLIFT_MARCH_CASE(NV)                                                                               \
     case NV: {                                                                                             \
-        CLIFT_CUDA(cudaFuncSetAttribute(march_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        march_kernel<NV><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);                                    \
+        if (fused) {                                                                                       \
+            CLIFT_CUDA(cudaFuncSetAttribute(march_kernel<NV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            march_kernel<NV, true><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);                          \
+        } else {                                                                                           \
+            CLIFT_CUDA(cudaFuncSetAttribute(march_kernel<NV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            march_kernel<NV, false><<<grid, kWarpsPerCta * 32, smem, stream>>>(P);                         \
+        }                                                                                                  \
         break;                                                                                             \
     }
     switch (comps / 16) {

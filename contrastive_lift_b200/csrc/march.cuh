@@ -33,7 +33,15 @@ struct MarchParams {
     float* depth;       // [B]
     float* dist_ray;    // [B] or null
     float* points;      // [B,3] or null
-    unsigned long long* stats;   // [8] u64: 0 n_active 1 n_inbox 2 overflow
+    unsigned long long* stats;   // [8] u64: 0 n_active 1 n_inbox 2 overflow 3 n_tiles 4 group ticket (fused compaction)
+    // fused compaction (inference; null scan_state = off): the march itself emits the ray-major active-sample records -
+    // groups of 8 consecutive rays are claimed in ticket order and their record offsets come from a decoupled look-back
+    // over `scan_state` (one u64 per group: flag << 62 | count), so no dense [B,S] weight array is written or re-read
+    unsigned long long* scan_state;   // [ceil(B / 8)], zeroed by the caller
+    float4* rec_pos;
+    int32_t* rec_ray;
+    int32_t* rec_idx;
+    long long cap;
 };
 
 inline GeomParams make_geom(const clift_render_cfg* c) {
