@@ -471,6 +471,10 @@ def run_ours(args):
                                                                 distributed=True)
         except Exception as e:
             multi["train_step_cfg4"] = {"error": f"{type(e).__name__}: {e}"}
+    if dist is not None:
+        from contrastive_lift_b200 import parallel as _par
+        torch.cuda.synchronize(dev)
+        _par.destroy_nccl_communicators()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

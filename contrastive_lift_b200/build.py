@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libclift_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["api.cu", "march.cu", "heads.cu", "heads_tc.cu", "heads_tc16.cu", "heads_x16.cu", "wgrad_tc.cu", "backward.cu", "pack.cu", "rays.cu", "loss.cu", "epoch.cu"]
+SOURCES = ["api.cu", "march.cu", "heads.cu", "heads_tc.cu", "heads_tc16.cu", "heads_x16.cu", "wgrad_tc.cu", "backward.cu", "pack.cu", "rays.cu", "loss.cu", "epoch.cu", "collective.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -79,7 +79,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     open(STAMP, "w").write("".join(f"{k} {v}\n" for k, v in stamp.items() if k in want))
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *[obj_of(src) for src in SOURCES]]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *[obj_of(src) for src in SOURCES], "-ldl"]
     subprocess.run(cmd, check=True)
     return LIB
 

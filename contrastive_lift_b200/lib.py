@@ -146,6 +146,7 @@ SIGNATURES = {
     "clift_assign_centroids": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp]),
     "clift_assign_clusters": (C.c_int32, [_vp, C.c_int64, C.c_int32, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "clift_labels_onehot": (C.c_int32, [_vp, C.c_int64, C.c_int32, _vp, _vp]),
+    "clift_allreduce_grads": (C.c_int32, [_vp, _vp, C.c_int64, _vp]),
 }
 
 

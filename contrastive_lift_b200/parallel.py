@@ -8,10 +8,66 @@ DistributedSampler does), so torch.distributed's NCCL all-reduce over NVLink is 
 """
 from __future__ import annotations
 
+import ctypes as C
+import os
 from typing import Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+class _NcclUniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+_NCCL_LIB = None
+_COMMS = {}
+
+
+def _nccl_lib():
+    """ctypes handle of the libnccl this process already uses (PyTorch's bundled copy)."""
+    global _NCCL_LIB
+    if _NCCL_LIB is None:
+        bundled = os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2")
+        lib = C.CDLL(bundled if os.path.exists(bundled) else "libnccl.so.2")
+        lib.ncclGetUniqueId.argtypes = [C.POINTER(_NcclUniqueId)]
+        lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _NcclUniqueId, C.c_int]
+        lib.ncclCommDestroy.argtypes = [C.c_void_p]
+        lib.ncclGetErrorString.restype = C.c_char_p
+        _NCCL_LIB = lib
+    return _NCCL_LIB
+
+
+def nccl_communicator(device: torch.device, group=None) -> int:
+    """An ncclComm_t of this rank for ``clift_allreduce_grads`` (the C-ABI collective): torch.distributed does not hand out
+    its own communicator, so one is created next to it - rank 0 draws the unique id, torch.distributed broadcasts it, every
+    rank calls ncclCommInitRank.  Cached per (device, group); lives until ``destroy_nccl_communicators()``."""
+    key = (torch.device(device), id(group))
+    if key in _COMMS:
+        return _COMMS[key]
+    nccl = _nccl_lib()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = _NcclUniqueId()
+    if rank == 0:
+        rc = nccl.ncclGetUniqueId(C.byref(uid))
+        if rc != 0:
+            raise RuntimeError(f"ncclGetUniqueId: {nccl.ncclGetErrorString(rc).decode()}")
+    raw = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=device)
+    dist.broadcast(raw, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    uid = _NcclUniqueId.from_buffer_copy(bytes(raw.cpu().tolist()))
+    comm = C.c_void_p()
+    with torch.cuda.device(device):
+        rc = nccl.ncclCommInitRank(C.byref(comm), world, uid, rank)
+    if rc != 0:
+        raise RuntimeError(f"ncclCommInitRank: {nccl.ncclGetErrorString(rc).decode()}")
+    _COMMS[key] = comm.value
+    return comm.value
+
+
+def destroy_nccl_communicators() -> None:
+    for comm in _COMMS.values():
+        _nccl_lib().ncclCommDestroy(C.c_void_p(comm))
+    _COMMS.clear()
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -48,6 +104,8 @@ def gather_rays_output(local: torch.Tensor, n_total: int, group=None) -> torch.T
 
 class GradientArena:
     """Persistent flat fp32 arena for the gradient all-reduce of one optimizer's parameters (DDP's bucket, kept across steps).
+    On CUDA / NCCL the collective is the library's own C-ABI entry ``clift_allreduce_grads``, stream-ordered on the
+    compute stream like every other launch of the path.
 
     ``reduce()`` gathers the live ``.grad``s into the arena with one multi-tensor copy, issues ONE ``all_reduce(SUM)`` on
     the arena (+ one presence flag per parameter, see below) and scatters the sums back with one multi-tensor copy; the 1/N
@@ -60,9 +118,14 @@ class GradientArena:
     the reduced gradient if ANY rank had one; here the passes are the same on every rank by construction, so a differing
     None pattern is a bug: the summed flags are checked one call later (no sync on the hot path) and raise."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, c_abi: Optional[bool] = None):
+        """``c_abi``: issue the collective through the library's own entry ``clift_allreduce_grads`` on a communicator created
+        by ``nccl_communicator`` (default for CUDA parameters under the NCCL backend; CLIFT_ALLREDUCE_TORCH=1 or False: through
+        ``torch.distributed.all_reduce``, which is also what CPU / gloo groups use)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
+        self.c_abi = c_abi
+        self._comm = None
         if not self.params:
             raise ValueError("GradientArena: no trainable parameters")
         dev = self.params[0].device
@@ -109,7 +172,17 @@ class GradientArena:
             torch._foreach_copy_([s for s, _ in live], [g for _, g in live])
         self._host_flags.copy_(torch.tensor([0.0 if p.grad is None else 1.0 for p in self.params]))
         self.flags.copy_(self._host_flags, non_blocking=True)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        use_c = self.c_abi
+        if use_c is None:
+            use_c = self.flat.is_cuda and dist.get_backend(self.group) == "nccl" and os.environ.get("CLIFT_ALLREDUCE_TORCH") != "1"
+        if use_c:
+            from . import lib as L
+            if self._comm is None:
+                self._comm = nccl_communicator(self.flat.device, self.group)
+            with L.on(self.flat.device):
+                L.check(L.load().clift_allreduce_grads(self._comm, L.ptr(self.flat), self.flat.numel(), L.stream_ptr(self.flat.device)))
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if average:
             self.flat[:self.total].mul_(1.0 / world)
         if live:

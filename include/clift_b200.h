@@ -395,6 +395,13 @@ int32_t clift_assign_clusters(const float* features, int64_t n, int32_t dim, int
                               int32_t* labels, uint32_t* class_scratch, int32_t* stats2, void* stream);
 int32_t clift_labels_onehot(const int32_t* labels, int64_t n, int32_t width, double* onehot, void* stream);
 
+/* ---- the path's one collective.  Sum-all-reduce (in place) of `count` fp32 values - the flat gradient arena of
+ * one optimizer's parameters - over the caller's NCCL communicator (an ncclComm_t, passed as void*) on `stream`; what
+ * Lightning's DDP does after every manual_backward (trainer/__init__.py:95-108; trainer:198,220).  The mean's 1/N is left to
+ * clift_adam_step (grad_scale).  NCCL is not linked: ncclAllReduce is resolved at first call from the libnccl.so.2 already
+ * loaded in the process (CLIFT_ERR_UNSUPPORTED when there is none). */
+int32_t clift_allreduce_grads(void* nccl_comm, float* arena, int64_t count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,7 +217,7 @@ def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False
                 "clift_launches_per_step": launches, "optimizer": adam.__name__, "loss_main": float(losses[0]),
                 "loss_slow_fast": float(losses[1])})
     if arenas is not None:
-        out["allreduce"] = {"collective": "NCCL all_reduce(SUM) of one persistent fp32 arena per optimizer, inside the timed step",
+        out["allreduce"] = {"collective": "clift_allreduce_grads (NCCL sum-all-reduce through the C ABI) of one persistent fp32 arena per optimizer, inside the timed step",
                             "main_pass_ms": ar0, "instance_pass_ms": ar1,
                             "main_pass_bytes": arenas[0].nbytes, "instance_pass_bytes": arenas[1].nbytes,
                             "note": "device time between CUDA events around gather-copy + all_reduce + scatter-copy, max over "

@@ -181,3 +181,11 @@ def test_fused_adam_step_bumps_the_packed_parameter_epoch():
     e0 = L.param_epoch()
     opt.step()
     assert L.param_epoch() == e0 + 1
+
+
+def test_allreduce_entry_refuses_a_null_communicator():
+    """clift_allreduce_grads (the path's one collective) validates its arguments before touching NCCL."""
+    lib = L.load()
+    assert lib.clift_allreduce_grads(None, None, 16, None) == -1
+    assert b"communicator" in lib.clift_last_error()
+    assert lib.clift_allreduce_grads(C.c_void_p(1), None, 0, None) == 0          # empty arena: nothing to do
