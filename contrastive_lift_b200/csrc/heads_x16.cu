@@ -225,7 +225,11 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
 template <bool kPair>
 __device__ __forceinline__ uint32_t fin_kstep_bytes(int n_pad) { return (kPair ? 48u : 64u) * (uint32_t)n_pad; }
 template <bool kPair>
-__device__ __forceinline__ int fin_ksteps_per_stage(int n_pad) { return Cfg<kPair>::kStageBytes / (int)fin_kstep_bytes<kPair>(n_pad); }
+__device__ __forceinline__ int fin_ksteps_per_stage(int n_pad) {
+    // four k-steps per stage whenever they fit (always for n_pad <= 64): the final layer's issue loop is then four fixed
+    // groups of 8 MMAs + the bias step, with no per-k-step stage bookkeeping
+    return min(4, Cfg<kPair>::kStageBytes / (int)fin_kstep_bytes<kPair>(n_pad));
+}
 template <bool kPair>
 __device__ __forceinline__ int gemm_stages(const XGemm& g) {
     if (g.kind != kFin) return 2 * ((g.k_steps + 2) / 2);
@@ -439,42 +443,64 @@ __device__ __forceinline__ void issue_final(const Smem& s, Issuer<kPair>& I, uin
     wait_d_free<kPair>(s, I.unit);
     I.stamp(0);
     const uint32_t d = tmem + kColD + (I.unit & 1u) * 128u;
-    // k-steps [0, 8) need the first half of the operand, [8, k_steps) the second; the bias step closes the unit.  The stage
-    // boundaries (per k-steps each) are handled by a running position inside the stage, so the loops carry no other tests.
-    uint32_t st = 0, w = 0;
-    int left = 0, done = 0;                                  // k-steps left in the current stage / stages consumed
-    auto next_block = [&]() {
-        if (left == 0) {
-            if (done) {
-                commit<kPair>(&s.empty[st]);
-                ++I.cnt;
-            }
-            w = wait_stage<kPair>(s, I, st);
-            left = per;
-            ++done;
-        } else {
-            w += kstep16;
-        }
-        --left;
+    // k-steps [0, 8) need the first half of the operand, [8, k_steps) the second; the bias step closes the unit
+    uint32_t st = 0;
+    auto kstep = [&](uint32_t w, uint32_t acc) {
+        mma_ts<kPair>(d, ah, mk_desc(w | (rows1 << 16)), idesc2, acc);
+        mma_ss<kPair>(d, mk_desc(al), mk_desc((w + off2) | (rows2 << 16)), idesc, 1u);
+        ah += 8u;
+        al += 2u * (kChunkBytes >> 4);
     };
-    const int mid = min(8, k_steps);
     wait_a_ready<kPair>(s, I, in, 0);
     I.stamp(1);
-    for (int kk = 0; kk < mid; ++kk, ah += 8u, al += 2u * (kChunkBytes >> 4)) {
+    if (per == 4 && k_steps == 16) {            // the shipped shape: 4 stages of 4 k-steps + the bias stage
+#pragma unroll 1
+        for (int g4 = 0; g4 < 4; ++g4) {
+            if (g4 == 2) wait_a_ready<kPair>(s, I, in, 1);
+            const uint32_t w = wait_stage<kPair>(s, I, st);
+            kstep(w, g4 > 0 ? 1u : 0u);
+            kstep(w + kstep16, 1u);
+            kstep(w + 2u * kstep16, 1u);
+            kstep(w + 3u * kstep16, 1u);
+            commit<kPair>(&s.empty[st]);
+            ++I.cnt;
+        }
+        const uint32_t w = wait_stage<kPair>(s, I, st);
+        mma_ss<kPair>(d, on, mk_desc(w | (rows1 << 16)), idesc2, 1u);
+        commit<kPair>(&s.empty[st]);
+        ++I.cnt;
+    } else {                                    // general shape: running position inside the stage
+        uint32_t w = 0;
+        int left = 0, done = 0;
+        auto next_block = [&]() {
+            if (left == 0) {
+                if (done) {
+                    commit<kPair>(&s.empty[st]);
+                    ++I.cnt;
+                }
+                w = wait_stage<kPair>(s, I, st);
+                left = per;
+                ++done;
+            } else {
+                w += kstep16;
+            }
+            --left;
+        };
+        const int mid = min(8, k_steps);
+        for (int kk = 0; kk < mid; ++kk) {
+            next_block();
+            kstep(w, kk > 0 ? 1u : 0u);
+        }
+        wait_a_ready<kPair>(s, I, in, 1);
+        for (int kk = mid; kk < k_steps; ++kk) {
+            next_block();
+            kstep(w, 1u);
+        }
         next_block();
-        mma_ts<kPair>(d, ah, mk_desc(w | (rows1 << 16)), idesc2, kk > 0 ? 1u : 0u);
-        mma_ss<kPair>(d, mk_desc(al), mk_desc((w + off2) | (rows2 << 16)), idesc, 1u);
+        mma_ss<kPair>(d, on, mk_desc(w | (rows1 << 16)), idesc2, 1u);
+        commit<kPair>(&s.empty[st]);
+        ++I.cnt;
     }
-    wait_a_ready<kPair>(s, I, in, 1);
-    for (int kk = mid; kk < k_steps; ++kk, ah += 8u, al += 2u * (kChunkBytes >> 4)) {
-        next_block();
-        mma_ts<kPair>(d, ah, mk_desc(w | (rows1 << 16)), idesc2, 1u);
-        mma_ss<kPair>(d, mk_desc(al), mk_desc((w + off2) | (rows2 << 16)), idesc, 1u);
-    }
-    next_block();
-    mma_ss<kPair>(d, on, mk_desc(w | (rows1 << 16)), idesc2, 1u);
-    commit<kPair>(&s.empty[st]);
-    ++I.cnt;
     (void)steps;
     commit<kPair>(&s.d_full[I.unit & 1u]);
     I.stamp(2);
