@@ -202,22 +202,35 @@ def psnr_match(rend, model, cpu_rays, cpu_maps, dev):
            "rays": int(cpu_rays.shape[0]), "against": "CPU reference, same rays (cpu_baseline sample)"}
     if out[1] is not None and cpu_sem is not None:
         res["semantic_prob_max_abs_err"] = float((out[1].float().cpu().exp() - cpu_sem.exp()).abs().max())
-    over = 0
+    over = at_thres = 0
     if out[2] is not None and cpu_ins is not None:
         ins = out[2].float().cpu()
         per_ray = (ins - cpu_ins).abs().amax(-1) / cpu_ins.abs().max().clamp_min(1e-12)
         res["instance_max_rel_err"] = float(per_ray.max())
         over = int((per_ray >= 1e-4).sum())
         res["instance_rays_over_1e-4"] = over
+        if 0 < over <= 4096:
+            # are those the rays with a sample at the activity threshold?  (CPU oracle weights of just those rays; the same
+            # 2e-3 relative margin the parity tests use, tests/gpu_util.py: flip_risk)
+            from contrastive_lift_b200 import synthetic as syn
+            from oracle import clift_oracle as orc
+            samples = int(rend.n_samples)
+            cfg = orc.RenderConfig(aabb=syn.default_aabb(), grid_dim=GRID, step_ratio=orc.ratio_for_samples(syn.default_aabb(), GRID, samples)).refresh()
+            with torch.no_grad():
+                w = orc._march(syn.make_field_params(0, GRID, N_CLS, N_INS), cfg, cpu_rays[per_ray >= 1e-4], None)[6]
+            at_thres = int((((w - cfg.weight_thres).abs() < 2e-3 * cfg.weight_thres).sum(-1) > 0).sum())
+            res["instance_rays_over_1e-4_with_a_sample_at_the_threshold"] = at_thres
     res["tolerance"] = ("1e-4 scale-relative (max |diff| / max |reference|) per map; semantic in probability space.  A sample "
                         "whose weight straddles raymarch_weight_thres = 1e-4 within fp32 rounding may be active in one "
                         "implementation and not the other (renderer:103); that moves its ray's un-normalised instance "
                         "embedding by thres x |embedding| ~ 1e-4 of the scale, so rays_over counts such rays")
     res["ok_strict"] = bool(res["rgb_max_abs_err"] < 1e-4 and res["depth_max_rel_err"] < 1e-4 and
                             res.get("semantic_prob_max_abs_err", 0.0) < 1e-4 and res.get("instance_max_rel_err", 0.0) < 1e-4)
+    # ok: every map inside 1e-4 except rays that demonstrably carry a sample at the threshold (one flip moves the
+    # un-normalised embedding by at most thres x |embedding|, i.e. ~1e-4 of the scale: 2e-4 bounds two flips)
     res["ok"] = bool(res["rgb_max_abs_err"] < 1e-4 and res["depth_max_rel_err"] < 1e-4 and
-                     res.get("semantic_prob_max_abs_err", 0.0) < 1e-4 and res.get("instance_max_rel_err", 0.0) < 3e-4 and
-                     over <= max(2, int(2e-5 * res["rays"])))
+                     res.get("semantic_prob_max_abs_err", 0.0) < 1e-4 and res.get("instance_max_rel_err", 0.0) < 2e-4 and
+                     (over == 0 or at_thres == over))
     return res
 
 
@@ -521,19 +534,20 @@ def run_ours(args):
                                 "(fp32-faithful heads issue 3 tf32 MMAs per product = 6x the bf16 cost, so the reachable "
                                 "fraction of this peak is 1/6 by construction)")},
         "roofline_march": {"kernel": "march_kernel", "bound": "hbm", "achieved": march_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                           "frac": march_gbs / pk["hbm"], "traffic": ncu_traffic("r01_ncu_march", args.frame, args.samples),
-                           "traffic_source": "committed ncu capture profiles/r01_ncu_march.json (kernel unchanged since), not measured in this run",
+                           "frac": march_gbs / pk["hbm"], "traffic": ncu_traffic("r02_ncu_march", args.frame, args.samples),
+                           "traffic_source": "committed ncu capture profiles/r02_ncu_march.json (march with fused compaction), not measured in this run",
                            "algorithmic_bytes_per_launch": march_bytes,
                            "not_a_roofline": "frac > 1: the 12.6 MB of factors are L1/L2-resident, so the ALGORITHMIC gather rate "
                                              "(1152 B per in-box sample) exceeds the HBM peak; HBM does not bound this kernel",
-                           "binding_unit": {"unit": "L1/TEX", "pct_of_peak": ncu_metric("r01_ncu_march", "l1tex__throughput.avg.pct_of_peak_sustained_active", args.frame, args.samples),
-                                            "l1_hit_pct": ncu_metric("r01_ncu_march", "l1tex__t_sector_hit_rate.pct", args.frame, args.samples),
-                                            "source": "profiles/r01_ncu_march.json"},
+                           "binding_unit": {"unit": "L1/TEX", "pct_of_peak": ncu_metric("r02_ncu_march", "l1tex__throughput.avg.pct_of_peak_sustained_active", args.frame, args.samples),
+                                            "l1_hit_pct": ncu_metric("r02_ncu_march", "l1tex__t_sector_hit_rate.pct", args.frame, args.samples),
+                                            "source": "profiles/r02_ncu_march.json"},
                            "dram_bytes_over_compulsory": (lambda t, c: None if t is None else t / c)(
-                               ncu_traffic("r01_ncu_march", args.frame, args.samples), 32.0 * n_rays + 12.6e6 + 16.0 * n_rays),
+                               ncu_traffic("r02_ncu_march", args.frame, args.samples),
+                               32.0 * n_rays + 12.6e6 + 16.0 * n_rays + 24.0 * n_act),
                            "compulsory_note": "compulsory = rays in (32 B/ray) + one read of the factors (12.6 MB) + per-ray outputs "
-                                              "(16 B/ray); the excess is the dense [B,S] weight array the march writes and the "
-                                              "compaction re-reads (fusing them is open)",
+                                              "(16 B/ray) + the active-sample records the march now emits itself (24 B each); round 1's "
+                                              "two-pass form moved 30x its compulsory bytes (dense [B,S] weights written and re-read)",
                            "note": "algorithmic gather bytes (1152 B per in-box sample) + ray/weight streams; factors are "
                                    "L2-resident so DRAM traffic is far below this by design"},
     }
