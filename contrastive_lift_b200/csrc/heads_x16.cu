@@ -65,6 +65,9 @@ constexpr int kMaxStacks = 3;
 constexpr int kMaxGemms = 16;
 constexpr int kHeaderFloats = 16;
 constexpr int kScratchRows = 32;
+constexpr int kScrStride = kScratchRows + 1;   // scratch is [record][channel], odd stride: the per-ray run sums read (run, channel)
+                                              // items channel-fastest, which at [channel][record] put 8 items of a warp on ONE bank
+                                              // and slowed the MMAs running beside them (A_lo / B operand reads share the banks)
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColD = 0, kColAH = 256;
 
@@ -100,7 +103,7 @@ struct Smem {
     unsigned char* w;       // [kStages][kStageBytes]
     unsigned char* xyz;     // hi [2 chunks] | lo [2 chunks]
     unsigned char* ones;    // [2 chunks], element 0 of every row = 1
-    float* scratch;         // [kScratchRows][kRows]
+    float* scratch;         // [kRows][kScrStride]
     int* ray;               // [kRows]
     int* runs;              // [kRows + 1]
     int* n_runs;
@@ -116,7 +119,7 @@ struct Smem {
 };
 
 constexpr size_t kSmemBytes = 2 * (size_t)kALoBytes + (size_t)kRingBytes + 4 * kChunkBytes + 2 * kChunkBytes +
-                              (size_t)kScratchRows * kRows * 4 + (2 * kRows + 8) * 4 + kMaxGemms * 8 + (3 * kMaxStagesAny + 9) * 8 + 64;
+                              (size_t)kScrStride * kRows * 4 + (2 * kRows + 8) * 4 + kMaxGemms * 8 + (3 * kMaxStagesAny + 9) * 8 + 64;
 static_assert(kSmemBytes <= 232448, "shared memory budget of one sm_100a CTA");
 
 __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
@@ -126,7 +129,7 @@ __device__ __forceinline__ Smem carve_smem(unsigned char* raw) {
     s.xyz = s.w + (size_t)kRingBytes;
     s.ones = s.xyz + 4 * kChunkBytes;
     s.scratch = reinterpret_cast<float*>(s.ones + 2 * kChunkBytes);
-    s.ray = reinterpret_cast<int*>(s.scratch + kScratchRows * kRows);
+    s.ray = reinterpret_cast<int*>(s.scratch + kScrStride * kRows);
     s.runs = s.ray + kRows;
     s.n_runs = s.runs + kRows + 1;
     s.sc = reinterpret_cast<float2*>(s.n_runs + 7);
@@ -573,7 +576,7 @@ __device__ __forceinline__ void epilogue_half(const Smem& s, Row& r, int h, int 
     ++r.tu;
 }
 
-// final layer, phase A: the stacked accumulator's two column blocks summed, un-scaled (x `mul`) -> scratch[c][row]
+// final layer, phase A: the stacked accumulator's two column blocks summed, un-scaled (x `mul`) -> scratch[row][c]
 template <bool kPair>
 __device__ __forceinline__ void final_to_scratch(const Smem& s, Row& r, int n_out, int n_pad, float mul) {
     const uint32_t d = wait_d_full(s, r);
@@ -585,7 +588,7 @@ __device__ __forceinline__ void final_to_scratch(const Smem& s, Row& r, int n_ou
         tc::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-            if (c0 + i < n_out) s.scratch[(size_t)(c0 + i) * kRows + r.row] = (v[i] + u[i]) * mul;
+            if (c0 + i < n_out) s.scratch[(size_t)r.row * kScrStride + c0 + i] = (v[i] + u[i]) * mul;
     }
     release_d<kPair>(s, r);
 }
@@ -606,7 +609,7 @@ __device__ __forceinline__ void reduce_runs(const Smem& s, int rt, int nch, floa
             const int m0 = s.runs[rr], m1 = s.runs[rr + 1];
             const int len = m1 - m0, q = (len + 3) >> 2;
             const int a = m0 + min(sub * q, len), b = m0 + min((sub + 1) * q, len);
-            for (int m = a; m < b; ++m) acc += s.scratch[(size_t)c * kRows + m];
+            for (int m = a; m < b; ++m) acc += s.scratch[(size_t)m * kScrStride + c];
             ray = s.ray[m0];
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
@@ -624,7 +627,7 @@ __device__ __forceinline__ void final_reduce(const Smem& s, const Row& r, const 
             const int n = P.n_cls;
             float v[kScratchRows];
 #pragma unroll
-            for (int i = 0; i < kScratchRows; ++i) v[i] = i < n ? s.scratch[(size_t)i * kRows + r.row] : 0.0f;
+            for (int i = 0; i < kScratchRows; ++i) v[i] = i < n ? s.scratch[(size_t)r.row * kScrStride + i] : 0.0f;
             if (P.softmax) {
                 float mx = -INFINITY;
 #pragma unroll
@@ -645,7 +648,7 @@ __device__ __forceinline__ void final_reduce(const Smem& s, const Row& r, const 
             }
 #pragma unroll
             for (int i = 0; i < kScratchRows; ++i)
-                if (i < n) s.scratch[(size_t)i * kRows + r.row] = v[i];
+                if (i < n) s.scratch[(size_t)r.row * kScrStride + i] = v[i];
         }
         reduce_runs(s, r.rt, P.n_cls, P.sem_raw, P.n_cls, 0);
     } else {
