@@ -471,3 +471,78 @@ def test_config1_density_rgb_heads_only(path):
     cfg = orc.RenderConfig(aabb=aabb, grid_dim=grid, step_ratio=ratio).refresh()
     ref_rgb, ref_depth = orc.density_rgb_only(params, cfg, rays.cpu())
     assert gpu.rel_err(rgb, ref_rgb) < REL and gpu.rel_err(depth, ref_depth) < REL
+
+
+# ---- round 2: the kernel variants behind the development switches must all agree --------------------------------------
+def _frame_maps(env, monkeypatch, frame=96, samples=256, heads=None):
+    """Renders one small frame of the bench scene under the given environment switches -> (rgb, sem, ins, depth) on the CPU."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    grid = (128, 128, 128)
+    params = syn.make_field_params(0, grid, 21, 3)
+    aabb = syn.default_aabb()
+    model, rend = gpu.build(params, grid, 21, 3, True, True, aabb, orc.ratio_for_samples(aabb, grid, samples))
+    k, c2w = syn.camera(frame, frame)
+    rays = cl.get_rays_checked(frame, frame, k.numpy(), c2w.numpy())
+    with torch.no_grad():
+        out = rend(model, rays, 1.0, False, False) if heads is None else rend._run(model, rays, None, False, heads, False)
+    stats = rend.last_stats("cuda:0")
+    for k in env:
+        monkeypatch.delenv(k)
+    return [o.float().cpu() for o in out[:4]], stats
+
+
+def test_fused_march_emits_the_same_records_as_the_two_pass_form(monkeypatch):
+    """The march that emits the active-sample records itself (ticket-ordered ray groups + decoupled look-back) keeps the ray
+    order, so every map is BIT-identical to march -> scan -> fill, and so are the counters."""
+    fused, st_f = _frame_maps({"CLIFT_MARCH_FUSED": "1"}, monkeypatch)
+    two_pass, st_t = _frame_maps({"CLIFT_MARCH_FUSED": "0"}, monkeypatch)
+    assert st_f == st_t and st_f[0] > 0
+    for a, b in zip(fused, two_pass):
+        assert torch.equal(a, b)
+    again, _ = _frame_maps({"CLIFT_MARCH_FUSED": "1"}, monkeypatch)          # run-to-run reproducible
+    for a, b in zip(fused, again):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("env", [{"CLIFT_X16_PAIR": "0"}, {"CLIFT_X16": "0"}], ids=["single_cta", "serial_kernel"])
+def test_pipelined_xyz_kernel_variants_agree(env, monkeypatch):
+    """CTA pairs (default) vs single CTAs vs round 1's serial kernel: the same fp16-split arithmetic in three schedules.
+    Semantic / instance maps agree to 1e-6 of their scale (accumulation order inside a GEMM differs: two N = 128 units
+    instead of one N = 256 MMA per k-step), rgb and depth - untouched by the pipelined kernel - bit for bit."""
+    ref, _ = _frame_maps({}, monkeypatch)
+    alt, _ = _frame_maps(env, monkeypatch)
+    assert torch.equal(ref[3], alt[3])
+    assert gpu.rel_err(alt[0], ref[0]) < 1e-6
+    assert gpu.rel_err(alt[1].exp(), ref[1].exp()) < 1e-6 and gpu.rel_err(alt[2], ref[2]) < 1e-6
+
+
+@pytest.mark.parametrize("heads", [L.HEAD_SEMANTIC, L.HEAD_INSTANCE, L.HEAD_SEMANTIC | L.HEAD_INSTANCE],
+                         ids=["semantic", "instance", "both"])
+def test_pipelined_xyz_kernel_head_subsets_and_ragged_tiles(heads, monkeypatch):
+    """forward_segment_feature / forward_instance_feature shapes of the pipelined kernel (1, 2 or 3 stacks per tile) on a
+    frame whose active-sample count is not a multiple of 128 nor of a CTA pair's two tiles, against the serial kernel."""
+    new, st = _frame_maps({}, monkeypatch, frame=37, samples=96, heads=heads)
+    old, _ = _frame_maps({"CLIFT_X16": "0"}, monkeypatch, frame=37, samples=96, heads=heads)
+    assert st[0] % 128 != 0
+    for a, b in zip(new[:3], old[:3]):
+        if a.numel():
+            assert gpu.rel_err(a, b) < 1e-6
+
+
+@pytest.mark.parametrize("name", gu.RENDER_CASES[:2])
+def test_data_gradient_engines_agree(name, monkeypatch):
+    """heads_backward_kernel's data gradients on tcgen05 (default; what the golden gradient tests above run) against the
+    FP32-FMA tile GEMM (CLIFT_DGRAD_FMA=1) on the same forward: every parameter gradient within the strict per-element bound."""
+    monkeypatch.setenv("CLIFT_TRAIN_FWD_FMA", "1")          # FP32 forward for both: no ReLU-sign flips between the runs
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CLIFT_DGRAD_FMA", mode)
+        fx, params, cfg, rays, model, rend = case(name)
+        torch.manual_seed(7)
+        out = rend(model, rays.cuda(), 1.0, False, True)
+        gu.train_loss(out, fx, "trn").backward()
+        grads[mode] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    assert set(grads["0"]) == set(grads["1"]) and len(grads["0"]) > 10
+    for k in grads["0"]:
+        assert gpu.grad_close(grads["0"][k], grads["1"][k], "fma"), k
