@@ -433,6 +433,9 @@ class TensorVMSplit(nn.Module):
         return plane_coef, line_coef
 
     # ---- optimizer groups (tensoRF.py:199-246) --------------------------------------------------
+    # The param-group schema (which parameter lists, in which order, with which lr / weight_decay keys) IS the drop-in
+    # contract: trainer/__init__.py:134-139 builds its optimizers from these lists and checkpoints store optimizer state by
+    # group index, so the four methods below reproduce the reference's groups one for one.
     def get_optimizable_parameters(self, lr_grid, lr_net, weight_decay=0):
         grad_vars = [{'params': self.density_line, 'lr': lr_grid, 'weight_decay': weight_decay},
                      {'params': self.appearance_line, 'lr': lr_grid},

@@ -237,6 +237,11 @@ class TensoRFRenderer(nn.Module):
         self.update_step_size(self.grid_dim)
 
     # ---- renderer:59-78 ---------------------------------------------------------------------------
+    # update_step_size / update_step_ratio / get_target_resolution and the host half of update_bbox_aabb_and_shrink below are
+    # deliberate TRANSCRIPTIONS of the reference's host-side bookkeeping (renderer:59-78, 683-713, 756-761): step size, sample
+    # count and the shrunk box must come out of the same fp32 tensor operations in the same order, or n_samples / the sample
+    # positions stop being bit-exact.  They are a handful of scalar tensor ops; everything per-ray / per-voxel runs in the
+    # library.
     def update_step_size(self, grid_dim):
         box_extent = self.bbox_aabb[1] - self.bbox_aabb[0]
         self.grid_dim.data = torch.tensor(grid_dim, device=self.bbox_aabb.device) if isinstance(grid_dim, tuple) else grid_dim
