@@ -449,13 +449,18 @@ __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c,
 
 // rows [0, rows_pad) of act -> Z-stash; rows [0, n_out) summed over the tile into the bias gradient.
 __device__ __forceinline__ void emit_dz(const Smem& sm, float* __restrict__ zdst, int rows_pad, int n_out, float* __restrict__ g_bias) {
-    store_rows(sm, zdst, rows_pad);
-    if (g_bias) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int r = warp; r < n_out; r += kThreads / 32) {
-            const float4 v = *reinterpret_cast<const float4*>(sm.act + (size_t)r * kTile + lane * 4);
+    // one pass: a warp iteration covers exactly one row (32 lanes x float4 = 128 records), so the row's stash store and its
+    // bias-gradient sum (fixed-order lane tree, one atomic per row and tile) share the shared-memory read
+    float4* d4 = reinterpret_cast<float4*>(zdst);
+    const float4* s4 = reinterpret_cast<const float4*>(sm.act);
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < rows_pad * (kTile / 4); i += kThreads) {
+        const int row = i >> 5;
+        const float4 v = s4[i];
+        d4[stash_idx4(rows_pad, row, i & 31)] = v;
+        if (g_bias && row < n_out) {          // warp-uniform
             const float s = warp_sum((v.x + v.y) + (v.z + v.w));
-            if (lane == 0) atomicAdd(g_bias + r, s);
+            if (lane == 0) atomicAdd(g_bias + row, s);
         }
     }
 }
@@ -486,7 +491,11 @@ __device__ __forceinline__ void dg_load(const DgEngine& E, const unsigned char* 
 // (rows >= n_in zero).  `w16` = clift_pack_linear_tc16() operand of W^T (K = the layer's out width, N = its in width).
 // The operand scale is dynamic: s = 2^floor(log2(2^14 / max|dZ|)) over the tile (exact power of two), so every scaled
 // dZ is below 2^14 and splits into fp16 (hi, lo) with 22 significant bits; the weight scale is the pack-time one.
-__device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const void* w16, int K, int n_in, int out_rows) {
+// `mask` (may be null): the A-stash block of this layer's input (mask_rows rows, stash_idx layout) - the ReLU mask
+// (input > 0) is applied while the accumulator is read back, its loads issued one 16-column chunk ahead (the first before
+// the wait for the MMAs), so the separate mask pass over the activation tile and its exposed HBM latency disappear.
+__device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const void* w16, int K, int n_in, int out_rows,
+                                             const float* __restrict__ mask = nullptr, int mask_rows = 0) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int k_steps = (K + 15) >> 4, kp = k_steps * 16;
     const int n_pad = (n_in + 31) & ~31;
@@ -576,13 +585,25 @@ __device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const 
         ++E.w_used;
         if (ks >= 1 && ks - 1 + n_pre < k_steps) ++E.w_loads;
     }
+    const int q = warp & 3, mrow = q * 32 + lane;
+    float mk_next[16];
+    auto load_mask = [&](int c0, float* mk) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mk[i] = (c0 + i < mask_rows) ? __ldg(mask + stash_idx(mask_rows, c0 + i, mrow)) : 1.0f;
+    };
+    if (mask && (warp >> 2) * 16 < n_pad) load_mask((warp >> 2) * 16, mk_next);
     tc::mbar_wait(E.d_done, E.d_count & 1u);
     ++E.d_count;
     tc::fence_after_sync();
     {   // accumulator (lane = record, column = n) -> act[n][m]; warps w and w + 4 share a lane quarter and split the columns
-        const int q = warp & 3, mrow = q * 32 + lane;
         const uint32_t taddr = E.tmem + ((uint32_t)(q * 32) << 16);
         for (int c0 = (warp >> 2) * 16; c0 < n_pad; c0 += 32) {
+            float mk[16];
+            if (mask) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) mk[i] = mk_next[i];
+                if (c0 + 32 < n_pad) load_mask(c0 + 32, mk_next);
+            }
             float v[16];
             tc::tmem_ld16(taddr + (uint32_t)c0, v);
             if (stacked) {
@@ -595,7 +616,7 @@ __device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const 
                 tc::tmem_wait_ld();
             }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) sm.act[(size_t)(c0 + i) * kTile + mrow] = v[i] * inv;
+            for (int i = 0; i < 16; ++i) sm.act[(size_t)(c0 + i) * kTile + mrow] = (!mask || mk[i] > 0.0f) ? v[i] * inv : 0.0f;
         }
         float4* d4 = reinterpret_cast<float4*>(sm.act + (size_t)n_pad * kTile);
         for (int i = tid; i < (out_rows - n_pad) * (kTile / 4); i += kThreads) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -613,10 +634,13 @@ __device__ __forceinline__ void mlp_backward(const Smem& sm, DgEngine& E, const 
         const int n_out = mlp.dims[l + 1], n_in = mlp.dims[l];
         emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
         if (l == 0 && !need_input_grad) break;
-        if (E.on && mlp.w_dg16[l])
-            run_dgrad_tc(sm, E, mlp.w_dg16[l], n_out, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256));
-        else
-            run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
+        if (E.on && mlp.w_dg16[l]) {
+            // tensor-core engine: the ReLU mask of layer l's input rides in the accumulator read-back
+            run_dgrad_tc(sm, E, mlp.w_dg16[l], n_out, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256),
+                         l > 0 ? stash_a + (size_t)a_off[l] * kTile : nullptr, (n_in + 15) & ~15);
+            continue;
+        }
+        run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
         if (l > 0) {   // ReLU mask from the saved input of layer l (= post-ReLU output of layer l-1)
             const float4* a4 = reinterpret_cast<const float4*>(stash_a + (size_t)a_off[l] * kTile);
             float4* d4 = reinterpret_cast<float4*>(sm.act);
