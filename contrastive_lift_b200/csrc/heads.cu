@@ -634,13 +634,12 @@ __device__ __forceinline__ void mlp_backward(const Smem& sm, DgEngine& E, const 
         const int n_out = mlp.dims[l + 1], n_in = mlp.dims[l];
         emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
         if (l == 0 && !need_input_grad) break;
-        if (E.on && mlp.w_dg16[l]) {
-            // tensor-core engine: the ReLU mask of layer l's input rides in the accumulator read-back
-            run_dgrad_tc(sm, E, mlp.w_dg16[l], n_out, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256),
-                         l > 0 ? stash_a + (size_t)a_off[l] * kTile : nullptr, (n_in + 15) & ~15);
-            continue;
-        }
-        run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
+        // (folding the ReLU mask into run_dgrad_tc's accumulator read-back - its `mask` argument - was measured SLOWER:
+        // 16 scalar stash loads per chunk and 32 more live registers cost more than the float4 mask pass below)
+        if (E.on && mlp.w_dg16[l])
+            run_dgrad_tc(sm, E, mlp.w_dg16[l], n_out, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256));
+        else
+            run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
         if (l > 0) {   // ReLU mask from the saved input of layer l (= post-ReLU output of layer l-1)
             const float4* a4 = reinterpret_cast<const float4*>(stash_a + (size_t)a_off[l] * kTile);
             float4* d4 = reinterpret_cast<float4*>(sm.act);
