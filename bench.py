@@ -15,13 +15,20 @@ symmetric under that roll), so per-GPU work is fixed: rays shard with no data-pa
             flushed between steps outside the timed spans.
 `e2e`     : the same frame through the public TensoRFRenderer.forward call with the rays in pinned HOST memory
             (as the reference's dataset produces them): H2D of the rays, render, D2H of the four output maps.
-`roofline`: the dominant kernel (MLP heads, compute-bound) and, as `roofline_march`, the HBM/L2-gather-bound
-            march kernel, both from CUDA events recorded inside libclift_b200.so around those launches.
-`train_step`: (N=1) BASELINE config 3 through the same public classes - ms per training step (scripts/train_step_bench.py).
-`cpu_baseline` / `--impl reference`: the reference's algorithm on the host cores.  The reference is pure Python
-            on PyTorch and /root/reference does not travel to the GPU box, so this is the reference-pinned
-            port in oracle/ (kind "port"), replaying render_panopli.py's chunk loop (chunk=2048) on a bounded
-            ray sample of the same frame.
+`roofline`: the dominant kernel - the pipelined tensor-core kernel of the semantic / instance stacks (92 % of the head
+            FLOPs; `heads_all` gives the figure over both head kernels) - from CUDA events recorded inside libclift_b200.so
+            around its launch; `roofline_march`: the march (L1/TEX-bound gather; labelled as not-a-roofline, with its
+            binding unit and DRAM bytes over compulsory bytes).
+`train_step`: (N=1) BASELINE config 3 through the same public classes - ms per training step and `parity` (step-0 losses
+            and every parameter gradient against the CPU oracle on the same RNG draws; scripts/train_step_bench.py);
+            `train_step_cfg4`: BASELINE config 4's 8192-ray batch on this many GPUs.
+N > 1 adds  `ddp_check` (N-GPU == 1-GPU equivalence, run before anything is timed), `frame_split` (ONE frame sharded over the
+            ranks + all-gather of the maps, strong scaling) and `train_step_cfg4` (batch sharded over the ranks, the
+            gradient all-reduce - clift_allreduce_grads - inside the timed step).
+`cpu_baseline` / `--impl reference`: the reference's own CPU implementation on the host cores: the unmodified reference
+            modules staged under oracle/_ref by oracle/vendor_reference.py (kind "reference"; the reference-pinned port in
+            oracle/ - kind "port" - only when they are absent), replaying render_panopli.py's chunk loop (chunk=2048) on a
+            bounded ray sample of the same frame.  `psnr_match`: the CUDA render of those rays against the CPU maps.
 """
 from __future__ import annotations
 
