@@ -288,12 +288,15 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
                 path = CLIFT_HEADS_TENSOR;
         }
         const int xyz_heads = heads & (CLIFT_HEAD_SEMANTIC | CLIFT_HEAD_INSTANCE);
-        if (path == CLIFT_HEADS_TENSOR16 && !save && xyz_heads && heads_x16_available(field, xyz_heads)) {
-            // inference: the xyz stacks on the pipelined kernel, the rgb stack (gather, basis, encoding) on the serial one
-            rc = launch_heads_forward_x16(cfg, field, ws, max_active, n_rays, o_sem, o_ins, stream);
+        if (path == CLIFT_HEADS_TENSOR16 && xyz_heads && heads_x16_available(field, xyz_heads)) {
+            // the xyz stacks on the pipelined kernel, the rgb stack (gather, basis, encoding) on the serial one; training
+            // forwards record the stash from both
+            rc = launch_heads_forward_x16(cfg, field, ws, max_active, n_rays, o_sem, o_ins, stream, save ? &lay : nullptr);
             profile_mark(5, stream);
             g_ev_split = g_profile;
-            if (!rc && o_rgb) rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, nullptr, nullptr, stream, nullptr);
+            if (!rc && o_rgb)
+                rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, nullptr, nullptr, stream,
+                                               save ? &lay : nullptr);
         } else if (path == CLIFT_HEADS_TENSOR16)
             rc = launch_heads_forward_tc16(cfg, field, rays, ws, max_active, n_rays, o_rgb, o_sem, o_ins, stream, save ? &lay : nullptr);
         else if (path == CLIFT_HEADS_TENSOR)

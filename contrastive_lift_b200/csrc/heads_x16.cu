@@ -82,6 +82,7 @@ struct XGemm {
 
 struct XStack {
     int n_layers, g_first, n_out, is_sem, out_col0;
+    int stash_id;      // training: StashLayout id of the stack (0 semantic, 1 instance fast, 2 instance slow)
 };
 
 struct XParams {
@@ -96,6 +97,10 @@ struct XParams {
     float* sem_raw;
     float* ins;
     long long* trace;
+    // training forwards (save_for_backward): every layer input is also written, unscaled fp32, to the A-stash the backward
+    // kernels read (StashLayout / stash_idx in common.cuh), the softmax probabilities to its prob block; null = inference
+    float* stash_a;
+    StashLayout lay;
 };
 
 struct Smem {
@@ -545,7 +550,8 @@ __device__ __forceinline__ void release_d(const Smem& s, Row& r) {
 // one accumulator unit (128 columns = k rows [128 h, 128 h + 128) of the next layer's operand): ReLU, rescale to the next
 // layer's operand scale, fp16 split; hi -> tensor memory (buffer `out`), lo -> shared memory
 template <bool kPair>
-__device__ __forceinline__ void epilogue_half(const Smem& s, Row& r, int h, int out, float e) {
+__device__ __forceinline__ void epilogue_half(const Smem& s, Row& r, int h, int out, float e, float* st_blk = nullptr,
+                                              float inv = 0.0f) {
     const uint32_t d = wait_d_full(s, r);
     float v[3][16];
     const int n_chunks = r.part < 2 ? 3 : 2;              // chunks part, part + 3, part + 6 of the unit's eight
@@ -560,6 +566,10 @@ __device__ __forceinline__ void epilogue_half(const Smem& s, Row& r, int h, int 
         if (j >= n_chunks) break;
         const int c = r.part + 3 * j;
         uint32_t hi[8], lo[8];
+        if (st_blk) {      // training: the next layer's input block (256 rows) gets the unscaled activation
+#pragma unroll
+            for (int i = 0; i < 16; ++i) st_blk[stash_idx(256, 128 * h + 16 * c + i, r.row)] = fmaxf(v[j][i], 0.0f) * inv;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
             split2(fmaxf(v[j][2 * i], 0.0f) * e, fmaxf(v[j][2 * i + 1], 0.0f) * e, hi[i], lo[i]);
@@ -620,7 +630,8 @@ __device__ __forceinline__ void reduce_runs(const Smem& s, int rt, int nch, floa
 }
 
 // final layer, phase B: (softmax, x compositing weight,) per-ray run sums
-__device__ __forceinline__ void final_reduce(const Smem& s, const Row& r, const XParams& P, const XStack& st, float w) {
+__device__ __forceinline__ void final_reduce(const Smem& s, const Row& r, const XParams& P, const XStack& st, float w,
+                                             float* st_prob = nullptr) {
     if (st.is_sem) {
         tc::named_bar_sync(1, kRowThreads);            // scratch complete (two parts wrote it)
         if (r.part == 0) {
@@ -638,6 +649,12 @@ __device__ __forceinline__ void final_reduce(const Smem& s, const Row& r, const 
                 for (int i = 0; i < kScratchRows; ++i) {
                     v[i] = i < n ? expf(v[i] - mx) : 0.0f;
                     tot += v[i];
+                }
+                if (st_prob) {      // training: the softmax backward needs the probabilities
+                    const float it = 1.0f / tot;
+#pragma unroll
+                    for (int i = 0; i < kScratchRows; ++i)
+                        if (i < n) st_prob[stash_idx(n, i, r.row)] = v[i] * it;
                 }
                 const float sc = w / tot;
 #pragma unroll
@@ -673,7 +690,7 @@ __device__ __forceinline__ void build_xyz(const Smem& s, const Row& r, const flo
 
 // kPair: clusters of two CTAs; both run the same number of iterations (a CTA whose tile index is past the end carries an
 // empty tile through the same schedule), the leader (cluster rank 0) issues every MMA for the pair
-template <bool kPair>
+template <bool kPair, bool kStash>
 __global__ void __launch_bounds__(kThreads, 1) heads_x16_kernel(const __grid_constant__ XParams P) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Smem s = carve_smem(smem_raw);
@@ -802,19 +819,30 @@ __global__ void __launch_bounds__(kThreads, 1) heads_x16_kernel(const __grid_con
                 }
             }
             int pending = -1;                               // stack whose final layer waits in the scratch for its reduction
+            float* stash = nullptr;                         // training: this tile's A-stash
+            if (kStash) stash = P.stash_a + (size_t)tile * P.lay.a_rows * kRows;
+            float* st_prob = kStash ? stash + (size_t)P.lay.prob_off * kRows : nullptr;
             for (int si = 0; si < P.n_stacks; ++si) {
                 const XStack& st = P.st[si];
+                if (kStash && r.part == 0) {                // layer-0 input of the stack (pe = 0): 16 rows, 3 valid
+                    float* b = stash + (size_t)P.lay.a_off[st.stash_id][0] * kRows;
+                    b[stash_idx(16, 0, r.row)] = p.x;
+                    b[stash_idx(16, 1, r.row)] = p.y;
+                    b[stash_idx(16, 2, r.row)] = p.z;
+                    for (int k = 3; k < 16; ++k) b[stash_idx(16, k, r.row)] = 0.0f;
+                }
                 for (int l = 0; l + 1 < st.n_layers; ++l) {
                     const int gi = st.g_first + l;
                     // un-scale of this accumulator, re-scale to the next layer's operand (all powers of two)
                     const float inv = l == 0 ? s.sc[gi].y * (s.sc[gi].x / ca0) : s.sc[gi].y;
                     const float e = s.sc[gi + 1].x * inv;
                     const int out = r.cur ^ 1;
-                    epilogue_half<kPair>(s, r, 0, out, e);
-                    epilogue_half<kPair>(s, r, 1, out, e);
+                    float* blk = kStash ? stash + (size_t)P.lay.a_off[st.stash_id][l + 1] * kRows : nullptr;
+                    epilogue_half<kPair>(s, r, 0, out, e, blk, inv);
+                    epilogue_half<kPair>(s, r, 1, out, e, blk, inv);
                     r.cur = out;
                     if (l == 0 && pending >= 0) {           // under the next stack's first hidden layer
-                        final_reduce(s, r, P, P.st[pending], p.w);
+                        final_reduce(s, r, P, P.st[pending], p.w, st_prob);
                         pending = -1;
                     }
                 }
@@ -823,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_x16_kernel(const __grid_con
                 pending = si;
                 if (si + 1 == P.n_stacks) {
                     if (more) build_xyz<kPair>(s, r, p_next, ca0);   // the next tile's first layers start now
-                    final_reduce(s, r, P, st, p.w);
+                    final_reduce(s, r, P, st, p.w, st_prob);
                     pending = -1;
                 }
             }
@@ -856,6 +884,31 @@ __global__ void __launch_bounds__(256) pack_x16_kernel(const uint4* __restrict__
     }
 }
 
+// clift_pack_linear_x16_batch: block b finds its job by binary search over the jobs' first-block prefix
+__global__ void __launch_bounds__(256) pack_x16_batch_kernel(const clift_x16_job* __restrict__ jobs, int n_jobs) {
+    int lo = 0, hi = n_jobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].first_block <= (int)blockIdx.x)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const clift_x16_job J = jobs[lo];
+    const int64_t total = (int64_t)J.steps * 1024;
+    const int64_t i = (int64_t)((int)blockIdx.x - J.first_block) * 256 + threadIdx.x;
+    if (i >= total) return;
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(J.w_tc16) + kHeaderFloats);
+    uint4* dst = reinterpret_cast<uint4*>(J.dst);
+    const int ks = (int)(i >> 10), rem = (int)(i & 1023);
+    const int part = rem >> 9, chunk = (rem >> 8) & 1, row = rem & 255;
+    const int h = row >> 7, r = row & 127;
+    const uint4 v = src[i];
+    dst[((int64_t)(h * J.steps + ks) << 9) + (part << 8) + (chunk << 7) + r] = v;
+    const int rank = r >> 6, rr = r & 63;
+    dst[total + (int64_t)rank * (2 * J.steps * 256) + ((int64_t)(h * J.steps + ks) << 8) + (part << 7) + (chunk << 6) + rr] = v;
+}
+
 }  // namespace
 
 static bool x16_stack_ok(const clift_mlp& m, int n_out) {
@@ -881,7 +934,7 @@ bool heads_x16_available(const clift_field* f, int heads) {
 }
 
 int launch_heads_forward_x16(const clift_render_cfg* cfg, const clift_field* field, const Workspace& ws, int64_t cap,
-                             int64_t n_rays, float* sem_raw, float* ins, cudaStream_t stream) {
+                             int64_t n_rays, float* sem_raw, float* ins, cudaStream_t stream, const StashLayout* lay) {
     XParams P;
     memset(&P, 0, sizeof(P));
     P.rec_pos = ws.rec_pos;
@@ -894,8 +947,13 @@ int launch_heads_forward_x16(const clift_render_cfg* cfg, const clift_field* fie
     P.sem_raw = sem_raw;
     P.ins = ins;
     P.trace = get_tc_trace();
-    auto add = [&](const clift_mlp& m, int is_sem, int col0) {
+    if (lay) {      // training forward: record the stash
+        P.stash_a = ws.stash_a;
+        P.lay = *lay;
+    }
+    auto add = [&](const clift_mlp& m, int is_sem, int col0, int stash_id) {
         XStack& st = P.st[P.n_stacks++];
+        st.stash_id = stash_id;
         st.n_layers = m.n_layers;
         st.g_first = P.n_gemms;
         st.n_out = m.dims[m.n_layers];
@@ -913,10 +971,10 @@ int launch_heads_forward_x16(const clift_render_cfg* cfg, const clift_field* fie
             g.w_pair = g.w + (fin ? steps * 64 * g.n_pad : steps * 16384);
         }
     };
-    if (sem_raw) add(field->semantic, 1, 0);
+    if (sem_raw) add(field->semantic, 1, 0, 0);
     if (ins) {
-        add(field->instance_fast, 0, 0);
-        if (field->slow_fast) add(field->instance_slow, 0, field->dim_instance);
+        add(field->instance_fast, 0, 0, 1);
+        if (field->slow_fast) add(field->instance_slow, 0, field->dim_instance, 2);
     }
     if (P.n_stacks == 0 || n_rays <= 0) return CLIFT_OK;
     // CTA pairs by default (each SM stages half of every weight stage); CLIFT_X16_PAIR=0: single CTAs
@@ -939,10 +997,14 @@ int launch_heads_forward_x16(const clift_render_cfg* cfg, const clift_field* fie
         lc.numAttrs = 1;
         return cudaLaunchKernelEx(&lc, kernel, P);
     };
-    if (pair)
-        CLIFT_CUDA(launch(heads_x16_kernel<true>, sm_count() & ~1, 2));
+    if (pair && lay)
+        CLIFT_CUDA(launch(heads_x16_kernel<true, true>, sm_count() & ~1, 2));
+    else if (pair)
+        CLIFT_CUDA(launch(heads_x16_kernel<true, false>, sm_count() & ~1, 2));
+    else if (lay)
+        CLIFT_CUDA(launch(heads_x16_kernel<false, true>, sm_count(), 1));
     else
-        CLIFT_CUDA(launch(heads_x16_kernel<false>, sm_count(), 1));
+        CLIFT_CUDA(launch(heads_x16_kernel<false, false>, sm_count(), 1));
     CLIFT_AFTER_LAUNCH("heads_x16_kernel");
     return CLIFT_OK;
 }
@@ -954,6 +1016,14 @@ using namespace clift;
 extern "C" int64_t clift_x16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias) {
     if (n_out != 256 || n_in <= 0 || n_in > 256) return CLIFT_ERR_UNSUPPORTED;
     return ((int64_t)ceil_div(n_in, 16) + (has_bias ? 1 : 0)) * 16384 * 2;     // single-CTA stages + CTA-pair stages
+}
+
+extern "C" int32_t clift_pack_linear_x16_batch(const clift_x16_job* jobs, int32_t n_jobs, int32_t total_blocks, void* stream) {
+    CLIFT_CHECK_ARG(n_jobs >= 0 && total_blocks >= 0 && (n_jobs == 0 || jobs), "null table or negative size");
+    if (n_jobs == 0 || total_blocks == 0) return CLIFT_OK;
+    pack_x16_batch_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs, n_jobs);
+    CLIFT_AFTER_LAUNCH("pack_x16_batch_kernel");
+    return CLIFT_OK;
 }
 
 extern "C" int32_t clift_pack_linear_x16(const void* w_tc16, void* dst, int32_t n_out, int32_t n_in, int32_t has_bias, void* stream) {

@@ -46,7 +46,7 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
 // heads_x16.cu: pipelined tensor-core kernel of the xyz stacks (semantic / instance), inference
 bool heads_x16_available(const clift_field* f, int heads);
 int launch_heads_forward_x16(const clift_render_cfg* cfg, const clift_field* field, const Workspace& ws, int64_t cap,
-                             int64_t n_rays, float* sem_raw, float* ins, cudaStream_t stream);
+                             int64_t n_rays, float* sem_raw, float* ins, cudaStream_t stream, const StashLayout* lay = nullptr);
 
 // wgrad_tc.cu: tensor-core (tcgen05 3xTF32) weight gradients over the training stashes, all layers in one launch
 constexpr int kWgradTcMaxLayers = 24;

@@ -169,8 +169,9 @@ class _PackedMlp:
                 bound_ptr = -1      # chain broken: the rest of this stack stays off the fp16 path
                 self.w_tc16[i] = None
 
-    def pack_x16(self, lib, stream):
-        """Stages of the pipelined xyz-stack kernel (inference): re-layout of the fp16-split operands just packed."""
+    def pack_x16(self, lib, jobs: list):
+        """Queue the stages of the pipelined xyz-stack kernel: re-layout of the fp16-split operands just packed
+        (``jobs``: [X16Job, ...] of the whole model, run as one clift_pack_linear_x16_batch launch)."""
         for i, l in enumerate(self.linears):
             has_bias = 1 if l.bias is not None else 0
             nb = lib.clift_x16_weight_bytes(l.out_features, l.in_features, has_bias)
@@ -179,8 +180,11 @@ class _PackedMlp:
                 continue
             if self.w_x16[i] is None:
                 self.w_x16[i] = torch.zeros((nb // 4,), device=self.wt[i].device)
-            L.check(lib.clift_pack_linear_x16(L.ptr(self.w_tc16[i]), L.ptr(self.w_x16[i]), l.out_features, l.in_features,
-                                              has_bias, stream))
+            j = L.X16Job()
+            j.w_tc16, j.dst = L.ptr(self.w_tc16[i]), L.ptr(self.w_x16[i])
+            j.steps = (l.in_features + 15) // 16 + has_bias
+            j.first_block = (jobs[-1].first_block + (jobs[-1].steps * 1024 + 255) // 256) if jobs else 0
+            jobs.append(j)
 
     def pack_dgrad16(self, lib, tc16: "L.Tc16Batch", chain: int):
         """Queue the tensor-core data-gradient operands: clift_pack_linear_tc16 of W^T (no bias; the operand scale of dZ is
@@ -637,10 +641,16 @@ class PackedField:
                 if m is not None:
                     m.pack_dgrad16(lib, tc16, chain)
         tc16.run(lib, self.device)
-        if not training:   # inference: stages of the pipelined kernel for the xyz stacks (MLP-mode heads)
-            for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
-                if m is not None and name not in self.grid_basis:
-                    m.pack_x16(lib, st)
+        # stages of the pipelined kernel for the xyz stacks (MLP-mode heads): inference and training forwards
+        jobs: list = []
+        for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
+            if m is not None and name not in self.grid_basis:
+                m.pack_x16(lib, jobs)
+        if jobs:
+            raw = bytes((L.X16Job * len(jobs))(*jobs))
+            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device, non_blocking=True)
+            blocks = jobs[-1].first_block + (jobs[-1].steps * 1024 + 255) // 256
+            L.check(lib.clift_pack_linear_x16_batch(L.ptr(table), len(jobs), blocks, st))
         f = self.field
         for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
             if name in self.grid_basis:

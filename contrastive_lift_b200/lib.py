@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -86,6 +86,10 @@ class Tc16Job(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class X16Job(C.Structure):
+    _fields_ = [("w_tc16", _vp), ("dst", _vp), ("steps", C.c_int32), ("first_block", C.c_int32)]
+
+
 class AdamTensor(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_int64)]
 
@@ -116,6 +120,7 @@ SIGNATURES = {
     "clift_pack_linear_tc": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "clift_x16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "clift_pack_linear_x16": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "clift_pack_linear_x16_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "clift_debug_tc_gemm": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_tc16_weight_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
     "clift_pack_linear_tc16": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, C.c_float, _vp]),

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 11
+#define CLIFT_ABI_VERSION 12
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -239,6 +239,15 @@ int32_t clift_pack_linear_tc(const float* w, const float* bias, float* dst, int3
  * half 0's stages first, the bias step last in each half.  clift_x16_weight_bytes() sizes dst (< 0: layer not eligible). */
 int64_t clift_x16_weight_bytes(int32_t n_out, int32_t n_in, int32_t has_bias);
 int32_t clift_pack_linear_x16(const void* w_tc16, void* dst, int32_t n_out, int32_t n_in, int32_t has_bias, void* stream);
+/* The same for a device-resident table of layers in ONE launch (job i covers blocks [first_block, first_block +
+ * ceil(steps * 1024 / 256)) of the launch; steps = ceil(n_in / 16) + has_bias; total_blocks = their sum). */
+typedef struct {
+    const void* w_tc16;
+    void* dst;
+    int32_t steps;
+    int32_t first_block;
+} clift_x16_job;
+int32_t clift_pack_linear_x16_batch(const clift_x16_job* jobs, int32_t n_jobs, int32_t total_blocks, void* stream);
 /* Bring-up / parity entry for the tensor-core GEMM core: out[128][round_up(n_out,32)] = a[128][k] * W^T (+ bias) with
  * the 3xTF32 split (one CTA).  Used by tests only. */
 int32_t clift_debug_tc_gemm(const float* a, const float* w_tc, float* out, int32_t k, int32_t n_out, int32_t has_bias,
