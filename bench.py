@@ -452,13 +452,12 @@ def run_ours(args):
         except Exception as e:
             multi["ddp_check"] = {"ok": False, "error": f"{type(e).__name__}: {e}"}
         c2w0 = syn.camera(H, W)[1].numpy()
-        b0, b1 = par.shard_range(n_rays, rank, world)
 
         def step_split():
-            rays, _bad = cl.get_rays(H, W, k_np, c2w0, device=dev)          # every rank: the same frame, its own ray range
-            out = rend(model, rays[b0:b1].contiguous(), 1.0, False, False)
+            rays, _bad = cl.get_rays(H, W, k_np, c2w0, device=dev)          # every rank: the same frame, its own rows
+            out = rend(model, par.shard_rows_cyclic(rays, H, W, rank, world).contiguous(), 1.0, False, False)
             maps = torch.cat([out[0], out[1], out[2], out[3][:, None]], 1)
-            return par.gather_rays_output(maps, n_rays)
+            return par.gather_rows_cyclic(maps, H, W)
 
         with torch.no_grad():
             for _ in range(3):
@@ -477,8 +476,9 @@ def run_ours(args):
             del full, single
         t = torch.tensor([sum(ms_split)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        multi["frame_split"] = {"workload": f"ONE {H}x{W} frame, ray ranges sharded over {world} GPUs, maps all-gathered "
-                                            f"({(3 + N_CLS + 2 * N_INS + 1) * 4} B/ray) to every rank, inside the timed region",
+        multi["frame_split"] = {"workload": f"ONE {H}x{W} frame, image rows dealt round-robin to {world} GPUs (equal cost per rank), "
+                                            f"maps all-gathered ({(3 + N_CLS + 2 * N_INS + 1) * 4} B/ray) to every rank in ray order, "
+                                            "inside the timed region",
                                 "ms_per_frame": float(t) / args.steps, "Mrays_per_s": n_rays * args.steps / (float(t) * 1e-3) / 1e6,
                                 "scaling": "strong"}
         if rank == 0:

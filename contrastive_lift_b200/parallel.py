@@ -102,6 +102,35 @@ def gather_rays_output(local: torch.Tensor, n_total: int, group=None) -> torch.T
     return torch.cat([p[:n] for p, n in zip(parts, sizes)], 0)
 
 
+def shard_rows_cyclic(rays: torch.Tensor, height: int, width: int, rank: Optional[int] = None,
+                      world: Optional[int] = None) -> torch.Tensor:
+    """Rows rank, rank + world, rank + 2 world, ... of an [H*W, K] frame (ray index = row * W + col).  A frame's cost is not
+    uniform over its rows (the object sits in the middle), so contiguous ranges leave the edge ranks idle while the centre
+    ranks work; row-cyclic shards cost the same on every rank.  ``gather_rows_cyclic`` restores the ray order."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    return rays.view(height, width, -1)[rank::world].reshape(-1, rays.shape[-1])
+
+
+def gather_rows_cyclic(local: torch.Tensor, height: int, width: int, group=None) -> torch.Tensor:
+    """Inverse of shard_rows_cyclic for an output map [rows_local * W, K] -> [H * W, K] on every rank: ONE all-gather into a
+    single buffer (ranks with one row less are padded), then a strided view puts row r * world + k back in place."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    rows = (height + world - 1) // world
+    mine = len(range(rank, height, world))
+    k = local.shape[-1] if local.dim() > 1 else 1
+    if local.shape[0] != mine * width:
+        raise ValueError(f"gather_rows_cyclic: this rank holds {local.shape[0]} rays, its cyclic shard has {mine * width}")
+    send = local.reshape(mine, width, k)
+    if mine < rows:
+        send = torch.cat([send, send.new_zeros((rows - mine, width, k))], 0)
+    out = send.new_empty((world * rows, width, k))                                # concatenated form (gloo accepts only this)
+    dist.all_gather_into_tensor(out, send.contiguous(), group=group)
+    full = out.view(world, rows, width, k).permute(1, 0, 2, 3).reshape(rows * world, width, k)[:height]   # row = local_row * world + rank
+    full = full.reshape(height * width, k)
+    return full if local.dim() > 1 else full[:, 0]
+
+
 class GradientArena:
     """Persistent flat fp32 arena for the gradient all-reduce of one optimizer's parameters (DDP's bucket, kept across steps).
     On CUDA / NCCL the collective is the library's own C-ABI entry ``clift_allreduce_grads``, stream-ordered on the

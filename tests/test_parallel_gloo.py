@@ -54,6 +54,13 @@ def _worker(rank, world, port, out):
             assert torch.equal(par.gather_rays_output(par.shard_rays(m[:, 0]), n), m[:, 0]), n
         with pytest.raises(ValueError):
             par.gather_rays_output(x, x.shape[0])          # the whole frame is not this rank's shard
+        # row-cyclic shards of a frame (balanced cost) gather back in ray order, ragged row counts included
+        for h, w in ((6, 4), (7, 3), (1, 5), (2 * world + 1, 2)):
+            frame = torch.arange(h * w * 3, dtype=torch.float32).reshape(h * w, 3)
+            mine = par.shard_rows_cyclic(frame, h, w)
+            assert mine.shape[0] == len(range(rank, h, world)) * w
+            assert torch.equal(par.gather_rows_cyclic(mine * 2.0, h, w), frame * 2.0), (h, w)
+            assert torch.equal(par.gather_rows_cyclic(mine[:, 0].contiguous(), h, w), frame[:, 0]), (h, w)
         # a None pattern that differs across ranks (one rank skipped a head) is reported by the next reduce
         arena = par.GradientArena(net.parameters())
         for p in net.parameters():
