@@ -98,6 +98,52 @@ def _param_version(p: torch.Tensor) -> Optional[int]:
         return None
 
 
+def param_list(model: nn.Module) -> List[torch.Tensor]:
+    """The parameters of ``model`` in ``named_parameters()`` order (modules in pre-order, shared modules / parameters
+    once), without the generator stack of ``nn.Module.named_parameters``: the render entries walk the model on every call."""
+    out, seen_m, seen_p = [], set(), set()
+    stack = [model]
+    while stack:
+        m = stack.pop()
+        if m is None or id(m) in seen_m:
+            continue
+        seen_m.add(id(m))
+        for q in m._parameters.values():
+            if q is not None and id(q) not in seen_p:
+                seen_p.add(id(q))
+                out.append(q)
+        stack.extend(reversed(m._modules.values()))
+    return out
+
+
+class _PackPlan:
+    """The library calls of one PackedField refresh, recorded so that the next refresh of the same parameter storage
+    replays them (same device tables, same operand buffers) instead of rebuilding ~100 job descriptors on the host.
+    Every recorded entry takes the stream as its last argument; it is re-read at replay time."""
+
+    RECORDED = ("clift_pack_batch", "clift_tc16_factor_bound", "clift_pack_linear_tc16_batch", "clift_pack_linear_x16_batch",
+                "clift_pack_linear_tc", "clift_pack_linear_tc16")
+
+    def __init__(self, lib, key):
+        self._lib, self.key = lib, key
+        self.calls: list = []
+        self.keep: list = []          # device job tables the recorded pointers refer to
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name not in self.RECORDED:
+            return fn
+
+        def call(*args):
+            self.calls.append((fn, args[:-1]))
+            return fn(*args)
+        return call
+
+    def replay(self, stream) -> None:
+        for fn, args in self.calls:
+            L.check(fn(*args, stream))
+
+
 def _linears(seq: nn.Sequential) -> List[nn.Linear]:
     return [m for m in seq if isinstance(m, nn.Linear)]
 
@@ -345,8 +391,9 @@ class TensorVMSplit(nn.Module):
         return (self.density_plane[0].shape[3], self.density_plane[0].shape[2], self.density_line[0].shape[2])
 
     # ---- packed view ---------------------------------------------------------------------------
-    def packed(self, training: bool) -> "PackedField":
-        if self._packed is None or not self._packed.matches(self):
+    def packed(self, training: bool, params: Optional[Sequence[torch.Tensor]] = None) -> "PackedField":
+        """``params``: param_list(self) when the caller already walked the model."""
+        if self._packed is None or not self._packed.matches(self, params):
             self._packed = PackedField(self)
         self._packed.refresh(training)
         return self._packed
@@ -524,12 +571,13 @@ class PackedField:
             raise L.CliftError("TensorVMSplit must live on a CUDA device: libclift_b200 has no CPU path")
         self.device = dev
         self.grid = model.grid_dim()
-        self.ids = self._ids(model)
         self.versions: Optional[Tuple[int, ...]] = None
         self.tc_stale = True
         self.trained = False
         self.has_train = self.has_infer = False
         self.model_params = list(model.parameters())
+        self.param_names = [n for n, _ in model.named_parameters()]
+        self.plans: Dict[bool, _PackPlan] = {}
         mk = lambda plist: [torch.empty((p.shape[2], p.shape[3], p.shape[1]), device=dev) for p in plist]
         mkl = lambda plist: [torch.empty((p.shape[2], p.shape[1]), device=dev) for p in plist]
         self.planes = {"density": mk(model.density_plane), "appearance": mk(model.appearance_plane)}
@@ -581,12 +629,10 @@ class PackedField:
         self.g_planes: Dict[str, List[Optional[torch.Tensor]]] = {k: [None] * 3 for k in self.planes}
         self.g_lines: Dict[str, List[Optional[torch.Tensor]]] = {k: [None] * 3 for k in self.planes}
 
-    @staticmethod
-    def _ids(model) -> Tuple[int, ...]:
-        return tuple(id(p) for p in model.parameters())
-
-    def matches(self, model) -> bool:
-        return self.ids == self._ids(model) and self.device == model.density_plane[0].device
+    def matches(self, model, params: Optional[Sequence[torch.Tensor]] = None) -> bool:
+        params = param_list(model) if params is None else params
+        return len(params) == len(self.model_params) and all(a is b for a, b in zip(params, self.model_params)) and \
+            self.device == model.density_plane[0].device
 
     def refresh(self, training: bool) -> None:
         # The packed copy is reused while no parameter changed: autograd version counters (optimizer steps, in-place ops),
@@ -595,22 +641,32 @@ class PackedField:
         # through raw pointers).  The two chunk renders of one training step therefore share one packing.  A training
         # packing carries the data-gradient operands, an inference packing the 3xTF32 / pipelined-kernel operands; each is
         # built on first use for a given parameter state.
-        versions = tuple(_param_version(p) for p in self.model_params) + tuple(p.data_ptr() for p in self.model_params) + \
-            (L.param_epoch(),)
+        ptrs = tuple(p.data_ptr() for p in self.model_params)
+        versions = tuple(_param_version(p) for p in self.model_params) + ptrs + (L.param_epoch(),)
         same = versions == self.versions and None not in versions
         if same and (self.has_train if training else self.has_infer):
             return
         if not same:
             self.has_train = self.has_infer = False
         with L.on(self.device):
-            self._refresh(training, versions)
+            plan = self.plans.get(training)
+            if plan is not None and plan.key == ptrs:
+                # same storage, new values (an optimizer step): the recorded launches read the parameters afresh
+                plan.replay(L.stream_ptr(self.device))
+                self.versions = versions
+                self.tc_stale = training
+            else:
+                self.plans.pop(training, None)
+                plan = _PackPlan(self.lib, ptrs)
+                self._refresh(training, versions, plan)
+                self.plans[training] = plan           # only a refresh that ran to the end is replayed
         if training:
             self.has_train = True
         else:
             self.has_infer = True
 
-    def _refresh(self, training: bool, versions) -> None:
-        lib, st = self.lib, L.stream_ptr(self.device)
+    def _refresh(self, training: bool, versions, plan: "_PackPlan") -> None:
+        lib, st = plan, L.stream_ptr(self.device)        # the plan forwards to the library and records the launches
         # every fp32 layout job of the model (factor transposes, W^T + bias, data-gradient copies) in ONE launch
         batch = L.PackBatch()
         for name in self.src:
@@ -622,7 +678,7 @@ class PackedField:
         for m in [self.basis, self.rgb, self.sem, self.insf, self.inss] + list(self.grid_basis.values()):
             if m is not None:
                 m.collect(batch, training)
-        batch.run(lib, self.device)
+        plan.keep.append(batch.run(lib, self.device))
         # fp16-split operand chain: |plane*line| bound -> basis -> (features, dirs, sin/cos) -> rgb stack
         vp3, i3 = C.c_void_p * 3, C.c_int64 * 3
         ap, al = self.planes["appearance"], self.lines["appearance"]
@@ -640,7 +696,7 @@ class PackedField:
             for chain, m in enumerate((self.basis, self.rgb, self.sem, self.insf, self.inss), start=4):
                 if m is not None:
                     m.pack_dgrad16(lib, tc16, chain)
-        tc16.run(lib, self.device)
+        plan.keep.append(tc16.run(lib, self.device))
         # stages of the pipelined kernel for the xyz stacks (MLP-mode heads): inference and training forwards
         jobs: list = []
         for name, m in (("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)):
@@ -650,6 +706,7 @@ class PackedField:
             raw = bytes((L.X16Job * len(jobs))(*jobs))
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device, non_blocking=True)
             blocks = jobs[-1].first_block + (jobs[-1].steps * 1024 + 255) // 256
+            plan.keep.append(table)
             L.check(lib.clift_pack_linear_x16_batch(L.ptr(table), len(jobs), blocks, st))
         f = self.field
         for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):

@@ -288,6 +288,7 @@ class PackBatch:
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
             check(lib.clift_pack_batch(ptr(table), len(self.jobs), int(self.tiles), stream_ptr(device)))
         self.jobs, self.tiles = [], 0
+        return table          # a caller that records the launch for replay keeps the job table alive
 
 
 class Tc16Batch:
@@ -320,3 +321,4 @@ class Tc16Batch:
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
             check(lib.clift_pack_linear_tc16_batch(ptr(table), len(self.jobs), int(self.chains), int(self.blocks), stream_ptr(device)))
         self.jobs, self.blocks, self.chains = [], 0, 0
+        return table

@@ -148,7 +148,8 @@ class _TotalTV(torch.autograd.Function):
                 _, c, h, w = p.shape
                 batch.unplane(gh, g, c, h, w)
             batch.run(lib, dev)
-            total = (vals * torch.tensor([float(c) for c in coefs], device=dev)).sum()
+            # coefficients: small pageable copy queued on the stream (torch.tensor(..., device=) would wait for the stream)
+            total = (vals * torch.tensor([float(c) for c in coefs]).to(dev, non_blocking=True)).sum()
         ctx.grads = grads
         return total
 

@@ -165,8 +165,9 @@ class GradientArena:
         self.flags = self.flat[self.total:]
         self._events: List[tuple] = []
         self._pending_flags = None
-        self._host_flags = torch.zeros((len(self.params),), dtype=torch.float32).pin_memory() if dev.type == "cuda" else \
-            torch.zeros((len(self.params),), dtype=torch.float32)
+        pin = (lambda x: x.pin_memory()) if dev.type == "cuda" else (lambda x: x)
+        self._host_flags = pin(torch.zeros((len(self.params),), dtype=torch.float32))
+        self._host_sums = pin(torch.zeros((len(self.params),), dtype=torch.float32))     # summed flags of the previous reduce
 
     @property
     def nbytes(self) -> int:
@@ -176,8 +177,10 @@ class GradientArena:
         """Raise if, in the previous reduce, some ranks had a gradient for a parameter and others did not."""
         if self._pending_flags is None:
             return
-        flags, world = self._pending_flags
+        flags, world, ev = self._pending_flags
         self._pending_flags = None
+        if ev is not None:
+            ev.synchronize()          # the copy was queued a whole step ago: long done, no stall
         bad = [i for i, v in enumerate(flags.tolist()) if v not in (0.0, float(world))]
         if bad:
             raise RuntimeError(f"GradientArena: gradient None-pattern differs across ranks for parameter slots {bad[:8]} "
@@ -219,7 +222,13 @@ class GradientArena:
         if ev is not None:
             ev[1].record()
             self._events.append(ev)
-        self._pending_flags = (self.flags.to("cpu", non_blocking=True) if self.flat.is_cuda else self.flags.clone(), world)
+        if self.flat.is_cuda:         # pinned destination + event: a pageable one would make the copy a host sync
+            self._host_sums.copy_(self.flags, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+            self._pending_flags = (self._host_sums, world, done)
+        else:
+            self._pending_flags = (self.flags.clone(), world, None)
         return self.total * 4
 
     def drain_ms(self) -> float:

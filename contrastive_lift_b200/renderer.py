@@ -12,14 +12,16 @@ random-background coin with ``torch.rand((1,))`` from the CPU default generator,
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
+import warnings
 from typing import List, Optional, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import lib as L
-from .field import TensorVMSplit
+from .field import TensorVMSplit, param_list
 
 _WORKSPACES = {}
 
@@ -51,7 +53,8 @@ class _Render(torch.autograd.Function):
         # outputs no loss consumes arrive as None in backward (not as zero tensors): the main training pass never uses
         # instance_map (trainer:154), so its backward skips the instance head like the reference's autograd does
         ctx.set_materialize_grads(False)
-        pk = model.packed(need_grad)
+        renderer._poll_overflow()          # an earlier render whose check was deferred: known by now?
+        pk = model.packed(need_grad, params)
         cfg = renderer._cfg(model, heads)
         B = rays.shape[0]
         C_, DI = model.num_semantic_classes, (model.dim_feature_instance or 0)
@@ -70,7 +73,9 @@ class _Render(torch.autograd.Function):
         for k, v in t.items():
             setattr(out, k, L.ptr(v))
         out.save_for_backward = 2 if need_grad else 0      # 2: the backward's dL/dZ stash is allocated at backward time
-        cap = renderer.max_active(B, need_grad)
+        cap = renderer.max_active(B, need_grad, heads)
+        # training renders with a capacity history verify the capacity WITHOUT stalling the host (see _defer_overflow_check)
+        deferred = need_grad and renderer.deferred_overflow_check and heads in renderer._active_hist
         while True:
             nbytes = lib.clift_render_workspace_bytes(C.byref(cfg), C.byref(pk.field), B, cap, out.save_for_backward)
             if nbytes < 0:
@@ -86,8 +91,11 @@ class _Render(torch.autograd.Function):
                                              L.ptr(ws), ws.numel(), cap, C.byref(out), L.stream_ptr(dev)))
             if B == 0 or not renderer.check_overflow:
                 break
+            if deferred:
+                renderer._defer_overflow_check(ws, B, cap, heads)
+                break
             n_act, _, overflow, _ = renderer.last_stats(dev)       # one 32-byte D2H (the reference syncs ~10x per call)
-            renderer._active_per_ray = max(1.0, n_act / max(B, 1))
+            renderer._note_active(heads, n_act, B)
             if not overflow:
                 break
             cap = (n_act + 127) // 128 * 128                          # rerun with the exact active-sample count
@@ -98,7 +106,7 @@ class _Render(torch.autograd.Function):
             # only tensors that are NOT outputs are kept on ctx (an output kept here would be a reference cycle)
             ctx.t = {k: t[k] for k in ("rgb_raw", "semantic_raw", "opacity") if k in t}
             ctx.ws = ws
-            ctx.param_names = [n for n, _ in model.named_parameters()]
+            ctx.param_names = pk.param_names
         empty = rays.new_zeros((0,))
         res = (t.get("rgb", empty), t.get("semantic", empty), t.get("instance", empty), t["depth"],
                t["dist_reg"].reshape(()) if "dist_reg" in t else empty, t.get("points", empty))
@@ -116,6 +124,7 @@ class _Render(torch.autograd.Function):
         if not ctx.need_grad:
             raise L.CliftError("backward through a render that was run without need_grad")
         renderer, model, pk = ctx.renderer, ctx.model, ctx.pk
+        renderer._poll_overflow()
         if ctx.ws is None:
             raise L.CliftError("backward called twice on the same render (its saved state was consumed)")
         lib = L.load()
@@ -226,6 +235,18 @@ class TensoRFRenderer(nn.Module):
         # overflow is detected after the call (check_overflow) and the call is repeated at the exact size.
         self.max_active_per_ray = 192
         self.check_overflow = True
+        # Training renders (the ones that size their stash by the capacity) check the capacity without a host sync once a
+        # previous render with the same head set has told them what to expect: the 32-byte stats record goes to pinned
+        # memory behind the render and is read by a later call (the next render / backward, or
+        # synchronize_overflow_checks()).  An overflow found that way cannot be repaired - the truncated maps were already
+        # handed out - so it raises (overflow_policy "raise") or warns ("warn") and the capacity history is corrected for
+        # the following calls.  False: every render is verified before it returns (one D2H sync per call), and an
+        # overflow repeats the call at the exact size.
+        self.deferred_overflow_check = True
+        self.overflow_policy = "raise"
+        self._active_hist = {}            # head set -> decayed maximum of active samples per ray
+        self._pending = collections.deque()
+        self._pinned = []
         # lib.HEADS_AUTO: tcgen05 tensor-core heads for inference, FP32-FMA heads for training forwards
         self.head_path = L.HEADS_AUTO
         self._active_per_ray = None
@@ -276,16 +297,60 @@ class TensoRFRenderer(nn.Module):
         target_res = ((xyz_max - xyz_min) / voxel_size).long().tolist()
         return tuple(max(x, 1) for x in target_res)
 
-    def max_active(self, n_rays: int, training: bool = False) -> int:
+    def max_active(self, n_rays: int, training: bool = False, heads: Optional[int] = None) -> int:
         """<= 0 means worst case (every sample active) to the C ABI.  Training forwards size their activation stash
-        by this capacity, so they follow the measured active count of the previous call (x1.25) instead of the
-        static per-ray bound; an overflow still repeats the call at the exact size."""
+        by this capacity, so they follow the measured active count of the previous calls with the same head set (decayed
+        maximum x1.25 + 8 per ray) instead of the static per-ray bound; an overflow repeats the call at the exact size
+        (checked renders) or is reported by a later call (deferred check)."""
         if self.max_active_per_ray <= 0:
             return 0
         per_ray = min(int(self.max_active_per_ray), int(self.n_samples))
-        if training and self.check_overflow and self._active_per_ray is not None:
-            per_ray = min(per_ray, int(self._active_per_ray * 1.25) + 8)
+        hist = self._active_hist.get(heads, self._active_per_ray)
+        if training and self.check_overflow and hist is not None:
+            per_ray = min(per_ray, int(hist * 1.25) + 8)
         return max(128, int(n_rays) * per_ray)
+
+    # ---- capacity bookkeeping -------------------------------------------------------------------------
+    def _note_active(self, heads: int, n_act: int, n_rays: int) -> None:
+        apr = n_act / max(n_rays, 1)
+        self._active_per_ray = max(1.0, apr)
+        self._active_hist[heads] = max(1.0, apr, 0.9 * self._active_hist.get(heads, 0.0))
+
+    def _defer_overflow_check(self, ws: torch.Tensor, n_rays: int, cap: int, heads: int) -> None:
+        """Queue the stats record of the render just launched: device -> pinned host behind the render, no host wait."""
+        dev = ws.device
+        st = torch.empty((4,), dtype=torch.int64, device=dev)
+        L.check(L.load().clift_render_stats(L.ptr(ws), L.ptr(st), L.stream_ptr(dev)))
+        host = self._pinned.pop() if self._pinned else torch.empty((4,), dtype=torch.int64).pin_memory()
+        host.copy_(st, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._pending.append((ev, host, n_rays, cap, heads))
+
+    def _poll_overflow(self, wait: bool = False) -> None:
+        """Read the deferred records whose copies have landed (all of them with ``wait``)."""
+        while self._pending and (wait or self._pending[0][0].query()):
+            ev, host, n_rays, cap, heads = self._pending.popleft()
+            if wait:
+                ev.synchronize()
+            n_act, _, overflow, _ = (int(v) for v in host.tolist())
+            self._pinned.append(host)
+            self._note_active(heads, n_act, n_rays)
+            if overflow:
+                self._active_hist[heads] = max(self._active_hist[heads], n_act / max(n_rays, 1))
+                msg = (f"a training render of {n_rays} rays had {n_act} active samples but room for {cap}: its maps and "
+                       "gradients were computed from the first samples only.  The capacity history now covers this case; "
+                       "repeat the step, or set renderer.deferred_overflow_check = False to verify every render before it "
+                       "returns (one host sync per call)")
+                if self.overflow_policy == "warn":
+                    warnings.warn(msg, RuntimeWarning)
+                else:
+                    self._pending.clear()
+                    raise L.CliftError(msg)
+
+    def synchronize_overflow_checks(self) -> None:
+        """Wait for every deferred capacity check (end of an epoch / before trusting the last step's numbers)."""
+        self._poll_overflow(wait=True)
 
     @staticmethod
     def _check_weight_mode(mode) -> None:
@@ -313,11 +378,11 @@ class TensoRFRenderer(nn.Module):
                                    "anything else together (trainer:54,67), and the kernels switch both with one flag")
         # one D2H of 10 floats per geometry change, not per call.  The key also catches buffers replaced or written behind
         # update_step_size's back (on_load_checkpoint assigns renderer.bbox_aabb directly, trainer:466)
-        key = (_tensor_key(self.bbox_aabb), _tensor_key(self.inv_box_extent), id(self.step_size))
-        if self._host is None or self._host[3] != key or key[0][1] is None or key[1][1] is None:
+        key = (_tensor_key(self.bbox_aabb), _tensor_key(self.inv_box_extent), id(self.step_size), _tensor_key(self.grid_dim))
+        if self._host is None or self._host[3] != key or None in (key[0][1], key[1][1], key[3][1]):
             self._host = (self.bbox_aabb.detach().cpu().tolist(), self.inv_box_extent.detach().cpu().tolist(),
-                          float(self.step_size), key)
-        aabb, inv, step, _ = self._host
+                          float(self.step_size), key, tuple(self.grid_dim.tolist()))
+        aabb, inv, step, _, grid = self._host
         cfg = L.RenderCfg()
         L.fill3(cfg.aabb_min, aabb[0])
         L.fill3(cfg.aabb_max, aabb[1])
@@ -329,8 +394,8 @@ class TensoRFRenderer(nn.Module):
         cfg.semantic_softmax = 1 if self.semantic_weight_mode == "softmax" else 0
         cfg.heads = heads
         cfg.head_path = int(self.head_path)
-        if tuple(self.grid_dim.tolist()) != tuple(model.grid_dim()):
-            raise L.CliftError(f"renderer.grid_dim {self.grid_dim.tolist()} != model factor grid {model.grid_dim()}")
+        if grid != tuple(model.grid_dim()):
+            raise L.CliftError(f"renderer.grid_dim {list(grid)} != model factor grid {model.grid_dim()}")
         return cfg
 
     @staticmethod
@@ -348,7 +413,7 @@ class TensoRFRenderer(nn.Module):
         if not rays.is_cuda:
             raise L.CliftError("rays must be a CUDA tensor: this renderer has no CPU path")
         rays = rays.detach().contiguous().float()
-        params = [p for _, p in tensorf.named_parameters()]
+        params = param_list(tensorf)
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         limit = ((1 << 31) - 1) // max(int(self.n_samples), 1)        # one C call handles n_rays*n_samples < 2^31
         if self.max_rays_per_call is not None:

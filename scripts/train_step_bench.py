@@ -201,6 +201,7 @@ def measure(steps=10, warmup=3, device_index=0, with_cpu=False, torch_adam=False
         losses = gpu_step(model, rend, opt_main, opt_ins, batch, arenas, timed=True)
     t1.record()
     torch.cuda.synchronize(dev)
+    rend.synchronize_overflow_checks()      # every render of the timed steps fitted its capacity (raises otherwise)
     ar_ms = [ar.drain_ms() for ar in arenas] if arenas is not None else [0.0, 0.0]
     ms = t0.elapsed_time(t1) / steps
     if distributed:

@@ -546,3 +546,44 @@ def test_data_gradient_engines_agree(name, monkeypatch):
     assert set(grads["0"]) == set(grads["1"]) and len(grads["0"]) > 10
     for k in grads["0"]:
         assert gpu.grad_close(grads["0"][k], grads["1"][k], "fma"), k
+
+
+@pytest.mark.gpu
+def test_training_renders_check_their_capacity_without_a_host_sync():
+    """Once a render with the same head set has been measured, a training render queues its stats record behind the
+    launch (deferred check): results equal the checked mode's, the record is read by a later call, and an overflow that
+    was found late raises there (and the following render is sized for it)."""
+    fx, params, cfg, rays, model, rend = case("render_a")
+    r = rays.cuda()
+    torch.manual_seed(5)
+    a = rend(model, r, 0.0, True, True)               # no history yet: verified before it returns
+    assert not rend._pending and rend._active_hist
+    b = rend(model, r, 0.0, True, True)               # deferred
+    assert len(rend._pending) == 1
+    for x, y in zip(a[:4], b[:4]):
+        assert torch.equal(x, y)
+    (b[0].sum() + b[1].sum()).backward()
+    g_def = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+    rend.synchronize_overflow_checks()
+    assert not rend._pending
+    model.zero_grad(set_to_none=True)
+    rend.deferred_overflow_check = False
+    c = rend(model, r, 0.0, True, True)
+    assert not rend._pending
+    (c[0].sum() + c[1].sum()).backward()
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert gpu.rel_err(g_def[n], p.grad) < 1e-5, n
+    # an overflow found late
+    rend.deferred_overflow_check = True
+    heads = rend._heads(model)
+    rend.max_active_per_ray = 1                        # room for one active sample per ray: the deferred render overflows
+    rend(model, r, 0.0, True, True)
+    torch.cuda.synchronize()
+    rend.max_active_per_ray = 192
+    with pytest.raises(L.CliftError, match="active samples but room for"):
+        rend(model, r, 0.0, True, True)
+    d = rend(model, r, 0.0, True, True)               # sized from the corrected history
+    rend.synchronize_overflow_checks()
+    for x, y in zip(a[:4], d[:4]):
+        assert torch.equal(x, y)
