@@ -35,6 +35,7 @@ static bool g_profile = false;
 static cudaEvent_t g_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // [5]: between the two head kernels
 static bool g_ev_valid = false;
 static bool g_ev_split = false;
+static int g_last_head_path = 0;     // clift_debug_last_head_path()
 
 static void profile_mark(int i, cudaStream_t stream) {
     if (g_profile && g_ev[i]) cudaEventRecord(g_ev[i], stream);
@@ -277,18 +278,20 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         if (cfg->head_path == CLIFT_HEADS_TENSOR || cfg->head_path == CLIFT_HEADS_TENSOR16) {
             CLIFT_CHECK_SUPPORTED(!save || (cfg->head_path == CLIFT_HEADS_TENSOR16 && tc16_train),
                                   "this tensor-core head path cannot record the training stash for this field (use CLIFT_HEADS_AUTO/FMA)");
-            CLIFT_CHECK_SUPPORTED(!grid_heads, "grid-mode semantic/instance heads run on the FP32-FMA kernels (use CLIFT_HEADS_AUTO/FMA)");
-            path = cfg->head_path;
+            // grid-mode heads exist on the fp16-split kernel only: _TENSOR means that kernel for them
+            path = grid_heads ? CLIFT_HEADS_TENSOR16 : cfg->head_path;
         } else if (cfg->head_path == CLIFT_HEADS_AUTO && save) {
             if (tc16_train) path = CLIFT_HEADS_TENSOR16;
-        } else if (cfg->head_path == CLIFT_HEADS_AUTO && !grid_heads) {
+        } else if (cfg->head_path == CLIFT_HEADS_AUTO) {
             if (heads_tc16_available(field, heads))
                 path = CLIFT_HEADS_TENSOR16;
-            else if (heads_tc_available(field, heads))
+            else if (!grid_heads && heads_tc_available(field, heads))
                 path = CLIFT_HEADS_TENSOR;
         }
-        const int xyz_heads = heads & (CLIFT_HEAD_SEMANTIC | CLIFT_HEAD_INSTANCE);
+        const int xyz_heads = grid_heads ? 0 : heads & (CLIFT_HEAD_SEMANTIC | CLIFT_HEAD_INSTANCE);
+        g_last_head_path = path;
         if (path == CLIFT_HEADS_TENSOR16 && xyz_heads && heads_x16_available(field, xyz_heads)) {
+            g_last_head_path = path | 16;
             // the xyz stacks on the pipelined kernel, the rgb stack (gather, basis, encoding) on the serial one; training
             // forwards record the stash from both
             rc = launch_heads_forward_x16(cfg, field, ws, max_active, n_rays, o_sem, o_ins, stream, save ? &lay : nullptr);
@@ -332,6 +335,8 @@ extern "C" int32_t clift_profile_stage_ms(float* ms4) {
     for (int i = 0; i < 4; ++i) CLIFT_CUDA(cudaEventElapsedTime(&ms4[i], g_ev[i], g_ev[i + 1]));
     return CLIFT_OK;
 }
+
+extern "C" int32_t clift_debug_last_head_path(void) { return g_last_head_path; }
 
 extern "C" int32_t clift_profile_heads_split_ms(float* ms2) {
     CLIFT_CHECK_ARG(ms2 != nullptr, "null pointer");

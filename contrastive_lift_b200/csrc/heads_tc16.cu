@@ -415,6 +415,8 @@ struct HeadsParams {
     long long cap;
     const float* rays;
     FactorParams app;
+    FactorParams semg, insg;    // grid-mode semantic / instance heads (comps == 0: MLP mode, the stack reads xyz): the stack's
+                                // first GEMM is then the bias-free basis Linear over the set's plane*line products
     int dim_app, pe_view, pe_feat, pe_sem, pe_ins;
     int n_cls, d_ins, slow_fast, softmax, use_sets;
     int n_gemms;
@@ -444,9 +446,11 @@ __device__ __forceinline__ void stamp(const HeadsParams& P, int tile_local, int 
 // hidden-layer epilogue: D (bias included) -> ReLU -> * e (rescale to the next layer's operand scale) -> fp16 pairs
 // `st_blk` (training): the stash block of the NEXT layer's input (st_rows rows); it gets the unscaled activation D * inv
 __device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0, float* v, float e, float* st_blk, int st_rows,
-                                           float inv) {
+                                           float inv, bool relu = true) {
+    if (relu) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+    }
     if (st_blk) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) st_blk[stash_idx(st_rows, c0 + i, r.row)] = v[i] * inv;
@@ -459,8 +463,10 @@ __device__ __forceinline__ void relu_put16(const Smem& s, const RowId& r, int c0
 // Streams the next layer's operand: round j = this thread's chunk of accumulator columns [48 j, 48 j + 48), i.e. K rows
 // (3 k-steps) of the next GEMM, which the MMA thread issues as soon as all 384 row threads have arrived on bar_a[j] - the
 // next layer's MMAs (into the other accumulator buffer) overlap the rest of this epilogue.
+// `relu` false: a basis Linear (grid-mode heads) - its output is the next layer's input as it is.
 __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, uint32_t d, const Gemm& g, float e, bool stream,
-                                                uint32_t leader_bar_a, float* st_blk = nullptr, int st_rows = 0, float inv = 0.0f) {
+                                                uint32_t leader_bar_a, float* st_blk = nullptr, int st_rows = 0, float inv = 0.0f,
+                                                bool relu = true) {
     const int n_pad = g.n_pad;
     const int rounds = (n_pad + kRoundCols - 1) / kRoundCols;
     const int c_begin = r.part * 16;
@@ -469,7 +475,7 @@ __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, u
             if (c0 < n_pad) {
                 float v[16];
                 ld_acc16(d, c0, n_pad, g.n_sets, v);
-                relu_put16(s, r, c0, v, e, st_blk, st_rows, inv);
+                relu_put16(s, r, c0, v, e, st_blk, st_rows, inv, relu);
             }
             if (stream) arrive_round(s, j, leader_bar_a);
         }
@@ -481,7 +487,7 @@ __device__ __forceinline__ void epilogue_hidden(const Smem& s, const RowId& r, u
             float v[16];
             tc::tmem_ld16(d + (uint32_t)c0, v);
             tc::tmem_wait_ld();
-            relu_put16(s, r, c0, v, e, st_blk, st_rows, inv);
+            relu_put16(s, r, c0, v, e, st_blk, st_rows, inv, relu);
         }
         if (stream) arrive_round(s, j, leader_bar_a);
     }
@@ -606,9 +612,10 @@ __device__ __forceinline__ void reduce_runs(const Smem& s, int rt, int nch, floa
 
 // all tap loads of one (record, mode) gather item in flight at once: NV x 4 plane taps (L2, the long latency) first, then
 // the line taps (L1-resident); out-of-range taps carry weight 0 and read a clamped (valid) texel
+// `c_off`: first channel of the NV x 16 handled by this call (sets wider than the register budget go in two calls)
 template <int NV>
 __device__ __forceinline__ void gather_item(const FactorParams& f, int mode, const float4& pm, int q, float ca, const Smem& s,
-                                            int m) {
+                                            int m, int c_off = 0) {
     const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
     const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
     const int W = f.pw[mode], H = f.ph[mode], Ln = f.ll[mode], C = f.comps;
@@ -617,12 +624,12 @@ __device__ __forceinline__ void gather_item(const FactorParams& f, int mode, con
     const int x0 = min(max(t2.x0, 0), W - 1), x1 = min(max(t2.x0 + 1, 0), W - 1);
     const int y0 = min(max(t2.y0, 0), H - 1), y1 = min(max(t2.y0 + 1, 0), H - 1);
     const int z0 = min(max(t1.z0, 0), Ln - 1), z1 = min(max(t1.z0 + 1, 0), Ln - 1);
-    const float* p00 = f.plane[mode] + ((int64_t)y0 * W + x0) * C + q * 4;
-    const float* p10 = f.plane[mode] + ((int64_t)y0 * W + x1) * C + q * 4;
-    const float* p01 = f.plane[mode] + ((int64_t)y1 * W + x0) * C + q * 4;
-    const float* p11 = f.plane[mode] + ((int64_t)y1 * W + x1) * C + q * 4;
-    const float* l0 = f.line[mode] + (int64_t)z0 * C + q * 4;
-    const float* l1 = f.line[mode] + (int64_t)z1 * C + q * 4;
+    const float* p00 = f.plane[mode] + ((int64_t)y0 * W + x0) * C + q * 4 + c_off;
+    const float* p10 = f.plane[mode] + ((int64_t)y0 * W + x1) * C + q * 4 + c_off;
+    const float* p01 = f.plane[mode] + ((int64_t)y1 * W + x0) * C + q * 4 + c_off;
+    const float* p11 = f.plane[mode] + ((int64_t)y1 * W + x1) * C + q * 4 + c_off;
+    const float* l0 = f.line[mode] + (int64_t)z0 * C + q * 4 + c_off;
+    const float* l1 = f.line[mode] + (int64_t)z1 * C + q * 4 + c_off;
     float4 a[NV], b[NV], c[NV], d[NV], u[NV], w[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -645,7 +652,7 @@ __device__ __forceinline__ void gather_item(const FactorParams& f, int mode, con
         fma4(pv, d[v], t2.w11);
         fma4(lv, u[v], t1.w0);
         fma4(lv, w[v], t1.w1);
-        const int k = mode * C + v * 16 + q * 4;      // multiple of 4
+        const int k = mode * C + c_off + v * 16 + q * 4;      // multiple of 4
         uint32_t h0, lo0, h1, lo1;
         split2(pv.x * lv.x * ca, pv.y * lv.y * ca, h0, lo0);
         split2(pv.z * lv.z * ca, pv.w * lv.w * ca, h1, lo1);
@@ -809,11 +816,29 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
                 for (int k = 3; k < 16; ++k) b[stash_idx(16, k, row)] = 0.0f;
             }
         };
-        auto run_hidden = [&](int n_layers, int id) {
+        // grid-mode head (tensoRF.py:72-85, 142-156): the stack's first operand = plane*line products of the head's own factor
+        // set, in quad layout like the burst form of the appearance gather (comps 64: two passes of 32 channels)
+        auto gather_set = [&](const FactorParams& f, float ca) {
+            const int q = r.rt & 3;
+            for (int item = r.rt >> 2; item < 3 * kRows; item += kRowThreads / 4) {
+                const int m = item / 3, mode = item - m * 3;
+                switch (f.comps) {
+                    case 16: gather_item<1>(f, mode, s.pos[m], q, ca, s, m); break;
+                    case 32: gather_item<2>(f, mode, s.pos[m], q, ca, s, m); break;
+                    case 48: gather_item<3>(f, mode, s.pos[m], q, ca, s, m); break;
+                    default:
+                        gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 0);
+                        gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 32);
+                        break;
+                }
+            }
+        };
+        // `basis_first`: GEMM 0 of the stack is a grid-mode head's basis Linear (no bias, no ReLU)
+        auto run_hidden = [&](int n_layers, int id, bool basis_first = false) {
             for (int l = 0; l + 1 < n_layers; ++l, ++gi) {
                 wait_d();
                 epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a, st_block(id, l + 1),
-                                P.g[gi].n_pad, s.sc[gi].y);
+                                P.g[gi].n_pad, s.sc[gi].y, !(basis_first && l == 0));
                 if (threadIdx.x == 64) stamp(P, tl, gi + 1, 1);
                 if (!prefetch && park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice(p);   // hides under that GEMM
                 if (prefetch && park_next < 2 * NV) park_slice(p_next);
@@ -860,10 +885,14 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             }
             gi = 0;
             if (P.n_sem > 0) {
-                build_xyz(s, r, p, P.pe_sem, s.sc[gi].x);
-                stash_xyz(0);
+                if (!kStash && P.semg.comps) {       // (training forwards of grid-mode heads run on the FMA kernel)
+                    gather_set(P.semg, s.sc[gi].x);
+                } else {
+                    build_xyz(s, r, p, P.pe_sem, s.sc[gi].x);
+                    stash_xyz(0);
+                }
                 publish(gi);
-                run_hidden(P.n_sem, 0);
+                run_hidden(P.n_sem, 0, !kStash && P.semg.comps != 0);
                 if (P.n_cls <= 32) {
                     epilogue_semantic32(s, r, d, P.n_cls, P.g[gi], P.softmax, p.w, s.sc[gi].y,
                                         kStash ? st + (size_t)P.lay.prob_off * kRows : nullptr);
@@ -892,10 +921,14 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             if (P.n_ins > 0) {
                 const int width = P.d_ins * (P.slow_fast ? 2 : 1);
                 for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
-                    build_xyz(s, r, p, P.pe_ins, s.sc[gi].x);
-                    stash_xyz(1 + net);
+                    if (!kStash && P.insg.comps) {        // fast and slow nets read the same basis feature (tensoRF.py:497-511)
+                        gather_set(P.insg, s.sc[gi].x);
+                    } else {
+                        build_xyz(s, r, p, P.pe_ins, s.sc[gi].x);
+                        stash_xyz(1 + net);
+                    }
                     publish(gi);
-                    run_hidden(P.n_ins, 1 + net);
+                    run_hidden(P.n_ins, 1 + net, !kStash && P.insg.comps != 0);
                     epilogue_final(s, r, d, P.d_ins, P.g[gi], s.sc[gi].y * p.w);
                     ++gi;
                     if (threadIdx.x == 64) stamp(P, tl, gi, 6);
@@ -1236,15 +1269,37 @@ static bool tc16_add_stack(HeadsParams& P, const clift_mlp& m) {
     return true;
 }
 
+// the bias-free basis Linear of a factor set (appearance, or a grid-mode head's own set) as the next GEMM of P
+static bool tc16_add_basis(HeadsParams& P, const void* basis_tc16, int comps, int dim) {
+    if (!basis_tc16 || P.n_gemms >= kMaxGemms) return false;
+    Gemm& g = P.g[P.n_gemms];
+    g.meta = reinterpret_cast<const float*>(basis_tc16);
+    g.w = reinterpret_cast<const __half*>(g.meta + kHeaderFloats);
+    g.k_steps = (int)ceil_div(3 * comps, kStepK);
+    g.n_pad = (int)round_up(dim, 32);
+    g.has_bias = 0;    // appearance_basis_mat / semantic_basis_mat / instance_basis_mat have bias=False (tensoRF.py:65,74,83)
+    g.w_pair = g.w + (size_t)g.k_steps * 2 * kStepK * g.n_pad;
+    g.a_rounds = 1;
+    g.n_sets = P.use_sets ? std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps)) : 1;
+    ++P.n_gemms;
+    return true;
+}
+
 bool heads_tc16_available(const clift_field* f, int heads) {
     auto ok = [](const clift_mlp& m) {
         for (int l = 0; l < m.n_layers; ++l)
             if (!m.w_tc16[l] || m.dims[l] > kMaxK || m.dims[l + 1] > 256) return false;
         return m.n_layers >= 1;
     };
+    // grid-mode head: fp16-split operand of its basis, factor set inside the gather's envelope
+    auto grid_ok = [](const clift_grid_head& g) {
+        return g.comps == 0 || (g.basis_tc16 && g.comps % 16 == 0 && 3 * g.comps <= kMaxK && g.dim <= 64);
+    };
     if (f->num_classes > CLIFT_MAX_HEAD_OUT || f->dim_instance > CLIFT_MAX_HEAD_OUT) return false;
-    if ((heads & CLIFT_HEAD_SEMANTIC) && !ok(f->semantic)) return false;
-    if ((heads & CLIFT_HEAD_INSTANCE) && (!ok(f->instance_fast) || (f->slow_fast && !ok(f->instance_slow)))) return false;
+    if ((heads & CLIFT_HEAD_SEMANTIC) && (!ok(f->semantic) || !grid_ok(f->semantic_grid))) return false;
+    if ((heads & CLIFT_HEAD_INSTANCE) &&
+        (!ok(f->instance_fast) || (f->slow_fast && !ok(f->instance_slow)) || !grid_ok(f->instance_grid)))
+        return false;
     if (heads & CLIFT_HEAD_RGB) {
         if (!ok(f->rgb) || !f->basis_tc16 || f->dim_appearance > 64 || f->appearance_comps % 16 || 3 * f->appearance_comps > kMaxK)
             return false;
@@ -1262,9 +1317,12 @@ bool heads_tc16_stash_ok(const clift_field* f, int heads) {
             if (m.dims[l] % 32) return false;
         return true;
     };
-    if ((heads & CLIFT_HEAD_SEMANTIC) && (f->pe_sem != 0 || f->num_classes > 32 || !hidden_ok(f->semantic))) return false;
+    // (grid-mode heads: the stash blocks of their factor products / basis outputs have writers in the FMA forward only)
+    if ((heads & CLIFT_HEAD_SEMANTIC) &&
+        (f->pe_sem != 0 || f->num_classes > 32 || !hidden_ok(f->semantic) || f->semantic_grid.comps))
+        return false;
     if ((heads & CLIFT_HEAD_INSTANCE) &&
-        (f->pe_ins != 0 || !hidden_ok(f->instance_fast) || (f->slow_fast && !hidden_ok(f->instance_slow))))
+        (f->pe_ins != 0 || !hidden_ok(f->instance_fast) || (f->slow_fast && !hidden_ok(f->instance_slow)) || f->instance_grid.comps))
         return false;
     if ((heads & CLIFT_HEAD_RGB) && !hidden_ok(f->rgb)) return false;
     const char* e = getenv("CLIFT_TRAIN_FWD_FMA");       // development switch: training forwards on the FP32-FMA kernel
@@ -1320,31 +1378,28 @@ int launch_heads_forward_tc16(const clift_render_cfg* cfg, const clift_field* fi
     }
     int heads = (sem_raw ? CLIFT_HEAD_SEMANTIC : 0) | (ins ? CLIFT_HEAD_INSTANCE : 0) | (rgb_raw ? CLIFT_HEAD_RGB : 0);
     bool ok = heads_tc16_available(field, heads) && (!lay || heads_tc16_stash_ok(field, heads));
+    // a grid-mode head's stack = [basis of its factor set, MLP layers]; n_sem / n_ins count the GEMMs of one stack
     if (ok && sem_raw) {
-        P.n_sem = field->semantic.n_layers;
+        const clift_grid_head& gh = field->semantic_grid;
+        P.n_sem = field->semantic.n_layers + (gh.comps ? 1 : 0);
+        if (gh.comps) {
+            P.semg = make_grid_factors(field, gh);
+            ok = ok && tc16_add_basis(P, gh.basis_tc16, gh.comps, gh.dim);
+        }
         ok = ok && tc16_add_stack(P, field->semantic);
     }
     if (ok && ins) {
-        P.n_ins = field->instance_fast.n_layers;
-        ok = ok && tc16_add_stack(P, field->instance_fast);
-        if (field->slow_fast) ok = ok && tc16_add_stack(P, field->instance_slow);
+        const clift_grid_head& gh = field->instance_grid;
+        P.n_ins = field->instance_fast.n_layers + (gh.comps ? 1 : 0);
+        if (gh.comps) P.insg = make_grid_factors(field, gh);
+        for (int net = 0; net < (field->slow_fast ? 2 : 1); ++net) {
+            if (gh.comps) ok = ok && tc16_add_basis(P, gh.basis_tc16, gh.comps, gh.dim);
+            ok = ok && tc16_add_stack(P, net == 0 ? field->instance_fast : field->instance_slow);
+        }
     }
     if (ok && rgb_raw) {
         P.n_rgb = field->rgb.n_layers;
-        if (P.n_gemms < kMaxGemms) {
-            Gemm& g = P.g[P.n_gemms];
-            g.meta = reinterpret_cast<const float*>(field->basis_tc16);
-            g.w = reinterpret_cast<const __half*>(g.meta + kHeaderFloats);
-            g.k_steps = (int)ceil_div(3 * field->appearance_comps, kStepK);
-            g.n_pad = (int)round_up(field->dim_appearance, 32);
-            g.has_bias = 0;    // appearance_basis_mat has bias=False (tensoRF.py:65)
-            g.w_pair = g.w + (size_t)g.k_steps * 2 * kStepK * g.n_pad;
-            g.a_rounds = 1;
-            g.n_sets = P.use_sets ? std::max(1, std::min(std::min(4, 128 / g.n_pad), g.k_steps)) : 1;
-            ++P.n_gemms;
-        } else {
-            ok = false;
-        }
+        ok = ok && tc16_add_basis(P, field->basis_tc16, field->appearance_comps, field->dim_appearance);
         ok = ok && tc16_add_stack(P, field->rgb);
     }
     if (!ok) {

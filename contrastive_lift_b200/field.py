@@ -595,6 +595,7 @@ class PackedField:
             self.grid_basis[name] = _PackedMlp([getattr(model, f"{name}_basis_mat")], dev)
         self.basis = _PackedMlp([model.appearance_basis_mat], dev)
         self.tc16_scratch = torch.zeros((8,), device=dev)
+        self.grid_scratch = {name: torch.zeros((8,), device=dev) for name in self.grid_basis}   # factor bounds of the grid sets
         self.rgb = _PackedMlp(_linears(model.render_appearance_mlp.mlp), dev)
         self.sem = _PackedMlp(_linears(model.render_semantic_mlp.mlp), dev)
         self.insf = _PackedMlp(_linears(model.render_instance_mlp.mlp), dev) if model.render_instance_mlp is not None else None
@@ -688,10 +689,24 @@ class PackedField:
         tc16 = L.Tc16Batch()          # chain 0: basis -> rgb stack; chains 1-3: the xyz stacks
         self.basis.pack(lib, st, training, self.tc16_scratch.data_ptr() + 24, 0.0, tc16, 0)
         self.rgb.pack(lib, st, training, self.basis.out_bound_ptr(), 1.0, tc16, 0)
+        # grid-mode heads: |plane*line| bound of the head's own factor set -> its basis -> the head's stack(s).  One CTA plans
+        # a chain in table order, so a basis sits in the SAME chain as the stacks that read its output bound (the instance
+        # basis feeds the fast and the slow net: both follow it in chain 2).
         for chain, (name, m) in enumerate((("semantic", self.sem), ("instance", self.insf), ("instance", self.inss)), start=1):
-            if m is not None:
-                # a grid-mode head's stack stays off the fp16-split operand chain (bound pointer -1): it runs on the FMA kernels
-                m.pack(lib, st, training, -1 if name in self.grid_basis else None, 1.0, tc16, chain)
+            if m is None:
+                continue
+            gb = self.grid_basis.get(name)
+            if gb is None:
+                m.pack(lib, st, training, None, 1.0, tc16, chain)          # MLP mode: xyz (+ sin/cos), |x| <= 1
+                continue
+            chain = 1 if name == "semantic" else 2
+            if m is not self.inss:
+                gp, gl = self.planes[name], self.lines[name]
+                L.check(lib.clift_tc16_factor_bound(vp3(*[L.ptr(t) for t in gp]), vp3(*[L.ptr(t) for t in gl]),
+                                                    i3(*[t.numel() for t in gp]), i3(*[t.numel() for t in gl]),
+                                                    L.ptr(self.grid_scratch[name]), st))
+                gb.pack(lib, st, training, self.grid_scratch[name].data_ptr() + 24, 0.0, tc16, chain)
+            m.pack(lib, st, training, gb.out_bound_ptr(), 0.0, tc16, chain)     # input = the basis feature
         if training:      # tensor-core data-gradient operands (W^T), one planning chain per stack
             for chain, m in enumerate((self.basis, self.rgb, self.sem, self.insf, self.inss), start=4):
                 if m is not None:
@@ -712,9 +727,9 @@ class PackedField:
         for name, gh in (("semantic", f.semantic_grid), ("instance", f.instance_grid)):
             if name in self.grid_basis:
                 gb = self.grid_basis[name]
-                gb.pack(lib, st, training, -1)
                 gh.basis = L.ptr(gb.wt[0])
                 gh.basis_dgrad = L.ptr(gb.w_dgrad[0])
+                gh.basis_tc16 = L.ptr(gb.w_tc16[0])
         f.basis = L.ptr(self.basis.wt[0])
         f.basis_dgrad = L.ptr(self.basis.w_dgrad[0])
         f.basis_tc = L.ptr(self.basis.w_tc[0])

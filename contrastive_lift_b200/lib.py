@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 MAX_LAYERS = 8
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 HEAD_RGB, HEAD_SEMANTIC, HEAD_INSTANCE, HEAD_ALL = 1, 2, 4, 7
 HEADS_AUTO, HEADS_FMA, HEADS_TENSOR, HEADS_TENSOR16 = 0, 1, 2, 3
@@ -35,7 +35,7 @@ class MlpGrad(C.Structure):
 
 class GridHead(C.Structure):
     _fields_ = [("comps", C.c_int32), ("dim", C.c_int32), ("plane", _vp * 3), ("line", _vp * 3), ("basis", _vp),
-                ("basis_dgrad", _vp)]
+                ("basis_dgrad", _vp), ("basis_tc16", _vp)]
 
 
 class GridHeadGrad(C.Structure):
@@ -109,6 +109,7 @@ SIGNATURES = {
     "clift_profile_enable": (C.c_int32, [C.c_int32]),
     "clift_profile_stage_ms": (C.c_int32, [_fp]),
     "clift_profile_heads_split_ms": (C.c_int32, [_fp]),
+    "clift_debug_last_head_path": (C.c_int32, []),
     "clift_pack_plane": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "clift_pack_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, _vp]),
     "clift_pack_linear_tc16_batch": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp]),

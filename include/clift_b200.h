@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define CLIFT_ABI_VERSION 12
+#define CLIFT_ABI_VERSION 13
 #define CLIFT_MAX_LAYERS 8
 #define CLIFT_MAX_WIDTH 256      /* widest MLP layer / widest head input */
 #define CLIFT_MAX_HEAD_OUT 64    /* semantic classes, and instance-embedding width per net */
@@ -81,6 +81,7 @@ typedef struct {
     const float* line[3];
     const float* basis;          /* clift_pack_linear() of the basis weight */
     const float* basis_dgrad;    /* clift_pack_linear_dgrad() of it (training only, else null) */
+    const void* basis_tc16;      /* clift_pack_linear_tc16() of it (tensor-core heads at inference, else null) */
 } clift_grid_head;
 
 typedef struct {
@@ -145,9 +146,11 @@ typedef struct {
 
 /* MLP-head implementation.  AUTO = tcgen05 tensor cores for inference - the fp16-split path (3 kind::f16 MMAs per
  * product, scaled operands, fp32-faithful) when the field carries w_tc16 operands, else the 3xTF32 path (w_tc) -
- * and FP32 FMA otherwise and always for save_for_backward forwards (they record the training stash).  Grid-mode
- * semantic / instance heads (clift_grid_head.comps > 0) run on the FP32-FMA kernels; asking for a tensor path
- * explicitly with such a head evaluated returns CLIFT_ERR_UNSUPPORTED. */
+ * and FP32 FMA otherwise.  save_for_backward forwards (they record the training stash) take the fp16-split path when every
+ * stash block has a writer there, else FP32 FMA.  Grid-mode semantic / instance heads (clift_grid_head.comps > 0): inference
+ * runs on the fp16-split tensor-core kernel (gather of the head's factor set -> basis GEMM -> MLP stack) when the head carries
+ * basis_tc16; for such heads _TENSOR means the same kernel (there is no 3xTF32 form of them) and training forwards run on
+ * the FP32-FMA kernel. */
 #define CLIFT_HEADS_AUTO 0
 #define CLIFT_HEADS_FMA 1
 #define CLIFT_HEADS_TENSOR 2
@@ -195,6 +198,10 @@ int32_t clift_profile_stage_ms(float* ms4);
 /* When the last profiled forward ran the heads as two kernels (pipelined xyz-stack kernel + rgb-stack kernel, the inference
  * default): their device times {xyz, rgb} in ms; {0, 0} when one kernel evaluated all heads. */
 int32_t clift_profile_heads_split_ms(float* ms2);
+/* Which head kernels the last clift_render_forward of this process chose: CLIFT_HEADS_FMA / _TENSOR / _TENSOR16, + 16 when
+ * the xyz stacks ran on the pipelined kernel (heads_x16) next to the fp16-split rgb kernel; 0 = none yet.  Tests use it to
+ * prove a configuration did not fall back to another path. */
+int32_t clift_debug_last_head_path(void);
 
 /* ---- layout packing (one transpose kernel; used for parameters and, inverted, for gradients) --- */
 /* (1,C,H,W) -> [H][W][C]  and back.   tensoRF.py:99-106 layouts. */

@@ -1,16 +1,17 @@
 """Summarise an ncu launch list (`ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file X.csv CMD`)
 into a per-kernel markdown table (launch count, total time, share) for profiles/.
 
-    python scripts/launch_summary.py gpurun_out/launches.csv profiles/r01_launches_x.md "title" ["note line"]
+    python scripts/launch_summary.py gpurun_out/launches.csv profiles/r01_launches_x.md "title" ["note line"] [--minus other.csv]
+
+``--minus other.csv``: subtract the launch list of a shorter run of the same command (setup launches cancel, what is left is
+the steady-state steps in between).
 """
 import csv
 import sys
 from collections import OrderedDict
 
 
-def main():
-    src, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
-    note = sys.argv[4] if len(sys.argv) > 4 else ""
+def aggregate(src):
     lines = [l for l in open(src, errors="replace") if not l.startswith("==")]
     rows = list(csv.reader(lines))
     hdr = rows[0]
@@ -24,6 +25,24 @@ def main():
         us = float(r[k_val].replace(",", "")) * scale.get(r[k_unit], 1.0)
         n, t = agg.get(r[k_name], (0, 0.0))
         agg[r[k_name]] = (n + 1, t + us)
+    return agg
+
+
+def main():
+    argv = list(sys.argv)
+    minus = None
+    if "--minus" in argv:
+        i = argv.index("--minus")
+        minus = argv[i + 1]
+        del argv[i:i + 2]
+    src, out, title = argv[1], argv[2], argv[3]
+    note = argv[4] if len(argv) > 4 else ""
+    agg = aggregate(src)
+    if minus:
+        for name, (n, t) in aggregate(minus).items():
+            n0, t0 = agg.get(name, (0, 0.0))
+            agg[name] = (n0 - n, t0 - t)
+        agg = OrderedDict((k, v) for k, v in agg.items() if v[0] > 0)
     total = sum(t for _, t in agg.values())
     md = [f"# {title}", ""]
     if note:

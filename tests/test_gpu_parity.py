@@ -98,14 +98,16 @@ def test_density_matches_reference(name):
 def test_render_inference_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
     rend.head_path = path
-    if name in gu.GRID_CASES and path != L.HEADS_FMA:
-        # grid-mode heads run on the FP32-FMA kernels: an explicit tensor path is refused, AUTO picks FMA
-        with pytest.raises(L.CliftError), torch.no_grad():
-            rend(model, rays.cuda(), 1.0, False, False)
-        rend.head_path = L.HEADS_AUTO
+    # grid-mode heads (render_d/e/f): HEADS_TENSOR16 = gather of the head's factor set -> basis GEMM -> MLP stack on the
+    # fp16-split tensor-core kernel; HEADS_TENSOR means the same kernel for them (no 3xTF32 form)
     with torch.no_grad():
         rgb, sem, ins, depth, feats, dist = rend(model, rays.cuda(), 1.0, False, False)
     assert feats.shape == (1, 1) and rgb.grad_fn is None
+    # the kernel that ran is the one asked for (grid-mode heads: _TENSOR = the fp16-split kernel; MLP-mode heads on
+    # _TENSOR16: xyz stacks on the pipelined kernel, flag 16)
+    ran = L.load().clift_debug_last_head_path()
+    want = L.HEADS_TENSOR16 if (name in gu.GRID_CASES and path == L.HEADS_TENSOR) else path
+    assert ran & 15 == want, (ran, want)
     n_act, n_in, overflow, _ = rend.last_stats("cuda:0")
     assert n_in == int(fx["inf_inbox"].sum()), "in-box sample count must be exact"
     flips = abs(n_act - int(fx["inf_active"].sum()))
@@ -175,7 +177,7 @@ def test_render_training_forward_rng_parity(name, tag, seed):
 @pytest.mark.parametrize("name", gu.RENDER_CASES)
 def test_instance_and_segment_golden(name, path):
     fx, params, cfg, rays, model, rend = case(name)
-    rend.head_path = L.HEADS_AUTO if name in gu.GRID_CASES and path != L.HEADS_FMA else path
+    rend.head_path = path
     with torch.no_grad():
         torch.manual_seed(11)
         ins, pts = rend.forward_instance_feature(model, rays.cuda(), 1.0, True)
