@@ -274,7 +274,7 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
         int path = CLIFT_HEADS_FMA;
         const bool grid_heads = ((heads & CLIFT_HEAD_SEMANTIC) && field->semantic_grid.comps) ||
                                 ((heads & CLIFT_HEAD_INSTANCE) && field->instance_grid.comps);
-        const bool tc16_train = save && !grid_heads && heads_tc16_available(field, heads) && heads_tc16_stash_ok(field, heads);
+        const bool tc16_train = save && heads_tc16_available(field, heads) && heads_tc16_stash_ok(field, heads);
         if (cfg->head_path == CLIFT_HEADS_TENSOR || cfg->head_path == CLIFT_HEADS_TENSOR16) {
             CLIFT_CHECK_SUPPORTED(!save || (cfg->head_path == CLIFT_HEADS_TENSOR16 && tc16_train),
                                   "this tensor-core head path cannot record the training stash for this field (use CLIFT_HEADS_AUTO/FMA)");

@@ -613,9 +613,10 @@ __device__ __forceinline__ void reduce_runs(const Smem& s, int rt, int nch, floa
 // all tap loads of one (record, mode) gather item in flight at once: NV x 4 plane taps (L2, the long latency) first, then
 // the line taps (L1-resident); out-of-range taps carry weight 0 and read a clamped (valid) texel
 // `c_off`: first channel of the NV x 16 handled by this call (sets wider than the register budget go in two calls)
+// `st` (training): stash block of 3*C rows that receives the unscaled products (the basis weight gradient reads them)
 template <int NV>
 __device__ __forceinline__ void gather_item(const FactorParams& f, int mode, const float4& pm, int q, float ca, const Smem& s,
-                                            int m, int c_off = 0) {
+                                            int m, int c_off = 0, float* st = nullptr) {
     const float c_a = mode == 2 ? pm.y : pm.x, c_b = mode == 0 ? pm.y : pm.z;
     const float c_v = mode == 0 ? pm.z : (mode == 1 ? pm.y : pm.x);
     const int W = f.pw[mode], H = f.ph[mode], Ln = f.ll[mode], C = f.comps;
@@ -653,6 +654,12 @@ __device__ __forceinline__ void gather_item(const FactorParams& f, int mode, con
         fma4(lv, u[v], t1.w0);
         fma4(lv, w[v], t1.w1);
         const int k = mode * C + c_off + v * 16 + q * 4;      // multiple of 4
+        if (st) {
+            st[stash_idx(3 * C, k, m)] = pv.x * lv.x;
+            st[stash_idx(3 * C, k + 1, m)] = pv.y * lv.y;
+            st[stash_idx(3 * C, k + 2, m)] = pv.z * lv.z;
+            st[stash_idx(3 * C, k + 3, m)] = pv.w * lv.w;
+        }
         uint32_t h0, lo0, h1, lo1;
         split2(pv.x * lv.x * ca, pv.y * lv.y * ca, h0, lo0);
         split2(pv.z * lv.z * ca, pv.w * lv.w * ca, h1, lo1);
@@ -818,17 +825,17 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         };
         // grid-mode head (tensoRF.py:72-85, 142-156): the stack's first operand = plane*line products of the head's own factor
         // set, in quad layout like the burst form of the appearance gather (comps 64: two passes of 32 channels)
-        auto gather_set = [&](const FactorParams& f, float ca) {
+        auto gather_set = [&](const FactorParams& f, float ca, float* st_prod) {
             const int q = r.rt & 3;
             for (int item = r.rt >> 2; item < 3 * kRows; item += kRowThreads / 4) {
                 const int m = item / 3, mode = item - m * 3;
                 switch (f.comps) {
-                    case 16: gather_item<1>(f, mode, s.pos[m], q, ca, s, m); break;
-                    case 32: gather_item<2>(f, mode, s.pos[m], q, ca, s, m); break;
-                    case 48: gather_item<3>(f, mode, s.pos[m], q, ca, s, m); break;
+                    case 16: gather_item<1>(f, mode, s.pos[m], q, ca, s, m, 0, st_prod); break;
+                    case 32: gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 0, st_prod); break;
+                    case 48: gather_item<3>(f, mode, s.pos[m], q, ca, s, m, 0, st_prod); break;
                     default:
-                        gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 0);
-                        gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 32);
+                        gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 0, st_prod);
+                        gather_item<2>(f, mode, s.pos[m], q, ca, s, m, 32, st_prod);
                         break;
                 }
             }
@@ -837,8 +844,9 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
         auto run_hidden = [&](int n_layers, int id, bool basis_first = false) {
             for (int l = 0; l + 1 < n_layers; ++l, ++gi) {
                 wait_d();
-                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a, st_block(id, l + 1),
-                                P.g[gi].n_pad, s.sc[gi].y, !(basis_first && l == 0));
+                // training: the epilogue of GEMM l writes the input of the NEXT Linear of stack `id` (the basis is not one)
+                epilogue_hidden(s, r, d, P.g[gi], s.sc[gi + 1].x * s.sc[gi].y, P.stream != 0, leader_bar_a,
+                                st_block(id, l + (basis_first ? 0 : 1)), P.g[gi].n_pad, s.sc[gi].y, !(basis_first && l == 0));
                 if (threadIdx.x == 64) stamp(P, tl, gi + 1, 1);
                 if (!prefetch && park_next < 2 * NV && P.g[gi + 1].k_steps >= 8 && P.g[gi + 1].n_pad > 128) park_slice(p);   // hides under that GEMM
                 if (prefetch && park_next < 2 * NV) park_slice(p_next);
@@ -885,14 +893,14 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             }
             gi = 0;
             if (P.n_sem > 0) {
-                if (!kStash && P.semg.comps) {       // (training forwards of grid-mode heads run on the FMA kernel)
-                    gather_set(P.semg, s.sc[gi].x);
+                if (P.semg.comps) {
+                    gather_set(P.semg, s.sc[gi].x, st_block(5, 0));
                 } else {
                     build_xyz(s, r, p, P.pe_sem, s.sc[gi].x);
                     stash_xyz(0);
                 }
                 publish(gi);
-                run_hidden(P.n_sem, 0, !kStash && P.semg.comps != 0);
+                run_hidden(P.n_sem, 0, P.semg.comps != 0);
                 if (P.n_cls <= 32) {
                     epilogue_semantic32(s, r, d, P.n_cls, P.g[gi], P.softmax, p.w, s.sc[gi].y,
                                         kStash ? st + (size_t)P.lay.prob_off * kRows : nullptr);
@@ -921,14 +929,14 @@ __global__ void __launch_bounds__(kThreads, 1) heads_tc16_forward_kernel(const _
             if (P.n_ins > 0) {
                 const int width = P.d_ins * (P.slow_fast ? 2 : 1);
                 for (int net = 0; net < (P.slow_fast ? 2 : 1); ++net) {
-                    if (!kStash && P.insg.comps) {        // fast and slow nets read the same basis feature (tensoRF.py:497-511)
-                        gather_set(P.insg, s.sc[gi].x);
+                    if (P.insg.comps) {        // fast and slow nets read the same basis feature (tensoRF.py:497-511)
+                        gather_set(P.insg, s.sc[gi].x, net == 0 ? st_block(6, 0) : nullptr);
                     } else {
                         build_xyz(s, r, p, P.pe_ins, s.sc[gi].x);
                         stash_xyz(1 + net);
                     }
                     publish(gi);
-                    run_hidden(P.n_ins, 1 + net, !kStash && P.insg.comps != 0);
+                    run_hidden(P.n_ins, 1 + net, P.insg.comps != 0);
                     epilogue_final(s, r, d, P.d_ins, P.g[gi], s.sc[gi].y * p.w);
                     ++gi;
                     if (threadIdx.x == 64) stamp(P, tl, gi, 6);
@@ -1317,12 +1325,14 @@ bool heads_tc16_stash_ok(const clift_field* f, int heads) {
             if (m.dims[l] % 32) return false;
         return true;
     };
-    // (grid-mode heads: the stash blocks of their factor products / basis outputs have writers in the FMA forward only)
+    // grid-mode heads: the basis output (accumulator columns, padded to 32) is the stash block of the MLP input (16-row pad)
+    auto grid_ok = [](const clift_grid_head& g) { return g.comps == 0 || round_up(g.dim, 16) == round_up(g.dim, 32); };
     if ((heads & CLIFT_HEAD_SEMANTIC) &&
-        (f->pe_sem != 0 || f->num_classes > 32 || !hidden_ok(f->semantic) || f->semantic_grid.comps))
+        ((f->pe_sem != 0 && !f->semantic_grid.comps) || f->num_classes > 32 || !hidden_ok(f->semantic) || !grid_ok(f->semantic_grid)))
         return false;
     if ((heads & CLIFT_HEAD_INSTANCE) &&
-        (f->pe_ins != 0 || !hidden_ok(f->instance_fast) || (f->slow_fast && !hidden_ok(f->instance_slow)) || f->instance_grid.comps))
+        ((f->pe_ins != 0 && !f->instance_grid.comps) || !hidden_ok(f->instance_fast) ||
+         (f->slow_fast && !hidden_ok(f->instance_slow)) || !grid_ok(f->instance_grid)))
         return false;
     if ((heads & CLIFT_HEAD_RGB) && !hidden_ok(f->rgb)) return false;
     const char* e = getenv("CLIFT_TRAIN_FWD_FMA");       // development switch: training forwards on the FP32-FMA kernel

@@ -81,7 +81,7 @@ typedef struct {
     const float* line[3];
     const float* basis;          /* clift_pack_linear() of the basis weight */
     const float* basis_dgrad;    /* clift_pack_linear_dgrad() of it (training only, else null) */
-    const void* basis_tc16;      /* clift_pack_linear_tc16() of it (tensor-core heads at inference, else null) */
+    const void* basis_tc16;      /* clift_pack_linear_tc16() of it (tensor-core heads, else null) */
 } clift_grid_head;
 
 typedef struct {
@@ -149,8 +149,7 @@ typedef struct {
  * and FP32 FMA otherwise.  save_for_backward forwards (they record the training stash) take the fp16-split path when every
  * stash block has a writer there, else FP32 FMA.  Grid-mode semantic / instance heads (clift_grid_head.comps > 0): inference
  * runs on the fp16-split tensor-core kernel (gather of the head's factor set -> basis GEMM -> MLP stack) when the head carries
- * basis_tc16; for such heads _TENSOR means the same kernel (there is no 3xTF32 form of them) and training forwards run on
- * the FP32-FMA kernel. */
+ * basis_tc16 (inference and training forwards); for such heads _TENSOR means the same kernel (there is no 3xTF32 form). */
 #define CLIFT_HEADS_AUTO 0
 #define CLIFT_HEADS_FMA 1
 #define CLIFT_HEADS_TENSOR 2

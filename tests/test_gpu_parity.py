@@ -194,12 +194,14 @@ def test_instance_and_segment_golden(name, path):
 @pytest.mark.parametrize("tag,seed", [("trn", 7), ("trn2", 8)])
 def test_render_training_gradients_golden(name, tag, seed, fwd, monkeypatch):
     """fwd: which kernel runs the training forward and records the stash (tcgen05 fp16-split by default, FP32 FMA with
-    CLIFT_TRAIN_FWD_FMA=1; grid-mode heads always FMA) - see gpu_util.grad_close for the two tolerances."""
+    CLIFT_TRAIN_FWD_FMA=1; grid-mode heads likewise) - see gpu_util.grad_close for the two tolerances."""
     monkeypatch.setenv("CLIFT_TRAIN_FWD_FMA", "1" if fwd == "fma" else "0")
     fx, params, cfg, rays, model, rend = case(name)
     torch.manual_seed(seed)
     out = rend(model, rays.cuda(), 1.0, False, True)
     assert out[0].grad_fn is not None and out[3].grad_fn is None       # depth carries no grad (renderer:173)
+    # the forward that recorded the stash ran where it was asked to (grid-mode heads included)
+    assert L.load().clift_debug_last_head_path() & 15 == (L.HEADS_TENSOR16 if fwd == "tc16" else L.HEADS_FMA)
     risk = gpu.flip_risk(params, cfg, rays, tn(fx[f"{tag}_jitter"]))
     if int((risk > 0).sum()) > 0:
         # A sample sitting on the activity threshold (|w - 1e-4| < 2e-7) may flip; in softmax mode its ray's semantic
