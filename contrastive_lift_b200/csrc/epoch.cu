@@ -19,8 +19,28 @@ struct AdamScalars {
     float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps, wd, grad_scale;
 };
 
+// Up to CLIFT_MAX_ADAM_GROUPS param groups in one launch: tensor blockIdx.y belongs to the group whose [first, first + count)
+// range holds it and is updated with that group's scalars.
+struct AdamGroups {
+    AdamScalars a[CLIFT_MAX_ADAM_GROUPS];
+    int first[CLIFT_MAX_ADAM_GROUPS + 1];      // first[n_groups] = n_tensors
+    int n_groups;
+};
+
+__device__ __forceinline__ void adam_update(const clift_adam_tensor& t, const AdamScalars& a);
+
 __global__ void __launch_bounds__(256) adam_kernel(const clift_adam_tensor* __restrict__ table, AdamScalars a) {
-    const clift_adam_tensor t = table[blockIdx.y];
+    adam_update(table[blockIdx.y], a);
+}
+
+__global__ void __launch_bounds__(256) adam_groups_kernel(const clift_adam_tensor* __restrict__ table,
+                                                          const __grid_constant__ AdamGroups G) {
+    int g = 0;
+    while (g + 1 < G.n_groups && (int)blockIdx.y >= G.first[g + 1]) ++g;
+    adam_update(table[blockIdx.y], G.a[g]);
+}
+
+__device__ __forceinline__ void adam_update(const clift_adam_tensor& t, const AdamScalars& a) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t n4 = ((reinterpret_cast<uintptr_t>(t.param) | reinterpret_cast<uintptr_t>(t.grad) |
                          reinterpret_cast<uintptr_t>(t.exp_avg) | reinterpret_cast<uintptr_t>(t.exp_avg_sq)) & 15) == 0
@@ -359,6 +379,41 @@ extern "C" int32_t clift_adam_step(const clift_adam_tensor* table_dev, int32_t n
     const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_n, 256 * 4), 4 * sm_count()));
     adam_kernel<<<dim3(gx, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(table_dev, a);
     CLIFT_AFTER_LAUNCH("adam_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_adam_step_groups(const clift_adam_tensor* table_dev, int32_t n_tensors, int64_t max_n,
+                                          const clift_adam_group* groups, int32_t n_groups, float grad_scale, void* stream) {
+    CLIFT_CHECK_ARG(n_tensors >= 0 && max_n >= 0 && n_groups >= 0, "negative size");
+    if (n_tensors == 0 || max_n == 0 || n_groups == 0) return CLIFT_OK;
+    CLIFT_CHECK_ARG(table_dev && groups, "null table");
+    CLIFT_CHECK_SUPPORTED(n_tensors <= 65535 && n_groups <= CLIFT_MAX_ADAM_GROUPS, "more than 65535 tensors or too many groups in one call");
+    AdamGroups G;
+    memset(&G, 0, sizeof(G));
+    G.n_groups = n_groups;
+    int next = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        const clift_adam_group& h = groups[g];
+        CLIFT_CHECK_ARG(h.step >= 1 && h.count >= 0 && h.first == next, "groups must tile the table in order, step >= 1");
+        next += h.count;
+        // scalars as torch computes them (Python doubles, then one rounding to fp32)
+        const double bc1 = 1.0 - pow((double)h.beta1, (double)h.step), bc2 = 1.0 - pow((double)h.beta2, (double)h.step);
+        AdamScalars& a = G.a[g];
+        a.one_minus_b1 = (float)(1.0 - (double)h.beta1);
+        a.b2 = h.beta2;
+        a.one_minus_b2 = (float)(1.0 - (double)h.beta2);
+        a.step_size = (float)((double)h.lr / bc1);
+        a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+        a.eps = h.eps;
+        a.wd = h.weight_decay;
+        a.grad_scale = grad_scale;
+        G.first[g] = h.first;
+    }
+    CLIFT_CHECK_ARG(next == n_tensors, "groups do not cover the table");
+    G.first[n_groups] = n_tensors;
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_n, 256 * 4), 4 * sm_count()));
+    adam_groups_kernel<<<dim3(gx, (unsigned)n_tensors), 256, 0, (cudaStream_t)stream>>>(table_dev, G);
+    CLIFT_AFTER_LAUNCH("adam_groups_kernel");
     return CLIFT_OK;
 }
 

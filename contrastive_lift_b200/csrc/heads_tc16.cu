@@ -144,7 +144,7 @@ __device__ __forceinline__ void relay(const Smem& s, const Gemm& g, PipeState& p
     const int steps = g.k_steps + g.has_bias;
     for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
         tc::mbar_wait(&s.full[ps.stage], ps.phase);
-        tc::mbar_arrive_cluster(leader_full_peer + 8u * (uint32_t)ps.stage);
+        tc::mbar_arrive_cluster_relaxed(leader_full_peer + 8u * (uint32_t)ps.stage);
     }
 }
 
@@ -196,10 +196,9 @@ __device__ __forceinline__ void issue(const Smem& s, const Gemm& gm, PipeState& 
     int rounds_seen = 0;
     auto need_round = [&](int r) {     // operand rounds 0..r written and published by every row thread
         while (rounds_seen <= r) {
-            if (kPair)
-                tc::mbar_wait_cluster(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
-            else
-                tc::mbar_wait(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
+            // (CTA pairs: CTA-scope wait + relaxed remote arrives, as in heads_x16.cu - each SM's tensor core reads its own
+            // CTA's operand rows, published there with fence.proxy.async; the cluster-scope forms cost ~1 K cycles per hand-off)
+            tc::mbar_wait(&s.bar_a[rounds_seen], (a_parity >> rounds_seen) & 1u);
             a_parity ^= 1u << rounds_seen;
             ++rounds_seen;
             tc::fence_after_sync();
@@ -211,7 +210,7 @@ __device__ __forceinline__ void issue(const Smem& s, const Gemm& gm, PipeState& 
     uint32_t set_off = 0u;
     for (int k0 = 0; k0 < steps; k0 += per, ps.advance()) {
         tc::mbar_wait(&s.full[ps.stage], ps.phase);
-        if (kPair) tc::mbar_wait_cluster(&s.full_peer[ps.stage], ps.phase);
+        if (kPair) tc::mbar_wait(&s.full_peer[ps.stage], ps.phase);
         tc::fence_after_sync();
         if (trace && k0 == 0) trace[5] = clock64();
         uint32_t w_lo = w_base + (uint32_t)ps.stage * kStage16;
@@ -296,7 +295,7 @@ __device__ __forceinline__ void arrive_round(const Smem& s, int r, uint32_t lead
     tc::fence_proxy_async_smem();
     tc::fence_before_sync();
     if (leader_bar_a)
-        tc::mbar_arrive_cluster(leader_bar_a + 8u * (uint32_t)r);
+        tc::mbar_arrive_cluster_relaxed(leader_bar_a + 8u * (uint32_t)r);
     else
         tc::mbar_arrive(&s.bar_a[r]);
 }
@@ -1247,6 +1246,25 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));
 }
 
+// the six factor tensors of a VM set in one launch: blockIdx.y = tensor, slot blockIdx.y of dst
+struct AbsmaxSix {
+    const float* x[6];
+    long long n[6];
+};
+__global__ void absmax6_kernel(const __grid_constant__ AbsmaxSix A, float* __restrict__ dst) {
+    const float* __restrict__ x = A.x[blockIdx.y];
+    const int64_t n = A.n[blockIdx.y];
+    float m = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(dst + blockIdx.y), __float_as_uint(m));
+}
+
 __global__ void factor_bound_kernel(float* __restrict__ scratch8) {   // [0..2] plane maxima, [3..5] line maxima -> [6]
     float b = 0.0f;
     for (int m = 0; m < 3; ++m) b = fmaxf(b, scratch8[m] * scratch8[3 + m]);
@@ -1500,15 +1518,19 @@ extern "C" int32_t clift_tc16_factor_bound(const float* const* planes3, const fl
     CLIFT_CHECK_ARG(planes3 && lines3 && plane_elems3 && line_elems3 && scratch8, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     CLIFT_CUDA(cudaMemsetAsync(scratch8, 0, 8 * sizeof(float), st));
+    AbsmaxSix A;
+    int64_t largest = 1;
     for (int m = 0; m < 3; ++m) {
         CLIFT_CHECK_ARG(planes3[m] && lines3[m] && plane_elems3[m] > 0 && line_elems3[m] > 0, "null factor or empty factor");
-        const int grid_p = (int)std::min<int64_t>(ceil_div(plane_elems3[m], 256 * 8), 4 * sm_count());
-        absmax_kernel<<<std::max(grid_p, 1), 256, 0, st>>>(planes3[m], plane_elems3[m], scratch8 + m);
-        CLIFT_AFTER_LAUNCH("absmax_kernel");
-        const int grid_l = (int)std::min<int64_t>(ceil_div(line_elems3[m], 256 * 8), 4 * sm_count());
-        absmax_kernel<<<std::max(grid_l, 1), 256, 0, st>>>(lines3[m], line_elems3[m], scratch8 + 3 + m);
-        CLIFT_AFTER_LAUNCH("absmax_kernel");
+        A.x[m] = planes3[m];
+        A.n[m] = plane_elems3[m];
+        A.x[3 + m] = lines3[m];
+        A.n[3 + m] = line_elems3[m];
+        largest = std::max<int64_t>(largest, std::max(plane_elems3[m], line_elems3[m]));
     }
+    const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(largest, 256 * 8), 2 * sm_count()));
+    absmax6_kernel<<<dim3((unsigned)gx, 6), 256, 0, st>>>(A, scratch8);      // slots 0-2 planes, 3-5 lines
+    CLIFT_AFTER_LAUNCH("absmax6_kernel");
     factor_bound_kernel<<<1, 1, 0, st>>>(scratch8);
     CLIFT_AFTER_LAUNCH("factor_bound_kernel");
     return CLIFT_OK;

@@ -316,12 +316,31 @@ __global__ void ema_kernel(float* __restrict__ slow, const float* __restrict__ f
     if (i < n) slow[i] = __fadd_rn(__fmul_rn(slow[i], m), __fmul_rn(om, fast[i]));   // mul_ then add_ of a scaled copy
 }
 
+// every (slow, fast) pair of a network in one launch: blockIdx.y = pair, same arithmetic as ema_kernel
+__global__ void ema_batch_kernel(const clift_ema_pair* __restrict__ table, float m, float om) {
+    const clift_ema_pair t = table[blockIdx.y];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (int64_t)gridDim.x * blockDim.x)
+        t.slow[i] = __fadd_rn(__fmul_rn(t.slow[i], m), __fmul_rn(om, t.fast[i]));
+}
+
 // One thread-block cluster of kTvCluster CTAs (fixed-order sum, no scratch memory, no atomics): every CTA reduces a strided
 // share of the plane, parks its two partial sums in its own shared memory, and rank 0 adds the partials in rank order through
 // distributed shared memory - run-to-run identical, 16x the bandwidth of a single CTA (one 128^2 x 48 plane: ~0.37 ms -> ~25 us).
 constexpr int kTvCluster = 16;
 
+__device__ __forceinline__ void tv_value_body(const float* __restrict__ x, int C, int H, int W, float* __restrict__ out);
+
 __global__ void __launch_bounds__(1024) tv_value_kernel(const float* __restrict__ x, int C, int H, int W, float* __restrict__ out) {
+    tv_value_body(x, C, H, W, out);
+}
+
+// clift_tv_loss_batch: cluster c of the grid reduces plane c of the table (same fixed-order sum per plane)
+__global__ void __launch_bounds__(1024) tv_value_batch_kernel(const clift_tv_job* __restrict__ jobs) {
+    const clift_tv_job j = jobs[blockIdx.x / kTvCluster];
+    if (j.loss) tv_value_body(j.plane_hwc, j.comps, j.h, j.w, j.loss);
+}
+
+__device__ __forceinline__ void tv_value_body(const float* __restrict__ x, int C, int H, int W, float* __restrict__ out) {
     __shared__ float s_red[33];
     __shared__ float s_part[2];
     const int64_t n = (int64_t)H * W * C;
@@ -359,9 +378,25 @@ __global__ void __launch_bounds__(1024) tv_value_kernel(const float* __restrict_
     cluster_sync_all();      // peers' shared memory stays alive until rank 0 has read it
 }
 
+__device__ __forceinline__ void tv_grad_body(const float* __restrict__ x, int C, int H, int W, float* __restrict__ g, float scale,
+                                             int64_t i);
+
 __global__ void __launch_bounds__(256) tv_grad_kernel(const float* __restrict__ x, int C, int H, int W, float* __restrict__ g,
                                                       float scale) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    tv_grad_body(x, C, H, W, g, scale, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// clift_tv_loss_batch: blockIdx.y = plane of the table, grid-stride over its elements
+__global__ void __launch_bounds__(256) tv_grad_batch_kernel(const clift_tv_job* __restrict__ jobs) {
+    const clift_tv_job j = jobs[blockIdx.y];
+    if (!j.grad_hwc) return;
+    const int64_t n = (int64_t)j.comps * j.h * j.w;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        tv_grad_body(j.plane_hwc, j.comps, j.h, j.w, j.grad_hwc, j.grad_scale, i);
+}
+
+__device__ __forceinline__ void tv_grad_body(const float* __restrict__ x, int C, int H, int W, float* __restrict__ g, float scale,
+                                             int64_t i) {
     if (i >= (int64_t)H * W * C) return;
     const int64_t pix = i / C;
     const int h = (int)(pix / W), w = (int)(pix - (int64_t)h * W);
@@ -444,6 +479,47 @@ extern "C" int32_t clift_ema_update(float* slow, const float* fast, int64_t n, d
     const float om = (float)(1.0 - momentum);
     ema_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(slow, fast, n, (float)momentum, om);
     CLIFT_AFTER_LAUNCH("ema_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_ema_update_batch(const clift_ema_pair* table_dev, int32_t n_pairs, int64_t max_n, double momentum,
+                                          void* stream) {
+    CLIFT_CHECK_ARG(n_pairs >= 0 && max_n >= 0, "negative size");
+    if (n_pairs == 0 || max_n == 0) return CLIFT_OK;
+    CLIFT_CHECK_ARG(table_dev != nullptr, "null table");
+    CLIFT_CHECK_SUPPORTED(n_pairs <= 65535, "more than 65535 pairs in one call");
+    const float om = (float)(1.0 - momentum);       // as clift_ema_update
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_n, 256), 4 * sm_count()));
+    ema_batch_kernel<<<dim3(gx, (unsigned)n_pairs), 256, 0, (cudaStream_t)stream>>>(table_dev, (float)momentum, om);
+    CLIFT_AFTER_LAUNCH("ema_batch_kernel");
+    return CLIFT_OK;
+}
+
+extern "C" int32_t clift_tv_loss_batch(const clift_tv_job* jobs_dev, int32_t n_jobs, int64_t max_n, void* stream) {
+    CLIFT_CHECK_ARG(n_jobs >= 0 && max_n >= 0, "negative size");
+    if (n_jobs == 0 || max_n == 0) return CLIFT_OK;
+    CLIFT_CHECK_ARG(jobs_dev != nullptr, "null table");
+    CLIFT_CHECK_SUPPORTED(n_jobs <= 4096, "more than 4096 planes in one call");
+    {
+        CLIFT_CUDA(cudaFuncSetAttribute(tv_value_batch_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)(kTvCluster * n_jobs));
+        lc.blockDim = dim3(1024);
+        lc.dynamicSmemBytes = 0;
+        lc.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kTvCluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        lc.attrs = attr;
+        lc.numAttrs = 1;
+        CLIFT_CUDA(cudaLaunchKernelEx(&lc, tv_value_batch_kernel, jobs_dev));
+        CLIFT_AFTER_LAUNCH("tv_value_batch_kernel");
+    }
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(max_n, 256), 4 * sm_count()));
+    tv_grad_batch_kernel<<<dim3(gx, (unsigned)n_jobs), 256, 0, (cudaStream_t)stream>>>(jobs_dev);
+    CLIFT_AFTER_LAUNCH("tv_grad_batch_kernel");
     return CLIFT_OK;
 }
 

@@ -197,6 +197,12 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* smem_ptr, uint32_t r
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(smem_ptr)), "r"(rank));
     return r;
 }
+// remote arrive without a cluster-scope release: for barriers that order tensor-core / TMA traffic on each CTA's OWN shared
+// and tensor memory (covered by fence.proxy.async and the tcgen05 fences on both sides), where no generic-proxy data crosses
+// the CTAs.  The release.cluster / acquire.cluster forms cost ~700-1000 cycles per hand-off (profiles/r02_x16_ab.md).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }

@@ -94,6 +94,23 @@ class AdamTensor(C.Structure):
     _fields_ = [("param", _vp), ("grad", _vp), ("exp_avg", _vp), ("exp_avg_sq", _vp), ("n", C.c_int64)]
 
 
+MAX_ADAM_GROUPS = 8
+
+
+class AdamGroup(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("first", C.c_int32), ("count", C.c_int32), ("reserved", C.c_int32), ("step", C.c_int64)]
+
+
+class EmaPair(C.Structure):
+    _fields_ = [("slow", _vp), ("fast", _vp), ("n", C.c_int64)]
+
+
+class TvJob(C.Structure):
+    _fields_ = [("plane_hwc", _vp), ("loss", _vp), ("grad_hwc", _vp), ("comps", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("grad_scale", C.c_float)]
+
+
 class CliftError(RuntimeError):
     pass
 
@@ -142,6 +159,9 @@ SIGNATURES = {
                                           C.POINTER(FieldGrad), _vp]),
     "clift_slowfast_loss": (C.c_int32, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "clift_ema_update": (C.c_int32, [_vp, _vp, C.c_int64, C.c_double, _vp]),
+    "clift_ema_update_batch": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_double, _vp]),
+    "clift_tv_loss_batch": (C.c_int32, [_vp, C.c_int32, C.c_int64, _vp]),
+    "clift_adam_step_groups": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.POINTER(AdamGroup), C.c_int32, C.c_float, _vp]),
     "clift_contrastive_loss": (C.c_int32, [_vp, _vp, C.c_int32, C.c_int32, C.c_float, _vp, _vp, _vp]),
     "clift_tv_loss": (C.c_int32, [_vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, C.c_float, _vp]),
     "clift_adam_step": (C.c_int32, [_vp, C.c_int32, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64,

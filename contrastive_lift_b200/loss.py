@@ -78,10 +78,27 @@ def contrastive_loss(features: torch.Tensor, instance_labels: torch.Tensor, temp
 def ema_update(slow_params: Iterable[torch.Tensor], fast_params: Iterable[torch.Tensor], momentum: float = 0.9) -> None:
     """param_k = param_k * momentum + (1 - momentum) * param_q for every pair (trainer:325-329)."""
     lib = L.load()
-    for q, k in zip(fast_params, slow_params):
-        with L.on(k.device):
-            L.check(lib.clift_ema_update(L.ptr(k.data), L.ptr(q.data), k.numel(), float(momentum), L.stream_ptr(k.device)))
+    pairs = [(k.data, q.data) for q, k in zip(fast_params, slow_params)]
+    if not pairs:
+        return
+    dev = pairs[0][0].device
+    if any(k.device != dev or q.device != dev for k, q in pairs):
+        raise L.CliftError("ema_update: slow and fast parameters must live on one CUDA device")
+    # one launch for all pairs; the device table is reused while the parameters keep their storage
+    key = tuple((L.ptr(k), L.ptr(q), k.numel()) for k, q in pairs)
+    cached = _EMA_TABLES.get(dev)
+    if cached is None or cached[0] != key:
+        rows = (L.EmaPair * len(key))()
+        for r, (pk, pq, n) in zip(rows, key):
+            r.slow, r.fast, r.n = pk, pq, n
+        table = torch.frombuffer(bytearray(bytes(rows)), dtype=torch.uint8).to(dev, non_blocking=True)
+        cached = _EMA_TABLES[dev] = (key, table, max(n for _, _, n in key))
+    with L.on(dev):
+        L.check(lib.clift_ema_update_batch(L.ptr(cached[1]), len(key), cached[2], float(momentum), L.stream_ptr(dev)))
     L.bump_param_epoch()     # parameters were mutated through raw pointers: packed copies are stale
+
+
+_EMA_TABLES: dict = {}
 
 
 def ema_update_slownet(slow_net: nn.Module, fast_net: nn.Module, momentum: float = 0.9) -> None:
@@ -139,9 +156,13 @@ class _TotalTV(torch.autograd.Function):
                 off += n
             batch.run(lib, dev)
             vals = torch.empty((len(srcs),), device=dev)
-            for i, (p, coef) in enumerate(zip(srcs, coefs)):
+            jobs = (L.TvJob * len(srcs))()              # all values in one launch, all gradients in another
+            for i, (j, p, coef) in enumerate(zip(jobs, srcs, coefs)):
                 _, c, h, w = p.shape
-                L.check(lib.clift_tv_loss(L.ptr(hwc[i]), c, h, w, vals.data_ptr() + 4 * i, L.ptr(g_hwc[i]), float(coef), st))
+                j.plane_hwc, j.loss, j.grad_hwc = L.ptr(hwc[i]), vals.data_ptr() + 4 * i, L.ptr(g_hwc[i])
+                j.comps, j.h, j.w, j.grad_scale = c, h, w, float(coef)
+            table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(dev, non_blocking=True)
+            L.check(lib.clift_tv_loss_batch(L.ptr(table), len(srcs), max(sizes), st))
             grads = [torch.empty_like(p) for p in srcs]
             batch = L.PackBatch()
             for p, g, gh in zip(srcs, grads, g_hwc):

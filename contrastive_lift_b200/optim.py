@@ -4,8 +4,8 @@ Drop-in for the ``torch.optim.Adam`` the reference builds in ``get_optimizer_and
 (trainer/__init__.py:134-139; groups from tensoRF.py:199-246, betas trainer:98-103): same constructor
 arguments, same ``param_groups`` keys and the same per-parameter state (``step``, ``exp_avg``, ``exp_avg_sq``),
 so ``state_dict()`` / ``load_state_dict()`` and LR schedulers are interchangeable with the stock optimizer
-and checkpoints keep their format.  ``step()`` issues ONE ``clift_adam_step`` launch per param group
-instead of a dozen ATen kernels per tensor.
+and checkpoints keep their format.  ``step()`` issues ONE ``clift_adam_step_groups`` launch for all param groups
+(up to 8 groups / step histories per launch) instead of a dozen ATen kernels per tensor.
 """
 from __future__ import annotations
 
@@ -37,6 +37,11 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         lib = L.load()
         keep: List[torch.Tensor] = []      # contiguous gradient copies stay alive until every launch of this step is enqueued
+        # segments of the launch under construction: (group, step count, first entry, number of entries); a segment ends when
+        # the param group, the step history or the device changes
+        self._entries: List[L.AdamTensor] = []
+        self._segments: list = []
+        self._max_n, self._device = 0, None
         for group in self.param_groups:
             entries: List[L.AdamTensor] = []
             step = None
@@ -69,20 +74,39 @@ class FusedAdam(torch.optim.Optimizer):
                 entries.append(e)
                 max_n = max(max_n, p.numel())
             self._launch(lib, entries, max_n, group, step, device)
+        self._flush(lib)
         # parameters were rewritten through raw pointers: autograd's version counters did not move, so cached packed copies
         # (PackedField.refresh) must be told (ema_update does the same)
         L.bump_param_epoch()
         return loss
 
     def _launch(self, lib, entries, max_n, group, step, device):
+        """Queue one (param group, step count) segment; the launch goes out when the table is full, the device changes, or
+        at the end of step()."""
         if not entries:
             return
+        if self._segments and (device != self._device or len(self._segments) == L.MAX_ADAM_GROUPS):
+            self._flush(lib)
+        self._device = device
+        self._segments.append((group, int(step), len(self._entries), len(entries)))
+        self._entries += entries
+        self._max_n = max(self._max_n, int(max_n))
+
+    def _flush(self, lib):
+        if not self._segments:
+            return
+        entries, device = self._entries, self._device
         raw = bytes((L.AdamTensor * len(entries))(*entries))
-        b1, b2 = group["betas"]
+        groups = (L.AdamGroup * len(self._segments))()
+        for g, (group, step, first, count) in zip(groups, self._segments):
+            b1, b2 = group["betas"]
+            g.lr, g.beta1, g.beta2, g.eps, g.weight_decay = float(group["lr"]), float(b1), float(b2), float(group["eps"]), \
+                float(group["weight_decay"])
+            g.first, g.count, g.step = first, count, step
         with L.on(device):
             table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
-            L.check(lib.clift_adam_step(L.ptr(table), len(entries), int(max_n), float(group["lr"]), float(b1), float(b2),
-                                        float(group["eps"]), float(group["weight_decay"]), int(step), self.grad_scale,
-                                        L.stream_ptr(device)))
+            L.check(lib.clift_adam_step_groups(L.ptr(table), len(entries), self._max_n, groups, len(self._segments),
+                                               self.grad_scale, L.stream_ptr(device)))
         # the caching allocator may not hand the table's block to another stream-ordered tensor before the launch ran:
         # same stream, so ordering holds without a record_stream
+        self._entries, self._segments, self._max_n = [], [], 0

@@ -354,12 +354,29 @@ int32_t clift_slowfast_loss(const float* features, const int64_t* labels, const 
 /* trainer:325-329: slow = slow*momentum + (1-momentum)*fast over a flat fp32 arena.  `momentum` is the Python
  * double: the reference rounds momentum and (1 - momentum) to fp32 separately, which needs the double here. */
 int32_t clift_ema_update(float* slow, const float* fast, int64_t n, double momentum, void* stream);
+/* Every (slow, fast) parameter pair of a network in ONE launch; `table` is a DEVICE array, max_n the largest n. */
+typedef struct {
+    float* slow;
+    const float* fast;
+    int64_t n;
+} clift_ema_pair;
+int32_t clift_ema_update_batch(const clift_ema_pair* table, int32_t n_pairs, int64_t max_n, double momentum, void* stream);
 /* ---- L2: model/loss/loss.py:62-82. features [N,D]. */
 int32_t clift_contrastive_loss(const float* features, const int64_t* labels, int32_t n, int32_t dim,
                                float temperature, float* loss, float* grad_features, void* stream);
 /* ---- TV: model/loss/loss.py:9-26 on a packed plane [H][W][C]; adds scale*dTV/dplane into grad (may be null). */
 int32_t clift_tv_loss(const float* plane_hwc, int32_t comps, int32_t h, int32_t w, float* loss,
                       float* grad_hwc, float grad_scale, void* stream);
+/* The same for a list of planes in two launches (all values, then all gradients); `jobs` is a DEVICE array, max_n the
+ * largest comps*h*w; a null loss / grad_hwc skips that half for the plane. */
+typedef struct {
+    const float* plane_hwc;
+    float* loss;
+    float* grad_hwc;
+    int32_t comps, h, w;
+    float grad_scale;
+} clift_tv_job;
+int32_t clift_tv_loss_batch(const clift_tv_job* jobs, int32_t n_jobs, int64_t max_n, void* stream);
 
 /* ---- torch.optim.Adam step (trainer/__init__.py:134-139; trainer:98-103,199,221), fused over a table
  * of tensors: ONE launch updates every parameter of a param group (amsgrad=False, maximize=False - the reference's use).
@@ -374,6 +391,18 @@ typedef struct {
 } clift_adam_tensor;
 int32_t clift_adam_step(const clift_adam_tensor* table, int32_t n_tensors, int64_t max_n, float lr, float beta1, float beta2,
                         float eps, float weight_decay, int64_t step, float grad_scale, void* stream);
+/* The same for several param groups (an optimizer's whole step) in ONE launch: `groups` is a HOST array of n_groups <=
+ * CLIFT_MAX_ADAM_GROUPS entries that tile the table in order (group g owns tensors [first, first + count)), each with its own
+ * hyper-parameters and step count. */
+#define CLIFT_MAX_ADAM_GROUPS 8
+typedef struct {
+    float lr, beta1, beta2, eps, weight_decay;
+    int32_t first, count;
+    int32_t reserved;
+    int64_t step;
+} clift_adam_group;
+int32_t clift_adam_step_groups(const clift_adam_tensor* table, int32_t n_tensors, int64_t max_n, const clift_adam_group* groups,
+                               int32_t n_groups, float grad_scale, void* stream);
 
 /* ---- epoch-boundary volume operations.
  * clift_dense_alpha  (renderer:717-729,744-748): alpha[i][j][k] = 1 - exp(-sigma(p_ijk) * cfg->step_size) at the lattice

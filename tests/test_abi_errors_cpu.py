@@ -155,6 +155,22 @@ def test_loss_ray_and_epoch_entries_validate_before_touching_the_device():
     assert lib.clift_ema_update(FAKE, FAKE, -1, 0.9, None) == ERR_ARG
     assert lib.clift_tv_loss(None, 16, 8, 8, FAKE, None, 1.0, None) == ERR_ARG
     assert lib.clift_tv_loss(FAKE, 16, 0, 8, FAKE, None, 1.0, None) == ERR_ARG
+    assert lib.clift_ema_update_batch(None, 3, 16, 0.9, None) == ERR_ARG
+    assert lib.clift_ema_update_batch(FAKE, -1, 16, 0.9, None) == ERR_ARG
+    assert lib.clift_ema_update_batch(None, 0, 0, 0.9, None) == 0                      # nothing to do
+    assert lib.clift_tv_loss_batch(None, 2, 64, None) == ERR_ARG
+    assert lib.clift_tv_loss_batch(FAKE, 5000, 64, None) == ERR_UNSUPPORTED
+    # grouped Adam: the groups must tile the table in order, with step >= 1, at most CLIFT_MAX_ADAM_GROUPS of them
+    grp = (L.AdamGroup * 2)()
+    grp[0].lr, grp[0].beta1, grp[0].beta2, grp[0].eps, grp[0].first, grp[0].count, grp[0].step = 0.01, 0.9, 0.99, 1e-8, 0, 2, 1
+    grp[1].lr, grp[1].beta1, grp[1].beta2, grp[1].eps, grp[1].first, grp[1].count, grp[1].step = 0.01, 0.9, 0.99, 1e-8, 2, 1, 1
+    assert lib.clift_adam_step_groups(None, 3, 16, grp, 2, 1.0, None) == ERR_ARG
+    assert lib.clift_adam_step_groups(FAKE, 4, 16, grp, 2, 1.0, None) == ERR_ARG and "cover" in err(lib)
+    grp[1].first = 1
+    assert lib.clift_adam_step_groups(FAKE, 3, 16, grp, 2, 1.0, None) == ERR_ARG and "tile" in err(lib)
+    grp[1].first, grp[1].step = 2, 0
+    assert lib.clift_adam_step_groups(FAKE, 3, 16, grp, 2, 1.0, None) == ERR_ARG
+    assert lib.clift_adam_step_groups(FAKE, 3, 16, grp, L.MAX_ADAM_GROUPS + 1, 1.0, None) == ERR_UNSUPPORTED
     # ray generation (util/ray.py): null camera, empty frame, misaligned output (one ray = two 16-byte stores)
     k = (C.c_float * 9)(*[1.0] * 9)
     pose = (C.c_float * 16)(*[0.0] * 16)

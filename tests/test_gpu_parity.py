@@ -509,7 +509,9 @@ def test_fused_march_emits_the_same_records_as_the_two_pass_form(monkeypatch):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("env", [{"CLIFT_X16_PAIR": "0"}, {"CLIFT_X16": "0"}], ids=["single_cta", "serial_kernel"])
+@pytest.mark.parametrize("env", [{"CLIFT_X16_PAIR": "0"}, {"CLIFT_X16": "0"}, {"CLIFT_TC16_PAIR": "1"},
+                                 {"CLIFT_X16": "0", "CLIFT_TC16_PAIR": "1"}],
+                         ids=["single_cta", "serial_kernel", "rgb_kernel_in_pairs", "serial_kernel_in_pairs"])
 def test_pipelined_xyz_kernel_variants_agree(env, monkeypatch):
     """CTA pairs (default) vs single CTAs vs round 1's serial kernel: the same fp16-split arithmetic in three schedules.
     Semantic / instance maps agree to 1e-6 of their scale (accumulation order inside a GEMM differs: two N = 128 units
