@@ -73,6 +73,7 @@ struct Smem {
 
 // state of the tensor-core dgrad engine; the counters are identical in every thread (uniform control flow)
 struct DgEngine {
+    bool mask_pass;          // ReLU masks in a pass of their own instead of inside the next emit pass
     unsigned char* a_op;     // [2][kDgABytes]
     unsigned char* w_ring;   // [kDgStages][kDgStageBytes]
     uint64_t* w_full;        // [kDgStages]
@@ -422,6 +423,7 @@ struct HeadsBwdParams {
     const float* basis_dgrad;
     const void* basis_dg16;           // tensor-core operand of the basis data gradient (null: FP32 FMA)
     int use_tc;                       // 1: data gradients with a w_dg16 operand run on tcgen05
+    int mask_pass;                    // 1: ReLU masks in a pass of their own (development switch CLIFT_BWD_MASK_PASS=1)
     int dim_app, pe_view, pe_feat;
     FactorParams semg, insg;          // grid-mode semantic / instance heads (comps == 0: MLP mode)
     float* g_semg_plane[3];
@@ -463,6 +465,43 @@ __device__ __forceinline__ void emit_dz(const Smem& sm, float* __restrict__ zdst
             if (lane == 0) atomicAdd(g_bias + row, s);
         }
     }
+}
+
+// emit_dz with the ReLU mask of the layer above folded in: act rows [0, rows_pad) hold dL/d(post-ReLU output) of this layer;
+// `a_src` = the A-stash block of that output (rows_pad rows, saved as the next layer's input): where it is <= 0 the gradient
+// is zeroed - in shared memory (the data-gradient GEMM reads it next), in the Z-stash and in the bias sums - in one pass
+// whose stash loads run four deep under the stores of the previous group.  Ends with the barrier the mask pass had.
+__device__ __forceinline__ void emit_dz_masked(const Smem& sm, float* __restrict__ zdst, int rows_pad, int n_out,
+                                               float* __restrict__ g_bias, const float* __restrict__ a_src) {
+    float4* d4 = reinterpret_cast<float4*>(zdst);
+    float4* s4 = reinterpret_cast<float4*>(sm.act);
+    const float4* a4 = reinterpret_cast<const float4*>(a_src);
+    const int lane = threadIdx.x & 31;
+    const int total = rows_pad * (kTile / 4);            // a multiple of 4 * kThreads for rows_pad in {64, 128, 256}
+    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kThreads) {
+        float4 a[4], v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads;
+            a[u] = __ldg(a4 + stash_idx4(rows_pad, i >> 5, i & 31));
+            v[u] = s4[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads, row = i >> 5;
+            v[u].x = a[u].x > 0.0f ? v[u].x : 0.0f;
+            v[u].y = a[u].y > 0.0f ? v[u].y : 0.0f;
+            v[u].z = a[u].z > 0.0f ? v[u].z : 0.0f;
+            v[u].w = a[u].w > 0.0f ? v[u].w : 0.0f;
+            s4[i] = v[u];
+            d4[stash_idx4(rows_pad, row, i & 31)] = v[u];
+            if (g_bias && row < n_out) {          // warp-uniform
+                const float s = warp_sum((v[u].x + v[u].y) + (v[u].z + v[u].w));
+                if (lane == 0) atomicAdd(g_bias + row, s);
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // dA[k][m] = sum_n W[n][k] dZ[n][m] with the clift_pack_linear_dgrad() operand ([up16(out)][dgrad_pad(in)])
@@ -630,9 +669,14 @@ __device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const 
 __device__ __forceinline__ void mlp_backward(const Smem& sm, DgEngine& E, const clift_mlp& mlp, const clift_mlp_grad& g,
                                              const float* stash_a, float* stash_z, const int* a_off, const int* z_off,
                                              bool need_input_grad) {
+    const float* mask_src = nullptr;      // A-stash block whose sign masks act; applied by the next layer's emit pass
     for (int l = mlp.n_layers - 1; l >= 0; --l) {
         const int n_out = mlp.dims[l + 1], n_in = mlp.dims[l];
-        emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
+        if (mask_src)
+            emit_dz_masked(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l], mask_src);
+        else
+            emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
+        mask_src = nullptr;
         if (l == 0 && !need_input_grad) break;
         // (folding the ReLU mask into run_dgrad_tc's accumulator read-back - its `mask` argument - was measured SLOWER:
         // 16 scalar stash loads per chunk and 32 more live registers cost more than the float4 mask pass below)
@@ -640,7 +684,12 @@ __device__ __forceinline__ void mlp_backward(const Smem& sm, DgEngine& E, const 
             run_dgrad_tc(sm, E, mlp.w_dg16[l], n_out, n_in, n_in <= 64 ? 64 : (n_in <= 128 ? 128 : 256));
         else
             run_dgrad(sm, mlp.w_dgrad[l], n_out, n_in);
-        if (l > 0) {   // ReLU mask from the saved input of layer l (= post-ReLU output of layer l-1)
+        // ReLU mask from the saved input of layer l (= post-ReLU output of layer l-1).  Hidden widths that are multiples of
+        // 64 (every shipped stack: 128 / 256): the stash block and the Z-stash block of layer l-1 have the same row count, so
+        // the mask rides in that layer's emit pass instead of a pass of its own
+        if (l > 0 && (n_in & 63) == 0 && !E.mask_pass) {
+            mask_src = stash_a + (size_t)a_off[l] * kTile;       // (both data-gradient forms end with a barrier)
+        } else if (l > 0) {
             const float4* a4 = reinterpret_cast<const float4*>(stash_a + (size_t)a_off[l] * kTile);
             float4* d4 = reinterpret_cast<float4*>(sm.act);
             const int rows = (n_in + 15) & ~15;
@@ -731,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
     // run at the same time), operand chunks, barriers, tensor memory
     DgEngine E;
     E.on = P.use_tc != 0;
+    E.mask_pass = P.mask_pass != 0;
     E.w_ring = reinterpret_cast<unsigned char*>(sm.wslab);
     {
         // layout after the FMA regions: [pos | ray | runs | dir] stay where they are; the engine's extra stage, operand
@@ -1217,6 +1267,8 @@ int launch_heads_backward(const clift_render_cfg* cfg, const clift_field* field,
     {   // development switch: CLIFT_DGRAD_FMA=1 keeps every data gradient on the FP32-FMA tile GEMM
         const char* e = getenv("CLIFT_DGRAD_FMA");
         P.use_tc = !(e && atoi(e) != 0);
+        const char* m = getenv("CLIFT_BWD_MASK_PASS");     // A/B of the mask fused into the emit pass (default) vs its own pass
+        P.mask_pass = (m && atoi(m) != 0) ? 1 : 0;
     }
     P.dim_app = field->dim_appearance;
     P.pe_view = field->pe_view;
