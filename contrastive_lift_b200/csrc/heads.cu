@@ -456,15 +456,37 @@ __device__ __forceinline__ void emit_dz(const Smem& sm, float* __restrict__ zdst
     float4* d4 = reinterpret_cast<float4*>(zdst);
     const float4* s4 = reinterpret_cast<const float4*>(sm.act);
     const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < rows_pad * (kTile / 4); i += kThreads) {
-        const int row = i >> 5;
-        const float4 v = s4[i];
-        d4[stash_idx4(rows_pad, row, i & 31)] = v;
-        if (g_bias && row < n_out) {          // warp-uniform
-            const float s = warp_sum((v.x + v.y) + (v.z + v.w));
-            if (lane == 0) atomicAdd(g_bias + row, s);
+    const int total = rows_pad * (kTile / 4);            // a multiple of 8 * kThreads for rows_pad in {64, 128, 256}
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * kThreads) {
+        float part[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * kThreads;
+            const float4 v = s4[i];
+            d4[stash_idx4(rows_pad, i >> 5, i & 31)] = v;
+            part[u] = (v.x + v.y) + (v.z + v.w);
+        }
+        if (g_bias) {      // the eight rows' lane trees side by side (same fixed order per row as warp_sum)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = (i0 + u * kThreads) >> 5;
+                if (lane == 0 && row < n_out) atomicAdd(g_bias + row, part[u]);
+            }
         }
     }
+}
+
+// the `rows` x 128 floats of a stash block -> L2 (one 128-byte line per request), issued before a data-gradient GEMM for the
+// block the pass after it reads: its loads then cost an L2 hit instead of a DRAM round trip
+__device__ __forceinline__ void prefetch_block(const float* __restrict__ blk, int rows) {
+    const char* p = reinterpret_cast<const char*>(blk);
+    const int lines = rows * kTile * 4 / 128;
+    for (int i = threadIdx.x; i < lines; i += kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)i * 128));
 }
 
 // emit_dz with the ReLU mask of the layer above folded in: act rows [0, rows_pad) hold dL/d(post-ReLU output) of this layer;
@@ -477,27 +499,37 @@ __device__ __forceinline__ void emit_dz_masked(const Smem& sm, float* __restrict
     float4* s4 = reinterpret_cast<float4*>(sm.act);
     const float4* a4 = reinterpret_cast<const float4*>(a_src);
     const int lane = threadIdx.x & 31;
-    const int total = rows_pad * (kTile / 4);            // a multiple of 4 * kThreads for rows_pad in {64, 128, 256}
-    for (int i0 = threadIdx.x; i0 < total; i0 += 4 * kThreads) {
-        float4 a[4], v[4];
+    const int total = rows_pad * (kTile / 4);            // a multiple of 8 * kThreads for rows_pad in {64, 128, 256}
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * kThreads) {
+        float4 a[8];                                     // eight stash loads in flight per thread (L2 hits: prefetch_block)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * kThreads;
             a[u] = __ldg(a4 + stash_idx4(rows_pad, i >> 5, i & 31));
-            v[u] = s4[i];
         }
+        float part[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * kThreads, row = i >> 5;
-            v[u].x = a[u].x > 0.0f ? v[u].x : 0.0f;
-            v[u].y = a[u].y > 0.0f ? v[u].y : 0.0f;
-            v[u].z = a[u].z > 0.0f ? v[u].z : 0.0f;
-            v[u].w = a[u].w > 0.0f ? v[u].w : 0.0f;
-            s4[i] = v[u];
-            d4[stash_idx4(rows_pad, row, i & 31)] = v[u];
-            if (g_bias && row < n_out) {          // warp-uniform
-                const float s = warp_sum((v[u].x + v[u].y) + (v[u].z + v[u].w));
-                if (lane == 0) atomicAdd(g_bias + row, s);
+            float4 v = s4[i];
+            v.x = a[u].x > 0.0f ? v.x : 0.0f;
+            v.y = a[u].y > 0.0f ? v.y : 0.0f;
+            v.z = a[u].z > 0.0f ? v.z : 0.0f;
+            v.w = a[u].w > 0.0f ? v.w : 0.0f;
+            s4[i] = v;
+            d4[stash_idx4(rows_pad, row, i & 31)] = v;
+            part[u] = (v.x + v.y) + (v.z + v.w);
+        }
+        if (g_bias) {      // the eight rows' lane trees side by side (same fixed order per row as warp_sum)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int row = (i0 + u * kThreads) >> 5;
+                if (lane == 0 && row < n_out) atomicAdd(g_bias + row, part[u]);
             }
         }
     }
@@ -678,6 +710,7 @@ __device__ __forceinline__ void mlp_backward(const Smem& sm, DgEngine& E, const 
             emit_dz(sm, stash_z + (size_t)z_off[l] * kTile, (n_out + 63) & ~63, n_out, g.bias[l]);
         mask_src = nullptr;
         if (l == 0 && !need_input_grad) break;
+        if (l > 0) prefetch_block(stash_a + (size_t)a_off[l] * kTile, (n_in + 15) & ~15);      // the mask this GEMM's output meets
         // (folding the ReLU mask into run_dgrad_tc's accumulator read-back - its `mask` argument - was measured SLOWER:
         // 16 scalar stash loads per chunk and 32 more live registers cost more than the float4 mask pass below)
         if (E.on && mlp.w_dg16[l])
