@@ -35,7 +35,9 @@ constexpr int kSlabRows = 16;
 // clift_pack_linear_tc16() slabs of W^T streamed by bulk TMA through a small ring, the accumulator lives in tensor memory.
 constexpr int kDgStages = 3;                 // weight ring depth (16 KB slabs: one k-step at N = 256)
 constexpr int kDgStageBytes = 16384;
-constexpr int kDgABytes = 8192;              // one operand chunk: [hi | lo][2 k-chunks][128 rows][8 halves]
+constexpr int kDgABytes = 8192;              // one k-step of the operand: [hi | lo][2 k-chunks][128 rows][8 halves]
+constexpr int kDgGroup = 2;                  // k-steps converted, published and issued per barrier (operand buffer = a group)
+constexpr int kDgBufBytes = kDgGroup * kDgABytes;
 constexpr uint32_t kDgTmemCols = 256;
 constexpr int kDgHeaderFloats = 16;          // header of a clift_pack_linear_tc16() operand
 
@@ -74,7 +76,7 @@ struct Smem {
 // state of the tensor-core dgrad engine; the counters are identical in every thread (uniform control flow)
 struct DgEngine {
     bool mask_pass;          // ReLU masks in a pass of their own instead of inside the next emit pass
-    unsigned char* a_op;     // [2][kDgABytes]
+    unsigned char* a_op;     // [2][kDgBufBytes]
     unsigned char* w_ring;   // [kDgStages][kDgStageBytes]
     uint64_t* w_full;        // [kDgStages]
     uint64_t* w_empty;       // [kDgStages]
@@ -89,11 +91,13 @@ struct DgEngine {
     bool on;
 };
 // the weight ring aliases the FMA path's two 16 KB cp.async slabs (the two engines never run at the same time) + one more
-constexpr size_t kDgExtraBytes = 1024 + (size_t)(kDgStages - 2) * kDgStageBytes + 2 * kDgABytes + (2 * kDgStages + 3) * 8 + 64;
+constexpr size_t kDgExtraBytes = 1024 + (size_t)(kDgStages - 2) * kDgStageBytes + 2 * kDgBufBytes + (2 * kDgStages + 3) * 8 + 64;
 static_assert(kDgStageBytes == kSlabRows * 256 * 4, "ring stage = one FMA weight slab");
 
 constexpr size_t kSmemBytes = (size_t)kActRows * kTile * 4 + 2 * kSlabRows * 256 * 4 + kTile * 16 + kTile * 4 +
                               (kTile + 4) * 4 + 3 * kTile * 4;
+
+static_assert(kSmemBytes + kDgExtraBytes <= 232448, "backward kernel: shared memory budget of one sm_100a CTA");
 
 // act[k][m] (all kpad rows valid) x W^T[k][n] -> act[n][m], bias, optional ReLU.  N = 64*NJ.
 template <int NJ>
@@ -604,11 +608,14 @@ __device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const 
         ++E.w_loads;
     }
     const int m = tid & (kTile - 1), c = tid >> 7;
-    for (int ks = 0; ks < k_steps; ++ks) {
-        const int b = ks & 1;
+    // kDgGroup k-steps per round: every thread converts its share of the group, one barrier publishes it, thread 0 issues the
+    // group's MMAs (its fixed issue cost - waits, descriptors, commits - and the barrier are paid per group, not per k-step)
+    for (int ks0 = 0; ks0 < k_steps; ks0 += kDgGroup) {
+        const int b = (ks0 / kDgGroup) & 1, ks1 = min(k_steps, ks0 + kDgGroup);
         if (E.a_fills[b] > 0) tc::mbar_wait(&E.a_free[b], (E.a_fills[b] - 1) & 1u);
         ++E.a_fills[b];
-        {   // records m, K rows [16 ks + 8 c, + 8) -> one 16-byte row of the hi chunk and one of the lo chunk
+        for (int ks = ks0; ks < ks1; ++ks) {
+            // records m, K rows [16 ks + 8 c, + 8) -> one 16-byte row of the hi chunk and one of the lo chunk
             const float* src = sm.act + (size_t)(ks * 16 + c * 8) * kTile + m;
             uint32_t h[4], l[4];
 #pragma unroll
@@ -619,42 +626,45 @@ __device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const 
                 h[i] = dg_bits(hh);
                 l[i] = dg_bits(__floats2half2_rn(x - back.x, y - back.y));
             }
-            unsigned char* dst = E.a_op + (size_t)b * kDgABytes + ((size_t)c * kTile + m) * 16;
+            unsigned char* dst = E.a_op + (size_t)b * kDgBufBytes + (size_t)(ks - ks0) * kDgABytes + ((size_t)c * kTile + m) * 16;
             *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
             *reinterpret_cast<uint4*>(dst + kDgABytes / 2) = make_uint4(l[0], l[1], l[2], l[3]);
         }
         tc::fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
-            const uint32_t st = E.w_used % kDgStages;
-            tc::mbar_wait(&E.w_full[st], (E.w_used / kDgStages) & 1u);
-            tc::fence_after_sync();
-            constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO 128 B, descriptor version 1
-            auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
-            const uint32_t a_lbo = (kTile * 16u >> 4) << 16;
-            const uint32_t ah = (tc::smem_addr(E.a_op + (size_t)b * kDgABytes) >> 4) | a_lbo;
-            const uint32_t al = (tc::smem_addr(E.a_op + (size_t)b * kDgABytes + kDgABytes / 2) >> 4) | a_lbo;
-            const uint32_t w_lo = tc::smem_addr(E.w_ring + (size_t)st * kDgStageBytes) >> 4;
-            const uint32_t rows1 = stacked ? 2u * n_pad : (uint32_t)n_pad;
-            const uint32_t idesc = tc::make_idesc_f16(kTile, n_pad);
-            const uint64_t b1 = desc(w_lo | (rows1 << 16));
-            const uint32_t acc = ks > 0 ? 1u : 0u;
-            if (stacked) {      // slab = [2 k-chunks][hi | lo][n_pad][8]: A_hi*[W_hi ; W_lo] in one MMA, then A_lo*W_hi
-                tc::mma_ss_f16(E.tmem, desc(ah), b1, tc::make_idesc_f16(kTile, 2 * n_pad), acc);
-                tc::mma_ss_f16(E.tmem, desc(al), b1, idesc, 1u);
-            } else {            // slab = [hi | lo][2 k-chunks][n_pad][8]
-                tc::mma_ss_f16(E.tmem, desc(ah), b1, idesc, acc);
-                tc::mma_ss_f16(E.tmem, desc(ah), desc((w_lo + 2u * rows1) | (rows1 << 16)), idesc, 1u);
-                tc::mma_ss_f16(E.tmem, desc(al), b1, idesc, 1u);
+        for (int ks = ks0; ks < ks1; ++ks) {        // every thread keeps the ring counters; thread 0 does the work
+            if (tid == 0) {
+                const uint32_t st = E.w_used % kDgStages;
+                tc::mbar_wait(&E.w_full[st], (E.w_used / kDgStages) & 1u);
+                tc::fence_after_sync();
+                constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO 128 B, descriptor version 1
+                auto desc = [](uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; };
+                const uint32_t a_lbo = (kTile * 16u >> 4) << 16;
+                const unsigned char* a_base = E.a_op + (size_t)b * kDgBufBytes + (size_t)(ks - ks0) * kDgABytes;
+                const uint32_t ah = (tc::smem_addr(a_base) >> 4) | a_lbo;
+                const uint32_t al = (tc::smem_addr(a_base + kDgABytes / 2) >> 4) | a_lbo;
+                const uint32_t w_lo = tc::smem_addr(E.w_ring + (size_t)st * kDgStageBytes) >> 4;
+                const uint32_t rows1 = stacked ? 2u * n_pad : (uint32_t)n_pad;
+                const uint32_t idesc = tc::make_idesc_f16(kTile, n_pad);
+                const uint64_t b1 = desc(w_lo | (rows1 << 16));
+                const uint32_t acc = ks > 0 ? 1u : 0u;
+                if (stacked) {      // slab = [2 k-chunks][hi | lo][n_pad][8]: A_hi*[W_hi ; W_lo] in one MMA, then A_lo*W_hi
+                    tc::mma_ss_f16(E.tmem, desc(ah), b1, tc::make_idesc_f16(kTile, 2 * n_pad), acc);
+                    tc::mma_ss_f16(E.tmem, desc(al), b1, idesc, 1u);
+                } else {            // slab = [hi | lo][2 k-chunks][n_pad][8]
+                    tc::mma_ss_f16(E.tmem, desc(ah), b1, idesc, acc);
+                    tc::mma_ss_f16(E.tmem, desc(ah), desc((w_lo + 2u * rows1) | (rows1 << 16)), idesc, 1u);
+                    tc::mma_ss_f16(E.tmem, desc(al), b1, idesc, 1u);
+                }
+                tc::mma_commit(&E.w_empty[st]);
+                if (ks == ks1 - 1) tc::mma_commit(&E.a_free[b]);
+                if (ks == k_steps - 1) tc::mma_commit(E.d_done);
+                // refill one k-step late: the stage of slab ks - 1 is free (or about to be) while this k-step's MMAs run
+                if (ks >= 1 && ks - 1 + n_pre < k_steps) dg_load(E, slabs, slab_bytes, ks - 1 + n_pre);
             }
-            tc::mma_commit(&E.w_empty[st]);
-            tc::mma_commit(&E.a_free[b]);
-            if (ks == k_steps - 1) tc::mma_commit(E.d_done);
-            // refill one k-step late: the stage of slab ks - 1 is free (or about to be) while this k-step's MMAs run
-            if (ks >= 1 && ks - 1 + n_pre < k_steps) dg_load(E, slabs, slab_bytes, ks - 1 + n_pre);
+            ++E.w_used;
+            if (ks >= 1 && ks - 1 + n_pre < k_steps) ++E.w_loads;
         }
-        ++E.w_used;
-        if (ks >= 1 && ks - 1 + n_pre < k_steps) ++E.w_loads;
     }
     const int q = warp & 3, mrow = q * 32 + lane;
     float mk_next[16];
@@ -822,7 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
         p = (p + 1023) & ~(uintptr_t)1023;
         unsigned char* q = reinterpret_cast<unsigned char*>(p);
         E.a_op = q;
-        q += 2 * kDgABytes;
+        q += 2 * kDgBufBytes;
         E.w_full = reinterpret_cast<uint64_t*>(q);
         E.w_empty = E.w_full + kDgStages;
         E.a_free = E.w_empty + kDgStages;
