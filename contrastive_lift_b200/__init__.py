@@ -5,7 +5,7 @@ Public surface = the reference's own class/function names for that path (SURVEY.
     TensorVMSplit, TensoRFRenderer                      model + renderer drop-ins
     slow_fast_loss, contrastive_loss, ema_update, TVLoss    loss drop-ins
     get_rays                                            per-frame ray generation
-    FusedAdam                                           torch.optim.Adam drop-in, one launch per param group (8f rank 2)
+    FusedAdam                                           torch.optim.Adam drop-in, one launch per optimizer step (8f rank 2)
     nearest_centroid, assign_clusters                   embedding -> centroid labels at inference (8f rank 4)
 
 Everything computes inside ``libclift_b200.so`` (C ABI in include/clift_b200.h); importing the package
