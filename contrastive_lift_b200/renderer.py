@@ -257,6 +257,14 @@ class TensoRFRenderer(nn.Module):
         self.max_rays_per_call = None
         self.update_step_size(self.grid_dim)
 
+    def __getstate__(self):
+        # copy.deepcopy / pickle (ddp_spawn, checkpointing the module object): outstanding capacity checks hold CUDA events and
+        # pinned buffers of THIS process - a copy starts with none (the capacity history, plain numbers, travels)
+        state = self.__dict__.copy()
+        state["_pending"] = collections.deque()
+        state["_pinned"] = []
+        return state
+
     # ---- renderer:59-78 ---------------------------------------------------------------------------
     # update_step_size / update_step_ratio / get_target_resolution and the host half of update_bbox_aabb_and_shrink below are
     # deliberate TRANSCRIPTIONS of the reference's host-side bookkeeping (renderer:59-78, 683-713, 756-761): step size, sample

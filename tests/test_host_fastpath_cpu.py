@@ -99,3 +99,16 @@ def test_deferred_overflow_is_reported_by_a_later_call():
     with pytest.warns(RuntimeWarning, match="5000 active samples"):
         r._poll_overflow()
     assert r._active_hist[3] == pytest.approx(50.0)
+
+
+def test_a_copied_renderer_starts_without_outstanding_checks():
+    import copy
+    import pickle
+    r = _renderer()
+    r._note_active(3, 1000, 100)
+    r._pending = collections.deque([(_Event(False), torch.zeros(4, dtype=torch.int64), 100, 1500, 3)])
+    r._pinned = [torch.zeros(4, dtype=torch.int64)]
+    for twin in (copy.deepcopy(r), pickle.loads(pickle.dumps(r))):
+        assert not twin._pending and not twin._pinned and twin._active_hist == {3: 10.0}
+        assert torch.equal(twin.bbox_aabb, r.bbox_aabb) and twin.n_samples == r.n_samples
+    assert len(r._pending) == 1          # the original keeps its own
