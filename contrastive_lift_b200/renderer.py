@@ -76,6 +76,12 @@ class _Render(torch.autograd.Function):
         cap = renderer.max_active(B, need_grad, heads)
         # training renders with a capacity history verify the capacity WITHOUT stalling the host (see _defer_overflow_check)
         deferred = need_grad and renderer.deferred_overflow_check and heads in renderer._active_hist
+        # small inference calls (the reference's chunk loop: 2048 rays per call, render_panopli.py:108-121) get room for
+        # EVERY sample (24 bytes each): nothing can overflow, so there is nothing to read back and the loop never waits
+        exact = (not need_grad and renderer.check_overflow and renderer.max_active_per_ray > 0
+                 and B * int(renderer.n_samples) * 24 <= renderer.worst_case_capacity_bytes)
+        if exact:
+            cap = 0
         while True:
             nbytes = lib.clift_render_workspace_bytes(C.byref(cfg), C.byref(pk.field), B, cap, out.save_for_backward)
             if nbytes < 0:
@@ -89,7 +95,7 @@ class _Render(torch.autograd.Function):
                 ws = _workspace(dev, nbytes)
             L.check(lib.clift_render_forward(C.byref(cfg), C.byref(pk.field), L.ptr(rays), L.ptr(jitter), B, int(add_bg),
                                              L.ptr(ws), ws.numel(), cap, C.byref(out), L.stream_ptr(dev)))
-            if B == 0 or not renderer.check_overflow:
+            if B == 0 or not renderer.check_overflow or exact:
                 break
             if deferred:
                 renderer._defer_overflow_check(ws, B, cap, heads)
@@ -244,6 +250,8 @@ class TensoRFRenderer(nn.Module):
         # overflow repeats the call at the exact size.
         self.deferred_overflow_check = True
         self.overflow_policy = "raise"
+        # inference calls whose worst case (every sample active) fits this many bytes of records skip the check altogether
+        self.worst_case_capacity_bytes = 1 << 30
         self._active_hist = {}            # head set -> decayed maximum of active samples per ray
         self._pending = collections.deque()
         self._pinned = []

@@ -345,10 +345,23 @@ def test_active_list_overflow_is_reported():
     assert overflow == 1 and n_act > rays.shape[0]
     # with the check on, the shim repeats the call at the exact size and the result is the full one
     rend.check_overflow = True
+    rend.worst_case_capacity_bytes = 0                 # (force the checked path: a call this small would get room for everything)
     with torch.no_grad():
         out = rend(model, rays.cuda(), 1.0, False, False)
     assert rend.last_stats("cuda:0")[2] == 0
     assert gpu.rel_err(out[0], tn(fx["inf_rgb"])) < REL
+    # default: small inference calls get room for every sample - no overflow possible, nothing read back
+    rend.worst_case_capacity_bytes = 1 << 30
+    launches = L.load().clift_launch_count()
+    with torch.no_grad():
+        out2 = rend(model, rays.cuda(), 1.0, False, False)
+    once = L.load().clift_launch_count() - launches
+    assert rend.last_stats("cuda:0")[2] == 0 and torch.equal(out2[0], out[0])
+    rend.worst_case_capacity_bytes = 0
+    launches = L.load().clift_launch_count()
+    with torch.no_grad():
+        rend(model, rays.cuda(), 1.0, False, False)
+    assert L.load().clift_launch_count() - launches > once      # capacity 1 per ray: overflow, the call ran twice
 
 
 @pytest.mark.parametrize("path", [L.HEADS_FMA, L.HEADS_TENSOR, L.HEADS_TENSOR16], ids=["fma", "tcgen05", "tcgen05_f16"])
