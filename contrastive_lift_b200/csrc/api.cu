@@ -239,10 +239,11 @@ extern "C" int32_t clift_render_forward(const clift_render_cfg* cfg, const clift
     M.rec_ray = ws.rec_ray;
     M.rec_idx = ws.rec_idx;
     M.cap = max_active;
-    // inference: the march emits the active-sample records itself (no dense [B,S] weights, no scan / fill launches); the
-    // per-group scan state lives in the (then unused) offset array.  Training and callers that ask for the dense weights
-    // keep the two-pass form.  CLIFT_MARCH_FUSED=0: development switch back to the two-pass form.
-    bool fused = heads && !save && !out->weights && (int64_t)round_up(cfg->n_samples, 32) * 8 * 4 <= 96 * 1024;
+    // the march emits the active-sample records itself (no dense [B,S] weights, no scan / fill launches); the per-group scan
+    // state lives in the (then unused) offset array.  Training forwards additionally write sigma and T of the in-box samples
+    // for the march backward.  Callers that ask for the dense weights keep the two-pass form.  CLIFT_MARCH_FUSED=0:
+    // development switch back to the two-pass form.
+    bool fused = heads && !out->weights && (int64_t)round_up(cfg->n_samples, 32) * 8 * 4 <= 96 * 1024;
     {
         const char* e = getenv("CLIFT_MARCH_FUSED");
         if (e && atoi(e) == 0) fused = false;

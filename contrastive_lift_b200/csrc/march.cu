@@ -169,6 +169,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) march_kernel(const __grid_c
             }
             if (kFused) {
                 wst[i] = w;
+                if (valid && P.sigma_dense) {       // training: the march backward reads sigma and T of every in-box sample
+                    P.sigma_dense[ray * S + i] = sigma_out;
+                    P.trans_dense[ray * S + i] = trans_out;
+                }
             } else if (valid) {
                 wrow[i] = w;
                 if (P.sigma_dense) {
