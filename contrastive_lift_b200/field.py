@@ -578,6 +578,7 @@ class PackedField:
         self.model_params = list(model.parameters())
         self.param_names = [n for n, _ in model.named_parameters()]
         self.plans: Dict[bool, _PackPlan] = {}
+        self.unpack_plans: dict = {}          # renderer._UnpackPlan per combination of flowing gradients
         mk = lambda plist: [torch.empty((p.shape[2], p.shape[3], p.shape[1]), device=dev) for p in plist]
         mkl = lambda plist: [torch.empty((p.shape[2], p.shape[1]), device=dev) for p in plist]
         self.planes = {"density": mk(model.density_plane), "appearance": mk(model.appearance_plane)}

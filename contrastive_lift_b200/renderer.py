@@ -161,7 +161,14 @@ class _Render(torch.autograd.Function):
                                           C.byref(fg), L.stream_ptr(dev)))
         ctx.ws = None        # consumed
         st = L.stream_ptr(dev)
-        batch = L.PackBatch()        # every gradient goes back to checkpoint layout in one launch
+        # every gradient goes back to checkpoint layout in one launch.  The job list depends only on which gradients flow, so
+        # it is built once per combination and replayed into one flat buffer afterwards (_UnpackPlan)
+        plan_key = (want_density, g_rgb is not None, g_sem is not None, g_ins is not None)
+        plan = pk.unpack_plans.get(plan_key)
+        if plan is not None:
+            grads = plan.run(lib, dev)
+            return (None,) * 8 + tuple(grads.get(n) for n in ctx.param_names)
+        batch = L.PackBatch()
         grads = {}
         if want_density:
             gp, gl = pk.unpack_factor_grads("density", batch)
@@ -189,8 +196,42 @@ class _Render(torch.autograd.Function):
             if pk.inss is not None:
                 for n, g in zip(_mlp_names("render_instance_mlp.slow_mlp", pk.inss), pk.inss.unpack_grads(lib, st, batch)):
                     grads[n] = g
+        pk.unpack_plans[plan_key] = _UnpackPlan(batch, grads)
         batch.run(lib, dev)
         return (None,) * 8 + tuple(grads.get(n) for n in ctx.param_names)
+
+
+class _UnpackPlan:
+    """The layout jobs that bring one combination of gradients back to checkpoint layout, with every destination expressed as
+    an offset into ONE flat buffer: a later backward allocates that buffer, views it per parameter and launches the cached
+    job table (one table per buffer address the caching allocator hands out) instead of ~45 allocations and job
+    descriptors."""
+
+    def __init__(self, batch: "L.PackBatch", grads):
+        self.items, offset_of, off = [], {}, 0
+        for name, g in grads.items():
+            self.items.append((name, tuple(g.shape), g.numel(), off))
+            offset_of[g.data_ptr()] = off * 4
+            off += (g.numel() + 63) // 64 * 64                   # 256-byte aligned slots
+        self.total = off
+        self.jobs = [(j, offset_of[j.dst]) for j in batch.jobs]  # (descriptor with the planning run's dst, byte offset)
+        self.tiles = int(batch.tiles)
+        self.tables = {}
+
+    def run(self, lib, dev):
+        flat = torch.empty((self.total,), device=dev, dtype=torch.float32)
+        base = flat.data_ptr()
+        table = self.tables.get(base)
+        if table is None:
+            if len(self.tables) >= 8:
+                self.tables.clear()
+            rows = (L.PackJob * len(self.jobs))()
+            for r, (j, off) in zip(rows, self.jobs):
+                C.memmove(C.byref(r), C.byref(j), C.sizeof(L.PackJob))
+                r.dst = base + off
+            table = self.tables[base] = torch.frombuffer(bytearray(bytes(rows)), dtype=torch.uint8).to(dev, non_blocking=True)
+        L.check(lib.clift_pack_batch(L.ptr(table), len(self.jobs), self.tiles, L.stream_ptr(dev)))
+        return {name: flat[off:off + n].view(shape) for name, shape, n, off in self.items}
 
 
 def _tensor_key(t: torch.Tensor):

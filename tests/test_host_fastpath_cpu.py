@@ -112,3 +112,23 @@ def test_a_copied_renderer_starts_without_outstanding_checks():
         assert not twin._pending and not twin._pinned and twin._active_hist == {3: 10.0}
         assert torch.equal(twin.bbox_aabb, r.bbox_aabb) and twin.n_samples == r.n_samples
     assert len(r._pending) == 1          # the original keeps its own
+
+
+def test_unpack_plan_lays_gradients_out_in_one_flat_buffer():
+    """_UnpackPlan turns the planning run's jobs (absolute destination pointers of ~45 separate tensors) into offsets of one
+    flat buffer: 256-byte aligned slots in gradient order, every job mapped to the slot of the tensor it wrote."""
+    from contrastive_lift_b200 import renderer as R
+    grads = {"a.weight": torch.zeros(5, 7), "a.bias": torch.zeros(5), "plane.0": torch.zeros(1, 16, 9, 9)}
+
+    class Batch:
+        jobs, tiles = [], 11
+    for g in (grads["plane.0"], grads["a.weight"], grads["a.bias"]):       # job order differs from gradient order
+        j = L.PackJob()
+        j.src, j.dst, j.d_rows, j.d_cols = 0x1000, g.data_ptr(), 3, 4
+        Batch.jobs.append(j)
+    plan = R._UnpackPlan(Batch, grads)
+    assert [(n, s, k, o) for n, s, k, o in plan.items] == [("a.weight", (5, 7), 35, 0), ("a.bias", (5,), 5, 64),
+                                                            ("plane.0", (1, 16, 9, 9), 1296, 128)]
+    assert plan.total == 128 + 1344 and plan.tiles == 11                  # 1296 floats round up to 21 slots of 64
+    assert [off for _, off in plan.jobs] == [128 * 4, 0, 64 * 4]
+    assert all(j.src == 0x1000 and j.d_rows == 3 for j, _ in plan.jobs)
