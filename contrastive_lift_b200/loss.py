@@ -9,6 +9,7 @@ All of them call libclift_b200.so; none has a PyTorch fallback.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Iterable
 
 import torch
@@ -99,6 +100,7 @@ def ema_update(slow_params: Iterable[torch.Tensor], fast_params: Iterable[torch.
 
 
 _EMA_TABLES: dict = {}
+_TV_TABLES: dict = {}
 
 
 def ema_update_slownet(slow_net: nn.Module, fast_net: nn.Module, momentum: float = 0.9) -> None:
@@ -144,35 +146,44 @@ class _TotalTV(torch.autograd.Function):
             st = L.stream_ptr(dev)
             srcs = [p.detach().contiguous() for p in planes]               # bound until the launches are enqueued
             sizes = [p.numel() for p in srcs]
-            flat = torch.empty((sum(sizes),), device=dev)                   # packed copies (channel-last)
-            g_flat = torch.zeros((sum(sizes),), device=dev)                 # their gradients
-            hwc, g_hwc, off = [], [], 0
-            batch = L.PackBatch()
-            for p, n in zip(srcs, sizes):
-                _, c, h, w = p.shape
-                hwc.append(flat[off:off + n].view(h, w, c))
-                g_hwc.append(g_flat[off:off + n].view(h, w, c))
-                batch.plane(p, hwc[-1], c, h, w)
-                off += n
-            batch.run(lib, dev)
+            total = sum(sizes)
+            flat = torch.empty((total,), device=dev)                        # packed copies (channel-last)
+            g_flat = torch.zeros((total,), device=dev)                      # their gradients (channel-last)
+            out_flat = torch.empty((total,), device=dev)                    # ... back in (1,C,H,W) layout, one view per plane
             vals = torch.empty((len(srcs),), device=dev)
-            jobs = (L.TvJob * len(srcs))()              # all values in one launch, all gradients in another
-            for i, (j, p, coef) in enumerate(zip(jobs, srcs, coefs)):
-                _, c, h, w = p.shape
-                j.plane_hwc, j.loss, j.grad_hwc = L.ptr(hwc[i]), vals.data_ptr() + 4 * i, L.ptr(g_hwc[i])
-                j.comps, j.h, j.w, j.grad_scale = c, h, w, float(coef)
-            table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(dev, non_blocking=True)
-            L.check(lib.clift_tv_loss_batch(L.ptr(table), len(srcs), max(sizes), st))
-            grads = [torch.empty_like(p) for p in srcs]
-            batch = L.PackBatch()
-            for p, g, gh in zip(srcs, grads, g_hwc):
-                _, c, h, w = p.shape
-                batch.unplane(gh, g, c, h, w)
-            batch.run(lib, dev)
-            # coefficients: small pageable copy queued on the stream (torch.tensor(..., device=) would wait for the stream)
-            total = (vals * torch.tensor([float(c) for c in coefs]).to(dev, non_blocking=True)).sum()
+            # the three job tables depend only on addresses and shapes: reused while the parameters keep their storage and the
+            # caching allocator returns the scratch buffers at the same places (the usual case from the second step on)
+            key = (tuple((p.data_ptr(), tuple(p.shape), float(c)) for p, c in zip(srcs, coefs)),
+                   flat.data_ptr(), g_flat.data_ptr(), out_flat.data_ptr(), vals.data_ptr())
+            tables = _TV_TABLES.get(dev)
+            if tables is None or tables[0] != key:
+                pack, unpack = L.PackBatch(), L.PackBatch()
+                jobs = (L.TvJob * len(srcs))()
+                off = 0
+                for i, (j, p, n, coef) in enumerate(zip(jobs, srcs, sizes, coefs)):
+                    _, c, h, w = p.shape
+                    hwc, g_hwc = flat[off:off + n].view(h, w, c), g_flat[off:off + n].view(h, w, c)
+                    pack.plane(p, hwc, c, h, w)
+                    unpack.unplane(g_hwc, out_flat[off:off + n].view(1, c, h, w), c, h, w)
+                    j.plane_hwc, j.loss, j.grad_hwc = L.ptr(hwc), vals.data_ptr() + 4 * i, L.ptr(g_hwc)
+                    j.comps, j.h, j.w, j.grad_scale = c, h, w, float(coef)
+                    off += n
+                up = lambda raw: torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev, non_blocking=True)
+                tables = _TV_TABLES[dev] = (key, up(bytes((L.PackJob * len(pack.jobs))(*pack.jobs))), int(pack.tiles),
+                                            up(bytes(jobs)), up(bytes((L.PackJob * len(unpack.jobs))(*unpack.jobs))),
+                                            int(unpack.tiles), up(bytes((C.c_float * len(srcs))(*[float(c) for c in coefs])))
+                                            .view(torch.float32))
+            _, t_pack, tiles_pack, t_tv, t_unpack, tiles_unpack, coef_dev = tables
+            L.check(lib.clift_pack_batch(L.ptr(t_pack), len(srcs), tiles_pack, st))
+            L.check(lib.clift_tv_loss_batch(L.ptr(t_tv), len(srcs), max(sizes), st))     # all values, then all gradients
+            L.check(lib.clift_pack_batch(L.ptr(t_unpack), len(srcs), tiles_unpack, st))
+            total_loss = (vals * coef_dev).sum()
+            grads, off = [], 0
+            for p, n in zip(srcs, sizes):
+                grads.append(out_flat[off:off + n].view(p.shape))
+                off += n
         ctx.grads = grads
-        return total
+        return total_loss
 
     @staticmethod
     def backward(ctx, gout):

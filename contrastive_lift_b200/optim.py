@@ -38,18 +38,15 @@ class FusedAdam(torch.optim.Optimizer):
         lib = L.load()
         keep: List[torch.Tensor] = []      # contiguous gradient copies stay alive until every launch of this step is enqueued
         # segments of the launch under construction: (group, step count, first entry, number of entries); a segment ends when
-        # the param group, the step history or the device changes
-        self._entries: List[L.AdamTensor] = []
+        # the param group, the step history or the device changes.  Entries are (param, grad, exp_avg, exp_avg_sq, n) rows
+        self._entries: list = []
         self._segments: list = []
         self._max_n, self._device = 0, None
         for group in self.param_groups:
-            entries: List[L.AdamTensor] = []
-            step = None
-            device = None
-            max_n = 0
-            for p in group["params"]:
-                if p.grad is None:
-                    continue
+            live = [p for p in group["params"] if p.grad is not None]
+            if not live:
+                continue
+            for p in live:
                 if not p.is_cuda:
                     raise L.CliftError("FusedAdam: parameters must live on a CUDA device (no CPU path)")
                 if p.grad.is_sparse or p.dtype != torch.float32 or not p.is_contiguous():
@@ -59,8 +56,19 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = torch.tensor(0.0, dtype=torch.float32)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                st["step"] += 1
-                t = int(st["step"].item()) if st["step"].device.type == "cpu" else int(st["step"])
+            states = [self.state[p] for p in live]
+            steps = [st["step"] for st in states]
+            if all(s.device.type == "cpu" for s in steps):
+                torch._foreach_add_(steps, 1.0)            # one call for the group's step counters (host tensors, as torch's)
+            else:
+                for s in steps:
+                    s += 1
+            entries: list = []
+            step = None
+            device = None
+            max_n = 0
+            for p, st, s in zip(live, states, steps):
+                t = int(s)
                 if step is None:
                     step, device = t, p.device
                 elif t != step or p.device != device:      # mixed histories: flush what we have, start a new launch
@@ -68,11 +76,10 @@ class FusedAdam(torch.optim.Optimizer):
                     entries, max_n, step, device = [], 0, t, p.device
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 keep.append(g)
-                e = L.AdamTensor()
-                e.param, e.grad, e.exp_avg, e.exp_avg_sq, e.n = p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), \
-                    st["exp_avg_sq"].data_ptr(), p.numel()
-                entries.append(e)
-                max_n = max(max_n, p.numel())
+                n = p.numel()
+                entries.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), n))
+                if n > max_n:
+                    max_n = n
             self._launch(lib, entries, max_n, group, step, device)
         self._flush(lib)
         # parameters were rewritten through raw pointers: autograd's version counters did not move, so cached packed copies
@@ -96,7 +103,19 @@ class FusedAdam(torch.optim.Optimizer):
         if not self._segments:
             return
         entries, device = self._entries, self._device
-        raw = bytes((L.AdamTensor * len(entries))(*entries))
+        # the device table of a launch is reused while every pointer in it repeats (parameters and optimizer state never
+        # move; the gradients of a pass come back at the same addresses once the caching allocator has settled)
+        key = tuple(entries)
+        cache = self.__dict__.setdefault("_tables", {})
+        table = cache.get(key)
+        if table is None:
+            if len(cache) >= 8:
+                cache.clear()
+            rows = (L.AdamTensor * len(entries))()
+            for r, e in zip(rows, entries):
+                r.param, r.grad, r.exp_avg, r.exp_avg_sq, r.n = e
+            with L.on(device):
+                table = cache[key] = torch.frombuffer(bytearray(bytes(rows)), dtype=torch.uint8).to(device, non_blocking=True)
         groups = (L.AdamGroup * len(self._segments))()
         for g, (group, step, first, count) in zip(groups, self._segments):
             b1, b2 = group["betas"]
@@ -104,9 +123,6 @@ class FusedAdam(torch.optim.Optimizer):
                 float(group["weight_decay"])
             g.first, g.count, g.step = first, count, step
         with L.on(device):
-            table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device, non_blocking=True)
             L.check(lib.clift_adam_step_groups(L.ptr(table), len(entries), self._max_n, groups, len(self._segments),
                                                self.grad_scale, L.stream_ptr(device)))
-        # the caching allocator may not hand the table's block to another stream-ordered tensor before the launch ran:
-        # same stream, so ordering holds without a record_stream
         self._entries, self._segments, self._max_n = [], [], 0
