@@ -310,6 +310,22 @@ def test_ema_bit_exact_and_tv_golden():
     assert abs(float(tot) - float(fx["tv_total"])) <= 1e-5 * float(fx["tv_total"])
     tot.backward()
     assert gpu.rel_err(model.density_plane[1].grad, tn(fx["tv_grad_density_plane.1"])) < 1e-4
+    # repeated calls (job tables cached by address; the scratch buffers may or may not come back at the same places) give the
+    # same value and gradient, also after a parameter changed in place
+    first = model.density_plane[1].grad.clone()
+    for rep in range(3):
+        junk = torch.empty((1 << (18 + rep),), device="cuda")          # perturb the allocator between the calls
+        model.zero_grad(set_to_none=True)
+        again = model.total_tv_loss(None, Cfg, 5)
+        again.backward()
+        assert torch.equal(again, tot) and torch.equal(model.density_plane[1].grad, first)
+        del junk
+    with torch.no_grad():
+        model.density_plane[1].mul_(2.0)
+    model.zero_grad(set_to_none=True)
+    scaled = model.total_tv_loss(None, Cfg, 5)
+    scaled.backward()
+    assert float(scaled) > float(tot) and gpu.rel_err(model.density_plane[1].grad, 2.0 * first) < 1e-6
 
 
 def test_edge_cases_empty_and_missing_rays():
