@@ -1233,20 +1233,8 @@ __global__ void __launch_bounds__(256) pack_linear_tc16_batch_kernel(const clift
                           (int64_t)((int)blockIdx.x - J.first_block) * 256 + threadIdx.x);
 }
 
-// dst[slot] = max |x| (dst zeroed by the caller; |x| >= 0 so the uint order of the bits is the float order)
-__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ dst) {
-    float m = 0.0f;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(x[i]));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(dst), __float_as_uint(m));
-}
-
-// the six factor tensors of a VM set in one launch: blockIdx.y = tensor, slot blockIdx.y of dst
+// dst[slot] = max |x| of the six factor tensors of a VM set in one launch: blockIdx.y = tensor = slot (dst zeroed by the
+// caller; |x| >= 0 so the uint order of the bits is the float order)
 struct AbsmaxSix {
     const float* x[6];
     long long n[6];

@@ -39,21 +39,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
-// wait with cluster-scope acquire: the arrivals came from (or on behalf of) the peer CTA of a pair
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TC_WAITC_LOOP_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TC_WAITC_DONE_%=;\n"
-        "bra TC_WAITC_LOOP_%=;\n"
-        "TC_WAITC_DONE_%=:\n"
-        "}\n" ::"r"(smem_addr(bar)),
-        "r"(parity)
-        : "memory");
-}
-
 // ---- bulk TMA (global -> shared, 1-D) ------------------------------------------------------------------
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
@@ -202,9 +187,6 @@ __device__ __forceinline__ uint32_t map_to_rank(const void* smem_ptr, uint32_t r
 // the CTAs.  The release.cluster / acquire.cluster forms cost ~700-1000 cycles per hand-off (profiles/r02_x16_ab.md).
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t cols) {   // same warp id in both CTAs
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(cols) : "memory");
