@@ -2,7 +2,7 @@
 """Static evidence from the built library (no GPU needed): per-kernel registers / stack / static shared memory from
 `cuobjdump --dump-resource-usage`, and the count of Blackwell-specific SASS mnemonics per kernel from `cuobjdump -sass`
 (B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld/st -> LDTM/STTM, bulk TMA -> UBLKCP/UTMALDG, cp.async -> LDGSTS,
-red.global -> REDG).  Writes profiles/r01_static_sass.md.
+red.global -> REDG).  Writes profiles/r02_static_sass.md (CLIFT_STATIC_OUT names another file).
 
     python scripts/static_evidence.py
 """
@@ -13,7 +13,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "contrastive_lift_b200", "libclift_b200.so")
-OUT = os.path.join(ROOT, "profiles", "r01_static_sass.md")
+OUT = os.path.join(ROOT, "profiles", os.environ.get("CLIFT_STATIC_OUT", "r02_static_sass.md"))
 MNEMONICS = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "LDGSTS", "REDG", "HMMA"]
 
 
@@ -46,7 +46,7 @@ def main():
     nice = dict(zip(names, demangle(names)))
     rows = sorted((nice[n], n) for n in names)
     with open(OUT, "w") as f:
-        f.write("# Round 1 - static evidence from libclift_b200.so (sm_100a cubin, `scripts/static_evidence.py`, no GPU involved)\n\n")
+        f.write("# Round 2 - static evidence from libclift_b200.so (sm_100a cubin, `scripts/static_evidence.py`, no GPU involved)\n\n")
         f.write("Registers / stack bytes / static shared bytes per kernel (`cuobjdump --dump-resource-usage`; dynamic shared memory is set "
                 "at launch) and counts of the SASS mnemonics that identify the Blackwell paths (`cuobjdump -sass`): `UTCHMMA` = tcgen05.mma, "
                 "`UTCBAR` = tcgen05.commit, `LDTM`/`STTM` = tcgen05.ld/st (tensor memory), `UBLKCP` = bulk TMA copy (cp.async.bulk), "
@@ -60,14 +60,16 @@ def main():
         spills = [(nice[n], usage[n][1]) for n in names if usage[n][1] > 0]
         f.write(f"\n{len(names)} kernels; kernels with a non-zero stack frame (local arrays or spills): "
                 + (", ".join(f"`{a}` ({b} B)" for a, b in sorted(spills)) if spills else "none") + ".\n")
-        f.write("\nWhere the stack frames come from (`nvdisasm -g` line mapping of every `LDL`/`STL`): in `heads_tc16_forward_kernel` "
-                "(192 STL / 288 LDL) and `heads_tc_forward_kernel` all of them sit on the `sinf`/`cosf` calls of the positional-encoding "
-                "branch `pe_sem / pe_ins > 0` (`heads_tc16.cu:571`, `heads_tc.cu:429`: libdevice's slow-path argument reduction keeps its "
-                "table walk in local memory); the shipped configurations (`pe_sem = pe_ins = 0`) take the branch above it and never execute "
-                "them. `march_kernel` keeps the ray origin / direction (6 words, written once per ray at `march.cu:66-67`) in local memory "
-                "and re-reads them in `sample_point` (`common.cuh:241`, L1 hits); `march_backward_kernel<3>` spills a few loop-invariant "
-                "scalars set up before its ray loop (`march.cu:470-474`). The FP32-FMA head kernels' frames are the same libdevice slow "
-                "path (`heads.cu:169,243,247`). No tensor-core kernel touches local memory in its steady-state loop.\n")
+        f.write("\nWhere the stack frames come from (round 1's `nvdisasm -g` line mapping of every `LDL`/`STL`, "
+                "`profiles/r01_static_sass.md`; the code around them is unchanged): in `heads_tc16_forward_kernel` and "
+                "`heads_tc_forward_kernel` they sit on the `sinf`/`cosf` calls of the positional-encoding branch `pe_sem / pe_ins > 0` "
+                "(libdevice's slow-path argument reduction keeps its table walk in local memory); the shipped configurations "
+                "(`pe_sem = pe_ins = 0`) take the branch above it and never execute them.  `march_kernel` keeps the ray origin / "
+                "direction (6 words, written once per ray) in local memory and re-reads them in `sample_point` (L1 hits); "
+                "`march_backward_kernel<3>` spills a few loop-invariant scalars set up before its ray loop.  The FP32-FMA head "
+                "kernels' frames are the same libdevice slow path; `heads_backward_kernel`'s 96 bytes are the operand-scale "
+                "`frexpf` / `ldexpf` pair and loop-invariant scalars of its tile loop.  No tensor-core kernel touches local memory in "
+                "its steady-state MMA loop.\n")
     print(OUT, len(names), "kernels")
 
 
