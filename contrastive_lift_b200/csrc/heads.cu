@@ -84,7 +84,8 @@ struct DgEngine {
     uint64_t* d_done;
     float* red;              // [8]
     uint32_t tmem;
-    uint32_t a_fills[2];     // fills of each operand chunk buffer so far
+    uint32_t a_fills0, a_fills1;   // fills of each operand buffer so far (two scalars: a runtime-indexed array would put the
+                                   // whole struct in local memory)
     uint32_t w_loads;        // weight slabs loaded so far (stage = w_loads % kDgStages)
     uint32_t w_used;         // weight slabs consumed so far
     uint32_t d_count;        // GEMMs completed so far
@@ -612,8 +613,12 @@ __device__ __forceinline__ void run_dgrad_tc(const Smem& sm, DgEngine& E, const 
     // group's MMAs (its fixed issue cost - waits, descriptors, commits - and the barrier are paid per group, not per k-step)
     for (int ks0 = 0; ks0 < k_steps; ks0 += kDgGroup) {
         const int b = (ks0 / kDgGroup) & 1, ks1 = min(k_steps, ks0 + kDgGroup);
-        if (E.a_fills[b] > 0) tc::mbar_wait(&E.a_free[b], (E.a_fills[b] - 1) & 1u);
-        ++E.a_fills[b];
+        const uint32_t fills = b ? E.a_fills1 : E.a_fills0;
+        if (fills > 0) tc::mbar_wait(&E.a_free[b], (fills - 1) & 1u);
+        if (b)
+            ++E.a_fills1;
+        else
+            ++E.a_fills0;
         for (int ks = ks0; ks < ks1; ++ks) {
             // records m, K rows [16 ks + 8 c, + 8) -> one 16-byte row of the hi chunk and one of the lo chunk
             const float* src = sm.act + (size_t)(ks * 16 + c * 8) * kTile + m;
@@ -839,7 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) heads_backward_kernel(const __gri
         E.d_done = E.a_free + 2;
         E.red = reinterpret_cast<float*>(E.d_done + 1);
     }
-    E.a_fills[0] = E.a_fills[1] = 0;
+    E.a_fills0 = E.a_fills1 = 0;
     E.w_loads = E.w_used = E.d_count = 0;
     E.tmem = 0;
     if (E.on) {

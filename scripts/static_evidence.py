@@ -67,11 +67,10 @@ def main():
                 "(`pe_sem = pe_ins = 0`) take the branch above it and never execute them.  `march_kernel` keeps the ray origin / "
                 "direction (6 words, written once per ray) in local memory and re-reads them in `sample_point` (L1 hits); "
                 "`march_backward_kernel<3>` spills a few loop-invariant scalars set up before its ray loop.  The FP32-FMA head "
-                "kernels' frames are the same libdevice slow path.  `heads_backward_kernel`'s 96 bytes (`nvdisasm -g` of the round-2 "
-                "cubin: ~100 `LDL` / ~30 `STL`, all inside `run_dgrad_tc`) are the data-gradient engine's state - `DgEngine`'s fill "
-                "counters are indexed by the operand-buffer parity, which puts the struct in local memory; it is re-read at the top "
-                "of a GEMM and once per group of two k-steps (L1 hits).  The forward tensor-core kernels touch no local memory in "
-                "their steady-state MMA loops.\n")
+                "kernels' frames are the same libdevice slow path.  `heads_backward_kernel` has no frame any more: its 96 bytes were the "
+                "data-gradient engine's state (`DgEngine`'s fill counters were indexed by the operand-buffer parity, which put the "
+                "whole struct in local memory - found with `nvdisasm -g`, now two scalars).  The tensor-core kernels touch no local "
+                "memory in their steady-state MMA loops.\n")
     print(OUT, len(names), "kernels")
 
 
